@@ -1,0 +1,99 @@
+// Kernel-level entry points used by tests/ and profiling only (declared in include/mdc_debug.h).
+// They run a single kernel of the hot path on caller-provided device buffers so each kernel can be
+// checked against the oracle / a torch fp32 reference in isolation.
+#pragma once
+#include "gemm.cuh"
+#include "pack.cuh"
+
+namespace mdc {
+
+inline std::string& last_error() {
+  static thread_local std::string e;
+  return e;
+}
+
+template <typename F>
+inline int guarded(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const HostError& e) {
+    last_error() = e.msg;
+    return 1;
+  } catch (const std::exception& e) {
+    last_error() = e.what();
+    return 2;
+  }
+}
+
+inline float time_plan(const GemmPlan& g, int iters, cudaStream_t st) {
+  cudaEvent_t e0, e1;
+  MDC_CUDA(cudaEventCreate(&e0));
+  MDC_CUDA(cudaEventCreate(&e1));
+  run_gemm(g, st);  // warm-up / correctness launch
+  MDC_CUDA(cudaGetLastError());
+  MDC_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  if (iters > 0) {
+    MDC_CUDA(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i) run_gemm(g, st);
+    MDC_CUDA(cudaEventRecord(e1, st));
+    MDC_CUDA(cudaEventSynchronize(e1));
+    MDC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= iters;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return ms;
+}
+
+}  // namespace mdc
+
+extern "C" {
+
+const char* mdc_last_error() { return mdc::last_error().c_str(); }
+
+int mdc_dbg_gemm(int M, int N, int K, const void* A, int a_mn, long long lda, long long sa0, long long sa1,
+                 const void* B, int b_mn, long long ldb, long long sb0, long long sb1, void* out, int out_f32,
+                 long long ldc, long long sc0, long long sc1, const float* bias, const void* res, long long ldr,
+                 long long sr0, long long sr1, float alpha, int nb0, int nb1, int bn_override, int iters,
+                 float* ms_out) {
+  return mdc::guarded([&] {
+    mdc::Operand a{A, a_mn, lda, sa0, sa1}, b{B, b_mn, ldb, sb0, sb1};
+    mdc::Epilogue e;
+    e.out = out, e.out_f32 = out_f32, e.ldc = ldc, e.sc0 = sc0, e.sc1 = sc1, e.bias = bias;
+    e.res = static_cast<const __nv_bfloat16*>(res), e.ldr = ldr, e.sr0 = sr0, e.sr1 = sr1, e.alpha = alpha;
+    mdc::GemmPlan g = mdc::plan_gemm(M, N, K, a, b, e, nb0, nb1, bn_override);
+    float ms = mdc::time_plan(g, iters, 0);
+    if (ms_out) *ms_out = ms;
+  });
+}
+
+// x: NHWC bf16 (pixel stride ldx); w: OIHW fp32 [Cout][C][3][3]; mode 0 = forward conv, 1 = input gradient
+// (x is then dy with Cout channels and the result has C channels).
+int mdc_dbg_conv3x3(int NB, int H, int W, int C, int Cout, const void* x, long long ldx, const float* w_oihw,
+                    int dgrad, const float* bias, const float* bias_img, const void* res, long long ldr, void* out,
+                    long long ldc, int iters, float* ms_out) {
+  return mdc::guarded([&] {
+    const int Cin_g = dgrad ? Cout : C;   // channels of the tensor being convolved
+    const int Cout_g = dgrad ? C : Cout;  // channels produced
+    const int Kp = ((Cin_g + 63) / 64) * 64;
+    __nv_bfloat16* wpk = nullptr;
+    MDC_CUDA(cudaMalloc(&wpk, sizeof(__nv_bfloat16) * 9ull * Kp * Cout_g));
+    if (!dgrad)
+      mdc::pack_conv3x3_fwd_kernel<float><<<592, 256>>>(w_oihw, wpk, Cout, C, Kp);
+    else
+      mdc::pack_conv3x3_dgrad_kernel<float><<<592, 256>>>(w_oihw, wpk, Cout, C, Kp);
+    MDC_CUDA(cudaGetLastError());
+    mdc::Epilogue e;
+    e.out = out, e.ldc = ldc, e.bias = bias, e.bias_img = bias_img;
+    e.res = static_cast<const __nv_bfloat16*>(res), e.ldr = ldr;
+    mdc::GemmPlan g = mdc::plan_conv3x3(NB, H, W, Cin_g, Cout_g, x, ldx, wpk, e);
+    float ms = mdc::time_plan(g, iters, 0);
+    if (ms_out) *ms_out = ms;
+    MDC_CUDA(cudaDeviceSynchronize());
+    cudaFree(wpk);
+  });
+}
+
+}  // extern "C"

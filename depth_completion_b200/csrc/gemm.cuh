@@ -1,0 +1,546 @@
+// Persistent, warp-specialised tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   D[M,N] = alpha * A[M,K] . B[N,K]^T  (+ bias[N]) (+ bias_img[img][N]) (+ residual)      bf16 in, fp32 acc
+//
+// One CTA per SM loops over 128 x BN output tiles.  Warp 0 (one lane) is the TMA producer, warp 1
+// (one lane) issues tcgen05.mma into a double-buffered TMEM accumulator (2 x 256 columns), warps 2..5
+// drain TMEM with tcgen05.ld and run the epilogue.  Operands are staged in shared memory in the
+// 128-byte-swizzled canonical UMMA layout, written directly by TMA:
+//   * K-major operand  : box [64 k, rows]      -> rows x 128 B, 8-row groups 1024 B apart (SBO)
+//   * MN-major operand : boxes [64 mn, 64 k]   -> 64 k-rows x 128 B each, chunks 8192 B apart (LBO)
+//   * conv3x3 A operand: box [64 c, BW, BH, 1] of the NHWC input at (w0+s-1, h0+r-1); TMA zero-fills
+//     out-of-bounds coordinates, which is exactly the conv's zero padding, so no im2col buffer exists.
+// This plays the role cuDNN implicit-GEMM / cuBLAS play under the reference.
+#pragma once
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ptx.cuh"
+
+namespace mdc {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_A_STAGE = GEMM_BM * GEMM_BK * 2;  // 16 KiB
+constexpr int GEMM_MAX_STAGES = 8;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_SMEM_BUDGET = 200 * 1024;
+constexpr int GEMM_TMEM_COLS = 512;
+
+struct GemmParams {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  // tiling
+  int m_tiles, n_tiles, nb0, nb1;
+  int num_k_chunks;
+  int BN;
+  int stages;
+  int a_mn, b_mn;
+  uint32_t idesc;
+  uint32_t bytesA, bytesB;
+  int M, N;  // valid rows per batch (GEMM mode) / valid columns
+  // conv3x3 mode
+  int conv;
+  int H, W, tiles_h, tiles_w, BW, BH, chunks_per_tap;
+  // epilogue
+  void* out;
+  int out_f32;
+  int vec_ok;
+  long long ldc, sc0, sc1;  // element strides of the output: row, batch0, batch1 (conv: sc1 = per image)
+  const float* bias;
+  const float* bias_img;  // [images][N]; image = conv image or batch1
+  const __nv_bfloat16* res;
+  long long ldr, sr0, sr1;
+  float alpha;
+};
+
+__device__ __forceinline__ void gemm_decode_tile(const GemmParams& p, int tile, int& n_tile, int& m_tile, int& b0,
+                                                 int& b1) {
+  n_tile = tile % p.n_tiles;
+  int rest = tile / p.n_tiles;
+  m_tile = rest % p.m_tiles;
+  int b = rest / p.m_tiles;
+  b0 = b % p.nb0;
+  b1 = b / p.nb0;
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // barriers live in the first 1 KiB of the aligned region, stage buffers follow.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + GEMM_MAX_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* sA = smem + 1024;
+  const uint32_t b_stage = static_cast<uint32_t>(p.BN) * 128u;
+  uint8_t* sB = sA + p.stages * GEMM_A_STAGE;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.nb0 * p.nb1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull_bar[i], 1);
+      ptx::mbar_init(&tempty_bar[i], 4);
+    }
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&p.tmA);
+    ptx::prefetch_tmap(&p.tmB);
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, GEMM_TMEM_COLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int n_tile, m_tile, b0, b1;
+        gemm_decode_tile(p, tile, n_tile, m_tile, b0, b1);
+        const int n0 = n_tile * p.BN;
+        int m0 = m_tile * GEMM_BM, img = 0, h0 = 0, w0 = 0;
+        if (p.conv) {
+          int tw = m_tile % p.tiles_w;
+          int r = m_tile / p.tiles_w;
+          int th = r % p.tiles_h;
+          img = r / p.tiles_h;
+          h0 = th * p.BH;
+          w0 = tw * p.BW;
+        }
+        for (int kc = 0; kc < p.num_k_chunks; ++kc) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_expect_tx(&full_bar[stage], p.bytesA + p.bytesB);
+          uint8_t* a_dst = sA + stage * GEMM_A_STAGE;
+          uint8_t* b_dst = sB + stage * b_stage;
+          const int k0 = kc * GEMM_BK;
+          if (p.conv) {
+            const int tap = kc / p.chunks_per_tap;
+            const int cc = kc - tap * p.chunks_per_tap;
+            const int r = tap / 3, s = tap - r * 3;
+            ptx::tma_load_4d(&p.tmA, &full_bar[stage], a_dst, cc * GEMM_BK, w0 + s - 1, h0 + r - 1, img);
+            ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst, k0, n0, 0, 0);
+          } else {
+            if (!p.a_mn) {
+              ptx::tma_load_4d(&p.tmA, &full_bar[stage], a_dst, k0, m0, b0, b1);
+            } else {
+              ptx::tma_load_4d(&p.tmA, &full_bar[stage], a_dst, m0, k0, b0, b1);
+              ptx::tma_load_4d(&p.tmA, &full_bar[stage], a_dst + 8192, m0 + 64, k0, b0, b1);
+            }
+            if (!p.b_mn) {
+              ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst, k0, n0, b0, b1);
+            } else {
+              for (int i = 0; i < p.BN / 64; ++i)
+                ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst + i * 8192, n0 + i * 64, k0, b0, b1);
+            }
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
+      const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * 256u;
+        for (int kc = 0; kc < p.num_k_chunks; ++kc) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(sA + stage * GEMM_A_STAGE);
+          const uint32_t b_addr = ptx::smem_u32(sB + stage * b_stage);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
+            const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
+            ptx::umma_bf16(d_tmem, adesc, bdesc, p.idesc, (kc | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue warps (TMEM -> global)
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int n_tile, m_tile, b0, b1;
+      gemm_decode_tile(p, tile, n_tile, m_tile, b0, b1);
+      const int n0 = n_tile * p.BN;
+      bool valid;
+      long long off_c, off_r;
+      int img;
+      if (p.conv) {
+        int tw = m_tile % p.tiles_w;
+        int r = m_tile / p.tiles_w;
+        int th = r % p.tiles_h;
+        img = r / p.tiles_h;
+        int hh = th * p.BH + row / p.BW;
+        int ww = tw * p.BW + row % p.BW;
+        valid = (row < p.BW * p.BH) && hh < p.H && ww < p.W;
+        long long pix = (static_cast<long long>(hh) * p.W + ww);
+        off_c = img * p.sc1 + pix * p.ldc;
+        off_r = img * p.sr1 + pix * p.ldr;
+      } else {
+        int m = m_tile * GEMM_BM + row;
+        valid = m < p.M;
+        img = b1;
+        off_c = b0 * p.sc0 + b1 * p.sc1 + static_cast<long long>(m) * p.ldc;
+        off_r = b0 * p.sr0 + b1 * p.sr1 + static_cast<long long>(m) * p.ldr;
+      }
+      ptx::mbar_wait(&tfull_bar[as], aphase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as) * 256u;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t raw[16];
+        ptx::tmem_ld16(t_row + c0, raw);
+        ptx::tmem_ld_wait();
+        const int col0 = n0 + c0;
+        if (valid && col0 < p.N) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+          const bool full = (col0 + 16 <= p.N) && p.vec_ok;
+          if (full) {
+            if (p.bias) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float4 b = __ldg(b4 + j);
+                v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
+              }
+            }
+            if (p.bias_img) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias_img + static_cast<long long>(img) * p.N + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float4 b = __ldg(b4 + j);
+                v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
+              }
+            }
+            if (p.res) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off_r + col0);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                uint4 r = r4[j];
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  float2 f = __bfloat1622float2(h[t]);
+                  v[8 * j + 2 * t] += f.x;
+                  v[8 * j + 2 * t + 1] += f.y;
+                }
+              }
+            }
+            if (p.out_f32) {
+              float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(p.out) + off_c + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off_c + col0);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                uint4 o;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]);
+                o4[j] = o;
+              }
+            }
+          } else {
+            for (int j = 0; j < 16; ++j) {
+              const int col = col0 + j;
+              if (col >= p.N) break;
+              float x = v[j];
+              if (p.bias) x += p.bias[col];
+              if (p.bias_img) x += p.bias_img[static_cast<long long>(img) * p.N + col];
+              if (p.res) x += __bfloat162float(p.res[off_r + col]);
+              if (p.out_f32)
+                static_cast<float*>(p.out)[off_c + col] = x;
+              else
+                static_cast<__nv_bfloat16*>(p.out)[off_c + col] = __float2bfloat16(x);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, GEMM_TMEM_COLS);
+}
+
+// ======================================================================= host side
+struct HostError {
+  std::string msg;
+};
+#define MDC_CHECK(cond, ...)                              \
+  do {                                                    \
+    if (!(cond)) {                                        \
+      char _b[512];                                       \
+      snprintf(_b, sizeof(_b), __VA_ARGS__);              \
+      throw ::mdc::HostError{std::string(_b)};            \
+    }                                                     \
+  } while (0)
+#define MDC_CUDA(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      throw ::mdc::HostError{std::string(#expr) + ": " + cudaGetErrorString(_e)};                  \
+  } while (0)
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    MDC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    MDC_CHECK(p != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 4-D bf16 tensor map, 128B swizzle, zero fill out of bounds.  dims/box in elements (dim 0 innermost),
+// strides in elements for dims 1..3.
+inline CUtensorMap make_tmap_bf16(const void* base, const uint64_t dims[4], const uint64_t strides_el[3],
+                                  const uint32_t box[4]) {
+  CUtensorMap m;
+  cuuint64_t gdims[4], gstr[3];
+  cuuint32_t gbox[4], estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) gdims[i] = dims[i], gbox[i] = box[i];
+  for (int i = 0; i < 3; ++i) gstr[i] = strides_el[i] * 2;
+  MDC_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base %p not 16-byte aligned", base);
+  for (int i = 0; i < 3; ++i) MDC_CHECK(gstr[i] % 16 == 0 && gstr[i] > 0, "TMA stride %d = %llu bytes invalid", i, (unsigned long long)gstr[i]);
+  MDC_CHECK(box[0] * 2 <= 128, "inner box exceeds the 128B swizzle span");
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdims, gstr, gbox, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MDC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): dims %llu %llu %llu %llu box %u %u %u %u", (int)r,
+            (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+            (unsigned long long)dims[3], box[0], box[1], box[2], box[3]);
+  return m;
+}
+
+// A bf16 matrix operand.  mn_major = 0: element (mn, k) at ptr[mn*ld + k];  1: at ptr[k*ld + mn].
+struct Operand {
+  const void* ptr = nullptr;
+  int mn_major = 0;
+  long long ld = 0;
+  long long sb0 = 0, sb1 = 0;  // batch strides in elements
+};
+struct Epilogue {
+  void* out = nullptr;
+  int out_f32 = 0;
+  long long ldc = 0, sc0 = 0, sc1 = 0;
+  const float* bias = nullptr;
+  const float* bias_img = nullptr;
+  const __nv_bfloat16* res = nullptr;
+  long long ldr = 0, sr0 = 0, sr1 = 0;
+  float alpha = 1.f;
+};
+
+struct GemmPlan {
+  GemmParams p;
+  int grid = 0;
+  int smem = 0;
+  double flops = 0;
+};
+
+inline int pick_bn(int N) {
+  // largest multiple of 16 that is <= 256 and divides N; otherwise min(256, roundup16(N)).
+  for (int bn = 256; bn >= 64; bn -= 16)
+    if (N % bn == 0) return bn;
+  int r = ((N + 15) / 16) * 16;
+  return r > 256 ? 256 : r;
+}
+
+inline int g_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+inline void finish_plan(GemmPlan& g) {
+  GemmParams& p = g.p;
+  const int b_stage = p.BN * 128;
+  int stages = (GEMM_SMEM_BUDGET - 2048) / (GEMM_A_STAGE + b_stage);
+  stages = std::max(2, std::min(stages, GEMM_MAX_STAGES));
+  p.stages = stages;
+  g.smem = 2048 + stages * (GEMM_A_STAGE + b_stage);
+  p.idesc = ptx::make_idesc_bf16(GEMM_BM, p.BN, p.a_mn, p.b_mn);
+  long long total = 1LL * p.m_tiles * p.n_tiles * p.nb0 * p.nb1;
+  g.grid = static_cast<int>(std::min<long long>(total, g_num_sms()));
+  const uintptr_t o = reinterpret_cast<uintptr_t>(p.out), r = reinterpret_cast<uintptr_t>(p.res);
+  bool ok = (o % 16 == 0) && (p.ldc % 8 == 0) && (p.sc0 % 8 == 0) && (p.sc1 % 8 == 0) && (p.N % 8 == 0);
+  if (p.res) ok = ok && (r % 16 == 0) && (p.ldr % 8 == 0) && (p.sr0 % 8 == 0) && (p.sr1 % 8 == 0);
+  if (p.bias) ok = ok && (reinterpret_cast<uintptr_t>(p.bias) % 16 == 0);
+  if (p.bias_img) ok = ok && (reinterpret_cast<uintptr_t>(p.bias_img) % 16 == 0) && (p.N % 4 == 0);
+  p.vec_ok = ok ? 1 : 0;
+}
+
+inline void fill_epilogue(GemmParams& p, const Epilogue& e) {
+  p.out = e.out, p.out_f32 = e.out_f32, p.ldc = e.ldc, p.sc0 = e.sc0, p.sc1 = e.sc1;
+  p.bias = e.bias, p.bias_img = e.bias_img, p.res = e.res, p.ldr = e.ldr, p.sr0 = e.sr0, p.sr1 = e.sr1;
+  p.alpha = e.alpha;
+}
+
+// Batched GEMM: for each (b0, b1): D = alpha * A . B^T (+...).  K need not be a multiple of 64 (TMA zero-fills).
+inline GemmPlan plan_gemm(int M, int N, int K, const Operand& A, const Operand& B, const Epilogue& e, int nb0 = 1,
+                          int nb1 = 1, int bn_override = 0) {
+  GemmPlan g;
+  memset(&g.p, 0, sizeof(g.p));
+  GemmParams& p = g.p;
+  p.M = M, p.N = N;
+  p.nb0 = nb0, p.nb1 = nb1;
+  p.a_mn = A.mn_major, p.b_mn = B.mn_major;
+  p.BN = bn_override ? bn_override : pick_bn(N);
+  if (p.b_mn) p.BN = (N >= 256) ? 256 : ((N + 63) / 64) * 64;  // MN-major B is loaded in 64-wide chunks
+  MDC_CHECK(p.BN % 16 == 0 && p.BN >= 16 && p.BN <= 256, "bad BN %d", p.BN);
+  MDC_CHECK(!p.b_mn || p.BN % 64 == 0, "MN-major B needs BN %% 64 == 0");
+  p.m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  p.n_tiles = (N + p.BN - 1) / p.BN;
+  p.num_k_chunks = (K + GEMM_BK - 1) / GEMM_BK;
+  p.bytesA = GEMM_A_STAGE;
+  p.bytesB = p.BN * 128;
+  auto mk = [&](const Operand& o, int MN, int rows_box) {
+    uint64_t dims[4], str[3];
+    uint32_t box[4];
+    long long s0 = o.sb0 ? o.sb0 : 8, s1 = o.sb1 ? o.sb1 : 8;
+    if (!o.mn_major) {
+      dims[0] = K, dims[1] = MN, box[0] = 64, box[1] = rows_box;
+    } else {
+      dims[0] = MN, dims[1] = K, box[0] = 64, box[1] = 64;
+    }
+    dims[2] = nb0, dims[3] = nb1, box[2] = 1, box[3] = 1;
+    str[0] = o.ld, str[1] = s0, str[2] = s1;
+    return make_tmap_bf16(o.ptr, dims, str, box);
+  };
+  p.tmA = mk(A, M, GEMM_BM);
+  p.tmB = mk(B, N, p.BN);
+  fill_epilogue(p, e);
+  finish_plan(g);
+  g.flops = 2.0 * M * N * K * nb0 * nb1;
+  return g;
+}
+
+// Choose the rectangular pixel tile (BW x BH <= 128) that needs the fewest tiles for an H x W image.
+inline void pick_conv_tile(int H, int W, int& BW, int& BH) {
+  long long best = -1;
+  BW = 1, BH = 1;
+  for (int bw = 1; bw <= 128 && bw <= W; ++bw) {
+    int bh = std::min(128 / bw, H);
+    if (bh < 1) continue;
+    long long tiles = 1LL * ((W + bw - 1) / bw) * ((H + bh - 1) / bh);
+    if (best < 0 || tiles < best || (tiles == best && bw > BW)) best = tiles, BW = bw, BH = bh;
+  }
+}
+
+// 3x3 stride-1 pad-1 convolution over an NHWC bf16 tensor as an implicit GEMM.
+//   x   : [NB, H, W, C] with pixel stride ldx (>= C, multiple of 8)
+//   wpk : packed weights [Cout, 9 * Cp] bf16, Cp = roundup(C, 64), k = (r*3+s)*Cp + c
+//   out : [NB, H, W, Cout] with pixel stride e.ldc; e.sc1 / e.sr1 are per-image strides.
+inline GemmPlan plan_conv3x3(int NB, int H, int W, int C, int Cout, const void* x, long long ldx, const void* wpk,
+                             Epilogue e) {
+  GemmPlan g;
+  memset(&g.p, 0, sizeof(g.p));
+  GemmParams& p = g.p;
+  const int Cp = ((C + 63) / 64) * 64;
+  p.conv = 1;
+  p.H = H, p.W = W;
+  pick_conv_tile(H, W, p.BW, p.BH);
+  p.tiles_w = (W + p.BW - 1) / p.BW;
+  p.tiles_h = (H + p.BH - 1) / p.BH;
+  p.m_tiles = NB * p.tiles_h * p.tiles_w;
+  p.M = 0, p.N = Cout;
+  p.nb0 = 1, p.nb1 = 1;
+  p.BN = pick_bn(Cout);
+  p.n_tiles = (Cout + p.BN - 1) / p.BN;
+  p.chunks_per_tap = Cp / 64;
+  p.num_k_chunks = 9 * p.chunks_per_tap;
+  p.bytesA = 64u * p.BW * p.BH * 2u;
+  p.bytesB = p.BN * 128;
+  {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+    uint64_t str[3] = {(uint64_t)ldx, (uint64_t)ldx * W, (uint64_t)ldx * W * H};
+    uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+    p.tmA = make_tmap_bf16(x, dims, str, box);
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)9 * Cp, (uint64_t)Cout, 1, 1};
+    uint64_t str[3] = {(uint64_t)9 * Cp, (uint64_t)9 * Cp * Cout, (uint64_t)9 * Cp * Cout};
+    uint32_t box[4] = {64, (uint32_t)p.BN, 1, 1};
+    p.tmB = make_tmap_bf16(wpk, dims, str, box);
+  }
+  if (!e.sc1) e.sc1 = 1LL * H * W * e.ldc;
+  if (e.res && !e.sr1) e.sr1 = 1LL * H * W * e.ldr;
+  fill_epilogue(p, e);
+  finish_plan(g);
+  g.flops = 2.0 * NB * H * W * 9.0 * C * Cout;
+  return g;
+}
+
+inline void gemm_set_smem_attr() {
+  static bool done = false;
+  if (!done) {
+    MDC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BUDGET + 4096));
+    done = true;
+  }
+}
+
+inline void run_gemm(const GemmPlan& g, cudaStream_t st) {
+  gemm_set_smem_attr();
+  umma_gemm_kernel<<<g.grid, GEMM_THREADS, g.smem + 1024, st>>>(g.p);
+}
+
+}  // namespace mdc

@@ -1,0 +1,72 @@
+// Weight re-packing kernels (run once, at mdc_set_weight time; not on the hot path).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace mdc {
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) {
+  return v;
+}
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) {
+  return __bfloat162float(v);
+}
+
+// OIHW [Cout][C][3][3] -> forward pack [Cout][9*Cp], k = (r*3+s)*Cp + c  (zero padded to Cp).
+template <typename T>
+__global__ void pack_conv3x3_fwd_kernel(const T* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int C,
+                                        int Cp) {
+  long long total = 1LL * Cout * 9 * Cp;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    int c = i % Cp;
+    int tap = (i / Cp) % 9;
+    int co = i / (9LL * Cp);
+    float v = 0.f;
+    if (c < C) v = to_f32(w[((1LL * co * C + c) * 9) + tap]);
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+// OIHW [Cout][C][3][3] -> input-gradient pack [C][9*Cop]: the dgrad of a stride-1 pad-1 3x3 conv is a 3x3
+// conv of dy with the taps flipped and the channel roles swapped.
+template <typename T>
+__global__ void pack_conv3x3_dgrad_kernel(const T* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int C,
+                                          int Cop) {
+  long long total = 1LL * C * 9 * Cop;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    int co = i % Cop;
+    int tap = (i / Cop) % 9;
+    int ci = i / (9LL * Cop);
+    float v = 0.f;
+    if (co < Cout) v = to_f32(w[((1LL * co * C + ci) * 9) + (8 - tap)]);
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+// [rows][cols] -> bf16 copy (optionally transposed: out[cols][rows]).
+template <typename T>
+__global__ void pack_matrix_kernel(const T* __restrict__ w, __nv_bfloat16* __restrict__ out, int rows, int cols,
+                                   int transpose) {
+  long long total = 1LL * rows * cols;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    int c = i % cols;
+    int r = i / cols;
+    float v = to_f32(w[i]);
+    if (transpose)
+      out[1LL * c * rows + r] = __float2bfloat16(v);
+    else
+      out[i] = __float2bfloat16(v);
+  }
+}
+
+template <typename T>
+__global__ void to_f32_kernel(const T* __restrict__ w, float* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n; i += 1LL * gridDim.x * blockDim.x)
+    out[i] = to_f32(w[i]);
+}
+
+}  // namespace mdc
