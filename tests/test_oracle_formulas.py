@@ -1,0 +1,167 @@
+"""CPU known-answer tests that pin the oracle.
+
+The reference ships no tests or golden vectors, so these are the pins: closed-form values derived from
+the formulas in marigold_dc.py / the diffusers scheduler config, and structural pins (parameter counts,
+state-dict key names).
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import marigold_dc as om
+from oracle.scheduler import DDIMScheduler
+from oracle import image_processor as ip
+from oracle.sd2_modules import (AutoencoderKL, UNet2DConditionModel, count_params, timestep_embedding,
+                                tiny_unet_config, tiny_vae_config)
+
+
+def test_param_counts_and_keys():
+    with torch.device("meta"):
+        u, v = UNet2DConditionModel(), AutoencoderKL()
+    assert count_params(u) == 865_922_244  # 865.9 M
+    assert count_params(v.decoder) + count_params(v.post_quant_conv) == 49_490_199  # 49.5 M
+    ku, kv = set(u.state_dict()), set(v.state_dict())
+    assert len(ku) == 686
+    for k in ["conv_in.weight", "time_embedding.linear_1.weight", "down_blocks.0.resnets.0.time_emb_proj.bias",
+              "down_blocks.0.attentions.1.transformer_blocks.0.attn2.to_k.weight",
+              "down_blocks.2.downsamplers.0.conv.weight", "mid_block.attentions.0.proj_out.bias",
+              "up_blocks.0.upsamplers.0.conv.bias", "up_blocks.3.attentions.2.transformer_blocks.0.ff.net.0.proj.weight",
+              "up_blocks.1.resnets.2.conv_shortcut.weight", "conv_norm_out.weight", "conv_out.bias"]:
+        assert k in ku, k
+    assert "down_blocks.3.attentions.0.norm.weight" not in ku and "up_blocks.0.attentions.0.norm.weight" not in ku
+    for k in ["encoder.conv_in.weight", "encoder.down_blocks.1.resnets.0.conv_shortcut.weight",
+              "encoder.down_blocks.2.downsamplers.0.conv.bias", "decoder.mid_block.attentions.0.to_q.bias",
+              "decoder.mid_block.attentions.0.group_norm.weight", "decoder.mid_block.attentions.0.to_out.0.weight",
+              "decoder.up_blocks.2.upsamplers.0.conv.weight", "decoder.up_blocks.3.resnets.0.conv_shortcut.bias",
+              "decoder.conv_norm_out.bias", "quant_conv.weight", "post_quant_conv.bias"]:
+        assert k in kv, k
+    sd = u.state_dict()
+    assert tuple(sd["up_blocks.1.resnets.2.conv1.weight"].shape) == (1280, 1920, 3, 3)
+    assert tuple(sd["up_blocks.3.resnets.0.conv1.weight"].shape) == (320, 960, 3, 3)
+    assert tuple(sd["down_blocks.0.attentions.0.transformer_blocks.0.ff.net.0.proj.weight"].shape) == (2560, 320)
+    assert tuple(sd["mid_block.attentions.0.transformer_blocks.0.attn2.to_k.weight"].shape) == (1280, 1024)
+
+
+def test_scheduler_known_answers():
+    s = DDIMScheduler()
+    s.set_timesteps(50)
+    ts = s.timesteps.tolist()
+    assert ts == list(range(999, 0, -20)) and ts[0] == 999 and ts[-1] == 19 and len(ts) == 50
+    assert abs(s.alphas_cumprod[999].item() - 0.0046601) < 1e-6
+    assert abs(s.alphas_cumprod[19].item() - 0.982244) < 1e-5
+    assert abs(s.alphas_cumprod[0].item() - 0.99915) < 1e-6
+    x, v = torch.randn(2, 4, 3, 5), torch.randn(2, 4, 3, 5)
+    for t in (999, 499, 19):
+        a = s.alphas_cumprod[t].item()
+        out = s.step(v, torch.tensor(t), x)
+        x0 = math.sqrt(a) * x - math.sqrt(1 - a) * v
+        eps = math.sqrt(a) * v + math.sqrt(1 - a) * x
+        ap = s.alphas_cumprod[t - 20].item() if t >= 20 else s.alphas_cumprod[0].item()
+        assert torch.allclose(out.pred_original_sample, x0, atol=1e-6)
+        assert torch.allclose(out.prev_sample, math.sqrt(ap) * x0 + math.sqrt(1 - ap) * eps, atol=1e-6)
+        # v-prediction identity: x = sqrt(a) x0 + sqrt(1-a) eps
+        assert torch.allclose(math.sqrt(a) * x0 + math.sqrt(1 - a) * eps, x, atol=1e-5)
+    # bf16 samples stay bf16 (0-dim fp32 scalar does not promote)
+    assert s.step(v.bfloat16(), torch.tensor(999), x.bfloat16()).prev_sample.dtype == torch.bfloat16
+
+
+def test_timestep_embedding_layout():
+    e = timestep_embedding(torch.tensor([999.0]), 320)
+    assert e.shape == (1, 320)
+    assert abs(e[0, 0].item() - math.cos(999.0)) < 1e-4 and abs(e[0, 160].item() - math.sin(999.0)) < 1e-4
+    f1 = math.exp(-math.log(10000.0) / 160)
+    assert abs(e[0, 1].item() - math.cos(999.0 * f1)) < 1e-3
+
+
+def test_affine_lsq_known_answer():
+    g = torch.Generator().manual_seed(0)
+    a = torch.rand(3, 1, 8, 9, generator=g)
+    m = torch.rand(3, 1, 8, 9, generator=g) > 0.5
+    guide = 2.5 * a - 0.75
+    s, t = om.compute_affine_params(a, guide * m, m)
+    assert torch.allclose(s, torch.full((3,), 2.5), atol=1e-3) and torch.allclose(t, torch.full((3,), -0.75), atol=1e-3)
+    with pytest.raises(ValueError):
+        om.compute_affine_params(a, guide, torch.zeros_like(m))
+
+
+def test_loss_and_gradient_known_answer():
+    d = torch.tensor([[[[0.2, 0.9], [0.5, 0.1]]]], requires_grad=True)
+    s = torch.tensor([[[[0.4, 0.0], [0.1, 0.0]]]])
+    m = s > 0
+    loss = om.compute_loss(d, s, m)
+    # L1 = (0.2 + 0.4)/2 = 0.3 ; L2 = (0.04 + 0.16)/2 = 0.1
+    assert abs(loss.item() - 0.4) < 1e-6
+    loss.backward(torch.ones_like(loss))
+    # d/dd = sign(d-s)/n + 2(d-s)/n on valid pixels, 0 elsewhere
+    exp = torch.tensor([[[[(-1 - 0.4) / 2, 0.0], [(1 + 0.8) / 2, 0.0]]]])
+    assert torch.allclose(d.grad, exp, atol=1e-6)
+    with pytest.raises(ValueError):
+        om.compute_loss(d, s, m, loss_funcs=[])
+    with pytest.raises(ValueError):
+        om.compute_loss(d, s, m, loss_funcs=["huber"])
+
+
+def test_masked_minmax_and_metrics():
+    x = torch.tensor([[1.0, 5.0, 3.0], [7.0, 2.0, 9.0]])
+    m = torch.tensor([[True, False, True], [False, True, True]])
+    lo, hi = om.masked_minmax(x, m, dim=-1)
+    assert lo.tolist() == [1.0, 2.0] and hi.tolist() == [3.0, 9.0]
+    with pytest.raises(ValueError):
+        om.masked_minmax(x, torch.zeros_like(m), dim=-1)
+    with pytest.raises(ValueError):
+        om.masked_minmax(x, m[:, :2], dim=-1)
+    p, t = torch.tensor([1.0, 2.0, 4.0]), torch.tensor([1.0, 4.0, 0.0])
+    mk = torch.tensor([True, True, False])
+    assert abs(om.mae(p, t, mk).item() - 1.0) < 1e-6 and abs(om.rmse(p, t, mk).item() - math.sqrt(2.0)) < 1e-6
+
+
+def test_adam_first_step_is_lr_sign():
+    x = torch.nn.Parameter(torch.zeros(5))
+    opt = torch.optim.Adam([{"params": [x], "lr": 0.05}])
+    x.grad = torch.tensor([3.0, -2.0, 1e-3, -7.0, 0.5])
+    opt.step()
+    assert torch.allclose(x.detach(), -0.05 * torch.sign(x.grad), atol=1e-6)
+
+
+def test_latent_size_vs_padding_G9():
+    # reference latent size and processor padding agree at 480x640/768 and 352x1216/1216, not 352x1216/768
+    for (H, W, res, ok) in [(480, 640, 768, True), (480, 640, 640, True), (352, 1216, 1216, True), (352, 1216, 768, False),
+                            (768, 1024, 1024, True)]:
+        EH, EW = om.latent_size(H, W, res)
+        img, pad, _ = ip.preprocess(torch.zeros(1, 3, H, W, dtype=torch.uint8), res, "cpu", torch.float32)
+        assert ((img.shape[-2] // 8, img.shape[-1] // 8) == (EH, EW)) == ok
+    assert om.latent_size(480, 640, 768) == (72, 96) and om.latent_size(352, 1216, 1216) == (44, 152)
+
+
+def test_image_processor_ranges_and_unpad():
+    g = torch.Generator().manual_seed(0)
+    img = torch.randint(0, 256, (1, 3, 30, 50), generator=g, dtype=torch.uint8)
+    out, (ph, pw), orig = ip.preprocess(img, 50, "cpu", torch.float32)
+    assert orig == (30, 50) and out.shape == (1, 3, 32, 56) and (ph, pw) == (2, 6)
+    assert out.min() >= -1 and out.max() <= 1
+    assert torch.equal(out[:, :, 29, :50], out[:, :, 31, :50])  # replicate padding
+    assert ip.unpad_image(out, (ph, pw)).shape == (1, 3, 30, 50)
+    with pytest.raises(ValueError):
+        ip.preprocess(img.float(), 50, "cpu", torch.float32)  # raw floats outside [0,1]
+
+
+def test_oracle_loop_runs_and_decreases_loss():
+    torch.manual_seed(1234)
+    from depth_completion_b200.synthetic import make_frame
+
+    unet, vae = UNet2DConditionModel(tiny_unet_config()), AutoencoderKL(tiny_vae_config())
+    pipe = om.OraclePipeline(unet, vae, om.make_empty_text_embedding(64))
+    fr = make_frame(H=48, W=64, n_points=50)
+    tr = []
+    d, x = pipe(fr["img"], fr["sparse"], fr["max_depth"], steps=50, resolution=64, trace=tr.append, max_steps=4)
+    assert d.shape == (1, 1, 48, 64) and x.shape == (1, 4, 6, 8) and d.dtype == torch.float32
+    assert tr[-1]["losses"].item() < tr[0]["losses"].item()
+    # grad-norm rescale: after rescale the latent gradient norm equals ||eps_hat||, so Adam step 1 moves
+    # every element by lr (= 0.05) in magnitude.
+    step1 = (tr[0]["x_adam"] - tr[0]["x_in"]).abs()
+    assert torch.allclose(step1, torch.full_like(step1, 0.05), atol=1e-4)
+    with pytest.raises(ValueError):
+        pipe(fr["img"], torch.zeros_like(fr["sparse"]), 10.0, resolution=64, max_steps=1)
+    with pytest.raises(ValueError):
+        pipe(fr["img"][0], fr["sparse"], 10.0)
