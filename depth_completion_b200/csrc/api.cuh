@@ -1,0 +1,184 @@
+// extern "C" surface of libmdc_b200.so (include/mdc.h, include/mdc_debug.h) over mdc::Engine.
+#pragma once
+#include "debug_api.cuh"
+#include "engine.cuh"
+
+struct mdc_handle {
+  mdc::Engine* e = nullptr;
+  std::vector<std::string> keys, tnames;
+};
+
+namespace mdc {
+__global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ src, int N, int HW, int C, bf16* __restrict__ dst,
+                                        long long ld) {
+  long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+  if (i >= 1LL * N * HW * ld) return;
+  int c = i % ld;
+  long long p = i / ld;
+  int n = p / HW, q = p % HW;
+  dst[i] = __float2bfloat16(c < C ? src[(1LL * n * C + c) * HW + q] : 0.f);
+}
+inline void load_nchw(Tensor* t, bf16* dst, const float* src, cudaStream_t st) {
+  long long tot = t->rows() * t->ld;
+  nchw_f32_to_nhwc_kernel<<<static_cast<int>((tot + 255) / 256), 256, 0, st>>>(src, t->n, t->h * t->w, t->c, dst, t->ld);
+}
+inline void store_nchw(Tensor* t, const bf16* src, float* dst, cudaStream_t st) {
+  long long tot = t->rows() * t->c;
+  nhwc_to_nchw_f32_kernel<<<static_cast<int>((tot + 255) / 256), 256, 0, st>>>(src, t->ld, t->n, t->h * t->w, t->c, dst);
+}
+}  // namespace mdc
+
+extern "C" {
+
+int mdc_create(const mdc_config* cfg, mdc_handle** out) {
+  return mdc::guarded([&] {
+    MDC_CHECK(cfg && out, "null argument");
+    auto* h = new mdc_handle();
+    try {
+      h->e = new mdc::Engine(*cfg);
+    } catch (...) {
+      delete h;
+      throw;
+    }
+    for (auto& kv : h->e->wmap) h->keys.push_back(kv.first);
+    for (auto& kv : h->e->named) h->tnames.push_back(kv.first);
+    *out = h;
+  });
+}
+void mdc_destroy(mdc_handle* h) {
+  if (!h) return;
+  cudaDeviceSynchronize();
+  delete h->e;
+  delete h;
+}
+int mdc_num_weights(mdc_handle* h) { return h ? static_cast<int>(h->keys.size()) : 0; }
+const char* mdc_weight_key(mdc_handle* h, int i) {
+  return (h && i >= 0 && i < static_cast<int>(h->keys.size())) ? h->keys[i].c_str() : nullptr;
+}
+int mdc_set_weight(mdc_handle* h, const char* key, const void* dev_ptr, const long long* shape_host, int ndim, int dtype) {
+  return mdc::guarded([&] {
+    MDC_CHECK(h && key && dev_ptr && shape_host, "null argument");
+    h->e->set_weight(key, dev_ptr, shape_host, ndim, dtype);
+  });
+}
+int mdc_prepare(mdc_handle* h, const void* ctx_bf16, const float* alphas_cumprod_host, const int* timesteps_host,
+                int n_steps) {
+  return mdc::guarded([&] {
+    MDC_CHECK(h && ctx_bf16 && alphas_cumprod_host && timesteps_host, "null argument");
+    h->e->prepare(ctx_bf16, alphas_cumprod_host, timesteps_host, n_steps);
+  });
+}
+int mdc_begin(mdc_handle* h, const void* img_latents_bf16, const void* x_bf16, const float* guide, const uint8_t* mask,
+              const float* guide_minmax_host, const float* depth_minmax_host, float lr_latent, float lr_scaling) {
+  return mdc::guarded([&] {
+    MDC_CHECK(h && img_latents_bf16 && x_bf16 && guide && mask && guide_minmax_host && depth_minmax_host, "null argument");
+    h->e->begin(img_latents_bf16, x_bf16, guide, mask, guide_minmax_host, depth_minmax_host, lr_latent, lr_scaling);
+  });
+}
+int mdc_run(mdc_handle* h, int n_steps) {
+  return mdc::guarded([&] {
+    MDC_CHECK(h, "null handle");
+    for (int i = 0; i < n_steps; ++i) h->e->step();
+    MDC_CUDA(cudaGetLastError());
+  });
+}
+int mdc_get_state(mdc_handle* h, void* x_out_bf16, float* scale_host, float* shift_host, float* loss_host) {
+  return mdc::guarded([&] {
+    MDC_CHECK(h, "null handle");
+    mdc::Engine* e = h->e;
+    MDC_CUDA(cudaStreamSynchronize(e->stream));
+    MDC_CUDA(cudaGetLastError());
+    if (x_out_bf16)
+      MDC_CUDA(cudaMemcpy(x_out_bf16, e->x, 8ull * e->N * e->lh * e->lw, cudaMemcpyDeviceToDevice));
+    mdc::StepAccum a;
+    MDC_CUDA(cudaMemcpy(&a, e->accum, sizeof(a), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < e->N; ++i) {
+      if (scale_host) scale_host[i] = a.scale[i];
+      if (shift_host) shift_host[i] = a.shift[i];
+      if (loss_host) loss_host[i] = a.loss[i];
+    }
+  });
+}
+int mdc_decode_final(mdc_handle* h, float* dense_out) {
+  return mdc::guarded([&] {
+    MDC_CHECK(h && dense_out, "null argument");
+    h->e->decode_final(dense_out);
+  });
+}
+long long mdc_launch_count(mdc_handle* h) { return h ? h->e->launches : 0; }
+long long mdc_device_bytes(mdc_handle* h) { return h ? static_cast<long long>(h->e->arena.total) : 0; }
+
+// ---------------------------------------------------------------------------------------------- debug
+int mdc_dbg_forward(mdc_handle* h, int which, int step, const float* in_nchw, float* out_nchw) {
+  return mdc::guarded([&] {
+    mdc::Engine* e = h->e;
+    MDC_CHECK(e->prepared, "prepare first");
+    mdc::Tensor* in = which == 0 ? e->unet_in : e->dec_in;
+    mdc::Tensor* out = which == 0 ? e->unet_out : e->dec_out;
+    int s = step;
+    MDC_CUDA(cudaMemcpy(e->counter, &s, 4, cudaMemcpyHostToDevice));
+    mdc::begin_step_kernel<<<1, 1024, 0, e->stream>>>(e->tables, e->counter, e->cur, e->temb_cur, e->lr_x, e->lr_s);
+    mdc::load_nchw(in, in->d, in_nchw, e->stream);
+    e->run_ops(which == 0 ? e->unet_ops : e->dec_ops, false);
+    mdc::store_nchw(out, out->d, out_nchw, e->stream);
+    MDC_CUDA(cudaGetLastError());
+    MDC_CUDA(cudaStreamSynchronize(e->stream));
+  });
+}
+int mdc_dbg_backward(mdc_handle* h, int which, const float* dout_nchw, float* din_nchw) {
+  return mdc::guarded([&] {
+    mdc::Engine* e = h->e;
+    mdc::Tensor* in = which == 0 ? e->unet_in : e->dec_in;
+    mdc::Tensor* out = which == 0 ? e->unet_out : e->dec_out;
+    mdc::load_nchw(out, out->g, dout_nchw, e->stream);
+    e->run_ops(which == 0 ? e->unet_ops : e->dec_ops, true);
+    mdc::store_nchw(in, in->g, din_nchw, e->stream);
+    MDC_CUDA(cudaGetLastError());
+    MDC_CUDA(cudaStreamSynchronize(e->stream));
+  });
+}
+int mdc_dbg_read_tensor(mdc_handle* h, const char* name, int which, float* out_nchw) {
+  return mdc::guarded([&] { h->e->read_tensor(name, which, out_nchw); });
+}
+int mdc_dbg_tensor_shape(mdc_handle* h, const char* name, int* nchw_host) {
+  return mdc::guarded([&] {
+    auto it = h->e->named.find(name);
+    MDC_CHECK(it != h->e->named.end(), "unknown tensor '%s'", name);
+    nchw_host[0] = it->second->n, nchw_host[1] = it->second->c, nchw_host[2] = it->second->h, nchw_host[3] = it->second->w;
+  });
+}
+int mdc_dbg_num_tensors(mdc_handle* h) { return static_cast<int>(h->tnames.size()); }
+const char* mdc_dbg_tensor_name(mdc_handle* h, int i) {
+  return (i >= 0 && i < static_cast<int>(h->tnames.size())) ? h->tnames[i].c_str() : nullptr;
+}
+int mdc_dbg_read_x_adam(mdc_handle* h, void* x_out_bf16) {
+  return mdc::guarded([&] {
+    mdc::Engine* e = h->e;
+    MDC_CUDA(cudaStreamSynchronize(e->stream));
+    MDC_CUDA(cudaMemcpy(x_out_bf16, e->x_adam_dbg, 8ull * e->N * e->lh * e->lw, cudaMemcpyDeviceToDevice));
+  });
+}
+int mdc_dbg_time_tapes(mdc_handle* h, int iters, float* ms_host) {
+  return mdc::guarded([&] {
+    mdc::Engine* e = h->e;
+    cudaEvent_t e0, e1;
+    MDC_CUDA(cudaEventCreate(&e0));
+    MDC_CUDA(cudaEventCreate(&e1));
+    for (int k = 0; k < 4; ++k) {
+      auto& ops = k < 2 ? e->unet_ops : e->dec_ops;
+      const bool bwd = k & 1;
+      e->run_ops(ops, bwd);
+      MDC_CUDA(cudaStreamSynchronize(e->stream));
+      MDC_CUDA(cudaEventRecord(e0, e->stream));
+      for (int i = 0; i < iters; ++i) e->run_ops(ops, bwd);
+      MDC_CUDA(cudaEventRecord(e1, e->stream));
+      MDC_CUDA(cudaEventSynchronize(e1));
+      MDC_CUDA(cudaGetLastError());
+      MDC_CUDA(cudaEventElapsedTime(&ms_host[k], e0, e1));
+      ms_host[k] /= iters;
+    }
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,1100 @@
+// The step engine: a static tape of layer ops for the SD2-derived depth UNet and the SD2 VAE decoder, each with a
+// hand-written forward and input-gradient backward (weights are frozen, so no weight gradients exist -- SURVEY.md G8).
+//
+// Design (B200-first, not a translation of autograd):
+//   * every activation is NHWC bf16 and lives for the whole handle lifetime in HBM (180 GB: no recompute, no
+//     allocator on the hot path); all GEMM/conv launch plans (TMA descriptors included) are built once;
+//   * skip-connection concats are zero-copy: producers write straight into channel slices of the concat buffer;
+//   * residual adds, biases and time-embedding adds ride in the GEMM/conv epilogue; gradient accumulation at
+//     fan-out points rides in the consumer kernels (`acc` flag resolved at plan time);
+//   * only the saved tensors the input-gradient path needs are kept: GroupNorm/LayerNorm inputs + statistics,
+//     attention probabilities, GEGLU pre-activations.
+#pragma once
+#include <cmath>
+#include <deque>
+#include <functional>
+#include <map>
+#include <memory>
+
+#include "../../include/mdc.h"
+#include "gemm.cuh"
+#include "pack.cuh"
+#include "tail.cuh"
+
+namespace mdc {
+
+// ------------------------------------------------------------------------------------------------ memory
+struct Arena {
+  std::vector<void*> blocks;
+  size_t total = 0;
+  void* alloc(size_t bytes) {
+    void* p = nullptr;
+    bytes = (bytes + 255) & ~size_t(255);
+    MDC_CUDA(cudaMalloc(&p, bytes));
+    MDC_CUDA(cudaMemset(p, 0, bytes));
+    blocks.push_back(p);
+    total += bytes;
+    return p;
+  }
+  template <typename T>
+  T* make(size_t n) {
+    return static_cast<T*>(alloc(n * sizeof(T)));
+  }
+  ~Arena() {
+    for (void* p : blocks) cudaFree(p);
+  }
+};
+
+struct Tensor {
+  bf16* d = nullptr;
+  bf16* g = nullptr;
+  int n = 0, h = 0, w = 0, c = 0;
+  long long ld = 0;
+  bool grad_set = false;
+  std::string name;
+  long long rows() const { return 1LL * n * h * w; }
+};
+
+struct Op {
+  std::string name;
+  virtual ~Op() {}
+  virtual void plan_bwd() {}
+  virtual void fwd(cudaStream_t) = 0;
+  virtual void bwd(cudaStream_t) {}
+};
+
+enum WKind { W_CONV3 = 0, W_LIN = 1, W_VEC = 2 };
+struct WeightSlot {
+  WKind kind;
+  int out = 0, in = 0;          // logical dims ([out, in, 3, 3] / [out, in] / [out])
+  bf16* w = nullptr;            // CONV3: fwd pack; LIN: [out rows at w][ld_w]
+  long long ld_w = 0;
+  bf16* wt = nullptr;           // CONV3: dgrad pack; LIN: transposed pack (column offset applied), ld_wt
+  long long ld_wt = 0;
+  float* vec = nullptr;         // VEC destination
+  bool loaded = false;
+};
+
+struct Engine;
+
+// ------------------------------------------------------------------------------------------------ ops
+struct ConvOp : Op {  // 3x3 stride-1 pad-1 convolution (+bias, +residual)
+  Engine* E;
+  Tensor *x, *y, *res;
+  WeightSlot* W;
+  const float* bias;
+  GemmPlan pf, pb;
+  bool acc_res = false;
+  void plan_bwd() override;
+  void fwd(cudaStream_t st) override { run_gemm(pf, st); }
+  void bwd(cudaStream_t st) override;
+};
+struct LinearOp : Op {  // y[rows, out] = x[rows, in] W^T (+bias, +residual)
+  Engine* E;
+  Tensor *x, *y, *res;
+  bf16 *w, *wt;
+  long long ld_w, ld_wt;
+  const float* bias;
+  GemmPlan pf, pb;
+  bool acc_res = false;
+  void plan_bwd() override;
+  void fwd(cudaStream_t st) override { run_gemm(pf, st); }
+  void bwd(cudaStream_t st) override;
+};
+struct GroupNormOp : Op {
+  Engine* E;
+  Tensor *x, *y;
+  const float *gamma, *beta;
+  float eps;
+  int groups, silu;
+  float* stats;
+  GNShape s;
+  int threads;
+  bool acc = false;
+  void plan_bwd() override {
+    acc = x->grad_set;
+    x->grad_set = true;
+  }
+  void fwd(cudaStream_t st) override;
+  void bwd(cudaStream_t st) override;
+};
+struct LayerNormOp : Op {
+  Tensor *x, *y;
+  const float *gamma, *beta;
+  float* stats;
+  bool acc = false;
+  void plan_bwd() override {
+    acc = x->grad_set;
+    x->grad_set = true;
+  }
+  void fwd(cudaStream_t st) override {
+    int rows = static_cast<int>(x->rows());
+    ln_fwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x->d, x->ld, rows, x->c, gamma, beta, 1e-5f, y->d, y->ld, stats);
+  }
+  void bwd(cudaStream_t st) override {
+    int rows = static_cast<int>(x->rows());
+    ln_bwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x->d, x->ld, y->g, y->ld, rows, x->c, gamma, stats, x->g, x->ld, acc);
+  }
+};
+struct GegluOp : Op {
+  Tensor *x, *y;
+  bool acc = false;
+  void plan_bwd() override {
+    acc = x->grad_set;
+    x->grad_set = true;
+  }
+  void fwd(cudaStream_t st) override {
+    geglu_fwd_kernel<<<ew_grid(x->rows() * (y->c / 8)), 256, 0, st>>>(x->d, x->ld, x->rows(), y->c, y->d, y->ld);
+  }
+  void bwd(cudaStream_t st) override {
+    geglu_bwd_kernel<<<ew_grid(x->rows() * (y->c / 8)), 256, 0, st>>>(x->d, x->ld, y->g, y->ld, x->rows(), y->c, x->g,
+                                                                     x->ld, acc);
+  }
+};
+struct SelfAttnOp : Op {  // softmax(q k^T / sqrt(dh)) v over the tokens of each image; qkv [rows, 3*d] fused
+  Engine* E;
+  Tensor *qkv, *o;
+  int heads, dh, T;
+  long long ldS;
+  bf16* P;  // saved probabilities [n, heads, T, ldS]
+  GemmPlan p_s, p_o, p_dv, p_dp, p_dq, p_dk;
+  void plan_bwd() override;
+  void fwd(cudaStream_t st) override;
+  void bwd(cudaStream_t st) override;
+};
+struct CrossAttn2Op : Op {  // attention over the 2 tokens of the empty-prompt embedding (step-invariant K, V)
+  Tensor *q, *o;
+  int heads;
+  const float *kc, *vc;
+  bool acc = false;
+  void plan_bwd() override {
+    acc = q->grad_set;
+    q->grad_set = true;
+  }
+  void fwd(cudaStream_t st) override {
+    long long warps = q->rows() * heads;
+    xattn2_fwd_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, st>>>(q->d, q->ld, q->rows(), heads, kc, vc,
+                                                                                 0.125f, o->d, o->ld);
+  }
+  void bwd(cudaStream_t st) override {
+    long long warps = q->rows() * heads;
+    xattn2_bwd_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, st>>>(q->d, q->ld, o->g, o->ld, q->rows(),
+                                                                                 heads, kc, vc, 0.125f, q->g, q->ld, acc);
+  }
+};
+struct UpsampleOp : Op {
+  Tensor *x, *y;
+  bool acc = false;
+  void plan_bwd() override {
+    acc = x->grad_set;
+    x->grad_set = true;
+  }
+  void fwd(cudaStream_t st) override {
+    upsample_nearest_fwd_kernel<<<ew_grid(y->rows() * (y->c / 8)), 256, 0, st>>>(x->d, x->ld, x->n, x->h, x->w, x->c,
+                                                                                y->d, y->ld, y->h, y->w);
+  }
+  void bwd(cudaStream_t st) override {
+    upsample_nearest_bwd_kernel<<<ew_grid(x->rows() * (x->c / 8)), 256, 0, st>>>(y->g, y->ld, x->n, x->h, x->w, x->c,
+                                                                                x->g, x->ld, y->h, y->w, acc);
+  }
+};
+struct SubsampleOp : Op {
+  Tensor *x, *y;
+  int off;
+  bool acc = false;
+  void plan_bwd() override {
+    acc = x->grad_set;
+    x->grad_set = true;
+  }
+  void fwd(cudaStream_t st) override {
+    subsample2_fwd_kernel<<<ew_grid(y->rows() * (y->c / 8)), 256, 0, st>>>(x->d, x->ld, x->n, x->h, x->w, x->c, off, y->d,
+                                                                          y->ld, y->h, y->w);
+  }
+  void bwd(cudaStream_t st) override {
+    subsample2_bwd_kernel<<<ew_grid(x->rows() * (x->c / 8)), 256, 0, st>>>(y->g, y->ld, x->n, x->h, x->w, x->c, off, x->g,
+                                                                          x->ld, y->h, y->w, acc);
+  }
+};
+struct ConcatOp : Op {  // zero-copy: a and b are channel-slice views of cat; only propagates the plan-time flags
+  Tensor *a, *b, *cat;
+  void plan_bwd() override { a->grad_set = b->grad_set = cat->grad_set; }
+  void fwd(cudaStream_t) override {}
+};
+
+// ------------------------------------------------------------------------------------------------ engine
+struct Engine {
+  mdc_config cfg;
+  Arena arena;
+  std::deque<Tensor> tensors;
+  std::map<std::string, Tensor*> named;
+  std::map<std::string, std::vector<WeightSlot*>> wmap;
+  std::deque<WeightSlot> wslots;
+  std::vector<std::unique_ptr<Op>> unet_ops, dec_ops;
+  std::vector<std::unique_ptr<Op>>* cur_ops = nullptr;
+  cudaStream_t stream = 0;
+
+  // geometry
+  int N, H, W, ph, pw, PPH, PPW, lh, lw;
+  // graph endpoints
+  Tensor *unet_in = nullptr, *unet_out = nullptr, *dec_in = nullptr, *dec_out = nullptr;
+  // shared scratch
+  float* gn_partial = nullptr;
+  size_t gn_partial_floats = 0;
+  float* gn_gstats = nullptr;
+  float* attn_S = nullptr;
+  size_t attn_S_floats = 0;
+  // time embedding
+  struct TembUse {
+    WeightSlot* proj_w;
+    WeightSlot* proj_b;
+    WeightSlot* conv_b;
+    int off, cout;
+  };
+  std::vector<TembUse> temb_uses;
+  int temb_total = 0;
+  float* temb_cur = nullptr;
+  float* temb_table = nullptr;
+  WeightSlot *te_l1w = nullptr, *te_l1b = nullptr, *te_l2w = nullptr, *te_l2b = nullptr;
+  // cross attention K/V
+  struct XUse {
+    WeightSlot *wk, *wv;
+    float *kc, *vc;
+    int d;
+  };
+  std::vector<XUse> xuses;
+  // step state
+  StepTables tables{};
+  StepCur* cur = nullptr;
+  StepAccum* accum = nullptr;
+  int* counter = nullptr;
+  float *d_sqrt_a = nullptr, *d_sqrt_1ma = nullptr, *d_sqrt_ap = nullptr, *d_sqrt_1map = nullptr;
+  bf16 *x = nullptr, *m1 = nullptr, *m2 = nullptr, *img_lat = nullptr, *x_adam_dbg = nullptr;
+  float *dx_direct = nullptr, *gbuf = nullptr, *eps_part = nullptr, *g_part = nullptr, *dmean = nullptr;
+  int parts_per_img = 1;
+  int* pt_idx = nullptr;
+  float* pt_val = nullptr;
+  int* pt_off = nullptr;
+  float *gminmax = nullptr, *depth_minmax = nullptr;
+  float lr_x = 0.05f, lr_s = 0.005f;
+  bool prepared = false, begun = false;
+  int steps_done = 0;
+  long long launches = 0;
+
+  explicit Engine(const mdc_config& c);
+  // builders
+  Tensor* new_tensor(int n, int h, int w, int c, const std::string& name, bool with_grad = true, long long ld = 0);
+  Tensor* view(Tensor* parent, int c0, int c, const std::string& name);
+  WeightSlot* slot(const std::string& key, WKind kind, int out, int in);
+  WeightSlot* slot_lin_into(const std::string& key, int out, int in, bf16* w, long long ld_w, bf16* wt, long long ld_wt);
+  WeightSlot* slot_vec_into(const std::string& key, int n, float* dst);
+  void push(Op* op, const std::string& name) {
+    op->name = name;
+    cur_ops->emplace_back(op);
+  }
+  Tensor* conv3x3(Tensor* x, int cout, const std::string& key, Tensor* res = nullptr, Tensor* out = nullptr,
+                  const std::string& temb_key = "");
+  Tensor* linear(Tensor* x, int cout, const std::string& key, bool has_bias, Tensor* res = nullptr, Tensor* out = nullptr);
+  Tensor* group_norm(Tensor* x, const std::string& key, float eps, bool silu);
+  Tensor* layer_norm(Tensor* x, const std::string& key);
+  Tensor* resnet(Tensor* x, int cout, const std::string& key, bool temb, float eps, Tensor* out = nullptr);
+  Tensor* transformer(Tensor* x, int heads, const std::string& key, Tensor* out = nullptr);
+  Tensor* self_attention(Tensor* qkv, int heads, const std::string& name);
+  Tensor* upsample_conv(Tensor* x, int H2, int W2, const std::string& key, Tensor* out = nullptr);
+  Tensor* downsample_conv(Tensor* x, const std::string& key, Tensor* out = nullptr);
+  void build_unet();
+  void build_decoder();
+  void finalize_plans();
+  // runtime
+  void set_weight(const std::string& key, const void* src, const long long* shape, int ndim, int dtype);
+  void prepare(const void* ctx_bf16, const float* alphas_cumprod, const int* timesteps, int n_steps);
+  void begin(const void* img_latents, const void* x0, const float* guide, const uint8_t* mask, const float* gmm,
+             const float* dmm, float lrx, float lrs);
+  void run_ops(std::vector<std::unique_ptr<Op>>& ops, bool backward);
+  void step();
+  void decode_final(float* dense_out);
+  void read_tensor(const std::string& name, int which, float* out_nchw);
+};
+
+// ================================================================================================ op bodies
+inline void ConvOp::plan_bwd() {
+  Epilogue e;
+  e.out = x->g, e.ldc = x->ld;
+  if (x->grad_set) e.res = x->g, e.ldr = x->ld;
+  x->grad_set = true;
+  pb = plan_conv3x3(y->n, y->h, y->w, y->c, x->c, y->g, y->ld, W->wt, e);
+  if (res) {
+    acc_res = res->grad_set;
+    res->grad_set = true;
+  }
+}
+inline void ConvOp::bwd(cudaStream_t st) {
+  run_gemm(pb, st);
+  if (res)
+    add_rows_kernel<<<ew_grid(res->rows() * (res->c / 8)), 256, 0, st>>>(y->g, y->ld, res->g, res->ld, res->rows(), res->c,
+                                                                        acc_res);
+}
+inline void LinearOp::plan_bwd() {
+  Epilogue e;
+  e.out = x->g, e.ldc = x->ld;
+  if (x->grad_set) e.res = x->g, e.ldr = x->ld;
+  x->grad_set = true;
+  Operand A{y->g, 0, y->ld, 0, 0}, B{wt, 0, ld_wt, 0, 0};
+  pb = plan_gemm(static_cast<int>(x->rows()), x->c, y->c, A, B, e);
+  if (res) {
+    acc_res = res->grad_set;
+    res->grad_set = true;
+  }
+}
+inline void LinearOp::bwd(cudaStream_t st) {
+  run_gemm(pb, st);
+  if (res)
+    add_rows_kernel<<<ew_grid(res->rows() * (res->c / 8)), 256, 0, st>>>(y->g, y->ld, res->g, res->ld, res->rows(), res->c,
+                                                                        acc_res);
+}
+inline void GroupNormOp::fwd(cudaStream_t st) {
+  const int grid = s.N * s.blocks_per_img;
+  gn_stats_kernel<<<grid, threads, 2 * s.G * sizeof(float), st>>>(x->d, s, E->gn_partial);
+  gn_finalize_kernel<<<(s.N * s.G + 127) / 128, 128, 0, st>>>(E->gn_partial, s.N, s.G, s.blocks_per_img,
+                                                              1.0 * s.HW * (s.C / s.G), eps, 0, stats);
+  gn_apply_kernel<<<grid, threads, 0, st>>>(x->d, s, stats, gamma, beta, silu, y->d, y->ld);
+}
+inline void GroupNormOp::bwd(cudaStream_t st) {
+  const int grid = s.N * s.blocks_per_img;
+  gn_bwd_stats_kernel<<<grid, threads, 2 * s.G * sizeof(float), st>>>(x->d, y->g, y->ld, s, stats, gamma, beta, silu,
+                                                                      E->gn_partial);
+  gn_finalize_kernel<<<(s.N * s.G + 127) / 128, 128, 0, st>>>(E->gn_partial, s.N, s.G, s.blocks_per_img,
+                                                              1.0 * s.HW * (s.C / s.G), 0.f, 1, E->gn_gstats);
+  gn_bwd_apply_kernel<<<grid, threads, 0, st>>>(x->d, y->g, y->ld, s, stats, E->gn_gstats, gamma, beta, silu, x->g, x->ld,
+                                                acc);
+}
+
+inline void SelfAttnOp::plan_bwd() {
+  const int d = heads * dh, n = qkv->n;
+  const long long ldq = qkv->ld, tok = 1LL * T * ldq;
+  const long long sP0 = 1LL * T * ldS, sP1 = 1LL * heads * T * ldS;
+  bf16 *q = qkv->d, *k = qkv->d + d, *v = qkv->d + 2 * d;
+  bf16 *dq = qkv->g, *dk = qkv->g + d, *dv = qkv->g + 2 * d;
+  const float scale = 1.f / sqrtf(static_cast<float>(dh));
+  (void)scale;
+  // dV[key, c] = sum_q P[q, key] dO[q, c]     A = P^T (M-major), B = dO^T (N-major)
+  {
+    Operand A{P, 1, ldS, sP0, sP1}, B{o->g, 1, o->ld, dh, 1LL * T * o->ld};
+    Epilogue e;
+    e.out = dv, e.ldc = ldq, e.sc0 = dh, e.sc1 = tok;
+    p_dv = plan_gemm(T, dh, T, A, B, e, heads, n);
+  }
+  // dP[q, key] = sum_c dO[q, c] V[key, c]      -> fp32 scratch
+  {
+    Operand A{o->g, 0, o->ld, dh, 1LL * T * o->ld}, B{v, 0, ldq, dh, tok};
+    Epilogue e;
+    e.out = E->attn_S, e.out_f32 = 1, e.ldc = ldS, e.sc0 = sP0, e.sc1 = sP1;
+    p_dp = plan_gemm(T, T, dh, A, B, e, heads, n);
+  }
+  // dQ[q, c] = sum_key dS[q, key] K[key, c]    A = dS (K-major), B = K^T (N-major)
+  {
+    Operand A{P, 0, ldS, sP0, sP1}, B{k, 1, ldq, dh, tok};
+    Epilogue e;
+    e.out = dq, e.ldc = ldq, e.sc0 = dh, e.sc1 = tok;
+    p_dq = plan_gemm(T, dh, T, A, B, e, heads, n);
+  }
+  // dK[key, c] = sum_q dS[q, key] Q[q, c]      A = dS^T (M-major), B = Q^T (N-major)
+  {
+    Operand A{P, 1, ldS, sP0, sP1}, B{q, 1, ldq, dh, tok};
+    Epilogue e;
+    e.out = dk, e.ldc = ldq, e.sc0 = dh, e.sc1 = tok;
+    p_dk = plan_gemm(T, dh, T, A, B, e, heads, n);
+  }
+  qkv->grad_set = true;  // q, k, v slices are each written exactly once
+}
+inline void SelfAttnOp::fwd(cudaStream_t st) {
+  run_gemm(p_s, st);
+  const int rows = qkv->n * heads * T;
+  softmax_fwd_kernel<<<rows, 256, (((T + 3) & ~3) + 32) * sizeof(float), st>>>(E->attn_S, P, T, ldS);
+  run_gemm(p_o, st);
+}
+inline void SelfAttnOp::bwd(cudaStream_t st) {
+  run_gemm(p_dv, st);
+  run_gemm(p_dp, st);
+  const int rows = qkv->n * heads * T;
+  softmax_bwd_kernel<<<rows, 256, (((T + 3) & ~3) + 32) * sizeof(float), st>>>(E->attn_S, P, T, ldS,
+                                                                              1.f / sqrtf(static_cast<float>(dh)));
+  run_gemm(p_dq, st);
+  run_gemm(p_dk, st);
+}
+
+// ================================================================================================ builders
+inline Tensor* Engine::new_tensor(int n, int h, int w, int c, const std::string& name, bool with_grad, long long ld) {
+  tensors.emplace_back();
+  Tensor* t = &tensors.back();
+  t->n = n, t->h = h, t->w = w, t->c = c;
+  t->ld = ld ? ld : ((c + 7) / 8) * 8;
+  t->name = name;
+  size_t el = static_cast<size_t>(t->rows()) * t->ld + 64;
+  t->d = arena.make<bf16>(el);
+  if (with_grad) t->g = arena.make<bf16>(el);
+  if (!name.empty()) named[name] = t;
+  return t;
+}
+inline Tensor* Engine::view(Tensor* parent, int c0, int c, const std::string& name) {
+  tensors.emplace_back();
+  Tensor* t = &tensors.back();
+  *t = *parent;
+  t->c = c;
+  t->d = parent->d + c0;
+  t->g = parent->g ? parent->g + c0 : nullptr;
+  t->grad_set = false;
+  t->name = name;
+  if (!name.empty()) named[name] = t;
+  return t;
+}
+inline WeightSlot* Engine::slot(const std::string& key, WKind kind, int out, int in) {
+  wslots.emplace_back();
+  WeightSlot* s = &wslots.back();
+  s->kind = kind, s->out = out, s->in = in;
+  if (kind == W_CONV3) {
+    const int inp = ((in + 63) / 64) * 64, outp = ((out + 63) / 64) * 64;
+    s->w = arena.make<bf16>(9ull * inp * out + 64);
+    s->wt = arena.make<bf16>(9ull * outp * in + 64);
+  } else if (kind == W_LIN) {
+    s->ld_w = ((in + 7) / 8) * 8, s->ld_wt = ((out + 7) / 8) * 8;  // TMA needs 16-byte row strides
+    s->w = arena.make<bf16>(1ull * out * s->ld_w + 64);
+    s->wt = arena.make<bf16>(1ull * in * s->ld_wt + 64);
+  } else {
+    s->vec = arena.make<float>(out + 16);
+  }
+  wmap[key].push_back(s);
+  return s;
+}
+inline WeightSlot* Engine::slot_lin_into(const std::string& key, int out, int in, bf16* w, long long ld_w, bf16* wt,
+                                         long long ld_wt) {
+  wslots.emplace_back();
+  WeightSlot* s = &wslots.back();
+  s->kind = W_LIN, s->out = out, s->in = in, s->w = w, s->ld_w = ld_w, s->wt = wt, s->ld_wt = ld_wt;
+  wmap[key].push_back(s);
+  return s;
+}
+inline WeightSlot* Engine::slot_vec_into(const std::string& key, int n, float* dst) {
+  wslots.emplace_back();
+  WeightSlot* s = &wslots.back();
+  s->kind = W_VEC, s->out = n, s->vec = dst;
+  wmap[key].push_back(s);
+  return s;
+}
+
+inline Tensor* Engine::conv3x3(Tensor* x, int cout, const std::string& key, Tensor* res, Tensor* out,
+                               const std::string& temb_key) {
+  WeightSlot* W = slot(key + ".weight", W_CONV3, cout, x->c);
+  WeightSlot* B = slot(key + ".bias", W_VEC, cout, 0);
+  Tensor* y = out ? out : new_tensor(x->n, x->h, x->w, cout, "");
+  auto* op = new ConvOp();
+  op->E = this, op->x = x, op->y = y, op->res = res, op->W = W;
+  op->bias = B->vec;
+  if (!temb_key.empty()) {  // conv bias + time_emb_proj(silu(temb)) of the current step (filled by begin_step_kernel)
+    TembUse u;
+    u.proj_w = slot(temb_key + ".weight", W_LIN, cout, cfg.unet_block_ch[0] * 4);
+    u.proj_b = slot(temb_key + ".bias", W_VEC, cout, 0);
+    u.conv_b = B, u.off = temb_total, u.cout = cout;
+    temb_total += ((cout + 3) / 4) * 4;
+    temb_uses.push_back(u);
+    op->bias = reinterpret_cast<const float*>(static_cast<uintptr_t>(u.off) + 1);  // patched in finalize_plans()
+  }
+  Epilogue e;
+  e.out = y->d, e.ldc = y->ld, e.bias = op->bias;
+  if (res) e.res = res->d, e.ldr = res->ld;
+  op->pf = plan_conv3x3(x->n, x->h, x->w, x->c, cout, x->d, x->ld, W->w, e);
+  push(op, key);
+  return y;
+}
+inline Tensor* Engine::linear(Tensor* x, int cout, const std::string& key, bool has_bias, Tensor* res, Tensor* out) {
+  WeightSlot* W = slot(key + ".weight", W_LIN, cout, x->c);
+  WeightSlot* B = has_bias ? slot(key + ".bias", W_VEC, cout, 0) : nullptr;
+  Tensor* y = out ? out : new_tensor(x->n, x->h, x->w, cout, "");
+  auto* op = new LinearOp();
+  op->E = this, op->x = x, op->y = y, op->res = res;
+  op->w = W->w, op->wt = W->wt, op->ld_w = W->ld_w, op->ld_wt = W->ld_wt;
+  op->bias = B ? B->vec : nullptr;
+  Epilogue e;
+  e.out = y->d, e.ldc = y->ld, e.bias = op->bias;
+  if (res) e.res = res->d, e.ldr = res->ld;
+  Operand A{x->d, 0, x->ld, 0, 0}, Bm{W->w, 0, W->ld_w, 0, 0};
+  op->pf = plan_gemm(static_cast<int>(x->rows()), cout, x->c, A, Bm, e);
+  push(op, key);
+  return y;
+}
+inline Tensor* Engine::group_norm(Tensor* x, const std::string& key, float eps, bool silu) {
+  const int G = cur_ops == &unet_ops ? cfg.unet_groups : cfg.vae_groups;
+  MDC_CHECK(x->c % G == 0 && (x->c / G) % 2 == 0 && x->c % 8 == 0, "GroupNorm: C=%d G=%d unsupported", x->c, G);
+  WeightSlot* ga = slot(key + ".weight", W_VEC, x->c, 0);
+  WeightSlot* be = slot(key + ".bias", W_VEC, x->c, 0);
+  Tensor* y = new_tensor(x->n, x->h, x->w, x->c, "");
+  auto* op = new GroupNormOp();
+  op->E = this, op->x = x, op->y = y, op->gamma = ga->vec, op->beta = be->vec, op->eps = eps, op->groups = G;
+  op->silu = silu ? 1 : 0;
+  const int CV = x->c / 8;
+  MDC_CHECK(CV <= 512, "GroupNorm: C=%d too wide", x->c);
+  const int R = std::max(1, 512 / CV);
+  op->threads = CV * R;
+  GNShape s;
+  s.N = x->n, s.HW = x->h * x->w, s.C = x->c, s.G = G, s.ld = x->ld;
+  int want_blocks = std::max(1, (2 * g_num_sms()) / x->n);
+  int ppb = std::max(R, (s.HW + want_blocks - 1) / want_blocks);
+  ppb = ((ppb + R - 1) / R) * R;
+  s.pix_per_block = ppb;
+  s.blocks_per_img = (s.HW + ppb - 1) / ppb;
+  op->s = s;
+  op->stats = arena.make<float>(2ull * x->n * G);
+  gn_partial_floats = std::max<size_t>(gn_partial_floats, static_cast<size_t>(2) * G * x->n * s.blocks_per_img);
+  push(op, key);
+  return y;
+}
+inline Tensor* Engine::layer_norm(Tensor* x, const std::string& key) {
+  MDC_CHECK(x->c % 8 == 0 && x->c <= 32 * 8 * LN_MAXV, "LayerNorm: d=%d unsupported", x->c);
+  WeightSlot* ga = slot(key + ".weight", W_VEC, x->c, 0);
+  WeightSlot* be = slot(key + ".bias", W_VEC, x->c, 0);
+  Tensor* y = new_tensor(x->n, x->h, x->w, x->c, "");
+  auto* op = new LayerNormOp();
+  op->x = x, op->y = y, op->gamma = ga->vec, op->beta = be->vec;
+  op->stats = arena.make<float>(2ull * x->rows());
+  push(op, key);
+  return y;
+}
+inline Tensor* Engine::resnet(Tensor* x, int cout, const std::string& key, bool temb, float eps, Tensor* out) {
+  Tensor* h = group_norm(x, key + ".norm1", eps, true);
+  h = conv3x3(h, cout, key + ".conv1", nullptr, nullptr, temb ? key + ".time_emb_proj" : "");
+  h = group_norm(h, key + ".norm2", eps, true);
+  Tensor* sc = x;
+  if (x->c != cout) sc = linear(x, cout, key + ".conv_shortcut", true);
+  Tensor* y = conv3x3(h, cout, key + ".conv2", sc, out);
+  if (y->name.empty()) y->name = key, named[key] = y;
+  return y;
+}
+inline Tensor* Engine::self_attention(Tensor* qkv, int heads, const std::string& name) {
+  const int d = qkv->c / 3, dh = d / heads, T = qkv->h * qkv->w, n = qkv->n;
+  MDC_CHECK(dh % 64 == 0 && dh <= 512, "attention head_dim %d unsupported (need a multiple of 64)", dh);
+  Tensor* o = new_tensor(n, qkv->h, qkv->w, d, "");
+  auto* op = new SelfAttnOp();
+  op->E = this, op->qkv = qkv, op->o = o, op->heads = heads, op->dh = dh, op->T = T;
+  op->ldS = ((T + 7) / 8) * 8;
+  const long long ldS = op->ldS, ldq = qkv->ld, tok = 1LL * T * ldq;
+  const long long sP0 = 1LL * T * ldS, sP1 = 1LL * heads * T * ldS;
+  op->P = arena.make<bf16>(static_cast<size_t>(n) * heads * T * ldS + 64);
+  attn_S_floats = std::max<size_t>(attn_S_floats, static_cast<size_t>(n) * heads * T * ldS + 64);
+  // S = scale * Q K^T -> fp32 scratch (allocated after the graph is built; patched in finalize_plans)
+  {
+    Operand A{qkv->d, 0, ldq, dh, tok}, B{qkv->d + d, 0, ldq, dh, tok};
+    Epilogue e;
+    e.out = nullptr, e.out_f32 = 1, e.ldc = ldS, e.sc0 = sP0, e.sc1 = sP1, e.alpha = 1.f / sqrtf(static_cast<float>(dh));
+    op->p_s = plan_gemm(T, T, dh, A, B, e, heads, n);
+  }
+  // O = P V : B = V^T is N-major
+  {
+    Operand A{op->P, 0, ldS, sP0, sP1}, B{qkv->d + 2 * d, 1, ldq, dh, tok};
+    Epilogue e;
+    e.out = o->d, e.ldc = o->ld, e.sc0 = dh, e.sc1 = 1LL * T * o->ld;
+    op->p_o = plan_gemm(T, dh, T, A, B, e, heads, n);
+  }
+  push(op, name);
+  return o;
+}
+inline Tensor* Engine::transformer(Tensor* x, int heads, const std::string& key, Tensor* out) {
+  const int d = x->c;
+  const std::string tb = key + ".transformer_blocks.0";
+  Tensor* h = group_norm(x, key + ".norm", 1e-6f, false);
+  h = linear(h, d, key + ".proj_in", true);
+  // --- self attention (fused q/k/v projection, no bias)
+  Tensor* n1 = layer_norm(h, tb + ".norm1");
+  Tensor* qkv = new_tensor(x->n, x->h, x->w, 3 * d, "");
+  {
+    bf16* w = arena.make<bf16>(3ull * d * d + 64);
+    bf16* wt = arena.make<bf16>(3ull * d * d + 64);
+    const char* nm[3] = {".attn1.to_q.weight", ".attn1.to_k.weight", ".attn1.to_v.weight"};
+    for (int i = 0; i < 3; ++i) slot_lin_into(tb + nm[i], d, d, w + 1ull * i * d * d, d, wt + i * d, 3 * d);
+    auto* op = new LinearOp();
+    op->E = this, op->x = n1, op->y = qkv, op->res = nullptr, op->w = w, op->wt = wt, op->ld_w = d, op->ld_wt = 3 * d;
+    op->bias = nullptr;
+    Epilogue e;
+    e.out = qkv->d, e.ldc = qkv->ld;
+    Operand A{n1->d, 0, n1->ld, 0, 0}, Bm{w, 0, d, 0, 0};
+    op->pf = plan_gemm(static_cast<int>(n1->rows()), 3 * d, d, A, Bm, e);
+    push(op, tb + ".attn1.to_qkv");
+  }
+  Tensor* ao = self_attention(qkv, heads, tb + ".attn1");
+  h = linear(ao, d, tb + ".attn1.to_out.0", true, h);
+  // --- cross attention over the 2 empty-prompt tokens (K, V precomputed in prepare())
+  Tensor* n2 = layer_norm(h, tb + ".norm2");
+  Tensor* q2 = linear(n2, d, tb + ".attn2.to_q", false);
+  Tensor* o2 = new_tensor(x->n, x->h, x->w, d, "");
+  {
+    XUse u;
+    u.wk = slot(tb + ".attn2.to_k.weight", W_LIN, d, cfg.cross_dim);
+    u.wv = slot(tb + ".attn2.to_v.weight", W_LIN, d, cfg.cross_dim);
+    u.kc = arena.make<float>(2ull * d);
+    u.vc = arena.make<float>(2ull * d);
+    u.d = d;
+    xuses.push_back(u);
+    auto* op = new CrossAttn2Op();
+    op->q = q2, op->o = o2, op->heads = heads, op->kc = u.kc, op->vc = u.vc;
+    MDC_CHECK(d / heads == 64, "cross-attention head_dim must be 64 (got %d)", d / heads);
+    push(op, tb + ".attn2");
+  }
+  h = linear(o2, d, tb + ".attn2.to_out.0", true, h);
+  // --- GEGLU feed-forward
+  Tensor* n3 = layer_norm(h, tb + ".norm3");
+  Tensor* pr = linear(n3, 8 * d, tb + ".ff.net.0.proj", true);
+  Tensor* gg = new_tensor(x->n, x->h, x->w, 4 * d, "");
+  {
+    auto* op = new GegluOp();
+    op->x = pr, op->y = gg;
+    push(op, tb + ".ff.net.0");
+  }
+  h = linear(gg, d, tb + ".ff.net.2", true, h);
+  Tensor* y = linear(h, d, key + ".proj_out", true, x, out);
+  if (y->name.empty()) y->name = key, named[key] = y;
+  return y;
+}
+inline Tensor* Engine::upsample_conv(Tensor* x, int H2, int W2, const std::string& key, Tensor* out) {
+  Tensor* up = new_tensor(x->n, H2, W2, x->c, "");
+  auto* op = new UpsampleOp();
+  op->x = x, op->y = up;
+  push(op, key + ".nearest");
+  Tensor* y = conv3x3(up, x->c, key + ".conv", nullptr, out);
+  if (y->name.empty()) y->name = key, named[key] = y;
+  return y;
+}
+inline Tensor* Engine::downsample_conv(Tensor* x, const std::string& key, Tensor* out) {
+  Tensor* full = conv3x3(x, x->c, key + ".conv");
+  const int Ho = (x->h - 1) / 2 + 1, Wo = (x->w - 1) / 2 + 1;
+  Tensor* y = out ? out : new_tensor(x->n, Ho, Wo, x->c, "");
+  MDC_CHECK(y->h == Ho && y->w == Wo, "downsample: bad output size");
+  auto* op = new SubsampleOp();
+  op->x = full, op->y = y, op->off = 0;
+  push(op, key);
+  if (y->name.empty()) y->name = key, named[key] = y;
+  return y;
+}
+
+// ------------------------------------------------------------------------------------------------ UNet graph
+inline void Engine::build_unet() {
+  cur_ops = &unet_ops;
+  const int nb = cfg.unet_nblocks, L = cfg.unet_layers_per_block;
+  const int* boc = cfg.unet_block_ch;
+  const std::string U = "unet.";
+  unet_in = new_tensor(N, lh, lw, cfg.unet_in_ch, "unet.in");
+  // Plan of the up path's concat buffers (consumption order), so that skip producers can write into them directly.
+  struct CatPlan {
+    int rin, skipc;
+  };
+  std::vector<CatPlan> plan;
+  {
+    int cout = boc[nb - 1];
+    for (int i = 0; i < nb; ++i) {
+      int prev = cout;
+      cout = boc[nb - 1 - i];
+      int cin = boc[std::max(nb - 2 - i, 0)];
+      for (int j = 0; j < L + 1; ++j) plan.push_back({j == 0 ? prev : cout, j == L ? cin : cout});
+    }
+  }
+  const int n_skips = static_cast<int>(plan.size());
+  std::vector<Tensor*> cats(n_skips, nullptr), skip_views(n_skips, nullptr);
+  int skip_idx = 0;  // push order
+  auto skip_target = [&](int h, int w) -> Tensor* {
+    const int ci = n_skips - 1 - skip_idx;
+    const CatPlan& cp = plan[ci];
+    Tensor* cat = new_tensor(N, h, w, cp.rin + cp.skipc, "unet.cat" + std::to_string(ci));
+    cats[ci] = cat;
+    ++skip_idx;
+    skip_views[ci] = view(cat, cp.rin, cp.skipc, "");
+    return skip_views[ci];
+  };
+  Tensor* h = conv3x3(unet_in, boc[0], U + "conv_in", nullptr, skip_target(lh, lw));
+  named["unet.conv_in"] = h;
+  for (int i = 0; i < nb; ++i) {
+    const std::string B = U + "down_blocks." + std::to_string(i);
+    for (int j = 0; j < L; ++j) {
+      const bool attn = cfg.unet_down_attn[i] != 0;
+      Tensor* tgt = skip_target(h->h, h->w);
+      h = resnet(h, boc[i], B + ".resnets." + std::to_string(j), true, 1e-5f, attn ? nullptr : tgt);
+      if (attn) h = transformer(h, cfg.unet_heads[i], B + ".attentions." + std::to_string(j), tgt);
+    }
+    if (i != nb - 1) {
+      const int Ho = (h->h - 1) / 2 + 1, Wo = (h->w - 1) / 2 + 1;
+      h = downsample_conv(h, B + ".downsamplers.0", skip_target(Ho, Wo));
+    }
+  }
+  MDC_CHECK(skip_idx == n_skips, "skip bookkeeping mismatch");
+  const int cm = boc[nb - 1];
+  h = resnet(h, cm, U + "mid_block.resnets.0", true, 1e-5f);
+  h = transformer(h, cfg.unet_heads[nb - 1], U + "mid_block.attentions.0");
+  h = resnet(h, cm, U + "mid_block.resnets.1", true, 1e-5f, view(cats[0], 0, plan[0].rin, ""));
+  int ci = 0;
+  for (int i = 0; i < nb; ++i) {
+    const std::string B = U + "up_blocks." + std::to_string(i);
+    const int cout = boc[nb - 1 - i];
+    const bool attn = cfg.unet_down_attn[nb - 1 - i] != 0;
+    for (int j = 0; j < L + 1; ++j, ++ci) {
+      Tensor* cat = cats[ci];
+      {
+        auto* op = new ConcatOp();
+        op->a = h, op->b = skip_views[ci], op->cat = cat;  // the very Tensor objects the producers wrote
+        MDC_CHECK(h->d == cat->d && h->c == plan[ci].rin && h->ld == cat->ld, "concat %d: producer did not write in place", ci);
+        push(op, "cat" + std::to_string(ci));
+      }
+      const bool last_in_block = (j == L);
+      const bool has_up = last_in_block && (i != nb - 1);
+      Tensor* next_tgt = nullptr;
+      if (!has_up && ci + 1 < n_skips) next_tgt = view(cats[ci + 1], 0, plan[ci + 1].rin, "");
+      h = resnet(cat, cout, B + ".resnets." + std::to_string(j), true, 1e-5f, attn ? nullptr : next_tgt);
+      if (attn) h = transformer(h, cfg.unet_heads[nb - 1 - i], B + ".attentions." + std::to_string(j), next_tgt);
+      if (has_up) {
+        Tensor* nxt = cats[ci + 1];
+        h = upsample_conv(h, nxt->h, nxt->w, B + ".upsamplers.0", view(nxt, 0, plan[ci + 1].rin, ""));
+      }
+    }
+  }
+  h = group_norm(h, U + "conv_norm_out", 1e-5f, true);
+  unet_out = conv3x3(h, cfg.unet_out_ch, U + "conv_out");
+  named["unet.out"] = unet_out;
+  // time embedding MLP (evaluated for all steps in prepare())
+  te_l1w = slot(U + "time_embedding.linear_1.weight", W_LIN, boc[0] * 4, boc[0]);
+  te_l1b = slot(U + "time_embedding.linear_1.bias", W_VEC, boc[0] * 4, 0);
+  te_l2w = slot(U + "time_embedding.linear_2.weight", W_LIN, boc[0] * 4, boc[0] * 4);
+  te_l2b = slot(U + "time_embedding.linear_2.bias", W_VEC, boc[0] * 4, 0);
+}
+
+// ------------------------------------------------------------------------------------------------ VAE decoder graph
+inline void Engine::build_decoder() {
+  cur_ops = &dec_ops;
+  const int nb = cfg.vae_nblocks, L = cfg.vae_layers_per_block;
+  const int* boc = cfg.vae_block_ch;
+  const std::string V = "vae.";
+  dec_in = new_tensor(N, lh, lw, cfg.vae_latent_ch, "vae.in");
+  Tensor* h = linear(dec_in, cfg.vae_latent_ch, V + "post_quant_conv", true);
+  named["vae.post_quant_conv"] = h;
+  const int c0 = boc[nb - 1];
+  h = conv3x3(h, c0, V + "decoder.conv_in");
+  named["vae.decoder.conv_in"] = h;
+  h = resnet(h, c0, V + "decoder.mid_block.resnets.0", false, 1e-6f);
+  {  // single-head attention with bias and residual
+    const std::string A = V + "decoder.mid_block.attentions.0";
+    Tensor* gn = group_norm(h, A + ".group_norm", 1e-6f, false);
+    Tensor* qkv = new_tensor(N, h->h, h->w, 3 * c0, "");
+    bf16* w = arena.make<bf16>(3ull * c0 * c0 + 64);
+    bf16* wt = arena.make<bf16>(3ull * c0 * c0 + 64);
+    float* b = arena.make<float>(3ull * c0 + 16);
+    const char* nm[3] = {".to_q", ".to_k", ".to_v"};
+    for (int i = 0; i < 3; ++i) {
+      slot_lin_into(A + nm[i] + ".weight", c0, c0, w + 1ull * i * c0 * c0, c0, wt + i * c0, 3 * c0);
+      slot_vec_into(A + nm[i] + ".bias", c0, b + i * c0);
+    }
+    auto* op = new LinearOp();
+    op->E = this, op->x = gn, op->y = qkv, op->res = nullptr, op->w = w, op->wt = wt, op->ld_w = c0, op->ld_wt = 3 * c0;
+    op->bias = b;
+    Epilogue e;
+    e.out = qkv->d, e.ldc = qkv->ld, e.bias = b;
+    Operand Aop{gn->d, 0, gn->ld, 0, 0}, Bm{w, 0, c0, 0, 0};
+    op->pf = plan_gemm(static_cast<int>(gn->rows()), 3 * c0, c0, Aop, Bm, e);
+    push(op, A + ".to_qkv");
+    Tensor* ao = self_attention(qkv, 1, A + ".sdpa");
+    h = linear(ao, c0, A + ".to_out.0", true, h);
+    h->name = A, named[A] = h;
+  }
+  h = resnet(h, c0, V + "decoder.mid_block.resnets.1", false, 1e-6f);
+  for (int i = 0; i < nb; ++i) {
+    const std::string B = V + "decoder.up_blocks." + std::to_string(i);
+    const int cout = boc[nb - 1 - i];
+    for (int j = 0; j < L + 1; ++j) h = resnet(h, cout, B + ".resnets." + std::to_string(j), false, 1e-6f);
+    if (i != nb - 1) h = upsample_conv(h, h->h * 2, h->w * 2, B + ".upsamplers.0");
+  }
+  h = group_norm(h, V + "decoder.conv_norm_out", 1e-6f, true);
+  dec_out = conv3x3(h, 3, V + "decoder.conv_out");
+  named["vae.out"] = dec_out;
+  MDC_CHECK(dec_out->h == PPH && dec_out->w == PPW, "decoder output %dx%d != padded size %dx%d", dec_out->h, dec_out->w,
+            PPH, PPW);
+}
+
+inline void Engine::finalize_plans() {
+  gn_partial = arena.make<float>(gn_partial_floats + 64);
+  gn_gstats = arena.make<float>(2ull * 64 * MAXN + 64);
+  attn_S = arena.make<float>(attn_S_floats + 64);
+  temb_cur = arena.make<float>(temb_total + 64);
+  for (auto* ops : {&unet_ops, &dec_ops}) {
+    for (auto& op : *ops) {
+      if (auto* c = dynamic_cast<ConvOp*>(op.get())) {
+        uintptr_t tag = reinterpret_cast<uintptr_t>(c->bias);
+        if (tag & 1) {  // tagged time-embedding offset
+          c->bias = temb_cur + (tag - 1);
+          c->pf.p.bias = c->bias;
+          finish_plan(c->pf);
+        }
+      } else if (auto* a = dynamic_cast<SelfAttnOp*>(op.get())) {
+        a->p_s.p.out = attn_S;
+        finish_plan(a->p_s);
+      }
+    }
+    for (auto it = ops->rbegin(); it != ops->rend(); ++it) (*it)->plan_bwd();
+  }
+}
+
+inline Engine::Engine(const mdc_config& c) : cfg(c) {
+  N = c.n_batch, H = c.height, W = c.width, ph = c.proc_h, pw = c.proc_w;
+  PPH = ph + c.pad_h, PPW = pw + c.pad_w;
+  MDC_CHECK(N >= 1 && N <= MAXN, "n_batch %d out of range (1..%d)", N, MAXN);
+  MDC_CHECK(PPH % 8 == 0 && PPW % 8 == 0, "padded processing size %dx%d is not a multiple of 8", PPH, PPW);
+  MDC_CHECK(c.unet_in_ch == 8 && c.unet_out_ch == 4 && c.vae_latent_ch == 4, "unsupported channel configuration");
+  MDC_CHECK(c.unet_nblocks >= 2 && c.unet_nblocks <= 8 && c.vae_nblocks >= 2 && c.vae_nblocks <= 8, "bad block count");
+  MDC_CHECK(c.steps >= 1 && c.steps <= 1000, "bad step count %d", c.steps);
+  lh = PPH / 8, lw = PPW / 8;
+  int expect = 1;
+  for (int i = 1; i < c.vae_nblocks; ++i) expect *= 2;
+  MDC_CHECK(expect == 8, "VAE must upsample by 8 (got %d)", expect);
+  MDC_CUDA(cudaSetDevice(c.device));
+  gemm_set_smem_attr();
+  MDC_CUDA(cudaFuncSetAttribute(softmax_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  MDC_CUDA(cudaFuncSetAttribute(softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  build_unet();
+  build_decoder();
+  finalize_plans();
+  // step state
+  const size_t lat = 4ull * N * lh * lw;
+  x = arena.make<bf16>(lat), m1 = arena.make<bf16>(lat), m2 = arena.make<bf16>(lat), img_lat = arena.make<bf16>(lat);
+  x_adam_dbg = arena.make<bf16>(lat);
+  dx_direct = arena.make<float>(lat), gbuf = arena.make<float>(lat);
+  parts_per_img = std::max(1, std::min(64, (lh * lw + 255) / 256));
+  eps_part = arena.make<float>(1ull * N * parts_per_img), g_part = arena.make<float>(1ull * N * parts_per_img);
+  dmean = arena.make<float>(1ull * N * PPH * PPW);
+  pt_idx = arena.make<int>(1ull * N * H * W), pt_val = arena.make<float>(1ull * N * H * W);
+  pt_off = arena.make<int>(N + 1);
+  gminmax = arena.make<float>(2 * MAXN), depth_minmax = arena.make<float>(2 * MAXN);
+  cur = arena.make<StepCur>(1), accum = arena.make<StepAccum>(1), counter = arena.make<int>(1);
+  d_sqrt_a = arena.make<float>(c.steps), d_sqrt_1ma = arena.make<float>(c.steps);
+  d_sqrt_ap = arena.make<float>(c.steps), d_sqrt_1map = arena.make<float>(c.steps);
+  temb_table = arena.make<float>(1ull * c.steps * temb_total + 64);
+  MDC_CUDA(cudaDeviceSynchronize());
+}
+
+// ================================================================================================ runtime
+inline void Engine::set_weight(const std::string& key, const void* src, const long long* shape, int ndim, int dtype) {
+  auto it = wmap.find(key);
+  MDC_CHECK(it != wmap.end(), "unknown weight key '%s'", key.c_str());
+  MDC_CHECK(dtype == MDC_DTYPE_F32 || dtype == MDC_DTYPE_BF16, "weight dtype %d unsupported", dtype);
+  for (WeightSlot* s : it->second) {
+    long long numel = 1;
+    for (int i = 0; i < ndim; ++i) numel *= shape[i];
+    const bool f32 = dtype == MDC_DTYPE_F32;
+    if (s->kind == W_CONV3) {
+      MDC_CHECK(ndim == 4 && shape[0] == s->out && shape[1] == s->in && shape[2] == 3 && shape[3] == 3,
+                "weight '%s': expected [%d,%d,3,3]", key.c_str(), s->out, s->in);
+      const int inp = ((s->in + 63) / 64) * 64, outp = ((s->out + 63) / 64) * 64;
+      if (f32) {
+        pack_conv3x3_fwd_kernel<float><<<1184, 256, 0, stream>>>((const float*)src, s->w, s->out, s->in, inp);
+        pack_conv3x3_dgrad_kernel<float><<<1184, 256, 0, stream>>>((const float*)src, s->wt, s->out, s->in, outp);
+      } else {
+        pack_conv3x3_fwd_kernel<bf16><<<1184, 256, 0, stream>>>((const bf16*)src, s->w, s->out, s->in, inp);
+        pack_conv3x3_dgrad_kernel<bf16><<<1184, 256, 0, stream>>>((const bf16*)src, s->wt, s->out, s->in, outp);
+      }
+    } else if (s->kind == W_LIN) {
+      MDC_CHECK(numel == 1LL * s->out * s->in && shape[0] == s->out, "weight '%s': expected [%d,%d]", key.c_str(), s->out,
+                s->in);
+      if (f32) {
+        pack_matrix_kernel<float><<<1184, 256, 0, stream>>>((const float*)src, s->w, s->out, s->in, s->ld_w, 0);
+        pack_matrix_kernel<float><<<1184, 256, 0, stream>>>((const float*)src, s->wt, s->out, s->in, s->ld_wt, 1);
+      } else {
+        pack_matrix_kernel<bf16><<<1184, 256, 0, stream>>>((const bf16*)src, s->w, s->out, s->in, s->ld_w, 0);
+        pack_matrix_kernel<bf16><<<1184, 256, 0, stream>>>((const bf16*)src, s->wt, s->out, s->in, s->ld_wt, 1);
+      }
+    } else {
+      MDC_CHECK(numel == s->out, "weight '%s': expected %d elements, got %lld", key.c_str(), s->out, numel);
+      if (f32)
+        to_f32_kernel<float><<<32, 256, 0, stream>>>((const float*)src, s->vec, numel);
+      else  // bf16 parameters are used at bf16 precision, like the reference's bf16 modules
+        to_f32_kernel<bf16><<<32, 256, 0, stream>>>((const bf16*)src, s->vec, numel);
+    }
+    s->loaded = true;
+  }
+  MDC_CUDA(cudaGetLastError());
+}
+
+inline void Engine::prepare(const void* ctx_bf16, const float* alphas_cumprod, const int* timesteps, int n_steps) {
+  for (auto& kv : wmap)
+    for (WeightSlot* s : kv.second) MDC_CHECK(s->loaded, "weight '%s' has not been set", kv.first.c_str());
+  MDC_CHECK(n_steps == cfg.steps, "prepare: n_steps %d != configured steps %d", n_steps, cfg.steps);
+  // DDIM scalars (host, double -> float like torch's 0-dim fp32 tensors)
+  std::vector<float> sa(n_steps), sb(n_steps), sap(n_steps), sbp(n_steps);
+  const int stride = 1000 / n_steps;
+  for (int i = 0; i < n_steps; ++i) {
+    const int t = timesteps[i], tp = t - stride;
+    MDC_CHECK(t >= 0 && t < 1000, "timestep %d out of range", t);
+    const float a = alphas_cumprod[t], ap = tp >= 0 ? alphas_cumprod[tp] : alphas_cumprod[0];
+    sa[i] = sqrtf(a), sb[i] = sqrtf(1.f - a), sap[i] = sqrtf(ap), sbp[i] = sqrtf(1.f - ap);
+  }
+  MDC_CUDA(cudaMemcpy(d_sqrt_a, sa.data(), n_steps * 4, cudaMemcpyHostToDevice));
+  MDC_CUDA(cudaMemcpy(d_sqrt_1ma, sb.data(), n_steps * 4, cudaMemcpyHostToDevice));
+  MDC_CUDA(cudaMemcpy(d_sqrt_ap, sap.data(), n_steps * 4, cudaMemcpyHostToDevice));
+  MDC_CUDA(cudaMemcpy(d_sqrt_1map, sbp.data(), n_steps * 4, cudaMemcpyHostToDevice));
+  // time embedding for every step: sinusoid -> linear_1 -> SiLU -> linear_2, then per resnet time_emb_proj(SiLU(.)) + conv bias
+  const int c0 = cfg.unet_block_ch[0], tc = c0 * 4;
+  int* d_ts = nullptr;
+  float *emb = nullptr, *h1 = nullptr, *h2 = nullptr;
+  MDC_CUDA(cudaMalloc(&d_ts, n_steps * 4));
+  MDC_CUDA(cudaMalloc(&emb, 4ull * n_steps * c0));
+  MDC_CUDA(cudaMalloc(&h1, 4ull * n_steps * tc));
+  MDC_CUDA(cudaMalloc(&h2, 4ull * n_steps * tc));
+  MDC_CUDA(cudaMemcpy(d_ts, timesteps, n_steps * 4, cudaMemcpyHostToDevice));
+  timestep_embedding_kernel<<<(n_steps * c0 + 255) / 256, 256, 0, stream>>>(d_ts, n_steps, c0, emb);
+  auto lin = [&](const bf16* Wm, long long ldw, const float* b, const float* in, long long ldin, int In, int Out, int silu,
+                 float* out, long long ldout, int S) {
+    long long warps = 1LL * S * Out;
+    small_linear_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, stream>>>(Wm, ldw, b, in, ldin, S, In, Out,
+                                                                                        silu, out, ldout);
+  };
+  lin(te_l1w->w, te_l1w->ld_w, te_l1b->vec, emb, c0, c0, tc, 0, h1, tc, n_steps);
+  lin(te_l2w->w, te_l2w->ld_w, te_l2b->vec, h1, tc, tc, tc, 1, h2, tc, n_steps);
+  MDC_CUDA(cudaMemsetAsync(temb_table, 0, 4ull * n_steps * temb_total, stream));
+  for (auto& u : temb_uses) {
+    lin(u.proj_w->w, u.proj_w->ld_w, u.proj_b->vec, h2, tc, tc, u.cout, 1, temb_table + u.off, temb_total, n_steps);
+  }
+  // add the conv bias: table[s][off + c] += conv_b[c]   (small host loop over uses, one kernel each would be overkill)
+  MDC_CUDA(cudaStreamSynchronize(stream));
+  {
+    std::vector<float> tab(1ull * n_steps * temb_total), cb;
+    MDC_CUDA(cudaMemcpy(tab.data(), temb_table, tab.size() * 4, cudaMemcpyDeviceToHost));
+    for (auto& u : temb_uses) {
+      cb.resize(u.cout);
+      MDC_CUDA(cudaMemcpy(cb.data(), u.conv_b->vec, u.cout * 4, cudaMemcpyDeviceToHost));
+      for (int s = 0; s < n_steps; ++s)
+        for (int c = 0; c < u.cout; ++c) tab[1ull * s * temb_total + u.off + c] += cb[c];
+    }
+    MDC_CUDA(cudaMemcpy(temb_table, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+  }
+  // cross-attention K / V of the 2 empty-prompt tokens: [2, d] = ctx [2, cross] . W^T
+  {
+    float* ctxf = nullptr;
+    MDC_CUDA(cudaMalloc(&ctxf, 4ull * 2 * cfg.cross_dim));
+    to_f32_kernel<bf16><<<8, 256, 0, stream>>>(static_cast<const bf16*>(ctx_bf16), ctxf, 2LL * cfg.cross_dim);
+    for (auto& u : xuses) {
+      lin(u.wk->w, u.wk->ld_w, nullptr, ctxf, cfg.cross_dim, cfg.cross_dim, u.d, 0, u.kc, u.d, 2);
+      lin(u.wv->w, u.wv->ld_w, nullptr, ctxf, cfg.cross_dim, cfg.cross_dim, u.d, 0, u.vc, u.d, 2);
+    }
+    MDC_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(ctxf);
+  }
+  cudaFree(d_ts), cudaFree(emb), cudaFree(h1), cudaFree(h2);
+  tables.sqrt_a = d_sqrt_a, tables.sqrt_1ma = d_sqrt_1ma, tables.sqrt_ap = d_sqrt_ap, tables.sqrt_1map = d_sqrt_1map;
+  tables.temb_bias = temb_table, tables.temb_total = temb_total, tables.steps = n_steps;
+  MDC_CUDA(cudaGetLastError());
+  prepared = true;
+}
+
+inline void Engine::begin(const void* img_latents, const void* x0, const float* guide, const uint8_t* mask,
+                          const float* gmm, const float* dmm, float lrx, float lrs) {
+  MDC_CHECK(prepared, "mdc_begin called before mdc_prepare");
+  const size_t lat = 4ull * N * lh * lw;
+  MDC_CUDA(cudaMemcpyAsync(img_lat, img_latents, lat * 2, cudaMemcpyDeviceToDevice, stream));
+  MDC_CUDA(cudaMemcpyAsync(x, x0, lat * 2, cudaMemcpyDeviceToDevice, stream));
+  MDC_CUDA(cudaMemsetAsync(m1, 0, lat * 2, stream));
+  MDC_CUDA(cudaMemsetAsync(m2, 0, lat * 2, stream));
+  MDC_CUDA(cudaMemsetAsync(dmean, 0, 4ull * N * PPH * PPW, stream));
+  MDC_CUDA(cudaMemsetAsync(counter, 0, 4, stream));
+  StepAccum a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < MAXN; ++i) a.scale[i] = 1.f;
+  MDC_CUDA(cudaMemcpyAsync(accum, &a, sizeof(a), cudaMemcpyHostToDevice, stream));
+  MDC_CUDA(cudaMemcpyAsync(gminmax, gmm, 8ull * N, cudaMemcpyHostToDevice, stream));
+  MDC_CUDA(cudaMemcpyAsync(depth_minmax, dmm, 8ull * N, cudaMemcpyHostToDevice, stream));
+  // valid-point lists (host does the counting once per call; not on the per-step path)
+  std::vector<uint8_t> hm(1ull * N * H * W);
+  MDC_CUDA(cudaMemcpyAsync(hm.data(), mask, hm.size(), cudaMemcpyDeviceToHost, stream));
+  MDC_CUDA(cudaStreamSynchronize(stream));
+  std::vector<int> off(N + 1, 0);
+  for (int n = 0; n < N; ++n) {
+    int c = 0;
+    const uint8_t* p = hm.data() + 1ull * n * H * W;
+    for (int i = 0; i < H * W; ++i) c += p[i] != 0;
+    MDC_CHECK(c > 0, "sample %d has no valid sparse-depth point (empty mask)", n);
+    off[n + 1] = off[n] + c;
+  }
+  MDC_CUDA(cudaMemcpyAsync(pt_off, off.data(), (N + 1) * 4, cudaMemcpyHostToDevice, stream));
+  compact_points_kernel<<<N, 1024, 0, stream>>>(guide, mask, H * W, pt_off, pt_idx, pt_val);
+  MDC_CUDA(cudaGetLastError());
+  MDC_CUDA(cudaStreamSynchronize(stream));
+  lr_x = lrx, lr_s = lrs;
+  steps_done = 0;
+  begun = true;
+}
+
+inline void Engine::run_ops(std::vector<std::unique_ptr<Op>>& ops, bool backward) {
+  if (!backward)
+    for (auto& op : ops) op->fwd(stream);
+  else
+    for (auto it = ops.rbegin(); it != ops.rend(); ++it) (*it)->bwd(stream);
+}
+
+inline void Engine::step() {
+  MDC_CHECK(begun, "mdc_step called before mdc_begin");
+  MDC_CHECK(steps_done < cfg.steps, "all %d steps already done", cfg.steps);
+  const int hw = lh * lw, lat_pix = N * hw;
+  const int pgrid = N * parts_per_img;
+  TailGeom g{N, H, W, ph, pw, PPH, PPW, dec_out->ld};
+  begin_step_kernel<<<1, 1024, 0, stream>>>(tables, counter, cur, temb_cur, lr_x, lr_s);
+  unet_input_kernel<<<(lat_pix + 255) / 256, 256, 0, stream>>>(img_lat, x, N, hw, unet_in->d);
+  run_ops(unet_ops, false);
+  x0_kernel<<<pgrid, 256, 0, stream>>>(unet_out->d, x, cur, N, hw, cfg.vae_scaling, dec_in->d, eps_part);
+  run_ops(dec_ops, false);
+  loss_points_kernel<<<N, 512, 0, stream>>>(dec_out->d, g, pt_idx, pt_val, pt_off, gminmax, accum, dmean);
+  const long long npix = 1LL * N * PPH * PPW;
+  dec_grad_kernel<<<static_cast<int>((npix + 255) / 256), 256, 0, stream>>>(dmean, npix, dec_out->g);
+  run_ops(dec_ops, true);
+  dx0_kernel<<<(lat_pix + 255) / 256, 256, 0, stream>>>(dec_in->g, cur, N, hw, cfg.vae_scaling, unet_out->g, dx_direct);
+  run_ops(unet_ops, true);
+  grad_total_kernel<<<pgrid, 256, 0, stream>>>(dx_direct, unet_in->g, N, hw, gbuf, g_part);
+  adam_ddim_kernel<<<pgrid, 256, 0, stream>>>(gbuf, eps_part, g_part, parts_per_img, unet_out->d, cur, N, hw, x, m1, m2,
+                                              accum, counter, x_adam_dbg);
+  ++steps_done;
+}
+
+inline void Engine::decode_final(float* dense_out) {
+  MDC_CHECK(begun, "mdc_decode_final called before mdc_begin");
+  const int hw = lh * lw;
+  // z = x / scaling as NHWC (reuse x0_kernel algebra with sqrt_a = 1, sqrt_1ma = 0 via a dedicated tiny path)
+  StepCur one;
+  memset(&one, 0, sizeof(one));
+  one.sqrt_a = 1.f, one.sqrt_1ma = 0.f;
+  StepCur* tmp = nullptr;
+  MDC_CUDA(cudaMalloc(&tmp, sizeof(StepCur)));
+  MDC_CUDA(cudaMemcpyAsync(tmp, &one, sizeof(one), cudaMemcpyHostToDevice, stream));
+  MDC_CUDA(cudaMemsetAsync(unet_out->d, 0, static_cast<size_t>(unet_out->rows()) * unet_out->ld * 2, stream));
+  float* scratch = nullptr;
+  MDC_CUDA(cudaMalloc(&scratch, 4ull * N * parts_per_img));
+  x0_kernel<<<N * parts_per_img, 256, 0, stream>>>(unet_out->d, x, tmp, N, hw, cfg.vae_scaling, dec_in->d, scratch);
+  run_ops(dec_ops, false);
+  TailGeom g{N, H, W, ph, pw, PPH, PPW, dec_out->ld};
+  const long long tot = 1LL * N * H * W;
+  dense_out_kernel<<<static_cast<int>((tot + 255) / 256), 256, 0, stream>>>(dec_out->d, g, gminmax, depth_minmax, accum,
+                                                                           dense_out);
+  MDC_CUDA(cudaGetLastError());
+  MDC_CUDA(cudaStreamSynchronize(stream));
+  cudaFree(tmp), cudaFree(scratch);
+}
+
+// NHWC bf16 -> NCHW fp32 copy of a named tensor (which = 0 data, 1 gradient); debug / tests only.
+__global__ void nhwc_to_nchw_f32_kernel(const bf16* __restrict__ src, long long ld, int N, int HW, int C,
+                                        float* __restrict__ out) {
+  long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+  if (i >= 1LL * N * HW * C) return;
+  int p = i % HW, c = (i / HW) % C, n = i / (1LL * HW * C);
+  out[i] = __bfloat162float(src[(1LL * n * HW + p) * ld + c]);
+}
+inline void Engine::read_tensor(const std::string& name, int which, float* out_nchw) {
+  auto it = named.find(name);
+  MDC_CHECK(it != named.end(), "unknown tensor '%s'", name.c_str());
+  Tensor* t = it->second;
+  const bf16* src = which ? t->g : t->d;
+  MDC_CHECK(src != nullptr, "tensor '%s' has no gradient buffer", name.c_str());
+  long long tot = t->rows() * t->c;
+  nhwc_to_nchw_f32_kernel<<<static_cast<int>((tot + 255) / 256), 256, 0, stream>>>(src, t->ld, t->n, t->h * t->w, t->c,
+                                                                                  out_nchw);
+  MDC_CUDA(cudaGetLastError());
+  MDC_CUDA(cudaStreamSynchronize(stream));
+}
+
+}  // namespace mdc

@@ -1,0 +1,633 @@
+// Bandwidth-bound kernels of the hot path (everything that is not a dense contraction):
+// GroupNorm(+SiLU) fwd/bwd, LayerNorm fwd/bwd, GEGLU fwd/bwd, softmax fwd/bwd, the 2-token
+// cross-attention, nearest resampling and its adjoint, channel-slice add/copy.
+// Activations are NHWC bf16 ("rows" = n*h*w pixels/tokens, "ld" = elements between rows).
+// All kernels use 16-byte vector loads/stores, fp32 math, warp-shuffle reductions, and an
+// `acc` flag (accumulate into the destination) so the backward tape needs no separate add kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mdc {
+
+typedef __nv_bfloat16 bf16;
+
+struct alignas(16) BF8 {
+  __nv_bfloat162 v[4];
+};
+__device__ __forceinline__ void bf8_to_f(const BF8& b, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(b.v[i]);
+    f[2 * i] = t.x, f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ BF8 f_to_bf8(const float (&f)[8]) {
+  BF8 b;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) b.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return b;
+}
+__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16(x)); }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Block-wide sum for blockDim.x <= 1024; `sh` must hold 32 floats. Result valid in all threads.
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float r = (lane < nw) ? sh[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float r = (lane < nw) ? sh[lane] : -INFINITY;
+  r = warp_max(r);
+  return r;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
+__device__ __forceinline__ float silu_grad(float x) {
+  float s = sigmoidf_(x);
+  return s * (1.f + x * (1.f - s));
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
+// =========================================================================== GroupNorm
+// Thread layout shared by all GroupNorm kernels: blockDim = CV * R (CV = C/8 channel vectors per pixel),
+// thread -> (cv = tid % CV, r = tid / CV); each block walks `pix_per_block` pixels of one image.  A thread's
+// channel vector, hence the groups of its 4 channel pairs, is fixed, so statistics accumulate in registers.
+struct GNShape {
+  int N, HW, C, G;
+  long long ld;        // pixel stride of x / y (elements)
+  int pix_per_block;   // pixels handled by one block
+  int blocks_per_img;  // gridDim.x = N * blocks_per_img
+};
+
+// pass 1 of forward: per-block partial (sum, sumsq) per group -> partial[(n*bpi + b)*G*2 + g*2 + {0,1}]
+__global__ void gn_stats_kernel(const bf16* __restrict__ x, GNShape s, float* __restrict__ partial) {
+  extern __shared__ float sh[];  // 2*G
+  const int CV = s.C >> 3, cpg = s.C / s.G;
+  const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
+  const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
+  for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  float sum[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
+  const int p0 = b * s.pix_per_block, p1 = min(s.HW, p0 + s.pix_per_block);
+  const bf16* base = x + (1LL * n * s.HW) * s.ld + cv * 8;
+  for (int p = p0 + r; p < p1; p += R) {
+    BF8 v = *reinterpret_cast<const BF8*>(base + 1LL * p * s.ld);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __bfloat1622float2(v.v[i]);
+      sum[i] += t.x + t.y;
+      sq[i] += t.x * t.x + t.y * t.y;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int g = (cv * 8 + 2 * i) / cpg;
+    atomicAdd(&sh[2 * g], sum[i]);
+    atomicAdd(&sh[2 * g + 1], sq[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) partial[1LL * blockIdx.x * 2 * s.G + i] = sh[i];
+}
+
+// Reduce the per-block partials in a fixed order (deterministic), in double.  mode 0: (sum, sumsq) -> (mean, rstd);
+// mode 1: plain sums scaled by 1/m (used by the backward pass).
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int N, int G, int bpi, double m, float eps,
+                                   int mode, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * G) return;
+  int n = i / G, g = i % G;
+  double a = 0, b = 0;
+  for (int k = 0; k < bpi; ++k) {
+    const float* p = partial + (1LL * (n * bpi + k) * G + g) * 2;
+    a += p[0], b += p[1];
+  }
+  if (mode == 0) {
+    double mean = a / m, var = b / m - mean * mean;
+    if (var < 0) var = 0;
+    out[2 * i] = static_cast<float>(mean);
+    out[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + eps));
+  } else {
+    out[2 * i] = static_cast<float>(a / m);
+    out[2 * i + 1] = static_cast<float>(b / m);
+  }
+}
+
+// pass 2 of forward: y = act((x - mean) * rstd * gamma + beta)
+__global__ void gn_apply_kernel(const bf16* __restrict__ x, GNShape s, const float* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                                bf16* __restrict__ y, long long ldy) {
+  const int CV = s.C >> 3, cpg = s.C / s.G;
+  const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
+  const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
+  float sc[8], sf[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int c = cv * 8 + i, g = c / cpg;
+    float mean = stats[2 * (n * s.G + g)], rstd = stats[2 * (n * s.G + g) + 1];
+    sc[i] = rstd * gamma[c];
+    sf[i] = beta[c] - mean * sc[i];
+  }
+  const int p0 = b * s.pix_per_block, p1 = min(s.HW, p0 + s.pix_per_block);
+  const bf16* xb = x + (1LL * n * s.HW) * s.ld + cv * 8;
+  bf16* yb = y + (1LL * n * s.HW) * ldy + cv * 8;
+  for (int p = p0 + r; p < p1; p += R) {
+    BF8 v = *reinterpret_cast<const BF8*>(xb + 1LL * p * s.ld);
+    float f[8];
+    bf8_to_f(v, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float h = f[i] * sc[i] + sf[i];
+      f[i] = silu ? siluf_(bf16r(h)) : h;
+    }
+    *reinterpret_cast<BF8*>(yb + 1LL * p * ldy) = f_to_bf8(f);
+  }
+}
+
+// backward pass 1: per-block partial (sum dxhat, sum dxhat*xhat) per group, dxhat = dy * act'(h) * gamma
+__global__ void gn_bwd_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, long long lddy, GNShape s,
+                                    const float* __restrict__ stats, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, int silu, float* __restrict__ partial) {
+  extern __shared__ float sh[];
+  const int CV = s.C >> 3, cpg = s.C / s.G;
+  const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
+  const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
+  for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  float mean[8], rstd[8], ga[8], be[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int c = cv * 8 + i, g = c / cpg;
+    mean[i] = stats[2 * (n * s.G + g)], rstd[i] = stats[2 * (n * s.G + g) + 1];
+    ga[i] = gamma[c], be[i] = beta[c];
+  }
+  float sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
+  const int p0 = b * s.pix_per_block, p1 = min(s.HW, p0 + s.pix_per_block);
+  const bf16* xb = x + (1LL * n * s.HW) * s.ld + cv * 8;
+  const bf16* db = dy + (1LL * n * s.HW) * lddy + cv * 8;
+  for (int p = p0 + r; p < p1; p += R) {
+    float fx[8], fd[8];
+    bf8_to_f(*reinterpret_cast<const BF8*>(xb + 1LL * p * s.ld), fx);
+    bf8_to_f(*reinterpret_cast<const BF8*>(db + 1LL * p * lddy), fd);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float xh = (fx[i] - mean[i]) * rstd[i];
+      float d = fd[i];
+      if (silu) d *= silu_grad(bf16r(xh * ga[i] + be[i]));
+      d *= ga[i];
+      sa[i >> 1] += d;
+      sb[i >> 1] += d * xh;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int g = (cv * 8 + 2 * i) / cpg;
+    atomicAdd(&sh[2 * g], sa[i]);
+    atomicAdd(&sh[2 * g + 1], sb[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) partial[1LL * blockIdx.x * 2 * s.G + i] = sh[i];
+}
+
+// backward pass 2: dx (+)= rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat*xhat))
+__global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, long long lddy, GNShape s,
+                                    const float* __restrict__ stats, const float* __restrict__ gstats,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                                    bf16* __restrict__ dx, long long lddx, int acc) {
+  const int CV = s.C >> 3, cpg = s.C / s.G;
+  const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
+  const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
+  float mean[8], rstd[8], ga[8], be[8], m1[8], m2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int c = cv * 8 + i, g = c / cpg;
+    mean[i] = stats[2 * (n * s.G + g)], rstd[i] = stats[2 * (n * s.G + g) + 1];
+    m1[i] = gstats[2 * (n * s.G + g)], m2[i] = gstats[2 * (n * s.G + g) + 1];
+    ga[i] = gamma[c], be[i] = beta[c];
+  }
+  const int p0 = b * s.pix_per_block, p1 = min(s.HW, p0 + s.pix_per_block);
+  const bf16* xb = x + (1LL * n * s.HW) * s.ld + cv * 8;
+  const bf16* db = dy + (1LL * n * s.HW) * lddy + cv * 8;
+  bf16* ob = dx + (1LL * n * s.HW) * lddx + cv * 8;
+  for (int p = p0 + r; p < p1; p += R) {
+    float fx[8], fd[8], o[8];
+    bf8_to_f(*reinterpret_cast<const BF8*>(xb + 1LL * p * s.ld), fx);
+    bf8_to_f(*reinterpret_cast<const BF8*>(db + 1LL * p * lddy), fd);
+    if (acc) bf8_to_f(*reinterpret_cast<const BF8*>(ob + 1LL * p * lddx), o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float xh = (fx[i] - mean[i]) * rstd[i];
+      float d = fd[i];
+      if (silu) d *= silu_grad(bf16r(xh * ga[i] + be[i]));
+      d *= ga[i];
+      float g = rstd[i] * (d - m1[i] - xh * m2[i]);
+      o[i] = acc ? o[i] + g : g;
+    }
+    *reinterpret_cast<BF8*>(ob + 1LL * p * lddx) = f_to_bf8(o);
+  }
+}
+
+// =========================================================================== LayerNorm (one warp per row)
+constexpr int LN_MAXV = 5;  // supports d <= 32*8*5 = 1280
+
+__global__ void ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, int rows, int d, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float eps, bf16* __restrict__ y, long long ldy,
+                              float* __restrict__ stats) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nv = d >> 3;
+  float f[LN_MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k) {
+    int v = lane + 32 * k;
+    if (v < nv) {
+      bf8_to_f(*reinterpret_cast<const BF8*>(x + row * ldx + v * 8), f[k]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += f[k][i];
+    }
+  }
+  const float mean = warp_sum(s) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k) {
+    int v = lane + 32 * k;
+    if (v < nv) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float t = f[k][i] - mean;
+        q += t * t;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / d + eps);
+  if (lane == 0) stats[2 * row] = mean, stats[2 * row + 1] = rstd;
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k) {
+    int v = lane + 32 * k;
+    if (v < nv) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (f[k][i] - mean) * rstd * gamma[v * 8 + i] + beta[v * 8 + i];
+      *reinterpret_cast<BF8*>(y + row * ldy + v * 8) = f_to_bf8(o);
+    }
+  }
+}
+
+__global__ void ln_bwd_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ dy, long long lddy,
+                              int rows, int d, const float* __restrict__ gamma, const float* __restrict__ stats,
+                              bf16* __restrict__ dx, long long lddx, int acc) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nv = d >> 3;
+  const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+  float xh[LN_MAXV][8], dh[LN_MAXV][8];
+  float a = 0.f, b = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k) {
+    int v = lane + 32 * k;
+    if (v < nv) {
+      float fx[8], fd[8];
+      bf8_to_f(*reinterpret_cast<const BF8*>(x + row * ldx + v * 8), fx);
+      bf8_to_f(*reinterpret_cast<const BF8*>(dy + row * lddy + v * 8), fd);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        xh[k][i] = (fx[i] - mean) * rstd;
+        dh[k][i] = fd[i] * gamma[v * 8 + i];
+        a += dh[k][i];
+        b += dh[k][i] * xh[k][i];
+      }
+    }
+  }
+  a = warp_sum(a) / d;
+  b = warp_sum(b) / d;
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k) {
+    int v = lane + 32 * k;
+    if (v < nv) {
+      float o[8];
+      if (acc) bf8_to_f(*reinterpret_cast<const BF8*>(dx + row * lddx + v * 8), o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float g = rstd * (dh[k][i] - a - xh[k][i] * b);
+        o[i] = acc ? o[i] + g : g;
+      }
+      *reinterpret_cast<BF8*>(dx + row * lddx + v * 8) = f_to_bf8(o);
+    }
+  }
+}
+
+// =========================================================================== GEGLU
+// x [rows, 2F] -> y [rows, F] = x[:, :F] * gelu(x[:, F:])
+__global__ void geglu_fwd_kernel(const bf16* __restrict__ x, long long ldx, long long rows, int F, bf16* __restrict__ y,
+                                 long long ldy) {
+  const int fv = F >> 3;
+  const long long total = rows * fv;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    long long r = i / fv;
+    int v = i % fv;
+    float a[8], g[8], o[8];
+    bf8_to_f(*reinterpret_cast<const BF8*>(x + r * ldx + v * 8), a);
+    bf8_to_f(*reinterpret_cast<const BF8*>(x + r * ldx + F + v * 8), g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = a[k] * bf16r(gelu_erf(g[k]));
+    *reinterpret_cast<BF8*>(y + r * ldy + v * 8) = f_to_bf8(o);
+  }
+}
+__global__ void geglu_bwd_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ dy, long long lddy,
+                                 long long rows, int F, bf16* __restrict__ dx, long long lddx, int acc) {
+  const int fv = F >> 3;
+  const long long total = rows * fv;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    long long r = i / fv;
+    int v = i % fv;
+    float a[8], g[8], d[8], oa[8], og[8];
+    bf8_to_f(*reinterpret_cast<const BF8*>(x + r * ldx + v * 8), a);
+    bf8_to_f(*reinterpret_cast<const BF8*>(x + r * ldx + F + v * 8), g);
+    bf8_to_f(*reinterpret_cast<const BF8*>(dy + r * lddy + v * 8), d);
+    if (acc) {
+      bf8_to_f(*reinterpret_cast<const BF8*>(dx + r * lddx + v * 8), oa);
+      bf8_to_f(*reinterpret_cast<const BF8*>(dx + r * lddx + F + v * 8), og);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float ga = d[k] * bf16r(gelu_erf(g[k]));
+      float gg = d[k] * a[k] * gelu_erf_grad(g[k]);
+      oa[k] = acc ? oa[k] + ga : ga;
+      og[k] = acc ? og[k] + gg : gg;
+    }
+    *reinterpret_cast<BF8*>(dx + r * lddx + v * 8) = f_to_bf8(oa);
+    *reinterpret_cast<BF8*>(dx + r * lddx + F + v * 8) = f_to_bf8(og);
+  }
+}
+
+// =========================================================================== softmax over rows of fp32 scores
+// S [rows, ld] fp32 (already scaled), T valid columns -> P [rows, ld] bf16.  One block per row, the row is
+// cached in shared memory.  ld is a multiple of 8 so rows are 16-byte aligned; T need not be.
+__device__ __forceinline__ void st_bf16x4(bf16* p, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&lo), o.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = o;
+}
+__device__ __forceinline__ float4 ld_bf16x4(const bf16* p) {
+  uint2 pr = *reinterpret_cast<const uint2*>(p);
+  float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&pr.x));
+  float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&pr.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__global__ void softmax_fwd_kernel(const float* __restrict__ S, bf16* __restrict__ P, int T, long long ld) {
+  extern __shared__ float row[];  // T4 floats + 32
+  const int T4 = T & ~3;
+  float* red = row + ((T + 3) & ~3);
+  const float* s = S + 1LL * blockIdx.x * ld;
+  bf16* p = P + 1LL * blockIdx.x * ld;
+  float m = -INFINITY;
+  for (int i = threadIdx.x * 4; i < T4; i += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<const float4*>(s + i);
+    *reinterpret_cast<float4*>(row + i) = v;
+    m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+  for (int i = T4 + threadIdx.x; i < T; i += blockDim.x) {
+    row[i] = s[i];
+    m = fmaxf(m, row[i]);
+  }
+  m = block_max(m, red);
+  float sum = 0.f;
+  for (int i = threadIdx.x * 4; i < T4; i += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<float4*>(row + i);
+    v.x = __expf(v.x - m), v.y = __expf(v.y - m), v.z = __expf(v.z - m), v.w = __expf(v.w - m);
+    *reinterpret_cast<float4*>(row + i) = v;
+    sum += v.x + v.y + v.z + v.w;
+  }
+  for (int i = T4 + threadIdx.x; i < T; i += blockDim.x) {
+    row[i] = __expf(row[i] - m);
+    sum += row[i];
+  }
+  sum = block_sum(sum, red);
+  const float inv = 1.f / sum;
+  for (int i = threadIdx.x * 4; i < T4; i += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<float4*>(row + i);
+    st_bf16x4(p + i, v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+  }
+  for (int i = T4 + threadIdx.x; i < T; i += blockDim.x) p[i] = __float2bfloat16(row[i] * inv);
+}
+// dS = P * (dP - sum_j P dP) * scale, written in place over P (bf16).
+__global__ void softmax_bwd_kernel(const float* __restrict__ dP, bf16* __restrict__ P, int T, long long ld,
+                                   float scale) {
+  extern __shared__ float row[];
+  const int T4 = T & ~3;
+  float* red = row + ((T + 3) & ~3);
+  const float* d = dP + 1LL * blockIdx.x * ld;
+  bf16* p = P + 1LL * blockIdx.x * ld;
+  float dot = 0.f;
+  for (int i = threadIdx.x * 4; i < T4; i += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<const float4*>(d + i);
+    float4 a = ld_bf16x4(p + i);
+    *reinterpret_cast<float4*>(row + i) = v;
+    dot += a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
+  }
+  for (int i = T4 + threadIdx.x; i < T; i += blockDim.x) {
+    row[i] = d[i];
+    dot += __bfloat162float(p[i]) * row[i];
+  }
+  dot = block_sum(dot, red);
+  for (int i = threadIdx.x * 4; i < T4; i += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<float4*>(row + i);
+    float4 a = ld_bf16x4(p + i);
+    st_bf16x4(p + i, a.x * (v.x - dot) * scale, a.y * (v.y - dot) * scale, a.z * (v.z - dot) * scale,
+              a.w * (v.w - dot) * scale);
+  }
+  for (int i = T4 + threadIdx.x; i < T; i += blockDim.x)
+    p[i] = __float2bfloat16(__bfloat162float(p[i]) * (row[i] - dot) * scale);
+}
+
+// =========================================================================== cross-attention with 2 key tokens
+// q [rows, d] (heads x 64), kc/vc [2, d] fp32 (step-invariant).  One warp per (row, head); lane owns 2 channels.
+__global__ void xattn2_fwd_kernel(const bf16* __restrict__ q, long long ldq, long long rows, int heads,
+                                  const float* __restrict__ kc, const float* __restrict__ vc, float scale,
+                                  bf16* __restrict__ o, long long ldo) {
+  const long long w = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= rows * heads) return;
+  const long long r = w / heads;
+  const int h = w % heads, d = heads * 64, c = h * 64 + lane * 2;
+  float2 qv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q + r * ldq + c));
+  float s0 = qv.x * kc[c] + qv.y * kc[c + 1], s1 = qv.x * kc[d + c] + qv.y * kc[d + c + 1];
+  s0 = warp_sum(s0) * scale, s1 = warp_sum(s1) * scale;
+  float m = fmaxf(s0, s1), e0 = __expf(s0 - m), e1 = __expf(s1 - m), inv = 1.f / (e0 + e1);
+  float p0 = bf16r(e0 * inv), p1 = bf16r(e1 * inv);
+  *reinterpret_cast<__nv_bfloat162*>(o + r * ldo + c) =
+      __floats2bfloat162_rn(p0 * vc[c] + p1 * vc[d + c], p0 * vc[c + 1] + p1 * vc[d + c + 1]);
+}
+__global__ void xattn2_bwd_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ dout,
+                                  long long lddo, long long rows, int heads, const float* __restrict__ kc,
+                                  const float* __restrict__ vc, float scale, bf16* __restrict__ dq, long long lddq,
+                                  int acc) {
+  const long long w = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= rows * heads) return;
+  const long long r = w / heads;
+  const int h = w % heads, d = heads * 64, c = h * 64 + lane * 2;
+  float2 qv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q + r * ldq + c));
+  float2 gv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dout + r * lddo + c));
+  float s0 = qv.x * kc[c] + qv.y * kc[c + 1], s1 = qv.x * kc[d + c] + qv.y * kc[d + c + 1];
+  float dp0 = gv.x * vc[c] + gv.y * vc[c + 1], dp1 = gv.x * vc[d + c] + gv.y * vc[d + c + 1];
+  s0 = warp_sum(s0) * scale, s1 = warp_sum(s1) * scale;
+  dp0 = warp_sum(dp0), dp1 = warp_sum(dp1);
+  float m = fmaxf(s0, s1), e0 = __expf(s0 - m), e1 = __expf(s1 - m), inv = 1.f / (e0 + e1);
+  float p0 = e0 * inv, p1 = e1 * inv, dot = p0 * dp0 + p1 * dp1;
+  float ds0 = p0 * (dp0 - dot) * scale, ds1 = p1 * (dp1 - dot) * scale;
+  float gx = ds0 * kc[c] + ds1 * kc[d + c], gy = ds0 * kc[c + 1] + ds1 * kc[d + c + 1];
+  __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(dq + r * lddq + c);
+  if (acc) {
+    float2 old = __bfloat1622float2(*dst);
+    gx += old.x, gy += old.y;
+  }
+  *dst = __floats2bfloat162_rn(gx, gy);
+}
+
+// =========================================================================== resampling
+__device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
+  return min(static_cast<int>(floorf(dst * scale)), in_size - 1);
+}
+// nearest upsample [N, h, w, C] -> [N, H, W, C] (torch F.interpolate(mode="nearest") index rule)
+__global__ void upsample_nearest_fwd_kernel(const bf16* __restrict__ x, long long ldx, int N, int h, int w, int C,
+                                            bf16* __restrict__ y, long long ldy, int H, int W) {
+  const int cv = C >> 3;
+  const long long total = 1LL * N * H * W * cv;
+  const float sh = static_cast<float>(h) / H, sw = static_cast<float>(w) / W;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    int v = i % cv;
+    long long p = i / cv;
+    int X = p % W, Y = (p / W) % H, n = p / (1LL * W * H);
+    int sy = nearest_src(Y, sh, h), sx = nearest_src(X, sw, w);
+    *reinterpret_cast<BF8*>(y + p * ldy + v * 8) =
+        *reinterpret_cast<const BF8*>(x + ((1LL * n * h + sy) * w + sx) * ldx + v * 8);
+  }
+}
+// adjoint: dx[n, sy, sx] (+)= sum of dy over the destination pixels that read (sy, sx)
+__global__ void upsample_nearest_bwd_kernel(const bf16* __restrict__ dy, long long lddy, int N, int h, int w, int C,
+                                            bf16* __restrict__ dx, long long lddx, int H, int W, int acc) {
+  const int cv = C >> 3;
+  const long long total = 1LL * N * h * w * cv;
+  const float sh = static_cast<float>(h) / H, sw = static_cast<float>(w) / W;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    int v = i % cv;
+    long long p = i / cv;
+    int sx = p % w, sy = (p / w) % h, n = p / (1LL * w * h);
+    float o[8];
+    if (acc)
+      bf8_to_f(*reinterpret_cast<const BF8*>(dx + p * lddx + v * 8), o);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = 0.f;
+    }
+    int y0 = max(0, static_cast<int>(sy / sh) - 2), y1 = min(H - 1, static_cast<int>((sy + 1) / sh) + 2);
+    int x0 = max(0, static_cast<int>(sx / sw) - 2), x1 = min(W - 1, static_cast<int>((sx + 1) / sw) + 2);
+    for (int Y = y0; Y <= y1; ++Y) {
+      if (nearest_src(Y, sh, h) != sy) continue;
+      for (int X = x0; X <= x1; ++X) {
+        if (nearest_src(X, sw, w) != sx) continue;
+        float f[8];
+        bf8_to_f(*reinterpret_cast<const BF8*>(dy + ((1LL * n * H + Y) * W + X) * lddy + v * 8), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += f[k];
+      }
+    }
+    *reinterpret_cast<BF8*>(dx + p * lddx + v * 8) = f_to_bf8(o);
+  }
+}
+// y[n, oy, ox] = x[n, 2*oy + off, 2*ox + off]   (stride-2 conv = stride-1 conv + this subsample)
+__global__ void subsample2_fwd_kernel(const bf16* __restrict__ x, long long ldx, int N, int H, int W, int C, int off,
+                                      bf16* __restrict__ y, long long ldy, int Ho, int Wo) {
+  const int cv = C >> 3;
+  const long long total = 1LL * N * Ho * Wo * cv;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    int v = i % cv;
+    long long p = i / cv;
+    int ox = p % Wo, oy = (p / Wo) % Ho, n = p / (1LL * Wo * Ho);
+    *reinterpret_cast<BF8*>(y + p * ldy + v * 8) =
+        *reinterpret_cast<const BF8*>(x + ((1LL * n * H + 2 * oy + off) * W + 2 * ox + off) * ldx + v * 8);
+  }
+}
+// adjoint: zero-insert
+__global__ void subsample2_bwd_kernel(const bf16* __restrict__ dy, long long lddy, int N, int H, int W, int C, int off,
+                                      bf16* __restrict__ dx, long long lddx, int Ho, int Wo, int acc) {
+  const int cv = C >> 3;
+  const long long total = 1LL * N * H * W * cv;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    int v = i % cv;
+    long long p = i / cv;
+    int X = p % W, Y = (p / W) % H, n = p / (1LL * W * H);
+    float o[8];
+    if (acc)
+      bf8_to_f(*reinterpret_cast<const BF8*>(dx + p * lddx + v * 8), o);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = 0.f;
+    }
+    int yy = Y - off, xx = X - off;
+    if (yy >= 0 && xx >= 0 && !(yy & 1) && !(xx & 1) && (yy >> 1) < Ho && (xx >> 1) < Wo) {
+      float f[8];
+      bf8_to_f(*reinterpret_cast<const BF8*>(dy + ((1LL * n * Ho + (yy >> 1)) * Wo + (xx >> 1)) * lddy + v * 8), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] += f[k];
+    }
+    *reinterpret_cast<BF8*>(dx + p * lddx + v * 8) = f_to_bf8(o);
+  }
+}
+
+// dst[rows, C] (+)= src[rows, C]  (channel-slice copy/accumulate with independent row strides)
+__global__ void add_rows_kernel(const bf16* __restrict__ src, long long lds, bf16* __restrict__ dst, long long ldd,
+                                long long rows, int C, int acc) {
+  const int cv = C >> 3;
+  const long long total = rows * cv;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    long long r = i / cv;
+    int v = i % cv;
+    BF8 s = *reinterpret_cast<const BF8*>(src + r * lds + v * 8);
+    if (acc) {
+      float a[8], b[8];
+      bf8_to_f(s, a);
+      bf8_to_f(*reinterpret_cast<const BF8*>(dst + r * ldd + v * 8), b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] += b[k];
+      s = f_to_bf8(a);
+    }
+    *reinterpret_cast<BF8*>(dst + r * ldd + v * 8) = s;
+  }
+}
+
+inline int ew_grid(long long work_items, int block = 256) {
+  long long b = (work_items + block - 1) / block;
+  long long cap = 148LL * 16;
+  return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace mdc

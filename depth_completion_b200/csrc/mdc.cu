@@ -1,2 +1,2 @@
 // Single translation unit of libmdc_b200.so (C ABI declared in include/mdc.h, include/mdc_debug.h).
-#include "debug_api.cuh"
+#include "api.cuh"

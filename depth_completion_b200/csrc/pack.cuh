@@ -47,19 +47,19 @@ __global__ void pack_conv3x3_dgrad_kernel(const T* __restrict__ w, __nv_bfloat16
   }
 }
 
-// [rows][cols] -> bf16 copy (optionally transposed: out[cols][rows]).
+// [rows][cols] source -> bf16: out[r*ld + c] (transpose = 0) or out[c*ld + r] (transpose = 1).
 template <typename T>
 __global__ void pack_matrix_kernel(const T* __restrict__ w, __nv_bfloat16* __restrict__ out, int rows, int cols,
-                                   int transpose) {
+                                   long long ld, int transpose) {
   long long total = 1LL * rows * cols;
   for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
     int c = i % cols;
     int r = i / cols;
     float v = to_f32(w[i]);
     if (transpose)
-      out[1LL * c * rows + r] = __float2bfloat16(v);
+      out[1LL * c * ld + r] = __float2bfloat16(v);
     else
-      out[i] = __float2bfloat16(v);
+      out[1LL * r * ld + c] = __float2bfloat16(v);
   }
 }
 

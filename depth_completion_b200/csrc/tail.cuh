@@ -1,0 +1,364 @@
+// The small, bandwidth-bound "tail" of one guided step (marigold_dc.py:813-904, :970-984):
+// UNet input assembly, DDIM x0-prediction, the sparse-mask L1+L2 loss with its gradient, the
+// grad-norm rescale, the fused Adam update of latent/scale/shift and the DDIM step.
+//
+// Everything step-dependent (sqrt(alpha_bar_t) ..., Adam bias corrections, the per-resnet
+// time-embedding biases) is read from device memory selected by a device-side step counter, so one
+// guided step is a fixed launch sequence (CUDA-graph friendly, no host sync inside the loop).
+//
+// bf16 mode of the reference computes this algebra with bf16 tensors and 0-dim fp32 scalars; every
+// torch op rounds its result to bf16.  The kernels reproduce those rounding points (bf16r).
+#pragma once
+#include "kernels.cuh"
+
+namespace mdc {
+
+struct StepTables {            // device arrays of length `steps`
+  const float* sqrt_a;         // sqrt(alpha_bar_t)
+  const float* sqrt_1ma;       // sqrt(1 - alpha_bar_t)
+  const float* sqrt_ap;        // sqrt(alpha_bar_prev)
+  const float* sqrt_1map;      // sqrt(1 - alpha_bar_prev)
+  const float* temb_bias;      // [steps][temb_total]
+  int temb_total;
+  int steps;
+};
+struct StepCur {               // scalars of the step being executed (device memory)
+  float sqrt_a, sqrt_1ma, sqrt_ap, sqrt_1map;
+  float adam_step_size_x, adam_step_size_s, adam_bc2_sqrt;
+  int step;
+};
+constexpr int MAXN = 16;       // max frames per handle
+struct StepAccum {             // per-sample accumulators (device memory)
+  float loss[MAXN], s_grad[MAXN], t_grad[MAXN];
+  float scale[MAXN], shift[MAXN];
+  float s_m[MAXN], s_v[MAXN], t_m[MAXN], t_v[MAXN];
+};
+
+// Select the step: fill StepCur and the current time-embedding biases.  One block.
+__global__ void begin_step_kernel(StepTables tb, int* __restrict__ counter, StepCur* __restrict__ cur,
+                                  float* __restrict__ temb_cur, float lr_x, float lr_s) {
+  const int s = min(*counter, tb.steps - 1);
+  if (threadIdx.x == 0) {
+    cur->sqrt_a = tb.sqrt_a[s], cur->sqrt_1ma = tb.sqrt_1ma[s];
+    cur->sqrt_ap = tb.sqrt_ap[s], cur->sqrt_1map = tb.sqrt_1map[s];
+    const double t = s + 1;
+    const double bc1 = 1.0 - pow(0.9, t), bc2 = 1.0 - pow(0.999, t);
+    cur->adam_step_size_x = static_cast<float>(lr_x / bc1);
+    cur->adam_step_size_s = static_cast<float>(lr_s / bc1);
+    cur->adam_bc2_sqrt = static_cast<float>(sqrt(bc2));
+    cur->step = s;
+  }
+  for (int i = threadIdx.x; i < tb.temb_total; i += blockDim.x) temb_cur[i] = tb.temb_bias[1LL * s * tb.temb_total + i];
+}
+
+// cat([img_latents, x], dim=1) as NHWC [N, h, w, 8]  (marigold_dc.py:459)
+__global__ void unet_input_kernel(const bf16* __restrict__ img_lat, const bf16* __restrict__ x, int N, int hw,
+                                  bf16* __restrict__ out) {
+  long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+  if (i >= 1LL * N * hw) return;
+  long long n = i / hw, p = i % hw;
+  BF8 o;
+  bf16* ob = reinterpret_cast<bf16*>(&o);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    ob[c] = img_lat[(n * 4 + c) * hw + p];
+    ob[4 + c] = x[(n * 4 + c) * hw + p];
+  }
+  *reinterpret_cast<BF8*>(out + i * 8) = o;
+}
+
+// x0 = sqrt(a) x - sqrt(1-a) v ; eps = sqrt(a) v + sqrt(1-a) x  (marigold_dc.py:813-826); z = x0 / scaling -> NHWC
+// eps_part[n*bpi + b] = partial sum of eps^2 (fixed-order reduction later).
+__global__ void x0_kernel(const bf16* __restrict__ v_nhwc, const bf16* __restrict__ x, const StepCur* __restrict__ cur,
+                          int N, int hw, float scaling, bf16* __restrict__ z_nhwc, float* __restrict__ eps_part) {
+  __shared__ float red[32];
+  const int bpi = gridDim.x / N, n = blockIdx.x / bpi, b = blockIdx.x % bpi;
+  const float sa = cur->sqrt_a, sb = cur->sqrt_1ma;
+  float acc = 0.f;
+  for (int p = b * blockDim.x + threadIdx.x; p < hw; p += bpi * blockDim.x) {
+    BF8 vv = *reinterpret_cast<const BF8*>(v_nhwc + (1LL * n * hw + p) * 8);
+    const bf16* vb = reinterpret_cast<const bf16*>(&vv);
+    BF8 o;
+    bf16* ob = reinterpret_cast<bf16*>(&o);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float xv = __bfloat162float(x[(1LL * n * 4 + c) * hw + p]), vf = __bfloat162float(vb[c]);
+      float x0 = bf16r(bf16r(sa * xv) - bf16r(sb * vf));
+      float e = bf16r(bf16r(sa * vf) + bf16r(sb * xv));
+      acc += e * e;
+      ob[c] = __float2bfloat16(x0 / scaling);
+      ob[4 + c] = __float2bfloat16(0.f);
+    }
+    *reinterpret_cast<BF8*>(z_nhwc + (1LL * n * hw + p) * 8) = o;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) eps_part[blockIdx.x] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Geometry of the decoder output -> input-resolution map (marigold_dc.py:366-370):
+// decoder output [N, PPH, PPW, 3]; unpad to [ph, pw]; bilinear (align_corners=False, no antialias) to [H, W].
+struct TailGeom {
+  int N, H, W, ph, pw, PPH, PPW;
+  long long ld_dec;  // pixel stride of the decoder output (8)
+};
+__device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+  float src = scale * (dst + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = min(static_cast<int>(src), in_size - 1);
+  i1 = min(i0 + 1, in_size - 1);
+  l1 = src - i0;
+}
+// affine-invariant prediction at one decoder pixel: (clip(mean_c dec, -1, 1) + 1) / 2, with the bf16 rounding points
+__device__ __forceinline__ float affine_at(const bf16* __restrict__ dec, long long ld, long long pix, bool& inside) {
+  const bf16* p = dec + pix * ld;
+  float m = bf16r((__bfloat162float(p[0]) + __bfloat162float(p[1]) + __bfloat162float(p[2])) / 3.f);
+  inside = (m >= -1.f && m <= 1.f);
+  m = fminf(fmaxf(m, -1.f), 1.f);
+  return bf16r((m + 1.f) * 0.5f);
+}
+
+// Masked L1+L2 loss at the valid points of one sample and its gradient (marigold_dc.py:829-840, :181-193, :877).
+// pts: compacted valid pixels of all samples, sample n owns [pt_off[n], pt_off[n+1]).  One block per sample.
+// dmean[N, PPH, PPW] (fp32, zero on entry) receives d loss / d mean_c(dec) by atomics (4 taps per point).
+__global__ void loss_points_kernel(const bf16* __restrict__ dec, TailGeom g, const int* __restrict__ pt_idx,
+                                   const float* __restrict__ pt_val, const int* __restrict__ pt_off,
+                                   const float* __restrict__ gminmax, StepAccum* __restrict__ acc,
+                                   float* __restrict__ dmean) {
+  __shared__ float red[32];
+  const int n = blockIdx.x;
+  const int p0 = pt_off[n], p1 = pt_off[n + 1];
+  const float cnt = static_cast<float>(p1 - p0);
+  const float s = acc->scale[n], t = acc->shift[n];
+  const float gmin = gminmax[2 * n], gmax = gminmax[2 * n + 1], range = gmax - gmin;
+  const float sy = static_cast<float>(g.ph) / g.H, sx = static_cast<float>(g.pw) / g.W;
+  float l_sum = 0.f, ds = 0.f, dt = 0.f;
+  for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x) {
+    const int pix = pt_idx[i];
+    const int Y = pix / g.W, X = pix % g.W;
+    const float guide = pt_val[i];
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilinear_src(Y, sy, g.ph, y0, y1, ly);
+    bilinear_src(X, sx, g.pw, x0, x1, lx);
+    const long long base = 1LL * n * g.PPH * g.PPW;
+    const long long q00 = base + 1LL * y0 * g.PPW + x0, q01 = base + 1LL * y0 * g.PPW + x1;
+    const long long q10 = base + 1LL * y1 * g.PPW + x0, q11 = base + 1LL * y1 * g.PPW + x1;
+    bool in00, in01, in10, in11;
+    const float a00 = affine_at(dec, g.ld_dec, q00, in00), a01 = affine_at(dec, g.ld_dec, q01, in01);
+    const float a10 = affine_at(dec, g.ld_dec, q10, in10), a11 = affine_at(dec, g.ld_dec, q11, in11);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    const float aff = bf16r(w00 * a00 + w01 * a01 + w10 * a10 + w11 * a11);
+    const float pre = s * s * range * aff + t * t * gmin;
+    const float dense = fminf(fmaxf(pre, 0.f), 1.f);
+    const float diff = dense - guide;
+    l_sum += (fabsf(diff) + diff * diff) / cnt;
+    float dd = ((diff > 0.f) - (diff < 0.f) + 2.f * diff) / cnt;
+    if (pre < 0.f || pre > 1.f) dd = 0.f;  // clamp backward
+    ds += dd * 2.f * s * range * aff;
+    dt += dd * 2.f * t * gmin;
+    const float da = dd * s * s * range * 0.5f;  // through (m + 1) / 2
+    if (in00) atomicAdd(&dmean[q00], da * w00);
+    if (in01) atomicAdd(&dmean[q01], da * w01);
+    if (in10) atomicAdd(&dmean[q10], da * w10);
+    if (in11) atomicAdd(&dmean[q11], da * w11);
+  }
+  l_sum = block_sum(l_sum, red);
+  ds = block_sum(ds, red);
+  dt = block_sum(dt, red);
+  if (threadIdx.x == 0) acc->loss[n] = l_sum, acc->s_grad[n] = ds, acc->t_grad[n] = dt;
+}
+// d dec[n, y, x, c] = dmean / 3 for c < 3 (bf16); clears dmean for the next step.
+__global__ void dec_grad_kernel(float* __restrict__ dmean, long long npix, bf16* __restrict__ ddec) {
+  long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  float d = dmean[i] * (1.f / 3.f);
+  dmean[i] = 0.f;
+  BF8 o;
+  bf16* ob = reinterpret_cast<bf16*>(&o);
+  bf16 dv = __float2bfloat16(d), z = __float2bfloat16(0.f);
+  ob[0] = dv, ob[1] = dv, ob[2] = dv, ob[3] = z, ob[4] = z, ob[5] = z, ob[6] = z, ob[7] = z;
+  *reinterpret_cast<BF8*>(ddec + i * 8) = o;
+}
+
+// dz (decoder-input gradient, NHWC) -> d x0 = dz / scaling; dv = -sqrt(1-a) d x0 (UNet output gradient, NHWC);
+// direct part of dx = sqrt(a) d x0 (NCHW fp32 holding bf16-rounded values).
+__global__ void dx0_kernel(const bf16* __restrict__ dz_nhwc, const StepCur* __restrict__ cur, int N, int hw,
+                           float scaling, bf16* __restrict__ dv_nhwc, float* __restrict__ dx_direct) {
+  long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+  if (i >= 1LL * N * hw) return;
+  long long n = i / hw, p = i % hw;
+  const float sa = cur->sqrt_a, sb = cur->sqrt_1ma;
+  BF8 in = *reinterpret_cast<const BF8*>(dz_nhwc + i * 8);
+  const bf16* ib = reinterpret_cast<const bf16*>(&in);
+  BF8 o;
+  bf16* ob = reinterpret_cast<bf16*>(&o);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float d0 = bf16r(__bfloat162float(ib[c]) / scaling);
+    ob[c] = __float2bfloat16(-sb * d0);
+    ob[4 + c] = __float2bfloat16(0.f);
+    dx_direct[(n * 4 + c) * hw + p] = bf16r(sa * d0);
+  }
+  *reinterpret_cast<BF8*>(dv_nhwc + i * 8) = o;
+}
+
+// total latent gradient g = direct + UNet path (channels 4..7 of the UNet-input gradient); partial sums of g^2.
+__global__ void grad_total_kernel(const float* __restrict__ dx_direct, const bf16* __restrict__ din_nhwc, int N, int hw,
+                                  float* __restrict__ gbuf, float* __restrict__ g_part) {
+  __shared__ float red[32];
+  const int bpi = gridDim.x / N, n = blockIdx.x / bpi, b = blockIdx.x % bpi;
+  float acc = 0.f;
+  for (int p = b * blockDim.x + threadIdx.x; p < hw; p += bpi * blockDim.x) {
+    BF8 in = *reinterpret_cast<const BF8*>(din_nhwc + (1LL * n * hw + p) * 8);
+    const bf16* ib = reinterpret_cast<const bf16*>(&in);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      long long j = (1LL * n * 4 + c) * hw + p;
+      float gg = bf16r(dx_direct[j] + __bfloat162float(ib[4 + c]));
+      gbuf[j] = gg;
+      acc += gg * gg;
+    }
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) g_part[blockIdx.x] = acc;
+}
+
+// grad-norm rescale (marigold_dc.py:881-894) + torch.optim.Adam foreach update in the parameter dtype (bf16 latent,
+// fp32 scale/shift; :897) + DDIM prev_sample with the stale v and the updated x (:901-904).  Advances the step counter.
+__global__ void adam_ddim_kernel(const float* __restrict__ gbuf, const float* __restrict__ eps_part,
+                                 const float* __restrict__ g_part, int parts_per_img, const bf16* __restrict__ v_nhwc,
+                                 const StepCur* __restrict__ cur, int N, int hw, bf16* __restrict__ x,
+                                 bf16* __restrict__ m1, bf16* __restrict__ m2, StepAccum* __restrict__ acc,
+                                 int* __restrict__ counter, bf16* __restrict__ x_adam_dbg) {
+  const int bpi = gridDim.x / N, n = blockIdx.x / bpi, b = blockIdx.x % bpi;
+  float e2 = 0.f, g2 = 0.f;
+  for (int k = 0; k < parts_per_img; ++k) e2 += eps_part[n * parts_per_img + k], g2 += g_part[n * parts_per_img + k];
+  const float en = bf16r(sqrtf(e2)), gn = bf16r(sqrtf(g2));
+  const float factor = bf16r(en / fmaxf(gn, 1e-7f));
+  const float sa = cur->sqrt_a, sb = cur->sqrt_1ma, sap = cur->sqrt_ap, sbp = cur->sqrt_1map;
+  const float step_size = cur->adam_step_size_x, bc2s = cur->adam_bc2_sqrt;
+  for (int p = b * blockDim.x + threadIdx.x; p < hw; p += bpi * blockDim.x) {
+    BF8 vv = *reinterpret_cast<const BF8*>(v_nhwc + (1LL * n * hw + p) * 8);
+    const bf16* vb = reinterpret_cast<const bf16*>(&vv);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const long long j = (1LL * n * 4 + c) * hw + p;
+      const float g = bf16r(gbuf[j] * factor);
+      float m = __bfloat162float(m1[j]), v2 = __bfloat162float(m2[j]), xv = __bfloat162float(x[j]);
+      m = bf16r(m + 0.1f * (g - m));                      // exp_avg.lerp_(grad, 1 - beta1)
+      v2 = bf16r(v2 * 0.999f);                            // exp_avg_sq.mul_(beta2)
+      v2 = bf16r(v2 + 0.001f * g * g);                    //           .addcmul_(grad, grad, 1 - beta2)
+      float den = bf16r(sqrtf(v2));
+      den = bf16r(den / bc2s);
+      den = bf16r(den + 1e-8f);
+      xv = bf16r(xv - step_size * (m / den));             // param.addcdiv_(exp_avg, denom, -step_size)
+      m1[j] = __float2bfloat16(m), m2[j] = __float2bfloat16(v2);
+      if (x_adam_dbg) x_adam_dbg[j] = __float2bfloat16(xv);
+      const float vf = __bfloat162float(vb[c]);
+      const float x0 = bf16r(bf16r(sa * xv) - bf16r(sb * vf));
+      const float e = bf16r(bf16r(sa * vf) + bf16r(sb * xv));
+      x[j] = __float2bfloat16(bf16r(sap * x0) + bf16r(sbp * e));
+    }
+  }
+  if (b == 0 && threadIdx.x == 0) {  // fp32 Adam on scale / shift of sample n
+    const float ss = cur->adam_step_size_s;
+    float gs = acc->s_grad[n], gt = acc->t_grad[n];
+    float sm = acc->s_m[n] + 0.1f * (gs - acc->s_m[n]), sv = acc->s_v[n] * 0.999f + 0.001f * gs * gs;
+    float tm = acc->t_m[n] + 0.1f * (gt - acc->t_m[n]), tv = acc->t_v[n] * 0.999f + 0.001f * gt * gt;
+    acc->scale[n] -= ss * (sm / (sqrtf(sv) / bc2s + 1e-8f));
+    acc->shift[n] -= ss * (tm / (sqrtf(tv) / bc2s + 1e-8f));
+    acc->s_m[n] = sm, acc->s_v[n] = sv, acc->t_m[n] = tm, acc->t_v[n] = tv;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *counter = *counter + 1;
+}
+
+// Final dense map (marigold_dc.py:970-984): clamp(s^2 range aff + t^2 gmin, 0, 1) * (max - min) + min -> fp32 [N,1,H,W]
+__global__ void dense_out_kernel(const bf16* __restrict__ dec, TailGeom g, const float* __restrict__ gminmax,
+                                 const float* __restrict__ depth_minmax, const StepAccum* __restrict__ acc,
+                                 float* __restrict__ out) {
+  long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+  if (i >= 1LL * g.N * g.H * g.W) return;
+  const int X = i % g.W, Y = (i / g.W) % g.H, n = i / (1LL * g.W * g.H);
+  const float sy = static_cast<float>(g.ph) / g.H, sx = static_cast<float>(g.pw) / g.W;
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilinear_src(Y, sy, g.ph, y0, y1, ly);
+  bilinear_src(X, sx, g.pw, x0, x1, lx);
+  const long long base = 1LL * n * g.PPH * g.PPW;
+  bool in;
+  const float a00 = affine_at(dec, g.ld_dec, base + 1LL * y0 * g.PPW + x0, in);
+  const float a01 = affine_at(dec, g.ld_dec, base + 1LL * y0 * g.PPW + x1, in);
+  const float a10 = affine_at(dec, g.ld_dec, base + 1LL * y1 * g.PPW + x0, in);
+  const float a11 = affine_at(dec, g.ld_dec, base + 1LL * y1 * g.PPW + x1, in);
+  const float aff = bf16r((1.f - ly) * ((1.f - lx) * a00 + lx * a01) + ly * ((1.f - lx) * a10 + lx * a11));
+  const float s = acc->scale[n], t = acc->shift[n];
+  const float gmin = gminmax[2 * n], gmax = gminmax[2 * n + 1];
+  float d = s * s * (gmax - gmin) * aff + t * t * gmin;
+  d = fminf(fmaxf(d, 0.f), 1.f);
+  const float dmin = depth_minmax[2 * n], dmax = depth_minmax[2 * n + 1];
+  out[i] = d * (dmax - dmin) + dmin;
+}
+
+// Ordered compaction of the valid pixels of one sample (mask != 0): one block per sample, run once per call.
+__global__ void compact_points_kernel(const float* __restrict__ guide, const uint8_t* __restrict__ mask, int HW,
+                                      const int* __restrict__ pt_off, int* __restrict__ pt_idx,
+                                      float* __restrict__ pt_val) {
+  __shared__ int wcount[32];
+  __shared__ int base;
+  const int n = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (threadIdx.x == 0) base = pt_off[n];
+  __syncthreads();
+  for (int p0 = 0; p0 < HW; p0 += blockDim.x) {
+    const int p = p0 + threadIdx.x;
+    const bool valid = p < HW && mask[1LL * n * HW + p] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) wcount[w] = __popc(bal);
+    __syncthreads();
+    int before = 0;
+    for (int k = 0; k < w; ++k) before += wcount[k];
+    if (valid) {
+      const int dst = base + before + __popc(bal & ((1u << lane) - 1));
+      pt_idx[dst] = p;
+      pt_val[dst] = guide[1LL * n * HW + p];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int k = 0; k < nw; ++k) tot += wcount[k];
+      base += tot;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// prepare-time helpers (not on the hot path): sinusoidal timestep embedding and small dense layers
+// out[s][o] = act_out( sum_i W[o][i] * act_in(in[s][i]) + b[o] ), every stage rounded to bf16 like torch's bf16 ops.
+__global__ void timestep_embedding_kernel(const int* __restrict__ timesteps, int steps, int dim, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= steps * dim) return;
+  int s = i / dim, j = i % dim, half = dim / 2;
+  int k = j < half ? j : j - half;
+  float freq = expf(-logf(10000.f) * k / half);
+  float arg = static_cast<float>(timesteps[s]) * freq;
+  out[i] = bf16r(j < half ? cosf(arg) : sinf(arg));  // flip_sin_to_cos: [cos | sin]
+}
+__global__ void small_linear_kernel(const bf16* __restrict__ W, long long ldw, const float* __restrict__ bias,
+                                    const float* __restrict__ in, long long ldin, int S, int In, int Out, int silu_in,
+                                    float* __restrict__ out, long long ldout) {
+  const long long wid = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= 1LL * S * Out) return;
+  const int s = wid / Out, o = wid % Out;
+  float acc = 0.f;
+  for (int i = lane; i < In; i += 32) {
+    float a = in[s * ldin + i];
+    if (silu_in) a = bf16r(siluf_(a));
+    acc += __bfloat162float(W[o * ldw + i]) * a;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[s * ldout + o] = bf16r(acc + (bias ? bias[o] : 0.f));
+}
+
+}  // namespace mdc

@@ -1,0 +1,221 @@
+"""ctypes binding of the C ABI in include/mdc.h: one StepEngine per (device, shapes, model config).
+
+All arithmetic of the guided loop happens in libmdc_b200.so; this class only marshals device pointers of torch
+tensors and keeps the handle alive.  There is no fallback: every method raises MdcError if the library is missing
+or a call fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import MdcError, check, lib, ptr
+from .config import UNetConfig, VAEConfig, processed_geometry
+
+MAX_BLOCKS = 8
+
+
+class MdcConfig(C.Structure):
+    _fields_ = [
+        ("device", C.c_int), ("n_batch", C.c_int), ("height", C.c_int), ("width", C.c_int),
+        ("proc_h", C.c_int), ("proc_w", C.c_int), ("pad_h", C.c_int), ("pad_w", C.c_int), ("steps", C.c_int),
+        ("unet_in_ch", C.c_int), ("unet_out_ch", C.c_int), ("unet_nblocks", C.c_int),
+        ("unet_layers_per_block", C.c_int), ("unet_groups", C.c_int), ("cross_dim", C.c_int),
+        ("unet_block_ch", C.c_int * MAX_BLOCKS), ("unet_heads", C.c_int * MAX_BLOCKS),
+        ("unet_down_attn", C.c_int * MAX_BLOCKS),
+        ("vae_nblocks", C.c_int), ("vae_layers_per_block", C.c_int), ("vae_groups", C.c_int),
+        ("vae_latent_ch", C.c_int), ("vae_block_ch", C.c_int * MAX_BLOCKS), ("vae_scaling", C.c_float),
+    ]
+
+
+def _declare(l):
+    if getattr(l, "_mdc_declared", False):
+        return
+    l.mdc_create.argtypes = [C.POINTER(MdcConfig), C.POINTER(C.c_void_p)]
+    l.mdc_destroy.argtypes = [C.c_void_p]
+    l.mdc_destroy.restype = None
+    l.mdc_num_weights.argtypes = [C.c_void_p]
+    l.mdc_weight_key.argtypes = [C.c_void_p, C.c_int]
+    l.mdc_weight_key.restype = C.c_char_p
+    l.mdc_set_weight.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_longlong), C.c_int, C.c_int]
+    l.mdc_prepare.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    l.mdc_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                            C.c_float, C.c_float]
+    l.mdc_run.argtypes = [C.c_void_p, C.c_int]
+    l.mdc_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.mdc_decode_final.argtypes = [C.c_void_p, C.c_void_p]
+    l.mdc_launch_count.argtypes = [C.c_void_p]
+    l.mdc_launch_count.restype = C.c_longlong
+    l.mdc_device_bytes.argtypes = [C.c_void_p]
+    l.mdc_device_bytes.restype = C.c_longlong
+    l.mdc_dbg_forward.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    l.mdc_dbg_backward.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    l.mdc_dbg_read_tensor.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p]
+    l.mdc_dbg_tensor_shape.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+    l.mdc_dbg_num_tensors.argtypes = [C.c_void_p]
+    l.mdc_dbg_tensor_name.argtypes = [C.c_void_p, C.c_int]
+    l.mdc_dbg_tensor_name.restype = C.c_char_p
+    l.mdc_dbg_read_x_adam.argtypes = [C.c_void_p, C.c_void_p]
+    l.mdc_dbg_time_tapes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    l._mdc_declared = True
+
+
+class StepEngine:
+    """Owns one mdc_handle: the UNet + VAE-decoder tapes and workspace for fixed (N, H, W, resolution, steps)."""
+
+    def __init__(self, unet_cfg: UNetConfig, vae_cfg: VAEConfig, n_batch: int, height: int, width: int,
+                 resolution: int, steps: int, device: torch.device | int = 0):
+        self._h = C.c_void_p(0)
+        self.lib = lib()
+        _declare(self.lib)
+        dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+        if dev.type != "cuda":
+            raise MdcError("the guided loop runs on a CUDA device only (no CPU path exists)")
+        self.device = dev
+        ph, pw, pad_h, pad_w = processed_geometry(height, width, resolution)
+        self.n, self.H, self.W, self.steps = n_batch, height, width, steps
+        self.ph, self.pw, self.pad = ph, pw, (pad_h, pad_w)
+        self.lh, self.lw = (ph + pad_h) // 8, (pw + pad_w) // 8
+        self.unet_cfg, self.vae_cfg = unet_cfg, vae_cfg
+        c = MdcConfig()
+        c.device = dev.index or 0
+        c.n_batch, c.height, c.width = n_batch, height, width
+        c.proc_h, c.proc_w, c.pad_h, c.pad_w, c.steps = ph, pw, pad_h, pad_w, steps
+        c.unet_in_ch, c.unet_out_ch = unet_cfg.in_channels, unet_cfg.out_channels
+        c.unet_nblocks, c.unet_layers_per_block = len(unet_cfg.block_out_channels), unet_cfg.layers_per_block
+        c.unet_groups, c.cross_dim = unet_cfg.norm_num_groups, unet_cfg.cross_attention_dim
+        for i, v in enumerate(unet_cfg.block_out_channels):
+            c.unet_block_ch[i] = v
+            c.unet_heads[i] = unet_cfg.attention_heads[i]
+            c.unet_down_attn[i] = int(unet_cfg.down_attention[i])
+        c.vae_nblocks, c.vae_layers_per_block = len(vae_cfg.block_out_channels), vae_cfg.layers_per_block
+        c.vae_groups, c.vae_latent_ch, c.vae_scaling = vae_cfg.norm_num_groups, vae_cfg.latent_channels, vae_cfg.scaling_factor
+        for i, v in enumerate(vae_cfg.block_out_channels):
+            c.vae_block_ch[i] = v
+        with torch.cuda.device(dev):
+            check(self.lib.mdc_create(C.byref(c), C.byref(self._h)))
+        self._keep = []
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.mdc_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def weight_keys(self):
+        n = self.lib.mdc_num_weights(self._h)
+        return [self.lib.mdc_weight_key(self._h, i).decode() for i in range(n)]
+
+    def load_weights(self, unet_sd: dict, vae_sd: dict):
+        """Hands every parameter the tapes need to mdc_set_weight (keys: 'unet.' / 'vae.' + diffusers name)."""
+        missing = []
+        for key in self.weight_keys():
+            prefix, name = key.split(".", 1)
+            sd = unet_sd if prefix == "unet" else vae_sd
+            if name not in sd:
+                missing.append(key)
+                continue
+            t = sd[name].detach()
+            if t.dtype not in (torch.float32, torch.bfloat16):
+                t = t.float()
+            t = t.to(self.device).contiguous()
+            shape = (C.c_longlong * t.ndim)(*t.shape)
+            dt = 0 if t.dtype == torch.float32 else 1
+            check(self.lib.mdc_set_weight(self._h, key.encode(), ptr(t), shape, t.ndim, dt))
+        if missing:
+            raise MdcError(f"state dicts lack {len(missing)} parameters, e.g. {missing[:3]}")
+        torch.cuda.synchronize(self.device)
+
+    def prepare(self, ctx: torch.Tensor, alphas_cumprod: torch.Tensor, timesteps: np.ndarray):
+        ctx = ctx.to(self.device, torch.bfloat16).contiguous()
+        assert ctx.numel() == 2 * self.unet_cfg.cross_attention_dim, "empty-prompt embedding must be [1, 2, cross_dim]"
+        ac = np.ascontiguousarray(alphas_cumprod.detach().float().cpu().numpy())
+        ts = np.ascontiguousarray(np.asarray(timesteps, dtype=np.int32))
+        assert ac.shape[0] == 1000 and ts.shape[0] == self.steps
+        check(self.lib.mdc_prepare(self._h, ptr(ctx), ac.ctypes.data_as(C.c_void_p), ts.ctypes.data_as(C.c_void_p),
+                                   int(ts.shape[0])))
+
+    # ------------------------------------------------------------------ per call
+    def begin(self, img_latents, x, guide, mask, guide_minmax, depth_minmax, lr_latent=0.05, lr_scaling=0.005):
+        il = img_latents.to(self.device, torch.bfloat16).contiguous()
+        x = x.to(self.device, torch.bfloat16).contiguous()
+        guide = guide.to(self.device, torch.float32).contiguous()
+        mask = mask.to(self.device, torch.uint8).contiguous()
+        assert tuple(il.shape) == (self.n, 4, self.lh, self.lw) and tuple(x.shape) == tuple(il.shape), (il.shape, x.shape)
+        assert guide.numel() == self.n * self.H * self.W and mask.numel() == guide.numel()
+        gmm = np.ascontiguousarray(np.asarray(guide_minmax, dtype=np.float32).reshape(self.n, 2))
+        dmm = np.ascontiguousarray(np.asarray(depth_minmax, dtype=np.float32).reshape(self.n, 2))
+        check(self.lib.mdc_begin(self._h, ptr(il), ptr(x), ptr(guide), ptr(mask), gmm.ctypes.data_as(C.c_void_p),
+                                 dmm.ctypes.data_as(C.c_void_p), float(lr_latent), float(lr_scaling)))
+
+    def run(self, n_steps: int):
+        check(self.lib.mdc_run(self._h, int(n_steps)))
+
+    def get_state(self):
+        x = torch.empty(self.n, 4, self.lh, self.lw, device=self.device, dtype=torch.bfloat16)
+        sc = np.zeros(self.n, np.float32)
+        sh = np.zeros(self.n, np.float32)
+        ls = np.zeros(self.n, np.float32)
+        check(self.lib.mdc_get_state(self._h, ptr(x), sc.ctypes.data_as(C.c_void_p), sh.ctypes.data_as(C.c_void_p),
+                                     ls.ctypes.data_as(C.c_void_p)))
+        return x, torch.from_numpy(sc), torch.from_numpy(sh), torch.from_numpy(ls)
+
+    def decode_final(self) -> torch.Tensor:
+        out = torch.empty(self.n, 1, self.H, self.W, device=self.device, dtype=torch.float32)
+        check(self.lib.mdc_decode_final(self._h, ptr(out)))
+        return out
+
+    def device_bytes(self) -> int:
+        return int(self.lib.mdc_device_bytes(self._h))
+
+    # ------------------------------------------------------------------ debug (tests / profiling)
+    def _io_shapes(self, which):
+        if which == 0:
+            return (self.n, 8, self.lh, self.lw), (self.n, 4, self.lh, self.lw)
+        return (self.n, 4, self.lh, self.lw), (self.n, 3, self.lh * 8, self.lw * 8)
+
+    def dbg_forward(self, which: int, step: int, x: torch.Tensor) -> torch.Tensor:
+        ishape, oshape = self._io_shapes(which)
+        x = x.to(self.device, torch.float32).contiguous()
+        assert tuple(x.shape) == ishape, (x.shape, ishape)
+        out = torch.empty(oshape, device=self.device, dtype=torch.float32)
+        check(self.lib.mdc_dbg_forward(self._h, which, step, ptr(x), ptr(out)))
+        return out
+
+    def dbg_backward(self, which: int, dout: torch.Tensor) -> torch.Tensor:
+        ishape, oshape = self._io_shapes(which)
+        dout = dout.to(self.device, torch.float32).contiguous()
+        assert tuple(dout.shape) == oshape
+        din = torch.empty(ishape, device=self.device, dtype=torch.float32)
+        check(self.lib.mdc_dbg_backward(self._h, which, ptr(dout), ptr(din)))
+        return din
+
+    def dbg_tensor_names(self):
+        n = self.lib.mdc_dbg_num_tensors(self._h)
+        return [self.lib.mdc_dbg_tensor_name(self._h, i).decode() for i in range(n)]
+
+    def dbg_read(self, name: str, grad: bool = False) -> torch.Tensor:
+        shp = (C.c_int * 4)()
+        check(self.lib.mdc_dbg_tensor_shape(self._h, name.encode(), shp))
+        out = torch.empty(tuple(shp), device=self.device, dtype=torch.float32)
+        check(self.lib.mdc_dbg_read_tensor(self._h, name.encode(), int(grad), ptr(out)))
+        return out
+
+    def dbg_x_adam(self) -> torch.Tensor:
+        x = torch.empty(self.n, 4, self.lh, self.lw, device=self.device, dtype=torch.bfloat16)
+        check(self.lib.mdc_dbg_read_x_adam(self._h, ptr(x)))
+        return x
+
+    def dbg_time_tapes(self, iters: int = 3):
+        ms = (C.c_float * 4)()
+        check(self.lib.mdc_dbg_time_tapes(self._h, iters, ms))
+        return dict(unet_fwd=ms[0], unet_bwd=ms[1], dec_fwd=ms[2], dec_bwd=ms[3])

@@ -1,0 +1,219 @@
+"""Drop-in for the hot path of tier4/depth_completion: `MarigoldDepthCompletionPipeline.__call__`
+(/root/reference/marigold_dc.py:467-985) with the guided denoising loop (:799-909) and the final decode
+(:970-985) executed by libmdc_b200.so (hand-written sm_100a kernels) instead of diffusers + autograd.
+
+Same constructor and call signature, same return tuple `(denses [N,1,H,W] fp32 metric, pred_latents [N,4,EH,EW])`,
+same ValueError conventions.  Non-default branches the north star leaves out of scope
+(log/inverse projection, percentile norm, sgd/adagrad, kld/edge/smooth losses, closed-form / no-grad paths,
+per-input training) raise NotImplementedError instead of silently doing something else.
+
+The host keeps, in PyTorch, only what runs once per call: argument checks, image resize/pad, the VAE *encoder*,
+sparse-depth normalisation and the seeded initial latent (marigold_dc.py:659-756).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ddim, prologue
+from ._lib import MdcError
+from .config import processed_geometry, unet_config_from, vae_config_from
+from .engine import StepEngine
+
+SUPPORTED_LOSS_FUNCS = ["l1", "l2", "edge", "smooth"]  # marigold_dc.py:19
+EPSILON = 1e-7  # marigold_dc.py:20
+EMPTY_PROMPT_IDS = (49406, 49407)  # CLIP BOS, EOS: tokenizer("", padding="do_not_pad")
+
+
+class MarigoldDepthCompletionPipeline:
+    """Constructor mirrors marigold_dc.py:258-282.
+
+    `unet` / `vae` are anything exposing `.state_dict()` with diffusers key names plus a diffusers-style
+    `.config` (or our dataclass `.cfg`).  `scheduler` may be a diffusers DDIMScheduler-like object
+    (`alphas_cumprod`, `set_timesteps`, `timesteps`) or None for the built-in trailing DDIM tables.
+    `text_encoder` / `tokenizer` are only used to produce the empty-prompt embedding once
+    (marigold_dc.py:664-674); alternatively assign `pipe.empty_text_embedding` ([1, 2, cross_dim]).
+    """
+
+    def __init__(self, unet, vae, scheduler=None, text_encoder=None, tokenizer=None, prediction_type=None,
+                 scale_invariant=True, shift_invariant=True, default_denoising_steps=None,
+                 default_processing_resolution=None):
+        self.unet, self.vae, self.scheduler = unet, vae, scheduler
+        self.text_encoder, self.tokenizer = text_encoder, tokenizer
+        self.prediction_type = prediction_type
+        self.scale_invariant, self.shift_invariant = scale_invariant, shift_invariant
+        self.default_denoising_steps = default_denoising_steps
+        self.default_processing_resolution = default_processing_resolution
+        self.empty_text_embedding = None
+        self.unet_cfg = unet_config_from(unet)
+        self.vae_cfg = vae_config_from(vae)
+        p = next(iter(unet.state_dict().values()))
+        self.device = p.device
+        self.dtype = torch.bfloat16  # the engine computes in bf16 (BASELINE.json configs b-e)
+        self._engines: dict = {}
+        self._sd_cache = None
+
+    # ------------------------------------------------------------------ plumbing
+    def to(self, device):
+        self.device = torch.device(device)
+        for m in (self.unet, self.vae, self.text_encoder):
+            if m is not None and hasattr(m, "to"):
+                m.to(self.device)
+        self._sd_cache = None
+        self._engines.clear()
+        return self
+
+    def _state_dicts(self):
+        if self._sd_cache is None:
+            usd = {k: v.detach().to(self.device) for k, v in self.unet.state_dict().items()}
+            vsd = {k: v.detach().to(self.device) for k, v in self.vae.state_dict().items()}
+            vsd_enc = {k: v.to(self.dtype) for k, v in vsd.items() if k.startswith(("encoder.", "quant_conv."))}
+            self._sd_cache = (usd, vsd, vsd_enc)
+        return self._sd_cache
+
+    def _empty_embedding(self):
+        if self.empty_text_embedding is None:
+            if self.text_encoder is None:
+                raise ValueError("no text_encoder given and pipe.empty_text_embedding is not set")
+            ids = torch.tensor([list(EMPTY_PROMPT_IDS)], device=self.device)
+            if self.tokenizer is not None:
+                try:
+                    tok = self.tokenizer("", padding="do_not_pad", max_length=self.tokenizer.model_max_length,
+                                         truncation=True, return_tensors="pt")
+                    if tok.input_ids.shape[-1] == 2:
+                        ids = tok.input_ids.to(self.device)
+                except Exception:
+                    pass
+            with torch.no_grad():
+                self.empty_text_embedding = self.text_encoder(ids)[0]
+        return self.empty_text_embedding
+
+    def _engine(self, N, H, W, resolution, steps) -> StepEngine:
+        key = (N, H, W, resolution, steps, str(self.device))
+        eng = self._engines.get(key)
+        if eng is None:
+            if self.device.type != "cuda":
+                raise MdcError("MarigoldDepthCompletionPipeline needs a CUDA device: call .to('cuda') (no CPU path)")
+            for old in self._engines.values():  # one resident workspace at a time
+                old.close()
+            self._engines.clear()
+            usd, vsd, _ = self._state_dicts()
+            eng = StepEngine(self.unet_cfg, self.vae_cfg, N, H, W, resolution, steps, self.device)
+            eng.load_weights(usd, vsd)
+            ac, ts = ddim.tables_from_scheduler(self.scheduler, steps)
+            eng.prepare(self._empty_embedding(), ac, ts)
+            self._engines[key] = eng
+        return eng
+
+    # ------------------------------------------------------------------ the call (marigold_dc.py:467-493)
+    def __call__(self, imgs, sparses, max_depth, min_depth=0.0, projection="linear", inv=False, norm="minmax",
+                 percentile=(0.01, 0.99), pred_latents_prev=None, beta=0.9, steps=50, resolution=768,
+                 closed_form=None, opt="adam", lr=None, kld=False, kld_weight=0.1, kld_mode="simple",
+                 interp_mode="bilinear", loss_funcs=None, seed=2024, train_latents=True, train_method="per-step",
+                 train_steps=10):
+        # --- argument validation, same order and conditions as marigold_dc.py:583-656
+        if (imgs.ndim != 4 or sparses.ndim != 4 or imgs.shape[0] != sparses.shape[0]
+                or imgs.shape[-2:] != sparses.shape[-2:]):
+            raise ValueError("Shape of image must be [N, C, H, W] and shape of sparse must be [N, 1, H, W], but got "
+                             f"image.shape: {imgs.shape} and sparse.shape: {sparses.shape}")
+        N, _, H, W = imgs.shape
+        EH = resolution * H // (8 * max(H, W))
+        EW = resolution * W // (8 * max(H, W))
+        if pred_latents_prev is not None:
+            if pred_latents_prev.ndim != 4 or tuple(pred_latents_prev.shape) != (N, 4, EH, EW):
+                raise ValueError(f"Shape of pred_latents_prev must be [N, 4, EH, EW], but got {pred_latents_prev.shape}")
+        if closed_form is None:
+            closed_form = not train_latents
+        elif not closed_form and not train_latents:
+            raise ValueError("Closed form solution must be enabled when trainable latents are not used. "
+                             "Set closed_form=True when train_latents=False, or just leave closed_form=None")
+        if train_method not in ["per-step", "per-input"]:
+            raise ValueError(f"Unknown train_method: {train_method}")
+        if train_method == "per-input" and train_steps <= 0:
+            raise ValueError("train_steps must be > 0 when per-input training is enabled")
+        if not (0 < beta < 1):
+            raise ValueError(f"beta must be in (0, 1), but got {beta}")
+        if norm == "percentile" and not all(0 <= p <= 1 for p in percentile):
+            raise ValueError(f"percentile must be in [0, 1], but got {percentile}")
+        if projection not in ["linear", "log", "log10"]:
+            raise ValueError(f"Unknown projection method: {projection}")
+        if (projection in ["log", "log10"] or inv) and min_depth <= EPSILON:
+            raise ValueError(f"min_depth must be > {EPSILON} when projection is 'log' or 'log10' or inv is True, "
+                             f"but got {min_depth}")
+        lr_latent, lr_scaling = (0.05, 0.005) if lr is None else lr
+        if loss_funcs is None:
+            loss_funcs = ["l1", "l2"]
+        else:
+            for f in loss_funcs:
+                if f not in SUPPORTED_LOSS_FUNCS:
+                    raise ValueError(f"Unknown loss function: {f}")
+        if norm not in ("minmax", "percentile", "const"):
+            raise ValueError(f"Unknown norm method: {norm}")
+        if opt not in ("adam", "sgd", "adagrad"):
+            raise ValueError(f"Unknown optimizer: {opt}")
+        # --- branches outside the hot path this library implements (OUT OF SCOPE rows)
+        unsupported = []
+        if projection != "linear" or inv:
+            unsupported.append("projection/inv")
+        if norm == "percentile":
+            unsupported.append("norm='percentile'")
+        if opt != "adam":
+            unsupported.append(f"opt='{opt}'")
+        if kld:
+            unsupported.append("kld")
+        if sorted(loss_funcs) != ["l1", "l2"]:
+            unsupported.append(f"loss_funcs={loss_funcs}")
+        if not train_latents or closed_form or train_method != "per-step":
+            unsupported.append("train_latents=False / closed_form / per-input")
+        if interp_mode != "bilinear":
+            unsupported.append(f"interp_mode='{interp_mode}'")
+        if unsupported:
+            raise NotImplementedError("outside the B200 hot path (guided per-step Adam, linear projection, l1+l2): "
+                                      + ", ".join(unsupported))
+        ph, pw, pad_h, pad_w = processed_geometry(H, W, resolution)
+        if ((ph + pad_h) // 8, (pw + pad_w) // 8) != (EH, EW):
+            raise ValueError(f"resolution={resolution} gives a {ph}x{pw} processed image whose padded latent "
+                             f"{(ph + pad_h) // 8}x{(pw + pad_w) // 8} differs from the pipeline's {EH}x{EW} "
+                             "(the reference fails at torch.cat for this combination, marigold_dc.py:459)")
+
+        dev = self.device
+        imgs, sparses = imgs.to(dev), sparses.to(dev)
+        eng = self._engine(N, H, W, resolution, steps)
+        _, _, vsd_enc = self._state_dicts()
+        with torch.no_grad():
+            # marigold_dc.py:661, :677-684 -- first draw of the seeded generator, in the pipeline dtype
+            gen = torch.Generator(device=dev).manual_seed(seed)
+            common = torch.randn((1, 4, EH, EW), device=dev, dtype=self.dtype, generator=gen).repeat(N, 1, 1, 1)
+            # marigold_dc.py:687-698
+            resized, _ = prologue.preprocess_image(imgs, resolution, self.dtype)
+            img_latents = prologue.vae_encode_mode(vsd_enc, self.vae_cfg, resized) * self.vae_cfg.scaling_factor
+            x = common if pred_latents_prev is None else beta * common + (1 - beta) * pred_latents_prev.to(dev)
+            # marigold_dc.py:707-756 (linear projection)
+            sparses = sparses.float()
+            masks = sparses > 0
+            if norm == "minmax":
+                lo, hi = prologue.masked_minmax(sparses.view(N, -1), masks.view(N, -1))
+                lo, hi = lo.view(N, 1, 1, 1), hi.view(N, 1, 1, 1)
+            else:  # "const"
+                lo = torch.full((N, 1, 1, 1), float(min_depth), device=dev)
+                hi = torch.full((N, 1, 1, 1), float(max_depth), device=dev)
+            clamped = sparses.clamp(min=lo, max=hi)
+            if norm == "minmax":
+                lo, hi = lo.clamp(min=min_depth), hi.clamp(max=max_depth)
+            guide = (clamped - lo) / (hi - lo)
+            # what _affine_to_metric recomputes every step (marigold_dc.py:326): masked min/max of the guide
+            gmin, gmax = prologue.masked_minmax(guide.view(N, -1), masks.view(N, -1))
+            gmm = torch.stack([gmin, gmax], dim=1).cpu().numpy()
+            dmm = torch.stack([lo.view(N), hi.view(N)], dim=1).cpu().numpy()
+        eng.begin(img_latents, x, guide, masks, gmm, dmm, lr_latent, lr_scaling)
+        eng.run(steps)                       # marigold_dc.py:799-909, no host sync inside
+        denses = eng.decode_final()          # marigold_dc.py:970-984
+        x_out, scales, shifts, losses = eng.get_state()
+        self.last_scales, self.last_shifts, self.last_losses = scales, shifts, losses
+        return denses, x_out
+
+
+def shard_frames(n_frames: int, rank: int, world: int) -> range:
+    """Contiguous frame shard of rank `rank`: frames are independent, weights replicated."""
+    base, rem = divmod(n_frames, world)
+    start = rank * base + min(rank, rem)
+    return range(start, start + base + (1 if rank < rem else 0))

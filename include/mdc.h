@@ -1,0 +1,92 @@
+/* libmdc_b200.so -- C ABI of the B200-native Marigold-DC guided denoising loop.
+ *
+ * Drop-in boundary for the hot path of tier4/depth_completion:
+ *   MarigoldDepthCompletionPipeline.__call__            /root/reference/marigold_dc.py:467-985
+ *     the 50-iteration guided DDIM loop                 marigold_dc.py:799-909
+ *     the final decode + de-normalisation               marigold_dc.py:970-985
+ * The reference has no FFI of its own (it is pure Python over diffusers/torch); the Python class
+ * depth_completion_b200.MarigoldDepthCompletionPipeline keeps the reference's call signature and binds these
+ * entry points with ctypes.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure with the message available from
+ * mdc_last_error() (thread-local).  Pointers are DEVICE pointers unless the name ends in _host.  One handle
+ * owns one device, one stream and all workspace; it is not thread-safe.  The library never frees or keeps
+ * caller memory beyond the call (weights are re-packed into library-owned layouts).
+ */
+#ifndef MDC_H_
+#define MDC_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDC_DTYPE_F32 0
+#define MDC_DTYPE_BF16 1
+#define MDC_MAX_BLOCKS 8
+
+typedef struct mdc_config {
+  int device;                 /* CUDA device ordinal */
+  int n_batch;                /* frames per call (N of imgs [N,C,H,W]), 1..16 */
+  int height, width;          /* input resolution H, W (marigold_dc.py:595) */
+  int proc_h, proc_w;         /* processed size before padding: H*res//max, W*res//max (image processor) */
+  int pad_h, pad_w;           /* replicate padding up to a multiple of 8 (bottom, right) */
+  int steps;                  /* number of DDIM steps (scheduler.set_timesteps, marigold_dc.py:800) */
+  /* UNet2DConditionModel config */
+  int unet_in_ch, unet_out_ch, unet_nblocks, unet_layers_per_block, unet_groups, cross_dim;
+  int unet_block_ch[MDC_MAX_BLOCKS];
+  int unet_heads[MDC_MAX_BLOCKS];
+  int unet_down_attn[MDC_MAX_BLOCKS];
+  /* AutoencoderKL decoder config (Appendix A.2) */
+  int vae_nblocks, vae_layers_per_block, vae_groups, vae_latent_ch;
+  int vae_block_ch[MDC_MAX_BLOCKS];
+  float vae_scaling;          /* 0.18215 */
+} mdc_config;
+
+typedef struct mdc_handle mdc_handle;
+
+const char* mdc_last_error(void);
+
+/* Builds the UNet + VAE-decoder tapes, all launch plans and all workspace for the configured shapes. */
+int mdc_create(const mdc_config* cfg, mdc_handle** out);
+void mdc_destroy(mdc_handle* h);
+
+/* Expected parameters, named by their diffusers state-dict key with a "unet." / "vae." prefix
+ * (SURVEY.md Appendix A.5), e.g. "unet.down_blocks.0.resnets.0.conv1.weight". */
+int mdc_num_weights(mdc_handle* h);
+const char* mdc_weight_key(mdc_handle* h, int i);
+/* Re-packs one parameter (device pointer, contiguous, dtype MDC_DTYPE_*) into the library's layouts. */
+int mdc_set_weight(mdc_handle* h, const char* key, const void* dev_ptr, const long long* shape_host, int ndim,
+                   int dtype);
+
+/* Step-invariant precomputation: DDIM scalars for `timesteps`, the time embedding of every step pushed through
+ * every resnet's time_emb_proj, and the cross-attention K/V of the empty-prompt embedding ctx [1,2,cross_dim] bf16
+ * (marigold_dc.py:664-674, :800).  alphas_cumprod_host has 1000 entries. */
+int mdc_prepare(mdc_handle* h, const void* ctx_bf16, const float* alphas_cumprod_host, const int* timesteps_host,
+                int n_steps);
+
+/* Per-call state (marigold_dc.py:696-789): image latents and initial depth latent [N,4,EH,EW] bf16 NCHW, normalised
+ * sparse depth `guide` [N,1,H,W] fp32 with `mask` [N,1,H,W] uint8, per-sample (min,max) of the masked guide and of the
+ * metric depth range (host, 2 floats per sample), learning rates of the latent and of scale/shift.
+ * Fails if a sample has an empty mask (reference: ValueError from utils.py:132). */
+int mdc_begin(mdc_handle* h, const void* img_latents_bf16, const void* x_bf16, const float* guide, const uint8_t* mask,
+              const float* guide_minmax_host, const float* depth_minmax_host, float lr_latent, float lr_scaling);
+
+/* n guided steps (marigold_dc.py:801-904 each), asynchronous, no host synchronisation inside. */
+int mdc_run(mdc_handle* h, int n_steps);
+
+/* Synchronises and copies out the current latent [N,4,EH,EW] bf16 and, per sample, scale, shift and the last loss
+ * (any pointer may be NULL).  x_out is a device pointer; the float arrays are host pointers. */
+int mdc_get_state(mdc_handle* h, void* x_out_bf16, float* scale_host, float* shift_host, float* loss_host);
+
+/* Final decode + affine + clamp + de-normalisation -> dense [N,1,H,W] fp32 metric depth (marigold_dc.py:970-984). */
+int mdc_decode_final(mdc_handle* h, float* dense_out);
+
+/* Number of kernel launches issued by the handle so far, and bytes of device memory it owns. */
+long long mdc_launch_count(mdc_handle* h);
+long long mdc_device_bytes(mdc_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDC_H_ */
