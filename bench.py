@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native Marigold-DC guided denoising loop (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU under torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  the reference algorithm's CPU path (oracle port) on the host cores
+
+A "step" is ONE GUIDED DDIM STEP of the hot path (marigold_dc.py:801-904): UNet forward, x0 prediction, VAE decode,
+masked L1+L2 loss, backward through decoder and UNet, grad-norm rescale, Adam on latent/scale/shift, DDIM update.
+Workload (config b of BASELINE.json): synthetic 480x640 RGB + 500 sparse points, resolution 768 (latent 72x96), bf16,
+random-init SD2 UNet / VAE.  `value` = guided steps/s over all ranks with every input resident in HBM; `e2e` = the same
+metric through the drop-in pipeline call with pinned HOST inputs and a host copy of the dense output, i.e. whole frames
+(prologue + 50 steps + final decode + copies).  Frames are independent, so ranks shard frames (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(H=480, W=640, resolution=768, n_points=500, frame_steps=50, max_depth=10.0)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=2, help="frames per rank for the e2e measurement")
+    ap.add_argument("--tiny", action="store_true", help="narrow UNet/VAE on a 96x128 frame (debugging only; invalid as a bench)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (nvidia-smi clocks line of B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "app_clocks": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ models / inputs
+def make_models(device, tiny: bool, dtype=torch.bfloat16, seed=1234):
+    """Random-init SD2-derived UNet (in_channels 8) and SD2 VAE; weights created directly on `device`."""
+    from oracle.sd2_modules import (AutoencoderKL, UNet2DConditionModel, UNetConfig, VAEConfig, tiny_unet_config,
+                                    tiny_vae_config)
+    from oracle.marigold_dc import make_empty_text_embedding
+
+    ucfg, vcfg = (tiny_unet_config(), tiny_vae_config()) if tiny else (UNetConfig(), VAEConfig())
+    torch.manual_seed(seed)
+    with torch.device(device):
+        unet, vae = UNet2DConditionModel(ucfg), AutoencoderKL(vcfg)
+    unet, vae = unet.to(dtype).requires_grad_(False), vae.to(dtype).requires_grad_(False)
+    ctx = make_empty_text_embedding(ucfg.cross_attention_dim, device=device, dtype=dtype)
+    return unet, vae, ctx
+
+
+def workload(tiny: bool):
+    w = dict(WORKLOAD)
+    if tiny:
+        w.update(H=96, W=128, resolution=128, n_points=100)
+    return w
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_reference_steps(n_steps: int, warmup: int, sample_res: int, tiny: bool):
+    """Times guided steps of the reference algorithm (oracle port, fp32) on the host cores, on a bounded sample:
+    the same frame at a lower processing resolution, scaled to the full workload by algorithmic FLOPs."""
+    from depth_completion_b200.config import UNetConfig, VAEConfig
+    from depth_completion_b200.flops import step_flops
+    from depth_completion_b200.synthetic import make_frame
+    from oracle.marigold_dc import OraclePipeline
+    from depth_completion_b200.config import unet_config_from, vae_config_from
+
+    w = workload(tiny)
+    unet, vae, ctx = make_models("cpu", tiny, dtype=torch.float32)
+    pipe = OraclePipeline(unet, vae, ctx)
+    fr = make_frame(H=w["H"], W=w["W"], n_points=w["n_points"], max_depth=w["max_depth"])
+    times = []
+
+    def tr(rec):
+        times.append(time.perf_counter())
+
+    t0 = time.perf_counter()
+    pipe(fr["img"], fr["sparse"], fr["max_depth"], steps=w["frame_steps"], resolution=sample_res, trace=tr,
+         max_steps=warmup + n_steps)
+    stamps = [t0] + times
+    dt = stamps[-1] - stamps[warmup]
+    pu, pv = unet_config_from(unet), vae_config_from(vae)
+    f_full = step_flops(pu, pv, w["H"], w["W"], w["resolution"])["step"]
+    f_samp = step_flops(pu, pv, w["H"], w["W"], sample_res)["step"]
+    sample_sps = n_steps / dt
+    return dict(value=sample_sps * f_samp / f_full, sample_steps_per_s=sample_sps, flop_ratio=f_samp / f_full,
+                cores=torch.get_num_threads(), seconds=dt,
+                sample=f"{n_steps} guided step(s) after {warmup} warm-up of the same {w['H']}x{w['W']} frame at "
+                       f"resolution={sample_res} ({f_samp / 1e12:.3f} TFLOP/step vs {f_full / 1e12:.3f}), fp32, "
+                       f"scaled by the FLOP ratio")
+
+
+# ------------------------------------------------------------------------------------------------ main arms
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    w = workload(args.tiny)
+    res = 128 if args.tiny else 224
+    r = cpu_reference_steps(max(1, args.steps), max(0, args.warmup), res, args.tiny)
+    line = {
+        "impl": "reference", "metric": "guided_steps_per_sec", "value": r["value"], "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / r["value"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{w['H']}x{w['W']} RGB + {w['n_points']} sparse points, resolution {w['resolution']}, "
+                               f"{w['frame_steps']}-step guided completion, random-init SD2 UNet/VAE"},
+        "cpu_baseline": {"value": r["value"], "unit": "steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    from depth_completion_b200 import prologue
+    from depth_completion_b200.flops import step_flops
+    from depth_completion_b200.pipeline import MarigoldDepthCompletionPipeline
+    from depth_completion_b200.synthetic import make_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    w = workload(args.tiny)
+    unet, vae, ctx = make_models(dev, args.tiny)
+    pipe = MarigoldDepthCompletionPipeline(unet, vae)
+    pipe.empty_text_embedding = ctx
+    H, W, res, fs = w["H"], w["W"], w["resolution"], w["frame_steps"]
+    # every rank owns its own frames (seed offset by rank): frames are independent
+    fr = make_batch(args.frames, H=H, W=W, n_points=w["n_points"], max_depth=w["max_depth"], seed=100 * rank)
+    imgs_h, sparses_h = fr["img"].pin_memory(), fr["sparse"].pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- one full call: builds the engine for these shapes, packs weights, warms every kernel up
+    dense, _ = pipe(imgs_h[:1].to(dev), sparses_h[:1].to(dev), w["max_depth"], steps=fs, resolution=res)
+    assert torch.isfinite(dense).all()
+    eng = next(iter(pipe._engines.values()))
+
+    # ---- device-resident timing of K guided steps (inputs already in HBM): re-begin a frame, W warm-up, K timed
+    def begin_frame():
+        # the pipeline's own prologue, then the engine is left at step 0 with everything resident
+        pipe(imgs_h[:1].to(dev), sparses_h[:1].to(dev), w["max_depth"], steps=fs, resolution=res, _begin_only=True)
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    begin_frame()
+    done, left_w = 0, args.warmup
+    while left_w > 0:  # warm-up steps
+        n = min(left_w, fs - done)
+        eng.run(n)
+        done += n
+        left_w -= n
+        if done == fs:
+            begin_frame()
+            done = 0
+    total_ms, left = 0.0, args.steps
+    launches0 = eng.launch_count()
+    barrier()
+    with ClockSampler(local) as clk:
+        while left > 0:
+            n = min(left, fs - done)
+            e0.record()
+            eng.run(n)
+            e1.record()
+            e1.synchronize()
+            total_ms += e0.elapsed_time(e1)
+            done += n
+            left -= n
+            if done == fs and left > 0:
+                begin_frame()
+                done = 0
+    barrier()
+    launches = eng.launch_count() - launches0
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = t.item()
+    steps_per_s = world * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end: pinned host inputs -> pipeline call (H2D, prologue, 50 steps, final decode) -> host dense
+    e2e = None
+    if not args.no_e2e:
+        out_h = torch.empty(args.frames, 1, H, W, dtype=torch.float32).pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.frames):
+            img_d = imgs_h[i:i + 1].to(dev, non_blocking=True)
+            sp_d = sparses_h[i:i + 1].to(dev, non_blocking=True)
+            d, _ = pipe(img_d, sp_d, w["max_depth"], steps=fs, resolution=res)
+            out_h[i:i + 1].copy_(d, non_blocking=True)
+        torch.cuda.synchronize()
+        if world > 1:  # gather the dense maps on the device (the only collective, outside the step)
+            gl = [torch.empty_like(d) for _ in range(world)]
+            dist.all_gather(gl, d)
+            torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = dt.item()
+        frames = world * args.frames
+        e2e = {"value": frames * fs / dt, "unit": "steps/s", "frames_per_sec": frames / dt, "sec_per_frame": dt / args.frames,
+               "h2d_bytes_per_step": (imgs_h[0].numel() + sparses_h[0].numel() * 4) / fs,
+               "d2h_bytes_per_step": H * W * 4 / fs}
+
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM / implicit-GEMM conv): FLOPs of its launches in one step
+    #      / the sum of their in-situ durations (CUDA events around every launch of an instrumented step)
+    burst, sustained, hbm, how = peaks()
+    prof = eng.profile_gemm_step()
+    sf = step_flops(pipe.unet_cfg, pipe.vae_cfg, H, W, res)
+    roof = {"bound": "tensor", "kernel": "umma_gemm_kernel", "achieved": prof["tflops"], "peak": sustained,
+            "unit": "TFLOP/s", "frac": prof["tflops"] / sustained, "traffic": None, "peak_source": how + " sustained",
+            "launches_per_step": prof["launches"], "kernel_ms_per_step": prof["ms"], "kernel_flops_per_step": prof["flops"],
+            "step_algorithmic_tflops": sf["step"] / 1e12,
+            "step_frac_of_peak": sf["step"] / 1e12 / (total_ms * 1e-3 / args.steps) / sustained}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            r = cpu_reference_steps(2, 1, 128 if args.tiny else 224, args.tiny)
+            cpu = {"value": r["value"], "unit": "steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        line = {
+            "metric": "guided_steps_per_sec", "value": steps_per_s, "unit": "steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{H}x{W} RGB + {w['n_points']} sparse points, resolution {res} (latent "
+                                   f"{eng.lh}x{eng.lw}), {fs}-step guided completion, 1 frame in flight per GPU, "
+                                   "random-init SD2 UNet (866M) / VAE decoder (49.5M)",
+                       "l2": "per-step working set (activations + 1.8 GB weights) >> 126 MB L2, no flush needed",
+                       "frames_sharding": "independent frames per rank, no collective inside the step"},
+            "frames_per_sec_device": steps_per_s / fs,
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "device_mem_gb": eng.device_bytes() / 2 ** 30,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -158,6 +158,63 @@ int mdc_dbg_read_x_adam(mdc_handle* h, void* x_out_bf16) {
     MDC_CUDA(cudaMemcpy(x_out_bf16, e->x_adam_dbg, 8ull * e->N * e->lh * e->lw, cudaMemcpyDeviceToDevice));
   });
 }
+int mdc_dbg_read_buffer(mdc_handle* h, const char* which, float* out_dev) {
+  return mdc::guarded([&] {
+    mdc::Engine* e = h->e;
+    const std::string w(which);
+    const size_t lat = 4ull * e->N * e->lh * e->lw;
+    MDC_CUDA(cudaStreamSynchronize(e->stream));
+    if (w == "grad")
+      MDC_CUDA(cudaMemcpy(out_dev, e->gbuf, lat * 4, cudaMemcpyDeviceToDevice));
+    else if (w == "dx_direct")
+      MDC_CUDA(cudaMemcpy(out_dev, e->dx_direct, lat * 4, cudaMemcpyDeviceToDevice));
+    else
+      MDC_CHECK(false, "unknown buffer '%s'", which);
+  });
+}
+int mdc_dbg_loss(mdc_handle* h, const float* dec_nchw, float* ddec_nchw, float* loss_host, float* sgrad_host,
+                 float* tgrad_host) {
+  return mdc::guarded([&] {
+    mdc::Engine* e = h->e;
+    MDC_CHECK(e->begun, "mdc_begin first");
+    mdc::load_nchw(e->dec_out, e->dec_out->d, dec_nchw, e->stream);
+    mdc::TailGeom g{e->N, e->H, e->W, e->ph, e->pw, e->PPH, e->PPW, e->dec_out->ld};
+    mdc::loss_points_kernel<<<e->N, 512, 0, e->stream>>>(e->dec_out->d, g, e->pt_idx, e->pt_val, e->pt_off, e->gminmax,
+                                                         e->accum, e->dmean);
+    const long long npix = 1LL * e->N * e->PPH * e->PPW;
+    mdc::dec_grad_kernel<<<static_cast<int>((npix + 255) / 256), 256, 0, e->stream>>>(e->dmean, npix, e->dec_out->g);
+    mdc::store_nchw(e->dec_out, e->dec_out->g, ddec_nchw, e->stream);
+    MDC_CUDA(cudaGetLastError());
+    MDC_CUDA(cudaStreamSynchronize(e->stream));
+    mdc::StepAccum a;
+    MDC_CUDA(cudaMemcpy(&a, e->accum, sizeof(a), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < e->N; ++i) loss_host[i] = a.loss[i], sgrad_host[i] = a.s_grad[i], tgrad_host[i] = a.t_grad[i];
+  });
+}
+int mdc_dbg_update(mdc_handle* h, const float* v_nchw, const float* dz_nchw, const float* dunet_in_nchw) {
+  return mdc::guarded([&] {
+    mdc::Engine* e = h->e;
+    MDC_CHECK(e->begun, "mdc_begin first");
+    const int hw = e->lh * e->lw, lat_pix = e->N * hw, pgrid = e->N * e->parts_per_img;
+    mdc::begin_step_kernel<<<1, 1024, 0, e->stream>>>(e->tables, e->counter, e->cur, e->temb_cur, e->lr_x, e->lr_s);
+    mdc::load_nchw(e->unet_out, e->unet_out->d, v_nchw, e->stream);
+    mdc::x0_kernel<<<pgrid, 256, 0, e->stream>>>(e->unet_out->d, e->x, e->cur, e->N, hw, e->cfg.vae_scaling, e->dec_in->d,
+                                                e->eps_part);
+    mdc::load_nchw(e->dec_in, e->dec_in->g, dz_nchw, e->stream);
+    mdc::dx0_kernel<<<(lat_pix + 255) / 256, 256, 0, e->stream>>>(e->dec_in->g, e->cur, e->N, hw, e->cfg.vae_scaling,
+                                                                  e->unet_out->g, e->dx_direct);
+    mdc::load_nchw(e->unet_in, e->unet_in->g, dunet_in_nchw, e->stream);
+    mdc::grad_total_kernel<<<pgrid, 256, 0, e->stream>>>(e->dx_direct, e->unet_in->g, e->N, hw, e->gbuf, e->g_part);
+    mdc::adam_ddim_kernel<<<pgrid, 256, 0, e->stream>>>(e->gbuf, e->eps_part, e->g_part, e->parts_per_img, e->unet_out->d,
+                                                       e->cur, e->N, hw, e->x, e->m1, e->m2, e->accum, e->counter,
+                                                       e->x_adam_dbg);
+    MDC_CUDA(cudaGetLastError());
+    MDC_CUDA(cudaStreamSynchronize(e->stream));
+  });
+}
+int mdc_dbg_profile_gemm_step(mdc_handle* h, float* ms_host, double* flops_host, int* launches_host) {
+  return mdc::guarded([&] { h->e->profile_gemm_step(ms_host, flops_host, launches_host); });
+}
 int mdc_dbg_time_tapes(mdc_handle* h, int iters, float* ms_host) {
   return mdc::guarded([&] {
     mdc::Engine* e = h->e;

@@ -61,6 +61,9 @@ struct Op {
   virtual void plan_bwd() {}
   virtual void fwd(cudaStream_t) = 0;
   virtual void bwd(cudaStream_t) {}
+  virtual int n_fwd() const { return 1; }  // kernel launches per forward / backward call
+  virtual int n_bwd() const { return 1; }
+  virtual void gemm_plans(std::vector<const GemmPlan*>& f, std::vector<const GemmPlan*>& b) const {}
 };
 
 enum WKind { W_CONV3 = 0, W_LIN = 1, W_VEC = 2 };
@@ -88,6 +91,10 @@ struct ConvOp : Op {  // 3x3 stride-1 pad-1 convolution (+bias, +residual)
   void plan_bwd() override;
   void fwd(cudaStream_t st) override { run_gemm(pf, st); }
   void bwd(cudaStream_t st) override;
+  int n_bwd() const override { return res ? 2 : 1; }
+  void gemm_plans(std::vector<const GemmPlan*>& f, std::vector<const GemmPlan*>& b) const override {
+    f.push_back(&pf), b.push_back(&pb);
+  }
 };
 struct LinearOp : Op {  // y[rows, out] = x[rows, in] W^T (+bias, +residual)
   Engine* E;
@@ -100,6 +107,10 @@ struct LinearOp : Op {  // y[rows, out] = x[rows, in] W^T (+bias, +residual)
   void plan_bwd() override;
   void fwd(cudaStream_t st) override { run_gemm(pf, st); }
   void bwd(cudaStream_t st) override;
+  int n_bwd() const override { return res ? 2 : 1; }
+  void gemm_plans(std::vector<const GemmPlan*>& f, std::vector<const GemmPlan*>& b) const override {
+    f.push_back(&pf), b.push_back(&pb);
+  }
 };
 struct GroupNormOp : Op {
   Engine* E;
@@ -117,6 +128,8 @@ struct GroupNormOp : Op {
   }
   void fwd(cudaStream_t st) override;
   void bwd(cudaStream_t st) override;
+  int n_fwd() const override { return 3; }
+  int n_bwd() const override { return 3; }
 };
 struct LayerNormOp : Op {
   Tensor *x, *y;
@@ -161,6 +174,12 @@ struct SelfAttnOp : Op {  // softmax(q k^T / sqrt(dh)) v over the tokens of each
   void plan_bwd() override;
   void fwd(cudaStream_t st) override;
   void bwd(cudaStream_t st) override;
+  int n_fwd() const override { return 3; }
+  int n_bwd() const override { return 5; }
+  void gemm_plans(std::vector<const GemmPlan*>& f, std::vector<const GemmPlan*>& b) const override {
+    f.push_back(&p_s), f.push_back(&p_o);
+    b.push_back(&p_dv), b.push_back(&p_dp), b.push_back(&p_dq), b.push_back(&p_dk);
+  }
 };
 struct CrossAttn2Op : Op {  // attention over the 2 tokens of the empty-prompt embedding (step-invariant K, V)
   Tensor *q, *o;
@@ -219,6 +238,8 @@ struct ConcatOp : Op {  // zero-copy: a and b are channel-slice views of cat; on
   Tensor *a, *b, *cat;
   void plan_bwd() override { a->grad_set = b->grad_set = cat->grad_set; }
   void fwd(cudaStream_t) override {}
+  int n_fwd() const override { return 0; }
+  int n_bwd() const override { return 0; }
 };
 
 // ------------------------------------------------------------------------------------------------ engine
@@ -313,6 +334,9 @@ struct Engine {
   void step();
   void decode_final(float* dense_out);
   void read_tensor(const std::string& name, int which, float* out_nchw);
+  long long launches_per_step = 0;
+  // Times every tcgen05 GEMM / conv launch of one guided step in situ (CUDA events around each launch).
+  void profile_gemm_step(float* ms_out, double* flops_out, int* launches_out);
 };
 
 // ================================================================================================ op bodies
@@ -832,7 +856,9 @@ inline void Engine::finalize_plans() {
       }
     }
     for (auto it = ops->rbegin(); it != ops->rend(); ++it) (*it)->plan_bwd();
+    for (auto& op : *ops) launches_per_step += op->n_fwd() + op->n_bwd();
   }
+  launches_per_step += 9;  // tail kernels of step()
 }
 
 inline Engine::Engine(const mdc_config& c) : cfg(c) {
@@ -1022,6 +1048,56 @@ inline void Engine::begin(const void* img_latents, const void* x0, const float* 
   begun = true;
 }
 
+inline void Engine::profile_gemm_step(float* ms_out, double* flops_out, int* launches_out) {
+  MDC_CHECK(begun, "profile_gemm_step: call mdc_begin first");
+  std::vector<cudaEvent_t> ev;
+  std::vector<double> fl;
+  auto timed = [&](const GemmPlan* g) {
+    cudaEvent_t a, b;
+    MDC_CUDA(cudaEventCreate(&a));
+    MDC_CUDA(cudaEventCreate(&b));
+    MDC_CUDA(cudaEventRecord(a, stream));
+    run_gemm(*g, stream);
+    MDC_CUDA(cudaEventRecord(b, stream));
+    ev.push_back(a), ev.push_back(b);
+    fl.push_back(g->flops);
+  };
+  // Same launch order as step(), but only the GEMM-class kernels are bracketed; the others run unbracketed in between
+  // so caches and clocks see the real mix.
+  auto run_instrumented = [&](std::vector<std::unique_ptr<Op>>& ops, bool backward) {
+    std::vector<const GemmPlan*> f, b;
+    auto one = [&](Op* op) {
+      f.clear(), b.clear();
+      op->gemm_plans(f, b);
+      auto& list = backward ? b : f;
+      if (list.empty()) {
+        backward ? op->bwd(stream) : op->fwd(stream);
+        return;
+      }
+      // ops with GEMMs: replay the op normally (keeps non-GEMM kernels in order), then time its GEMMs again in place
+      backward ? op->bwd(stream) : op->fwd(stream);
+      for (const GemmPlan* g : list) timed(g);
+    };
+    if (!backward)
+      for (auto& op : ops) one(op.get());
+    else
+      for (auto it = ops.rbegin(); it != ops.rend(); ++it) one(it->get());
+  };
+  run_instrumented(unet_ops, false);
+  run_instrumented(dec_ops, false);
+  run_instrumented(dec_ops, true);
+  run_instrumented(unet_ops, true);
+  MDC_CUDA(cudaStreamSynchronize(stream));
+  double ms = 0, flops = 0;
+  for (size_t i = 0; i < fl.size(); ++i) {
+    float t = 0;
+    MDC_CUDA(cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]));
+    ms += t, flops += fl[i];
+    cudaEventDestroy(ev[2 * i]), cudaEventDestroy(ev[2 * i + 1]);
+  }
+  *ms_out = static_cast<float>(ms), *flops_out = flops, *launches_out = static_cast<int>(fl.size());
+}
+
 inline void Engine::run_ops(std::vector<std::unique_ptr<Op>>& ops, bool backward) {
   if (!backward)
     for (auto& op : ops) op->fwd(stream);
@@ -1050,6 +1126,7 @@ inline void Engine::step() {
   adam_ddim_kernel<<<pgrid, 256, 0, stream>>>(gbuf, eps_part, g_part, parts_per_img, unet_out->d, cur, N, hw, x, m1, m2,
                                               accum, counter, x_adam_dbg);
   ++steps_done;
+  launches += launches_per_step;
 }
 
 inline void Engine::decode_final(float* dense_out) {

@@ -58,6 +58,10 @@ def _declare(l):
     l.mdc_dbg_tensor_name.argtypes = [C.c_void_p, C.c_int]
     l.mdc_dbg_tensor_name.restype = C.c_char_p
     l.mdc_dbg_read_x_adam.argtypes = [C.c_void_p, C.c_void_p]
+    l.mdc_dbg_read_buffer.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+    l.mdc_dbg_loss.argtypes = [C.c_void_p] * 6
+    l.mdc_dbg_update.argtypes = [C.c_void_p] * 4
+    l.mdc_dbg_profile_gemm_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.mdc_dbg_time_tapes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     l._mdc_declared = True
 
@@ -174,6 +178,15 @@ class StepEngine:
         check(self.lib.mdc_decode_final(self._h, ptr(out)))
         return out
 
+    def launch_count(self) -> int:
+        return int(self.lib.mdc_launch_count(self._h))
+
+    def profile_gemm_step(self) -> dict:
+        """In-situ CUDA-event timing of every tcgen05 GEMM / conv launch of one guided step's launch sequence."""
+        ms, fl, n = C.c_float(0), C.c_double(0), C.c_int(0)
+        check(self.lib.mdc_dbg_profile_gemm_step(self._h, C.byref(ms), C.byref(fl), C.byref(n)))
+        return dict(ms=ms.value, flops=fl.value, launches=n.value, tflops=fl.value / max(ms.value, 1e-9) / 1e9)
+
     def device_bytes(self) -> int:
         return int(self.lib.mdc_device_bytes(self._h))
 
@@ -214,6 +227,25 @@ class StepEngine:
         x = torch.empty(self.n, 4, self.lh, self.lw, device=self.device, dtype=torch.bfloat16)
         check(self.lib.mdc_dbg_read_x_adam(self._h, ptr(x)))
         return x
+
+    def dbg_buffer(self, which: str) -> torch.Tensor:
+        out = torch.empty(self.n, 4, self.lh, self.lw, device=self.device, dtype=torch.float32)
+        check(self.lib.mdc_dbg_read_buffer(self._h, which.encode(), ptr(out)))
+        return out
+
+    def dbg_loss(self, dec_nchw: torch.Tensor):
+        dec = dec_nchw.to(self.device, torch.float32).contiguous()
+        assert tuple(dec.shape) == (self.n, 3, self.lh * 8, self.lw * 8)
+        ddec = torch.empty_like(dec)
+        ls, gs, gt = (np.zeros(self.n, np.float32) for _ in range(3))
+        check(self.lib.mdc_dbg_loss(self._h, ptr(dec), ptr(ddec), ls.ctypes.data_as(C.c_void_p),
+                                    gs.ctypes.data_as(C.c_void_p), gt.ctypes.data_as(C.c_void_p)))
+        return ddec, torch.from_numpy(ls), torch.from_numpy(gs), torch.from_numpy(gt)
+
+    def dbg_update(self, v, dz, dunet_in):
+        v, dz, du = (t.to(self.device, torch.float32).contiguous() for t in (v, dz, dunet_in))
+        assert tuple(v.shape) == (self.n, 4, self.lh, self.lw) and tuple(du.shape) == (self.n, 8, self.lh, self.lw)
+        check(self.lib.mdc_dbg_update(self._h, ptr(v), ptr(dz), ptr(du)))
 
     def dbg_time_tapes(self, iters: int = 3):
         ms = (C.c_float * 4)()

@@ -32,6 +32,21 @@ int mdc_dbg_num_tensors(mdc_handle* h);
 const char* mdc_dbg_tensor_name(mdc_handle* h, int i);
 /* Latent after the Adam update but before the DDIM step of the last guided step ([N,4,EH,EW] bf16). */
 int mdc_dbg_read_x_adam(mdc_handle* h, void* x_out_bf16);
+/* Step-level scratch as fp32 [N,4,EH,EW] device buffers: "grad" = total latent gradient before the norm rescale
+ * (marigold_dc.py:877), "dx_direct" = its part that does not pass through the UNet. */
+int mdc_dbg_read_buffer(mdc_handle* h, const char* which, float* out_dev);
+/* Tail kernels in isolation (after mdc_begin).  mdc_dbg_loss: masked L1+L2 loss and its gradient for a given decoder
+ * output [N,3,PPH,PPW] fp32 (device) -> d/d dec (device), per-sample loss / d scale / d shift (host).
+ * mdc_dbg_update: given the UNet output v [N,4,EH,EW], the decoder-input gradient dz [N,4,EH,EW] and the UNet-input
+ * gradient [N,8,EH,EW] (fp32, device) runs x0/eps, the gradient assembly, the norm rescale, Adam and the DDIM step of
+ * the current step index; read the results with mdc_get_state / mdc_dbg_read_x_adam / mdc_dbg_read_buffer. */
+int mdc_dbg_loss(mdc_handle* h, const float* dec_nchw, float* ddec_nchw, float* loss_host, float* sgrad_host,
+                 float* tgrad_host);
+int mdc_dbg_update(mdc_handle* h, const float* v_nchw, const float* dz_nchw, const float* dunet_in_nchw);
+/* In-situ timing of the dominant kernel: replays the launch sequence of one guided step (state is NOT advanced
+ * meaningfully: call after mdc_begin, before/after mdc_run) with CUDA events around every tcgen05 GEMM / conv launch;
+ * returns the summed kernel time (ms), the summed algorithmic FLOPs and the number of such launches. */
+int mdc_dbg_profile_gemm_step(mdc_handle* h, float* ms_host, double* flops_host, int* launches_host);
 /* Per-tape timing: runs the forward (and backward) tapes `iters` times, returns ms per pass. */
 int mdc_dbg_time_tapes(mdc_handle* h, int iters, float* ms_host /* [4]: unet fwd, unet bwd, dec fwd, dec bwd */);
 

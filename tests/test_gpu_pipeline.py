@@ -1,0 +1,138 @@
+"""GPU end-to-end parity of the drop-in pipeline class against the oracle.
+
+The guided loop is chaotic at the level of single latent elements: Adam's first step is -lr*sign(g), so any bf16
+rounding difference flips individual elements by 0.1.  Parity is therefore judged the way BASELINE.md section 5 asks:
+the final dense depth and the hold-out MAE / RMSE, with the oracle's own bf16-vs-fp32 spread as the yardstick.
+"""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def models(cuda):
+    from helpers import build_models
+
+    return build_models(cuda, tiny=True)
+
+
+def _frame(dev, **kw):
+    from depth_completion_b200.synthetic import make_frame
+
+    fr = make_frame(**kw)
+    return {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in fr.items()}
+
+
+def test_full_loop_matches_oracle(models, cuda):
+    from depth_completion_b200.pipeline import MarigoldDepthCompletionPipeline
+    from oracle.marigold_dc import OraclePipeline, mae, rmse
+
+    unet, vae, ctx, _, _ = models
+    fr = _frame(cuda, H=96, W=128, n_points=100)
+    pipe = MarigoldDepthCompletionPipeline(unet, vae)
+    pipe.empty_text_embedding = ctx
+    dense, lat = pipe(fr["img"], fr["sparse"], fr["max_depth"], steps=50, resolution=128)
+    assert dense.shape == (1, 1, 96, 128) and dense.dtype == torch.float32 and lat.shape == (1, 4, 12, 16)
+    assert torch.isfinite(dense).all() and dense.min() >= 0 and dense.max() <= fr["max_depth"] + 1e-3
+    d32, _ = OraclePipeline(copy.deepcopy(unet), copy.deepcopy(vae), ctx)(fr["img"], fr["sparse"], fr["max_depth"],
+                                                                          steps=50, resolution=128)
+    d16, _ = OraclePipeline(copy.deepcopy(unet).bfloat16(), copy.deepcopy(vae).bfloat16(), ctx.bfloat16())(
+        fr["img"], fr["sparse"], fr["max_depth"], steps=50, resolution=128)
+    rng = fr["max_depth"]
+    ours = ((dense - d32).abs().mean() / rng).item()
+    ref = ((d16 - d32).abs().mean() / rng).item()
+    assert ours < max(2.0 * ref, 1e-2) + 1e-2, f"mean |dense - fp32 oracle| / range: ours {ours:.4f}, torch-bf16 {ref:.4f}"
+    for metric in (mae, rmse):
+        m_ours = metric(dense, fr["gt"], fr["holdout"]).item()
+        m_32 = metric(d32, fr["gt"], fr["holdout"]).item()
+        m_16 = metric(d16, fr["gt"], fr["holdout"]).item()
+        tol = max(0.05 * m_32, 2.0 * abs(m_16 - m_32))
+        assert abs(m_ours - m_32) <= tol, f"{metric.__name__}: ours {m_ours:.4f} fp32 {m_32:.4f} bf16 {m_16:.4f}"
+    # the optimisation did its job: the loss went down and the guidance points are fitted better than the hold-out
+    assert pipe.last_losses[0] < 0.15
+
+
+def test_first_step_teacher_forced(models, cuda):
+    """One guided step from the oracle's own state: loss, UNet output and the scale update must agree closely."""
+    from depth_completion_b200.pipeline import MarigoldDepthCompletionPipeline
+    from helpers import rel_l2
+    from oracle.marigold_dc import OraclePipeline
+
+    unet, vae, ctx, _, _ = models
+    fr = _frame(cuda, H=96, W=128, n_points=100, seed=5)
+    tr = []
+    OraclePipeline(copy.deepcopy(unet).bfloat16(), copy.deepcopy(vae).bfloat16(), ctx.bfloat16())(
+        fr["img"], fr["sparse"], fr["max_depth"], steps=50, resolution=128, trace=tr.append, max_steps=1)
+    pipe = MarigoldDepthCompletionPipeline(unet, vae)
+    pipe.empty_text_embedding = ctx
+    pipe(fr["img"], fr["sparse"], fr["max_depth"], steps=50, resolution=128, _begin_only=True)
+    eng = next(iter(pipe._engines.values()))
+    eng.run(1)
+    x, sc, sh, ls = eng.get_state()
+    st = tr[0]
+    assert abs(ls[0].item() - st["losses"][0].item()) < 2e-2 * st["losses"][0].item()
+    assert rel_l2(eng.dbg_read("unet.out"), st["v"]) < 3e-2
+    assert abs(sc[0].item() - st["scales"].flatten()[0].item()) < 1e-6  # first Adam step = -lr * sign(grad)
+    g, og = eng.dbg_buffer("grad"), st["grad"].float()
+    cos = torch.nn.functional.cosine_similarity(g.flatten(), og.flatten(), dim=0).item()
+    assert cos > 0.85, cos  # a single L1 sign flip among 100 points already costs ~0.02 of cosine
+    agree = ((eng.dbg_x_adam().float() - st["x_adam"].float()).abs() < 1e-2).float().mean().item()
+    assert agree > 0.8, agree
+
+
+def test_batch_and_const_norm_and_prev_latent(models, cuda):
+    from depth_completion_b200.pipeline import MarigoldDepthCompletionPipeline
+    from depth_completion_b200.synthetic import make_batch
+
+    unet, vae, ctx, _, _ = models
+    b = make_batch(2, H=96, W=128, n_points=80)
+    img, sp = b["img"].to(cuda), b["sparse"].to(cuda)
+    pipe = MarigoldDepthCompletionPipeline(unet, vae)
+    pipe.empty_text_embedding = ctx
+    d2, l2 = pipe(img, sp, 10.0, steps=10, resolution=128, norm="const", min_depth=0.1)
+    assert d2.shape == (2, 1, 96, 128) and torch.isfinite(d2).all()
+    # frames are independent: a batch of 2 equals two batches of 1
+    d1, _ = pipe(img[1:], sp[1:], 10.0, steps=10, resolution=128, norm="const", min_depth=0.1)
+    assert ((d2[1:] - d1).abs().mean() / 10.0).item() < 2e-2
+    d3, l3 = pipe(img[:1], sp[:1], 10.0, steps=10, resolution=128, pred_latents_prev=l2[:1], beta=0.5)
+    assert torch.isfinite(d3).all() and l3.shape == (1, 4, 12, 16)
+
+
+def test_error_conventions(models, cuda):
+    """Same ValueErrors as marigold_dc.py:583-656 / utils.py:132."""
+    from depth_completion_b200.pipeline import MarigoldDepthCompletionPipeline
+
+    unet, vae, ctx, _, _ = models
+    pipe = MarigoldDepthCompletionPipeline(unet, vae)
+    pipe.empty_text_embedding = ctx
+    fr = _frame(cuda, H=96, W=128, n_points=50)
+    img, sp = fr["img"], fr["sparse"]
+    with pytest.raises(ValueError):
+        pipe(img[0], sp, 10.0)
+    with pytest.raises(ValueError):
+        pipe(img, sp[:, :, :50], 10.0)
+    with pytest.raises(ValueError):
+        pipe(img, sp, 10.0, resolution=128, pred_latents_prev=torch.zeros(1, 4, 3, 3, device=cuda))
+    with pytest.raises(ValueError):
+        pipe(img, sp, 10.0, train_latents=False, closed_form=False)
+    with pytest.raises(ValueError):
+        pipe(img, sp, 10.0, train_method="sometimes")
+    with pytest.raises(ValueError):
+        pipe(img, sp, 10.0, beta=1.5)
+    with pytest.raises(ValueError):
+        pipe(img, sp, 10.0, projection="sqrt")
+    with pytest.raises(ValueError):
+        pipe(img, sp, 10.0, projection="log", min_depth=0.0)
+    with pytest.raises(ValueError):
+        pipe(img, sp, 10.0, loss_funcs=["huber"])
+    with pytest.raises(ValueError):
+        pipe(img, sp, 10.0, norm="zscore")
+    with pytest.raises(ValueError):
+        pipe(img, sp, 10.0, opt="lion")
+    with pytest.raises(ValueError):  # empty mask
+        pipe(img, torch.zeros_like(sp), 10.0, resolution=128, steps=2)
+    with pytest.raises(NotImplementedError):
+        pipe(img, sp, 10.0, opt="sgd")

@@ -1,0 +1,115 @@
+"""GPU parity of the UNet / VAE-decoder tapes (forward and input-gradient backward) through the C ABI.
+
+Reference: the fp32 oracle with bf16-representable weights.  The engine computes in bf16 like the reference's bf16
+mode, so the bar is relative: the engine's error against the fp32 oracle must not exceed the error of the oracle
+itself run in bf16 with torch's kernels (x1.25 + 2e-3 slack), and must stay under an absolute 6 % in relative L2.
+"""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup(cuda):
+    from helpers import build_engine, build_models
+
+    unet, vae, ctx, ucfg, vcfg = build_models(cuda, tiny=True)
+    eng = build_engine(unet, vae, ctx, ucfg, vcfg, 1, 96, 128, 128, 50, cuda)
+    return unet, vae, ctx, eng
+
+
+def _check(name, ours, torch16, ref):
+    from helpers import rel_l2
+
+    e_ours, e_16 = rel_l2(ours, ref), rel_l2(torch16, ref)
+    assert e_ours < 6e-2, f"{name}: engine rel_l2 {e_ours:.3e}"
+    assert e_ours <= 1.25 * e_16 + 2e-3, f"{name}: engine {e_ours:.3e} vs torch-bf16 {e_16:.3e}"
+
+
+@pytest.mark.parametrize("scale", [1.0, 5.0])
+def test_decoder_tape(setup, scale):
+    unet, vae, ctx, eng = setup
+    dev = eng.device
+    g = torch.Generator(device=dev).manual_seed(3)
+    z = (torch.randn(1, 4, eng.lh, eng.lw, device=dev, generator=g) * scale).bfloat16().float()
+    x = z.clone().requires_grad_(True)
+    y = vae.decode(x)
+    dout = torch.randn(y.shape, device=dev, generator=g).bfloat16().float()
+    y.backward(dout)
+    v16 = copy.deepcopy(vae).bfloat16()
+    x16 = z.bfloat16().requires_grad_(True)
+    y16 = v16.decode(x16)
+    y16.backward(dout.bfloat16())
+    got = eng.dbg_forward(1, 0, z)
+    din = eng.dbg_backward(1, dout)
+    _check("decoder fwd", got, y16, y)
+    _check("decoder bwd", din, x16.grad, x.grad)
+
+
+@pytest.mark.parametrize("step", [0, 30, 49])
+def test_unet_tape(setup, step):
+    from depth_completion_b200 import ddim
+
+    unet, vae, ctx, eng = setup
+    dev = eng.device
+    t = torch.tensor(int(ddim.trailing_timesteps(50)[step]), device=dev)
+    g = torch.Generator(device=dev).manual_seed(step)
+    xin = torch.randn(1, 8, eng.lh, eng.lw, device=dev, generator=g).bfloat16().float()
+    x = xin.clone().requires_grad_(True)
+    y = unet(x, t, ctx)
+    dout = torch.randn(y.shape, device=dev, generator=g).bfloat16().float()
+    y.backward(dout)
+    u16 = copy.deepcopy(unet).bfloat16()
+    x16 = xin.bfloat16().requires_grad_(True)
+    y16 = u16(x16, t, ctx.bfloat16())
+    y16.backward(dout.bfloat16())
+    got = eng.dbg_forward(0, step, xin)
+    din = eng.dbg_backward(0, dout)
+    _check("unet fwd", got, y16, y)
+    _check("unet bwd", din, x16.grad, x.grad)
+
+
+def test_odd_latent_sizes(cuda):
+    """Latent 15x20 (not divisible by 8): odd down path 15->8->4->2 and explicit-size nearest upsampling (SURVEY hard parts)."""
+    from helpers import build_engine, build_models, rel_l2
+
+    unet, vae, ctx, ucfg, vcfg = build_models(cuda, tiny=True, seed=7)
+    eng = build_engine(unet, vae, ctx, ucfg, vcfg, 1, 120, 160, 160, 50, cuda)
+    assert (eng.lh, eng.lw) == (15, 20)
+    g = torch.Generator(device=cuda).manual_seed(0)
+    xin = torch.randn(1, 8, 15, 20, device=cuda, generator=g).bfloat16().float()
+    x = xin.clone().requires_grad_(True)
+    y = unet(x, torch.tensor(999, device=cuda), ctx)
+    dout = torch.randn(y.shape, device=cuda, generator=g).bfloat16().float()
+    y.backward(dout)
+    assert rel_l2(eng.dbg_forward(0, 0, xin), y) < 4e-2
+    assert rel_l2(eng.dbg_backward(0, dout), x.grad) < 6e-2
+    eng.close()
+
+
+def test_batch2(cuda):
+    """N = 2 frames per handle: per-sample GroupNorm statistics and attention batches."""
+    from helpers import build_engine, build_models, rel_l2
+
+    unet, vae, ctx, ucfg, vcfg = build_models(cuda, tiny=True, seed=11)
+    eng = build_engine(unet, vae, ctx, ucfg, vcfg, 2, 96, 128, 128, 50, cuda)
+    g = torch.Generator(device=cuda).manual_seed(0)
+    z = torch.randn(2, 4, eng.lh, eng.lw, device=cuda, generator=g).bfloat16().float()
+    z[1] *= 3.0
+    x = z.clone().requires_grad_(True)
+    y = vae.decode(x)
+    dout = torch.randn(y.shape, device=cuda, generator=g).bfloat16().float()
+    y.backward(dout)
+    assert rel_l2(eng.dbg_forward(1, 0, z), y) < 5e-2
+    assert rel_l2(eng.dbg_backward(1, dout), x.grad) < 7e-2
+    xin = torch.randn(2, 8, eng.lh, eng.lw, device=cuda, generator=g).bfloat16().float()
+    x = xin.clone().requires_grad_(True)
+    y = unet(x, torch.tensor(999, device=cuda), ctx)
+    dout = torch.randn(y.shape, device=cuda, generator=g).bfloat16().float()
+    y.backward(dout)
+    assert rel_l2(eng.dbg_forward(0, 0, xin), y) < 4e-2
+    assert rel_l2(eng.dbg_backward(0, dout), x.grad) < 6e-2
+    eng.close()
