@@ -215,6 +215,46 @@ int mdc_dbg_update(mdc_handle* h, const float* v_nchw, const float* dz_nchw, con
 int mdc_dbg_profile_gemm_step(mdc_handle* h, float* ms_host, double* flops_host, int* launches_host) {
   return mdc::guarded([&] { h->e->profile_gemm_step(ms_host, flops_host, launches_host); });
 }
+int mdc_dbg_profile_ops(mdc_handle* h, const char* csv_path, int iters) {
+  return mdc::guarded([&] {
+    mdc::Engine* e = h->e;
+    FILE* f = fopen(csv_path, "w");
+    MDC_CHECK(f != nullptr, "cannot open %s", csv_path);
+    fprintf(f, "tape,idx,name,fwd_us,bwd_us,gemm_gflop_fwd,gemm_gflop_bwd,launches_fwd,launches_bwd\n");
+    cudaEvent_t e0, e1;
+    MDC_CUDA(cudaEventCreate(&e0));
+    MDC_CUDA(cudaEventCreate(&e1));
+    auto time_it = [&](mdc::Op* op, bool bwd) {
+      bwd ? op->bwd(e->stream) : op->fwd(e->stream);
+      MDC_CUDA(cudaEventRecord(e0, e->stream));
+      for (int i = 0; i < iters; ++i) bwd ? op->bwd(e->stream) : op->fwd(e->stream);
+      MDC_CUDA(cudaEventRecord(e1, e->stream));
+      MDC_CUDA(cudaEventSynchronize(e1));
+      MDC_CUDA(cudaGetLastError());
+      float ms = 0;
+      MDC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      return ms * 1e3f / iters;
+    };
+    int t = 0;
+    for (auto* ops : {&e->unet_ops, &e->dec_ops}) {
+      int idx = 0;
+      for (auto& op : *ops) {
+        std::vector<const mdc::GemmPlan*> gf, gb;
+        op->gemm_plans(gf, gb);
+        double ff = 0, fb = 0;
+        for (auto* g : gf) ff += g->flops;
+        for (auto* g : gb) fb += g->flops;
+        float tf = op->n_fwd() ? time_it(op.get(), false) : 0.f;
+        float tb = op->n_bwd() ? time_it(op.get(), true) : 0.f;
+        fprintf(f, "%s,%d,%s,%.2f,%.2f,%.3f,%.3f,%d,%d\n", t == 0 ? "unet" : "dec", idx++, op->name.c_str(), tf, tb,
+                ff / 1e9, fb / 1e9, op->n_fwd(), op->n_bwd());
+      }
+      ++t;
+    }
+    fclose(f);
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+  });
+}
 int mdc_dbg_time_tapes(mdc_handle* h, int iters, float* ms_host) {
   return mdc::guarded([&] {
     mdc::Engine* e = h->e;

@@ -17,6 +17,7 @@
 #include <memory>
 
 #include "../../include/mdc.h"
+#include "flash.cuh"
 #include "gemm.cuh"
 #include "pack.cuh"
 #include "tail.cuh"
@@ -120,7 +121,7 @@ struct GroupNormOp : Op {
   int groups, silu;
   float* stats;
   GNShape s;
-  int threads;
+  int threads, threads_b;
   bool acc = false;
   void plan_bwd() override {
     acc = x->grad_set;
@@ -169,14 +170,17 @@ struct SelfAttnOp : Op {  // softmax(q k^T / sqrt(dh)) v over the tokens of each
   Tensor *qkv, *o;
   int heads, dh, T;
   long long ldS;
-  bf16* P;  // saved probabilities [n, heads, T, ldS]
+  bf16* P;  // saved probabilities [n, heads, T, ldS] (unfused path only)
   GemmPlan p_s, p_o, p_dv, p_dp, p_dq, p_dk;
+  bool use_flash = false;  // head_dim 64: fused tcgen05 flash kernels (flash.cuh); otherwise GEMM + softmax kernels
+  FlashPlan fp;
   void plan_bwd() override;
   void fwd(cudaStream_t st) override;
   void bwd(cudaStream_t st) override;
-  int n_fwd() const override { return 3; }
-  int n_bwd() const override { return 5; }
+  int n_fwd() const override { return use_flash ? 1 : 3; }
+  int n_bwd() const override { return use_flash ? 3 : 5; }
   void gemm_plans(std::vector<const GemmPlan*>& f, std::vector<const GemmPlan*>& b) const override {
+    if (use_flash) return;
     f.push_back(&p_s), f.push_back(&p_o);
     b.push_back(&p_dv), b.push_back(&p_dp), b.push_back(&p_dq), b.push_back(&p_dk);
   }
@@ -331,10 +335,26 @@ struct Engine {
   void begin(const void* img_latents, const void* x0, const float* guide, const uint8_t* mask, const float* gmm,
              const float* dmm, float lrx, float lrs);
   void run_ops(std::vector<std::unique_ptr<Op>>& ops, bool backward);
-  void step();
+  void step_launches();  // the fixed launch sequence of one guided step
+  void step();           // replays it as a CUDA graph (captured once; every step-dependent value lives in device memory)
+  cudaGraphExec_t step_graph = nullptr;
+  bool use_graph = true;
+  ~Engine();
   void decode_final(float* dense_out);
   void read_tensor(const std::string& name, int which, float* out_nchw);
   long long launches_per_step = 0;
+  // split-K: plans with few output tiles and a long K loop share one fp32 partial-sum workspace
+  std::vector<GemmPlan*> split_plans;
+  size_t split_ws_floats = 0;
+  float* split_ws = nullptr;
+  void maybe_split(GemmPlan& g) {
+    if (getenv("MDC_NO_SPLITK")) return;
+    size_t fl = enable_splitk(g, choose_ksplit(g));
+    if (fl) {
+      split_ws_floats = std::max(split_ws_floats, fl);
+      split_plans.push_back(&g);
+    }
+  }
   // Times every tcgen05 GEMM / conv launch of one guided step in situ (CUDA events around each launch).
   void profile_gemm_step(float* ms_out, double* flops_out, int* launches_out);
 };
@@ -346,6 +366,7 @@ inline void ConvOp::plan_bwd() {
   if (x->grad_set) e.res = x->g, e.ldr = x->ld;
   x->grad_set = true;
   pb = plan_conv3x3(y->n, y->h, y->w, y->c, x->c, y->g, y->ld, W->wt, e);
+  E->maybe_split(pb);
   if (res) {
     acc_res = res->grad_set;
     res->grad_set = true;
@@ -364,6 +385,7 @@ inline void LinearOp::plan_bwd() {
   x->grad_set = true;
   Operand A{y->g, 0, y->ld, 0, 0}, B{wt, 0, ld_wt, 0, 0};
   pb = plan_gemm(static_cast<int>(x->rows()), x->c, y->c, A, B, e);
+  E->maybe_split(pb);
   if (res) {
     acc_res = res->grad_set;
     res->grad_set = true;
@@ -378,21 +400,25 @@ inline void LinearOp::bwd(cudaStream_t st) {
 inline void GroupNormOp::fwd(cudaStream_t st) {
   const int grid = s.N * s.blocks_per_img;
   gn_stats_kernel<<<grid, threads, 2 * s.G * sizeof(float), st>>>(x->d, s, E->gn_partial);
-  gn_finalize_kernel<<<(s.N * s.G + 127) / 128, 128, 0, st>>>(E->gn_partial, s.N, s.G, s.blocks_per_img,
+  gn_finalize_kernel<<<(s.N * s.G * 32 + 127) / 128, 128, 0, st>>>(E->gn_partial, s.N, s.G, s.blocks_per_img,
                                                               1.0 * s.HW * (s.C / s.G), eps, 0, stats);
   gn_apply_kernel<<<grid, threads, 0, st>>>(x->d, s, stats, gamma, beta, silu, y->d, y->ld);
 }
 inline void GroupNormOp::bwd(cudaStream_t st) {
   const int grid = s.N * s.blocks_per_img;
-  gn_bwd_stats_kernel<<<grid, threads, 2 * s.G * sizeof(float), st>>>(x->d, y->g, y->ld, s, stats, gamma, beta, silu,
+  gn_bwd_stats_kernel<<<grid, threads_b, 2 * s.G * sizeof(float), st>>>(x->d, y->g, y->ld, s, stats, gamma, beta, silu,
                                                                       E->gn_partial);
-  gn_finalize_kernel<<<(s.N * s.G + 127) / 128, 128, 0, st>>>(E->gn_partial, s.N, s.G, s.blocks_per_img,
+  gn_finalize_kernel<<<(s.N * s.G * 32 + 127) / 128, 128, 0, st>>>(E->gn_partial, s.N, s.G, s.blocks_per_img,
                                                               1.0 * s.HW * (s.C / s.G), 0.f, 1, E->gn_gstats);
-  gn_bwd_apply_kernel<<<grid, threads, 0, st>>>(x->d, y->g, y->ld, s, stats, E->gn_gstats, gamma, beta, silu, x->g, x->ld,
+  gn_bwd_apply_kernel<<<grid, threads_b, 0, st>>>(x->d, y->g, y->ld, s, stats, E->gn_gstats, gamma, beta, silu, x->g, x->ld,
                                                 acc);
 }
 
 inline void SelfAttnOp::plan_bwd() {
+  if (use_flash) {
+    qkv->grad_set = true;
+    return;
+  }
   const int d = heads * dh, n = qkv->n;
   const long long ldq = qkv->ld, tok = 1LL * T * ldq;
   const long long sP0 = 1LL * T * ldS, sP1 = 1LL * heads * T * ldS;
@@ -431,12 +457,20 @@ inline void SelfAttnOp::plan_bwd() {
   qkv->grad_set = true;  // q, k, v slices are each written exactly once
 }
 inline void SelfAttnOp::fwd(cudaStream_t st) {
+  if (use_flash) {
+    run_flash_fwd(fp, st);
+    return;
+  }
   run_gemm(p_s, st);
   const int rows = qkv->n * heads * T;
   softmax_fwd_kernel<<<rows, 256, (((T + 3) & ~3) + 32) * sizeof(float), st>>>(E->attn_S, P, T, ldS);
   run_gemm(p_o, st);
 }
 inline void SelfAttnOp::bwd(cudaStream_t st) {
+  if (use_flash) {
+    run_flash_bwd(fp, st);
+    return;
+  }
   run_gemm(p_dv, st);
   run_gemm(p_dp, st);
   const int rows = qkv->n * heads * T;
@@ -526,6 +560,7 @@ inline Tensor* Engine::conv3x3(Tensor* x, int cout, const std::string& key, Tens
   e.out = y->d, e.ldc = y->ld, e.bias = op->bias;
   if (res) e.res = res->d, e.ldr = res->ld;
   op->pf = plan_conv3x3(x->n, x->h, x->w, x->c, cout, x->d, x->ld, W->w, e);
+  maybe_split(op->pf);
   push(op, key);
   return y;
 }
@@ -542,6 +577,7 @@ inline Tensor* Engine::linear(Tensor* x, int cout, const std::string& key, bool 
   if (res) e.res = res->d, e.ldr = res->ld;
   Operand A{x->d, 0, x->ld, 0, 0}, Bm{W->w, 0, W->ld_w, 0, 0};
   op->pf = plan_gemm(static_cast<int>(x->rows()), cout, x->c, A, Bm, e);
+  maybe_split(op->pf);
   push(op, key);
   return y;
 }
@@ -555,9 +591,10 @@ inline Tensor* Engine::group_norm(Tensor* x, const std::string& key, float eps, 
   op->E = this, op->x = x, op->y = y, op->gamma = ga->vec, op->beta = be->vec, op->eps = eps, op->groups = G;
   op->silu = silu ? 1 : 0;
   const int CV = x->c / 8;
-  MDC_CHECK(CV <= 512, "GroupNorm: C=%d too wide", x->c);
+  MDC_CHECK(CV <= 384, "GroupNorm: C=%d too wide", x->c);
   const int R = std::max(1, 512 / CV);
   op->threads = CV * R;
+  op->threads_b = CV * std::max(1, 384 / CV);
   GNShape s;
   s.N = x->n, s.HW = x->h * x->w, s.C = x->c, s.G = G, s.ld = x->ld;
   int want_blocks = std::max(1, (2 * g_num_sms()) / x->n);
@@ -599,6 +636,15 @@ inline Tensor* Engine::self_attention(Tensor* qkv, int heads, const std::string&
   auto* op = new SelfAttnOp();
   op->E = this, op->qkv = qkv, op->o = o, op->heads = heads, op->dh = dh, op->T = T;
   op->ldS = ((T + 7) / 8) * 8;
+  if (dh == 64 && !getenv("MDC_NO_FLASH")) {
+    op->use_flash = true;
+    float* lse2 = arena.make<float>(static_cast<size_t>(n) * heads * T + 64);
+    float* delta = arena.make<float>(static_cast<size_t>(n) * heads * T + 64);
+    op->fp = plan_flash(n, T, heads, qkv->d, qkv->d + d, qkv->d + 2 * d, qkv->ld, o->d, o->g, o->ld, qkv->g, qkv->g + d,
+                        qkv->g + 2 * d, qkv->ld, lse2, delta);
+    push(op, name);
+    return o;
+  }
   const long long ldS = op->ldS, ldq = qkv->ld, tok = 1LL * T * ldq;
   const long long sP0 = 1LL * T * ldS, sP1 = 1LL * heads * T * ldS;
   op->P = arena.make<bf16>(static_cast<size_t>(n) * heads * T * ldS + 64);
@@ -640,6 +686,7 @@ inline Tensor* Engine::transformer(Tensor* x, int heads, const std::string& key,
     e.out = qkv->d, e.ldc = qkv->ld;
     Operand A{n1->d, 0, n1->ld, 0, 0}, Bm{w, 0, d, 0, 0};
     op->pf = plan_gemm(static_cast<int>(n1->rows()), 3 * d, d, A, Bm, e);
+    maybe_split(op->pf);
     push(op, tb + ".attn1.to_qkv");
   }
   Tensor* ao = self_attention(qkv, heads, tb + ".attn1");
@@ -858,6 +905,9 @@ inline void Engine::finalize_plans() {
     for (auto it = ops->rbegin(); it != ops->rend(); ++it) (*it)->plan_bwd();
     for (auto& op : *ops) launches_per_step += op->n_fwd() + op->n_bwd();
   }
+  split_ws = arena.make<float>(split_ws_floats + 64);
+  for (GemmPlan* g : split_plans) g->p.ws = split_ws;
+  launches_per_step += static_cast<long long>(split_plans.size());
   launches_per_step += 9;  // tail kernels of step()
 }
 
@@ -874,6 +924,8 @@ inline Engine::Engine(const mdc_config& c) : cfg(c) {
   for (int i = 1; i < c.vae_nblocks; ++i) expect *= 2;
   MDC_CHECK(expect == 8, "VAE must upsample by 8 (got %d)", expect);
   MDC_CUDA(cudaSetDevice(c.device));
+  MDC_CUDA(cudaStreamCreate(&stream));  // blocking stream: implicitly ordered with the legacy default stream (torch's)
+  use_graph = getenv("MDC_NO_GRAPH") == nullptr;
   gemm_set_smem_attr();
   MDC_CUDA(cudaFuncSetAttribute(softmax_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   MDC_CUDA(cudaFuncSetAttribute(softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -1105,9 +1157,36 @@ inline void Engine::run_ops(std::vector<std::unique_ptr<Op>>& ops, bool backward
     for (auto it = ops.rbegin(); it != ops.rend(); ++it) (*it)->bwd(stream);
 }
 
+inline Engine::~Engine() {
+  if (step_graph) cudaGraphExecDestroy(step_graph);
+  if (stream) cudaStreamDestroy(stream);
+}
 inline void Engine::step() {
   MDC_CHECK(begun, "mdc_step called before mdc_begin");
   MDC_CHECK(steps_done < cfg.steps, "all %d steps already done", cfg.steps);
+  if (!use_graph) {
+    step_launches();
+  } else {
+    if (!step_graph) {
+      cudaGraph_t graph = nullptr;
+      MDC_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        step_launches();
+      } catch (...) {
+        cudaStreamEndCapture(stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      MDC_CUDA(cudaStreamEndCapture(stream, &graph));
+      MDC_CUDA(cudaGraphInstantiate(&step_graph, graph, 0));
+      cudaGraphDestroy(graph);
+    }
+    MDC_CUDA(cudaGraphLaunch(step_graph, stream));
+  }
+  ++steps_done;
+  launches += launches_per_step;
+}
+inline void Engine::step_launches() {
   const int hw = lh * lw, lat_pix = N * hw;
   const int pgrid = N * parts_per_img;
   TailGeom g{N, H, W, ph, pw, PPH, PPW, dec_out->ld};
@@ -1125,8 +1204,6 @@ inline void Engine::step() {
   grad_total_kernel<<<pgrid, 256, 0, stream>>>(dx_direct, unet_in->g, N, hw, gbuf, g_part);
   adam_ddim_kernel<<<pgrid, 256, 0, stream>>>(gbuf, eps_part, g_part, parts_per_img, unet_out->d, cur, N, hw, x, m1, m2,
                                               accum, counter, x_adam_dbg);
-  ++steps_done;
-  launches += launches_per_step;
 }
 
 inline void Engine::decode_final(float* dense_out) {

@@ -1,0 +1,514 @@
+// Fused self-attention for head_dim 64 on tcgen05 / TMEM, forward and backward (the UNet's attn1 blocks).
+//
+// Replaces the unfused S = QK^T -> softmax -> PV chain (which streams a T x T matrix through HBM) for the
+// reference's F.scaled_dot_product_attention call (diffusers AttnProcessor2_0).
+//
+// All three kernels share one structure: a CTA owns a 128-row tile ("M side"), streams 64-row tiles of the other
+// side through a TMA pipeline, and alternates   MMA group 1 (scores)  ->  128 softmax threads (one per TMEM lane /
+// row)  ->  MMA group 2 (consumes the bf16 probabilities the softmax threads wrote to swizzled shared memory).
+// Everything is single-buffered inside a CTA; two CTAs share an SM (<= 96 KB smem, 256 TMEM columns each) so one
+// CTA's tensor work overlaps the other's exponentials.
+//
+//   flash_fwd_kernel : CTA = 128 queries.  S = Q K^T (N = 64 keys), online softmax in registers, O_tile = P V in TMEM,
+//                      running output in registers; writes O (bf16) and LSE2 = m2 + log2(l) (base-2, scale folded).
+//   flash_dkv_kernel : CTA = 128 keys.  S^T = K Q^T, dP^T = V dO^T, P^T = exp2(S^T c - LSE2[q]),
+//                      dS^T = P^T (dP^T - delta[q]) scale;  dV += P^T dO,  dK += dS^T Q  (TMEM accumulators).
+//   flash_dq_kernel  : CTA = 128 queries.  S = Q K^T, dP = dO V^T, dS likewise;  dQ += dS K.
+//
+// Shared-memory operand tiles are [rows x 64] bf16 = 128-byte rows in the 128B-swizzled UMMA layout: written either
+// by TMA (Q, K, V, dO) or by the softmax threads (P, dS; chunk c of row r lives at chunk c ^ (r & 7)).  A [keys x d]
+// tile serves both as a K-major operand (contraction over d) and as an MN-major operand (contraction over keys).
+#pragma once
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace mdc {
+
+constexpr int FA_THREADS = 192;
+constexpr int FA_STAGES = 2;
+constexpr float FA_LOG2E = 1.4426950408889634f;
+
+struct FlashParams {
+  CUtensorMap tmM1, tmM2;  // the two 128-row resident tiles (box 128 rows)   fwd: Q, -    dkv: K, V    dq: Q, dO
+  CUtensorMap tmS1, tmS2;  // the two streamed 64-row tiles (box 64 rows)     fwd: K, V    dkv: Q, dO   dq: K, V
+  int T, heads;
+  float scale;             // 1/sqrt(head_dim)
+  // outputs / side inputs
+  bf16* out1;              // fwd: O      dkv: dK     dq: dQ
+  bf16* out2;              //             dkv: dV
+  long long ld_out, img_stride_out;  // row stride and per-image stride (elements) of out1/out2 (head h at column h*64)
+  float* lse2;             // [n, heads, T]
+  const float* delta;      // [n, heads, T]
+};
+
+__device__ __forceinline__ void fa_store_row_chunk(uint8_t* tile, int r, int c, const float (&v)[8]) {
+  // 8 bf16 = one 16-byte chunk c of row r in a 128B-swizzled [rows x 64] tile
+  BF8 b = f_to_bf8(v);
+  *reinterpret_cast<BF8*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = b;
+}
+__device__ __forceinline__ void fa_mma_kmajor(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc,
+                                              bool accumulate_first) {
+  // D[128 x 64] (+)= A[128 x 64k] . B[64 x 64k]^T, both K-major
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    ptx::umma_bf16(d_tmem, ptx::make_smem_desc_sw128(a_addr + k * 32, 16, 1024),
+                   ptx::make_smem_desc_sw128(b_addr + k * 32, 16, 1024), idesc, (accumulate_first || k) ? 1u : 0u);
+}
+__device__ __forceinline__ void fa_mma_bmn(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc,
+                                           bool accumulate_first) {
+  // D[128 x 64n] (+)= A[128 x 64k] (K-major) . B[64k rows x 64n] (MN-major: rows are the contraction index)
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    ptx::umma_bf16(d_tmem, ptx::make_smem_desc_sw128(a_addr + k * 32, 16, 1024),
+                   ptx::make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024), idesc, (accumulate_first || k) ? 1u : 0u);
+}
+
+struct FaSmem {
+  uint64_t m_full, s_full[FA_STAGES], s_empty[FA_STAGES], acc_full, acc_empty, p_full, p_empty, o_full, o_empty;
+  uint32_t tmem_slot;
+};
+
+// Common prologue: carve shared memory, init barriers, allocate TMEM.  Layout after the 1 KiB header:
+// [M1 16K][M2 16K][S stages: FA_STAGES x (8K + 8K)][P1 16K][P2 16K]
+struct FaCtx {
+  FaSmem* b;
+  uint8_t *m1, *m2, *st, *p1, *p2;
+  uint32_t tmem;
+  int warp, lane;
+};
+__device__ __forceinline__ FaCtx fa_setup(uint8_t* smem_raw, uint32_t tmem_cols) {
+  FaCtx c;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  c.b = reinterpret_cast<FaSmem*>(smem);
+  c.m1 = smem + 1024, c.m2 = c.m1 + 16384, c.st = c.m2 + 16384;
+  c.p1 = c.st + FA_STAGES * 16384, c.p2 = c.p1 + 16384;
+  c.warp = threadIdx.x >> 5, c.lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&c.b->m_full, 1);
+    for (int i = 0; i < FA_STAGES; ++i) ptx::mbar_init(&c.b->s_full[i], 1), ptx::mbar_init(&c.b->s_empty[i], 1);
+    ptx::mbar_init(&c.b->acc_full, 1), ptx::mbar_init(&c.b->acc_empty, 4);
+    ptx::mbar_init(&c.b->p_full, 4), ptx::mbar_init(&c.b->p_empty, 1);
+    ptx::mbar_init(&c.b->o_full, 1), ptx::mbar_init(&c.b->o_empty, 4);
+    ptx::fence_mbar_init();
+  }
+  if (c.warp == 1) ptx::tmem_alloc(&c.b->tmem_slot, tmem_cols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  c.tmem = c.b->tmem_slot;
+  return c;
+}
+__device__ __forceinline__ void fa_teardown(const FaCtx& c, uint32_t tmem_cols) {
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (c.warp == 1) ptx::tmem_dealloc(c.tmem, tmem_cols);
+}
+// TMA producer shared by the three kernels: the resident tile(s) once, then the streamed pairs.
+__device__ __forceinline__ void fa_producer(const FaCtx& c, const FlashParams& p, int m_row0, int h, int n, int n_iter,
+                                            bool two_m) {
+  ptx::mbar_expect_tx(&c.b->m_full, two_m ? 32768u : 16384u);
+  ptx::tma_load_4d(&p.tmM1, &c.b->m_full, c.m1, 0, m_row0, h, n);
+  if (two_m) ptx::tma_load_4d(&p.tmM2, &c.b->m_full, c.m2, 0, m_row0, h, n);
+  for (int i = 0; i < n_iter; ++i) {
+    const int s = i % FA_STAGES;
+    ptx::mbar_wait(&c.b->s_empty[s], ((i / FA_STAGES) & 1) ^ 1);
+    ptx::mbar_expect_tx(&c.b->s_full[s], 16384u);
+    ptx::tma_load_4d(&p.tmS1, &c.b->s_full[s], c.st + s * 16384, 0, i * 64, h, n);
+    ptx::tma_load_4d(&p.tmS2, &c.b->s_full[s], c.st + s * 16384 + 8192, 0, i * 64, h, n);
+  }
+}
+__device__ __forceinline__ void fa_warp_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) ptx::mbar_arrive(bar);
+}
+
+// ---------------------------------------------------------------------------------------------------- forward
+__global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_constant__ FlashParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t TCOLS = 128;  // S: [0,64)  O tile: [64,128)
+  FaCtx c = fa_setup(smem_raw, TCOLS);
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, n = blockIdx.z;
+  const int n_iter = (p.T + 63) / 64;
+  const uint32_t idesc_s = ptx::make_idesc_bf16(128, 64, 0, 0), idesc_o = ptx::make_idesc_bf16(128, 64, 0, 1);
+  if (c.warp == 0) {
+    if (c.lane == 0) fa_producer(c, p, q0, h, n, n_iter, false);
+    __syncwarp();
+  } else if (c.warp == 1) {
+    if (c.lane == 0) {
+      ptx::mbar_wait(&c.b->m_full, 0);
+      for (int i = 0; i < n_iter; ++i) {
+        const int s = i % FA_STAGES;
+        ptx::mbar_wait(&c.b->s_full[s], (i / FA_STAGES) & 1);
+        ptx::mbar_wait(&c.b->acc_empty, (i & 1) ^ 1);
+        ptx::tc_fence_after();
+        fa_mma_kmajor(c.tmem, ptx::smem_u32(c.m1), ptx::smem_u32(c.st + s * 16384), idesc_s, false);  // S = Q K^T
+        ptx::umma_commit(&c.b->acc_full);
+        ptx::mbar_wait(&c.b->p_full, i & 1);
+        ptx::mbar_wait(&c.b->o_empty, (i & 1) ^ 1);
+        ptx::tc_fence_after();
+        fa_mma_bmn(c.tmem + 64, ptx::smem_u32(c.p1), ptx::smem_u32(c.st + s * 16384 + 8192), idesc_o, false);  // P V
+        ptx::umma_commit(&c.b->o_full);
+        ptx::umma_commit(&c.b->p_empty);
+        ptx::umma_commit(&c.b->s_empty[s]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = c.warp & 3, row = q * 32 + c.lane;
+    const uint32_t t_row = c.tmem + (static_cast<uint32_t>(q * 32) << 16);
+    const float c2 = p.scale * FA_LOG2E;
+    float m = -INFINITY, l = 0.f;
+    float o[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) o[j] = 0.f;
+    for (int i = 0; i < n_iter; ++i) {
+      ptx::mbar_wait(&c.b->acc_full, i & 1);
+      ptx::tc_fence_after();
+      uint32_t raw[64];
+      ptx::tmem_ld32(t_row, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
+      ptx::tmem_ld32(t_row + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      fa_warp_arrive(&c.b->acc_empty, c.lane);
+      const int valid = p.T - i * 64;  // keys of this tile that exist
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        float s = (j < valid) ? __uint_as_float(raw[j]) * c2 : -INFINITY;
+        raw[j] = __float_as_uint(s);
+        mx = fmaxf(mx, s);
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = exp2f(m - m_new);
+      float sum = 0.f;
+      ptx::mbar_wait(&c.b->p_empty, (i & 1) ^ 1);
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = exp2f(__uint_as_float(raw[ch * 8 + j]) - m_new);
+          sum += v[j];
+        }
+        fa_store_row_chunk(c.p1, row, ch, v);
+      }
+      ptx::fence_proxy_async_smem();
+      fa_warp_arrive(&c.b->p_full, c.lane);
+      l = l * alpha + sum;
+      m = m_new;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) o[j] *= alpha;
+      ptx::mbar_wait(&c.b->o_full, i & 1);
+      ptx::tc_fence_after();
+      ptx::tmem_ld32(t_row + 64, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
+      ptx::tmem_ld32(t_row + 96, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      fa_warp_arrive(&c.b->o_empty, c.lane);
+#pragma unroll
+      for (int j = 0; j < 64; ++j) o[j] += __uint_as_float(raw[j]);
+    }
+    if (q0 + row < p.T) {
+      const float inv = 1.f / l;
+      bf16* dst = p.out1 + n * p.img_stride_out + static_cast<long long>(q0 + row) * p.ld_out + h * 64;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = o[ch * 8 + j] * inv;
+        *reinterpret_cast<BF8*>(dst + ch * 8) = f_to_bf8(v);
+      }
+      p.lse2[(static_cast<long long>(n) * p.heads + h) * p.T + q0 + row] = m + log2f(l);
+    }
+  }
+  fa_teardown(c, TCOLS);
+}
+
+// delta[n, h, t] = sum_c dO[n, t, h*64 + c] * O[n, t, h*64 + c]     (one warp per (token, head))
+__global__ void flash_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, long long ld, int N, int T,
+                                   int heads, float* __restrict__ delta) {
+  const long long w = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= 1LL * N * T * heads) return;
+  const int h = w % heads;
+  const long long tok = w / heads;  // n * T + t
+  const long long off = tok * ld + h * 64 + lane * 2;
+  float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + off));
+  float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dout + off));
+  float s = warp_sum(a.x * b.x + a.y * b.y);
+  if (lane == 0) {
+    const long long n = tok / T, t = tok % T;
+    delta[(n * heads + h) * T + t] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- dK, dV
+__global__ void __launch_bounds__(FA_THREADS, 2) flash_dkv_kernel(const __grid_constant__ FlashParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t TCOLS = 256;  // S^T [0,64)  dP^T [64,128)  dV [128,192)  dK [192,256)
+  FaCtx c = fa_setup(smem_raw, TCOLS);
+  const int k0 = blockIdx.x * 128, h = blockIdx.y, n = blockIdx.z;
+  const int n_iter = (p.T + 63) / 64;  // query tiles
+  const uint32_t idesc_k = ptx::make_idesc_bf16(128, 64, 0, 0), idesc_mn = ptx::make_idesc_bf16(128, 64, 0, 1);
+  if (c.warp == 0) {
+    if (c.lane == 0) fa_producer(c, p, k0, h, n, n_iter, true);
+    __syncwarp();
+  } else if (c.warp == 1) {
+    if (c.lane == 0) {
+      ptx::mbar_wait(&c.b->m_full, 0);
+      for (int i = 0; i < n_iter; ++i) {
+        const int s = i % FA_STAGES;
+        const uint32_t q_addr = ptx::smem_u32(c.st + s * 16384), do_addr = q_addr + 8192;
+        ptx::mbar_wait(&c.b->s_full[s], (i / FA_STAGES) & 1);
+        ptx::mbar_wait(&c.b->acc_empty, (i & 1) ^ 1);
+        ptx::tc_fence_after();
+        fa_mma_kmajor(c.tmem, ptx::smem_u32(c.m1), q_addr, idesc_k, false);        // S^T  = K Q^T
+        fa_mma_kmajor(c.tmem + 64, ptx::smem_u32(c.m2), do_addr, idesc_k, false);  // dP^T = V dO^T
+        ptx::umma_commit(&c.b->acc_full);
+        ptx::mbar_wait(&c.b->p_full, i & 1);
+        ptx::tc_fence_after();
+        fa_mma_bmn(c.tmem + 128, ptx::smem_u32(c.p1), do_addr, idesc_mn, i > 0);  // dV += P^T  dO
+        fa_mma_bmn(c.tmem + 192, ptx::smem_u32(c.p2), q_addr, idesc_mn, i > 0);   // dK += dS^T Q
+        ptx::umma_commit(&c.b->p_empty);
+        ptx::umma_commit(&c.b->s_empty[s]);
+      }
+      ptx::umma_commit(&c.b->o_full);  // accumulators final
+    }
+    __syncwarp();
+  } else {
+    const int q = c.warp & 3, row = q * 32 + c.lane;
+    const uint32_t t_row = c.tmem + (static_cast<uint32_t>(q * 32) << 16);
+    const float c2 = p.scale * FA_LOG2E;
+    const float* lse = p.lse2 + (static_cast<long long>(n) * p.heads + h) * p.T;
+    const float* del = p.delta + (static_cast<long long>(n) * p.heads + h) * p.T;
+    for (int i = 0; i < n_iter; ++i) {
+      ptx::mbar_wait(&c.b->acc_full, i & 1);
+      ptx::tc_fence_after();
+      ptx::mbar_wait(&c.b->p_empty, (i & 1) ^ 1);
+      const int qbase = i * 64;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t rs[32], rd[32];
+        ptx::tmem_ld32(t_row + half * 32, rs);
+        ptx::tmem_ld32(t_row + 64 + half * 32, rd);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          float pv[8], dv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int qq = qbase + half * 32 + ch * 8 + j;
+            float pr = 0.f, ds = 0.f;
+            if (qq < p.T) {
+              pr = exp2f(__uint_as_float(rs[ch * 8 + j]) * c2 - __ldg(lse + qq));
+              ds = pr * (__uint_as_float(rd[ch * 8 + j]) - __ldg(del + qq)) * p.scale;
+            }
+            pv[j] = pr, dv[j] = ds;
+          }
+          fa_store_row_chunk(c.p1, row, half * 4 + ch, pv);
+          fa_store_row_chunk(c.p2, row, half * 4 + ch, dv);
+        }
+      }
+      ptx::tc_fence_before();
+      fa_warp_arrive(&c.b->acc_empty, c.lane);
+      ptx::fence_proxy_async_smem();
+      fa_warp_arrive(&c.b->p_full, c.lane);
+    }
+    ptx::mbar_wait(&c.b->o_full, 0);
+    ptx::tc_fence_after();
+    const bool ok = k0 + row < p.T;
+    const long long off = n * p.img_stride_out + static_cast<long long>(k0 + row) * p.ld_out + h * 64;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      bf16* dst = (which == 0 ? p.out2 : p.out1) + off;  // TMEM [128,192) = dV -> out2 ; [192,256) = dK -> out1
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        ptx::tmem_ld32(t_row + 128 + which * 64 + half * 32, r);
+        ptx::tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[ch * 8 + j]);
+            *reinterpret_cast<BF8*>(dst + half * 32 + ch * 8) = f_to_bf8(v);
+          }
+        }
+      }
+    }
+  }
+  fa_teardown(c, TCOLS);
+}
+
+// ---------------------------------------------------------------------------------------------------- dQ
+__global__ void __launch_bounds__(FA_THREADS, 2) flash_dq_kernel(const __grid_constant__ FlashParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t TCOLS = 256;  // S [0,64)  dP [64,128)  dQ [128,192)
+  FaCtx c = fa_setup(smem_raw, TCOLS);
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, n = blockIdx.z;
+  const int n_iter = (p.T + 63) / 64;  // key tiles
+  const uint32_t idesc_k = ptx::make_idesc_bf16(128, 64, 0, 0), idesc_mn = ptx::make_idesc_bf16(128, 64, 0, 1);
+  if (c.warp == 0) {
+    if (c.lane == 0) fa_producer(c, p, q0, h, n, n_iter, true);
+    __syncwarp();
+  } else if (c.warp == 1) {
+    if (c.lane == 0) {
+      ptx::mbar_wait(&c.b->m_full, 0);
+      for (int i = 0; i < n_iter; ++i) {
+        const int s = i % FA_STAGES;
+        const uint32_t k_addr = ptx::smem_u32(c.st + s * 16384), v_addr = k_addr + 8192;
+        ptx::mbar_wait(&c.b->s_full[s], (i / FA_STAGES) & 1);
+        ptx::mbar_wait(&c.b->acc_empty, (i & 1) ^ 1);
+        ptx::tc_fence_after();
+        fa_mma_kmajor(c.tmem, ptx::smem_u32(c.m1), k_addr, idesc_k, false);       // S  = Q  K^T
+        fa_mma_kmajor(c.tmem + 64, ptx::smem_u32(c.m2), v_addr, idesc_k, false);  // dP = dO V^T
+        ptx::umma_commit(&c.b->acc_full);
+        ptx::mbar_wait(&c.b->p_full, i & 1);
+        ptx::tc_fence_after();
+        fa_mma_bmn(c.tmem + 128, ptx::smem_u32(c.p1), k_addr, idesc_mn, i > 0);  // dQ += dS K
+        ptx::umma_commit(&c.b->p_empty);
+        ptx::umma_commit(&c.b->s_empty[s]);
+      }
+      ptx::umma_commit(&c.b->o_full);
+    }
+    __syncwarp();
+  } else {
+    const int q = c.warp & 3, row = q * 32 + c.lane;
+    const uint32_t t_row = c.tmem + (static_cast<uint32_t>(q * 32) << 16);
+    const float c2 = p.scale * FA_LOG2E;
+    const bool ok = q0 + row < p.T;
+    const long long sidx = (static_cast<long long>(n) * p.heads + h) * p.T + q0 + row;
+    const float lse = ok ? p.lse2[sidx] : 0.f, del = ok ? p.delta[sidx] : 0.f;
+    for (int i = 0; i < n_iter; ++i) {
+      ptx::mbar_wait(&c.b->acc_full, i & 1);
+      ptx::tc_fence_after();
+      ptx::mbar_wait(&c.b->p_empty, (i & 1) ^ 1);
+      const int valid = p.T - i * 64;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t rs[32], rd[32];
+        ptx::tmem_ld32(t_row + half * 32, rs);
+        ptx::tmem_ld32(t_row + 64 + half * 32, rd);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          float dv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int kk = half * 32 + ch * 8 + j;
+            float ds = 0.f;
+            if (kk < valid && ok) {
+              const float pr = exp2f(__uint_as_float(rs[ch * 8 + j]) * c2 - lse);
+              ds = pr * (__uint_as_float(rd[ch * 8 + j]) - del) * p.scale;
+            }
+            dv[j] = ds;
+          }
+          fa_store_row_chunk(c.p1, row, half * 4 + ch, dv);
+        }
+      }
+      ptx::tc_fence_before();
+      fa_warp_arrive(&c.b->acc_empty, c.lane);
+      ptx::fence_proxy_async_smem();
+      fa_warp_arrive(&c.b->p_full, c.lane);
+    }
+    ptx::mbar_wait(&c.b->o_full, 0);
+    ptx::tc_fence_after();
+    bf16* dst = p.out1 + n * p.img_stride_out + static_cast<long long>(q0 + row) * p.ld_out + h * 64;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r[32];
+      ptx::tmem_ld32(t_row + 128 + half * 32, r);
+      ptx::tmem_ld_wait();
+      if (ok) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[ch * 8 + j]);
+          *reinterpret_cast<BF8*>(dst + half * 32 + ch * 8) = f_to_bf8(v);
+        }
+      }
+    }
+  }
+  fa_teardown(c, TCOLS);
+}
+
+// ======================================================================================= host side
+constexpr int FA_SMEM = 1024 + 2 * 16384 + FA_STAGES * 16384 + 2 * 16384 + 1024;  // + alignment slack
+
+struct FlashPlan {
+  FlashParams fwd, dkv, dq;
+  dim3 grid;
+  // delta kernel
+  const bf16 *o, *dout;
+  long long ld_o;
+  int N, T, heads;
+  float* delta;
+  double flops_fwd = 0, flops_bwd = 0;
+};
+
+inline CUtensorMap fa_map(const bf16* base, long long ld, int T, int heads, int n, int box_rows) {
+  uint64_t dims[4] = {64, (uint64_t)T, (uint64_t)heads, (uint64_t)n};
+  uint64_t str[3] = {(uint64_t)ld, 64, (uint64_t)T * ld};
+  uint32_t box[4] = {64, (uint32_t)box_rows, 1, 1};
+  return make_tmap_bf16(base, dims, str, box);
+}
+
+// q, k, v (and their gradients dq, dk, dv) are column slices of [n, T, ld_qkv] tensors; o / dout of [n, T, ld_o].
+inline FlashPlan plan_flash(int n, int T, int heads, const bf16* q, const bf16* k, const bf16* v, long long ld_qkv, bf16* o,
+                            const bf16* dout, long long ld_o, bf16* dq, bf16* dk, bf16* dv, long long ld_dqkv, float* lse2,
+                            float* delta) {
+  FlashPlan f;
+  memset(&f.fwd, 0, sizeof(FlashParams));
+  f.grid = dim3((T + 127) / 128, heads, n);
+  FlashParams base;
+  memset(&base, 0, sizeof(base));
+  base.T = T, base.heads = heads, base.scale = 0.125f, base.lse2 = lse2, base.delta = delta;
+  f.fwd = base;
+  f.fwd.tmM1 = fa_map(q, ld_qkv, T, heads, n, 128);
+  f.fwd.tmM2 = f.fwd.tmM1;
+  f.fwd.tmS1 = fa_map(k, ld_qkv, T, heads, n, 64);
+  f.fwd.tmS2 = fa_map(v, ld_qkv, T, heads, n, 64);
+  f.fwd.out1 = o, f.fwd.ld_out = ld_o, f.fwd.img_stride_out = 1LL * T * ld_o;
+  f.dkv = base;
+  f.dkv.tmM1 = fa_map(k, ld_qkv, T, heads, n, 128);
+  f.dkv.tmM2 = fa_map(v, ld_qkv, T, heads, n, 128);
+  f.dkv.tmS1 = fa_map(q, ld_qkv, T, heads, n, 64);
+  f.dkv.tmS2 = fa_map(dout, ld_o, T, heads, n, 64);
+  f.dkv.out1 = dk, f.dkv.out2 = dv, f.dkv.ld_out = ld_dqkv, f.dkv.img_stride_out = 1LL * T * ld_dqkv;
+  f.dq = base;
+  f.dq.tmM1 = fa_map(q, ld_qkv, T, heads, n, 128);
+  f.dq.tmM2 = fa_map(dout, ld_o, T, heads, n, 128);
+  f.dq.tmS1 = fa_map(k, ld_qkv, T, heads, n, 64);
+  f.dq.tmS2 = fa_map(v, ld_qkv, T, heads, n, 64);
+  f.dq.out1 = dq, f.dq.ld_out = ld_dqkv, f.dq.img_stride_out = 1LL * T * ld_dqkv;
+  f.o = o, f.dout = dout, f.ld_o = ld_o, f.N = n, f.T = T, f.heads = heads, f.delta = delta;
+  f.flops_fwd = 4.0 * T * T * 64.0 * heads * n;
+  f.flops_bwd = f.flops_fwd;  // counted 1 x forward like every other backward
+  return f;
+}
+
+inline void flash_set_attrs() {
+  static bool done = false;
+  if (done) return;
+  MDC_CUDA(cudaFuncSetAttribute(flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+  MDC_CUDA(cudaFuncSetAttribute(flash_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+  MDC_CUDA(cudaFuncSetAttribute(flash_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+  done = true;
+}
+inline void run_flash_fwd(const FlashPlan& f, cudaStream_t st) {
+  flash_set_attrs();
+  flash_fwd_kernel<<<f.grid, FA_THREADS, FA_SMEM, st>>>(f.fwd);
+}
+inline void run_flash_bwd(const FlashPlan& f, cudaStream_t st) {
+  flash_set_attrs();
+  const long long warps = 1LL * f.N * f.T * f.heads;
+  flash_delta_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, st>>>(f.o, f.dout, f.ld_o, f.N, f.T, f.heads,
+                                                                                f.delta);
+  flash_dkv_kernel<<<f.grid, FA_THREADS, FA_SMEM, st>>>(f.dkv);
+  flash_dq_kernel<<<f.grid, FA_THREADS, FA_SMEM, st>>>(f.dq);
+}
+
+}  // namespace mdc

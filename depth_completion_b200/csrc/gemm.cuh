@@ -55,16 +55,23 @@ struct GemmParams {
   const __nv_bfloat16* res;
   long long ldr, sr0, sr1;
   float alpha;
+  // split-K (nb0 = nb1 = 1 only): CTA (tile, s) accumulates k-chunks [s*kc_per_split, ...) and writes its raw fp32
+  // partial to ws[s][row][col]; splitk_reduce_kernel sums the partials and applies the epilogue.
+  int ksplit, kc_per_split;
+  float* ws;
+  long long ws_ld, ws_split_stride;
 };
 
+// tile -> (n_tile, m_tile, b0, b1); with split-K the batch slot b0 carries the split index instead.
 __device__ __forceinline__ void gemm_decode_tile(const GemmParams& p, int tile, int& n_tile, int& m_tile, int& b0,
                                                  int& b1) {
   n_tile = tile % p.n_tiles;
   int rest = tile / p.n_tiles;
   m_tile = rest % p.m_tiles;
   int b = rest / p.m_tiles;
-  b0 = b % p.nb0;
-  b1 = b / p.nb0;
+  const int nb0 = p.ksplit > 1 ? p.ksplit : p.nb0;
+  b0 = b % nb0;
+  b1 = b / nb0;
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
@@ -82,7 +89,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles * p.nb0 * p.nb1;
+  const int total_tiles = p.m_tiles * p.n_tiles * (p.ksplit > 1 ? p.ksplit : p.nb0) * p.nb1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) {
@@ -121,7 +128,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
           h0 = th * p.BH;
           w0 = tw * p.BW;
         }
-        for (int kc = 0; kc < p.num_k_chunks; ++kc) {
+        int kc_begin = 0, kc_end = p.num_k_chunks;
+        if (p.ksplit > 1) {
+          kc_begin = b0 * p.kc_per_split, kc_end = min(p.num_k_chunks, kc_begin + p.kc_per_split);
+          b0 = 0;
+        }
+        for (int kc = kc_begin; kc < kc_end; ++kc) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           ptx::mbar_expect_tx(&full_bar[stage], p.bytesA + p.bytesB);
           uint8_t* a_dst = sA + stage * GEMM_A_STAGE;
@@ -168,7 +180,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
         ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * 256u;
-        for (int kc = 0; kc < p.num_k_chunks; ++kc) {
+        int nkc = p.num_k_chunks;
+        if (p.ksplit > 1) {
+          int n_tile, m_tile, b0, b1;
+          gemm_decode_tile(p, tile, n_tile, m_tile, b0, b1);
+          nkc = min(p.num_k_chunks, (b0 + 1) * p.kc_per_split) - b0 * p.kc_per_split;
+        }
+        for (int kc = 0; kc < nkc; ++kc) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(sA + stage * GEMM_A_STAGE);
@@ -222,6 +240,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
         off_c = b0 * p.sc0 + b1 * p.sc1 + static_cast<long long>(m) * p.ldc;
         off_r = b0 * p.sr0 + b1 * p.sr1 + static_cast<long long>(m) * p.ldr;
       }
+      // epilogue operands (split-K partials go to the fp32 workspace, raw)
+      void* e_out = p.out;
+      int e_f32 = p.out_f32, e_vec = p.vec_ok;
+      const float *e_bias = p.bias, *e_bias_img = p.bias_img;
+      const __nv_bfloat16* e_res = p.res;
+      float e_alpha = p.alpha;
+      if (p.ksplit > 1) {
+        e_out = p.ws + b0 * p.ws_split_stride;
+        off_c = (off_c / p.ldc) * p.ws_ld;  // same row index, workspace row stride
+        e_f32 = 1, e_vec = 1, e_bias = nullptr, e_bias_img = nullptr, e_res = nullptr, e_alpha = 1.f;
+      }
       ptx::mbar_wait(&tfull_bar[as], aphase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as) * 256u;
@@ -233,27 +262,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
         if (valid && col0 < p.N) {
           float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
-          const bool full = (col0 + 16 <= p.N) && p.vec_ok;
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * e_alpha;
+          const bool full = (col0 + 16 <= p.N) && e_vec;
           if (full) {
-            if (p.bias) {
-              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+            if (e_bias) {
+              const float4* b4 = reinterpret_cast<const float4*>(e_bias + col0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 float4 b = __ldg(b4 + j);
                 v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
               }
             }
-            if (p.bias_img) {
-              const float4* b4 = reinterpret_cast<const float4*>(p.bias_img + static_cast<long long>(img) * p.N + col0);
+            if (e_bias_img) {
+              const float4* b4 = reinterpret_cast<const float4*>(e_bias_img + static_cast<long long>(img) * p.N + col0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 float4 b = __ldg(b4 + j);
                 v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
               }
             }
-            if (p.res) {
-              const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off_r + col0);
+            if (e_res) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(e_res + off_r + col0);
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
                 uint4 r = r4[j];
@@ -266,12 +295,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
                 }
               }
             }
-            if (p.out_f32) {
-              float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(p.out) + off_c + col0);
+            if (e_f32) {
+              float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(e_out) + off_c + col0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             } else {
-              uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off_c + col0);
+              uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(e_out) + off_c + col0);
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
                 uint4 o;
@@ -286,13 +315,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
               const int col = col0 + j;
               if (col >= p.N) break;
               float x = v[j];
-              if (p.bias) x += p.bias[col];
-              if (p.bias_img) x += p.bias_img[static_cast<long long>(img) * p.N + col];
-              if (p.res) x += __bfloat162float(p.res[off_r + col]);
-              if (p.out_f32)
-                static_cast<float*>(p.out)[off_c + col] = x;
+              if (e_bias) x += e_bias[col];
+              if (e_bias_img) x += e_bias_img[static_cast<long long>(img) * p.N + col];
+              if (e_res) x += __bfloat162float(e_res[off_r + col]);
+              if (e_f32)
+                static_cast<float*>(e_out)[off_c + col] = x;
               else
-                static_cast<__nv_bfloat16*>(p.out)[off_c + col] = __float2bfloat16(x);
+                static_cast<__nv_bfloat16*>(e_out)[off_c + col] = __float2bfloat16(x);
             }
           }
         }
@@ -390,7 +419,36 @@ struct GemmPlan {
   int grid = 0;
   int smem = 0;
   double flops = 0;
+  long long rows = 0;  // output rows (pixels / tokens) -- used by the split-K reduction
 };
+
+// out[row, col] = alpha * sum_s ws[s][row][col] (+bias) (+bias_img) (+res) -> bf16 / fp32.  Rows are final output rows.
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int ksplit, long long split_stride, long long ws_ld,
+                                     long long rows, int N, void* __restrict__ out, int out_f32, long long ldc,
+                                     const float* __restrict__ bias, const __nv_bfloat16* __restrict__ res,
+                                     long long ldr, float alpha) {
+  const int nv = (N + 3) >> 2;
+  const long long total = rows * nv;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const long long r = i / nv;
+    const int c = static_cast<int>(i % nv) * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < ksplit; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(ws + s * split_stride + r * ws_ld + c);
+      a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+    }
+    float v[4] = {a.x * alpha, a.y * alpha, a.z * alpha, a.w * alpha};
+    for (int j = 0; j < 4 && c + j < N; ++j) {
+      float x = v[j];
+      if (bias) x += bias[c + j];
+      if (res) x += __bfloat162float(res[r * ldr + c + j]);
+      if (out_f32)
+        static_cast<float*>(out)[r * ldc + c + j] = x;
+      else
+        static_cast<__nv_bfloat16*>(out)[r * ldc + c + j] = __float2bfloat16(x);
+    }
+  }
+}
 
 inline int pick_bn(int N) {
   // largest multiple of 16 that is <= 256 and divides N; otherwise min(256, roundup16(N)).
@@ -419,7 +477,7 @@ inline void finish_plan(GemmPlan& g) {
   p.stages = stages;
   g.smem = 2048 + stages * (GEMM_A_STAGE + b_stage);
   p.idesc = ptx::make_idesc_bf16(GEMM_BM, p.BN, p.a_mn, p.b_mn);
-  long long total = 1LL * p.m_tiles * p.n_tiles * p.nb0 * p.nb1;
+  long long total = 1LL * p.m_tiles * p.n_tiles * (p.ksplit > 1 ? p.ksplit : p.nb0) * p.nb1;
   g.grid = static_cast<int>(std::min<long long>(total, g_num_sms()));
   const uintptr_t o = reinterpret_cast<uintptr_t>(p.out), r = reinterpret_cast<uintptr_t>(p.res);
   bool ok = (o % 16 == 0) && (p.ldc % 8 == 0) && (p.sc0 % 8 == 0) && (p.sc1 % 8 == 0) && (p.N % 8 == 0);
@@ -471,6 +529,7 @@ inline GemmPlan plan_gemm(int M, int N, int K, const Operand& A, const Operand& 
   fill_epilogue(p, e);
   finish_plan(g);
   g.flops = 2.0 * M * N * K * nb0 * nb1;
+  g.rows = M;
   return g;
 }
 
@@ -527,6 +586,7 @@ inline GemmPlan plan_conv3x3(int NB, int H, int W, int C, int Cout, const void* 
   fill_epilogue(p, e);
   finish_plan(g);
   g.flops = 2.0 * NB * H * W * 9.0 * C * Cout;
+  g.rows = 1LL * NB * H * W;
   return g;
 }
 
@@ -538,9 +598,41 @@ inline void gemm_set_smem_attr() {
   }
 }
 
+// Decide on split-K for a finished plan: few output tiles, long K loop.  `ws` must hold ws_floats(plan) floats.
+inline int choose_ksplit(const GemmPlan& g) {
+  const GemmParams& p = g.p;
+  if (p.nb0 != 1 || p.nb1 != 1 || p.bias_img || p.out_f32) return 1;
+  const int tiles = p.m_tiles * p.n_tiles;
+  if (tiles * 2 > g_num_sms() || p.num_k_chunks < 8) return 1;
+  int ks = (g_num_sms() + tiles - 1) / tiles;
+  ks = std::min(ks, p.num_k_chunks / 4);
+  return std::max(ks, 1);
+}
+inline size_t enable_splitk(GemmPlan& g, int ksplit) {  // returns the workspace size in floats
+  GemmParams& p = g.p;
+  if (ksplit <= 1) return 0;
+  p.kc_per_split = (p.num_k_chunks + ksplit - 1) / ksplit;
+  p.ksplit = (p.num_k_chunks + p.kc_per_split - 1) / p.kc_per_split;
+  if (p.ksplit <= 1) {
+    p.ksplit = 0;
+    return 0;
+  }
+  p.ws_ld = ((p.N + 15) / 16) * 16;
+  p.ws_split_stride = g.rows * p.ws_ld;
+  g.grid = std::min(p.m_tiles * p.n_tiles * p.ksplit, g_num_sms());
+  return static_cast<size_t>(p.ksplit) * p.ws_split_stride;
+}
+
 inline void run_gemm(const GemmPlan& g, cudaStream_t st) {
   gemm_set_smem_attr();
   umma_gemm_kernel<<<g.grid, GEMM_THREADS, g.smem + 1024, st>>>(g.p);
+  if (g.p.ksplit > 1) {
+    const GemmParams& p = g.p;
+    const long long work = g.rows * ((p.N + 3) / 4);
+    const int grid = static_cast<int>(std::min<long long>((work + 255) / 256, 148 * 8));
+    splitk_reduce_kernel<<<grid, 256, 0, st>>>(p.ws, p.ksplit, p.ws_split_stride, p.ws_ld, g.rows, p.N, p.out, p.out_f32,
+                                               p.ldc, p.bias, p.res, p.ldr, p.alpha);
+  }
 }
 
 }  // namespace mdc

@@ -77,7 +77,10 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 // =========================================================================== GroupNorm
 // Thread layout shared by all GroupNorm kernels: blockDim = CV * R (CV = C/8 channel vectors per pixel),
 // thread -> (cv = tid % CV, r = tid / CV); each block walks `pix_per_block` pixels of one image.  A thread's
-// channel vector, hence the groups of its 4 channel pairs, is fixed, so statistics accumulate in registers.
+// channel vector, hence the groups of its 4 channel pairs, is fixed, so statistics accumulate in registers and the
+// per-group constants are loaded once.  Loops are unrolled by GN_UNROLL pixels so every thread keeps several
+// independent 16-byte loads in flight (these kernels are pure HBM streams).
+constexpr int GN_UNROLL = 4;
 struct GNShape {
   int N, HW, C, G;
   long long ld;        // pixel stride of x / y (elements)
@@ -86,7 +89,8 @@ struct GNShape {
 };
 
 // pass 1 of forward: per-block partial (sum, sumsq) per group -> partial[(n*bpi + b)*G*2 + g*2 + {0,1}]
-__global__ void gn_stats_kernel(const bf16* __restrict__ x, GNShape s, float* __restrict__ partial) {
+__global__ void __launch_bounds__(512, 2) gn_stats_kernel(const bf16* __restrict__ x, GNShape s,
+                                                          float* __restrict__ partial) {
   extern __shared__ float sh[];  // 2*G
   const int CV = s.C >> 3, cpg = s.C / s.G;
   const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
@@ -96,14 +100,21 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, GNShape s, float* __
   float sum[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
   const int p0 = b * s.pix_per_block, p1 = min(s.HW, p0 + s.pix_per_block);
   const bf16* base = x + (1LL * n * s.HW) * s.ld + cv * 8;
-  for (int p = p0 + r; p < p1; p += R) {
-    BF8 v = *reinterpret_cast<const BF8*>(base + 1LL * p * s.ld);
+  for (int p = p0 + r; p < p1; p += R * GN_UNROLL) {
+    BF8 v[GN_UNROLL];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float2 t = __bfloat1622float2(v.v[i]);
-      sum[i] += t.x + t.y;
-      sq[i] += t.x * t.x + t.y * t.y;
-    }
+    for (int u = 0; u < GN_UNROLL; ++u)
+      if (p + u * R < p1) v[u] = *reinterpret_cast<const BF8*>(base + 1LL * (p + u * R) * s.ld);
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u)
+      if (p + u * R < p1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float2 t = __bfloat1622float2(v[u].v[i]);
+          sum[i] += t.x + t.y;
+          sq[i] += t.x * t.x + t.y * t.y;
+        }
+      }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -115,18 +126,24 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, GNShape s, float* __
   for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) partial[1LL * blockIdx.x * 2 * s.G + i] = sh[i];
 }
 
-// Reduce the per-block partials in a fixed order (deterministic), in double.  mode 0: (sum, sumsq) -> (mean, rstd);
-// mode 1: plain sums scaled by 1/m (used by the backward pass).
+// Reduce the per-block partials in a fixed order (deterministic), in double: one warp per (n, group).
+// mode 0: (sum, sumsq) -> (mean, rstd);  mode 1: plain sums scaled by 1/m (used by the backward pass).
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int N, int G, int bpi, double m, float eps,
                                    int mode, float* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= N * G) return;
-  int n = i / G, g = i % G;
+  const int n = i / G, g = i % G;
   double a = 0, b = 0;
-  for (int k = 0; k < bpi; ++k) {
-    const float* p = partial + (1LL * (n * bpi + k) * G + g) * 2;
-    a += p[0], b += p[1];
+  for (int k = lane; k < bpi; k += 32) {
+    const float2 p = *reinterpret_cast<const float2*>(partial + (1LL * (n * bpi + k) * G + g) * 2);
+    a += p.x, b += p.y;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane) return;
   if (mode == 0) {
     double mean = a / m, var = b / m - mean * mean;
     if (var < 0) var = 0;
@@ -139,9 +156,11 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int N, int
 }
 
 // pass 2 of forward: y = act((x - mean) * rstd * gamma + beta)
-__global__ void gn_apply_kernel(const bf16* __restrict__ x, GNShape s, const float* __restrict__ stats,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
-                                bf16* __restrict__ y, long long ldy) {
+__global__ void __launch_bounds__(512, 2) gn_apply_kernel(const bf16* __restrict__ x, GNShape s,
+                                                          const float* __restrict__ stats,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, int silu,
+                                                          bf16* __restrict__ y, long long ldy) {
   const int CV = s.C >> 3, cpg = s.C / s.G;
   const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
   const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
@@ -156,53 +175,88 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, GNShape s, const flo
   const int p0 = b * s.pix_per_block, p1 = min(s.HW, p0 + s.pix_per_block);
   const bf16* xb = x + (1LL * n * s.HW) * s.ld + cv * 8;
   bf16* yb = y + (1LL * n * s.HW) * ldy + cv * 8;
-  for (int p = p0 + r; p < p1; p += R) {
-    BF8 v = *reinterpret_cast<const BF8*>(xb + 1LL * p * s.ld);
-    float f[8];
-    bf8_to_f(v, f);
+  for (int p = p0 + r; p < p1; p += R * GN_UNROLL) {
+    BF8 v[GN_UNROLL];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float h = f[i] * sc[i] + sf[i];
-      f[i] = silu ? siluf_(bf16r(h)) : h;
-    }
-    *reinterpret_cast<BF8*>(yb + 1LL * p * ldy) = f_to_bf8(f);
+    for (int u = 0; u < GN_UNROLL; ++u)
+      if (p + u * R < p1) v[u] = *reinterpret_cast<const BF8*>(xb + 1LL * (p + u * R) * s.ld);
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u)
+      if (p + u * R < p1) {
+        float f[8];
+        bf8_to_f(v[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float h = f[i] * sc[i] + sf[i];
+          f[i] = silu ? siluf_(bf16r(h)) : h;
+        }
+        *reinterpret_cast<BF8*>(yb + 1LL * (p + u * R) * ldy) = f_to_bf8(f);
+      }
   }
 }
 
+// Per-thread constants of the backward kernels: group statistics per channel PAIR (a pair never straddles a group
+// because channels-per-group is even), affine parameters per channel.
+struct GNBwdConst {
+  float mean[4], rstd[4], ga[8], be[8];
+};
+__device__ __forceinline__ void gn_load_const(GNBwdConst& k, const GNShape& s, int n, int cv,
+                                              const float* __restrict__ stats, const float* __restrict__ gamma,
+                                              const float* __restrict__ beta) {
+  const int cpg = s.C / s.G;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int g = (cv * 8 + 2 * i) / cpg;
+    k.mean[i] = stats[2 * (n * s.G + g)], k.rstd[i] = stats[2 * (n * s.G + g) + 1];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) k.ga[i] = gamma[cv * 8 + i], k.be[i] = beta[cv * 8 + i];
+}
+
 // backward pass 1: per-block partial (sum dxhat, sum dxhat*xhat) per group, dxhat = dy * act'(h) * gamma
-__global__ void gn_bwd_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, long long lddy, GNShape s,
-                                    const float* __restrict__ stats, const float* __restrict__ gamma,
-                                    const float* __restrict__ beta, int silu, float* __restrict__ partial) {
+__global__ void __launch_bounds__(384, 2) gn_bwd_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                                              long long lddy, GNShape s,
+                                                              const float* __restrict__ stats,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, int silu,
+                                                              float* __restrict__ partial) {
   extern __shared__ float sh[];
   const int CV = s.C >> 3, cpg = s.C / s.G;
   const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
   const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
   for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
-  float mean[8], rstd[8], ga[8], be[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    int c = cv * 8 + i, g = c / cpg;
-    mean[i] = stats[2 * (n * s.G + g)], rstd[i] = stats[2 * (n * s.G + g) + 1];
-    ga[i] = gamma[c], be[i] = beta[c];
-  }
+  GNBwdConst k;
+  gn_load_const(k, s, n, cv, stats, gamma, beta);
   float sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
   const int p0 = b * s.pix_per_block, p1 = min(s.HW, p0 + s.pix_per_block);
   const bf16* xb = x + (1LL * n * s.HW) * s.ld + cv * 8;
   const bf16* db = dy + (1LL * n * s.HW) * lddy + cv * 8;
-  for (int p = p0 + r; p < p1; p += R) {
-    float fx[8], fd[8];
-    bf8_to_f(*reinterpret_cast<const BF8*>(xb + 1LL * p * s.ld), fx);
-    bf8_to_f(*reinterpret_cast<const BF8*>(db + 1LL * p * lddy), fd);
+  constexpr int U = 2;
+  for (int p = p0 + r; p < p1; p += R * U) {
+    BF8 vx[U], vd[U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float xh = (fx[i] - mean[i]) * rstd[i];
-      float d = fd[i];
-      if (silu) d *= silu_grad(bf16r(xh * ga[i] + be[i]));
-      d *= ga[i];
-      sa[i >> 1] += d;
-      sb[i >> 1] += d * xh;
-    }
+    for (int u = 0; u < U; ++u)
+      if (p + u * R < p1) {
+        vx[u] = *reinterpret_cast<const BF8*>(xb + 1LL * (p + u * R) * s.ld);
+        vd[u] = *reinterpret_cast<const BF8*>(db + 1LL * (p + u * R) * lddy);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (p + u * R < p1) {
+        float fx[8], fd[8];
+        bf8_to_f(vx[u], fx);
+        bf8_to_f(vd[u], fd);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float xh = (fx[i] - k.mean[i >> 1]) * k.rstd[i >> 1];
+          float d = fd[i];
+          if (silu) d *= silu_grad(bf16r(xh * k.ga[i] + k.be[i]));
+          d *= k.ga[i];
+          sa[i >> 1] += d;
+          sb[i >> 1] += d * xh;
+        }
+      }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -215,40 +269,56 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ x, const bf16* __re
 }
 
 // backward pass 2: dx (+)= rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat*xhat))
-__global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, long long lddy, GNShape s,
-                                    const float* __restrict__ stats, const float* __restrict__ gstats,
-                                    const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
-                                    bf16* __restrict__ dx, long long lddx, int acc) {
+__global__ void __launch_bounds__(384, 2) gn_bwd_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                                              long long lddy, GNShape s,
+                                                              const float* __restrict__ stats,
+                                                              const float* __restrict__ gstats,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, int silu,
+                                                              bf16* __restrict__ dx, long long lddx, int acc) {
   const int CV = s.C >> 3, cpg = s.C / s.G;
   const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
   const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
-  float mean[8], rstd[8], ga[8], be[8], m1[8], m2[8];
+  GNBwdConst k;
+  gn_load_const(k, s, n, cv, stats, gamma, beta);
+  float m1[4], m2[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    int c = cv * 8 + i, g = c / cpg;
-    mean[i] = stats[2 * (n * s.G + g)], rstd[i] = stats[2 * (n * s.G + g) + 1];
+  for (int i = 0; i < 4; ++i) {
+    int g = (cv * 8 + 2 * i) / cpg;
     m1[i] = gstats[2 * (n * s.G + g)], m2[i] = gstats[2 * (n * s.G + g) + 1];
-    ga[i] = gamma[c], be[i] = beta[c];
   }
   const int p0 = b * s.pix_per_block, p1 = min(s.HW, p0 + s.pix_per_block);
   const bf16* xb = x + (1LL * n * s.HW) * s.ld + cv * 8;
   const bf16* db = dy + (1LL * n * s.HW) * lddy + cv * 8;
   bf16* ob = dx + (1LL * n * s.HW) * lddx + cv * 8;
-  for (int p = p0 + r; p < p1; p += R) {
-    float fx[8], fd[8], o[8];
-    bf8_to_f(*reinterpret_cast<const BF8*>(xb + 1LL * p * s.ld), fx);
-    bf8_to_f(*reinterpret_cast<const BF8*>(db + 1LL * p * lddy), fd);
-    if (acc) bf8_to_f(*reinterpret_cast<const BF8*>(ob + 1LL * p * lddx), o);
+  constexpr int U = 2;
+  for (int p = p0 + r; p < p1; p += R * U) {
+    BF8 vx[U], vd[U], vo[U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float xh = (fx[i] - mean[i]) * rstd[i];
-      float d = fd[i];
-      if (silu) d *= silu_grad(bf16r(xh * ga[i] + be[i]));
-      d *= ga[i];
-      float g = rstd[i] * (d - m1[i] - xh * m2[i]);
-      o[i] = acc ? o[i] + g : g;
-    }
-    *reinterpret_cast<BF8*>(ob + 1LL * p * lddx) = f_to_bf8(o);
+    for (int u = 0; u < U; ++u)
+      if (p + u * R < p1) {
+        vx[u] = *reinterpret_cast<const BF8*>(xb + 1LL * (p + u * R) * s.ld);
+        vd[u] = *reinterpret_cast<const BF8*>(db + 1LL * (p + u * R) * lddy);
+        if (acc) vo[u] = *reinterpret_cast<const BF8*>(ob + 1LL * (p + u * R) * lddx);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (p + u * R < p1) {
+        float fx[8], fd[8], o[8];
+        bf8_to_f(vx[u], fx);
+        bf8_to_f(vd[u], fd);
+        if (acc) bf8_to_f(vo[u], o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float xh = (fx[i] - k.mean[i >> 1]) * k.rstd[i >> 1];
+          float d = fd[i];
+          if (silu) d *= silu_grad(bf16r(xh * k.ga[i] + k.be[i]));
+          d *= k.ga[i];
+          float g = k.rstd[i >> 1] * (d - m1[i >> 1] - xh * m2[i >> 1]);
+          o[i] = acc ? o[i] + g : g;
+        }
+        *reinterpret_cast<BF8*>(ob + 1LL * (p + u * R) * lddx) = f_to_bf8(o);
+      }
   }
 }
 

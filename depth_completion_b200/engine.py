@@ -62,6 +62,7 @@ def _declare(l):
     l.mdc_dbg_loss.argtypes = [C.c_void_p] * 6
     l.mdc_dbg_update.argtypes = [C.c_void_p] * 4
     l.mdc_dbg_profile_gemm_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.mdc_dbg_profile_ops.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     l.mdc_dbg_time_tapes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     l._mdc_declared = True
 
@@ -246,6 +247,9 @@ class StepEngine:
         v, dz, du = (t.to(self.device, torch.float32).contiguous() for t in (v, dz, dunet_in))
         assert tuple(v.shape) == (self.n, 4, self.lh, self.lw) and tuple(du.shape) == (self.n, 8, self.lh, self.lw)
         check(self.lib.mdc_dbg_update(self._h, ptr(v), ptr(dz), ptr(du)))
+
+    def dbg_profile_ops(self, csv_path: str, iters: int = 5):
+        check(self.lib.mdc_dbg_profile_ops(self._h, csv_path.encode(), iters))
 
     def dbg_time_tapes(self, iters: int = 3):
         ms = (C.c_float * 4)()

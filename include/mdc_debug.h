@@ -47,6 +47,9 @@ int mdc_dbg_update(mdc_handle* h, const float* v_nchw, const float* dz_nchw, con
  * meaningfully: call after mdc_begin, before/after mdc_run) with CUDA events around every tcgen05 GEMM / conv launch;
  * returns the summed kernel time (ms), the summed algorithmic FLOPs and the number of such launches. */
 int mdc_dbg_profile_gemm_step(mdc_handle* h, float* ms_host, double* flops_host, int* launches_host);
+/* Per-op timing report (CSV: tape, index, op name, fwd us, bwd us, GEMM GFLOP, launches): every op of both tapes is
+ * replayed `iters` times back to back (warm caches: use for ranking, not for absolute step time). */
+int mdc_dbg_profile_ops(mdc_handle* h, const char* csv_path, int iters);
 /* Per-tape timing: runs the forward (and backward) tapes `iters` times, returns ms per pass. */
 int mdc_dbg_time_tapes(mdc_handle* h, int iters, float* ms_host /* [4]: unet fwd, unet bwd, dec fwd, dec bwd */);
 

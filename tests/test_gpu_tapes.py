@@ -107,7 +107,7 @@ def test_batch2(cuda):
     assert rel_l2(eng.dbg_backward(1, dout), x.grad) < 7e-2
     xin = torch.randn(2, 8, eng.lh, eng.lw, device=cuda, generator=g).bfloat16().float()
     x = xin.clone().requires_grad_(True)
-    y = unet(x, torch.tensor(999, device=cuda), ctx)
+    y = unet(x, torch.tensor(999, device=cuda), ctx.repeat(2, 1, 1))
     dout = torch.randn(y.shape, device=cuda, generator=g).bfloat16().float()
     y.backward(dout)
     assert rel_l2(eng.dbg_forward(0, 0, xin), y) < 4e-2
