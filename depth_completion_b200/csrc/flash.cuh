@@ -63,9 +63,18 @@ __device__ __forceinline__ void fa_mma_bmn(uint32_t d_tmem, uint32_t a_addr, uin
                    ptx::make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024), idesc, (accumulate_first || k) ? 1u : 0u);
 }
 
+__device__ __forceinline__ float fa_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void fa_named_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 struct FaSmem {
   uint64_t m_full, s_full[FA_STAGES], s_empty[FA_STAGES], acc_full, acc_empty, p_full, p_empty, o_full, o_empty;
   uint32_t tmem_slot;
+  alignas(16) float lse_s[2][64];
+  alignas(16) float del_s[2][64];  // per-iteration staging of LSE2 / delta of the streamed queries (dkv kernel)
 };
 
 // Common prologue: carve shared memory, init barriers, allocate TMEM.  Layout after the 1 KiB header:
@@ -173,14 +182,23 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
       fa_warp_arrive(&c.b->acc_empty, c.lane);
       const int valid = p.T - i * 64;  // keys of this tile that exist
       float mx = -INFINITY;
+      if (valid >= 64) {
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        float s = (j < valid) ? __uint_as_float(raw[j]) * c2 : -INFINITY;
-        raw[j] = __float_as_uint(s);
-        mx = fmaxf(mx, s);
+        for (int j = 0; j < 64; ++j) {
+          float s = __uint_as_float(raw[j]) * c2;
+          raw[j] = __float_as_uint(s);
+          mx = fmaxf(mx, s);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          float s = (j < valid) ? __uint_as_float(raw[j]) * c2 : -INFINITY;
+          raw[j] = __float_as_uint(s);
+          mx = fmaxf(mx, s);
+        }
       }
       const float m_new = fmaxf(m, mx);
-      const float alpha = exp2f(m - m_new);
+      const float alpha = fa_exp2(m - m_new);
       float sum = 0.f;
       ptx::mbar_wait(&c.b->p_empty, (i & 1) ^ 1);
 #pragma unroll
@@ -188,7 +206,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          v[j] = exp2f(__uint_as_float(raw[ch * 8 + j]) - m_new);
+          v[j] = fa_exp2(__uint_as_float(raw[ch * 8 + j]) - m_new);
           sum += v[j];
         }
         fa_store_row_chunk(c.p1, row, ch, v);
@@ -282,32 +300,43 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dkv_kernel(const __grid_c
     const float c2 = p.scale * FA_LOG2E;
     const float* lse = p.lse2 + (static_cast<long long>(n) * p.heads + h) * p.T;
     const float* del = p.delta + (static_cast<long long>(n) * p.heads + h) * p.T;
+    const int st_tid = threadIdx.x - 64;  // 0..127
     for (int i = 0; i < n_iter; ++i) {
+      const int qbase = i * 64, sb = i & 1;
+      {  // stage LSE2 / delta of this query tile; out-of-range queries get LSE2 = +inf, i.e. probability 0
+        const int j = st_tid & 63, qq = qbase + j;
+        if (st_tid < 64)
+          c.b->lse_s[sb][j] = qq < p.T ? __ldg(lse + qq) : INFINITY;
+        else
+          c.b->del_s[sb][j] = qq < p.T ? __ldg(del + qq) : 0.f;
+      }
+      fa_named_sync();
       ptx::mbar_wait(&c.b->acc_full, i & 1);
       ptx::tc_fence_after();
       ptx::mbar_wait(&c.b->p_empty, (i & 1) ^ 1);
-      const int qbase = i * 64;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t rs[32], rd[32];
-        ptx::tmem_ld32(t_row + half * 32, rs);
-        ptx::tmem_ld32(t_row + 64 + half * 32, rd);
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint32_t rs[16], rd[16];
+        ptx::tmem_ld16(t_row + q4 * 16, rs);
+        ptx::tmem_ld16(t_row + 64 + q4 * 16, rd);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < 2; ++ch) {
           float pv[8], dv[8];
+          const float4 l0 = *reinterpret_cast<const float4*>(&c.b->lse_s[sb][q4 * 16 + ch * 8]);
+          const float4 l1 = *reinterpret_cast<const float4*>(&c.b->lse_s[sb][q4 * 16 + ch * 8 + 4]);
+          const float4 d0 = *reinterpret_cast<const float4*>(&c.b->del_s[sb][q4 * 16 + ch * 8]);
+          const float4 d1 = *reinterpret_cast<const float4*>(&c.b->del_s[sb][q4 * 16 + ch * 8 + 4]);
+          const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+          const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int qq = qbase + half * 32 + ch * 8 + j;
-            float pr = 0.f, ds = 0.f;
-            if (qq < p.T) {
-              pr = exp2f(__uint_as_float(rs[ch * 8 + j]) * c2 - __ldg(lse + qq));
-              ds = pr * (__uint_as_float(rd[ch * 8 + j]) - __ldg(del + qq)) * p.scale;
-            }
-            pv[j] = pr, dv[j] = ds;
+            const float pr = fa_exp2(fmaf(__uint_as_float(rs[ch * 8 + j]), c2, -ls[j]));
+            pv[j] = pr;
+            dv[j] = pr * (__uint_as_float(rd[ch * 8 + j]) - dl[j]) * p.scale;
           }
-          fa_store_row_chunk(c.p1, row, half * 4 + ch, pv);
-          fa_store_row_chunk(c.p2, row, half * 4 + ch, dv);
+          fa_store_row_chunk(c.p1, row, q4 * 2 + ch, pv);
+          fa_store_row_chunk(c.p2, row, q4 * 2 + ch, dv);
         }
       }
       ptx::tc_fence_before();
@@ -381,31 +410,36 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dq_kernel(const __grid_co
     const bool ok = q0 + row < p.T;
     const long long sidx = (static_cast<long long>(n) * p.heads + h) * p.T + q0 + row;
     const float lse = ok ? p.lse2[sidx] : 0.f, del = ok ? p.delta[sidx] : 0.f;
+    const float nlse = ok ? -lse : -INFINITY;  // rows past T produce probability 0
     for (int i = 0; i < n_iter; ++i) {
       ptx::mbar_wait(&c.b->acc_full, i & 1);
       ptx::tc_fence_after();
       ptx::mbar_wait(&c.b->p_empty, (i & 1) ^ 1);
       const int valid = p.T - i * 64;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t rs[32], rd[32];
-        ptx::tmem_ld32(t_row + half * 32, rs);
-        ptx::tmem_ld32(t_row + 64 + half * 32, rd);
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint32_t rs[16], rd[16];
+        ptx::tmem_ld16(t_row + q4 * 16, rs);
+        ptx::tmem_ld16(t_row + 64 + q4 * 16, rd);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < 2; ++ch) {
           float dv[8];
+          if (valid >= 64) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int kk = half * 32 + ch * 8 + j;
-            float ds = 0.f;
-            if (kk < valid && ok) {
-              const float pr = exp2f(__uint_as_float(rs[ch * 8 + j]) * c2 - lse);
-              ds = pr * (__uint_as_float(rd[ch * 8 + j]) - del) * p.scale;
+            for (int j = 0; j < 8; ++j) {
+              const float pr = fa_exp2(fmaf(__uint_as_float(rs[ch * 8 + j]), c2, nlse));
+              dv[j] = pr * (__uint_as_float(rd[ch * 8 + j]) - del) * p.scale;
             }
-            dv[j] = ds;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int kk = q4 * 16 + ch * 8 + j;
+              const float pr = kk < valid ? fa_exp2(fmaf(__uint_as_float(rs[ch * 8 + j]), c2, nlse)) : 0.f;
+              dv[j] = pr * (__uint_as_float(rd[ch * 8 + j]) - del) * p.scale;
+            }
           }
-          fa_store_row_chunk(c.p1, row, half * 4 + ch, dv);
+          fa_store_row_chunk(c.p1, row, q4 * 2 + ch, dv);
         }
       }
       ptx::tc_fence_before();

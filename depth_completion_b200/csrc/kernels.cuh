@@ -63,7 +63,12 @@ __device__ __forceinline__ float block_max(float v, float* sh) {
   r = warp_max(r);
   return r;
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// sigmoid(x) = 0.5 tanh(x/2) + 0.5: one MUFU op (tanh.approx, rel. error ~2^-11, far below bf16 resolution)
+__device__ __forceinline__ float sigmoidf_(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(t, 0.5f, 0.5f);
+}
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
 __device__ __forceinline__ float silu_grad(float x) {
   float s = sigmoidf_(x);
