@@ -77,7 +77,7 @@ struct FaSmem {
   alignas(16) float del_s[2][64];  // per-iteration staging of LSE2 / delta of the streamed queries (dkv kernel)
 };
 
-// Common prologue: carve shared memory, init barriers, allocate TMEM.  Layout after the 1 KiB header:
+// Common prologue: carve shared memory, init barriers, allocate TMEM.  Layout after the 2 KiB header:
 // [M1 16K][M2 16K][S stages: FA_STAGES x (8K + 8K)][P1 16K][P2 16K]
 struct FaCtx {
   FaSmem* b;
@@ -89,7 +89,8 @@ __device__ __forceinline__ FaCtx fa_setup(uint8_t* smem_raw, uint32_t tmem_cols)
   FaCtx c;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   c.b = reinterpret_cast<FaSmem*>(smem);
-  c.m1 = smem + 1024, c.m2 = c.m1 + 16384, c.st = c.m2 + 16384;
+  static_assert(sizeof(FaSmem) <= 2048, "FaSmem must fit the 2 KiB header");
+  c.m1 = smem + 2048, c.m2 = c.m1 + 16384, c.st = c.m2 + 16384;
   c.p1 = c.st + FA_STAGES * 16384, c.p2 = c.p1 + 16384;
   c.warp = threadIdx.x >> 5, c.lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dq_kernel(const __grid_co
 }
 
 // ======================================================================================= host side
-constexpr int FA_SMEM = 1024 + 2 * 16384 + FA_STAGES * 16384 + 2 * 16384 + 1024;  // + alignment slack
+constexpr int FA_SMEM = 2048 + 2 * 16384 + FA_STAGES * 16384 + 2 * 16384 + 1024;  // + alignment slack
 
 struct FlashPlan {
   FlashParams fwd, dkv, dq;
