@@ -67,7 +67,7 @@ struct Op {
   virtual void gemm_plans(std::vector<const GemmPlan*>& f, std::vector<const GemmPlan*>& b) const {}
 };
 
-enum WKind { W_CONV3 = 0, W_LIN = 1, W_VEC = 2 };
+enum WKind { W_CONV3 = 0, W_LIN = 1, W_VEC = 2, W_UPCONV = 3 };
 struct WeightSlot {
   WKind kind;
   int out = 0, in = 0;          // logical dims ([out, in, 3, 3] / [out, in] / [out])
@@ -143,11 +143,11 @@ struct LayerNormOp : Op {
   }
   void fwd(cudaStream_t st) override {
     int rows = static_cast<int>(x->rows());
-    ln_fwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x->d, x->ld, rows, x->c, gamma, beta, 1e-5f, y->d, y->ld, stats);
+    launch_k(ln_fwd_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, x->d, x->ld, rows, x->c, gamma, beta, 1e-5f, y->d, y->ld, stats);
   }
   void bwd(cudaStream_t st) override {
     int rows = static_cast<int>(x->rows());
-    ln_bwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x->d, x->ld, y->g, y->ld, rows, x->c, gamma, stats, x->g, x->ld, acc);
+    launch_k(ln_bwd_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, x->d, x->ld, y->g, y->ld, rows, x->c, gamma, stats, x->g, x->ld, acc);
   }
 };
 struct GegluOp : Op {
@@ -158,10 +158,10 @@ struct GegluOp : Op {
     x->grad_set = true;
   }
   void fwd(cudaStream_t st) override {
-    geglu_fwd_kernel<<<ew_grid(x->rows() * (y->c / 8)), 256, 0, st>>>(x->d, x->ld, x->rows(), y->c, y->d, y->ld);
+    launch_k(geglu_fwd_kernel, dim3(ew_grid(x->rows() * (y->c / 8))), dim3(256), 0, st, x->d, x->ld, x->rows(), y->c, y->d, y->ld);
   }
   void bwd(cudaStream_t st) override {
-    geglu_bwd_kernel<<<ew_grid(x->rows() * (y->c / 8)), 256, 0, st>>>(x->d, x->ld, y->g, y->ld, x->rows(), y->c, x->g,
+    launch_k(geglu_bwd_kernel, dim3(ew_grid(x->rows() * (y->c / 8))), dim3(256), 0, st, x->d, x->ld, y->g, y->ld, x->rows(), y->c, x->g,
                                                                      x->ld, acc);
   }
 };
@@ -196,12 +196,12 @@ struct CrossAttn2Op : Op {  // attention over the 2 tokens of the empty-prompt e
   }
   void fwd(cudaStream_t st) override {
     long long warps = q->rows() * heads;
-    xattn2_fwd_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, st>>>(q->d, q->ld, q->rows(), heads, kc, vc,
+    launch_k(xattn2_fwd_kernel, dim3(static_cast<int>((warps * 32 + 255) / 256)), dim3(256), 0, st, q->d, q->ld, q->rows(), heads, kc, vc,
                                                                                  0.125f, o->d, o->ld);
   }
   void bwd(cudaStream_t st) override {
     long long warps = q->rows() * heads;
-    xattn2_bwd_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, st>>>(q->d, q->ld, o->g, o->ld, q->rows(),
+    launch_k(xattn2_bwd_kernel, dim3(static_cast<int>((warps * 32 + 255) / 256)), dim3(256), 0, st, q->d, q->ld, o->g, o->ld, q->rows(),
                                                                                  heads, kc, vc, 0.125f, q->g, q->ld, acc);
   }
 };
@@ -213,12 +213,25 @@ struct UpsampleOp : Op {
     x->grad_set = true;
   }
   void fwd(cudaStream_t st) override {
-    upsample_nearest_fwd_kernel<<<ew_grid(y->rows() * (y->c / 8)), 256, 0, st>>>(x->d, x->ld, x->n, x->h, x->w, x->c,
+    launch_k(upsample_nearest_fwd_kernel, dim3(ew_grid(y->rows() * (y->c / 8))), dim3(256), 0, st, x->d, x->ld, x->n, x->h, x->w, x->c,
                                                                                 y->d, y->ld, y->h, y->w);
   }
   void bwd(cudaStream_t st) override {
-    upsample_nearest_bwd_kernel<<<ew_grid(x->rows() * (x->c / 8)), 256, 0, st>>>(y->g, y->ld, x->n, x->h, x->w, x->c,
+    launch_k(upsample_nearest_bwd_kernel, dim3(ew_grid(x->rows() * (x->c / 8))), dim3(256), 0, st, y->g, y->ld, x->n, x->h, x->w, x->c,
                                                                                 x->g, x->ld, y->h, y->w, acc);
+  }
+};
+struct UpConvOp : Op {  // fused nearest-2x upsample + conv3x3 (four 2x2 phase convolutions on the low-res input)
+  Engine* E;
+  Tensor *x, *y;
+  WeightSlot* W;
+  const float* bias;
+  GemmPlan pf, pb;
+  void plan_bwd() override;
+  void fwd(cudaStream_t st) override { run_gemm(pf, st); }
+  void bwd(cudaStream_t st) override { run_gemm(pb, st); }
+  void gemm_plans(std::vector<const GemmPlan*>& f, std::vector<const GemmPlan*>& b) const override {
+    f.push_back(&pf), b.push_back(&pb);
   }
 };
 struct SubsampleOp : Op {
@@ -230,11 +243,11 @@ struct SubsampleOp : Op {
     x->grad_set = true;
   }
   void fwd(cudaStream_t st) override {
-    subsample2_fwd_kernel<<<ew_grid(y->rows() * (y->c / 8)), 256, 0, st>>>(x->d, x->ld, x->n, x->h, x->w, x->c, off, y->d,
+    launch_k(subsample2_fwd_kernel, dim3(ew_grid(y->rows() * (y->c / 8))), dim3(256), 0, st, x->d, x->ld, x->n, x->h, x->w, x->c, off, y->d,
                                                                           y->ld, y->h, y->w);
   }
   void bwd(cudaStream_t st) override {
-    subsample2_bwd_kernel<<<ew_grid(x->rows() * (x->c / 8)), 256, 0, st>>>(y->g, y->ld, x->n, x->h, x->w, x->c, off, x->g,
+    launch_k(subsample2_bwd_kernel, dim3(ew_grid(x->rows() * (x->c / 8))), dim3(256), 0, st, y->g, y->ld, x->n, x->h, x->w, x->c, off, x->g,
                                                                           x->ld, y->h, y->w, acc);
   }
 };
@@ -375,8 +388,15 @@ inline void ConvOp::plan_bwd() {
 inline void ConvOp::bwd(cudaStream_t st) {
   run_gemm(pb, st);
   if (res)
-    add_rows_kernel<<<ew_grid(res->rows() * (res->c / 8)), 256, 0, st>>>(y->g, y->ld, res->g, res->ld, res->rows(), res->c,
+    launch_k(add_rows_kernel, dim3(ew_grid(res->rows() * (res->c / 8))), dim3(256), 0, st, y->g, y->ld, res->g, res->ld, res->rows(), res->c,
                                                                         acc_res);
+}
+inline void UpConvOp::plan_bwd() {
+  Epilogue e;
+  e.out = x->g, e.ldc = x->ld;
+  if (x->grad_set) e.res = x->g, e.ldr = x->ld;
+  x->grad_set = true;
+  pb = plan_upconv_bwd(x->n, x->h, x->w, x->c, y->c, y->g, y->ld, W->wt, e);
 }
 inline void LinearOp::plan_bwd() {
   Epilogue e;
@@ -394,23 +414,23 @@ inline void LinearOp::plan_bwd() {
 inline void LinearOp::bwd(cudaStream_t st) {
   run_gemm(pb, st);
   if (res)
-    add_rows_kernel<<<ew_grid(res->rows() * (res->c / 8)), 256, 0, st>>>(y->g, y->ld, res->g, res->ld, res->rows(), res->c,
+    launch_k(add_rows_kernel, dim3(ew_grid(res->rows() * (res->c / 8))), dim3(256), 0, st, y->g, y->ld, res->g, res->ld, res->rows(), res->c,
                                                                         acc_res);
 }
 inline void GroupNormOp::fwd(cudaStream_t st) {
   const int grid = s.N * s.blocks_per_img;
-  gn_stats_kernel<<<grid, threads, 2 * s.G * sizeof(float), st>>>(x->d, s, E->gn_partial);
-  gn_finalize_kernel<<<(s.N * s.G * 32 + 127) / 128, 128, 0, st>>>(E->gn_partial, s.N, s.G, s.blocks_per_img,
+  launch_k(gn_stats_kernel, dim3(grid), dim3(threads), 2 * s.G * sizeof(float), st, x->d, s, E->gn_partial);
+  launch_k(gn_finalize_kernel, dim3((s.N * s.G * 32 + 127) / 128), dim3(128), 0, st, E->gn_partial, s.N, s.G, s.blocks_per_img,
                                                               1.0 * s.HW * (s.C / s.G), eps, 0, stats);
-  gn_apply_kernel<<<grid, threads, 0, st>>>(x->d, s, stats, gamma, beta, silu, y->d, y->ld);
+  launch_k(gn_apply_kernel, dim3(grid), dim3(threads), 0, st, x->d, s, stats, gamma, beta, silu, y->d, y->ld);
 }
 inline void GroupNormOp::bwd(cudaStream_t st) {
   const int grid = s.N * s.blocks_per_img;
-  gn_bwd_stats_kernel<<<grid, threads_b, 2 * s.G * sizeof(float), st>>>(x->d, y->g, y->ld, s, stats, gamma, beta, silu,
+  launch_k(gn_bwd_stats_kernel, dim3(grid), dim3(threads_b), 2 * s.G * sizeof(float), st, x->d, y->g, y->ld, s, stats, gamma, beta, silu,
                                                                       E->gn_partial);
-  gn_finalize_kernel<<<(s.N * s.G * 32 + 127) / 128, 128, 0, st>>>(E->gn_partial, s.N, s.G, s.blocks_per_img,
+  launch_k(gn_finalize_kernel, dim3((s.N * s.G * 32 + 127) / 128), dim3(128), 0, st, E->gn_partial, s.N, s.G, s.blocks_per_img,
                                                               1.0 * s.HW * (s.C / s.G), 0.f, 1, E->gn_gstats);
-  gn_bwd_apply_kernel<<<grid, threads_b, 0, st>>>(x->d, y->g, y->ld, s, stats, E->gn_gstats, gamma, beta, silu, x->g, x->ld,
+  launch_k(gn_bwd_apply_kernel, dim3(grid), dim3(threads_b), 0, st, x->d, y->g, y->ld, s, stats, E->gn_gstats, gamma, beta, silu, x->g, x->ld,
                                                 acc);
 }
 
@@ -463,7 +483,7 @@ inline void SelfAttnOp::fwd(cudaStream_t st) {
   }
   run_gemm(p_s, st);
   const int rows = qkv->n * heads * T;
-  softmax_fwd_kernel<<<rows, 256, (((T + 3) & ~3) + 32) * sizeof(float), st>>>(E->attn_S, P, T, ldS);
+  launch_k(softmax_fwd_kernel, dim3(rows), dim3(256), (((T + 3) & ~3) + 32) * sizeof(float), st, E->attn_S, P, T, ldS);
   run_gemm(p_o, st);
 }
 inline void SelfAttnOp::bwd(cudaStream_t st) {
@@ -474,7 +494,7 @@ inline void SelfAttnOp::bwd(cudaStream_t st) {
   run_gemm(p_dv, st);
   run_gemm(p_dp, st);
   const int rows = qkv->n * heads * T;
-  softmax_bwd_kernel<<<rows, 256, (((T + 3) & ~3) + 32) * sizeof(float), st>>>(E->attn_S, P, T, ldS,
+  launch_k(softmax_bwd_kernel, dim3(rows), dim3(256), (((T + 3) & ~3) + 32) * sizeof(float), st, E->attn_S, P, T, ldS,
                                                                               1.f / sqrtf(static_cast<float>(dh)));
   run_gemm(p_dq, st);
   run_gemm(p_dk, st);
@@ -509,10 +529,11 @@ inline WeightSlot* Engine::slot(const std::string& key, WKind kind, int out, int
   wslots.emplace_back();
   WeightSlot* s = &wslots.back();
   s->kind = kind, s->out = out, s->in = in;
-  if (kind == W_CONV3) {
+  if (kind == W_CONV3 || kind == W_UPCONV) {
     const int inp = ((in + 63) / 64) * 64, outp = ((out + 63) / 64) * 64;
-    s->w = arena.make<bf16>(9ull * inp * out + 64);
-    s->wt = arena.make<bf16>(9ull * outp * in + 64);
+    const size_t taps = kind == W_CONV3 ? 9 : 16;
+    s->w = arena.make<bf16>(taps * inp * out + 64);
+    s->wt = arena.make<bf16>(taps * outp * in + 64);
   } else if (kind == W_LIN) {
     s->ld_w = ((in + 7) / 8) * 8, s->ld_wt = ((out + 7) / 8) * 8;  // TMA needs 16-byte row strides
     s->w = arena.make<bf16>(1ull * out * s->ld_w + 64);
@@ -724,6 +745,19 @@ inline Tensor* Engine::transformer(Tensor* x, int heads, const std::string& key,
   return y;
 }
 inline Tensor* Engine::upsample_conv(Tensor* x, int H2, int W2, const std::string& key, Tensor* out) {
+  if (H2 == 2 * x->h && W2 == 2 * x->w && !getenv("MDC_NO_UPCONV")) {
+    WeightSlot* W = slot(key + ".conv.weight", W_UPCONV, x->c, x->c);
+    WeightSlot* B = slot(key + ".conv.bias", W_VEC, x->c, 0);
+    Tensor* y = out ? out : new_tensor(x->n, H2, W2, x->c, "");
+    auto* op = new UpConvOp();
+    op->E = this, op->x = x, op->y = y, op->W = W, op->bias = B->vec;
+    Epilogue e;
+    e.out = y->d, e.ldc = y->ld, e.bias = B->vec;
+    op->pf = plan_upconv_fwd(x->n, x->h, x->w, x->c, x->c, x->d, x->ld, W->w, e);
+    push(op, key + ".conv");
+    if (y->name.empty()) y->name = key, named[key] = y;
+    return y;
+  }
   Tensor* up = new_tensor(x->n, H2, W2, x->c, "");
   auto* op = new UpsampleOp();
   op->x = x, op->y = up;
@@ -970,6 +1004,17 @@ inline void Engine::set_weight(const std::string& key, const void* src, const lo
         pack_conv3x3_fwd_kernel<bf16><<<1184, 256, 0, stream>>>((const bf16*)src, s->w, s->out, s->in, inp);
         pack_conv3x3_dgrad_kernel<bf16><<<1184, 256, 0, stream>>>((const bf16*)src, s->wt, s->out, s->in, outp);
       }
+    } else if (s->kind == W_UPCONV) {
+      MDC_CHECK(ndim == 4 && shape[0] == s->out && shape[1] == s->in && shape[2] == 3 && shape[3] == 3,
+                "weight '%s': expected [%d,%d,3,3]", key.c_str(), s->out, s->in);
+      const int inp = ((s->in + 63) / 64) * 64, outp = ((s->out + 63) / 64) * 64;
+      if (f32) {
+        pack_upconv_fwd_kernel<float><<<1184, 256, 0, stream>>>((const float*)src, s->w, s->out, s->in, inp);
+        pack_upconv_bwd_kernel<float><<<1184, 256, 0, stream>>>((const float*)src, s->wt, s->out, s->in, outp);
+      } else {
+        pack_upconv_fwd_kernel<bf16><<<1184, 256, 0, stream>>>((const bf16*)src, s->w, s->out, s->in, inp);
+        pack_upconv_bwd_kernel<bf16><<<1184, 256, 0, stream>>>((const bf16*)src, s->wt, s->out, s->in, outp);
+      }
     } else if (s->kind == W_LIN) {
       MDC_CHECK(numel == 1LL * s->out * s->in && shape[0] == s->out, "weight '%s': expected [%d,%d]", key.c_str(), s->out,
                 s->in);
@@ -1018,11 +1063,11 @@ inline void Engine::prepare(const void* ctx_bf16, const float* alphas_cumprod, c
   MDC_CUDA(cudaMalloc(&h1, 4ull * n_steps * tc));
   MDC_CUDA(cudaMalloc(&h2, 4ull * n_steps * tc));
   MDC_CUDA(cudaMemcpy(d_ts, timesteps, n_steps * 4, cudaMemcpyHostToDevice));
-  timestep_embedding_kernel<<<(n_steps * c0 + 255) / 256, 256, 0, stream>>>(d_ts, n_steps, c0, emb);
+  launch_k(timestep_embedding_kernel, dim3((n_steps * c0 + 255) / 256), dim3(256), 0, stream, d_ts, n_steps, c0, emb);
   auto lin = [&](const bf16* Wm, long long ldw, const float* b, const float* in, long long ldin, int In, int Out, int silu,
                  float* out, long long ldout, int S) {
     long long warps = 1LL * S * Out;
-    small_linear_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, stream>>>(Wm, ldw, b, in, ldin, S, In, Out,
+    launch_k(small_linear_kernel, dim3(static_cast<int>((warps * 32 + 255) / 256)), dim3(256), 0, stream, Wm, ldw, b, in, ldin, S, In, Out,
                                                                                         silu, out, ldout);
   };
   lin(te_l1w->w, te_l1w->ld_w, te_l1b->vec, emb, c0, c0, tc, 0, h1, tc, n_steps);
@@ -1092,7 +1137,7 @@ inline void Engine::begin(const void* img_latents, const void* x0, const float* 
     off[n + 1] = off[n] + c;
   }
   MDC_CUDA(cudaMemcpyAsync(pt_off, off.data(), (N + 1) * 4, cudaMemcpyHostToDevice, stream));
-  compact_points_kernel<<<N, 1024, 0, stream>>>(guide, mask, H * W, pt_off, pt_idx, pt_val);
+  launch_k(compact_points_kernel, dim3(N), dim3(1024), 0, stream, guide, mask, H * W, pt_off, pt_idx, pt_val);
   MDC_CUDA(cudaGetLastError());
   MDC_CUDA(cudaStreamSynchronize(stream));
   lr_x = lrx, lr_s = lrs;
@@ -1190,19 +1235,19 @@ inline void Engine::step_launches() {
   const int hw = lh * lw, lat_pix = N * hw;
   const int pgrid = N * parts_per_img;
   TailGeom g{N, H, W, ph, pw, PPH, PPW, dec_out->ld};
-  begin_step_kernel<<<1, 1024, 0, stream>>>(tables, counter, cur, temb_cur, lr_x, lr_s);
-  unet_input_kernel<<<(lat_pix + 255) / 256, 256, 0, stream>>>(img_lat, x, N, hw, unet_in->d);
+  launch_k(begin_step_kernel, dim3(1), dim3(1024), 0, stream, tables, counter, cur, temb_cur, lr_x, lr_s);
+  launch_k(unet_input_kernel, dim3((lat_pix + 255) / 256), dim3(256), 0, stream, img_lat, x, N, hw, unet_in->d);
   run_ops(unet_ops, false);
-  x0_kernel<<<pgrid, 256, 0, stream>>>(unet_out->d, x, cur, N, hw, cfg.vae_scaling, dec_in->d, eps_part);
+  launch_k(x0_kernel, dim3(pgrid), dim3(256), 0, stream, unet_out->d, x, cur, N, hw, cfg.vae_scaling, dec_in->d, eps_part);
   run_ops(dec_ops, false);
-  loss_points_kernel<<<N, 512, 0, stream>>>(dec_out->d, g, pt_idx, pt_val, pt_off, gminmax, accum, dmean);
+  launch_k(loss_points_kernel, dim3(N), dim3(512), 0, stream, dec_out->d, g, pt_idx, pt_val, pt_off, gminmax, accum, dmean);
   const long long npix = 1LL * N * PPH * PPW;
-  dec_grad_kernel<<<static_cast<int>((npix + 255) / 256), 256, 0, stream>>>(dmean, npix, dec_out->g);
+  launch_k(dec_grad_kernel, dim3(static_cast<int>((npix + 255) / 256)), dim3(256), 0, stream, dmean, npix, dec_out->g);
   run_ops(dec_ops, true);
-  dx0_kernel<<<(lat_pix + 255) / 256, 256, 0, stream>>>(dec_in->g, cur, N, hw, cfg.vae_scaling, unet_out->g, dx_direct);
+  launch_k(dx0_kernel, dim3((lat_pix + 255) / 256), dim3(256), 0, stream, dec_in->g, cur, N, hw, cfg.vae_scaling, unet_out->g, dx_direct);
   run_ops(unet_ops, true);
-  grad_total_kernel<<<pgrid, 256, 0, stream>>>(dx_direct, unet_in->g, N, hw, gbuf, g_part);
-  adam_ddim_kernel<<<pgrid, 256, 0, stream>>>(gbuf, eps_part, g_part, parts_per_img, unet_out->d, cur, N, hw, x, m1, m2,
+  launch_k(grad_total_kernel, dim3(pgrid), dim3(256), 0, stream, dx_direct, unet_in->g, N, hw, gbuf, g_part);
+  launch_k(adam_ddim_kernel, dim3(pgrid), dim3(256), 0, stream, gbuf, eps_part, g_part, parts_per_img, unet_out->d, cur, N, hw, x, m1, m2,
                                               accum, counter, x_adam_dbg);
 }
 
@@ -1219,11 +1264,11 @@ inline void Engine::decode_final(float* dense_out) {
   MDC_CUDA(cudaMemsetAsync(unet_out->d, 0, static_cast<size_t>(unet_out->rows()) * unet_out->ld * 2, stream));
   float* scratch = nullptr;
   MDC_CUDA(cudaMalloc(&scratch, 4ull * N * parts_per_img));
-  x0_kernel<<<N * parts_per_img, 256, 0, stream>>>(unet_out->d, x, tmp, N, hw, cfg.vae_scaling, dec_in->d, scratch);
+  launch_k(x0_kernel, dim3(N * parts_per_img), dim3(256), 0, stream, unet_out->d, x, tmp, N, hw, cfg.vae_scaling, dec_in->d, scratch);
   run_ops(dec_ops, false);
   TailGeom g{N, H, W, ph, pw, PPH, PPW, dec_out->ld};
   const long long tot = 1LL * N * H * W;
-  dense_out_kernel<<<static_cast<int>((tot + 255) / 256), 256, 0, stream>>>(dec_out->d, g, gminmax, depth_minmax, accum,
+  launch_k(dense_out_kernel, dim3(static_cast<int>((tot + 255) / 256)), dim3(256), 0, stream, dec_out->d, g, gminmax, depth_minmax, accum,
                                                                            dense_out);
   MDC_CUDA(cudaGetLastError());
   MDC_CUDA(cudaStreamSynchronize(stream));
@@ -1245,7 +1290,7 @@ inline void Engine::read_tensor(const std::string& name, int which, float* out_n
   const bf16* src = which ? t->g : t->d;
   MDC_CHECK(src != nullptr, "tensor '%s' has no gradient buffer", name.c_str());
   long long tot = t->rows() * t->c;
-  nhwc_to_nchw_f32_kernel<<<static_cast<int>((tot + 255) / 256), 256, 0, stream>>>(src, t->ld, t->n, t->h * t->w, t->c,
+  launch_k(nhwc_to_nchw_f32_kernel, dim3(static_cast<int>((tot + 255) / 256)), dim3(256), 0, stream, src, t->ld, t->n, t->h * t->w, t->c,
                                                                                   out_nchw);
   MDC_CUDA(cudaGetLastError());
   MDC_CUDA(cudaStreamSynchronize(stream));

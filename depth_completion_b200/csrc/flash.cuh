@@ -106,6 +106,8 @@ __device__ __forceinline__ FaCtx fa_setup(uint8_t* smem_raw, uint32_t tmem_cols)
   __syncthreads();
   ptx::tc_fence_after();
   c.tmem = c.b->tmem_slot;
+  ptx::pdl_wait();  // prologue above overlaps the previous kernel's tail; every CTA holds its TMEM before dependents start
+  ptx::pdl_launch();
   return c;
 }
 __device__ __forceinline__ void fa_teardown(const FaCtx& c, uint32_t tmem_cols) {
@@ -247,6 +249,8 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
 // delta[n, h, t] = sum_c dO[n, t, h*64 + c] * O[n, t, h*64 + c]     (one warp per (token, head))
 __global__ void flash_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, long long ld, int N, int T,
                                    int heads, float* __restrict__ delta) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   const long long w = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= 1LL * N * T * heads) return;
@@ -535,15 +539,15 @@ inline void flash_set_attrs() {
 }
 inline void run_flash_fwd(const FlashPlan& f, cudaStream_t st) {
   flash_set_attrs();
-  flash_fwd_kernel<<<f.grid, FA_THREADS, FA_SMEM, st>>>(f.fwd);
+  launch_k(flash_fwd_kernel, f.grid, dim3(FA_THREADS), FA_SMEM, st, f.fwd);
 }
 inline void run_flash_bwd(const FlashPlan& f, cudaStream_t st) {
   flash_set_attrs();
   const long long warps = 1LL * f.N * f.T * f.heads;
-  flash_delta_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, st>>>(f.o, f.dout, f.ld_o, f.N, f.T, f.heads,
-                                                                                f.delta);
-  flash_dkv_kernel<<<f.grid, FA_THREADS, FA_SMEM, st>>>(f.dkv);
-  flash_dq_kernel<<<f.grid, FA_THREADS, FA_SMEM, st>>>(f.dq);
+  launch_k(flash_delta_kernel, dim3(static_cast<unsigned>((warps * 32 + 255) / 256)), dim3(256), 0, st, f.o, f.dout, f.ld_o,
+           f.N, f.T, f.heads, f.delta);
+  launch_k(flash_dkv_kernel, f.grid, dim3(FA_THREADS), FA_SMEM, st, f.dkv);
+  launch_k(flash_dq_kernel, f.grid, dim3(FA_THREADS), FA_SMEM, st, f.dq);
 }
 
 }  // namespace mdc

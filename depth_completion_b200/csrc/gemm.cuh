@@ -14,6 +14,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,9 +43,13 @@ struct GemmParams {
   uint32_t idesc;
   uint32_t bytesA, bytesB;
   int M, N;  // valid rows per batch (GEMM mode) / valid columns
-  // conv3x3 mode
+  // conv mode: 0 = GEMM; 1 = implicit-GEMM conv over `ntaps` taps (3x3, or the four 2x2 phase convs of a fused
+  // nearest-2x-upsample + conv3x3, phase = batch slot b0); 2 = input gradient of that fused op (16 taps, 4 phase views)
   int conv;
   int H, W, tiles_h, tiles_w, BW, BH, chunks_per_tap;
+  int taps_w, ntaps, off_h0, off_w0, nphase;
+  long long out_sh, out_sw, out_pa, out_pb;  // output element strides: pixel row, pixel column, phase row, phase column
+  CUtensorMap tmA1, tmA2, tmA3;              // mode 2: phase views 1..3 of dy (tmA is phase 0)
   // epilogue
   void* out;
   int out_f32;
@@ -76,14 +81,15 @@ __device__ __forceinline__ void gemm_decode_tile(const GemmParams& p, int tile, 
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // barriers live in the first 1 KiB of the aligned region, stage buffers follow.
+  // barriers live in the first 1 KiB of the aligned region, the staged bias in the next 2 KiB; stage buffers at 4 KiB.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + GEMM_MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint8_t* sA = smem + 1024;
+  float* sbias_base = reinterpret_cast<float*>(smem + 1024);  // 2 x 256 floats
+  uint8_t* sA = smem + 4096;
   const uint32_t b_stage = static_cast<uint32_t>(p.BN) * 128u;
   uint8_t* sB = sA + p.stages * GEMM_A_STAGE;
 
@@ -109,6 +115,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail.
+  // All CTAs of this grid hold their TMEM before the next grid may start (no allocation deadlock).
+  ptx::pdl_wait();
+  ptx::pdl_launch();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -139,11 +149,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
           uint8_t* a_dst = sA + stage * GEMM_A_STAGE;
           uint8_t* b_dst = sB + stage * b_stage;
           const int k0 = kc * GEMM_BK;
-          if (p.conv) {
+          if (p.conv == 1) {
             const int tap = kc / p.chunks_per_tap;
             const int cc = kc - tap * p.chunks_per_tap;
-            const int r = tap / 3, s = tap - r * 3;
-            ptx::tma_load_4d(&p.tmA, &full_bar[stage], a_dst, cc * GEMM_BK, w0 + s - 1, h0 + r - 1, img);
+            const int r = tap / p.taps_w, s = tap - r * p.taps_w;
+            const int pa = p.nphase > 1 ? (b0 >> 1) : 0, pb = p.nphase > 1 ? (b0 & 1) : 0;
+            ptx::tma_load_4d(&p.tmA, &full_bar[stage], a_dst, cc * GEMM_BK, w0 + s + p.off_w0 + pb, h0 + r + p.off_h0 + pa,
+                             img);
+            ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst, k0 + b0 * p.num_k_chunks * GEMM_BK, n0, 0, 0);
+          } else if (p.conv == 2) {
+            const int tap = kc / p.chunks_per_tap;  // phase * 4 + tr * 2 + ts
+            const int cc = kc - tap * p.chunks_per_tap;
+            const int ph = tap >> 2, tr = (tap >> 1) & 1, ts = tap & 1;
+            const CUtensorMap* tm = ph == 0 ? &p.tmA : (ph == 1 ? &p.tmA1 : (ph == 2 ? &p.tmA2 : &p.tmA3));
+            ptx::tma_load_4d(tm, &full_bar[stage], a_dst, cc * GEMM_BK, w0 - (ts - 1 + (ph & 1)), h0 - (tr - 1 + (ph >> 1)), img);
             ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst, k0, n0, 0, 0);
           } else {
             if (!p.a_mn) {
@@ -231,7 +250,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
         int ww = tw * p.BW + row % p.BW;
         valid = (row < p.BW * p.BH) && hh < p.H && ww < p.W;
         long long pix = (static_cast<long long>(hh) * p.W + ww);
-        off_c = img * p.sc1 + pix * p.ldc;
+        off_c = img * p.sc1 + hh * p.out_sh + ww * p.out_sw;
+        if (p.nphase > 1) off_c += (b0 >> 1) * p.out_pa + (b0 & 1) * p.out_pb;
         off_r = img * p.sr1 + pix * p.ldr;
       } else {
         int m = m_tile * GEMM_BM + row;
@@ -251,80 +271,101 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
         off_c = (off_c / p.ldc) * p.ws_ld;  // same row index, workspace row stride
         e_f32 = 1, e_vec = 1, e_bias = nullptr, e_bias_img = nullptr, e_res = nullptr, e_alpha = 1.f;
       }
+      // Stage bias (+ per-image bias) of this tile's columns in shared memory once (double-buffered by accumulator
+      // stage), so the column loop below has no dependent global loads besides the residual.
+      float* sbias = sbias_base + as * 256;
+      const bool has_bias = (e_bias != nullptr) || (e_bias_img != nullptr);
+      if (has_bias) {
+        for (int c = threadIdx.x - 64; c < p.BN; c += 128) {
+          const int col = n0 + c;
+          float b = 0.f;
+          if (col < p.N) {
+            if (e_bias) b += __ldg(e_bias + col);
+            if (e_bias_img) b += __ldg(e_bias_img + static_cast<long long>(img) * p.N + col);
+          }
+          sbias[c] = b;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       ptx::mbar_wait(&tfull_bar[as], aphase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as) * 256u;
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t raw[16];
-        ptx::tmem_ld16(t_row + c0, raw);
-        ptx::tmem_ld_wait();
+      // 32-column chunks, TMEM loads double-buffered in registers: the load of chunk c+1 is in flight while chunk c is
+      // converted and stored.  A chunk may extend past BN (BN is a multiple of 16); those columns are masked.
+      uint32_t bufA[32], bufB[32];
+      ptx::tmem_ld32(t_row, bufA);
+      const int n_chunks = (p.BN + 31) >> 5;
+      auto process = [&](const uint32_t(&raw)[32], uint32_t(&nxt)[32], const int ci) {
+        const int c0 = ci << 5;
         const int col0 = n0 + c0;
-        if (valid && col0 < p.N) {
-          float v[16];
+        const int ncol = min(32, min(p.BN - c0, p.N - col0));  // valid columns of this chunk (may be <= 0)
+        const bool full = (ncol == 32) && e_vec;
+        uint4 rres[4];
+        if (e_res && valid && full) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(e_res + off_r + col0);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * e_alpha;
-          const bool full = (col0 + 16 <= p.N) && e_vec;
-          if (full) {
-            if (e_bias) {
-              const float4* b4 = reinterpret_cast<const float4*>(e_bias + col0);
+          for (int j = 0; j < 4; ++j) rres[j] = r4[j];
+        }
+        ptx::tmem_ld_wait();
+        if (ci + 1 < n_chunks) ptx::tmem_ld32(t_row + c0 + 32, nxt);
+        if (!valid || ncol <= 0) return;
+        if (full) {
+          float v[32];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float4 b = __ldg(b4 + j);
-                v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
-              }
-            }
-            if (e_bias_img) {
-              const float4* b4 = reinterpret_cast<const float4*>(e_bias_img + static_cast<long long>(img) * p.N + col0);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * e_alpha;
+          if (has_bias) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float4 b = __ldg(b4 + j);
-                v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
-              }
-            }
-            if (e_res) {
-              const uint4* r4 = reinterpret_cast<const uint4*>(e_res + off_r + col0);
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                uint4 r = r4[j];
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  float2 f = __bfloat1622float2(h[t]);
-                  v[8 * j + 2 * t] += f.x;
-                  v[8 * j + 2 * t + 1] += f.y;
-                }
-              }
-            }
-            if (e_f32) {
-              float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(e_out) + off_c + col0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            } else {
-              uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(e_out) + off_c + col0);
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                uint4 o;
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]);
-                o4[j] = o;
-              }
-            }
-          } else {
-            for (int j = 0; j < 16; ++j) {
-              const int col = col0 + j;
-              if (col >= p.N) break;
-              float x = v[j];
-              if (e_bias) x += e_bias[col];
-              if (e_bias_img) x += e_bias_img[static_cast<long long>(img) * p.N + col];
-              if (e_res) x += __bfloat162float(e_res[off_r + col]);
-              if (e_f32)
-                static_cast<float*>(e_out)[off_c + col] = x;
-              else
-                static_cast<__nv_bfloat16*>(e_out)[off_c + col] = __float2bfloat16(x);
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j);
+              v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
             }
           }
+          if (e_res) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rres[j]);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                float2 f = __bfloat1622float2(h[t]);
+                v[8 * j + 2 * t] += f.x;
+                v[8 * j + 2 * t + 1] += f.y;
+              }
+            }
+          }
+          if (e_f32) {
+            float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(e_out) + off_c + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(e_out) + off_c + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]);
+              o4[j] = o;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j >= ncol) break;
+            const int col = col0 + j;
+            float x = __uint_as_float(raw[j]) * e_alpha;
+            if (has_bias) x += sbias[c0 + j];
+            if (e_res) x += __bfloat162float(e_res[off_r + col]);
+            if (e_f32)
+              static_cast<float*>(e_out)[off_c + col] = x;
+            else
+              static_cast<__nv_bfloat16*>(e_out)[off_c + col] = __float2bfloat16(x);
+          }
         }
+      };
+#pragma unroll 1
+      for (int ci = 0; ci < n_chunks; ci += 2) {
+        process(bufA, bufB, ci);
+        if (ci + 1 < n_chunks) process(bufB, bufA, ci + 1);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -427,6 +468,8 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int ksplit, l
                                      long long rows, int N, void* __restrict__ out, int out_f32, long long ldc,
                                      const float* __restrict__ bias, const __nv_bfloat16* __restrict__ res,
                                      long long ldr, float alpha) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   const int nv = (N + 3) >> 2;
   const long long total = rows * nv;
   for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
@@ -472,10 +515,10 @@ inline int g_num_sms() {
 inline void finish_plan(GemmPlan& g) {
   GemmParams& p = g.p;
   const int b_stage = p.BN * 128;
-  int stages = (GEMM_SMEM_BUDGET - 2048) / (GEMM_A_STAGE + b_stage);
+  int stages = (GEMM_SMEM_BUDGET - 5120) / (GEMM_A_STAGE + b_stage);
   stages = std::max(2, std::min(stages, GEMM_MAX_STAGES));
   p.stages = stages;
-  g.smem = 2048 + stages * (GEMM_A_STAGE + b_stage);
+  g.smem = 5120 + stages * (GEMM_A_STAGE + b_stage);
   p.idesc = ptx::make_idesc_bf16(GEMM_BM, p.BN, p.a_mn, p.b_mn);
   long long total = 1LL * p.m_tiles * p.n_tiles * (p.ksplit > 1 ? p.ksplit : p.nb0) * p.nb1;
   g.grid = static_cast<int>(std::min<long long>(total, g_num_sms()));
@@ -557,6 +600,8 @@ inline GemmPlan plan_conv3x3(int NB, int H, int W, int C, int Cout, const void* 
   const int Cp = ((C + 63) / 64) * 64;
   p.conv = 1;
   p.H = H, p.W = W;
+  p.taps_w = 3, p.ntaps = 9, p.off_h0 = -1, p.off_w0 = -1, p.nphase = 1;
+  p.out_sh = 1LL * W * e.ldc, p.out_sw = e.ldc;
   pick_conv_tile(H, W, p.BW, p.BH);
   p.tiles_w = (W + p.BW - 1) / p.BW;
   p.tiles_h = (H + p.BH - 1) / p.BH;
@@ -590,6 +635,119 @@ inline GemmPlan plan_conv3x3(int NB, int H, int W, int C, int Cout, const void* 
   return g;
 }
 
+// Kernel launch with the programmatic-stream-serialization attribute (PDL); MDC_NO_PDL=1 disables it.
+inline bool g_use_pdl() {
+  static int v = -1;
+  if (v < 0) v = getenv("MDC_NO_PDL") ? 0 : 1;
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = g_use_pdl() ? 1 : 0;
+  MDC_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
+// Fused nearest-2x upsample + conv3x3 (pad 1) as four 2x2 "phase" convolutions on the LOW-resolution input:
+//   y[2i+a, 2j+b] = sum_{tr,ts} Weff[a][b][tr][ts] . x[i + tr - 1 + a, j + ts - 1 + b]      (2.25x fewer FLOPs, no upsampled
+// tensor).  x: [NB, H, W, C] (pixel stride ldx); wpk: [Cout, 16 * Cp] with k = ((phase*4 + tr*2 + ts) * Cp + c);
+// out: [NB, 2H, 2W, Cout] (pixel stride ldc).
+inline GemmPlan plan_upconv_fwd(int NB, int H, int W, int C, int Cout, const void* x, long long ldx, const void* wpk,
+                                Epilogue e) {
+  GemmPlan g;
+  memset(&g.p, 0, sizeof(g.p));
+  GemmParams& p = g.p;
+  const int Cp = ((C + 63) / 64) * 64;
+  p.conv = 1;
+  p.H = H, p.W = W;
+  p.taps_w = 2, p.ntaps = 4, p.off_h0 = -1, p.off_w0 = -1, p.nphase = 4;
+  const long long Wf = 2LL * W, Hf = 2LL * H;
+  p.out_sh = 2 * Wf * e.ldc, p.out_sw = 2 * e.ldc, p.out_pa = Wf * e.ldc, p.out_pb = e.ldc;
+  pick_conv_tile(H, W, p.BW, p.BH);
+  p.tiles_w = (W + p.BW - 1) / p.BW;
+  p.tiles_h = (H + p.BH - 1) / p.BH;
+  p.m_tiles = NB * p.tiles_h * p.tiles_w;
+  p.M = 0, p.N = Cout;
+  p.nb0 = 4, p.nb1 = 1;
+  p.BN = pick_bn(Cout);
+  p.n_tiles = (Cout + p.BN - 1) / p.BN;
+  p.chunks_per_tap = Cp / 64;
+  p.num_k_chunks = 4 * p.chunks_per_tap;
+  p.bytesA = 64u * p.BW * p.BH * 2u;
+  p.bytesB = p.BN * 128;
+  {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+    uint64_t str[3] = {(uint64_t)ldx, (uint64_t)ldx * W, (uint64_t)ldx * W * H};
+    uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+    p.tmA = make_tmap_bf16(x, dims, str, box);
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)16 * Cp, (uint64_t)Cout, 1, 1};
+    uint64_t str[3] = {(uint64_t)16 * Cp, (uint64_t)16 * Cp * Cout, (uint64_t)16 * Cp * Cout};
+    uint32_t box[4] = {64, (uint32_t)p.BN, 1, 1};
+    p.tmB = make_tmap_bf16(wpk, dims, str, box);
+  }
+  e.sc1 = Hf * Wf * e.ldc;
+  fill_epilogue(p, e);
+  finish_plan(g);
+  g.flops = 2.0 * NB * Hf * Wf * 9.0 * C * Cout;  // algorithmic FLOPs of the op it replaces
+  g.rows = 1LL * NB * H * W;
+  return g;
+}
+// Input gradient of the fused op: dx[i,j] = sum_{phase,tr,ts} Weff^T . dy_phase[i - (tr-1+a), j - (ts-1+b)].
+//   dy: [NB, 2H, 2W, Cout] (pixel stride lddy); wpk: [C, 16 * Coutp], k = (phase*4 + tr*2 + ts) * Coutp + co; out: [NB,H,W,C].
+inline GemmPlan plan_upconv_bwd(int NB, int H, int W, int C, int Cout, const void* dy, long long lddy, const void* wpk,
+                                Epilogue e) {
+  GemmPlan g;
+  memset(&g.p, 0, sizeof(g.p));
+  GemmParams& p = g.p;
+  const int Cop = ((Cout + 63) / 64) * 64;
+  p.conv = 2;
+  p.H = H, p.W = W;
+  p.taps_w = 2, p.ntaps = 16, p.nphase = 1;
+  p.out_sh = 1LL * W * e.ldc, p.out_sw = e.ldc;
+  pick_conv_tile(H, W, p.BW, p.BH);
+  p.tiles_w = (W + p.BW - 1) / p.BW;
+  p.tiles_h = (H + p.BH - 1) / p.BH;
+  p.m_tiles = NB * p.tiles_h * p.tiles_w;
+  p.M = 0, p.N = C;
+  p.nb0 = 1, p.nb1 = 1;
+  p.BN = pick_bn(C);
+  p.n_tiles = (C + p.BN - 1) / p.BN;
+  p.chunks_per_tap = Cop / 64;
+  p.num_k_chunks = 16 * p.chunks_per_tap;
+  p.bytesA = 64u * p.BW * p.BH * 2u;
+  p.bytesB = p.BN * 128;
+  const long long Wf = 2LL * W, Hf = 2LL * H;
+  CUtensorMap* maps[4] = {&p.tmA, &p.tmA1, &p.tmA2, &p.tmA3};
+  for (int ph = 0; ph < 4; ++ph) {
+    const int a = ph >> 1, b = ph & 1;
+    const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(dy) + (a * Wf + b) * lddy;
+    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+    uint64_t str[3] = {(uint64_t)(2 * lddy), (uint64_t)(2 * Wf * lddy), (uint64_t)(Hf * Wf * lddy)};
+    uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+    *maps[ph] = make_tmap_bf16(base, dims, str, box);
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)16 * Cop, (uint64_t)C, 1, 1};
+    uint64_t str[3] = {(uint64_t)16 * Cop, (uint64_t)16 * Cop * C, (uint64_t)16 * Cop * C};
+    uint32_t box[4] = {64, (uint32_t)p.BN, 1, 1};
+    p.tmB = make_tmap_bf16(wpk, dims, str, box);
+  }
+  if (!e.sc1) e.sc1 = 1LL * H * W * e.ldc;
+  if (e.res && !e.sr1) e.sr1 = 1LL * H * W * e.ldr;
+  fill_epilogue(p, e);
+  finish_plan(g);
+  g.flops = 2.0 * NB * Hf * Wf * 9.0 * C * Cout;
+  g.rows = 1LL * NB * H * W;
+  return g;
+}
+
 inline void gemm_set_smem_attr() {
   static bool done = false;
   if (!done) {
@@ -601,7 +759,7 @@ inline void gemm_set_smem_attr() {
 // Decide on split-K for a finished plan: few output tiles, long K loop.  `ws` must hold ws_floats(plan) floats.
 inline int choose_ksplit(const GemmPlan& g) {
   const GemmParams& p = g.p;
-  if (p.nb0 != 1 || p.nb1 != 1 || p.bias_img || p.out_f32) return 1;
+  if (p.nb0 != 1 || p.nb1 != 1 || p.bias_img || p.out_f32 || p.conv == 2 || p.nphase > 1) return 1;
   const int tiles = p.m_tiles * p.n_tiles;
   if (tiles * 2 > g_num_sms() || p.num_k_chunks < 8) return 1;
   int ks = (g_num_sms() + tiles - 1) / tiles;
@@ -625,13 +783,13 @@ inline size_t enable_splitk(GemmPlan& g, int ksplit) {  // returns the workspace
 
 inline void run_gemm(const GemmPlan& g, cudaStream_t st) {
   gemm_set_smem_attr();
-  umma_gemm_kernel<<<g.grid, GEMM_THREADS, g.smem + 1024, st>>>(g.p);
+  launch_k(umma_gemm_kernel, dim3(g.grid), dim3(GEMM_THREADS), g.smem + 1024, st, g.p);
   if (g.p.ksplit > 1) {
     const GemmParams& p = g.p;
     const long long work = g.rows * ((p.N + 3) / 4);
     const int grid = static_cast<int>(std::min<long long>((work + 255) / 256, 148 * 8));
-    splitk_reduce_kernel<<<grid, 256, 0, st>>>(p.ws, p.ksplit, p.ws_split_stride, p.ws_ld, g.rows, p.N, p.out, p.out_f32,
-                                               p.ldc, p.bias, p.res, p.ldr, p.alpha);
+    launch_k(splitk_reduce_kernel, dim3(grid), dim3(256), 0, st, p.ws, p.ksplit, p.ws_split_stride, p.ws_ld, g.rows, p.N,
+             p.out, p.out_f32, p.ldc, p.bias, p.res, p.ldr, p.alpha);
   }
 }
 

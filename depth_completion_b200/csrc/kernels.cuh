@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ptx.cuh"
+
 namespace mdc {
 
 typedef __nv_bfloat16 bf16;
@@ -96,6 +98,8 @@ struct GNShape {
 // pass 1 of forward: per-block partial (sum, sumsq) per group -> partial[(n*bpi + b)*G*2 + g*2 + {0,1}]
 __global__ void __launch_bounds__(512, 2) gn_stats_kernel(const bf16* __restrict__ x, GNShape s,
                                                           float* __restrict__ partial) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   extern __shared__ float sh[];  // 2*G
   const int CV = s.C >> 3, cpg = s.C / s.G;
   const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
@@ -135,6 +139,8 @@ __global__ void __launch_bounds__(512, 2) gn_stats_kernel(const bf16* __restrict
 // mode 0: (sum, sumsq) -> (mean, rstd);  mode 1: plain sums scaled by 1/m (used by the backward pass).
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int N, int G, int bpi, double m, float eps,
                                    int mode, float* __restrict__ out) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= N * G) return;
   const int n = i / G, g = i % G;
@@ -166,6 +172,8 @@ __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const bf16* __restrict
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, int silu,
                                                           bf16* __restrict__ y, long long ldy) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   const int CV = s.C >> 3, cpg = s.C / s.G;
   const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
   const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
@@ -225,6 +233,8 @@ __global__ void __launch_bounds__(384, 2) gn_bwd_stats_kernel(const bf16* __rest
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, int silu,
                                                               float* __restrict__ partial) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   extern __shared__ float sh[];
   const int CV = s.C >> 3, cpg = s.C / s.G;
   const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
@@ -281,6 +291,8 @@ __global__ void __launch_bounds__(384, 2) gn_bwd_apply_kernel(const bf16* __rest
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, int silu,
                                                               bf16* __restrict__ dx, long long lddx, int acc) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   const int CV = s.C >> 3, cpg = s.C / s.G;
   const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
   const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
@@ -333,6 +345,8 @@ constexpr int LN_MAXV = 5;  // supports d <= 32*8*5 = 1280
 __global__ void ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, int rows, int d, const float* __restrict__ gamma,
                               const float* __restrict__ beta, float eps, bf16* __restrict__ y, long long ldy,
                               float* __restrict__ stats) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int nv = d >> 3;
@@ -377,6 +391,8 @@ __global__ void ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, int row
 __global__ void ln_bwd_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ dy, long long lddy,
                               int rows, int d, const float* __restrict__ gamma, const float* __restrict__ stats,
                               bf16* __restrict__ dx, long long lddx, int acc) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int nv = d >> 3;
@@ -421,6 +437,8 @@ __global__ void ln_bwd_kernel(const bf16* __restrict__ x, long long ldx, const b
 // x [rows, 2F] -> y [rows, F] = x[:, :F] * gelu(x[:, F:])
 __global__ void geglu_fwd_kernel(const bf16* __restrict__ x, long long ldx, long long rows, int F, bf16* __restrict__ y,
                                  long long ldy) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   const int fv = F >> 3;
   const long long total = rows * fv;
   for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
@@ -436,6 +454,8 @@ __global__ void geglu_fwd_kernel(const bf16* __restrict__ x, long long ldx, long
 }
 __global__ void geglu_bwd_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ dy, long long lddy,
                                  long long rows, int F, bf16* __restrict__ dx, long long lddx, int acc) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   const int fv = F >> 3;
   const long long total = rows * fv;
   for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
@@ -477,6 +497,8 @@ __device__ __forceinline__ float4 ld_bf16x4(const bf16* p) {
   return make_float4(a.x, a.y, b.x, b.y);
 }
 __global__ void softmax_fwd_kernel(const float* __restrict__ S, bf16* __restrict__ P, int T, long long ld) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   extern __shared__ float row[];  // T4 floats + 32
   const int T4 = T & ~3;
   float* red = row + ((T + 3) & ~3);
@@ -515,6 +537,8 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ S, bf16* __restrict
 // dS = P * (dP - sum_j P dP) * scale, written in place over P (bf16).
 __global__ void softmax_bwd_kernel(const float* __restrict__ dP, bf16* __restrict__ P, int T, long long ld,
                                    float scale) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   extern __shared__ float row[];
   const int T4 = T & ~3;
   float* red = row + ((T + 3) & ~3);
@@ -547,6 +571,8 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ dP, bf16* __restric
 __global__ void xattn2_fwd_kernel(const bf16* __restrict__ q, long long ldq, long long rows, int heads,
                                   const float* __restrict__ kc, const float* __restrict__ vc, float scale,
                                   bf16* __restrict__ o, long long ldo) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   const long long w = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= rows * heads) return;
@@ -564,6 +590,8 @@ __global__ void xattn2_bwd_kernel(const bf16* __restrict__ q, long long ldq, con
                                   long long lddo, long long rows, int heads, const float* __restrict__ kc,
                                   const float* __restrict__ vc, float scale, bf16* __restrict__ dq, long long lddq,
                                   int acc) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   const long long w = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= rows * heads) return;
@@ -594,6 +622,8 @@ __device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
 // nearest upsample [N, h, w, C] -> [N, H, W, C] (torch F.interpolate(mode="nearest") index rule)
 __global__ void upsample_nearest_fwd_kernel(const bf16* __restrict__ x, long long ldx, int N, int h, int w, int C,
                                             bf16* __restrict__ y, long long ldy, int H, int W) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   const int cv = C >> 3;
   const long long total = 1LL * N * H * W * cv;
   const float sh = static_cast<float>(h) / H, sw = static_cast<float>(w) / W;
@@ -609,6 +639,8 @@ __global__ void upsample_nearest_fwd_kernel(const bf16* __restrict__ x, long lon
 // adjoint: dx[n, sy, sx] (+)= sum of dy over the destination pixels that read (sy, sx)
 __global__ void upsample_nearest_bwd_kernel(const bf16* __restrict__ dy, long long lddy, int N, int h, int w, int C,
                                             bf16* __restrict__ dx, long long lddx, int H, int W, int acc) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   const int cv = C >> 3;
   const long long total = 1LL * N * h * w * cv;
   const float sh = static_cast<float>(h) / H, sw = static_cast<float>(w) / W;
@@ -641,6 +673,8 @@ __global__ void upsample_nearest_bwd_kernel(const bf16* __restrict__ dy, long lo
 // y[n, oy, ox] = x[n, 2*oy + off, 2*ox + off]   (stride-2 conv = stride-1 conv + this subsample)
 __global__ void subsample2_fwd_kernel(const bf16* __restrict__ x, long long ldx, int N, int H, int W, int C, int off,
                                       bf16* __restrict__ y, long long ldy, int Ho, int Wo) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   const int cv = C >> 3;
   const long long total = 1LL * N * Ho * Wo * cv;
   for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
@@ -654,6 +688,8 @@ __global__ void subsample2_fwd_kernel(const bf16* __restrict__ x, long long ldx,
 // adjoint: zero-insert
 __global__ void subsample2_bwd_kernel(const bf16* __restrict__ dy, long long lddy, int N, int H, int W, int C, int off,
                                       bf16* __restrict__ dx, long long lddx, int Ho, int Wo, int acc) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   const int cv = C >> 3;
   const long long total = 1LL * N * H * W * cv;
   for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
@@ -681,6 +717,8 @@ __global__ void subsample2_bwd_kernel(const bf16* __restrict__ dy, long long ldd
 // dst[rows, C] (+)= src[rows, C]  (channel-slice copy/accumulate with independent row strides)
 __global__ void add_rows_kernel(const bf16* __restrict__ src, long long lds, bf16* __restrict__ dst, long long ldd,
                                 long long rows, int C, int acc) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   const int cv = C >> 3;
   const long long total = rows * cv;
   for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {

@@ -47,6 +47,44 @@ __global__ void pack_conv3x3_dgrad_kernel(const T* __restrict__ w, __nv_bfloat16
   }
 }
 
+// Effective 2x2 weights of the fused nearest-2x-upsample + conv3x3: rows {r} of the 3x3 kernel that land on the same
+// low-resolution input row are summed.  phase a = 0: tap 0 <- r{0}, tap 1 <- r{1,2};  a = 1: tap 0 <- r{0,1}, tap 1 <- r{2}.
+template <typename T>
+__device__ __forceinline__ float upconv_weff(const T* __restrict__ w, int co, int c, int C, int a, int b, int tr, int ts) {
+  const int r0 = (a == 0) ? (tr == 0 ? 0 : 1) : (tr == 0 ? 0 : 2), r1 = (a == 0) ? (tr == 0 ? 0 : 2) : (tr == 0 ? 1 : 2);
+  const int s0 = (b == 0) ? (ts == 0 ? 0 : 1) : (ts == 0 ? 0 : 2), s1 = (b == 0) ? (ts == 0 ? 0 : 2) : (ts == 0 ? 1 : 2);
+  float v = 0.f;
+  for (int r = r0; r <= r1; ++r)
+    for (int s = s0; s <= s1; ++s) v += to_f32(w[((1LL * co * C + c) * 9) + r * 3 + s]);
+  return v;
+}
+// forward pack [Cout][16*Cp], k = (phase*4 + tr*2 + ts)*Cp + c
+template <typename T>
+__global__ void pack_upconv_fwd_kernel(const T* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int C, int Cp) {
+  long long total = 1LL * Cout * 16 * Cp;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    int c = i % Cp;
+    int tap = (i / Cp) % 16;
+    int co = i / (16LL * Cp);
+    float v = 0.f;
+    if (c < C) v = upconv_weff(w, co, c, C, tap >> 3, (tap >> 2) & 1, (tap >> 1) & 1, tap & 1);
+    out[i] = __float2bfloat16(v);
+  }
+}
+// input-gradient pack [C][16*Cop], k = (phase*4 + tr*2 + ts)*Cop + co
+template <typename T>
+__global__ void pack_upconv_bwd_kernel(const T* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int C, int Cop) {
+  long long total = 1LL * C * 16 * Cop;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    int co = i % Cop;
+    int tap = (i / Cop) % 16;
+    int ci = i / (16LL * Cop);
+    float v = 0.f;
+    if (co < Cout) v = upconv_weff(w, co, ci, C, tap >> 3, (tap >> 2) & 1, (tap >> 1) & 1, tap & 1);
+    out[i] = __float2bfloat16(v);
+  }
+}
+
 // [rows][cols] source -> bf16: out[r*ld + c] (transpose = 0) or out[c*ld + r] (transpose = 1).
 template <typename T>
 __global__ void pack_matrix_kernel(const T* __restrict__ w, __nv_bfloat16* __restrict__ out, int rows, int cols,

@@ -37,6 +37,8 @@ struct StepAccum {             // per-sample accumulators (device memory)
 // Select the step: fill StepCur and the current time-embedding biases.  One block.
 __global__ void begin_step_kernel(StepTables tb, int* __restrict__ counter, StepCur* __restrict__ cur,
                                   float* __restrict__ temb_cur, float lr_x, float lr_s) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   const int s = min(*counter, tb.steps - 1);
   if (threadIdx.x == 0) {
     cur->sqrt_a = tb.sqrt_a[s], cur->sqrt_1ma = tb.sqrt_1ma[s];
@@ -54,6 +56,8 @@ __global__ void begin_step_kernel(StepTables tb, int* __restrict__ counter, Step
 // cat([img_latents, x], dim=1) as NHWC [N, h, w, 8]  (marigold_dc.py:459)
 __global__ void unet_input_kernel(const bf16* __restrict__ img_lat, const bf16* __restrict__ x, int N, int hw,
                                   bf16* __restrict__ out) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
   if (i >= 1LL * N * hw) return;
   long long n = i / hw, p = i % hw;
@@ -71,6 +75,8 @@ __global__ void unet_input_kernel(const bf16* __restrict__ img_lat, const bf16* 
 // eps_part[n*bpi + b] = partial sum of eps^2 (fixed-order reduction later).
 __global__ void x0_kernel(const bf16* __restrict__ v_nhwc, const bf16* __restrict__ x, const StepCur* __restrict__ cur,
                           int N, int hw, float scaling, bf16* __restrict__ z_nhwc, float* __restrict__ eps_part) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   __shared__ float red[32];
   const int bpi = gridDim.x / N, n = blockIdx.x / bpi, b = blockIdx.x % bpi;
   const float sa = cur->sqrt_a, sb = cur->sqrt_1ma;
@@ -125,6 +131,8 @@ __global__ void loss_points_kernel(const bf16* __restrict__ dec, TailGeom g, con
                                    const float* __restrict__ pt_val, const int* __restrict__ pt_off,
                                    const float* __restrict__ gminmax, StepAccum* __restrict__ acc,
                                    float* __restrict__ dmean) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   __shared__ float red[32];
   const int n = blockIdx.x;
   const int p0 = pt_off[n], p1 = pt_off[n + 1];
@@ -170,6 +178,8 @@ __global__ void loss_points_kernel(const bf16* __restrict__ dec, TailGeom g, con
 }
 // d dec[n, y, x, c] = dmean / 3 for c < 3 (bf16); clears dmean for the next step.
 __global__ void dec_grad_kernel(float* __restrict__ dmean, long long npix, bf16* __restrict__ ddec) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
   if (i >= npix) return;
   float d = dmean[i] * (1.f / 3.f);
@@ -185,6 +195,8 @@ __global__ void dec_grad_kernel(float* __restrict__ dmean, long long npix, bf16*
 // direct part of dx = sqrt(a) d x0 (NCHW fp32 holding bf16-rounded values).
 __global__ void dx0_kernel(const bf16* __restrict__ dz_nhwc, const StepCur* __restrict__ cur, int N, int hw,
                            float scaling, bf16* __restrict__ dv_nhwc, float* __restrict__ dx_direct) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
   if (i >= 1LL * N * hw) return;
   long long n = i / hw, p = i % hw;
@@ -206,6 +218,8 @@ __global__ void dx0_kernel(const bf16* __restrict__ dz_nhwc, const StepCur* __re
 // total latent gradient g = direct + UNet path (channels 4..7 of the UNet-input gradient); partial sums of g^2.
 __global__ void grad_total_kernel(const float* __restrict__ dx_direct, const bf16* __restrict__ din_nhwc, int N, int hw,
                                   float* __restrict__ gbuf, float* __restrict__ g_part) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   __shared__ float red[32];
   const int bpi = gridDim.x / N, n = blockIdx.x / bpi, b = blockIdx.x % bpi;
   float acc = 0.f;
@@ -231,6 +245,8 @@ __global__ void adam_ddim_kernel(const float* __restrict__ gbuf, const float* __
                                  const StepCur* __restrict__ cur, int N, int hw, bf16* __restrict__ x,
                                  bf16* __restrict__ m1, bf16* __restrict__ m2, StepAccum* __restrict__ acc,
                                  int* __restrict__ counter, bf16* __restrict__ x_adam_dbg) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   const int bpi = gridDim.x / N, n = blockIdx.x / bpi, b = blockIdx.x % bpi;
   float e2 = 0.f, g2 = 0.f;
   for (int k = 0; k < parts_per_img; ++k) e2 += eps_part[n * parts_per_img + k], g2 += g_part[n * parts_per_img + k];
@@ -277,6 +293,8 @@ __global__ void adam_ddim_kernel(const float* __restrict__ gbuf, const float* __
 __global__ void dense_out_kernel(const bf16* __restrict__ dec, TailGeom g, const float* __restrict__ gminmax,
                                  const float* __restrict__ depth_minmax, const StepAccum* __restrict__ acc,
                                  float* __restrict__ out) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
   long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
   if (i >= 1LL * g.N * g.H * g.W) return;
   const int X = i % g.W, Y = (i / g.W) % g.H, n = i / (1LL * g.W * g.H);

@@ -1,0 +1,187 @@
+"""CPU tests of the host side: C-ABI symbols, config/geometry, DDIM tables, argument validation, sharding (gloo)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from depth_completion_b200 import _lib
+
+    _lib.build()
+    lib = _lib.lib()
+    syms = []
+    for hdr in ("mdc.h", "mdc_debug.h"):
+        txt = open(os.path.join(ROOT, "include", hdr)).read()
+        syms += re.findall(r"\b(mdc_[a-z0-9_]+)\s*\(", txt)
+    syms = sorted(set(syms))
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert isinstance(lib.mdc_last_error(), bytes)
+
+
+def test_config_struct_matches_header():
+    """The ctypes mirror of struct mdc_config must list the header's fields in order."""
+    from depth_completion_b200.engine import MdcConfig
+
+    txt = open(os.path.join(ROOT, "include", "mdc.h")).read()
+    body = txt[txt.index("typedef struct mdc_config {"):txt.index("} mdc_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        m = re.search(r"\b(int|float)\s+([^{]*)$", decl, flags=re.S)
+        if m:
+            for part in m.group(2).split(","):
+                names.append(re.sub(r"\[.*\]", "", part).strip())
+    assert names == [f[0] for f in MdcConfig._fields_]
+
+
+def test_geometry_and_tables():
+    from depth_completion_b200 import ddim
+    from depth_completion_b200.config import processed_geometry
+
+    assert processed_geometry(480, 640, 768) == (576, 768, 0, 0)
+    assert processed_geometry(480, 640, 640) == (480, 640, 0, 0)
+    assert processed_geometry(352, 1216, 1216) == (352, 1216, 0, 0)
+    assert processed_geometry(352, 1216, 768) == (222, 768, 2, 0)   # 27 != 28 latent rows
+    ts = ddim.trailing_timesteps(50)
+    assert ts[0] == 999 and ts[-1] == 19 and len(ts) == 50 and ts.dtype == np.int32
+    ac = ddim.alphas_cumprod()
+    assert abs(ac[999].item() - 0.0046601) < 1e-6 and abs(ac[0].item() - 0.99915) < 1e-6
+
+
+def test_tables_match_oracle_scheduler():
+    from depth_completion_b200 import ddim
+    from oracle.scheduler import DDIMScheduler
+
+    s = DDIMScheduler()
+    s.set_timesteps(50)
+    assert np.array_equal(ddim.trailing_timesteps(50), s.timesteps.numpy().astype(np.int32))
+    assert torch.equal(ddim.alphas_cumprod(), s.alphas_cumprod)
+    ac, ts = ddim.tables_from_scheduler(s, 50)
+    assert torch.equal(ac, s.alphas_cumprod) and ts[0] == 999
+
+
+def test_flop_counter_matches_survey():
+    from depth_completion_b200.config import UNetConfig, VAEConfig
+    from depth_completion_b200.flops import step_flops
+
+    s = step_flops(UNetConfig(), VAEConfig(), 480, 640, 768)
+    assert s["latent"] == (72, 96)
+    assert abs(s["unet_fwd"] / 1e12 - 1.487) < 2e-3 and abs(s["dec_fwd"] / 1e12 - 4.283) < 2e-3
+    assert abs(s["step"] / 1e12 - 11.540) < 5e-3 and abs(s["frame"](50) / 1e12 - 583.2) < 0.2
+    s = step_flops(UNetConfig(), VAEConfig(), 352, 1216, 1216)
+    assert s["latent"] == (44, 152) and abs(s["step"] / 1e12 - 11.150) < 5e-3
+
+
+def test_prologue_matches_oracle_on_cpu():
+    """Image preprocessing, VAE encoder and masked min/max of the host prologue against the oracle."""
+    from depth_completion_b200 import prologue
+    from depth_completion_b200.config import vae_config_from
+    from oracle import image_processor as ip
+    from oracle.marigold_dc import masked_minmax
+    from oracle.sd2_modules import AutoencoderKL, tiny_vae_config
+
+    torch.manual_seed(0)
+    vae = AutoencoderKL(tiny_vae_config())
+    img = torch.randint(0, 256, (2, 3, 50, 70), dtype=torch.uint8)
+    a, pad = prologue.preprocess_image(img, 64, torch.float32)
+    b, pad_ref, _ = ip.preprocess(img, 64, "cpu", torch.float32)
+    assert pad == pad_ref and torch.equal(a, b)
+    za = prologue.vae_encode_mode(vae.state_dict(), vae_config_from(vae), a)
+    zb = vae.encode_mode(b)
+    assert torch.allclose(za, zb, atol=1e-5)
+    x = torch.rand(3, 40)
+    m = torch.rand(3, 40) > 0.6
+    lo, hi = prologue.masked_minmax(x, m)
+    lo2, hi2 = masked_minmax(x, m, dim=-1)
+    assert torch.equal(lo, lo2) and torch.equal(hi, hi2)
+    with pytest.raises(ValueError):
+        prologue.masked_minmax(x, torch.zeros_like(m))
+    with pytest.raises(ValueError):
+        prologue.preprocess_image(img.float(), 64, torch.float32)
+
+
+def test_pipeline_argument_validation_without_gpu():
+    """Every ValueError of marigold_dc.py:583-656 fires before any device work, so it can be checked on CPU."""
+    from depth_completion_b200._lib import MdcError
+    from depth_completion_b200.pipeline import MarigoldDepthCompletionPipeline
+    from oracle.sd2_modules import AutoencoderKL, UNet2DConditionModel, tiny_unet_config, tiny_vae_config
+
+    pipe = MarigoldDepthCompletionPipeline(UNet2DConditionModel(tiny_unet_config()), AutoencoderKL(tiny_vae_config()))
+    img = torch.zeros(1, 3, 96, 128, dtype=torch.uint8)
+    sp = torch.rand(1, 1, 96, 128)
+    bad = [dict(train_latents=False, closed_form=False), dict(train_method="x"), dict(train_method="per-input", train_steps=0),
+           dict(beta=0.0), dict(norm="percentile", percentile=(0.1, 1.5)), dict(projection="cubic"),
+           dict(projection="log10", min_depth=0.0), dict(inv=True), dict(loss_funcs=["l3"]), dict(norm="max"), dict(opt="rmsprop"),
+           dict(resolution=128, pred_latents_prev=torch.zeros(2, 4, 12, 16))]
+    for kw in bad:
+        with pytest.raises(ValueError):
+            pipe(img, sp, 10.0, **kw)
+    with pytest.raises(ValueError):
+        pipe(img, sp[:, :, :, :100], 10.0)
+    for kw in [dict(opt="adagrad"), dict(kld=True), dict(loss_funcs=["l1", "edge"]), dict(train_latents=False),
+               dict(projection="log", min_depth=0.5), dict(interp_mode="bicubic")]:
+        with pytest.raises(NotImplementedError):
+            pipe(img, sp, 10.0, **kw)
+    with pytest.raises(ValueError):  # 352x1216 at resolution 768
+        pipe(torch.zeros(1, 3, 352, 1216, dtype=torch.uint8), torch.rand(1, 1, 352, 1216), 80.0, resolution=768)
+    with pytest.raises(MdcError):  # no CPU path exists
+        pipe(img, sp, 10.0, resolution=128, steps=2)
+
+
+def test_shard_frames():
+    from depth_completion_b200.pipeline import shard_frames
+
+    for n, w in [(64, 8), (64, 4), (10, 4), (3, 8), (0, 2)]:
+        shards = [list(shard_frames(n, r, w)) for r in range(w)]
+        assert sum(shards, []) == list(range(n))
+        assert max(map(len, shards)) - min(map(len, shards)) <= 1
+
+
+WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from depth_completion_b200.pipeline import shard_frames
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+n_frames = 7
+mine = list(shard_frames(n_frames, r, w))
+# stand-in for the per-frame result: every rank "completes" its own frames, then outputs are gathered (no collective
+# inside the per-frame work), exactly the structure bench.py uses with NCCL
+local = torch.zeros(4, 1, 6, 8)
+for i, f in enumerate(mine):
+    local[i] = float(f) + 1.0
+counts = [None] * w
+dist.all_gather_object(counts, len(mine))
+bufs = [torch.zeros_like(local) for _ in range(w)]
+dist.all_gather(bufs, local)
+frames = torch.cat([b[:c] for b, c in zip(bufs, counts)], 0)
+assert frames.shape[0] == n_frames and [int(v) for v in frames[:, 0, 0, 0]] == list(range(1, n_frames + 1)), frames[:, 0, 0, 0]
+t = torch.tensor([float(r + 1)])
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+assert t.item() == w
+dist.destroy_process_group()
+print("ok", r)
+'''
+
+
+def test_two_rank_frame_sharding_gloo(tmp_path):
+    """world_size-2 CPU run of the N > 1 host logic: frame shards, output all_gather, max-over-ranks timing reduce."""
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(script), ROOT]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
