@@ -46,21 +46,28 @@ __device__ __forceinline__ void fa_store_row_chunk(uint8_t* tile, int r, int c, 
   BF8 b = f_to_bf8(v);
   *reinterpret_cast<BF8*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = b;
 }
-__device__ __forceinline__ void fa_mma_kmajor(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc,
+// The MMA helpers take PRECOMPUTED 64-bit shared-memory descriptors (128B swizzle, SBO 1024); only the 14-bit start
+// address field advances: +2 (32 B) per 16-wide K step of a K-major tile, +128 (2048 B = 16 rows) for an MN-major tile.
+__device__ __forceinline__ uint64_t fa_desc(const void* smem_ptr) {
+  return ptx::make_smem_desc_sw128(ptx::smem_u32(smem_ptr), 16, 1024);
+}
+constexpr uint64_t FA_MN_LBO_DELTA = static_cast<uint64_t>((8192u - 16u) >> 4) << 16;  // LBO field 16 B -> 8192 B
+__device__ __forceinline__ void fa_mma_kmajor(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                               bool accumulate_first) {
   // D[128 x 64] (+)= A[128 x 64k] . B[64 x 64k]^T, both K-major
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    ptx::umma_bf16(d_tmem, ptx::make_smem_desc_sw128(a_addr + k * 32, 16, 1024),
-                   ptx::make_smem_desc_sw128(b_addr + k * 32, 16, 1024), idesc, (accumulate_first || k) ? 1u : 0u);
+  ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate_first ? 1u : 0u);
+  ptx::umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+  ptx::umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+  ptx::umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
 }
-__device__ __forceinline__ void fa_mma_bmn(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc,
+__device__ __forceinline__ void fa_mma_bmn(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                            bool accumulate_first) {
   // D[128 x 64n] (+)= A[128 x 64k] (K-major) . B[64k rows x 64n] (MN-major: rows are the contraction index)
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    ptx::umma_bf16(d_tmem, ptx::make_smem_desc_sw128(a_addr + k * 32, 16, 1024),
-                   ptx::make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024), idesc, (accumulate_first || k) ? 1u : 0u);
+  const uint64_t b = bdesc + FA_MN_LBO_DELTA;
+  ptx::umma_bf16(d_tmem, adesc, b, idesc, accumulate_first ? 1u : 0u);
+  ptx::umma_bf16(d_tmem, adesc + 2, b + 128, idesc, 1u);
+  ptx::umma_bf16(d_tmem, adesc + 4, b + 256, idesc, 1u);
+  ptx::umma_bf16(d_tmem, adesc + 6, b + 384, idesc, 1u);
 }
 
 __device__ __forceinline__ float fa_exp2(float x) {
@@ -147,25 +154,31 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
     if (c.lane == 0) fa_producer(c, p, q0, h, n, n_iter, false);
     __syncwarp();
   } else if (c.warp == 1) {
-    if (c.lane == 0) {
-      ptx::mbar_wait(&c.b->m_full, 0);
-      for (int i = 0; i < n_iter; ++i) {
-        const int s = i % FA_STAGES;
-        ptx::mbar_wait(&c.b->s_full[s], (i / FA_STAGES) & 1);
-        ptx::mbar_wait(&c.b->acc_empty, (i & 1) ^ 1);
-        ptx::tc_fence_after();
-        fa_mma_kmajor(c.tmem, ptx::smem_u32(c.m1), ptx::smem_u32(c.st + s * 16384), idesc_s, false);  // S = Q K^T
+    const bool leader = ptx::elect_one();
+    const uint64_t d_q = fa_desc(c.m1), d_p = fa_desc(c.p1), d_st = fa_desc(c.st);
+    ptx::mbar_wait(&c.b->m_full, 0);
+    for (int i = 0; i < n_iter; ++i) {
+      const int s = i % FA_STAGES;
+      const uint64_t d_k = d_st + s * 1024, d_v = d_k + 512;
+      ptx::mbar_wait(&c.b->s_full[s], (i / FA_STAGES) & 1);
+      ptx::mbar_wait(&c.b->acc_empty, (i & 1) ^ 1);
+      ptx::tc_fence_after();
+      if (leader) {
+        fa_mma_kmajor(c.tmem, d_q, d_k, idesc_s, false);  // S = Q K^T
         ptx::umma_commit(&c.b->acc_full);
-        ptx::mbar_wait(&c.b->p_full, i & 1);
-        ptx::mbar_wait(&c.b->o_empty, (i & 1) ^ 1);
-        ptx::tc_fence_after();
-        fa_mma_bmn(c.tmem + 64, ptx::smem_u32(c.p1), ptx::smem_u32(c.st + s * 16384 + 8192), idesc_o, false);  // P V
+      }
+      __syncwarp();
+      ptx::mbar_wait(&c.b->p_full, i & 1);
+      ptx::mbar_wait(&c.b->o_empty, (i & 1) ^ 1);
+      ptx::tc_fence_after();
+      if (leader) {
+        fa_mma_bmn(c.tmem + 64, d_p, d_v, idesc_o, false);  // O_tile = P V
         ptx::umma_commit(&c.b->o_full);
         ptx::umma_commit(&c.b->p_empty);
         ptx::umma_commit(&c.b->s_empty[s]);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     const int q = c.warp & 3, row = q * 32 + c.lane;
     const uint32_t t_row = c.tmem + (static_cast<uint32_t>(q * 32) << 16);
@@ -278,26 +291,32 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dkv_kernel(const __grid_c
     if (c.lane == 0) fa_producer(c, p, k0, h, n, n_iter, true);
     __syncwarp();
   } else if (c.warp == 1) {
-    if (c.lane == 0) {
-      ptx::mbar_wait(&c.b->m_full, 0);
-      for (int i = 0; i < n_iter; ++i) {
-        const int s = i % FA_STAGES;
-        const uint32_t q_addr = ptx::smem_u32(c.st + s * 16384), do_addr = q_addr + 8192;
-        ptx::mbar_wait(&c.b->s_full[s], (i / FA_STAGES) & 1);
-        ptx::mbar_wait(&c.b->acc_empty, (i & 1) ^ 1);
-        ptx::tc_fence_after();
-        fa_mma_kmajor(c.tmem, ptx::smem_u32(c.m1), q_addr, idesc_k, false);        // S^T  = K Q^T
-        fa_mma_kmajor(c.tmem + 64, ptx::smem_u32(c.m2), do_addr, idesc_k, false);  // dP^T = V dO^T
+    const bool leader = ptx::elect_one();
+    const uint64_t d_k = fa_desc(c.m1), d_v = fa_desc(c.m2), d_p = fa_desc(c.p1), d_ds = fa_desc(c.p2), d_st = fa_desc(c.st);
+    ptx::mbar_wait(&c.b->m_full, 0);
+    for (int i = 0; i < n_iter; ++i) {
+      const int s = i % FA_STAGES;
+      const uint64_t d_q = d_st + s * 1024, d_do = d_q + 512;
+      ptx::mbar_wait(&c.b->s_full[s], (i / FA_STAGES) & 1);
+      ptx::mbar_wait(&c.b->acc_empty, (i & 1) ^ 1);
+      ptx::tc_fence_after();
+      if (leader) {
+        fa_mma_kmajor(c.tmem, d_k, d_q, idesc_k, false);        // S^T  = K Q^T
+        fa_mma_kmajor(c.tmem + 64, d_v, d_do, idesc_k, false);  // dP^T = V dO^T
         ptx::umma_commit(&c.b->acc_full);
-        ptx::mbar_wait(&c.b->p_full, i & 1);
-        ptx::tc_fence_after();
-        fa_mma_bmn(c.tmem + 128, ptx::smem_u32(c.p1), do_addr, idesc_mn, i > 0);  // dV += P^T  dO
-        fa_mma_bmn(c.tmem + 192, ptx::smem_u32(c.p2), q_addr, idesc_mn, i > 0);   // dK += dS^T Q
+      }
+      __syncwarp();
+      ptx::mbar_wait(&c.b->p_full, i & 1);
+      ptx::tc_fence_after();
+      if (leader) {
+        fa_mma_bmn(c.tmem + 128, d_p, d_do, idesc_mn, i > 0);  // dV += P^T  dO
+        fa_mma_bmn(c.tmem + 192, d_ds, d_q, idesc_mn, i > 0);  // dK += dS^T Q
         ptx::umma_commit(&c.b->p_empty);
         ptx::umma_commit(&c.b->s_empty[s]);
       }
-      ptx::umma_commit(&c.b->o_full);  // accumulators final
+      __syncwarp();
     }
+    if (leader) ptx::umma_commit(&c.b->o_full);  // accumulators final
     __syncwarp();
   } else {
     const int q = c.warp & 3, row = q * 32 + c.lane;
@@ -388,25 +407,31 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dq_kernel(const __grid_co
     if (c.lane == 0) fa_producer(c, p, q0, h, n, n_iter, true);
     __syncwarp();
   } else if (c.warp == 1) {
-    if (c.lane == 0) {
-      ptx::mbar_wait(&c.b->m_full, 0);
-      for (int i = 0; i < n_iter; ++i) {
-        const int s = i % FA_STAGES;
-        const uint32_t k_addr = ptx::smem_u32(c.st + s * 16384), v_addr = k_addr + 8192;
-        ptx::mbar_wait(&c.b->s_full[s], (i / FA_STAGES) & 1);
-        ptx::mbar_wait(&c.b->acc_empty, (i & 1) ^ 1);
-        ptx::tc_fence_after();
-        fa_mma_kmajor(c.tmem, ptx::smem_u32(c.m1), k_addr, idesc_k, false);       // S  = Q  K^T
-        fa_mma_kmajor(c.tmem + 64, ptx::smem_u32(c.m2), v_addr, idesc_k, false);  // dP = dO V^T
+    const bool leader = ptx::elect_one();
+    const uint64_t d_q = fa_desc(c.m1), d_do = fa_desc(c.m2), d_ds = fa_desc(c.p1), d_st = fa_desc(c.st);
+    ptx::mbar_wait(&c.b->m_full, 0);
+    for (int i = 0; i < n_iter; ++i) {
+      const int s = i % FA_STAGES;
+      const uint64_t d_k = d_st + s * 1024, d_v = d_k + 512;
+      ptx::mbar_wait(&c.b->s_full[s], (i / FA_STAGES) & 1);
+      ptx::mbar_wait(&c.b->acc_empty, (i & 1) ^ 1);
+      ptx::tc_fence_after();
+      if (leader) {
+        fa_mma_kmajor(c.tmem, d_q, d_k, idesc_k, false);        // S  = Q  K^T
+        fa_mma_kmajor(c.tmem + 64, d_do, d_v, idesc_k, false);  // dP = dO V^T
         ptx::umma_commit(&c.b->acc_full);
-        ptx::mbar_wait(&c.b->p_full, i & 1);
-        ptx::tc_fence_after();
-        fa_mma_bmn(c.tmem + 128, ptx::smem_u32(c.p1), k_addr, idesc_mn, i > 0);  // dQ += dS K
+      }
+      __syncwarp();
+      ptx::mbar_wait(&c.b->p_full, i & 1);
+      ptx::tc_fence_after();
+      if (leader) {
+        fa_mma_bmn(c.tmem + 128, d_ds, d_k, idesc_mn, i > 0);  // dQ += dS K
         ptx::umma_commit(&c.b->p_empty);
         ptx::umma_commit(&c.b->s_empty[s]);
       }
-      ptx::umma_commit(&c.b->o_full);
+      __syncwarp();
     }
+    if (leader) ptx::umma_commit(&c.b->o_full);
     __syncwarp();
   } else {
     const int q = c.warp & 3, row = q * 32 + c.lane;

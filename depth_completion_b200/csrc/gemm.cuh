@@ -121,45 +121,49 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
   ptx::pdl_launch();
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ TMA producer
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int n_tile, m_tile, b0, b1;
-        gemm_decode_tile(p, tile, n_tile, m_tile, b0, b1);
-        const int n0 = n_tile * p.BN;
-        int m0 = m_tile * GEMM_BM, img = 0, h0 = 0, w0 = 0;
-        if (p.conv) {
-          int tw = m_tile % p.tiles_w;
-          int r = m_tile / p.tiles_w;
-          int th = r % p.tiles_h;
-          img = r / p.tiles_h;
-          h0 = th * p.BH;
-          w0 = tw * p.BW;
-        }
-        int kc_begin = 0, kc_end = p.num_k_chunks;
-        if (p.ksplit > 1) {
-          kc_begin = b0 * p.kc_per_split, kc_end = min(p.num_k_chunks, kc_begin + p.kc_per_split);
-          b0 = 0;
-        }
-        for (int kc = kc_begin; kc < kc_end; ++kc) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full_bar[stage], p.bytesA + p.bytesB);
+    // ------------------------------------------------------------ TMA producer
+    // The whole warp runs the (warp-uniform) loop; one elected lane issues the copies.  No divisions inside the K loop:
+    // (tap, channel chunk) are carried as counters.
+    const bool leader = ptx::elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = p.bytesA + p.bytesB;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int n_tile, m_tile, b0, b1;
+      gemm_decode_tile(p, tile, n_tile, m_tile, b0, b1);
+      const int n0 = n_tile * p.BN;
+      int m0 = m_tile * GEMM_BM, img = 0, h0 = 0, w0 = 0;
+      if (p.conv) {
+        int tw = m_tile % p.tiles_w;
+        int r = m_tile / p.tiles_w;
+        int th = r % p.tiles_h;
+        img = r / p.tiles_h;
+        h0 = th * p.BH;
+        w0 = tw * p.BW;
+      }
+      int kc_begin = 0, kc_end = p.num_k_chunks;
+      if (p.ksplit > 1) {
+        kc_begin = b0 * p.kc_per_split, kc_end = min(p.num_k_chunks, kc_begin + p.kc_per_split);
+        b0 = 0;
+      }
+      // conv modes: tap / channel-chunk counters and the B k-offset of this phase
+      int tap = 0, cc = 0;
+      if (p.conv) tap = kc_begin / p.chunks_per_tap, cc = kc_begin - tap * p.chunks_per_tap;
+      const int pa = (p.conv == 1 && p.nphase > 1) ? (b0 >> 1) : 0, pb = (p.conv == 1 && p.nphase > 1) ? (b0 & 1) : 0;
+      const int kb_off = (p.conv == 1 && p.nphase > 1) ? b0 * p.num_k_chunks * GEMM_BK : 0;
+      for (int kc = kc_begin; kc < kc_end; ++kc) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) {
+          ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
           uint8_t* a_dst = sA + stage * GEMM_A_STAGE;
           uint8_t* b_dst = sB + stage * b_stage;
           const int k0 = kc * GEMM_BK;
           if (p.conv == 1) {
-            const int tap = kc / p.chunks_per_tap;
-            const int cc = kc - tap * p.chunks_per_tap;
-            const int r = tap / p.taps_w, s = tap - r * p.taps_w;
-            const int pa = p.nphase > 1 ? (b0 >> 1) : 0, pb = p.nphase > 1 ? (b0 & 1) : 0;
-            ptx::tma_load_4d(&p.tmA, &full_bar[stage], a_dst, cc * GEMM_BK, w0 + s + p.off_w0 + pb, h0 + r + p.off_h0 + pa,
-                             img);
-            ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst, k0 + b0 * p.num_k_chunks * GEMM_BK, n0, 0, 0);
-          } else if (p.conv == 2) {
-            const int tap = kc / p.chunks_per_tap;  // phase * 4 + tr * 2 + ts
-            const int cc = kc - tap * p.chunks_per_tap;
+            const int r = (p.taps_w == 3) ? (tap >= 6 ? 2 : (tap >= 3 ? 1 : 0)) : (tap >> 1);
+            const int sx = tap - r * p.taps_w;
+            ptx::tma_load_4d(&p.tmA, &full_bar[stage], a_dst, cc * GEMM_BK, w0 + sx + p.off_w0 + pb, h0 + r + p.off_h0 + pa, img);
+            ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst, k0 + kb_off, n0, 0, 0);
+          } else if (p.conv == 2) {  // tap = phase * 4 + tr * 2 + ts
             const int ph = tap >> 2, tr = (tap >> 1) & 1, ts = tap & 1;
             const CUtensorMap* tm = ph == 0 ? &p.tmA : (ph == 1 ? &p.tmA1 : (ph == 2 ? &p.tmA2 : &p.tmA3));
             ptx::tma_load_4d(tm, &full_bar[stage], a_dst, cc * GEMM_BK, w0 - (ts - 1 + (ph & 1)), h0 - (tr - 1 + (ph >> 1)), img);
@@ -178,56 +182,62 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
                 ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst + i * 8192, n0 + i * 64, k0, b0, b1);
             }
           }
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        if (++cc == p.chunks_per_tap) cc = 0, ++tap;
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
-      const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * 256u;
-        int nkc = p.num_k_chunks;
-        if (p.ksplit > 1) {
-          int n_tile, m_tile, b0, b1;
-          gemm_decode_tile(p, tile, n_tile, m_tile, b0, b1);
-          nkc = min(p.num_k_chunks, (b0 + 1) * p.kc_per_split) - b0 * p.kc_per_split;
-        }
-        for (int kc = 0; kc < nkc; ++kc) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(sA + stage * GEMM_A_STAGE);
-          const uint32_t b_addr = ptx::smem_u32(sB + stage * b_stage);
-#pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
-            const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
-            ptx::umma_bf16(d_tmem, adesc, bdesc, p.idesc, (kc | k) != 0 ? 1u : 0u);
-          }
-          ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        ptx::umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
+    // ------------------------------------------------------------ MMA issuer
+    // Whole warp runs the loop with warp-uniform values, one elected lane issues tcgen05.mma / commit.  The smem
+    // descriptors are linear in (stage, k): only the low word changes, by precomputed increments.
+    const bool leader = ptx::elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    const uint64_t a_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sA), p.a_mn ? 8192u : 16u, 1024);
+    const uint64_t b_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sB), p.b_mn ? 8192u : 16u, 1024);
+    const uint32_t a_kinc = (p.a_mn ? 2048u : 32u) >> 4, b_kinc = (p.b_mn ? 2048u : 32u) >> 4;
+    const uint32_t a_sinc = GEMM_A_STAGE >> 4, b_sinc = b_stage >> 4;
+    const uint32_t idesc = p.idesc;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * 256u;
+      int nkc = p.num_k_chunks;
+      if (p.ksplit > 1) {
+        int n_tile, m_tile, b0, b1;
+        gemm_decode_tile(p, tile, n_tile, m_tile, b0, b1);
+        nkc = min(p.num_k_chunks, (b0 + 1) * p.kc_per_split) - b0 * p.kc_per_split;
       }
+      for (int kc = 0; kc < nkc; ++kc) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        if (leader) {
+          const uint64_t ad = a_desc0 + static_cast<uint64_t>(stage * a_sinc);
+          const uint64_t bd = b_desc0 + static_cast<uint64_t>(stage * b_sinc);
+          ptx::umma_bf16(d_tmem, ad, bd, idesc, kc != 0 ? 1u : 0u);
+          ptx::umma_bf16(d_tmem, ad + a_kinc, bd + b_kinc, idesc, 1u);
+          ptx::umma_bf16(d_tmem, ad + 2 * a_kinc, bd + 2 * b_kinc, idesc, 1u);
+          ptx::umma_bf16(d_tmem, ad + 3 * a_kinc, bd + 3 * b_kinc, idesc, 1u);
+          ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (leader) ptx::umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+      __syncwarp();
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue warps (TMEM -> global)
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
