@@ -143,10 +143,26 @@ __device__ __forceinline__ void fa_warp_arrive(uint64_t* bar, int lane) {
 }
 
 // ---------------------------------------------------------------------------------------------------- forward
+// Software-pipelined: S is double-buffered in TMEM (S(i+1) = Q K(i+1)^T is issued before P(i) V(i)), P is
+// double-buffered in shared memory, and the read-back of O_tile(i-1) is deferred until after P(i) has been handed to the
+// tensor core, so the softmax threads never wait for an MMA they have just requested.
 __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_constant__ FlashParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr uint32_t TCOLS = 128;  // S: [0,64)  O tile: [64,128)
+  constexpr uint32_t TCOLS = 256;  // S0: [0,64)  S1: [64,128)  O tile: [128,192)
   FaCtx c = fa_setup(smem_raw, TCOLS);
+  // extra barriers for the double buffers live in the spare m2 tile slot's first bytes? no: reuse FaSmem fields:
+  //   acc_full/acc_empty -> S buffer 0, o_full/o_empty -> O tile, p_full/p_empty -> P buffer 0; buffer-1 barriers below.
+  uint64_t* x_bar = reinterpret_cast<uint64_t*>(c.m2);  // [0] s1_full [1] s1_empty [2] p1_full [3] p1_empty (m2 tile unused here)
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&x_bar[0], 1), ptx::mbar_init(&x_bar[1], 4), ptx::mbar_init(&x_bar[2], 4), ptx::mbar_init(&x_bar[3], 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  auto sacc_full = [&](int b) { return b ? &x_bar[0] : &c.b->acc_full; };
+  auto sacc_empty = [&](int b) { return b ? &x_bar[1] : &c.b->acc_empty; };
+  auto pf = [&](int b) { return b ? &x_bar[2] : &c.b->p_full; };
+  auto pe = [&](int b) { return b ? &x_bar[3] : &c.b->p_empty; };
+  auto pbuf = [&](int b) { return b ? c.p2 : c.p1; };
   const int q0 = blockIdx.x * 128, h = blockIdx.y, n = blockIdx.z;
   const int n_iter = (p.T + 63) / 64;
   const uint32_t idesc_s = ptx::make_idesc_bf16(128, 64, 0, 0), idesc_o = ptx::make_idesc_bf16(128, 64, 0, 1);
@@ -155,26 +171,36 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
     __syncwarp();
   } else if (c.warp == 1) {
     const bool leader = ptx::elect_one();
-    const uint64_t d_q = fa_desc(c.m1), d_p = fa_desc(c.p1), d_st = fa_desc(c.st);
+    const uint64_t d_q = fa_desc(c.m1), d_st = fa_desc(c.st);
+    const uint64_t d_p0 = fa_desc(c.p1), d_p1 = fa_desc(c.p2);
     ptx::mbar_wait(&c.b->m_full, 0);
+    ptx::mbar_wait(&c.b->s_full[0], 0);
+    ptx::tc_fence_after();
+    if (leader) {
+      fa_mma_kmajor(c.tmem, d_q, d_st, idesc_s, false);  // S(0)
+      ptx::umma_commit(sacc_full(0));
+    }
+    __syncwarp();
     for (int i = 0; i < n_iter; ++i) {
-      const int s = i % FA_STAGES;
-      const uint64_t d_k = d_st + s * 1024, d_v = d_k + 512;
-      ptx::mbar_wait(&c.b->s_full[s], (i / FA_STAGES) & 1);
-      ptx::mbar_wait(&c.b->acc_empty, (i & 1) ^ 1);
-      ptx::tc_fence_after();
-      if (leader) {
-        fa_mma_kmajor(c.tmem, d_q, d_k, idesc_s, false);  // S = Q K^T
-        ptx::umma_commit(&c.b->acc_full);
+      const int s = i % FA_STAGES, b = i & 1;
+      if (i + 1 < n_iter) {  // S(i+1) = Q K(i+1)^T into the other S buffer, ahead of P(i) V(i)
+        const int s1 = (i + 1) % FA_STAGES, b1 = (i + 1) & 1;
+        ptx::mbar_wait(&c.b->s_full[s1], ((i + 1) / FA_STAGES) & 1);
+        ptx::mbar_wait(sacc_empty(b1), (((i + 1) >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        if (leader) {
+          fa_mma_kmajor(c.tmem + b1 * 64, d_q, d_st + s1 * 1024, idesc_s, false);
+          ptx::umma_commit(sacc_full(b1));
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      ptx::mbar_wait(&c.b->p_full, i & 1);
+      ptx::mbar_wait(pf(b), (i >> 1) & 1);
       ptx::mbar_wait(&c.b->o_empty, (i & 1) ^ 1);
       ptx::tc_fence_after();
       if (leader) {
-        fa_mma_bmn(c.tmem + 64, d_p, d_v, idesc_o, false);  // O_tile = P V
+        fa_mma_bmn(c.tmem + 128, b ? d_p1 : d_p0, d_st + s * 1024 + 512, idesc_o, false);  // O_tile = P(i) V(i)
         ptx::umma_commit(&c.b->o_full);
-        ptx::umma_commit(&c.b->p_empty);
+        ptx::umma_commit(pe(b));
         ptx::umma_commit(&c.b->s_empty[s]);
       }
       __syncwarp();
@@ -188,14 +214,15 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
 #pragma unroll
     for (int j = 0; j < 64; ++j) o[j] = 0.f;
     for (int i = 0; i < n_iter; ++i) {
-      ptx::mbar_wait(&c.b->acc_full, i & 1);
+      const int b = i & 1;
+      ptx::mbar_wait(sacc_full(b), (i >> 1) & 1);
       ptx::tc_fence_after();
       uint32_t raw[64];
-      ptx::tmem_ld32(t_row, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
-      ptx::tmem_ld32(t_row + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
+      ptx::tmem_ld32(t_row + b * 64, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
+      ptx::tmem_ld32(t_row + b * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
-      fa_warp_arrive(&c.b->acc_empty, c.lane);
+      fa_warp_arrive(sacc_empty(b), c.lane);
       const int valid = p.T - i * 64;  // keys of this tile that exist
       float mx = -INFINITY;
       if (valid >= 64) {
@@ -216,7 +243,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
       const float m_new = fmaxf(m, mx);
       const float alpha = fa_exp2(m - m_new);
       float sum = 0.f;
-      ptx::mbar_wait(&c.b->p_empty, (i & 1) ^ 1);
+      ptx::mbar_wait(pe(b), ((i >> 1) & 1) ^ 1);
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
         float v[8];
@@ -225,21 +252,31 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
           v[j] = fa_exp2(__uint_as_float(raw[ch * 8 + j]) - m_new);
           sum += v[j];
         }
-        fa_store_row_chunk(c.p1, row, ch, v);
+        fa_store_row_chunk(pbuf(b), row, ch, v);
       }
       ptx::fence_proxy_async_smem();
-      fa_warp_arrive(&c.b->p_full, c.lane);
+      fa_warp_arrive(pf(b), c.lane);
       l = l * alpha + sum;
       m = m_new;
+      if (i > 0) {  // O_tile(i-1) has long completed: o = (o + O_tile(i-1)) * alpha_i
+        ptx::mbar_wait(&c.b->o_full, (i - 1) & 1);
+        ptx::tc_fence_after();
+        ptx::tmem_ld32(t_row + 128, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
+        ptx::tmem_ld32(t_row + 160, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        fa_warp_arrive(&c.b->o_empty, c.lane);
 #pragma unroll
-      for (int j = 0; j < 64; ++j) o[j] *= alpha;
-      ptx::mbar_wait(&c.b->o_full, i & 1);
+        for (int j = 0; j < 64; ++j) o[j] = (o[j] + __uint_as_float(raw[j])) * alpha;
+      }
+    }
+    {
+      uint32_t raw[64];
+      ptx::mbar_wait(&c.b->o_full, (n_iter - 1) & 1);
       ptx::tc_fence_after();
-      ptx::tmem_ld32(t_row + 64, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
-      ptx::tmem_ld32(t_row + 96, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
+      ptx::tmem_ld32(t_row + 128, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
+      ptx::tmem_ld32(t_row + 160, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
       ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      fa_warp_arrive(&c.b->o_empty, c.lane);
 #pragma unroll
       for (int j = 0; j < 64; ++j) o[j] += __uint_as_float(raw[j]);
     }
