@@ -331,18 +331,29 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dkv_kernel(const __grid_c
     const bool leader = ptx::elect_one();
     const uint64_t d_k = fa_desc(c.m1), d_v = fa_desc(c.m2), d_p = fa_desc(c.p1), d_ds = fa_desc(c.p2), d_st = fa_desc(c.st);
     ptx::mbar_wait(&c.b->m_full, 0);
+    ptx::mbar_wait(&c.b->s_full[0], 0);
+    ptx::tc_fence_after();
+    if (leader) {
+      fa_mma_kmajor(c.tmem, d_k, d_st, idesc_k, false);             // S^T(0)  = K Q(0)^T
+      fa_mma_kmajor(c.tmem + 64, d_v, d_st + 512, idesc_k, false);  // dP^T(0) = V dO(0)^T
+      ptx::umma_commit(&c.b->acc_full);
+    }
+    __syncwarp();
     for (int i = 0; i < n_iter; ++i) {
       const int s = i % FA_STAGES;
       const uint64_t d_q = d_st + s * 1024, d_do = d_q + 512;
-      ptx::mbar_wait(&c.b->s_full[s], (i / FA_STAGES) & 1);
-      ptx::mbar_wait(&c.b->acc_empty, (i & 1) ^ 1);
-      ptx::tc_fence_after();
-      if (leader) {
-        fa_mma_kmajor(c.tmem, d_k, d_q, idesc_k, false);        // S^T  = K Q^T
-        fa_mma_kmajor(c.tmem + 64, d_v, d_do, idesc_k, false);  // dP^T = V dO^T
-        ptx::umma_commit(&c.b->acc_full);
+      if (i + 1 < n_iter) {  // scores of the next query tile as soon as the softmax threads hold tile i in registers
+        const int s1 = (i + 1) % FA_STAGES;
+        ptx::mbar_wait(&c.b->s_full[s1], ((i + 1) / FA_STAGES) & 1);
+        ptx::mbar_wait(&c.b->acc_empty, i & 1);
+        ptx::tc_fence_after();
+        if (leader) {
+          fa_mma_kmajor(c.tmem, d_k, d_st + s1 * 1024, idesc_k, false);
+          fa_mma_kmajor(c.tmem + 64, d_v, d_st + s1 * 1024 + 512, idesc_k, false);
+          ptx::umma_commit(&c.b->acc_full);
+        }
+        __syncwarp();
       }
-      __syncwarp();
       ptx::mbar_wait(&c.b->p_full, i & 1);
       ptx::tc_fence_after();
       if (leader) {
@@ -374,34 +385,33 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dkv_kernel(const __grid_c
       fa_named_sync();
       ptx::mbar_wait(&c.b->acc_full, i & 1);
       ptx::tc_fence_after();
-      ptx::mbar_wait(&c.b->p_empty, (i & 1) ^ 1);
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        uint32_t rs[16], rd[16];
-        ptx::tmem_ld16(t_row + q4 * 16, rs);
-        ptx::tmem_ld16(t_row + 64 + q4 * 16, rd);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          float pv[8], dv[8];
-          const float4 l0 = *reinterpret_cast<const float4*>(&c.b->lse_s[sb][q4 * 16 + ch * 8]);
-          const float4 l1 = *reinterpret_cast<const float4*>(&c.b->lse_s[sb][q4 * 16 + ch * 8 + 4]);
-          const float4 d0 = *reinterpret_cast<const float4*>(&c.b->del_s[sb][q4 * 16 + ch * 8]);
-          const float4 d1 = *reinterpret_cast<const float4*>(&c.b->del_s[sb][q4 * 16 + ch * 8 + 4]);
-          const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-          const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float pr = fa_exp2(fmaf(__uint_as_float(rs[ch * 8 + j]), c2, -ls[j]));
-            pv[j] = pr;
-            dv[j] = pr * (__uint_as_float(rd[ch * 8 + j]) - dl[j]) * p.scale;
-          }
-          fa_store_row_chunk(c.p1, row, q4 * 2 + ch, pv);
-          fa_store_row_chunk(c.p2, row, q4 * 2 + ch, dv);
-        }
-      }
+      uint32_t rs[64], rd[64];  // whole S^T / dP^T row of this tile; frees the TMEM buffers for the next tile's MMAs
+      ptx::tmem_ld32(t_row, *reinterpret_cast<uint32_t(*)[32]>(&rs[0]));
+      ptx::tmem_ld32(t_row + 32, *reinterpret_cast<uint32_t(*)[32]>(&rs[32]));
+      ptx::tmem_ld32(t_row + 64, *reinterpret_cast<uint32_t(*)[32]>(&rd[0]));
+      ptx::tmem_ld32(t_row + 96, *reinterpret_cast<uint32_t(*)[32]>(&rd[32]));
+      ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       fa_warp_arrive(&c.b->acc_empty, c.lane);
+      ptx::mbar_wait(&c.b->p_empty, (i & 1) ^ 1);
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        float pv[8], dv[8];
+        const float4 l0 = *reinterpret_cast<const float4*>(&c.b->lse_s[sb][ch * 8]);
+        const float4 l1 = *reinterpret_cast<const float4*>(&c.b->lse_s[sb][ch * 8 + 4]);
+        const float4 d0 = *reinterpret_cast<const float4*>(&c.b->del_s[sb][ch * 8]);
+        const float4 d1 = *reinterpret_cast<const float4*>(&c.b->del_s[sb][ch * 8 + 4]);
+        const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float pr = fa_exp2(fmaf(__uint_as_float(rs[ch * 8 + j]), c2, -ls[j]));
+          pv[j] = pr;
+          dv[j] = pr * (__uint_as_float(rd[ch * 8 + j]) - dl[j]) * p.scale;
+        }
+        fa_store_row_chunk(c.p1, row, ch, pv);
+        fa_store_row_chunk(c.p2, row, ch, dv);
+      }
       ptx::fence_proxy_async_smem();
       fa_warp_arrive(&c.b->p_full, c.lane);
     }
@@ -447,18 +457,29 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dq_kernel(const __grid_co
     const bool leader = ptx::elect_one();
     const uint64_t d_q = fa_desc(c.m1), d_do = fa_desc(c.m2), d_ds = fa_desc(c.p1), d_st = fa_desc(c.st);
     ptx::mbar_wait(&c.b->m_full, 0);
+    ptx::mbar_wait(&c.b->s_full[0], 0);
+    ptx::tc_fence_after();
+    if (leader) {
+      fa_mma_kmajor(c.tmem, d_q, d_st, idesc_k, false);              // S(0)  = Q  K(0)^T
+      fa_mma_kmajor(c.tmem + 64, d_do, d_st + 512, idesc_k, false);  // dP(0) = dO V(0)^T
+      ptx::umma_commit(&c.b->acc_full);
+    }
+    __syncwarp();
     for (int i = 0; i < n_iter; ++i) {
       const int s = i % FA_STAGES;
-      const uint64_t d_k = d_st + s * 1024, d_v = d_k + 512;
-      ptx::mbar_wait(&c.b->s_full[s], (i / FA_STAGES) & 1);
-      ptx::mbar_wait(&c.b->acc_empty, (i & 1) ^ 1);
-      ptx::tc_fence_after();
-      if (leader) {
-        fa_mma_kmajor(c.tmem, d_q, d_k, idesc_k, false);        // S  = Q  K^T
-        fa_mma_kmajor(c.tmem + 64, d_do, d_v, idesc_k, false);  // dP = dO V^T
-        ptx::umma_commit(&c.b->acc_full);
+      const uint64_t d_k = d_st + s * 1024;
+      if (i + 1 < n_iter) {
+        const int s1 = (i + 1) % FA_STAGES;
+        ptx::mbar_wait(&c.b->s_full[s1], ((i + 1) / FA_STAGES) & 1);
+        ptx::mbar_wait(&c.b->acc_empty, i & 1);
+        ptx::tc_fence_after();
+        if (leader) {
+          fa_mma_kmajor(c.tmem, d_q, d_st + s1 * 1024, idesc_k, false);
+          fa_mma_kmajor(c.tmem + 64, d_do, d_st + s1 * 1024 + 512, idesc_k, false);
+          ptx::umma_commit(&c.b->acc_full);
+        }
+        __syncwarp();
       }
-      __syncwarp();
       ptx::mbar_wait(&c.b->p_full, i & 1);
       ptx::tc_fence_after();
       if (leader) {
@@ -481,36 +502,35 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dq_kernel(const __grid_co
     for (int i = 0; i < n_iter; ++i) {
       ptx::mbar_wait(&c.b->acc_full, i & 1);
       ptx::tc_fence_after();
+      uint32_t rs[64], rd[64];
+      ptx::tmem_ld32(t_row, *reinterpret_cast<uint32_t(*)[32]>(&rs[0]));
+      ptx::tmem_ld32(t_row + 32, *reinterpret_cast<uint32_t(*)[32]>(&rs[32]));
+      ptx::tmem_ld32(t_row + 64, *reinterpret_cast<uint32_t(*)[32]>(&rd[0]));
+      ptx::tmem_ld32(t_row + 96, *reinterpret_cast<uint32_t(*)[32]>(&rd[32]));
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      fa_warp_arrive(&c.b->acc_empty, c.lane);
       ptx::mbar_wait(&c.b->p_empty, (i & 1) ^ 1);
       const int valid = p.T - i * 64;
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        uint32_t rs[16], rd[16];
-        ptx::tmem_ld16(t_row + q4 * 16, rs);
-        ptx::tmem_ld16(t_row + 64 + q4 * 16, rd);
-        ptx::tmem_ld_wait();
+      for (int ch = 0; ch < 8; ++ch) {
+        float dv[8];
+        if (valid >= 64) {
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          float dv[8];
-          if (valid >= 64) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float pr = fa_exp2(fmaf(__uint_as_float(rs[ch * 8 + j]), c2, nlse));
-              dv[j] = pr * (__uint_as_float(rd[ch * 8 + j]) - del) * p.scale;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int kk = q4 * 16 + ch * 8 + j;
-              const float pr = kk < valid ? fa_exp2(fmaf(__uint_as_float(rs[ch * 8 + j]), c2, nlse)) : 0.f;
-              dv[j] = pr * (__uint_as_float(rd[ch * 8 + j]) - del) * p.scale;
-            }
+          for (int j = 0; j < 8; ++j) {
+            const float pr = fa_exp2(fmaf(__uint_as_float(rs[ch * 8 + j]), c2, nlse));
+            dv[j] = pr * (__uint_as_float(rd[ch * 8 + j]) - del) * p.scale;
           }
-          fa_store_row_chunk(c.p1, row, q4 * 2 + ch, dv);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int kk = ch * 8 + j;
+            const float pr = kk < valid ? fa_exp2(fmaf(__uint_as_float(rs[ch * 8 + j]), c2, nlse)) : 0.f;
+            dv[j] = pr * (__uint_as_float(rd[ch * 8 + j]) - del) * p.scale;
+          }
         }
+        fa_store_row_chunk(c.p1, row, ch, dv);
       }
-      ptx::tc_fence_before();
-      fa_warp_arrive(&c.b->acc_empty, c.lane);
       ptx::fence_proxy_async_smem();
       fa_warp_arrive(&c.b->p_full, c.lane);
     }
