@@ -129,8 +129,8 @@ struct GroupNormOp : Op {
   }
   void fwd(cudaStream_t st) override;
   void bwd(cudaStream_t st) override;
-  int n_fwd() const override { return 3; }
-  int n_bwd() const override { return 3; }
+  int n_fwd() const override { return 2; }
+  int n_bwd() const override { return 2; }
 };
 struct LayerNormOp : Op {
   Tensor *x, *y;
@@ -204,6 +204,39 @@ struct CrossAttn2Op : Op {  // attention over the 2 tokens of the empty-prompt e
     launch_k(xattn2_bwd_kernel, dim3(static_cast<int>((warps * 32 + 255) / 256)), dim3(256), 0, st, q->d, q->ld, o->g, o->ld, q->rows(),
                                                                                  heads, kc, vc, 0.125f, q->g, q->ld, acc);
   }
+};
+struct CrossAttnFusedOp : Op {  // LN2 + attn2 (2 constant key tokens) + to_out + residual, algebraically collapsed
+  Tensor *x, *y;
+  int heads;
+  const float *gamma, *beta, *At, *U, *bo;
+  float* stats;
+  bool acc = false;
+  void plan_bwd() override {
+    acc = x->grad_set;
+    x->grad_set = true;
+  }
+  template <int NV>
+  void run(cudaStream_t st, bool backward) {
+    const long long rows = x->rows();
+    const dim3 grid(static_cast<unsigned>((rows * 32 + 255) / 256)), block(256);
+    if (!backward)
+      launch_k(xattn_fused_fwd_kernel<NV>, grid, block, 0, st, x->d, x->ld, rows, x->c, 2 * heads, gamma, beta, At, U, bo, y->d,
+               y->ld, stats);
+    else
+      launch_k(xattn_fused_bwd_kernel<NV>, grid, block, 0, st, x->d, x->ld, y->g, y->ld, rows, x->c, 2 * heads, gamma, beta, At,
+               U, stats, x->g, x->ld, static_cast<int>(acc));
+  }
+  void dispatch(cudaStream_t st, bool backward) {
+    switch ((x->c / 8 + 31) / 32) {
+      case 1: run<1>(st, backward); break;
+      case 2: run<2>(st, backward); break;
+      case 3: run<3>(st, backward); break;
+      case 4: run<4>(st, backward); break;
+      default: run<5>(st, backward); break;
+    }
+  }
+  void fwd(cudaStream_t st) override { dispatch(st, false); }
+  void bwd(cudaStream_t st) override { dispatch(st, true); }
 };
 struct UpsampleOp : Op {
   Tensor *x, *y;
@@ -279,6 +312,7 @@ struct Engine {
   float* gn_partial = nullptr;
   size_t gn_partial_floats = 0;
   float* gn_gstats = nullptr;
+  unsigned int* gn_ticket = nullptr;
   float* attn_S = nullptr;
   size_t attn_S_floats = 0;
   // time embedding
@@ -298,6 +332,10 @@ struct Engine {
     WeightSlot *wk, *wv;
     float *kc, *vc;
     int d;
+    // collapsed form (CrossAttnFusedOp): At / U built from to_q / to_out.0 in prepare()
+    WeightSlot *wq = nullptr, *wo = nullptr;
+    float *At = nullptr, *U = nullptr;
+    int heads = 0;
   };
   std::vector<XUse> xuses;
   // step state
@@ -419,19 +457,16 @@ inline void LinearOp::bwd(cudaStream_t st) {
 }
 inline void GroupNormOp::fwd(cudaStream_t st) {
   const int grid = s.N * s.blocks_per_img;
-  launch_k(gn_stats_kernel, dim3(grid), dim3(threads), 2 * s.G * sizeof(float), st, x->d, s, E->gn_partial);
-  launch_k(gn_finalize_kernel, dim3((s.N * s.G * 32 + 127) / 128), dim3(128), 0, st, E->gn_partial, s.N, s.G, s.blocks_per_img,
-                                                              1.0 * s.HW * (s.C / s.G), eps, 0, stats);
+  launch_k(gn_stats_kernel, dim3(grid), dim3(threads), 2 * s.G * sizeof(float), st, x->d, s, E->gn_partial, eps, stats,
+           E->gn_ticket);
   launch_k(gn_apply_kernel, dim3(grid), dim3(threads), 0, st, x->d, s, stats, gamma, beta, silu, y->d, y->ld);
 }
 inline void GroupNormOp::bwd(cudaStream_t st) {
   const int grid = s.N * s.blocks_per_img;
-  launch_k(gn_bwd_stats_kernel, dim3(grid), dim3(threads_b), 2 * s.G * sizeof(float), st, x->d, y->g, y->ld, s, stats, gamma, beta, silu,
-                                                                      E->gn_partial);
-  launch_k(gn_finalize_kernel, dim3((s.N * s.G * 32 + 127) / 128), dim3(128), 0, st, E->gn_partial, s.N, s.G, s.blocks_per_img,
-                                                              1.0 * s.HW * (s.C / s.G), 0.f, 1, E->gn_gstats);
-  launch_k(gn_bwd_apply_kernel, dim3(grid), dim3(threads_b), 0, st, x->d, y->g, y->ld, s, stats, E->gn_gstats, gamma, beta, silu, x->g, x->ld,
-                                                acc);
+  launch_k(gn_bwd_stats_kernel, dim3(grid), dim3(threads_b), 2 * s.G * sizeof(float), st, x->d, y->g, y->ld, s, stats, gamma,
+           beta, silu, E->gn_partial, E->gn_gstats, E->gn_ticket);
+  launch_k(gn_bwd_apply_kernel, dim3(grid), dim3(threads_b), 0, st, x->d, y->g, y->ld, s, stats, E->gn_gstats, gamma, beta,
+           silu, x->g, x->ld, acc);
 }
 
 inline void SelfAttnOp::plan_bwd() {
@@ -713,10 +748,31 @@ inline Tensor* Engine::transformer(Tensor* x, int heads, const std::string& key,
   Tensor* ao = self_attention(qkv, heads, tb + ".attn1");
   h = linear(ao, d, tb + ".attn1.to_out.0", true, h);
   // --- cross attention over the 2 empty-prompt tokens (K, V precomputed in prepare())
-  Tensor* n2 = layer_norm(h, tb + ".norm2");
-  Tensor* q2 = linear(n2, d, tb + ".attn2.to_q", false);
-  Tensor* o2 = new_tensor(x->n, x->h, x->w, d, "");
-  {
+  MDC_CHECK(d / heads == 64 && 2 * heads <= XA_MAXC, "cross-attention needs head_dim 64 and <= %d heads", XA_MAXC / 2);
+  if (!getenv("MDC_NO_XFUSE")) {  // LN2 + to_q + attention + to_out + residual collapsed into one kernel
+    XUse u;
+    u.wk = slot(tb + ".attn2.to_k.weight", W_LIN, d, cfg.cross_dim);
+    u.wv = slot(tb + ".attn2.to_v.weight", W_LIN, d, cfg.cross_dim);
+    u.wq = slot(tb + ".attn2.to_q.weight", W_LIN, d, d);
+    u.wo = slot(tb + ".attn2.to_out.0.weight", W_LIN, d, d);
+    WeightSlot* bo = slot(tb + ".attn2.to_out.0.bias", W_VEC, d, 0);
+    WeightSlot* ga = slot(tb + ".norm2.weight", W_VEC, d, 0);
+    WeightSlot* be = slot(tb + ".norm2.bias", W_VEC, d, 0);
+    u.kc = arena.make<float>(2ull * d), u.vc = arena.make<float>(2ull * d);
+    u.At = arena.make<float>(2ull * heads * d), u.U = arena.make<float>(2ull * heads * d);
+    u.d = d, u.heads = heads;
+    xuses.push_back(u);
+    Tensor* h2 = new_tensor(x->n, x->h, x->w, d, "");
+    auto* op = new CrossAttnFusedOp();
+    op->x = h, op->y = h2, op->heads = heads, op->gamma = ga->vec, op->beta = be->vec, op->At = u.At, op->U = u.U;
+    op->bo = bo->vec;
+    op->stats = arena.make<float>(2ull * x->rows());
+    push(op, tb + ".attn2");
+    h = h2;
+  } else {
+    Tensor* n2 = layer_norm(h, tb + ".norm2");
+    Tensor* q2 = linear(n2, d, tb + ".attn2.to_q", false);
+    Tensor* o2 = new_tensor(x->n, x->h, x->w, d, "");
     XUse u;
     u.wk = slot(tb + ".attn2.to_k.weight", W_LIN, d, cfg.cross_dim);
     u.wv = slot(tb + ".attn2.to_v.weight", W_LIN, d, cfg.cross_dim);
@@ -726,10 +782,9 @@ inline Tensor* Engine::transformer(Tensor* x, int heads, const std::string& key,
     xuses.push_back(u);
     auto* op = new CrossAttn2Op();
     op->q = q2, op->o = o2, op->heads = heads, op->kc = u.kc, op->vc = u.vc;
-    MDC_CHECK(d / heads == 64, "cross-attention head_dim must be 64 (got %d)", d / heads);
     push(op, tb + ".attn2");
+    h = linear(o2, d, tb + ".attn2.to_out.0", true, h);
   }
-  h = linear(o2, d, tb + ".attn2.to_out.0", true, h);
   // --- GEGLU feed-forward
   Tensor* n3 = layer_norm(h, tb + ".norm3");
   Tensor* pr = linear(n3, 8 * d, tb + ".ff.net.0.proj", true);
@@ -920,6 +975,7 @@ inline void Engine::build_decoder() {
 inline void Engine::finalize_plans() {
   gn_partial = arena.make<float>(gn_partial_floats + 64);
   gn_gstats = arena.make<float>(2ull * 64 * MAXN + 64);
+  gn_ticket = arena.make<unsigned int>(MAXN + 16);
   attn_S = arena.make<float>(attn_S_floats + 64);
   temb_cur = arena.make<float>(temb_total + 64);
   for (auto* ops : {&unet_ops, &dec_ops}) {
@@ -1097,6 +1153,11 @@ inline void Engine::prepare(const void* ctx_bf16, const float* alphas_cumprod, c
     for (auto& u : xuses) {
       lin(u.wk->w, u.wk->ld_w, nullptr, ctxf, cfg.cross_dim, cfg.cross_dim, u.d, 0, u.kc, u.d, 2);
       lin(u.wv->w, u.wv->ld_w, nullptr, ctxf, cfg.cross_dim, cfg.cross_dim, u.d, 0, u.vc, u.d, 2);
+      if (u.At) {
+        const int tot = 2 * u.heads * u.d;
+        xattn_collapse_kernel<<<(tot + 255) / 256, 256, 0, stream>>>(u.wq->w, u.wq->ld_w, u.wo->w, u.wo->ld_w, u.kc, u.vc, u.d,
+                                                                     u.heads, 0.125f, u.At, u.U);
+      }
     }
     MDC_CUDA(cudaStreamSynchronize(stream));
     cudaFree(ctxf);
