@@ -749,7 +749,7 @@ inline Tensor* Engine::transformer(Tensor* x, int heads, const std::string& key,
   h = linear(ao, d, tb + ".attn1.to_out.0", true, h);
   // --- cross attention over the 2 empty-prompt tokens (K, V precomputed in prepare())
   MDC_CHECK(d / heads == 64 && 2 * heads <= XA_MAXC, "cross-attention needs head_dim 64 and <= %d heads", XA_MAXC / 2);
-  if (!getenv("MDC_NO_XFUSE")) {  // LN2 + to_q + attention + to_out + residual collapsed into one kernel
+  if (getenv("MDC_XFUSE")) {  // experimental (slower than the 4-kernel path at present): LN2 + to_q + attention + to_out + residual in one kernel
     XUse u;
     u.wk = slot(tb + ".attn2.to_k.weight", W_LIN, d, cfg.cross_dim);
     u.wv = slot(tb + ".attn2.to_v.weight", W_LIN, d, cfg.cross_dim);

@@ -28,7 +28,8 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_A_STAGE = GEMM_BM * GEMM_BK * 2;  // 16 KiB
 constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_SMEM_BUDGET = 200 * 1024;
+constexpr int GEMM_SMEM_BUDGET = 225 * 1024;
+constexpr int GEMM_HEADER = 4096 + 2 * 8192;  // barriers + staged bias (4 KiB) + two 128 x 32 bf16 store panels
 constexpr int GEMM_TMEM_COLS = 512;
 
 struct GemmParams {
@@ -60,6 +61,13 @@ struct GemmParams {
   const __nv_bfloat16* res;
   long long ldr, sr0, sr1;
   float alpha;
+  // TMA-store epilogue (bf16 outputs): each 128-row x 32-column chunk is staged in 64B-swizzled shared memory and
+  // written with one bulk tensor store (coalesced, hardware-clipped) instead of 16-byte scattered stores per thread.
+  int tma_store;
+  CUtensorMap tmC, tmC1, tmC2, tmC3;  // tmC1..3: phases 1..3 of the fused upsample conv
+  // cluster B-multicast: `cs` CTAs (consecutive m-tiles of one n-tile) form a cluster; each loads BN/cs rows of the
+  // B tile and multicasts them to all, so the weight tile crosses L2 -> SM once per cluster instead of once per CTA.
+  int cs;
   // split-K (nb0 = nb1 = 1 only): CTA (tile, s) accumulates k-chunks [s*kc_per_split, ...) and writes its raw fp32
   // partial to ws[s][row][col]; splitk_reduce_kernel sums the partials and applies the epilogue.
   int ksplit, kc_per_split;
@@ -67,13 +75,16 @@ struct GemmParams {
   long long ws_ld, ws_split_stride;
 };
 
-// tile -> (n_tile, m_tile, b0, b1); with split-K the batch slot b0 carries the split index instead.
+// work item -> (n_tile, m_tile, b0, b1); with split-K the batch slot b0 carries the split index instead.  With
+// clusters a work item is a group of `cs` consecutive m-tiles and CTA rank r takes m_tile = group * cs + r (which may
+// be >= m_tiles in the last group: such a CTA still feeds the multicast but stores nothing).
 __device__ __forceinline__ void gemm_decode_tile(const GemmParams& p, int tile, int& n_tile, int& m_tile, int& b0,
-                                                 int& b1) {
+                                                 int& b1, int rank = 0) {
   n_tile = tile % p.n_tiles;
   int rest = tile / p.n_tiles;
-  m_tile = rest % p.m_tiles;
-  int b = rest / p.m_tiles;
+  const int m_groups = (p.m_tiles + p.cs - 1) / p.cs;
+  m_tile = (rest % m_groups) * p.cs + rank;
+  int b = rest / m_groups;
   const int nb0 = p.ksplit > 1 ? p.ksplit : p.nb0;
   b0 = b % nb0;
   b1 = b / nb0;
@@ -89,18 +100,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* sbias_base = reinterpret_cast<float*>(smem + 1024);  // 2 x 256 floats
-  uint8_t* sA = smem + 4096;
+  uint8_t* spanel = smem + 4096;  // 2 x 8 KiB output panels
+  uint8_t* sA = smem + GEMM_HEADER;
   const uint32_t b_stage = static_cast<uint32_t>(p.BN) * 128u;
   uint8_t* sB = sA + p.stages * GEMM_A_STAGE;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles * (p.ksplit > 1 ? p.ksplit : p.nb0) * p.nb1;
+  const int total_tiles = ((p.m_tiles + p.cs - 1) / p.cs) * p.n_tiles * (p.ksplit > 1 ? p.ksplit : p.nb0) * p.nb1;
+  const int rank = p.cs > 1 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int cluster_id = blockIdx.x / p.cs, n_clusters = gridDim.x / p.cs;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
-      ptx::mbar_init(&empty_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], p.cs);  // every CTA of the cluster must release the stage before it is refilled
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
@@ -115,6 +129,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.cs > 1) ptx::cluster_sync_all();  // peers' barriers are initialised before any multicast / remote arrive
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail.
   // All CTAs of this grid hold their TMEM before the next grid may start (no allocation deadlock).
   ptx::pdl_wait();
@@ -128,9 +143,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t tx_bytes = p.bytesA + p.bytesB;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int bn_slice = p.BN / p.cs;                       // rows of the B tile this CTA loads (and multicasts)
+    const uint32_t b_slice = static_cast<uint32_t>(bn_slice) * 128u;
+    const uint16_t mc_mask = static_cast<uint16_t>((1u << p.cs) - 1);
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
       int n_tile, m_tile, b0, b1;
-      gemm_decode_tile(p, tile, n_tile, m_tile, b0, b1);
+      gemm_decode_tile(p, tile, n_tile, m_tile, b0, b1, rank);
       const int n0 = n_tile * p.BN;
       int m0 = m_tile * GEMM_BM, img = 0, h0 = 0, w0 = 0;
       if (p.conv) {
@@ -162,12 +180,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
             const int r = (p.taps_w == 3) ? (tap >= 6 ? 2 : (tap >= 3 ? 1 : 0)) : (tap >> 1);
             const int sx = tap - r * p.taps_w;
             ptx::tma_load_4d(&p.tmA, &full_bar[stage], a_dst, cc * GEMM_BK, w0 + sx + p.off_w0 + pb, h0 + r + p.off_h0 + pa, img);
-            ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst, k0 + kb_off, n0, 0, 0);
+            if (p.cs > 1)
+              ptx::tma_load_4d_mcast(&p.tmB, &full_bar[stage], b_dst + rank * b_slice, k0 + kb_off, n0 + rank * bn_slice, 0, 0, mc_mask);
+            else
+              ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst, k0 + kb_off, n0, 0, 0);
           } else if (p.conv == 2) {  // tap = phase * 4 + tr * 2 + ts
             const int ph = tap >> 2, tr = (tap >> 1) & 1, ts = tap & 1;
             const CUtensorMap* tm = ph == 0 ? &p.tmA : (ph == 1 ? &p.tmA1 : (ph == 2 ? &p.tmA2 : &p.tmA3));
             ptx::tma_load_4d(tm, &full_bar[stage], a_dst, cc * GEMM_BK, w0 - (ts - 1 + (ph & 1)), h0 - (tr - 1 + (ph >> 1)), img);
-            ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst, k0, n0, 0, 0);
+            if (p.cs > 1)
+              ptx::tma_load_4d_mcast(&p.tmB, &full_bar[stage], b_dst + rank * b_slice, k0, n0 + rank * bn_slice, 0, 0, mc_mask);
+            else
+              ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst, k0, n0, 0, 0);
           } else {
             if (!p.a_mn) {
               ptx::tma_load_4d(&p.tmA, &full_bar[stage], a_dst, k0, m0, b0, b1);
@@ -176,7 +200,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
               ptx::tma_load_4d(&p.tmA, &full_bar[stage], a_dst + 8192, m0 + 64, k0, b0, b1);
             }
             if (!p.b_mn) {
-              ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst, k0, n0, b0, b1);
+              if (p.cs > 1)
+                ptx::tma_load_4d_mcast(&p.tmB, &full_bar[stage], b_dst + rank * b_slice, k0, n0 + rank * bn_slice, b0, b1, mc_mask);
+              else
+                ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst, k0, n0, b0, b1);
             } else {
               for (int i = 0; i < p.BN / 64; ++i)
                 ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst + i * 8192, n0 + i * 64, k0, b0, b1);
@@ -205,14 +232,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
     const uint32_t a_kinc = (p.a_mn ? 2048u : 32u) >> 4, b_kinc = (p.b_mn ? 2048u : 32u) >> 4;
     const uint32_t a_sinc = GEMM_A_STAGE >> 4, b_sinc = b_stage >> 4;
     const uint32_t idesc = p.idesc;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const uint16_t mc_mask = static_cast<uint16_t>((1u << p.cs) - 1);
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
       ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * 256u;
       int nkc = p.num_k_chunks;
       if (p.ksplit > 1) {
         int n_tile, m_tile, b0, b1;
-        gemm_decode_tile(p, tile, n_tile, m_tile, b0, b1);
+        gemm_decode_tile(p, tile, n_tile, m_tile, b0, b1, rank);
         nkc = min(p.num_k_chunks, (b0 + 1) * p.kc_per_split) - b0 * p.kc_per_split;
       }
       for (int kc = 0; kc < nkc; ++kc) {
@@ -225,7 +253,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
           ptx::umma_bf16(d_tmem, ad + a_kinc, bd + b_kinc, idesc, 1u);
           ptx::umma_bf16(d_tmem, ad + 2 * a_kinc, bd + 2 * b_kinc, idesc, 1u);
           ptx::umma_bf16(d_tmem, ad + 3 * a_kinc, bd + 3 * b_kinc, idesc, 1u);
-          ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (p.cs > 1)
+            ptx::umma_commit_mcast(&empty_bar[stage], mc_mask);  // release the stage in every CTA of the cluster
+          else
+            ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -244,13 +275,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
     const int row = q * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    uint32_t ring = 0;  // chunk counter selecting the store panel (2-deep)
+    const bool store_leader = (warp == 2) && ptx::elect_one();
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
       int n_tile, m_tile, b0, b1;
-      gemm_decode_tile(p, tile, n_tile, m_tile, b0, b1);
+      gemm_decode_tile(p, tile, n_tile, m_tile, b0, b1, rank);
       const int n0 = n_tile * p.BN;
       bool valid;
       long long off_c, off_r;
       int img;
+      int sc1 = 0, sc2 = 0, sc3 = 0;  // TMA-store coordinates (dims 1..3) of this tile
       if (p.conv) {
         int tw = m_tile % p.tiles_w;
         int r = m_tile / p.tiles_w;
@@ -258,7 +292,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
         img = r / p.tiles_h;
         int hh = th * p.BH + row / p.BW;
         int ww = tw * p.BW + row % p.BW;
-        valid = (row < p.BW * p.BH) && hh < p.H && ww < p.W;
+        valid = (row < p.BW * p.BH) && hh < p.H && ww < p.W && m_tile < p.m_tiles;
+        sc1 = tw * p.BW, sc2 = th * p.BH, sc3 = img;
         long long pix = (static_cast<long long>(hh) * p.W + ww);
         off_c = img * p.sc1 + hh * p.out_sh + ww * p.out_sw;
         if (p.nphase > 1) off_c += (b0 >> 1) * p.out_pa + (b0 & 1) * p.out_pb;
@@ -267,6 +302,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
         int m = m_tile * GEMM_BM + row;
         valid = m < p.M;
         img = b1;
+        sc1 = m_tile * GEMM_BM, sc2 = b0, sc3 = b1;
         off_c = b0 * p.sc0 + b1 * p.sc1 + static_cast<long long>(m) * p.ldc;
         off_r = b0 * p.sr0 + b1 * p.sr1 + static_cast<long long>(m) * p.ldr;
       }
@@ -305,19 +341,77 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
       uint32_t bufA[32], bufB[32];
       ptx::tmem_ld32(t_row, bufA);
       const int n_chunks = (p.BN + 31) >> 5;
+      const bool use_ts = p.tma_store && !e_f32;
+      const bool tile_ok = m_tile < p.m_tiles || !p.conv;
       auto process = [&](const uint32_t(&raw)[32], uint32_t(&nxt)[32], const int ci) {
         const int c0 = ci << 5;
         const int col0 = n0 + c0;
         const int ncol = min(32, min(p.BN - c0, p.N - col0));  // valid columns of this chunk (may be <= 0)
-        const bool full = (ncol == 32) && e_vec;
+        const bool full = ((ncol == 32) || use_ts) && e_vec;
+        uint8_t* panel = spanel + (ring & 1) * 8192;
         uint4 rres[4];
-        if (e_res && valid && full) {
+        if (e_res && valid && full && ncol == 32) {
           const uint4* r4 = reinterpret_cast<const uint4*>(e_res + off_r + col0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) rres[j] = r4[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rres[j] = make_uint4(0, 0, 0, 0);
         }
         ptx::tmem_ld_wait();
         if (ci + 1 < n_chunks) ptx::tmem_ld32(t_row + c0 + 32, nxt);
+        if (use_ts) {
+          // stage this 128 x 32 chunk (64-byte rows, 64B swizzle) and hand it to the TMA store engine
+          if (valid && ncol > 0) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * e_alpha;
+            if (has_bias) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j);
+                v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
+              }
+            }
+            if (e_res) {
+              if (ncol == 32) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rres[j]);
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    float2 f = __bfloat1622float2(h[t]);
+                    v[8 * j + 2 * t] += f.x;
+                    v[8 * j + 2 * t + 1] += f.y;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncol) v[j] += __bfloat162float(e_res[off_r + col0 + j]);
+              }
+            }
+            uint4* o4 = reinterpret_cast<uint4*>(panel + row * 64);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]);
+              o4[j ^ ((row >> 1) & 3)] = o;
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          if (store_leader) ptx::bulk_wait_read<0>();  // every earlier store has finished reading its panel
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (store_leader && tile_ok && ncol > 0) {
+            const CUtensorMap* tm = (p.nphase > 1) ? (b0 == 0 ? &p.tmC : (b0 == 1 ? &p.tmC1 : (b0 == 2 ? &p.tmC2 : &p.tmC3))) : &p.tmC;
+            ptx::tma_store_4d(tm, panel, col0, sc1, (p.nphase > 1) ? sc2 : sc2, sc3);
+            ptx::bulk_commit();
+          }
+          ++ring;
+          return;
+        }
         if (!valid || ncol <= 0) return;
         if (full) {
           float v[32];
@@ -385,9 +479,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
     }
   }
 
+  if (p.tma_store && warp == 2) ptx::bulk_wait_all();  // (only the issuing lane has groups pending; a no-op elsewhere)
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  if (p.cs > 1) ptx::cluster_sync_all();  // no CTA may exit while a peer can still multicast into it / arrive on its barriers
   if (warp == 1) ptx::tmem_dealloc(tmem_base, GEMM_TMEM_COLS);
 }
 
@@ -429,7 +525,7 @@ inline PFN_encodeTiled get_encode_fn() {
 // 4-D bf16 tensor map, 128B swizzle, zero fill out of bounds.  dims/box in elements (dim 0 innermost),
 // strides in elements for dims 1..3.
 inline CUtensorMap make_tmap_bf16(const void* base, const uint64_t dims[4], const uint64_t strides_el[3],
-                                  const uint32_t box[4]) {
+                                  const uint32_t box[4], CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   CUtensorMap m;
   cuuint64_t gdims[4], gstr[3];
   cuuint32_t gbox[4], estr[4] = {1, 1, 1, 1};
@@ -437,9 +533,9 @@ inline CUtensorMap make_tmap_bf16(const void* base, const uint64_t dims[4], cons
   for (int i = 0; i < 3; ++i) gstr[i] = strides_el[i] * 2;
   MDC_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base %p not 16-byte aligned", base);
   for (int i = 0; i < 3; ++i) MDC_CHECK(gstr[i] % 16 == 0 && gstr[i] > 0, "TMA stride %d = %llu bytes invalid", i, (unsigned long long)gstr[i]);
-  MDC_CHECK(box[0] * 2 <= 128, "inner box exceeds the 128B swizzle span");
+  MDC_CHECK(box[0] * 2 <= (swz == CU_TENSOR_MAP_SWIZZLE_64B ? 64u : 128u), "inner box exceeds the swizzle span");
   CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdims, gstr, gbox, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MDC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): dims %llu %llu %llu %llu box %u %u %u %u", (int)r,
             (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
@@ -522,22 +618,53 @@ inline int g_num_sms() {
   return n;
 }
 
+// cluster of 2 along M when the B tile splits into two swizzle-atom-aligned halves (K-major B only); must be decided
+// BEFORE the B tensor map is encoded because each CTA's TMA box covers only its BN/cs rows.
+inline int decide_cs(const GemmParams& p) {
+  static const bool no_mc = getenv("MDC_NO_MCAST") != nullptr;
+  // only for launches with several tiles per CTA: the two cluster barriers cost more than they save on short kernels
+  const long long tiles = 1LL * p.m_tiles * p.n_tiles * (p.nb0 > 0 ? p.nb0 : 1) * (p.nb1 > 0 ? p.nb1 : 1);
+  return (!no_mc && !p.b_mn && tiles >= 2LL * g_num_sms() && (p.BN / 2) % 8 == 0 && p.BN >= 128) ? 2 : 1;
+}
 inline void finish_plan(GemmPlan& g) {
   GemmParams& p = g.p;
   const int b_stage = p.BN * 128;
-  int stages = (GEMM_SMEM_BUDGET - 5120) / (GEMM_A_STAGE + b_stage);
+  int stages = (GEMM_SMEM_BUDGET - GEMM_HEADER - 1024) / (GEMM_A_STAGE + b_stage);
   stages = std::max(2, std::min(stages, GEMM_MAX_STAGES));
   p.stages = stages;
-  g.smem = 5120 + stages * (GEMM_A_STAGE + b_stage);
+  g.smem = GEMM_HEADER + 1024 + stages * (GEMM_A_STAGE + b_stage);
   p.idesc = ptx::make_idesc_bf16(GEMM_BM, p.BN, p.a_mn, p.b_mn);
-  long long total = 1LL * p.m_tiles * p.n_tiles * (p.ksplit > 1 ? p.ksplit : p.nb0) * p.nb1;
-  g.grid = static_cast<int>(std::min<long long>(total, g_num_sms()));
+  if (p.cs < 1) p.cs = 1;  // set by the planners via decide_cs() before the B map was built
+  long long total = 1LL * ((p.m_tiles + p.cs - 1) / p.cs) * p.n_tiles * (p.ksplit > 1 ? p.ksplit : p.nb0) * p.nb1;
+  g.grid = static_cast<int>(std::min<long long>(total * p.cs, (g_num_sms() / p.cs) * p.cs));
   const uintptr_t o = reinterpret_cast<uintptr_t>(p.out), r = reinterpret_cast<uintptr_t>(p.res);
   bool ok = (o % 16 == 0) && (p.ldc % 8 == 0) && (p.sc0 % 8 == 0) && (p.sc1 % 8 == 0) && (p.N % 8 == 0);
   if (p.res) ok = ok && (r % 16 == 0) && (p.ldr % 8 == 0) && (p.sr0 % 8 == 0) && (p.sr1 % 8 == 0);
   if (p.bias) ok = ok && (reinterpret_cast<uintptr_t>(p.bias) % 16 == 0);
   if (p.bias_img) ok = ok && (reinterpret_cast<uintptr_t>(p.bias_img) % 16 == 0) && (p.N % 4 == 0);
   p.vec_ok = ok ? 1 : 0;
+  // TMA-store epilogue: bf16 output, aligned, whole 32-column chunks per n-tile
+  static const bool no_ts = getenv("MDC_NO_TMASTORE") != nullptr;
+  p.tma_store = 0;
+  if (!no_ts && ok && !p.out_f32 && p.BN % 32 == 0 && p.ksplit <= 1 && p.conv != 2 + 100) {
+    __nv_bfloat16* base = static_cast<__nv_bfloat16*>(p.out);
+    if (!p.conv) {
+      uint64_t dims[4] = {(uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.nb0, (uint64_t)p.nb1};
+      uint64_t str[3] = {(uint64_t)p.ldc, (uint64_t)(p.sc0 ? p.sc0 : 8), (uint64_t)(p.sc1 ? p.sc1 : 8)};
+      uint32_t box[4] = {32, GEMM_BM, 1, 1};
+      p.tmC = make_tmap_bf16(base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+      p.tma_store = 1;
+    } else {
+      uint64_t dims[4] = {(uint64_t)p.N, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)std::max<long long>(1, p.m_tiles / (p.tiles_h * p.tiles_w))};
+      uint64_t str[3] = {(uint64_t)p.out_sw, (uint64_t)p.out_sh, (uint64_t)p.sc1};
+      uint32_t box[4] = {32, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+      CUtensorMap* maps[4] = {&p.tmC, &p.tmC1, &p.tmC2, &p.tmC3};
+      const int nph = p.nphase > 1 ? 4 : 1;
+      for (int ph = 0; ph < nph; ++ph)
+        *maps[ph] = make_tmap_bf16(base + (ph >> 1) * p.out_pa + (ph & 1) * p.out_pb, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+      p.tma_store = 1;
+    }
+  }
 }
 
 inline void fill_epilogue(GemmParams& p, const Epilogue& e) {
@@ -577,8 +704,9 @@ inline GemmPlan plan_gemm(int M, int N, int K, const Operand& A, const Operand& 
     str[0] = o.ld, str[1] = s0, str[2] = s1;
     return make_tmap_bf16(o.ptr, dims, str, box);
   };
+  p.cs = decide_cs(p);
   p.tmA = mk(A, M, GEMM_BM);
-  p.tmB = mk(B, N, p.BN);
+  p.tmB = mk(B, N, p.BN / p.cs);
   fill_epilogue(p, e);
   finish_plan(g);
   g.flops = 2.0 * M * N * K * nb0 * nb1;
@@ -633,7 +761,8 @@ inline GemmPlan plan_conv3x3(int NB, int H, int W, int C, int Cout, const void* 
   {
     uint64_t dims[4] = {(uint64_t)9 * Cp, (uint64_t)Cout, 1, 1};
     uint64_t str[3] = {(uint64_t)9 * Cp, (uint64_t)9 * Cp * Cout, (uint64_t)9 * Cp * Cout};
-    uint32_t box[4] = {64, (uint32_t)p.BN, 1, 1};
+    p.cs = decide_cs(p);
+    uint32_t box[4] = {64, (uint32_t)(p.BN / p.cs), 1, 1};
     p.tmB = make_tmap_bf16(wpk, dims, str, box);
   }
   if (!e.sc1) e.sc1 = 1LL * H * W * e.ldc;
@@ -699,7 +828,8 @@ inline GemmPlan plan_upconv_fwd(int NB, int H, int W, int C, int Cout, const voi
   {
     uint64_t dims[4] = {(uint64_t)16 * Cp, (uint64_t)Cout, 1, 1};
     uint64_t str[3] = {(uint64_t)16 * Cp, (uint64_t)16 * Cp * Cout, (uint64_t)16 * Cp * Cout};
-    uint32_t box[4] = {64, (uint32_t)p.BN, 1, 1};
+    p.cs = decide_cs(p);
+    uint32_t box[4] = {64, (uint32_t)(p.BN / p.cs), 1, 1};
     p.tmB = make_tmap_bf16(wpk, dims, str, box);
   }
   e.sc1 = Hf * Wf * e.ldc;
@@ -746,7 +876,8 @@ inline GemmPlan plan_upconv_bwd(int NB, int H, int W, int C, int Cout, const voi
   {
     uint64_t dims[4] = {(uint64_t)16 * Cop, (uint64_t)C, 1, 1};
     uint64_t str[3] = {(uint64_t)16 * Cop, (uint64_t)16 * Cop * C, (uint64_t)16 * Cop * C};
-    uint32_t box[4] = {64, (uint32_t)p.BN, 1, 1};
+    p.cs = decide_cs(p);
+    uint32_t box[4] = {64, (uint32_t)(p.BN / p.cs), 1, 1};
     p.tmB = make_tmap_bf16(wpk, dims, str, box);
   }
   if (!e.sc1) e.sc1 = 1LL * H * W * e.ldc;
@@ -758,12 +889,33 @@ inline GemmPlan plan_upconv_bwd(int NB, int H, int W, int C, int Cout, const voi
   return g;
 }
 
+inline void launch_gemm_kernel(const GemmPlan& g, cudaStream_t st);
 inline void gemm_set_smem_attr() {
   static bool done = false;
   if (!done) {
-    MDC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BUDGET + 4096));
+    MDC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     done = true;
   }
+}
+
+inline void launch_gemm_kernel(const GemmPlan& g, cudaStream_t st) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(g.grid), cfg.blockDim = dim3(GEMM_THREADS), cfg.dynamicSmemBytes = g.smem + 1024, cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (g_use_pdl()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (g.p.cs > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = g.p.cs, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr, cfg.numAttrs = na;
+  MDC_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel, g.p));
 }
 
 // Decide on split-K for a finished plan: few output tiles, long K loop.  `ws` must hold ws_floats(plan) floats.
@@ -787,13 +939,13 @@ inline size_t enable_splitk(GemmPlan& g, int ksplit) {  // returns the workspace
   }
   p.ws_ld = ((p.N + 15) / 16) * 16;
   p.ws_split_stride = g.rows * p.ws_ld;
-  g.grid = std::min(p.m_tiles * p.n_tiles * p.ksplit, g_num_sms());
+  g.grid = std::min(((p.m_tiles + p.cs - 1) / p.cs) * p.cs * p.n_tiles * p.ksplit, (g_num_sms() / p.cs) * p.cs);
   return static_cast<size_t>(p.ksplit) * p.ws_split_stride;
 }
 
 inline void run_gemm(const GemmPlan& g, cudaStream_t st) {
   gemm_set_smem_attr();
-  launch_k(umma_gemm_kernel, dim3(g.grid), dim3(GEMM_THREADS), g.smem + 1024, st, g.p);
+  launch_gemm_kernel(g, st);
   if (g.p.ksplit > 1) {
     const GemmParams& p = g.p;
     const long long work = g.rows * ((p.N + 3) / 4);

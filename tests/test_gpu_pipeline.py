@@ -136,3 +136,26 @@ def test_error_conventions(models, cuda):
         pipe(img, torch.zeros_like(sp), 10.0, resolution=128, steps=2)
     with pytest.raises(NotImplementedError):
         pipe(img, sp, 10.0, opt="sgd")
+
+
+@pytest.mark.parametrize("H,W,res,kind,max_depth", [(88, 304, 304, "kitti", 80.0),   # config (c) shape /4: latent 11x38
+                                                    (120, 160, 160, "nyu", 10.0),    # config (b') res-640 analogue: 15x20
+                                                    (96, 128, 256, "nyu", 10.0)])    # upsampling processing resolution
+def test_other_configs_match_oracle(models, cuda, H, W, res, kind, max_depth):
+    """BASELINE.json configs (c)/(e) in miniature: LiDAR-line sparsity at 352x1216's aspect ratio (odd latent sizes,
+    ~5 % density), latent sizes not divisible by 8, and a processing resolution above the input resolution."""
+    from depth_completion_b200.pipeline import MarigoldDepthCompletionPipeline
+    from oracle.marigold_dc import OraclePipeline, mae
+
+    unet, vae, ctx, _, _ = models
+    fr = _frame(cuda, H=H, W=W, kind=kind, n_points=100, max_depth=max_depth, min_field=1.0 if kind == "kitti" else 0.5)
+    pipe = MarigoldDepthCompletionPipeline(unet, vae)
+    pipe.empty_text_embedding = ctx
+    dense, lat = pipe(fr["img"], fr["sparse"], max_depth, steps=20, resolution=res)
+    d16, l16 = OraclePipeline(copy.deepcopy(unet).bfloat16(), copy.deepcopy(vae).bfloat16(), ctx.bfloat16())(
+        fr["img"], fr["sparse"], max_depth, steps=20, resolution=res)
+    assert dense.shape == d16.shape and lat.shape == l16.shape and torch.isfinite(dense).all()
+    diff = ((dense - d16).abs().mean() / max_depth).item()
+    assert diff < 4e-2, diff
+    m_ours, m_ref = mae(dense, fr["gt"], fr["holdout"]).item(), mae(d16, fr["gt"], fr["holdout"]).item()
+    assert abs(m_ours - m_ref) <= 0.08 * m_ref, (m_ours, m_ref)
