@@ -988,8 +988,10 @@ inline void Engine::finalize_plans() {
           finish_plan(c->pf);
         }
       } else if (auto* a = dynamic_cast<SelfAttnOp*>(op.get())) {
-        a->p_s.p.out = attn_S;
-        finish_plan(a->p_s);
+        if (!a->use_flash) {
+          a->p_s.p.out = attn_S;
+          finish_plan(a->p_s);
+        }
       }
     }
     for (auto it = ops->rbegin(); it != ops->rend(); ++it) (*it)->plan_bwd();

@@ -532,7 +532,10 @@ inline CUtensorMap make_tmap_bf16(const void* base, const uint64_t dims[4], cons
   for (int i = 0; i < 4; ++i) gdims[i] = dims[i], gbox[i] = box[i];
   for (int i = 0; i < 3; ++i) gstr[i] = strides_el[i] * 2;
   MDC_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base %p not 16-byte aligned", base);
-  for (int i = 0; i < 3; ++i) MDC_CHECK(gstr[i] % 16 == 0 && gstr[i] > 0, "TMA stride %d = %llu bytes invalid", i, (unsigned long long)gstr[i]);
+  for (int i = 0; i < 3; ++i)
+    MDC_CHECK(gstr[i] % 16 == 0 && gstr[i] > 0, "TMA stride %d = %llu bytes invalid (dims %llu %llu %llu %llu box %u %u %u %u)", i,
+              (unsigned long long)gstr[i], (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+              (unsigned long long)dims[3], box[0], box[1], box[2], box[3]);
   MDC_CHECK(box[0] * 2 <= (swz == CU_TENSOR_MAP_SWIZZLE_64B ? 64u : 128u), "inner box exceeds the swizzle span");
   CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdims, gstr, gbox, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
