@@ -457,13 +457,13 @@ inline void LinearOp::bwd(cudaStream_t st) {
 }
 inline void GroupNormOp::fwd(cudaStream_t st) {
   const int grid = s.N * s.blocks_per_img;
-  launch_k(gn_stats_kernel, dim3(grid), dim3(threads), 2 * s.G * sizeof(float), st, x->d, s, E->gn_partial, eps, stats,
+  launch_k(gn_stats_kernel, dim3(grid), dim3(threads), ((threads + 31) / 32) * 2 * s.G * sizeof(float), st, x->d, s, E->gn_partial, eps, stats,
            E->gn_ticket);
   launch_k(gn_apply_kernel, dim3(grid), dim3(threads), 0, st, x->d, s, stats, gamma, beta, silu, y->d, y->ld);
 }
 inline void GroupNormOp::bwd(cudaStream_t st) {
   const int grid = s.N * s.blocks_per_img;
-  launch_k(gn_bwd_stats_kernel, dim3(grid), dim3(threads_b), 2 * s.G * sizeof(float), st, x->d, y->g, y->ld, s, stats, gamma,
+  launch_k(gn_bwd_stats_kernel, dim3(grid), dim3(threads_b), ((threads_b + 31) / 32) * 2 * s.G * sizeof(float), st, x->d, y->g, y->ld, s, stats, gamma,
            beta, silu, E->gn_partial, E->gn_gstats, E->gn_ticket);
   launch_k(gn_bwd_apply_kernel, dim3(grid), dim3(threads_b), 0, st, x->d, y->g, y->ld, s, stats, E->gn_gstats, gamma, beta,
            silu, x->g, x->ld, acc);

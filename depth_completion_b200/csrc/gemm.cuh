@@ -926,7 +926,8 @@ inline int choose_ksplit(const GemmPlan& g) {
   const GemmParams& p = g.p;
   if (p.nb0 != 1 || p.nb1 != 1 || p.bias_img || p.out_f32 || p.conv == 2 || p.nphase > 1) return 1;
   const int tiles = p.m_tiles * p.n_tiles;
-  if (tiles * 2 > g_num_sms() || p.num_k_chunks < 8) return 1;
+  static const int max_tiles = getenv("MDC_SPLITK_MAXTILES") ? atoi(getenv("MDC_SPLITK_MAXTILES")) : 32;  // measured sweep: 16 / 30 / 48 / 74 -> 26.2 / 25.5 / 25.5 / 25.9 ms per step
+  if (tiles > max_tiles || p.num_k_chunks < 8) return 1;
   int ks = (g_num_sms() + tiles - 1) / tiles;
   ks = std::min(ks, p.num_k_chunks / 4);
   return std::max(ks, 1);

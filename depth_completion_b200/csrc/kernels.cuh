@@ -150,7 +150,9 @@ __global__ void __launch_bounds__(512, 2) gn_stats_kernel(const bf16* __restrict
   const int CV = s.C >> 3, cpg = s.C / s.G;
   const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
   const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
-  for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) sh[i] = 0.f;
+  // sh: [warps][2G] per-warp accumulators (low-contention shared atomics), reduced across warps at the end
+  const int nwarps_ = (blockDim.x + 31) >> 5, wid_ = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < nwarps_ * 2 * s.G; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
   float sum[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
   const int p0 = b * s.pix_per_block, p1 = min(s.HW, p0 + s.pix_per_block);
@@ -171,14 +173,27 @@ __global__ void __launch_bounds__(512, 2) gn_stats_kernel(const bf16* __restrict
         }
       }
   }
+  {
+    float* mine = sh + wid_ * 2 * s.G;
+    int gprev = -1;
+    float a = 0.f, b = 0.f;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int g = (cv * 8 + 2 * i) / cpg;
-    atomicAdd(&sh[2 * g], sum[i]);
-    atomicAdd(&sh[2 * g + 1], sq[i]);
+    for (int i = 0; i < 4; ++i) {  // merge this thread's pairs that fall into the same group before touching smem
+      int g = (cv * 8 + 2 * i) / cpg;
+      if (g != gprev && gprev >= 0) {
+        atomicAdd(&mine[2 * gprev], a), atomicAdd(&mine[2 * gprev + 1], b);
+        a = b = 0.f;
+      }
+      gprev = g, a += sum[i], b += sq[i];
+    }
+    atomicAdd(&mine[2 * gprev], a), atomicAdd(&mine[2 * gprev + 1], b);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) partial[1LL * blockIdx.x * 2 * s.G + i] = sh[i];
+  for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < nwarps_; ++w) t += sh[w * 2 * s.G + i];
+    partial[1LL * blockIdx.x * 2 * s.G + i] = t;
+  }
   gn_finalize_last_block(partial, n, s.G, s.blocks_per_img, 1.0 * s.HW * cpg, eps, 0, stats_out, ticket);
 }
 
@@ -288,7 +303,8 @@ __global__ void __launch_bounds__(384, 2) gn_bwd_stats_kernel(const bf16* __rest
   const int CV = s.C >> 3, cpg = s.C / s.G;
   const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
   const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
-  for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) sh[i] = 0.f;
+  const int nwarps_ = (blockDim.x + 31) >> 5, wid_ = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < nwarps_ * 2 * s.G; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
   GNBwdConst k;
   gn_load_const(k, s, n, cv, stats, gamma, beta);
@@ -322,14 +338,27 @@ __global__ void __launch_bounds__(384, 2) gn_bwd_stats_kernel(const bf16* __rest
         }
       }
   }
+  {
+    float* mine = sh + wid_ * 2 * s.G;
+    int gprev = -1;
+    float a = 0.f, b = 0.f;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int g = (cv * 8 + 2 * i) / cpg;
-    atomicAdd(&sh[2 * g], sa[i]);
-    atomicAdd(&sh[2 * g + 1], sb[i]);
+    for (int i = 0; i < 4; ++i) {
+      int g = (cv * 8 + 2 * i) / cpg;
+      if (g != gprev && gprev >= 0) {
+        atomicAdd(&mine[2 * gprev], a), atomicAdd(&mine[2 * gprev + 1], b);
+        a = b = 0.f;
+      }
+      gprev = g, a += sa[i], b += sb[i];
+    }
+    atomicAdd(&mine[2 * gprev], a), atomicAdd(&mine[2 * gprev + 1], b);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) partial[1LL * blockIdx.x * 2 * s.G + i] = sh[i];
+  for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < nwarps_; ++w) t += sh[w * 2 * s.G + i];
+    partial[1LL * blockIdx.x * 2 * s.G + i] = t;
+  }
   gn_finalize_last_block(partial, n, s.G, s.blocks_per_img, 1.0 * s.HW * cpg, 0.f, 1, gstats_out, ticket);
 }
 
