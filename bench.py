@@ -115,6 +115,16 @@ def workload(tiny: bool):
     return w
 
 
+def config_dict(w, latent=None):
+    """Identical for both arms (the reference arm runs on our arm's config)."""
+    lat = f" (latent {latent[0]}x{latent[1]})" if latent else ""
+    return {"workload": f"{w['H']}x{w['W']} RGB + {w['n_points']} sparse points, resolution {w['resolution']}{lat}, "
+                        f"{w['frame_steps']}-step guided completion, 1 frame in flight per GPU, "
+                        "random-init SD2 UNet (866M) / VAE decoder (49.5M)",
+            "l2": "per-step working set (activations + 1.8 GB weights) >> 126 MB L2, no flush needed",
+            "frames_sharding": "independent frames per rank, no collective inside the step"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -171,8 +181,8 @@ def run_reference(args):
         "impl": "reference", "metric": "guided_steps_per_sec", "value": r["value"], "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / r["value"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{w['H']}x{w['W']} RGB + {w['n_points']} sparse points, resolution {w['resolution']}, "
-                               f"{w['frame_steps']}-step guided completion, random-init SD2 UNet/VAE"},
+        "config": config_dict(w, (w["resolution"] * w["H"] // (8 * max(w["H"], w["W"])),
+                                  w["resolution"] * w["W"] // (8 * max(w["H"], w["W"])))),
         "cpu_baseline": {"value": r["value"], "unit": "steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -302,11 +312,7 @@ def run_ours(args):
             "metric": "guided_steps_per_sec", "value": steps_per_s, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{H}x{W} RGB + {w['n_points']} sparse points, resolution {res} (latent "
-                                   f"{eng.lh}x{eng.lw}), {fs}-step guided completion, 1 frame in flight per GPU, "
-                                   "random-init SD2 UNet (866M) / VAE decoder (49.5M)",
-                       "l2": "per-step working set (activations + 1.8 GB weights) >> 126 MB L2, no flush needed",
-                       "frames_sharding": "independent frames per rank, no collective inside the step"},
+            "config": config_dict(w, (eng.lh, eng.lw)),
             "frames_per_sec_device": steps_per_s / fs,
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "device_mem_gb": eng.device_bytes() / 2 ** 30,
