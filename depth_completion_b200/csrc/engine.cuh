@@ -52,6 +52,7 @@ struct Tensor {
   int n = 0, h = 0, w = 0, c = 0;
   long long ld = 0;
   bool grad_set = false;
+  bool is_view = false;   // channel slice of a concat buffer: its gradient must stay inside the parent's
   std::string name;
   long long rows() const { return 1LL * n * h * w; }
 };
@@ -88,11 +89,11 @@ struct ConvOp : Op {  // 3x3 stride-1 pad-1 convolution (+bias, +residual)
   WeightSlot* W;
   const float* bias;
   GemmPlan pf, pb;
-  bool acc_res = false;
+  bool acc_res = false, alias_res = false;
   void plan_bwd() override;
   void fwd(cudaStream_t st) override { run_gemm(pf, st); }
   void bwd(cudaStream_t st) override;
-  int n_bwd() const override { return res ? 2 : 1; }
+  int n_bwd() const override { return (res && !alias_res) ? 2 : 1; }
   void gemm_plans(std::vector<const GemmPlan*>& f, std::vector<const GemmPlan*>& b) const override {
     f.push_back(&pf), b.push_back(&pb);
   }
@@ -104,11 +105,11 @@ struct LinearOp : Op {  // y[rows, out] = x[rows, in] W^T (+bias, +residual)
   long long ld_w, ld_wt;
   const float* bias;
   GemmPlan pf, pb;
-  bool acc_res = false;
+  bool acc_res = false, alias_res = false;
   void plan_bwd() override;
   void fwd(cudaStream_t st) override { run_gemm(pf, st); }
   void bwd(cudaStream_t st) override;
-  int n_bwd() const override { return res ? 2 : 1; }
+  int n_bwd() const override { return (res && !alias_res) ? 2 : 1; }
   void gemm_plans(std::vector<const GemmPlan*>& f, std::vector<const GemmPlan*>& b) const override {
     f.push_back(&pf), b.push_back(&pb);
   }
@@ -421,11 +422,17 @@ inline void ConvOp::plan_bwd() {
   if (res) {
     acc_res = res->grad_set;
     res->grad_set = true;
+    // First gradient contribution of a stand-alone residual tensor: d(res) == dy, so let res share dy's buffer instead
+    // of copying it (dy is dead once this op's own input gradient has been computed, which happens first).
+    if (!acc_res && !res->is_view && !y->is_view && res->ld == y->ld && res->c == y->c && !getenv("MDC_NO_ALIAS")) {
+      res->g = y->g;
+      alias_res = true;
+    }
   }
 }
 inline void ConvOp::bwd(cudaStream_t st) {
   run_gemm(pb, st);
-  if (res)
+  if (res && !alias_res)
     launch_k(add_rows_kernel, dim3(ew_grid(res->rows() * (res->c / 8))), dim3(256), 0, st, y->g, y->ld, res->g, res->ld, res->rows(), res->c,
                                                                         acc_res);
 }
@@ -447,11 +454,17 @@ inline void LinearOp::plan_bwd() {
   if (res) {
     acc_res = res->grad_set;
     res->grad_set = true;
+    // First gradient contribution of a stand-alone residual tensor: d(res) == dy, so let res share dy's buffer instead
+    // of copying it (dy is dead once this op's own input gradient has been computed, which happens first).
+    if (!acc_res && !res->is_view && !y->is_view && res->ld == y->ld && res->c == y->c && !getenv("MDC_NO_ALIAS")) {
+      res->g = y->g;
+      alias_res = true;
+    }
   }
 }
 inline void LinearOp::bwd(cudaStream_t st) {
   run_gemm(pb, st);
-  if (res)
+  if (res && !alias_res)
     launch_k(add_rows_kernel, dim3(ew_grid(res->rows() * (res->c / 8))), dim3(256), 0, st, y->g, y->ld, res->g, res->ld, res->rows(), res->c,
                                                                         acc_res);
 }
@@ -556,6 +569,7 @@ inline Tensor* Engine::view(Tensor* parent, int c0, int c, const std::string& na
   t->d = parent->d + c0;
   t->g = parent->g ? parent->g + c0 : nullptr;
   t->grad_set = false;
+  t->is_view = true;
   t->name = name;
   if (!name.empty()) named[name] = t;
   return t;
