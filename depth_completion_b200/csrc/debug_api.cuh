@@ -88,12 +88,61 @@ int mdc_dbg_conv3x3(int NB, int H, int W, int C, int Cout, const void* x, long l
     mdc::Epilogue e;
     e.out = out, e.ldc = ldc, e.bias = bias, e.bias_img = bias_img;
     e.res = static_cast<const __nv_bfloat16*>(res), e.ldr = ldr;
-    mdc::GemmPlan g = mdc::plan_conv3x3(NB, H, W, Cin_g, Cout_g, x, ldx, wpk, e);
-    float ms = mdc::time_plan(g, iters, 0);
+    // optional: several weight copies used round-robin (so the timed loop streams weights from HBM like the real step
+    // does) and split-K with its workspace, both selected through mdc_dbg_tune.
+    const int ncopy = std::max(1, mdc::g_tune().wcopies);
+    const size_t wbytes = sizeof(__nv_bfloat16) * 9ull * Kp * Cout_g;
+    std::vector<__nv_bfloat16*> copies(ncopy, wpk);
+    for (int i = 1; i < ncopy; ++i) {
+      MDC_CUDA(cudaMalloc(&copies[i], wbytes));
+      MDC_CUDA(cudaMemcpy(copies[i], wpk, wbytes, cudaMemcpyDeviceToDevice));
+    }
+    std::vector<mdc::GemmPlan> plans;
+    float* ws = nullptr;
+    for (int i = 0; i < ncopy; ++i) {
+      mdc::GemmPlan g = mdc::plan_conv3x3(NB, H, W, Cin_g, Cout_g, x, ldx, copies[i], e);
+      if (mdc::g_tune().ksplit) {
+        size_t fl = mdc::enable_splitk(g, mdc::choose_ksplit(g));
+        if (fl && !ws) MDC_CUDA(cudaMalloc(&ws, fl * 4 + 256));
+        g.p.ws = ws;
+      }
+      plans.push_back(g);
+    }
+    if (ms_out && mdc::g_tune().ksplit < 0) fprintf(stderr, "[dbg] auto ksplit = %d (tiles %d x %d, k-chunks %d, BN %d, cs %d)\n",
+                                                     plans[0].p.ksplit, plans[0].p.m_tiles, plans[0].p.n_tiles, plans[0].p.num_k_chunks, plans[0].p.BN, plans[0].p.cs);
+    float ms = 0.f;
+    if (ncopy == 1) {
+      ms = mdc::time_plan(plans[0], iters, 0);
+    } else {
+      cudaEvent_t e0, e1;
+      MDC_CUDA(cudaEventCreate(&e0));
+      MDC_CUDA(cudaEventCreate(&e1));
+      for (int i = 0; i < ncopy; ++i) mdc::run_gemm(plans[i], 0);
+      MDC_CUDA(cudaStreamSynchronize(0));
+      if (iters > 0) {
+        MDC_CUDA(cudaEventRecord(e0, 0));
+        for (int i = 0; i < iters; ++i) mdc::run_gemm(plans[i % ncopy], 0);
+        MDC_CUDA(cudaEventRecord(e1, 0));
+        MDC_CUDA(cudaEventSynchronize(e1));
+        MDC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        ms /= iters;
+      }
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
     if (ms_out) *ms_out = ms;
     MDC_CUDA(cudaDeviceSynchronize());
+    for (int i = 1; i < ncopy; ++i) cudaFree(copies[i]);
+    if (ws) cudaFree(ws);
     cudaFree(wpk);
   });
+}
+
+// Test / tuning overrides for the planners (0 = automatic): output-tile width, cluster size, split-K factor (-1 = use
+// the engine's cost model also in the debug entry points), number of weight copies rotated in timed loops.
+int mdc_dbg_tune(int bn, int cs, int ksplit, int wcopies) {
+  mdc::g_tune().bn = bn, mdc::g_tune().cs = cs, mdc::g_tune().ksplit = ksplit, mdc::g_tune().wcopies = wcopies > 0 ? wcopies : 1;
+  return 0;
 }
 
 }  // extern "C"

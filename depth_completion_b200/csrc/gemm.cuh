@@ -29,7 +29,8 @@ constexpr int GEMM_A_STAGE = GEMM_BM * GEMM_BK * 2;  // 16 KiB
 constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_THREADS = 192;
 constexpr int GEMM_SMEM_BUDGET = 225 * 1024;
-constexpr int GEMM_HEADER = 4096 + 2 * 8192;  // barriers + staged bias (4 KiB) + two 128 x 32 bf16 store panels
+constexpr int GEMM_HEADER0 = 4096;   // barriers + staged bias; followed by `npanel` 128 x 32 bf16 store panels (8 KiB each)
+constexpr int GEMM_PANEL = 8192;
 constexpr int GEMM_TMEM_COLS = 512;
 
 struct GemmParams {
@@ -64,10 +65,16 @@ struct GemmParams {
   // TMA-store epilogue (bf16 outputs): each 128-row x 32-column chunk is staged in 64B-swizzled shared memory and
   // written with one bulk tensor store (coalesced, hardware-clipped) instead of 16-byte scattered stores per thread.
   int tma_store;
+  int npanel;  // store panels in flight: 4 (up to three bulk stores outstanding) or 2 when shared memory is short
   CUtensorMap tmC, tmC1, tmC2, tmC3;  // tmC1..3: phases 1..3 of the fused upsample conv
   // cluster B-multicast: `cs` CTAs (consecutive m-tiles of one n-tile) form a cluster; each loads BN/cs rows of the
   // B tile and multicasts them to all, so the weight tile crosses L2 -> SM once per cluster instead of once per CTA.
   int cs;
+  // CTA-pair MMA (cs == 2 only): the two CTAs of a cluster run one M = 256 tcgen05.mma.cta_group::2 -- each stages
+  // its own 128 A rows and HALF of the B tile, so a k-chunk costs each SM 16 KiB + BN*64 B of L2 -> SM traffic instead
+  // of 16 KiB + BN*128 B; only the leader (rank 0) issues MMAs, its commits release stages / publish accumulators in
+  // both CTAs, and both CTAs' epilogues hand accumulator stages back to the leader.
+  int pair;
   // split-K (nb0 = nb1 = 1 only): CTA (tile, s) accumulates k-chunks [s*kc_per_split, ...) and writes its raw fp32
   // partial to ws[s][row][col]; splitk_reduce_kernel sums the partials and applies the epilogue.
   int ksplit, kc_per_split;
@@ -90,7 +97,8 @@ __device__ __forceinline__ void gemm_decode_tile(const GemmParams& p, int tile, 
   b1 = b / nb0;
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
+template <bool kPair>
+__device__ __forceinline__ void umma_gemm_body(const GemmParams& p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // barriers live in the first 1 KiB of the aligned region, the staged bias in the next 2 KiB; stage buffers at 4 KiB.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -100,9 +108,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* sbias_base = reinterpret_cast<float*>(smem + 1024);  // 2 x 256 floats
-  uint8_t* spanel = smem + 4096;  // 2 x 8 KiB output panels
-  uint8_t* sA = smem + GEMM_HEADER;
-  const uint32_t b_stage = static_cast<uint32_t>(p.BN) * 128u;
+  uint8_t* spanel = smem + GEMM_HEADER0;  // npanel x 8 KiB output panels
+  uint8_t* sA = spanel + p.npanel * GEMM_PANEL;
+  constexpr bool pair = kPair;
+  const uint32_t b_stage = static_cast<uint32_t>(pair ? p.BN / 2 : p.BN) * 128u;
   uint8_t* sB = sA + p.stages * GEMM_A_STAGE;
 
   const int warp = threadIdx.x >> 5;
@@ -113,18 +122,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) {
-      ptx::mbar_init(&full_bar[i], 1);
-      ptx::mbar_init(&empty_bar[i], p.cs);  // every CTA of the cluster must release the stage before it is refilled
+      ptx::mbar_init(&full_bar[i], pair ? 2 : 1);  // pair: one arrival per CTA's producer, on the leader's barrier
+      // multicast: every CTA of the cluster must release the stage before it is refilled; pair: one multicast commit
+      ptx::mbar_init(&empty_bar[i], pair ? 1 : p.cs);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], 4);
+      ptx::mbar_init(&tempty_bar[i], pair ? 8 : 4);  // pair: the epilogue warps of both CTAs, on the leader's barrier
     }
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&p.tmA);
     ptx::prefetch_tmap(&p.tmB);
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, GEMM_TMEM_COLS);
+  if (pair) ptx::cluster_sync_all();  // both CTAs are resident before the paired TMEM allocation
+  if (warp == 1) {
+    if (pair)
+      ptx::tmem_alloc_pair(tmem_slot, GEMM_TMEM_COLS);
+    else
+      ptx::tmem_alloc(tmem_slot, GEMM_TMEM_COLS);
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -142,10 +158,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
     const bool leader = ptx::elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx_bytes = p.bytesA + p.bytesB;
     const int bn_slice = p.BN / p.cs;                       // rows of the B tile this CTA loads (and multicasts)
     const uint32_t b_slice = static_cast<uint32_t>(bn_slice) * 128u;
+    const uint32_t tx_bytes = pair ? 2u * (p.bytesA + b_slice) : p.bytesA + p.bytesB;
     const uint16_t mc_mask = static_cast<uint16_t>((1u << p.cs) - 1);
+    const uint32_t full_leader = pair ? ptx::mapa_u32(&full_bar[0], 0) : 0u;  // leader's full barriers (cluster address)
+    // operand loads: plain / pair (bytes complete on the leader's barrier) / multicast B
+    auto load_a = [&](const CUtensorMap* tm, int stage, uint8_t* dst, int c0, int c1, int c2, int c3) {
+      if (pair)
+        ptx::tma_load_4d_pair(tm, full_leader + stage * 8, dst, c0, c1, c2, c3);
+      else
+        ptx::tma_load_4d(tm, &full_bar[stage], dst, c0, c1, c2, c3);
+    };
+    auto load_b = [&](int stage, uint8_t* b_dst, int k0, int n0, int b0, int b1) {
+      if (pair)
+        ptx::tma_load_4d_pair(&p.tmB, full_leader + stage * 8, b_dst, k0, n0 + rank * bn_slice, b0, b1);
+      else if (p.cs > 1)
+        ptx::tma_load_4d_mcast(&p.tmB, &full_bar[stage], b_dst + rank * b_slice, k0, n0 + rank * bn_slice, b0, b1, mc_mask);
+      else
+        ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst, k0, n0, b0, b1);
+    };
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
       int n_tile, m_tile, b0, b1;
       gemm_decode_tile(p, tile, n_tile, m_tile, b0, b1, rank);
@@ -172,43 +204,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
       for (int kc = kc_begin; kc < kc_end; ++kc) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         if (leader) {
-          ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+          if (!pair || rank == 0) ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
           uint8_t* a_dst = sA + stage * GEMM_A_STAGE;
           uint8_t* b_dst = sB + stage * b_stage;
           const int k0 = kc * GEMM_BK;
           if (p.conv == 1) {
             const int r = (p.taps_w == 3) ? (tap >= 6 ? 2 : (tap >= 3 ? 1 : 0)) : (tap >> 1);
             const int sx = tap - r * p.taps_w;
-            ptx::tma_load_4d(&p.tmA, &full_bar[stage], a_dst, cc * GEMM_BK, w0 + sx + p.off_w0 + pb, h0 + r + p.off_h0 + pa, img);
-            if (p.cs > 1)
-              ptx::tma_load_4d_mcast(&p.tmB, &full_bar[stage], b_dst + rank * b_slice, k0 + kb_off, n0 + rank * bn_slice, 0, 0, mc_mask);
-            else
-              ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst, k0 + kb_off, n0, 0, 0);
+            load_a(&p.tmA, stage, a_dst, cc * GEMM_BK, w0 + sx + p.off_w0 + pb, h0 + r + p.off_h0 + pa, img);
+            load_b(stage, b_dst, k0 + kb_off, n0, 0, 0);
           } else if (p.conv == 2) {  // tap = phase * 4 + tr * 2 + ts
             const int ph = tap >> 2, tr = (tap >> 1) & 1, ts = tap & 1;
             const CUtensorMap* tm = ph == 0 ? &p.tmA : (ph == 1 ? &p.tmA1 : (ph == 2 ? &p.tmA2 : &p.tmA3));
-            ptx::tma_load_4d(tm, &full_bar[stage], a_dst, cc * GEMM_BK, w0 - (ts - 1 + (ph & 1)), h0 - (tr - 1 + (ph >> 1)), img);
-            if (p.cs > 1)
-              ptx::tma_load_4d_mcast(&p.tmB, &full_bar[stage], b_dst + rank * b_slice, k0, n0 + rank * bn_slice, 0, 0, mc_mask);
-            else
-              ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst, k0, n0, 0, 0);
+            load_a(tm, stage, a_dst, cc * GEMM_BK, w0 - (ts - 1 + (ph & 1)), h0 - (tr - 1 + (ph >> 1)), img);
+            load_b(stage, b_dst, k0, n0, 0, 0);
           } else {
             if (!p.a_mn) {
-              ptx::tma_load_4d(&p.tmA, &full_bar[stage], a_dst, k0, m0, b0, b1);
+              load_a(&p.tmA, stage, a_dst, k0, m0, b0, b1);
             } else {
-              ptx::tma_load_4d(&p.tmA, &full_bar[stage], a_dst, m0, k0, b0, b1);
-              ptx::tma_load_4d(&p.tmA, &full_bar[stage], a_dst + 8192, m0 + 64, k0, b0, b1);
+              load_a(&p.tmA, stage, a_dst, m0, k0, b0, b1);
+              load_a(&p.tmA, stage, a_dst + 8192, m0 + 64, k0, b0, b1);
             }
             if (!p.b_mn) {
-              if (p.cs > 1)
-                ptx::tma_load_4d_mcast(&p.tmB, &full_bar[stage], b_dst + rank * b_slice, k0, n0 + rank * bn_slice, b0, b1, mc_mask);
-              else
-                ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst, k0, n0, b0, b1);
+              load_b(stage, b_dst, k0, n0, b0, b1);
             } else {
               for (int i = 0; i < p.BN / 64; ++i)
                 ptx::tma_load_4d(&p.tmB, &full_bar[stage], b_dst + i * 8192, n0 + i * 64, k0, b0, b1);
             }
           }
+          if (pair && rank != 0) ptx::mbar_arrive_cluster(full_leader + stage * 8);  // this CTA's copies are issued
         }
         if (++cc == p.chunks_per_tap) cc = 0, ++tap;
         if (++stage == p.stages) {
@@ -218,6 +242,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
       }
     }
     __syncwarp();
+  } else if (warp == 1 && pair && rank != 0) {
+    // the pair's MMAs are issued by the leader CTA only
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     // Whole warp runs the loop with warp-uniform values, one elected lane issues tcgen05.mma / commit.  The smem
@@ -249,11 +275,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
         if (leader) {
           const uint64_t ad = a_desc0 + static_cast<uint64_t>(stage * a_sinc);
           const uint64_t bd = b_desc0 + static_cast<uint64_t>(stage * b_sinc);
-          ptx::umma_bf16(d_tmem, ad, bd, idesc, kc != 0 ? 1u : 0u);
-          ptx::umma_bf16(d_tmem, ad + a_kinc, bd + b_kinc, idesc, 1u);
-          ptx::umma_bf16(d_tmem, ad + 2 * a_kinc, bd + 2 * b_kinc, idesc, 1u);
-          ptx::umma_bf16(d_tmem, ad + 3 * a_kinc, bd + 3 * b_kinc, idesc, 1u);
-          if (p.cs > 1)
+          if (pair) {
+            ptx::umma_bf16_pair(d_tmem, ad, bd, idesc, kc != 0 ? 1u : 0u);
+            ptx::umma_bf16_pair(d_tmem, ad + a_kinc, bd + b_kinc, idesc, 1u);
+            ptx::umma_bf16_pair(d_tmem, ad + 2 * a_kinc, bd + 2 * b_kinc, idesc, 1u);
+            ptx::umma_bf16_pair(d_tmem, ad + 3 * a_kinc, bd + 3 * b_kinc, idesc, 1u);
+            ptx::umma_commit_pair(&empty_bar[stage], mc_mask);  // release the stage in both CTAs
+          } else {
+            ptx::umma_bf16(d_tmem, ad, bd, idesc, kc != 0 ? 1u : 0u);
+            ptx::umma_bf16(d_tmem, ad + a_kinc, bd + b_kinc, idesc, 1u);
+            ptx::umma_bf16(d_tmem, ad + 2 * a_kinc, bd + 2 * b_kinc, idesc, 1u);
+            ptx::umma_bf16(d_tmem, ad + 3 * a_kinc, bd + 3 * b_kinc, idesc, 1u);
+          }
+          if (pair) {
+          } else if (p.cs > 1)
             ptx::umma_commit_mcast(&empty_bar[stage], mc_mask);  // release the stage in every CTA of the cluster
           else
             ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
@@ -264,7 +299,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
           phase ^= 1;
         }
       }
-      if (leader) ptx::umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+      if (leader) {  // accumulator complete -> epilogue (of both CTAs in pair mode)
+        if (pair)
+          ptx::umma_commit_pair(&tfull_bar[as], mc_mask);
+        else
+          ptx::umma_commit(&tfull_bar[as]);
+      }
       __syncwarp();
       as ^= 1;
       if (as == 0) aphase ^= 1;
@@ -275,8 +315,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
     const int row = q * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
-    uint32_t ring = 0;  // chunk counter selecting the store panel (2-deep)
+    uint32_t ring = 0;  // chunk counter selecting the store panel
+    const uint32_t ring_mask = static_cast<uint32_t>(p.npanel - 1);
     const bool store_leader = (warp == 2) && ptx::elect_one();
+    const uint32_t tempty_leader = pair ? ptx::mapa_u32(&tempty_bar[0], 0) : 0u;
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
       int n_tile, m_tile, b0, b1;
       gemm_decode_tile(p, tile, n_tile, m_tile, b0, b1, rank);
@@ -348,7 +390,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
         const int col0 = n0 + c0;
         const int ncol = min(32, min(p.BN - c0, p.N - col0));  // valid columns of this chunk (may be <= 0)
         const bool full = ((ncol == 32) || use_ts) && e_vec;
-        uint8_t* panel = spanel + (ring & 1) * 8192;
+        uint8_t* panel = spanel + (ring & ring_mask) * GEMM_PANEL;
         uint4 rres[4];
         if (e_res && valid && full && ncol == 32) {
           const uint4* r4 = reinterpret_cast<const uint4*>(e_res + off_r + col0);
@@ -402,12 +444,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
             }
           }
           ptx::fence_proxy_async_smem();
-          if (store_leader) ptx::bulk_wait_read<0>();  // every earlier store has finished reading its panel
+          // the panel written next (ring + 1) must have been read out by its previous store: with 4 panels that is the
+          // store issued three chunks ago, so two may stay in flight; with 2 panels every earlier store must be done
+          if (store_leader) {
+            if (ring_mask == 3)
+              ptx::bulk_wait_read<2>();
+            else
+              ptx::bulk_wait_read<0>();
+          }
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (store_leader && tile_ok && ncol > 0) {
-            const CUtensorMap* tm = (p.nphase > 1) ? (b0 == 0 ? &p.tmC : (b0 == 1 ? &p.tmC1 : (b0 == 2 ? &p.tmC2 : &p.tmC3))) : &p.tmC;
-            ptx::tma_store_4d(tm, panel, col0, sc1, (p.nphase > 1) ? sc2 : sc2, sc3);
-            ptx::bulk_commit();
+          if (store_leader) {
+            if (tile_ok && ncol > 0) {
+              const CUtensorMap* tm = (p.nphase > 1) ? (b0 == 0 ? &p.tmC : (b0 == 1 ? &p.tmC1 : (b0 == 2 ? &p.tmC2 : &p.tmC3))) : &p.tmC;
+              ptx::tma_store_4d(tm, panel, col0, sc1, sc2, sc3);
+            }
+            ptx::bulk_commit();  // one (possibly empty) group per chunk keeps the wait depth above exact
           }
           ++ring;
           return;
@@ -473,7 +524,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (pair)
+          ptx::mbar_arrive_cluster(tempty_leader + as * 8);
+        else
+          ptx::mbar_arrive(&tempty_bar[as]);
+      }
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
@@ -484,7 +540,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
   __syncthreads();
   ptx::tc_fence_after();
   if (p.cs > 1) ptx::cluster_sync_all();  // no CTA may exit while a peer can still multicast into it / arrive on its barriers
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, GEMM_TMEM_COLS);
+  if (warp == 1) {
+    if (pair)
+      ptx::tmem_dealloc_pair(tmem_base, GEMM_TMEM_COLS);
+    else
+      ptx::tmem_dealloc(tmem_base, GEMM_TMEM_COLS);
+  }
+}
+// Two entry points: a kernel containing cta_group::2 instructions can only be launched as a cluster of CTA pairs.
+__global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
+  umma_gemm_body<false>(p);
+}
+__global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_pair_kernel(const __grid_constant__ GemmParams p) {
+  umma_gemm_body<true>(p);
 }
 
 // ======================================================================= host side
@@ -602,7 +670,17 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int ksplit, l
   }
 }
 
+// Test / tuning overrides (set through mdc_dbg_tune only; 0 = automatic).
+struct GemmTune {
+  int bn = 0, cs = 0, ksplit = 0, wcopies = 1;
+};
+inline GemmTune& g_tune() {
+  static GemmTune t;
+  return t;
+}
+
 inline int pick_bn(int N) {
+  if (g_tune().bn) return g_tune().bn;
   // largest multiple of 16 that is <= 256 and divides N; otherwise min(256, roundup16(N)).
   for (int bn = 256; bn >= 64; bn -= 16)
     if (N % bn == 0) return bn;
@@ -621,23 +699,34 @@ inline int g_num_sms() {
   return n;
 }
 
-// cluster of 2 along M when the B tile splits into two swizzle-atom-aligned halves (K-major B only); must be decided
-// BEFORE the B tensor map is encoded because each CTA's TMA box covers only its BN/cs rows.
-inline int decide_cs(const GemmParams& p) {
-  static const bool no_mc = getenv("MDC_NO_MCAST") != nullptr;
-  // only for launches with several tiles per CTA: the two cluster barriers cost more than they save on short kernels
-  const long long tiles = 1LL * p.m_tiles * p.n_tiles * (p.nb0 > 0 ? p.nb0 : 1) * (p.nb1 > 0 ? p.nb1 : 1);
-  return (!no_mc && !p.b_mn && tiles >= 2LL * g_num_sms() && (p.BN / 2) % 8 == 0 && p.BN >= 128) ? 2 : 1;
+// Cluster mode of a launch; must be decided BEFORE the B tensor map is encoded because each CTA's TMA box covers only
+// its BN/cs rows.  pair: CTA-pair MMA (see GemmParams::pair); otherwise cs > 1 = B multicast over cs CTAs (consecutive
+// m-tiles of one n-tile).  Both need a K-major B whose per-CTA slice is a whole number of 8-row swizzle atoms.
+inline void decide_cluster(GemmParams& p) {
+  static const bool no_pair = getenv("MDC_NO_PAIR") != nullptr;
+  p.cs = 1, p.pair = 0;
+  if (p.b_mn) return;
+  const int t = g_tune().cs;  // 0 auto, 1 none, 2 pair, 3 multicast x2, 4 multicast x4
+  if (t == 1) return;
+  if (t == 3 || t == 4) {
+    const int cs = t == 3 ? 2 : 4;
+    if ((p.BN / cs) % 8 == 0) p.cs = cs;
+    return;
+  }
+  if ((t == 2 || !no_pair) && p.m_tiles >= 2 && p.BN % 16 == 0) p.cs = 2, p.pair = 1;
 }
 inline void finish_plan(GemmPlan& g) {
   GemmParams& p = g.p;
-  const int b_stage = p.BN * 128;
-  int stages = (GEMM_SMEM_BUDGET - GEMM_HEADER - 1024) / (GEMM_A_STAGE + b_stage);
-  stages = std::max(2, std::min(stages, GEMM_MAX_STAGES));
+  const int b_stage = (p.pair ? p.BN / 2 : p.BN) * 128;
+  auto stages_for = [&](int npanel) {
+    return std::min((GEMM_SMEM_BUDGET - GEMM_HEADER0 - npanel * GEMM_PANEL - 1024) / (GEMM_A_STAGE + b_stage), GEMM_MAX_STAGES);
+  };
+  p.npanel = (stages_for(4) == stages_for(2)) ? 4 : 2;  // never trade a pipeline stage for store depth
+  const int stages = std::max(2, stages_for(p.npanel));
   p.stages = stages;
-  g.smem = GEMM_HEADER + 1024 + stages * (GEMM_A_STAGE + b_stage);
-  p.idesc = ptx::make_idesc_bf16(GEMM_BM, p.BN, p.a_mn, p.b_mn);
-  if (p.cs < 1) p.cs = 1;  // set by the planners via decide_cs() before the B map was built
+  g.smem = GEMM_HEADER0 + p.npanel * GEMM_PANEL + 1024 + stages * (GEMM_A_STAGE + b_stage);
+  p.idesc = ptx::make_idesc_bf16(p.pair ? 2 * GEMM_BM : GEMM_BM, p.BN, p.a_mn, p.b_mn);
+  if (p.cs < 1) p.cs = 1, p.pair = 0;  // set by the planners via decide_cluster() before the B map was built
   long long total = 1LL * ((p.m_tiles + p.cs - 1) / p.cs) * p.n_tiles * (p.ksplit > 1 ? p.ksplit : p.nb0) * p.nb1;
   g.grid = static_cast<int>(std::min<long long>(total * p.cs, (g_num_sms() / p.cs) * p.cs));
   const uintptr_t o = reinterpret_cast<uintptr_t>(p.out), r = reinterpret_cast<uintptr_t>(p.res);
@@ -707,7 +796,7 @@ inline GemmPlan plan_gemm(int M, int N, int K, const Operand& A, const Operand& 
     str[0] = o.ld, str[1] = s0, str[2] = s1;
     return make_tmap_bf16(o.ptr, dims, str, box);
   };
-  p.cs = decide_cs(p);
+  decide_cluster(p);
   p.tmA = mk(A, M, GEMM_BM);
   p.tmB = mk(B, N, p.BN / p.cs);
   fill_epilogue(p, e);
@@ -764,7 +853,7 @@ inline GemmPlan plan_conv3x3(int NB, int H, int W, int C, int Cout, const void* 
   {
     uint64_t dims[4] = {(uint64_t)9 * Cp, (uint64_t)Cout, 1, 1};
     uint64_t str[3] = {(uint64_t)9 * Cp, (uint64_t)9 * Cp * Cout, (uint64_t)9 * Cp * Cout};
-    p.cs = decide_cs(p);
+    decide_cluster(p);
     uint32_t box[4] = {64, (uint32_t)(p.BN / p.cs), 1, 1};
     p.tmB = make_tmap_bf16(wpk, dims, str, box);
   }
@@ -831,7 +920,7 @@ inline GemmPlan plan_upconv_fwd(int NB, int H, int W, int C, int Cout, const voi
   {
     uint64_t dims[4] = {(uint64_t)16 * Cp, (uint64_t)Cout, 1, 1};
     uint64_t str[3] = {(uint64_t)16 * Cp, (uint64_t)16 * Cp * Cout, (uint64_t)16 * Cp * Cout};
-    p.cs = decide_cs(p);
+    decide_cluster(p);
     uint32_t box[4] = {64, (uint32_t)(p.BN / p.cs), 1, 1};
     p.tmB = make_tmap_bf16(wpk, dims, str, box);
   }
@@ -879,7 +968,7 @@ inline GemmPlan plan_upconv_bwd(int NB, int H, int W, int C, int Cout, const voi
   {
     uint64_t dims[4] = {(uint64_t)16 * Cop, (uint64_t)C, 1, 1};
     uint64_t str[3] = {(uint64_t)16 * Cop, (uint64_t)16 * Cop * C, (uint64_t)16 * Cop * C};
-    p.cs = decide_cs(p);
+    decide_cluster(p);
     uint32_t box[4] = {64, (uint32_t)(p.BN / p.cs), 1, 1};
     p.tmB = make_tmap_bf16(wpk, dims, str, box);
   }
@@ -897,6 +986,7 @@ inline void gemm_set_smem_attr() {
   static bool done = false;
   if (!done) {
     MDC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    MDC_CUDA(cudaFuncSetAttribute(umma_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     done = true;
   }
 }
@@ -918,19 +1008,32 @@ inline void launch_gemm_kernel(const GemmPlan& g, cudaStream_t st) {
     ++na;
   }
   cfg.attrs = attr, cfg.numAttrs = na;
-  MDC_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel, g.p));
+  MDC_CUDA(cudaLaunchKernelEx(&cfg, g.p.pair ? umma_gemm_pair_kernel : umma_gemm_kernel, g.p));
 }
 
 // Decide on split-K for a finished plan: few output tiles, long K loop.  `ws` must hold ws_floats(plan) floats.
 inline int choose_ksplit(const GemmPlan& g) {
   const GemmParams& p = g.p;
   if (p.nb0 != 1 || p.nb1 != 1 || p.bias_img || p.out_f32 || p.conv == 2 || p.nphase > 1) return 1;
-  const int tiles = p.m_tiles * p.n_tiles;
-  static const int max_tiles = getenv("MDC_SPLITK_MAXTILES") ? atoi(getenv("MDC_SPLITK_MAXTILES")) : 32;  // measured sweep: 16 / 30 / 48 / 74 -> 26.2 / 25.5 / 25.5 / 25.9 ms per step
-  if (tiles > max_tiles || p.num_k_chunks < 8) return 1;
-  int ks = (g_num_sms() + tiles - 1) / tiles;
-  ks = std::min(ks, p.num_k_chunks / 4);
-  return std::max(ks, 1);
+  if (g_tune().ksplit > 0) return g_tune().ksplit;
+  const int tiles = ((p.m_tiles + p.cs - 1) / p.cs) * p.cs * p.n_tiles, nk = p.num_k_chunks, sms = (g_num_sms() / p.cs) * p.cs;
+  static const int max_tiles = getenv("MDC_SPLITK_MAXTILES") ? atoi(getenv("MDC_SPLITK_MAXTILES")) : 100;
+  if (tiles > max_tiles || nk < 8) return 1;
+  // Cost model in microseconds.  A k-chunk is bound by the L2 -> SM fill of its operand tiles (~100 GB/s per SM when
+  // every SM pulls), an item (tile x split) pays a pipeline fill + epilogue, a split launch pays the reduction kernel
+  // and the fp32 partials' round trip through L2.  Work items beyond one wave of CTAs serialise.
+  const double t_chunk = (p.bytesA + p.BN * 128.0 / p.cs) / 100e3, t_item = 2.5, t_red = 4.0, l2_bytes_per_us = 5e6;
+  auto waves = [&](int items) { return (items + sms - 1) / sms; };
+  int best = 1;
+  double best_cost = waves(tiles) * (nk * t_chunk + t_item);
+  for (int s = 2; s <= std::min(nk / 4, 64); ++s) {
+    const int kc = (nk + s - 1) / s;
+    if ((nk + kc - 1) / kc != s) continue;  // enable_splitk would round this split count down
+    const int items = tiles * s;
+    const double cost = waves(items) * (kc * t_chunk + t_item) + t_red + 2.0 * items * GEMM_BM * p.BN * 4.0 / l2_bytes_per_us;
+    if (cost < (best == 1 ? 0.9 * best_cost : best_cost)) best = s, best_cost = cost;
+  }
+  return best;
 }
 inline size_t enable_splitk(GemmPlan& g, int ksplit) {  // returns the workspace size in floats
   GemmParams& p = g.p;

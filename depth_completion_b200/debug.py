@@ -72,3 +72,8 @@ def conv3x3(x_nhwc, w_oihw, *, dgrad=False, bias=None, bias_img=None, res=None, 
         ptr(w_oihw), C.c_int(int(dgrad)), ptr(bias), ptr(bias_img), ptr(res),
         _ll(res.stride(2) if res is not None else 0), ptr(out), _ll(ldo), C.c_int(iters), C.byref(ms)))
     return out[..., :Cres], ms.value
+
+
+def tune(bn=0, cs=0, ksplit=0, wcopies=1):
+    """Planner overrides for tests / sweeps (include/mdc_debug.h: mdc_dbg_tune); call tune() to reset."""
+    check(lib().mdc_dbg_tune(C.c_int(bn), C.c_int(cs), C.c_int(ksplit), C.c_int(wcopies)))
