@@ -76,3 +76,26 @@ def test_conv3x3(cuda, NB, H, W, C, Cout, dgrad):
     torch.cuda.synchronize()
     err = _rel_err(out, ref)
     assert err < 2 ** -7, f"conv rel err {err}"
+
+
+@pytest.mark.parametrize("cs,ksplit", [(1, 0), (2, 0), (3, 0), (4, 0), (1, 3), (2, 5), (1, -1), (2, -1)])
+@pytest.mark.parametrize("H,W,C,Cout", [(18, 24, 640, 320), (9, 12, 1280, 256), (23, 17, 192, 160)])
+def test_conv3x3_cluster_and_splitk_modes(cuda, H, W, C, Cout, cs, ksplit):
+    """Every launch mode of the GEMM kernel (single CTA, CTA pair = cta_group::2 MMA, B multicast over 2 / 4 CTAs,
+    forced and cost-model split-K) computes the same convolution; checked against torch fp32."""
+    from depth_completion_b200 import debug
+
+    g = torch.Generator(device="cuda").manual_seed(H * 131 + C)
+    w = torch.randn(Cout, C, 3, 3, device=cuda, generator=g) * (1.0 / (3 * C ** 0.5))
+    x = torch.randn(1, C, H, W, device=cuda, generator=g).bfloat16()
+    bias = torch.randn(Cout, device=cuda, generator=g)
+    res = torch.randn(1, H, W, Cout, device=cuda, generator=g).bfloat16()
+    ref = torch.nn.functional.conv2d(x.float(), w.bfloat16().float(), bias, padding=1).permute(0, 2, 3, 1) + res.float()
+    try:
+        debug.tune(cs=cs, ksplit=ksplit)
+        out, _ = debug.conv3x3(x.permute(0, 2, 3, 1).contiguous(), w, bias=bias, res=res)
+        torch.cuda.synchronize()
+    finally:
+        debug.tune()
+    err = _rel_err(out, ref)
+    assert err < 2 ** -7, f"conv rel err {err} (cs={cs}, ksplit={ksplit})"
