@@ -681,8 +681,11 @@ inline GemmTune& g_tune() {
 
 inline int pick_bn(int N) {
   if (g_tune().bn) return g_tune().bn;
-  // largest multiple of 16 that is <= 256 and divides N; otherwise min(256, roundup16(N)).
-  for (int bn = 256; bn >= 64; bn -= 16)
+  // largest divisor of N that is a multiple of 32 (whole 32-column chunks: the TMA-store epilogue applies), else of 16,
+  // and <= 256; otherwise min(256, roundup16(N)).
+  for (int bn = 256; bn >= 64; bn -= 32)
+    if (N % bn == 0) return bn;
+  for (int bn = 240; bn >= 64; bn -= 16)
     if (N % bn == 0) return bn;
   int r = ((N + 15) / 16) * 16;
   return r > 256 ? 256 : r;
