@@ -123,6 +123,10 @@ struct GroupNormOp : Op {
   float* stats;
   GNShape s;
   int threads, threads_b;
+  // single-launch variants (slab in shared memory + grid barrier) when the tensor is small enough
+  GNShape sfu;
+  bool fuse_f = false, fuse_b = false;
+  size_t smem_f = 0, smem_b = 0;
   bool acc = false;
   void plan_bwd() override {
     acc = x->grad_set;
@@ -130,8 +134,8 @@ struct GroupNormOp : Op {
   }
   void fwd(cudaStream_t st) override;
   void bwd(cudaStream_t st) override;
-  int n_fwd() const override { return 2; }
-  int n_bwd() const override { return 2; }
+  int n_fwd() const override { return fuse_f ? 1 : 2; }
+  int n_bwd() const override { return fuse_b ? 1 : 2; }
 };
 struct LayerNormOp : Op {
   Tensor *x, *y;
@@ -314,6 +318,7 @@ struct Engine {
   size_t gn_partial_floats = 0;
   float* gn_gstats = nullptr;
   unsigned int* gn_ticket = nullptr;
+  unsigned int* gn_bar = nullptr;  // grid barrier of the single-launch GroupNorm kernels (count, generation, timeout flag)
   float* attn_S = nullptr;
   size_t attn_S_floats = 0;
   // time embedding
@@ -469,12 +474,22 @@ inline void LinearOp::bwd(cudaStream_t st) {
                                                                         acc_res);
 }
 inline void GroupNormOp::fwd(cudaStream_t st) {
+  if (fuse_f) {
+    launch_k(gn_fused_fwd_kernel, dim3(sfu.N * sfu.blocks_per_img), dim3(threads), smem_f, st, x->d, sfu, E->gn_partial, eps, stats, E->gn_bar,
+             gamma, beta, silu, y->d, y->ld);
+    return;
+  }
   const int grid = s.N * s.blocks_per_img;
   launch_k(gn_stats_kernel, dim3(grid), dim3(threads), ((threads + 31) / 32) * 2 * s.G * sizeof(float), st, x->d, s, E->gn_partial, eps, stats,
            E->gn_ticket);
   launch_k(gn_apply_kernel, dim3(grid), dim3(threads), 0, st, x->d, s, stats, gamma, beta, silu, y->d, y->ld);
 }
 inline void GroupNormOp::bwd(cudaStream_t st) {
+  if (fuse_b) {
+    launch_k(gn_fused_bwd_kernel, dim3(sfu.N * sfu.blocks_per_img), dim3(threads), smem_b, st, x->d, y->g, y->ld, sfu, stats, gamma, beta, silu,
+             E->gn_partial, E->gn_bar, x->g, x->ld, acc);
+    return;
+  }
   const int grid = s.N * s.blocks_per_img;
   launch_k(gn_bwd_stats_kernel, dim3(grid), dim3(threads_b), ((threads_b + 31) / 32) * 2 * s.G * sizeof(float), st, x->d, y->g, y->ld, s, stats, gamma,
            beta, silu, E->gn_partial, E->gn_gstats, E->gn_ticket);
@@ -673,6 +688,29 @@ inline Tensor* Engine::group_norm(Tensor* x, const std::string& key, float eps, 
   s.pix_per_block = ppb;
   s.blocks_per_img = (s.HW + ppb - 1) / ppb;
   op->s = s;
+  {  // single-launch variant: one CTA per SM at most, its pixel slab (x, or x and dy) staged in shared memory
+    static const bool no_fuse = getenv("MDC_NO_GNFUSE") != nullptr;
+    GNShape f = s;
+    const int bpi = std::max(1, std::min(g_num_sms() / x->n, s.HW));
+    f.pix_per_block = (s.HW + bpi - 1) / bpi;
+    f.blocks_per_img = (s.HW + f.pix_per_block - 1) / f.pix_per_block;
+    const size_t slab = static_cast<size_t>(f.pix_per_block) * x->c * 2;
+    const size_t extra = (static_cast<size_t>((op->threads + 31) / 32) * 2 * G + 2 * G) * sizeof(float);
+    const size_t cap = 200 * 1024;
+    const bool ok = !no_fuse && op->threads >= 8 * G && x->n * f.blocks_per_img <= g_num_sms();
+    op->sfu = f;
+    op->smem_f = slab + extra, op->smem_b = 2 * slab + extra;
+    op->fuse_f = ok && op->smem_f <= cap;
+    op->fuse_b = ok && op->smem_b <= cap;
+    if (op->fuse_f || op->fuse_b) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        MDC_CUDA(cudaFuncSetAttribute(gn_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cap)));
+        MDC_CUDA(cudaFuncSetAttribute(gn_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cap)));
+        attr_set = true;
+      }
+    }
+  }
   op->stats = arena.make<float>(2ull * x->n * G);
   gn_partial_floats = std::max<size_t>(gn_partial_floats, static_cast<size_t>(2) * G * x->n * s.blocks_per_img);
   push(op, key);
@@ -990,6 +1028,7 @@ inline void Engine::finalize_plans() {
   gn_partial = arena.make<float>(gn_partial_floats + 64);
   gn_gstats = arena.make<float>(2ull * 64 * MAXN + 64);
   gn_ticket = arena.make<unsigned int>(MAXN + 16);
+  gn_bar = arena.make<unsigned int>(16);
   attn_S = arena.make<float>(attn_S_floats + 64);
   temb_cur = arena.make<float>(temb_total + 64);
   for (auto* ops : {&unet_ops, &dec_ops}) {

@@ -418,6 +418,245 @@ __global__ void __launch_bounds__(384, 2) gn_bwd_apply_kernel(const bf16* __rest
   }
 }
 
+// --------------------------------------------------------------------------- single-launch GroupNorm
+// For activations whose per-CTA slab fits in shared memory (every UNet tensor, the low-resolution decoder tensors) the
+// two passes run in ONE kernel: each CTA stages its pixel slab in shared memory while accumulating the group
+// partials, all CTAs meet at a grid barrier, every CTA reduces the partials of its image in a fixed order and applies
+// the normalisation from shared memory.  The tensor is read from global memory once and a launch disappears.
+// The grid never exceeds the SM count (one CTA per SM), so all CTAs are co-resident; dependents are released
+// (griddepcontrol.launch_dependents) only after the barrier, so no later grid can take an SM away before that.
+
+// Sense-reversing grid barrier: bar[0] arrival counter, bar[1] generation, bar[2] sticky timeout flag.  Self-cleaning.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned int* vgen = bar + 1;
+    const unsigned int gen = *vgen;  // read before arriving: the generation cannot advance without this CTA
+    __threadfence();
+    if (atomicAdd(bar, 1u) == nblocks - 1) {
+      bar[0] = 0u;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      const long long t0 = clock64();
+      while (*vgen == gen) {
+        if (clock64() - t0 > (4LL << 30)) {  // ~2 s: never hang the device; results are then garbage and flagged
+          atomicExch(bar + 2, 1u);
+          break;
+        }
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Fixed-order reduction of the per-block partials of image n: 8 lanes per group, each summing every 8th block in
+// double, combined by an xor tree.  Writes out2[2g], out2[2g+1] (shared memory) for all groups; needs >= 8*G threads.
+__device__ __forceinline__ void gn_reduce_partials(const float* __restrict__ partial, int n, int G, int bpi, double m,
+                                                   float eps, int mode, float* __restrict__ out2) {
+  const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
+  if (g < G) {
+    double a = 0, b = 0;
+#pragma unroll 4
+    for (int k = j; k < bpi; k += 8) {
+      const float2 pv = __ldcg(reinterpret_cast<const float2*>(partial + (1LL * (n * bpi + k) * G + g) * 2));
+      a += pv.x, b += pv.y;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (j == 0) {
+      if (mode == 0) {
+        double mean = a / m, var = b / m - mean * mean;
+        if (var < 0) var = 0;
+        out2[2 * g] = static_cast<float>(mean);
+        out2[2 * g + 1] = static_cast<float>(1.0 / sqrt(var + eps));
+      } else {
+        out2[2 * g] = static_cast<float>(a / m);
+        out2[2 * g + 1] = static_cast<float>(b / m);
+      }
+    }
+  }
+}
+
+// Merge a thread's 4 channel-pair sums into the per-warp shared accumulators, then the warps into partial[blockIdx].
+__device__ __forceinline__ void gn_block_partial(const float (&sa)[4], const float (&sb)[4], int cv, int cpg, int G,
+                                                 float* __restrict__ sh, float* __restrict__ partial) {
+  const int nwarps_ = (blockDim.x + 31) >> 5, wid_ = threadIdx.x >> 5;
+  float* mine = sh + wid_ * 2 * G;
+  int gprev = -1;
+  float a = 0.f, b = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int g = (cv * 8 + 2 * i) / cpg;
+    if (g != gprev && gprev >= 0) {
+      atomicAdd(&mine[2 * gprev], a), atomicAdd(&mine[2 * gprev + 1], b);
+      a = b = 0.f;
+    }
+    gprev = g, a += sa[i], b += sb[i];
+  }
+  atomicAdd(&mine[2 * gprev], a), atomicAdd(&mine[2 * gprev + 1], b);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < nwarps_; ++w) t += sh[w * 2 * G + i];
+    partial[1LL * blockIdx.x * 2 * G + i] = t;
+  }
+}
+
+// shared memory: [pix_per_block * C bf16 slab][nwarps * 2G floats][2G floats]
+__global__ void __launch_bounds__(512, 1) gn_fused_fwd_kernel(const bf16* __restrict__ x, GNShape s,
+                                                              float* __restrict__ partial, float eps,
+                                                              float* __restrict__ stats_out, unsigned int* __restrict__ bar,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, int silu,
+                                                              bf16* __restrict__ y, long long ldy) {
+  ptx::pdl_wait();
+  extern __shared__ __align__(16) uint8_t gn_smem[];
+  const int CV = s.C >> 3, cpg = s.C / s.G;
+  const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
+  const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
+  const int nwarps_ = (blockDim.x + 31) >> 5;
+  BF8* slab = reinterpret_cast<BF8*>(gn_smem);
+  float* sh = reinterpret_cast<float*>(gn_smem + static_cast<size_t>(s.pix_per_block) * s.C * 2);
+  float* sstat = sh + nwarps_ * 2 * s.G;
+  for (int i = threadIdx.x; i < nwarps_ * 2 * s.G; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  float sum[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
+  const int p0 = b * s.pix_per_block, p1 = min(s.HW, p0 + s.pix_per_block);
+  const bf16* xb = x + (1LL * n * s.HW) * s.ld + cv * 8;
+  for (int p = p0 + r; p < p1; p += R * GN_UNROLL) {
+    BF8 v[GN_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u)
+      if (p + u * R < p1) v[u] = *reinterpret_cast<const BF8*>(xb + 1LL * (p + u * R) * s.ld);
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u)
+      if (p + u * R < p1) {
+        slab[(p + u * R - p0) * CV + cv] = v[u];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float2 t = __bfloat1622float2(v[u].v[i]);
+          sum[i] += t.x + t.y;
+          sq[i] += t.x * t.x + t.y * t.y;
+        }
+      }
+  }
+  gn_block_partial(sum, sq, cv, cpg, s.G, sh, partial);
+  grid_barrier(bar, gridDim.x);
+  ptx::pdl_launch();
+  gn_reduce_partials(partial, n, s.G, s.blocks_per_img, 1.0 * s.HW * cpg, eps, 0, sstat);
+  __syncthreads();
+  if (b == 0)
+    for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) stats_out[2 * n * s.G + i] = sstat[i];
+  float sc[8], sf[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int c = cv * 8 + i, g = c / cpg;
+    sc[i] = sstat[2 * g + 1] * gamma[c];
+    sf[i] = beta[c] - sstat[2 * g] * sc[i];
+  }
+  bf16* yb = y + (1LL * n * s.HW) * ldy + cv * 8;
+  for (int p = p0 + r; p < p1; p += R) {  // each thread re-reads exactly the slab entries it wrote
+    float f[8];
+    bf8_to_f(slab[(p - p0) * CV + cv], f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float h = f[i] * sc[i] + sf[i];
+      f[i] = silu ? siluf_(bf16r(h)) : h;
+    }
+    *reinterpret_cast<BF8*>(yb + 1LL * p * ldy) = f_to_bf8(f);
+  }
+}
+
+// shared memory: [x slab][dy slab][nwarps * 2G floats][2G floats]
+__global__ void __launch_bounds__(512, 1) gn_fused_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                                              long long lddy, GNShape s,
+                                                              const float* __restrict__ stats,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, int silu,
+                                                              float* __restrict__ partial, unsigned int* __restrict__ bar,
+                                                              bf16* __restrict__ dx, long long lddx, int acc) {
+  ptx::pdl_wait();
+  extern __shared__ __align__(16) uint8_t gn_smem[];
+  const int CV = s.C >> 3, cpg = s.C / s.G;
+  const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
+  const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
+  const int nwarps_ = (blockDim.x + 31) >> 5;
+  const size_t slab_bytes = static_cast<size_t>(s.pix_per_block) * s.C * 2;
+  BF8* slab_x = reinterpret_cast<BF8*>(gn_smem);
+  BF8* slab_d = reinterpret_cast<BF8*>(gn_smem + slab_bytes);
+  float* sh = reinterpret_cast<float*>(gn_smem + 2 * slab_bytes);
+  float* sstat = sh + nwarps_ * 2 * s.G;
+  for (int i = threadIdx.x; i < nwarps_ * 2 * s.G; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  GNBwdConst k;
+  gn_load_const(k, s, n, cv, stats, gamma, beta);
+  float sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
+  const int p0 = b * s.pix_per_block, p1 = min(s.HW, p0 + s.pix_per_block);
+  const bf16* xb = x + (1LL * n * s.HW) * s.ld + cv * 8;
+  const bf16* db = dy + (1LL * n * s.HW) * lddy + cv * 8;
+  constexpr int U = 2;
+  for (int p = p0 + r; p < p1; p += R * U) {
+    BF8 vx[U], vd[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (p + u * R < p1) {
+        vx[u] = *reinterpret_cast<const BF8*>(xb + 1LL * (p + u * R) * s.ld);
+        vd[u] = *reinterpret_cast<const BF8*>(db + 1LL * (p + u * R) * lddy);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (p + u * R < p1) {
+        slab_x[(p + u * R - p0) * CV + cv] = vx[u];
+        slab_d[(p + u * R - p0) * CV + cv] = vd[u];
+        float fx[8], fd[8];
+        bf8_to_f(vx[u], fx);
+        bf8_to_f(vd[u], fd);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float xh = (fx[i] - k.mean[i >> 1]) * k.rstd[i >> 1];
+          float d = fd[i];
+          if (silu) d *= silu_grad(bf16r(xh * k.ga[i] + k.be[i]));
+          d *= k.ga[i];
+          sa[i >> 1] += d;
+          sb[i >> 1] += d * xh;
+        }
+      }
+  }
+  gn_block_partial(sa, sb, cv, cpg, s.G, sh, partial);
+  grid_barrier(bar, gridDim.x);
+  ptx::pdl_launch();
+  gn_reduce_partials(partial, n, s.G, s.blocks_per_img, 1.0 * s.HW * cpg, 0.f, 1, sstat);
+  __syncthreads();
+  float m1[4], m2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int g = (cv * 8 + 2 * i) / cpg;
+    m1[i] = sstat[2 * g], m2[i] = sstat[2 * g + 1];
+  }
+  bf16* ob = dx + (1LL * n * s.HW) * lddx + cv * 8;
+  for (int p = p0 + r; p < p1; p += R) {
+    float fx[8], fd[8], o[8];
+    bf8_to_f(slab_x[(p - p0) * CV + cv], fx);
+    bf8_to_f(slab_d[(p - p0) * CV + cv], fd);
+    if (acc) bf8_to_f(*reinterpret_cast<const BF8*>(ob + 1LL * p * lddx), o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float xh = (fx[i] - k.mean[i >> 1]) * k.rstd[i >> 1];
+      float d = fd[i];
+      if (silu) d *= silu_grad(bf16r(xh * k.ga[i] + k.be[i]));
+      d *= k.ga[i];
+      float g = k.rstd[i >> 1] * (d - m1[i >> 1] - xh * m2[i >> 1]);
+      o[i] = acc ? o[i] + g : g;
+    }
+    *reinterpret_cast<BF8*>(ob + 1LL * p * lddx) = f_to_bf8(o);
+  }
+}
+
 // =========================================================================== LayerNorm (one warp per row)
 constexpr int LN_MAXV = 5;  // supports d <= 32*8*5 = 1280
 
