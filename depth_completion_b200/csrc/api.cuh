@@ -99,6 +99,12 @@ int mdc_get_state(mdc_handle* h, void* x_out_bf16, float* scale_host, float* shi
     }
   });
 }
+int mdc_encode(mdc_handle* h, const void* imgs, int dtype, int channels, void* latents_out_bf16) {
+  return mdc::guarded([&] {
+    MDC_CHECK(h, "null handle");
+    h->e->encode(imgs, dtype, channels, latents_out_bf16);
+  });
+}
 int mdc_decode_final(mdc_handle* h, float* dense_out) {
   return mdc::guarded([&] {
     MDC_CHECK(h && dense_out, "null argument");

@@ -305,7 +305,10 @@ struct Engine {
   std::map<std::string, Tensor*> named;
   std::map<std::string, std::vector<WeightSlot*>> wmap;
   std::deque<WeightSlot> wslots;
-  std::vector<std::unique_ptr<Op>> unet_ops, dec_ops;
+  std::vector<std::unique_ptr<Op>> unet_ops, dec_ops, enc_ops;  // enc_ops: VAE encoder, forward only (per-frame prologue)
+  bool alloc_grads = true;
+  size_t n_split_step = 0;
+  Tensor *enc_in = nullptr, *enc_out = nullptr;
   std::vector<std::unique_ptr<Op>>* cur_ops = nullptr;
   cudaStream_t stream = 0;
 
@@ -398,6 +401,9 @@ struct Engine {
   bool use_graph = true;
   ~Engine();
   void decode_final(float* dense_out);
+  void build_encoder();
+  Tensor* vae_mid_attention(Tensor* h, const std::string& A);
+  void encode(const void* imgs, int dtype, int channels, void* latents_out);
   void read_tensor(const std::string& name, int which, float* out_nchw);
   long long launches_per_step = 0;
   // split-K: plans with few output tiles and a long K loop share one fp32 partial-sum workspace
@@ -572,7 +578,7 @@ inline Tensor* Engine::new_tensor(int n, int h, int w, int c, const std::string&
   t->name = name;
   size_t el = static_cast<size_t>(t->rows()) * t->ld + 64;
   t->d = arena.make<bf16>(el);
-  if (with_grad) t->g = arena.make<bf16>(el);
+  if (with_grad && alloc_grads) t->g = arena.make<bf16>(el);
   if (!name.empty()) named[name] = t;
   return t;
 }
@@ -973,6 +979,68 @@ inline void Engine::build_unet() {
   te_l2b = slot(U + "time_embedding.linear_2.bias", W_VEC, boc[0] * 4, 0);
 }
 
+// single-head attention of the VAE mid blocks (bias on q/k/v/out, residual): GroupNorm -> fused qkv linear -> SDPA -> out
+inline Tensor* Engine::vae_mid_attention(Tensor* h, const std::string& A) {
+  const int c0 = h->c;
+  Tensor* gn = group_norm(h, A + ".group_norm", 1e-6f, false);
+  Tensor* qkv = new_tensor(N, h->h, h->w, 3 * c0, "");
+  bf16* w = arena.make<bf16>(3ull * c0 * c0 + 64);
+  bf16* wt = arena.make<bf16>(3ull * c0 * c0 + 64);
+  float* b = arena.make<float>(3ull * c0 + 16);
+  const char* nm[3] = {".to_q", ".to_k", ".to_v"};
+  for (int i = 0; i < 3; ++i) {
+    slot_lin_into(A + nm[i] + ".weight", c0, c0, w + 1ull * i * c0 * c0, c0, wt + i * c0, 3 * c0);
+    slot_vec_into(A + nm[i] + ".bias", c0, b + i * c0);
+  }
+  auto* op = new LinearOp();
+  op->E = this, op->x = gn, op->y = qkv, op->res = nullptr, op->w = w, op->wt = wt, op->ld_w = c0, op->ld_wt = 3 * c0;
+  op->bias = b;
+  Epilogue e;
+  e.out = qkv->d, e.ldc = qkv->ld, e.bias = b;
+  Operand Aop{gn->d, 0, gn->ld, 0, 0}, Bm{w, 0, c0, 0, 0};
+  op->pf = plan_gemm(static_cast<int>(gn->rows()), 3 * c0, c0, Aop, Bm, e);
+  push(op, A + ".to_qkv");
+  Tensor* ao = self_attention(qkv, 1, A + ".sdpa");
+  Tensor* y = linear(ao, c0, A + ".to_out.0", true, h);
+  y->name = A, named[A] = y;
+  return y;
+}
+
+// ------------------------------------------------------------------------------------------------ VAE encoder graph
+// Forward only (marigold_dc.py:687-698 -> AutoencoderKL.encode(...).latent_dist.mode()).
+// Down-sampling is F.pad(x, (0,1,0,1)) + conv3x3 stride 2 pad 0 = the stride-1 pad-1 conv sampled at ODD positions.
+inline void Engine::build_encoder() {
+  cur_ops = &enc_ops;
+  alloc_grads = false;
+  const int nb = cfg.vae_nblocks, L = cfg.vae_layers_per_block;
+  const int* boc = cfg.vae_block_ch;
+  const std::string V = "vae.";
+  enc_in = new_tensor(N, PPH, PPW, 3, "vae.enc_in");
+  Tensor* h = conv3x3(enc_in, boc[0], V + "encoder.conv_in");
+  for (int i = 0; i < nb; ++i) {
+    const std::string B = V + "encoder.down_blocks." + std::to_string(i);
+    for (int j = 0; j < L; ++j) h = resnet(h, boc[i], B + ".resnets." + std::to_string(j), false, 1e-6f);
+    if (i != nb - 1) {
+      MDC_CHECK(h->h % 2 == 0 && h->w % 2 == 0, "encoder: odd feature map %dx%d", h->h, h->w);
+      Tensor* full = conv3x3(h, h->c, B + ".downsamplers.0.conv");
+      Tensor* y = new_tensor(N, h->h / 2, h->w / 2, h->c, "");
+      auto* op = new SubsampleOp();
+      op->x = full, op->y = y, op->off = 1;
+      push(op, B + ".downsamplers.0");
+      h = y;
+    }
+  }
+  h = resnet(h, h->c, V + "encoder.mid_block.resnets.0", false, 1e-6f);
+  h = vae_mid_attention(h, V + "encoder.mid_block.attentions.0");
+  h = resnet(h, h->c, V + "encoder.mid_block.resnets.1", false, 1e-6f);
+  h = group_norm(h, V + "encoder.conv_norm_out", 1e-6f, true);
+  h = conv3x3(h, 2 * cfg.vae_latent_ch, V + "encoder.conv_out");
+  enc_out = linear(h, 2 * cfg.vae_latent_ch, V + "quant_conv", true);
+  named["vae.enc_out"] = enc_out;
+  MDC_CHECK(enc_out->h == lh && enc_out->w == lw, "encoder output %dx%d != latent %dx%d", enc_out->h, enc_out->w, lh, lw);
+  alloc_grads = true;
+}
+
 // ------------------------------------------------------------------------------------------------ VAE decoder graph
 inline void Engine::build_decoder() {
   cur_ops = &dec_ops;
@@ -986,30 +1054,7 @@ inline void Engine::build_decoder() {
   h = conv3x3(h, c0, V + "decoder.conv_in");
   named["vae.decoder.conv_in"] = h;
   h = resnet(h, c0, V + "decoder.mid_block.resnets.0", false, 1e-6f);
-  {  // single-head attention with bias and residual
-    const std::string A = V + "decoder.mid_block.attentions.0";
-    Tensor* gn = group_norm(h, A + ".group_norm", 1e-6f, false);
-    Tensor* qkv = new_tensor(N, h->h, h->w, 3 * c0, "");
-    bf16* w = arena.make<bf16>(3ull * c0 * c0 + 64);
-    bf16* wt = arena.make<bf16>(3ull * c0 * c0 + 64);
-    float* b = arena.make<float>(3ull * c0 + 16);
-    const char* nm[3] = {".to_q", ".to_k", ".to_v"};
-    for (int i = 0; i < 3; ++i) {
-      slot_lin_into(A + nm[i] + ".weight", c0, c0, w + 1ull * i * c0 * c0, c0, wt + i * c0, 3 * c0);
-      slot_vec_into(A + nm[i] + ".bias", c0, b + i * c0);
-    }
-    auto* op = new LinearOp();
-    op->E = this, op->x = gn, op->y = qkv, op->res = nullptr, op->w = w, op->wt = wt, op->ld_w = c0, op->ld_wt = 3 * c0;
-    op->bias = b;
-    Epilogue e;
-    e.out = qkv->d, e.ldc = qkv->ld, e.bias = b;
-    Operand Aop{gn->d, 0, gn->ld, 0, 0}, Bm{w, 0, c0, 0, 0};
-    op->pf = plan_gemm(static_cast<int>(gn->rows()), 3 * c0, c0, Aop, Bm, e);
-    push(op, A + ".to_qkv");
-    Tensor* ao = self_attention(qkv, 1, A + ".sdpa");
-    h = linear(ao, c0, A + ".to_out.0", true, h);
-    h->name = A, named[A] = h;
-  }
+  h = vae_mid_attention(h, V + "decoder.mid_block.attentions.0");
   h = resnet(h, c0, V + "decoder.mid_block.resnets.1", false, 1e-6f);
   for (int i = 0; i < nb; ++i) {
     const std::string B = V + "decoder.up_blocks." + std::to_string(i);
@@ -1031,7 +1076,7 @@ inline void Engine::finalize_plans() {
   gn_bar = arena.make<unsigned int>(16);
   attn_S = arena.make<float>(attn_S_floats + 64);
   temb_cur = arena.make<float>(temb_total + 64);
-  for (auto* ops : {&unet_ops, &dec_ops}) {
+  for (auto* ops : {&unet_ops, &dec_ops, &enc_ops}) {
     for (auto& op : *ops) {
       if (auto* c = dynamic_cast<ConvOp*>(op.get())) {
         uintptr_t tag = reinterpret_cast<uintptr_t>(c->bias);
@@ -1047,12 +1092,13 @@ inline void Engine::finalize_plans() {
         }
       }
     }
+    if (ops == &enc_ops) continue;  // forward only, not part of the guided step
     for (auto it = ops->rbegin(); it != ops->rend(); ++it) (*it)->plan_bwd();
     for (auto& op : *ops) launches_per_step += op->n_fwd() + op->n_bwd();
   }
   split_ws = arena.make<float>(split_ws_floats + 64);
   for (GemmPlan* g : split_plans) g->p.ws = split_ws;
-  launches_per_step += static_cast<long long>(split_plans.size());
+  launches_per_step += static_cast<long long>(n_split_step);
   launches_per_step += 9;  // tail kernels of step()
 }
 
@@ -1076,6 +1122,8 @@ inline Engine::Engine(const mdc_config& c) : cfg(c) {
   MDC_CUDA(cudaFuncSetAttribute(softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   build_unet();
   build_decoder();
+  n_split_step = split_plans.size();
+  build_encoder();
   finalize_plans();
   // step state
   const size_t lat = 4ull * N * lh * lw;
@@ -1391,9 +1439,28 @@ inline void Engine::decode_final(float* dense_out) {
   cudaFree(tmp), cudaFree(scratch);
 }
 
+// Per-frame prologue behind the C ABI: image normalise / resize / pad + VAE encoder forward.
+// imgs: [N, channels, H, W] uint8 (dtype 0) or fp32 in [0, 1] (dtype 1); latents_out: [N, 4, lh, lw] bf16 NCHW.
+inline void Engine::encode(const void* imgs, int dtype, int channels, void* latents_out) {
+  MDC_CHECK(dtype == 0 || dtype == 1, "mdc_encode: dtype %d (0 = uint8, 1 = fp32)", dtype);
+  MDC_CHECK(channels == 1 || channels == 3, "Input image is not 1- or 3-channel: %d", channels);
+  MDC_CHECK(imgs && latents_out, "mdc_encode: null pointer");
+  PreGeom g{N, channels, H, W, ph, pw, PPH, PPW, dtype == 0 ? 1 : 0, enc_in->ld};
+  const long long tot = 1LL * N * PPH * PPW;
+  launch_k(preprocess_image_kernel, dim3(static_cast<int>((tot + 255) / 256)), dim3(256), 0, stream, imgs, g, enc_in->d);
+  run_ops(enc_ops, false);
+  const long long lt = 1LL * N * cfg.vae_latent_ch * lh * lw;
+  launch_k(latent_out_kernel, dim3(static_cast<int>((lt + 255) / 256)), dim3(256), 0, stream, enc_out->d, enc_out->ld, N, lh * lw,
+           cfg.vae_latent_ch, cfg.vae_scaling, static_cast<bf16*>(latents_out));
+  MDC_CUDA(cudaGetLastError());
+  MDC_CUDA(cudaStreamSynchronize(stream));
+}
+
 // NHWC bf16 -> NCHW fp32 copy of a named tensor (which = 0 data, 1 gradient); debug / tests only.
 __global__ void nhwc_to_nchw_f32_kernel(const bf16* __restrict__ src, long long ld, int N, int HW, int C,
                                         float* __restrict__ out) {
+  ptx::pdl_wait();  // every kernel launched through launch_k must order itself after its predecessor
+  ptx::pdl_launch();
   long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
   if (i >= 1LL * N * HW * C) return;
   int p = i % HW, c = (i / HW) % C, n = i / (1LL * HW * C);

@@ -1133,6 +1133,8 @@ __global__ void xattn_fused_bwd_kernel(const bf16* __restrict__ h, long long ldh
 __global__ void xattn_collapse_kernel(const bf16* __restrict__ Wq, long long ldq, const bf16* __restrict__ Wo, long long ldwo,
                                       const float* __restrict__ kc, const float* __restrict__ vc, int d, int heads,
                                       float scale, float* __restrict__ At, float* __restrict__ U) {
+  ptx::pdl_wait();  // every kernel launched through launch_k must order itself after its predecessor
+  ptx::pdl_launch();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over (c, e)
   const int C = 2 * heads;
   if (i >= C * d) return;

@@ -318,10 +318,83 @@ __global__ void dense_out_kernel(const bf16* __restrict__ dec, TailGeom g, const
   out[i] = d * (dmax - dmin) + dmin;
 }
 
+// ---------------------------------------------------------------------------------------------- per-frame prologue
+// MarigoldImageProcessor.preprocess (called at marigold_dc.py:687-694): integer images / 255,
+// * 2 - 1 (both rounded to bf16 like the reference's bf16 pipeline), antialiased bilinear resize to ph x pw
+// (F.interpolate(mode="bilinear", antialias=True): triangle filter whose support grows with the down-scaling factor,
+// weights normalised over the taps inside the image), replicate padding to PPH x PPW.  Output NHWC bf16, 3 channels.
+struct PreGeom {
+  int N, C, H, W, ph, pw, PPH, PPW;
+  int is_u8;
+  long long ld_out;
+};
+__device__ __forceinline__ void aa_span(int i, int in_size, float scale, int& lo, int& size, float& center, float& inv) {
+  const float support = scale >= 1.f ? scale : 1.f;
+  center = scale * (i + 0.5f);
+  inv = scale >= 1.f ? 1.f / scale : 1.f;
+  lo = max(static_cast<int>(center - support + 0.5f), 0);
+  size = min(static_cast<int>(center + support + 0.5f), in_size) - lo;
+}
+__device__ __forceinline__ float aa_tri(float x) {
+  x = fabsf(x);
+  return x < 1.f ? 1.f - x : 0.f;
+}
+__global__ void preprocess_image_kernel(const void* __restrict__ img, PreGeom g, bf16* __restrict__ out) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+  if (i >= 1LL * g.N * g.PPH * g.PPW) return;
+  const int ox = i % g.PPW, oy = (i / g.PPW) % g.PPH, n = i / (1LL * g.PPW * g.PPH);
+  const int ry = min(oy, g.ph - 1), rx = min(ox, g.pw - 1);  // replicate padding (bottom / right)
+  const float sh = static_cast<float>(g.H) / g.ph, sw = static_cast<float>(g.W) / g.pw;
+  int y0, ny, x0, nx;
+  float cy, cx, iy, ix;
+  aa_span(ry, g.H, sh, y0, ny, cy, iy);
+  aa_span(rx, g.W, sw, x0, nx, cx, ix);
+  float wy_tot = 0.f, wx_tot = 0.f;
+  for (int j = 0; j < ny; ++j) wy_tot += aa_tri((j + y0 - cy + 0.5f) * iy);
+  for (int k = 0; k < nx; ++k) wx_tot += aa_tri((k + x0 - cx + 0.5f) * ix);
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int j = 0; j < ny; ++j) {
+    float wy = aa_tri((j + y0 - cy + 0.5f) * iy);
+    if (wy_tot != 0.f) wy /= wy_tot;
+    float row[3] = {0.f, 0.f, 0.f};
+    for (int k = 0; k < nx; ++k) {
+      float wx = aa_tri((k + x0 - cx + 0.5f) * ix);
+      if (wx_tot != 0.f) wx /= wx_tot;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const long long idx = ((1LL * n * g.C + (g.C == 1 ? 0 : c)) * g.H + (y0 + j)) * g.W + (x0 + k);
+        float v = g.is_u8 ? bf16r(static_cast<float>(static_cast<const uint8_t*>(img)[idx]) / 255.f)
+                          : bf16r(static_cast<const float*>(img)[idx]);
+        v = bf16r(v * 2.f - 1.f);
+        row[c] += wx * v;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] += wy * row[c];
+  }
+  bf16* o = out + i * g.ld_out;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) o[c] = __float2bfloat16(acc[c]);
+}
+// img_latent = mode * scaling (marigold_dc.py:696-698): first `C` channels of the NHWC moments -> NCHW bf16
+__global__ void latent_out_kernel(const bf16* __restrict__ mom, long long ld, int N, int HW, int C, float scaling,
+                                  bf16* __restrict__ out) {
+  ptx::pdl_wait();  // launched with programmatic stream serialisation: without this the kernel would not wait
+  ptx::pdl_launch();
+  long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+  if (i >= 1LL * N * C * HW) return;
+  const int p = i % HW, c = (i / HW) % C, n = i / (1LL * HW * C);
+  out[i] = __float2bfloat16(__bfloat162float(mom[(1LL * n * HW + p) * ld + c]) * scaling);
+}
+
 // Ordered compaction of the valid pixels of one sample (mask != 0): one block per sample, run once per call.
 __global__ void compact_points_kernel(const float* __restrict__ guide, const uint8_t* __restrict__ mask, int HW,
                                       const int* __restrict__ pt_off, int* __restrict__ pt_idx,
                                       float* __restrict__ pt_val) {
+  ptx::pdl_wait();  // every kernel launched through launch_k must order itself after its predecessor
+  ptx::pdl_launch();
   __shared__ int wcount[32];
   __shared__ int base;
   const int n = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -354,6 +427,8 @@ __global__ void compact_points_kernel(const float* __restrict__ guide, const uin
 // prepare-time helpers (not on the hot path): sinusoidal timestep embedding and small dense layers
 // out[s][o] = act_out( sum_i W[o][i] * act_in(in[s][i]) + b[o] ), every stage rounded to bf16 like torch's bf16 ops.
 __global__ void timestep_embedding_kernel(const int* __restrict__ timesteps, int steps, int dim, float* __restrict__ out) {
+  ptx::pdl_wait();  // every kernel launched through launch_k must order itself after its predecessor
+  ptx::pdl_launch();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= steps * dim) return;
   int s = i / dim, j = i % dim, half = dim / 2;
@@ -365,6 +440,8 @@ __global__ void timestep_embedding_kernel(const int* __restrict__ timesteps, int
 __global__ void small_linear_kernel(const bf16* __restrict__ W, long long ldw, const float* __restrict__ bias,
                                     const float* __restrict__ in, long long ldin, int S, int In, int Out, int silu_in,
                                     float* __restrict__ out, long long ldout) {
+  ptx::pdl_wait();  // every kernel launched through launch_k must order itself after its predecessor
+  ptx::pdl_launch();
   const long long wid = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= 1LL * S * Out) return;

@@ -46,6 +46,7 @@ def _declare(l):
     l.mdc_run.argtypes = [C.c_void_p, C.c_int]
     l.mdc_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.mdc_decode_final.argtypes = [C.c_void_p, C.c_void_p]
+    l.mdc_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     l.mdc_launch_count.argtypes = [C.c_void_p]
     l.mdc_launch_count.restype = C.c_longlong
     l.mdc_device_bytes.argtypes = [C.c_void_p]
@@ -173,6 +174,22 @@ class StepEngine:
         check(self.lib.mdc_get_state(self._h, ptr(x), sc.ctypes.data_as(C.c_void_p), sh.ctypes.data_as(C.c_void_p),
                                      ls.ctypes.data_as(C.c_void_p)))
         return x, torch.from_numpy(sc), torch.from_numpy(sh), torch.from_numpy(ls)
+
+    def encode(self, imgs: torch.Tensor) -> torch.Tensor:
+        """Per-frame prologue in the library: preprocess + VAE encoder -> img_latents [N,4,EH,EW] bf16
+        (marigold_dc.py:687-698).  imgs: [N, 1|3, H, W] uint8, or floating point in [0, 1]."""
+        if imgs.ndim != 4 or imgs.shape[0] != self.n or tuple(imgs.shape[-2:]) != (self.H, self.W):
+            raise ValueError(f"imgs shape {tuple(imgs.shape)} does not match the engine ({self.n}, C, {self.H}, {self.W})")
+        if imgs.dtype == torch.uint8:
+            dt = 0
+        elif torch.is_floating_point(imgs):
+            imgs, dt = imgs.float(), 1
+        else:
+            raise ValueError(f"Image dtype={imgs.dtype} is not supported.")
+        imgs = imgs.to(self.device).contiguous()
+        out = torch.empty(self.n, 4, self.lh, self.lw, device=self.device, dtype=torch.bfloat16)
+        check(self.lib.mdc_encode(self._h, ptr(imgs), dt, int(imgs.shape[1]), ptr(out)))
+        return out
 
     def decode_final(self) -> torch.Tensor:
         out = torch.empty(self.n, 1, self.H, self.W, device=self.device, dtype=torch.float32)

@@ -178,14 +178,13 @@ class MarigoldDepthCompletionPipeline:
         dev = self.device
         imgs, sparses = imgs.to(dev), sparses.to(dev)
         eng = self._engine(N, H, W, resolution, steps)
-        _, _, vsd_enc = self._state_dicts()
         with torch.no_grad():
             # marigold_dc.py:661, :677-684 -- first draw of the seeded generator, in the pipeline dtype
             gen = torch.Generator(device=dev).manual_seed(seed)
             common = torch.randn((1, 4, EH, EW), device=dev, dtype=self.dtype, generator=gen).repeat(N, 1, 1, 1)
             # marigold_dc.py:687-698
-            resized, _ = prologue.preprocess_image(imgs, resolution, self.dtype)
-            img_latents = prologue.vae_encode_mode(vsd_enc, self.vae_cfg, resized) * self.vae_cfg.scaling_factor
+            prologue.check_image(imgs)
+            img_latents = eng.encode(imgs)   # preprocess + VAE encoder inside libmdc_b200.so (mdc_encode)
             x = common if pred_latents_prev is None else beta * common + (1 - beta) * pred_latents_prev.to(dev)
             # marigold_dc.py:707-756 (linear projection)
             sparses = sparses.float()

@@ -1,13 +1,27 @@
-"""Per-frame prologue (once per call, not per step): image normalise / resize / pad, VAE *encoder* forward and
-sparse-depth normalisation (marigold_dc.py:659-756).
+"""Per-frame prologue (once per call, not per step): input validation and sparse-depth normalisation
+(marigold_dc.py:659-756).
 
-SURVEY.md section 8(f)-1 lists this as the first "next" row; until it moves behind the C ABI it runs as plain
-PyTorch ops (library code, same kernels the reference uses for it) written functionally over the VAE state dict.
+The heavy part -- image normalise / resize / pad and the VAE *encoder* forward -- runs
+inside libmdc_b200.so (`mdc_encode`, StepEngine.encode).  `preprocess_image` and `vae_encode_mode` below are the
+same arithmetic as plain PyTorch ops over the VAE state dict; the product path does not call them, the GPU tests use
+them as the torch reference for `mdc_encode`.
 """
 from __future__ import annotations
 
 import torch
 import torch.nn.functional as F
+
+
+def check_image(image: torch.Tensor) -> None:
+    """The checks of MarigoldImageProcessor.preprocess that raise."""
+    if image.ndim != 4:
+        raise ValueError(f"Input image is not 4-dimensional: shape={tuple(image.shape)}")
+    if not torch.is_floating_point(image) and image.dtype != torch.uint8:
+        raise ValueError(f"Image dtype={image.dtype} is not supported.")
+    if image.shape[1] not in (1, 3):
+        raise ValueError(f"Input image is not 1- or 3-channel: {tuple(image.shape)}.")
+    if torch.is_floating_point(image) and (image.min().item() < 0.0 or image.max().item() > 1.0):
+        raise ValueError("Input image data is partially outside of the [0,1] range.")
 
 
 def preprocess_image(image: torch.Tensor, resolution: int, dtype):

@@ -65,6 +65,13 @@ int mdc_set_weight(mdc_handle* h, const char* key, const void* dev_ptr, const lo
 int mdc_prepare(mdc_handle* h, const void* ctx_bf16, const float* alphas_cumprod_host, const int* timesteps_host,
                 int n_steps);
 
+/* Per-frame prologue (marigold_dc.py:687-698): MarigoldImageProcessor.preprocess (integer / 255,
+ * * 2 - 1, antialiased bilinear resize to the processing resolution, replicate padding to a multiple of 8) followed by
+ * AutoencoderKL.encode(...).latent_dist.mode() * scaling_factor.  imgs: device [N, channels, H, W], uint8 (dtype 0) or
+ * fp32 in [0, 1] (dtype 1), channels 1 or 3 (a single channel is repeated).  latents_out: device [N,4,EH,EW] bf16,
+ * ready to be passed to mdc_begin as img_latents. */
+int mdc_encode(mdc_handle* h, const void* imgs, int dtype, int channels, void* latents_out_bf16);
+
 /* Per-call state (marigold_dc.py:696-789): image latents and initial depth latent [N,4,EH,EW] bf16 NCHW, normalised
  * sparse depth `guide` [N,1,H,W] fp32 with `mask` [N,1,H,W] uint8, per-sample (min,max) of the masked guide and of the
  * metric depth range (host, 2 floats per sample), learning rates of the latent and of scale/shift.

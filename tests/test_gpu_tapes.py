@@ -113,3 +113,44 @@ def test_batch2(cuda):
     assert rel_l2(eng.dbg_forward(0, 0, xin), y) < 4e-2
     assert rel_l2(eng.dbg_backward(0, dout), x.grad) < 6e-2
     eng.close()
+
+
+@pytest.mark.parametrize("H,W,res,kind", [(96, 128, 128, "u8"), (60, 80, 128, "u8"), (200, 264, 128, "u8"),
+                                          (150, 90, 120, "f32_gray")])
+def test_encoder_prologue(cuda, H, W, res, kind):
+    """mdc_encode (preprocess + VAE encoder inside the library) against the fp32 oracle
+    (MarigoldImageProcessor.preprocess + AutoencoderKL.encode(...).mode() * scaling), with torch's bf16 path as the
+    yardstick; the resized / padded image itself is checked against torch's antialiased bilinear resize."""
+    from helpers import build_engine, build_models, rel_l2
+    from depth_completion_b200 import prologue
+    from oracle import image_processor
+
+    unet, vae, ctx, ucfg, vcfg = build_models(cuda, tiny=True)
+    eng = build_engine(unet, vae, ctx, ucfg, vcfg, 2, H, W, res, 50, cuda)
+    g = torch.Generator(device=cuda).manual_seed(H + W)
+    if kind == "u8":
+        imgs = torch.randint(0, 256, (2, 3, H, W), device=cuda, generator=g, dtype=torch.uint8)
+    else:
+        imgs = torch.rand(2, 1, H, W, device=cuda, generator=g)
+    got = eng.encode(imgs)
+    # fp32 oracle
+    x32, _, _ = image_processor.preprocess(imgs, res, cuda, torch.float32)
+    ref = vae.encode_mode(x32) * vcfg.scaling_factor
+    # torch bf16 path (what the reference runs in bf16 mode)
+    x16, _ = prologue.preprocess_image(imgs, res, torch.bfloat16)
+    sd16 = {k: v.bfloat16() for k, v in vae.state_dict().items()}
+    pu, pv = __import__("helpers").product_cfgs(ucfg, vcfg)
+    y16 = prologue.vae_encode_mode(sd16, pv, x16) * vcfg.scaling_factor
+    assert got.shape == ref.shape
+    # the preprocessed image (values in [-1, 1] on the bf16 grid; /255, *2-1 and the resize each round to bf16 as in
+    # the reference's bf16 mode): within 2^-7 of the fp32 oracle's and of torch's bf16 result, and on average no further from the oracle than torch's bf16 result is
+    # (torch rounds the filter weights and the horizontal pass to bf16; the kernel keeps them in fp32)
+    mine = eng.dbg_read("vae.enc_in")
+    assert mine.shape == x16.shape
+    assert (mine - x16.float()).abs().max().item() <= 2 ** -7
+    err_mine, err_t16 = (mine - x32).abs(), (x16.float() - x32).abs()
+    assert err_mine.max().item() <= 2 ** -7
+    assert err_mine.mean().item() <= 1.05 * err_t16.mean().item() + 1e-6
+    e_ours, e_16 = rel_l2(got, ref), rel_l2(y16, ref)
+    assert e_ours < 6e-2, f"encoder rel_l2 {e_ours:.3e}"
+    assert e_ours <= 1.25 * e_16 + 2e-3, f"encoder: engine {e_ours:.3e} vs torch-bf16 {e_16:.3e}"
