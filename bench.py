@@ -296,8 +296,18 @@ def run_ours(args):
     burst, sustained, hbm, how = peaks()
     prof = eng.profile_gemm_step()
     sf = step_flops(pipe.unet_cfg, pipe.vae_cfg, H, W, res)
-    roof = {"bound": "tensor", "kernel": "umma_gemm_kernel", "achieved": prof["tflops"], "peak": sustained,
-            "unit": "TFLOP/s", "frac": prof["tflops"] / sustained, "traffic": None, "peak_source": how + " sustained",
+    # DRAM bytes per launch of that kernel from the committed ncu pass over one guided step of this workload
+    # (profiles/summarize_launches.py); only valid for the full-size default workload
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if not args.tiny and os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    roof = {"bound": "tensor", "kernel": "umma_gemm_pair_kernel + umma_gemm_kernel (gemm.cuh, cta_group::2 / ::1)",
+            "achieved": prof["tflops"], "peak": sustained,
+            "unit": "TFLOP/s", "frac": prof["tflops"] / sustained, "traffic": traffic,
+            "traffic_note": "dram__bytes_read+write per launch, mean over the step's launches (profiles/r01_gemm_traffic.json)",
+            "peak_source": how + " sustained",
             "launches_per_step": prof["launches"], "kernel_ms_per_step": prof["ms"], "kernel_flops_per_step": prof["flops"],
             "step_algorithmic_tflops": sf["step"] / 1e12,
             "step_frac_of_peak": sf["step"] / 1e12 / (total_ms * 1e-3 / args.steps) / sustained}
