@@ -9,8 +9,8 @@
 // Everything is single-buffered inside a CTA; two CTAs share an SM (<= 96 KB smem, 256 TMEM columns each) so one
 // CTA's tensor work overlaps the other's exponentials.
 //
-//   flash_fwd_kernel : CTA = 128 queries.  S = Q K^T (N = 64 keys), online softmax in registers, O_tile = P V in TMEM,
-//                      running output in registers; writes O (bf16) and LSE2 = m2 + log2(l) (base-2, scale folded).
+//   flash_fwd_kernel : CTA = 128 queries.  S = Q K^T (N = 64 keys), online softmax in registers, O += P V in TMEM
+//                      (rescaled lazily); writes O (bf16) and LSE2 = m2 + log2(l) (base-2, scale folded).
 //   flash_dkv_kernel : CTA = 128 keys.  S^T = K Q^T, dP^T = V dO^T, P^T = exp2(S^T c - LSE2[q]),
 //                      dS^T = P^T (dP^T - delta[q]) scale;  dV += P^T dO,  dK += dS^T Q  (TMEM accumulators).
 //   flash_dq_kernel  : CTA = 128 queries.  S = Q K^T, dP = dO V^T, dS likewise;  dQ += dS K.
@@ -74,6 +74,11 @@ __device__ __forceinline__ float fa_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+__device__ __forceinline__ float fa_max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
 }
 __device__ __forceinline__ void fa_named_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -144,8 +149,7 @@ __device__ __forceinline__ void fa_warp_arrive(uint64_t* bar, int lane) {
 
 // ---------------------------------------------------------------------------------------------------- forward
 // Software-pipelined: S is double-buffered in TMEM (S(i+1) = Q K(i+1)^T is issued before P(i) V(i)), P is
-// double-buffered in shared memory, and the read-back of O_tile(i-1) is deferred until after P(i) has been handed to the
-// tensor core, so the softmax threads never wait for an MMA they have just requested.
+// double-buffered in shared memory, O accumulates in TMEM (lazy rescaling, see the softmax loop).
 __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_constant__ FlashParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t TCOLS = 256;  // S0: [0,64)  S1: [64,128)  O tile: [128,192)
@@ -195,10 +199,9 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
         __syncwarp();
       }
       ptx::mbar_wait(pf(b), (i >> 1) & 1);
-      ptx::mbar_wait(&c.b->o_empty, (i & 1) ^ 1);
       ptx::tc_fence_after();
       if (leader) {
-        fa_mma_bmn(c.tmem + 128, b ? d_p1 : d_p0, d_st + s * 1024 + 512, idesc_o, false);  // O_tile = P(i) V(i)
+        fa_mma_bmn(c.tmem + 128, b ? d_p1 : d_p0, d_st + s * 1024 + 512, idesc_o, i > 0);  // O += P(i) V(i)
         ptx::umma_commit(&c.b->o_full);
         ptx::umma_commit(pe(b));
         ptx::umma_commit(&c.b->s_empty[s]);
@@ -209,10 +212,11 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
     const int q = c.warp & 3, row = q * 32 + c.lane;
     const uint32_t t_row = c.tmem + (static_cast<uint32_t>(q * 32) << 16);
     const float c2 = p.scale * FA_LOG2E;
+    // m is the reference maximum the stored exponentials are relative to.  It only moves when a row's maximum grows
+    // by more than 2^8 (the probabilities then stay below 256, exact enough in bf16 / fp32): O accumulates in TMEM
+    // across key tiles and is touched by the softmax threads only on those rare rescales and once at the end, so the
+    // per-tile TMEM read traffic (64 B/clk per SM, the bound of this kernel) is the 32 KB score tile alone.
     float m = -INFINITY, l = 0.f;
-    float o[64];
-#pragma unroll
-    for (int j = 0; j < 64; ++j) o[j] = 0.f;
     for (int i = 0; i < n_iter; ++i) {
       const int b = i & 1;
       ptx::mbar_wait(sacc_full(b), (i >> 1) & 1);
@@ -224,51 +228,53 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
       ptx::tc_fence_before();
       fa_warp_arrive(sacc_empty(b), c.lane);
       const int valid = p.T - i * 64;  // keys of this tile that exist
-      float mx = -INFINITY;
-      if (valid >= 64) {
+      if (valid < 64) {
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          float s = __uint_as_float(raw[j]) * c2;
-          raw[j] = __float_as_uint(s);
-          mx = fmaxf(mx, s);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          float s = (j < valid) ? __uint_as_float(raw[j]) * c2 : -INFINITY;
-          raw[j] = __float_as_uint(s);
-          mx = fmaxf(mx, s);
-        }
+        for (int j = 0; j < 64; ++j)
+          if (j >= valid) raw[j] = 0xff800000u;  // -inf
       }
-      const float m_new = fmaxf(m, mx);
-      const float alpha = fa_exp2(m - m_new);
-      float sum = 0.f;
+      // row maximum on the raw scores (the scale is positive), three-input max: 32 instructions for 64 columns
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 64; j += 2) mx = fa_max3(mx, __uint_as_float(raw[j]), __uint_as_float(raw[j + 1]));
+      mx *= c2;
+      const bool grow = mx > m + 8.f;  // always true for the first tile (m = -inf)
+      const float m_new = grow ? mx : m;
+      const float alpha = grow ? fa_exp2(m - m_new) : 1.f;
+      if (i > 0 && __any_sync(0xffffffffu, grow)) {  // rescale the TMEM accumulator rows of this warp
+        uint32_t acc[64];
+        ptx::mbar_wait(&c.b->o_full, (i - 1) & 1);  // P(i-1) V(i-1) and everything before it has completed
+        ptx::tc_fence_after();
+        ptx::tmem_ld32(t_row + 128, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
+        ptx::tmem_ld32(t_row + 160, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 64; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) * alpha);
+        ptx::tmem_st32(t_row + 128, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
+        ptx::tmem_st32(t_row + 160, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+      }
+      // p = exp2(s * c2 - m_new): one packed FMA per two columns, MUFU.EX2, packed row-sum
+      const float2 cc = make_float2(c2, c2), neg = make_float2(-m_new, -m_new);
+      float2 sum2 = make_float2(0.f, 0.f);
       ptx::mbar_wait(pe(b), ((i >> 1) & 1) ^ 1);
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
         float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          v[j] = fa_exp2(__uint_as_float(raw[ch * 8 + j]) - m_new);
-          sum += v[j];
+        for (int j = 0; j < 8; j += 2) {
+          const float2 a = __ffma2_rn(make_float2(__uint_as_float(raw[ch * 8 + j]), __uint_as_float(raw[ch * 8 + j + 1])), cc, neg);
+          const float2 e = make_float2(fa_exp2(a.x), fa_exp2(a.y));
+          v[j] = e.x, v[j + 1] = e.y;
+          sum2 = __fadd2_rn(sum2, e);
         }
         fa_store_row_chunk(pbuf(b), row, ch, v);
       }
       ptx::fence_proxy_async_smem();
-      fa_warp_arrive(pf(b), c.lane);
-      l = l * alpha + sum;
+      fa_warp_arrive(pf(b), c.lane);  // also orders the rescale above before P(i) V(i) is issued
+      l = l * alpha + (sum2.x + sum2.y);
       m = m_new;
-      if (i > 0) {  // O_tile(i-1) has long completed: o = (o + O_tile(i-1)) * alpha_i
-        ptx::mbar_wait(&c.b->o_full, (i - 1) & 1);
-        ptx::tc_fence_after();
-        ptx::tmem_ld32(t_row + 128, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
-        ptx::tmem_ld32(t_row + 160, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
-        ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        fa_warp_arrive(&c.b->o_empty, c.lane);
-#pragma unroll
-        for (int j = 0; j < 64; ++j) o[j] = (o[j] + __uint_as_float(raw[j])) * alpha;
-      }
     }
     {
       uint32_t raw[64];
@@ -277,20 +283,18 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
       ptx::tmem_ld32(t_row + 128, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
       ptx::tmem_ld32(t_row + 160, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
       ptx::tmem_ld_wait();
+      if (q0 + row < p.T) {
+        const float inv = 1.f / l;
+        bf16* dst = p.out1 + n * p.img_stride_out + static_cast<long long>(q0 + row) * p.ld_out + h * 64;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) o[j] += __uint_as_float(raw[j]);
-    }
-    if (q0 + row < p.T) {
-      const float inv = 1.f / l;
-      bf16* dst = p.out1 + n * p.img_stride_out + static_cast<long long>(q0 + row) * p.ld_out + h * 64;
+        for (int ch = 0; ch < 8; ++ch) {
+          float v[8];
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = o[ch * 8 + j] * inv;
-        *reinterpret_cast<BF8*>(dst + ch * 8) = f_to_bf8(v);
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[ch * 8 + j]) * inv;
+          *reinterpret_cast<BF8*>(dst + ch * 8) = f_to_bf8(v);
+        }
+        p.lse2[(static_cast<long long>(n) * p.heads + h) * p.T + q0 + row] = m + log2f(l);
       }
-      p.lse2[(static_cast<long long>(n) * p.heads + h) * p.T + q0 + row] = m + log2f(l);
     }
   }
   fa_teardown(c, TCOLS);
@@ -394,6 +398,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dkv_kernel(const __grid_c
       ptx::tc_fence_before();
       fa_warp_arrive(&c.b->acc_empty, c.lane);
       ptx::mbar_wait(&c.b->p_empty, (i & 1) ^ 1);
+      const float2 cc2 = make_float2(c2, c2), sc2 = make_float2(p.scale, p.scale);
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
         float pv[8], dv[8];
@@ -404,10 +409,15 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dkv_kernel(const __grid_c
         const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
         const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float pr = fa_exp2(fmaf(__uint_as_float(rs[ch * 8 + j]), c2, -ls[j]));
-          pv[j] = pr;
-          dv[j] = pr * (__uint_as_float(rd[ch * 8 + j]) - dl[j]) * p.scale;
+        for (int j = 0; j < 8; j += 2) {  // packed fp32x2: p = exp2(s c - lse), ds = p (dp - delta) scale
+          const float2 a = __ffma2_rn(make_float2(__uint_as_float(rs[ch * 8 + j]), __uint_as_float(rs[ch * 8 + j + 1])), cc2,
+                                      make_float2(-ls[j], -ls[j + 1]));
+          const float2 pr = make_float2(fa_exp2(a.x), fa_exp2(a.y));
+          const float2 t = __ffma2_rn(make_float2(__uint_as_float(rd[ch * 8 + j]), __uint_as_float(rd[ch * 8 + j + 1])), sc2,
+                                      make_float2(-dl[j] * p.scale, -dl[j + 1] * p.scale));
+          const float2 d = __fmul2_rn(pr, t);
+          pv[j] = pr.x, pv[j + 1] = pr.y;
+          dv[j] = d.x, dv[j + 1] = d.y;
         }
         fa_store_row_chunk(c.p1, row, ch, pv);
         fa_store_row_chunk(c.p2, row, ch, dv);
@@ -499,6 +509,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dq_kernel(const __grid_co
     const long long sidx = (static_cast<long long>(n) * p.heads + h) * p.T + q0 + row;
     const float lse = ok ? p.lse2[sidx] : 0.f, del = ok ? p.delta[sidx] : 0.f;
     const float nlse = ok ? -lse : -INFINITY;  // rows past T produce probability 0
+    const float ndel_s = -del * p.scale;
     for (int i = 0; i < n_iter; ++i) {
       ptx::mbar_wait(&c.b->acc_full, i & 1);
       ptx::tc_fence_after();
@@ -517,9 +528,14 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dq_kernel(const __grid_co
         float dv[8];
         if (valid >= 64) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float pr = fa_exp2(fmaf(__uint_as_float(rs[ch * 8 + j]), c2, nlse));
-            dv[j] = pr * (__uint_as_float(rd[ch * 8 + j]) - del) * p.scale;
+          for (int j = 0; j < 8; j += 2) {  // packed fp32x2
+            const float2 a = __ffma2_rn(make_float2(__uint_as_float(rs[ch * 8 + j]), __uint_as_float(rs[ch * 8 + j + 1])),
+                                        make_float2(c2, c2), make_float2(nlse, nlse));
+            const float2 pr = make_float2(fa_exp2(a.x), fa_exp2(a.y));
+            const float2 t = __ffma2_rn(make_float2(__uint_as_float(rd[ch * 8 + j]), __uint_as_float(rd[ch * 8 + j + 1])),
+                                        make_float2(p.scale, p.scale), make_float2(ndel_s, ndel_s));
+            const float2 d = __fmul2_rn(pr, t);
+            dv[j] = d.x, dv[j + 1] = d.y;
           }
         } else {
 #pragma unroll
