@@ -145,6 +145,12 @@ def cpu_reference_steps(n_steps: int, warmup: int, sample_res: int, tiny: bool):
     from depth_completion_b200.config import unet_config_from, vae_config_from
 
     w = workload(tiny)
+    # all host threads: torchrun exports OMP_NUM_THREADS=1 for nproc > 1, which would time a single core
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    torch.set_num_threads(max(1, ncpu))
     unet, vae, ctx = make_models("cpu", tiny, dtype=torch.float32)
     pipe = OraclePipeline(unet, vae, ctx)
     fr = make_frame(H=w["H"], W=w["W"], n_points=w["n_points"], max_depth=w["max_depth"])
