@@ -159,3 +159,33 @@ def test_other_configs_match_oracle(models, cuda, H, W, res, kind, max_depth):
     assert diff < 4e-2, diff
     m_ours, m_ref = mae(dense, fr["gt"], fr["holdout"]).item(), mae(d16, fr["gt"], fr["holdout"]).item()
     assert abs(m_ours - m_ref) <= 0.08 * m_ref, (m_ours, m_ref)
+
+
+def test_engine_against_golden_fixture(models, cuda):
+    """Teacher-forced comparison with the committed fp32 CPU-oracle run (tests/golden/tiny_96x128.npz): the library's
+    encoder prologue, then one guided step from the stored initial latent, against the stored UNet output, x0, loss,
+    latent gradient and Adam update.  Tolerances are bf16-level (the stored run is fp32)."""
+    import os
+
+    import numpy as np
+    from helpers import build_engine, rel_l2
+
+    unet, vae, ctx, ucfg, vcfg = models
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_96x128.npz"))
+    t = lambda k: torch.from_numpy(gold[k]).to(cuda)
+    eng = build_engine(unet, vae, ctx, ucfg, vcfg, 1, 96, 128, 128, 50, cuda)
+    lat = eng.encode(t("img"))
+    assert rel_l2(lat, t("img_latents")) < 4e-2
+    guide, mask = t("guide"), t("mask")
+    gm = guide[mask]
+    eng.begin(t("img_latents"), t("x_init"), guide, mask, [[gm.min().item(), gm.max().item()]],
+              [[float(gold["depth_min"].reshape(-1)[0]), float(gold["depth_max"].reshape(-1)[0])]])
+    eng.run(1)
+    x, sc, sh, ls = eng.get_state()
+    assert rel_l2(eng.dbg_read("unet.out"), t("step_v")[0]) < 4e-2
+    assert abs(ls[0].item() - float(gold["step_losses"][0, 0])) < 3e-2 * float(gold["step_losses"][0, 0])
+    assert abs(sc[0].item() - float(gold["step_scales"][0].reshape(-1)[0])) < 1e-6   # Adam step 1 = -lr * sign(grad)
+    g, og = eng.dbg_buffer("grad").flatten(), t("step_grad")[0].flatten()
+    assert torch.nn.functional.cosine_similarity(g, og, dim=0).item() > 0.85
+    agree = ((eng.dbg_x_adam().float() - t("step_x_adam")[0]).abs() < 1e-2).float().mean().item()
+    assert agree > 0.8, agree
