@@ -53,7 +53,8 @@ def test_gemm_epilogue(cuda, M, N, K):
 
 @pytest.mark.parametrize("NB,H,W,C,Cout", [(1, 8, 16, 64, 64), (2, 9, 12, 128, 320), (1, 36, 48, 320, 320),
                                            (1, 15, 20, 192, 64), (1, 72, 96, 8, 320), (1, 24, 40, 128, 3),
-                                           (1, 72, 96, 4, 128), (1, 11, 19, 64, 128)])
+                                           (1, 72, 96, 4, 128), (1, 11, 19, 64, 128),
+                                           (1, 192, 256, 64, 128), (2, 160, 224, 128, 64)])  # single n-tile, many tiles: B-resident mode
 @pytest.mark.parametrize("dgrad", [False, True])
 def test_conv3x3(cuda, NB, H, W, C, Cout, dgrad):
     from depth_completion_b200 import debug
