@@ -375,6 +375,22 @@ __device__ __forceinline__ void umma_gemm_body(const GemmParams& p) {
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
+      // residual rows are fetched one 32-column chunk ahead (the first one while the tile's MMAs are still running)
+      const int n_chunks = (p.BN + 31) >> 5;
+      auto load_res = [&](uint4(&dst)[4], const int ci) {
+        const int col0 = n0 + (ci << 5);
+        const int ncol = min(32, min(p.BN - (ci << 5), p.N - col0));
+        if (e_res && valid && e_vec && ncol == 32) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(e_res + off_r + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = r4[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(0, 0, 0, 0);
+        }
+      };
+      uint4 resA[4], resB[4];
+      load_res(resA, 0);
       ptx::mbar_wait(&tfull_bar[as], aphase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as) * 256u;
@@ -382,24 +398,15 @@ __device__ __forceinline__ void umma_gemm_body(const GemmParams& p) {
       // converted and stored.  A chunk may extend past BN (BN is a multiple of 16); those columns are masked.
       uint32_t bufA[32], bufB[32];
       ptx::tmem_ld32(t_row, bufA);
-      const int n_chunks = (p.BN + 31) >> 5;
       const bool use_ts = p.tma_store && !e_f32;
       const bool tile_ok = m_tile < p.m_tiles || !p.conv;
-      auto process = [&](const uint32_t(&raw)[32], uint32_t(&nxt)[32], const int ci) {
+      auto process = [&](const uint32_t(&raw)[32], uint32_t(&nxt)[32], const uint4(&rres)[4], uint4(&rnxt)[4], const int ci) {
         const int c0 = ci << 5;
         const int col0 = n0 + c0;
         const int ncol = min(32, min(p.BN - c0, p.N - col0));  // valid columns of this chunk (may be <= 0)
         const bool full = ((ncol == 32) || use_ts) && e_vec;
         uint8_t* panel = spanel + (ring & ring_mask) * GEMM_PANEL;
-        uint4 rres[4];
-        if (e_res && valid && full && ncol == 32) {
-          const uint4* r4 = reinterpret_cast<const uint4*>(e_res + off_r + col0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rres[j] = r4[j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rres[j] = make_uint4(0, 0, 0, 0);
-        }
+        if (ci + 1 < n_chunks) load_res(rnxt, ci + 1);
         ptx::tmem_ld_wait();
         if (ci + 1 < n_chunks) ptx::tmem_ld32(t_row + c0 + 32, nxt);
         if (use_ts) {
@@ -519,8 +526,8 @@ __device__ __forceinline__ void umma_gemm_body(const GemmParams& p) {
       };
 #pragma unroll 1
       for (int ci = 0; ci < n_chunks; ci += 2) {
-        process(bufA, bufB, ci);
-        if (ci + 1 < n_chunks) process(bufB, bufA, ci + 1);
+        process(bufA, bufB, resA, resB, ci);
+        if (ci + 1 < n_chunks) process(bufB, bufA, resB, resA, ci + 1);
       }
       ptx::tc_fence_before();
       __syncwarp();
