@@ -75,6 +75,13 @@ int mdc_begin(mdc_handle* h, const void* img_latents_bf16, const void* x_bf16, c
     h->e->begin(img_latents_bf16, x_bf16, guide, mask, guide_minmax_host, depth_minmax_host, lr_latent, lr_scaling);
   });
 }
+int mdc_begin_frame(mdc_handle* h, const void* imgs, int img_dtype, int channels, const float* sparse, const void* x_bf16,
+                    float max_depth, float min_depth, int norm_const, float lr_latent, float lr_scaling) {
+  return mdc::guarded([&] {
+    MDC_CHECK(h, "null handle");
+    h->e->begin_frame(imgs, img_dtype, channels, sparse, x_bf16, max_depth, min_depth, norm_const, lr_latent, lr_scaling);
+  });
+}
 int mdc_run(mdc_handle* h, int n_steps) {
   return mdc::guarded([&] {
     MDC_CHECK(h, "null handle");
@@ -176,6 +183,17 @@ int mdc_dbg_read_buffer(mdc_handle* h, const char* which, float* out_dev) {
       MDC_CUDA(cudaMemcpy(out_dev, e->dx_direct, lat * 4, cudaMemcpyDeviceToDevice));
     else
       MDC_CHECK(false, "unknown buffer '%s'", which);
+  });
+}
+int mdc_dbg_frame_state(mdc_handle* h, float* guide_dev, unsigned char* mask_dev, float* stats_host) {
+  return mdc::guarded([&] {
+    mdc::Engine* e = h->e;
+    MDC_CHECK(e->fr_guide != nullptr, "mdc_begin_frame has not been called");
+    const size_t n = 1ull * e->N * e->H * e->W;
+    MDC_CUDA(cudaStreamSynchronize(e->stream));
+    if (guide_dev) MDC_CUDA(cudaMemcpy(guide_dev, e->fr_guide, n * 4, cudaMemcpyDeviceToDevice));
+    if (mask_dev) MDC_CUDA(cudaMemcpy(mask_dev, e->fr_mask, n, cudaMemcpyDeviceToDevice));
+    if (stats_host) MDC_CUDA(cudaMemcpy(stats_host, e->fr_stats, 5ull * e->N * 4, cudaMemcpyDeviceToHost));
   });
 }
 int mdc_dbg_loss(mdc_handle* h, const float* dec_nchw, float* ddec_nchw, float* loss_host, float* sgrad_host,

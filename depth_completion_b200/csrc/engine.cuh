@@ -404,6 +404,12 @@ struct Engine {
   void build_encoder();
   Tensor* vae_mid_attention(Tensor* h, const std::string& A);
   void encode(const void* imgs, int dtype, int channels, void* latents_out);
+  void begin_frame(const void* imgs, int dtype, int channels, const float* sparse, const void* x0, float max_depth,
+                   float min_depth, int norm_const, float lrx, float lrs);
+  bf16* enc_lat = nullptr;       // img latents of the current frame (begin_frame)
+  float* fr_guide = nullptr;     // normalised sparse depth of the current frame
+  uint8_t* fr_mask = nullptr;
+  float* fr_stats = nullptr;     // per sample: lo, hi, guide min, guide max, valid count
   void read_tensor(const std::string& name, int which, float* out_nchw);
   long long launches_per_step = 0;
   // split-K: plans with few output tiles and a long K loop share one fp32 partial-sum workspace
@@ -1454,6 +1460,33 @@ inline void Engine::encode(const void* imgs, int dtype, int channels, void* late
            cfg.vae_latent_ch, cfg.vae_scaling, static_cast<bf16*>(latents_out));
   MDC_CUDA(cudaGetLastError());
   MDC_CUDA(cudaStreamSynchronize(stream));
+}
+
+// One call per frame: image prologue + sparse-depth normalisation + per-call state.
+// Raises "No valid values found in mask ..." for a sample without a positive sparse value, like utils.py:132-136.
+inline void Engine::begin_frame(const void* imgs, int dtype, int channels, const float* sparse, const void* x0,
+                                float max_depth, float min_depth, int norm_const, float lrx, float lrs) {
+  MDC_CHECK(sparse && x0, "mdc_begin_frame: null pointer");
+  if (!enc_lat) {
+    enc_lat = arena.make<bf16>(4ull * N * lh * lw + 64);
+    fr_guide = arena.make<float>(1ull * N * H * W + 64);
+    fr_mask = arena.make<uint8_t>(1ull * N * H * W + 64);
+    fr_stats = arena.make<float>(5ull * MAXN);
+  }
+  encode(imgs, dtype, channels, enc_lat);
+  launch_k(sparse_norm_kernel, dim3(N), dim3(1024), 0, stream, sparse, H * W, min_depth, max_depth, norm_const, fr_guide, fr_mask, fr_stats);
+  MDC_CUDA(cudaGetLastError());
+  std::vector<float> st(5ull * N);
+  MDC_CUDA(cudaMemcpyAsync(st.data(), fr_stats, st.size() * 4, cudaMemcpyDeviceToHost, stream));
+  MDC_CUDA(cudaStreamSynchronize(stream));
+  std::vector<float> gmm(2ull * N), dmm(2ull * N);
+  for (int n = 0; n < N; ++n) {
+    MDC_CHECK(st[5 * n + 4] > 0.f, "No valid values found in mask for some positions. Ensure that mask has at least one True value "
+                                   "along the specified dimensions. (sample %d)", n);
+    dmm[2 * n] = st[5 * n], dmm[2 * n + 1] = st[5 * n + 1];
+    gmm[2 * n] = st[5 * n + 2], gmm[2 * n + 1] = st[5 * n + 3];
+  }
+  begin(enc_lat, x0, fr_guide, fr_mask, gmm.data(), dmm.data(), lrx, lrs);
 }
 
 // NHWC bf16 -> NCHW fp32 copy of a named tensor (which = 0 data, 1 gradient); debug / tests only.

@@ -378,6 +378,63 @@ __global__ void preprocess_image_kernel(const void* __restrict__ img, PreGeom g,
 #pragma unroll
   for (int c = 0; c < 3; ++c) o[c] = __float2bfloat16(acc[c]);
 }
+// Sparse-depth normalisation (marigold_dc.py:707-756, linear projection): mask = sparse > 0; "minmax": (lo, hi) =
+// masked min / max of the sample, values clamped to it, then lo = max(lo, min_depth), hi = min(hi, max_depth);
+// "const": (lo, hi) = (min_depth, max_depth); guide = (clamp(sparse) - lo) / (hi - lo).  Also the masked min / max of
+// the guide that _affine_to_metric recomputes every step (:326).  One block per sample, fp32 like the reference.
+// out_stats[n] = {lo, hi, gmin, gmax, n_valid}.
+__global__ void sparse_norm_kernel(const float* __restrict__ sparse, int HW, float min_depth, float max_depth,
+                                   int norm_const, float* __restrict__ guide, uint8_t* __restrict__ mask,
+                                   float* __restrict__ out_stats) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  __shared__ float s_lo[32], s_hi[32];
+  __shared__ int s_cnt[32];
+  const int n = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* sp = sparse + 1LL * n * HW;
+  auto block_minmax = [&](float lo, float hi, int cnt, float& olo, float& ohi, int& ocnt) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    __syncthreads();
+    if (lane == 0) s_lo[w] = lo, s_hi[w] = hi, s_cnt[w] = cnt;
+    __syncthreads();
+    olo = INFINITY, ohi = -INFINITY, ocnt = 0;
+    for (int i = 0; i < nw; ++i) olo = fminf(olo, s_lo[i]), ohi = fmaxf(ohi, s_hi[i]), ocnt += s_cnt[i];
+  };
+  float lo = INFINITY, hi = -INFINITY;
+  int cnt = 0;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float v = sp[i];
+    if (v > 0.f) lo = fminf(lo, v), hi = fmaxf(hi, v), ++cnt;
+  }
+  float mlo, mhi;
+  int total;
+  block_minmax(lo, hi, cnt, mlo, mhi, total);
+  float clo = norm_const ? min_depth : mlo, chi = norm_const ? max_depth : mhi;  // clamp range of the raw values
+  float nlo = clo, nhi = chi;                                                      // normalisation range
+  if (!norm_const) nlo = fmaxf(clo, min_depth), nhi = fminf(chi, max_depth);
+  float glo = INFINITY, ghi = -INFINITY;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float v = sp[i];
+    const float g = (fminf(fmaxf(v, clo), chi) - nlo) / (nhi - nlo);
+    guide[1LL * n * HW + i] = g;
+    const bool m = v > 0.f;
+    mask[1LL * n * HW + i] = m ? 1 : 0;
+    if (m) glo = fminf(glo, g), ghi = fmaxf(ghi, g);
+  }
+  float ogl, ogh;
+  int dummy;
+  block_minmax(glo, ghi, 0, ogl, ogh, dummy);
+  if (threadIdx.x == 0) {
+    float* o = out_stats + 5 * n;
+    o[0] = nlo, o[1] = nhi, o[2] = ogl, o[3] = ogh, o[4] = static_cast<float>(total);
+  }
+}
+
 // img_latent = mode * scaling (marigold_dc.py:696-698): first `C` channels of the NHWC moments -> NCHW bf16
 __global__ void latent_out_kernel(const bf16* __restrict__ mom, long long ld, int N, int HW, int C, float scaling,
                                   bf16* __restrict__ out) {

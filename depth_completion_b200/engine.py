@@ -47,11 +47,14 @@ def _declare(l):
     l.mdc_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.mdc_decode_final.argtypes = [C.c_void_p, C.c_void_p]
     l.mdc_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    l.mdc_begin_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                  C.c_int, C.c_float, C.c_float]
     l.mdc_launch_count.argtypes = [C.c_void_p]
     l.mdc_launch_count.restype = C.c_longlong
     l.mdc_device_bytes.argtypes = [C.c_void_p]
     l.mdc_device_bytes.restype = C.c_longlong
     l.mdc_dbg_forward.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    l.mdc_dbg_frame_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.mdc_dbg_backward.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     l.mdc_dbg_read_tensor.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p]
     l.mdc_dbg_tensor_shape.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
@@ -178,6 +181,12 @@ class StepEngine:
     def encode(self, imgs: torch.Tensor) -> torch.Tensor:
         """Per-frame prologue in the library: preprocess + VAE encoder -> img_latents [N,4,EH,EW] bf16
         (marigold_dc.py:687-698).  imgs: [N, 1|3, H, W] uint8, or floating point in [0, 1]."""
+        imgs, dt = self._image_arg(imgs)
+        out = torch.empty(self.n, 4, self.lh, self.lw, device=self.device, dtype=torch.bfloat16)
+        check(self.lib.mdc_encode(self._h, ptr(imgs), dt, int(imgs.shape[1]), ptr(out)))
+        return out
+
+    def _image_arg(self, imgs: torch.Tensor):
         if imgs.ndim != 4 or imgs.shape[0] != self.n or tuple(imgs.shape[-2:]) != (self.H, self.W):
             raise ValueError(f"imgs shape {tuple(imgs.shape)} does not match the engine ({self.n}, C, {self.H}, {self.W})")
         if imgs.dtype == torch.uint8:
@@ -186,10 +195,22 @@ class StepEngine:
             imgs, dt = imgs.float(), 1
         else:
             raise ValueError(f"Image dtype={imgs.dtype} is not supported.")
-        imgs = imgs.to(self.device).contiguous()
-        out = torch.empty(self.n, 4, self.lh, self.lw, device=self.device, dtype=torch.bfloat16)
-        check(self.lib.mdc_encode(self._h, ptr(imgs), dt, int(imgs.shape[1]), ptr(out)))
-        return out
+        return imgs.to(self.device).contiguous(), dt
+
+    def begin_frame(self, imgs, sparses, x, max_depth, min_depth=0.0, norm="minmax", lr_latent=0.05, lr_scaling=0.005):
+        """The per-frame prologue in one library call (mdc_begin_frame): image preprocess + VAE encoder, sparse-depth
+        normalisation, per-call state (marigold_dc.py:687-789).  Raises ValueError for a sample with an empty mask."""
+        imgs, dt = self._image_arg(imgs)
+        sparses = sparses.to(self.device, torch.float32).contiguous()
+        x = x.to(self.device, torch.bfloat16).contiguous()
+        assert sparses.numel() == self.n * self.H * self.W and tuple(x.shape) == (self.n, 4, self.lh, self.lw)
+        try:
+            check(self.lib.mdc_begin_frame(self._h, ptr(imgs), dt, int(imgs.shape[1]), ptr(sparses), ptr(x), float(max_depth),
+                                           float(min_depth), 1 if norm == "const" else 0, float(lr_latent), float(lr_scaling)))
+        except MdcError as e:
+            if "No valid values found in mask" in str(e):
+                raise ValueError(str(e)) from None
+            raise
 
     def decode_final(self) -> torch.Tensor:
         out = torch.empty(self.n, 1, self.H, self.W, device=self.device, dtype=torch.float32)
@@ -250,6 +271,13 @@ class StepEngine:
         out = torch.empty(self.n, 4, self.lh, self.lw, device=self.device, dtype=torch.float32)
         check(self.lib.mdc_dbg_read_buffer(self._h, which.encode(), ptr(out)))
         return out
+
+    def dbg_frame_state(self):
+        guide = torch.empty(self.n, 1, self.H, self.W, device=self.device, dtype=torch.float32)
+        mask = torch.empty(self.n, 1, self.H, self.W, device=self.device, dtype=torch.uint8)
+        st = np.zeros((self.n, 5), np.float32)
+        check(self.lib.mdc_dbg_frame_state(self._h, ptr(guide), ptr(mask), st.ctypes.data_as(C.c_void_p)))
+        return guide, mask.bool(), st
 
     def dbg_loss(self, dec_nchw: torch.Tensor):
         dec = dec_nchw.to(self.device, torch.float32).contiguous()

@@ -182,28 +182,12 @@ class MarigoldDepthCompletionPipeline:
             # marigold_dc.py:661, :677-684 -- first draw of the seeded generator, in the pipeline dtype
             gen = torch.Generator(device=dev).manual_seed(seed)
             common = torch.randn((1, 4, EH, EW), device=dev, dtype=self.dtype, generator=gen).repeat(N, 1, 1, 1)
-            # marigold_dc.py:687-698
             prologue.check_image(imgs)
-            img_latents = eng.encode(imgs)   # preprocess + VAE encoder inside libmdc_b200.so (mdc_encode)
             x = common if pred_latents_prev is None else beta * common + (1 - beta) * pred_latents_prev.to(dev)
-            # marigold_dc.py:707-756 (linear projection)
-            sparses = sparses.float()
-            masks = sparses > 0
-            if norm == "minmax":
-                lo, hi = prologue.masked_minmax(sparses.view(N, -1), masks.view(N, -1))
-                lo, hi = lo.view(N, 1, 1, 1), hi.view(N, 1, 1, 1)
-            else:  # "const"
-                lo = torch.full((N, 1, 1, 1), float(min_depth), device=dev)
-                hi = torch.full((N, 1, 1, 1), float(max_depth), device=dev)
-            clamped = sparses.clamp(min=lo, max=hi)
-            if norm == "minmax":
-                lo, hi = lo.clamp(min=min_depth), hi.clamp(max=max_depth)
-            guide = (clamped - lo) / (hi - lo)
-            # what _affine_to_metric recomputes every step (marigold_dc.py:326): masked min/max of the guide
-            gmin, gmax = prologue.masked_minmax(guide.view(N, -1), masks.view(N, -1))
-            gmm = torch.stack([gmin, gmax], dim=1).cpu().numpy()
-            dmm = torch.stack([lo.view(N), hi.view(N)], dim=1).cpu().numpy()
-        eng.begin(img_latents, x, guide, masks, gmm, dmm, lr_latent, lr_scaling)
+        # marigold_dc.py:687-789 inside libmdc_b200.so (mdc_begin_frame): image preprocess + VAE encoder, sparse-depth
+        # normalisation (mask, masked min / max, clamp, guide and its min / max), per-call optimiser state.
+        # An empty mask raises ValueError like utils.py:132-136.
+        eng.begin_frame(imgs, sparses, x, max_depth, min_depth, norm, lr_latent, lr_scaling)
         if _begin_only:  # bench.py: leave the engine at step 0 with everything resident in HBM
             return None, None
         eng.run(steps)                       # marigold_dc.py:799-909, no host sync inside

@@ -98,6 +98,26 @@ def vae_encode_mode(sd: dict, cfg, x: torch.Tensor) -> torch.Tensor:
     return moments[:, : cfg.latent_channels]
 
 
+def normalise_sparse(sparses: torch.Tensor, max_depth: float, min_depth: float, norm: str):
+    """marigold_dc.py:707-756 (linear projection) as plain PyTorch: returns guide, mask, (lo, hi) of the depth range and
+    the masked (min, max) of the guide.  The product path does this inside mdc_begin_frame; tests compare the two."""
+    n = sparses.shape[0]
+    sparses = sparses.float()
+    masks = sparses > 0
+    if norm == "minmax":
+        lo, hi = masked_minmax(sparses.view(n, -1), masks.view(n, -1))
+        lo, hi = lo.view(n, 1, 1, 1), hi.view(n, 1, 1, 1)
+    else:
+        lo = torch.full((n, 1, 1, 1), float(min_depth), device=sparses.device)
+        hi = torch.full((n, 1, 1, 1), float(max_depth), device=sparses.device)
+    clamped = sparses.clamp(min=lo, max=hi)
+    if norm == "minmax":
+        lo, hi = lo.clamp(min=min_depth), hi.clamp(max=max_depth)
+    guide = (clamped - lo) / (hi - lo)
+    gmin, gmax = masked_minmax(guide.view(n, -1), masks.view(n, -1))
+    return guide, masks, (lo.view(n), hi.view(n)), (gmin, gmax)
+
+
 def masked_minmax(x: torch.Tensor, mask: torch.Tensor):
     """Row-wise masked min / max; ValueError for an empty row (reference: utils.py:89-138)."""
     if x.shape != mask.shape:

@@ -79,6 +79,15 @@ int mdc_encode(mdc_handle* h, const void* imgs, int dtype, int channels, void* l
 int mdc_begin(mdc_handle* h, const void* img_latents_bf16, const void* x_bf16, const float* guide, const uint8_t* mask,
               const float* guide_minmax_host, const float* depth_minmax_host, float lr_latent, float lr_scaling);
 
+/* The whole per-frame prologue in one call (marigold_dc.py:687-756, linear projection): mdc_encode on `imgs`, then the
+ * sparse-depth normalisation on the device -- mask = sparse > 0, per-sample masked min / max ("minmax", norm_const =
+ * 0) or the constant range [min_depth, max_depth] (norm_const = 1), clamp, guide = (d - lo) / (hi - lo), masked
+ * min / max of the guide -- then mdc_begin with those.  sparse: device [N,1,H,W] fp32 metres (0 = missing); x_bf16:
+ * the initial depth latent [N,4,EH,EW] (the reference draws it from torch's seeded generator, :677-684).
+ * Fails with the reference's "No valid values found in mask ..." message (utils.py:132-136) for an empty sample. */
+int mdc_begin_frame(mdc_handle* h, const void* imgs, int img_dtype, int channels, const float* sparse, const void* x_bf16,
+                    float max_depth, float min_depth, int norm_const, float lr_latent, float lr_scaling);
+
 /* n guided steps (marigold_dc.py:801-904 each), asynchronous, no host synchronisation inside. */
 int mdc_run(mdc_handle* h, int n_steps);
 

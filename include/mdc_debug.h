@@ -52,6 +52,9 @@ int mdc_dbg_profile_gemm_step(mdc_handle* h, float* ms_host, double* flops_host,
 int mdc_dbg_profile_ops(mdc_handle* h, const char* csv_path, int iters);
 /* Per-tape timing: runs the forward (and backward) tapes `iters` times, returns ms per pass. */
 int mdc_dbg_time_tapes(mdc_handle* h, int iters, float* ms_host /* [4]: unet fwd, unet bwd, dec fwd, dec bwd */);
+/* What mdc_begin_frame derived from the sparse depth: guide [N,1,H,W] fp32 and mask [N,1,H,W] uint8 (device pointers,
+ * may be NULL) and per sample {lo, hi, guide min, guide max, number of valid points} (host, 5 floats each). */
+int mdc_dbg_frame_state(mdc_handle* h, float* guide_dev, unsigned char* mask_dev, float* stats_host);
 /* Planner overrides for tests and tuning sweeps (0 = automatic): output-tile width BN, cluster size (B multicast),
  * split-K factor (> 0 forced, < 0 = the engine's cost model also in mdc_dbg_conv3x3), and the number of weight copies
  * mdc_dbg_conv3x3 rotates through in its timed loop (so weights stream from HBM as in the real step). */

@@ -189,3 +189,31 @@ def test_engine_against_golden_fixture(models, cuda):
     assert torch.nn.functional.cosine_similarity(g, og, dim=0).item() > 0.85
     agree = ((eng.dbg_x_adam().float() - t("step_x_adam")[0]).abs() < 1e-2).float().mean().item()
     assert agree > 0.8, agree
+
+
+@pytest.mark.parametrize("norm", ["minmax", "const"])
+def test_begin_frame_sparse_normalisation(models, cuda, norm):
+    """mdc_begin_frame's device-side sparse-depth normalisation (marigold_dc.py:707-756) is bit-identical to the same
+    arithmetic in PyTorch, and an empty mask raises the reference's ValueError (utils.py:132-136)."""
+    from helpers import build_engine
+    from depth_completion_b200 import prologue
+    from depth_completion_b200.synthetic import make_batch
+
+    unet, vae, ctx, ucfg, vcfg = models
+    b = make_batch(2, H=96, W=128, n_points=70)
+    img, sp = b["img"].to(cuda), b["sparse"].to(cuda)
+    sp[1] = sp[1] * 3.0  # beyond max_depth: exercises the clamps
+    eng = build_engine(unet, vae, ctx, ucfg, vcfg, 2, 96, 128, 128, 50, cuda)
+    x = torch.randn(2, 4, eng.lh, eng.lw, device=cuda).bfloat16()
+    eng.begin_frame(img, sp, x, 10.0, 0.6, norm)
+    guide, mask, st = eng.dbg_frame_state()
+    g_ref, m_ref, (lo, hi), (gmin, gmax) = prologue.normalise_sparse(sp, 10.0, 0.6, norm)
+    assert torch.equal(mask, m_ref) and torch.equal(guide, g_ref)
+    assert torch.equal(torch.from_numpy(st[:, 0]), lo.cpu()) and torch.equal(torch.from_numpy(st[:, 1]), hi.cpu())
+    assert torch.equal(torch.from_numpy(st[:, 2]), gmin.cpu()) and torch.equal(torch.from_numpy(st[:, 3]), gmax.cpu())
+    assert st[:, 4].tolist() == m_ref.view(2, -1).sum(1).tolist()
+    eng.run(2)
+    assert torch.isfinite(eng.decode_final()).all()
+    sp[0] = 0
+    with pytest.raises(ValueError, match="No valid values found in mask"):
+        eng.begin_frame(img, sp, x, 10.0, 0.6, norm)
