@@ -29,6 +29,13 @@ class VAEConfig:
     layers_per_block: int = 2
     norm_num_groups: int = 32
     scaling_factor: float = 0.18215
+    # kind "kl": AutoencoderKL (fields above).  kind "tiny": AutoencoderTiny, the reference CLI's default VAE
+    # (predict.py:44-52, 484-488): block_out_channels are the (equal) stage widths, layers_per_block / norm_num_groups
+    # are unused.
+    kind: str = "kl"
+    num_encoder_blocks: tuple = (1, 3, 3, 3)
+    num_decoder_blocks: tuple = (3, 3, 3, 1)
+    latent_magnitude: float = 3.0
 
 
 def _get(obj, name, default=None):
@@ -60,6 +67,18 @@ def vae_config_from(module) -> VAEConfig:
     if isinstance(module, VAEConfig):
         return module
     c = _get(module, "cfg") or _get(module, "config") or module
+    if _get(c, "decoder_block_out_channels") is not None:  # AutoencoderTiny (diffusers config names)
+        enc, dec = tuple(_get(c, "encoder_block_out_channels")), tuple(_get(c, "decoder_block_out_channels"))
+        if enc != dec or len(set(dec)) != 1:
+            raise ValueError(f"AutoencoderTiny: encoder / decoder stage widths must all be equal, got {enc} / {dec}")
+        if _get(c, "act_fn", "relu") != "relu" or _get(c, "upsampling_scaling_factor", 2) != 2:
+            raise ValueError("AutoencoderTiny: only act_fn='relu' and upsampling_scaling_factor=2 are supported")
+        return VAEConfig(in_channels=_get(c, "in_channels", 3), out_channels=_get(c, "out_channels", 3),
+                         latent_channels=_get(c, "latent_channels", 4), block_out_channels=dec, layers_per_block=0,
+                         norm_num_groups=0, scaling_factor=_get(c, "scaling_factor", 1.0), kind="tiny",
+                         num_encoder_blocks=tuple(_get(c, "num_encoder_blocks")),
+                         num_decoder_blocks=tuple(_get(c, "num_decoder_blocks")),
+                         latent_magnitude=float(_get(c, "latent_magnitude", 3)))
     return VAEConfig(in_channels=_get(c, "in_channels", 3), out_channels=_get(c, "out_channels", 3),
                      latent_channels=_get(c, "latent_channels", 4),
                      block_out_channels=tuple(_get(c, "block_out_channels")),

@@ -53,6 +53,8 @@ struct Tensor {
   long long ld = 0;
   bool grad_set = false;
   bool is_view = false;   // channel slice of a concat buffer: its gradient must stay inside the parent's
+  bool relu_out = false;  // produced by a conv + ReLU epilogue: its gradient is masked by (value > 0) once complete
+  bool mask_owned = false;  // ... by the backward of its first forward consumer (the last one to contribute)
   std::string name;
   long long rows() const { return 1LL * n * h * w; }
 };
@@ -77,6 +79,7 @@ struct WeightSlot {
   bf16* wt = nullptr;           // CONV3: dgrad pack; LIN: transposed pack (column offset applied), ld_wt
   long long ld_wt = 0;
   float* vec = nullptr;         // VEC destination
+  float vscale = 1.f, vshift = 0.f;  // VEC: stored as vscale * value + vshift (bias of a scaled / shifted epilogue)
   bool loaded = false;
 };
 
@@ -90,10 +93,12 @@ struct ConvOp : Op {  // 3x3 stride-1 pad-1 convolution (+bias, +residual)
   const float* bias;
   GemmPlan pf, pb;
   bool acc_res = false, alias_res = false;
+  float alpha = 1.f;     // y = alpha * conv(x) + bias (+ res); the input gradient carries the same factor
+  bool mask_x = false;   // x is a ReLU output and this op is its first consumer: mask x's finished gradient by (x > 0)
   void plan_bwd() override;
   void fwd(cudaStream_t st) override { run_gemm(pf, st); }
   void bwd(cudaStream_t st) override;
-  int n_bwd() const override { return (res && !alias_res) ? 2 : 1; }
+  int n_bwd() const override { return ((res && !alias_res) ? 2 : 1) + (mask_x ? 1 : 0); }
   void gemm_plans(std::vector<const GemmPlan*>& f, std::vector<const GemmPlan*>& b) const override {
     f.push_back(&pf), b.push_back(&pb);
   }
@@ -265,12 +270,41 @@ struct UpConvOp : Op {  // fused nearest-2x upsample + conv3x3 (four 2x2 phase c
   WeightSlot* W;
   const float* bias;
   GemmPlan pf, pb;
+  bool mask_x = false;  // see ConvOp::mask_x
   void plan_bwd() override;
   void fwd(cudaStream_t st) override { run_gemm(pf, st); }
-  void bwd(cudaStream_t st) override { run_gemm(pb, st); }
+  void bwd(cudaStream_t st) override;
+  int n_bwd() const override { return mask_x ? 2 : 1; }
   void gemm_plans(std::vector<const GemmPlan*>& f, std::vector<const GemmPlan*>& b) const override {
     f.push_back(&pf), b.push_back(&pb);
   }
+};
+struct TanhClampOp : Op {  // DecoderTiny: y = tanh(x / m) * m
+  Tensor *x, *y;
+  float m;
+  bool acc = false;
+  void plan_bwd() override {
+    acc = x->grad_set;
+    x->grad_set = true;
+  }
+  void fwd(cudaStream_t st) override {
+    const long long tot = x->rows() * x->c;
+    launch_k(tanh_clamp_fwd_kernel, dim3(static_cast<int>((tot + 255) / 256)), dim3(256), 0, st, x->d, x->ld, y->d, y->ld, x->rows(), x->c, m);
+  }
+  void bwd(cudaStream_t st) override {
+    const long long tot = x->rows() * x->c;
+    launch_k(tanh_clamp_bwd_kernel, dim3(static_cast<int>((tot + 255) / 256)), dim3(256), 0, st, x->d, x->ld, y->g, y->ld, x->g, x->ld, x->rows(),
+             x->c, m, acc ? 1 : 0);
+  }
+};
+struct UnitRangeOp : Op {  // EncoderTiny: y = (x + 1) / 2 (forward only)
+  Tensor *x, *y;
+  void fwd(cudaStream_t st) override {
+    const long long tot = x->rows() * x->c;
+    launch_k(unit_range_kernel, dim3(static_cast<int>((tot + 255) / 256)), dim3(256), 0, st, x->d, x->ld, y->d, y->ld, x->rows(), x->c);
+  }
+  void bwd(cudaStream_t) override {}
+  int n_bwd() const override { return 0; }
 };
 struct SubsampleOp : Op {
   Tensor *x, *y;
@@ -402,6 +436,12 @@ struct Engine {
   ~Engine();
   void decode_final(float* dense_out);
   void build_encoder();
+  void build_tiny_decoder();
+  void build_tiny_encoder();
+  Tensor* tiny_conv(Tensor* x, int cout, const std::string& key, bool has_bias, bool relu, Tensor* res = nullptr, float alpha = 1.f,
+                    float bias_shift = 0.f);
+  Tensor* tiny_block(Tensor* x, const std::string& key);
+  Tensor* tiny_upconv(Tensor* x, const std::string& key);
   Tensor* vae_mid_attention(Tensor* h, const std::string& A);
   void encode(const void* imgs, int dtype, int channels, void* latents_out);
   void begin_frame(const void* imgs, int dtype, int channels, const float* sparse, const void* x0, float max_depth,
@@ -431,7 +471,7 @@ struct Engine {
 // ================================================================================================ op bodies
 inline void ConvOp::plan_bwd() {
   Epilogue e;
-  e.out = x->g, e.ldc = x->ld;
+  e.out = x->g, e.ldc = x->ld, e.alpha = alpha;
   if (x->grad_set) e.res = x->g, e.ldr = x->ld;
   x->grad_set = true;
   pb = plan_conv3x3(y->n, y->h, y->w, y->c, x->c, y->g, y->ld, W->wt, e);
@@ -447,11 +487,15 @@ inline void ConvOp::plan_bwd() {
     }
   }
 }
+inline void relu_mask(Tensor* x, cudaStream_t st) {
+  launch_k(relu_mask_kernel, dim3(ew_grid(x->rows() * (x->c / 8))), dim3(256), 0, st, x->g, x->ld, x->d, x->ld, x->rows(), x->c);
+}
 inline void ConvOp::bwd(cudaStream_t st) {
   run_gemm(pb, st);
   if (res && !alias_res)
     launch_k(add_rows_kernel, dim3(ew_grid(res->rows() * (res->c / 8))), dim3(256), 0, st, y->g, y->ld, res->g, res->ld, res->rows(), res->c,
                                                                         acc_res);
+  if (mask_x) relu_mask(x, st);
 }
 inline void UpConvOp::plan_bwd() {
   Epilogue e;
@@ -459,6 +503,10 @@ inline void UpConvOp::plan_bwd() {
   if (x->grad_set) e.res = x->g, e.ldr = x->ld;
   x->grad_set = true;
   pb = plan_upconv_bwd(x->n, x->h, x->w, x->c, y->c, y->g, y->ld, W->wt, e);
+}
+inline void UpConvOp::bwd(cudaStream_t st) {
+  run_gemm(pb, st);
+  if (mask_x) relu_mask(x, st);
 }
 inline void LinearOp::plan_bwd() {
   Epilogue e;
@@ -724,7 +772,9 @@ inline Tensor* Engine::group_norm(Tensor* x, const std::string& key, float eps, 
     }
   }
   op->stats = arena.make<float>(2ull * x->n * G);
-  gn_partial_floats = std::max<size_t>(gn_partial_floats, static_cast<size_t>(2) * G * x->n * s.blocks_per_img);
+  // the single-launch variant may use MORE blocks than the two-pass one on small maps (one pixel row per block)
+  gn_partial_floats = std::max<size_t>(gn_partial_floats,
+                                       static_cast<size_t>(2) * G * x->n * std::max(s.blocks_per_img, op->sfu.blocks_per_img));
   push(op, key);
   return y;
 }
@@ -1047,6 +1097,109 @@ inline void Engine::build_encoder() {
   alloc_grads = true;
 }
 
+// ------------------------------------------------------------------------------------------------ AutoencoderTiny graphs
+// The VAE the reference CLI uses by default (predict.py:44-52, 484-488): plain 64-channel
+// conv3x3 + ReLU residual blocks, nearest x2 upsampling, no normalisation, no attention.  ReLU rides in the conv
+// epilogue; its backward is a mask applied to a tensor's gradient once the first forward consumer (the last backward
+// contributor) has added its part.
+inline Tensor* Engine::tiny_conv(Tensor* x, int cout, const std::string& key, bool has_bias, bool relu, Tensor* res, float alpha,
+                                 float bias_shift) {
+  WeightSlot* W = slot(key + ".weight", W_CONV3, cout, x->c);
+  WeightSlot* B = has_bias ? slot(key + ".bias", W_VEC, cout, 0) : nullptr;
+  if (B) B->vscale = alpha, B->vshift = bias_shift;
+  Tensor* y = new_tensor(x->n, x->h, x->w, cout, "");
+  auto* op = new ConvOp();
+  op->E = this, op->x = x, op->y = y, op->res = res, op->W = W, op->alpha = alpha;
+  op->bias = B ? B->vec : nullptr;
+  if (x->relu_out && !x->mask_owned && alloc_grads) op->mask_x = true, x->mask_owned = true;
+  Epilogue e;
+  e.out = y->d, e.ldc = y->ld, e.bias = op->bias, e.alpha = alpha, e.relu = relu ? 1 : 0;
+  if (res) e.res = res->d, e.ldr = res->ld;
+  op->pf = plan_conv3x3(x->n, x->h, x->w, x->c, cout, x->d, x->ld, W->w, e);
+  y->relu_out = relu;
+  push(op, key);
+  y->name = key, named[key] = y;
+  return y;
+}
+inline Tensor* Engine::tiny_block(Tensor* x, const std::string& key) {
+  Tensor* a = tiny_conv(x, x->c, key + ".conv.0", true, true);
+  a = tiny_conv(a, x->c, key + ".conv.2", true, true);
+  return tiny_conv(a, x->c, key + ".conv.4", true, true, x);  // relu(conv(a) + x)
+}
+inline Tensor* Engine::tiny_upconv(Tensor* x, const std::string& key) {  // nn.Upsample(x2, nearest) + conv3x3 without bias
+  WeightSlot* W = slot(key + ".weight", W_UPCONV, x->c, x->c);
+  Tensor* y = new_tensor(x->n, 2 * x->h, 2 * x->w, x->c, "");
+  auto* op = new UpConvOp();
+  op->E = this, op->x = x, op->y = y, op->W = W, op->bias = nullptr;
+  if (x->relu_out && !x->mask_owned && alloc_grads) op->mask_x = true, x->mask_owned = true;
+  Epilogue e;
+  e.out = y->d, e.ldc = y->ld;
+  op->pf = plan_upconv_fwd(x->n, x->h, x->w, x->c, x->c, x->d, x->ld, W->w, e);
+  push(op, key);
+  y->name = key, named[key] = y;
+  return y;
+}
+inline void Engine::build_tiny_decoder() {
+  cur_ops = &dec_ops;
+  const std::string L = "vae.decoder.layers.";
+  dec_in = new_tensor(N, lh, lw, cfg.vae_latent_ch, "vae.in");
+  Tensor* z = new_tensor(N, lh, lw, cfg.vae_latent_ch, "vae.decoder.clamped");
+  {
+    auto* op = new TanhClampOp();
+    op->x = dec_in, op->y = z, op->m = cfg.tiny_magnitude;
+    push(op, "vae.decoder.tanh");
+  }
+  Tensor* h = tiny_conv(z, cfg.vae_block_ch[0], L + "0", true, true);
+  int idx = 2;  // index 1 is the ReLU module
+  for (int i = 0; i < cfg.vae_nblocks; ++i) {
+    const bool last = i == cfg.vae_nblocks - 1;
+    MDC_CHECK(cfg.vae_block_ch[i] == h->c, "AutoencoderTiny: decoder widths must be equal (got %d after %d)", cfg.vae_block_ch[i], h->c);
+    for (int j = 0; j < cfg.tiny_dec_blocks[i]; ++j) h = tiny_block(h, L + std::to_string(idx++));
+    if (!last) {
+      ++idx;  // the nn.Upsample module
+      h = tiny_upconv(h, L + std::to_string(idx++));
+    } else {
+      // sample = conv(h) * 2 - 1: alpha = 2 with the bias stored as 2 b - 1
+      dec_out = tiny_conv(h, 3, L + std::to_string(idx++), true, false, nullptr, 2.f, -1.f);
+    }
+  }
+  named["vae.out"] = dec_out;
+  MDC_CHECK(dec_out->h == PPH && dec_out->w == PPW, "AutoencoderTiny decoder output %dx%d != %dx%d", dec_out->h, dec_out->w, PPH, PPW);
+}
+inline void Engine::build_tiny_encoder() {
+  cur_ops = &enc_ops;
+  alloc_grads = false;
+  const std::string L = "vae.encoder.layers.";
+  enc_in = new_tensor(N, PPH, PPW, 3, "vae.enc_in");
+  Tensor* u = new_tensor(N, PPH, PPW, 3, "");
+  {
+    auto* op = new UnitRangeOp();
+    op->x = enc_in, op->y = u;
+    push(op, "vae.encoder.unit_range");
+  }
+  Tensor* h = nullptr;
+  int idx = 0;
+  for (int i = 0; i < cfg.vae_nblocks; ++i) {
+    const int c = cfg.vae_block_ch[i];
+    if (i == 0) {
+      h = tiny_conv(u, c, L + std::to_string(idx++), true, false);
+    } else {  // conv3x3 stride 2 pad 1 without bias = the stride-1 conv sampled at even positions
+      MDC_CHECK(h->h % 2 == 0 && h->w % 2 == 0, "AutoencoderTiny encoder: odd feature map %dx%d", h->h, h->w);
+      Tensor* full = tiny_conv(h, c, L + std::to_string(idx++), false, false);
+      Tensor* y = new_tensor(N, h->h / 2, h->w / 2, c, "");
+      auto* op = new SubsampleOp();
+      op->x = full, op->y = y, op->off = 0;
+      push(op, full->name + ".stride2");
+      h = y;
+    }
+    for (int j = 0; j < cfg.tiny_enc_blocks[i]; ++j) h = tiny_block(h, L + std::to_string(idx++));
+  }
+  enc_out = tiny_conv(h, cfg.vae_latent_ch, L + std::to_string(idx++), true, false);
+  named["vae.enc_out"] = enc_out;
+  MDC_CHECK(enc_out->h == lh && enc_out->w == lw, "encoder output %dx%d != latent %dx%d", enc_out->h, enc_out->w, lh, lw);
+  alloc_grads = true;
+}
+
 // ------------------------------------------------------------------------------------------------ VAE decoder graph
 inline void Engine::build_decoder() {
   cur_ops = &dec_ops;
@@ -1127,9 +1280,9 @@ inline Engine::Engine(const mdc_config& c) : cfg(c) {
   MDC_CUDA(cudaFuncSetAttribute(softmax_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   MDC_CUDA(cudaFuncSetAttribute(softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   build_unet();
-  build_decoder();
+  if (cfg.vae_kind == 1) build_tiny_decoder(); else build_decoder();
   n_split_step = split_plans.size();
-  build_encoder();
+  if (cfg.vae_kind == 1) build_tiny_encoder(); else build_encoder();
   finalize_plans();
   // step state
   const size_t lat = 4ull * N * lh * lw;
@@ -1196,6 +1349,8 @@ inline void Engine::set_weight(const std::string& key, const void* src, const lo
         to_f32_kernel<float><<<32, 256, 0, stream>>>((const float*)src, s->vec, numel);
       else  // bf16 parameters are used at bf16 precision, like the reference's bf16 modules
         to_f32_kernel<bf16><<<32, 256, 0, stream>>>((const bf16*)src, s->vec, numel);
+      if (s->vscale != 1.f || s->vshift != 0.f)
+        vec_affine_kernel<<<static_cast<int>((numel + 255) / 256), 256, 0, stream>>>(s->vec, numel, s->vscale, s->vshift);
     }
     s->loaded = true;
   }
@@ -1310,6 +1465,15 @@ inline void Engine::begin(const void* img_latents, const void* x0, const float* 
   launch_k(compact_points_kernel, dim3(N), dim3(1024), 0, stream, guide, mask, H * W, pt_off, pt_idx, pt_val);
   MDC_CUDA(cudaGetLastError());
   MDC_CUDA(cudaStreamSynchronize(stream));
+  if (getenv("MDC_DEBUG_SYNC")) {  // consistency of the compacted point list
+    std::vector<int> idx(off[N]), o2(N + 1);
+    MDC_CUDA(cudaMemcpy(idx.data(), pt_idx, idx.size() * 4, cudaMemcpyDeviceToHost));
+    MDC_CUDA(cudaMemcpy(o2.data(), pt_off, o2.size() * 4, cudaMemcpyDeviceToHost));
+    for (int n = 0; n <= N; ++n) MDC_CHECK(o2[n] == off[n], "pt_off[%d] = %d, expected %d", n, o2[n], off[n]);
+    for (size_t i = 0; i < idx.size(); ++i) MDC_CHECK(idx[i] >= 0 && idx[i] < H * W, "pt_idx[%zu] = %d out of range (H*W = %d)", i, idx[i], H * W);
+    fprintf(stderr, "[mdc debug] begin: %d points, geometry H %d W %d ph %d pw %d PPH %d PPW %d dec ld %lld\n", off[N], H, W, ph, pw, PPH, PPW,
+            dec_out->ld);
+  }
   lr_x = lrx, lr_s = lrs;
   steps_done = 0;
   begun = true;
@@ -1366,8 +1530,21 @@ inline void Engine::profile_gemm_step(float* ms_out, double* flops_out, int* lau
 }
 
 inline void Engine::run_ops(std::vector<std::unique_ptr<Op>>& ops, bool backward) {
+  static const bool dbg = getenv("MDC_DEBUG_SYNC") != nullptr;
   if (!backward)
-    for (auto& op : ops) op->fwd(stream);
+    for (auto& op : ops) {
+      op->fwd(stream);
+      if (dbg && begun && pt_off) {  // which op scribbles over the point list?
+        int o2[2] = {0, 0};
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(stream, &cs);
+        if (cs == cudaStreamCaptureStatusNone) {
+          MDC_CUDA(cudaMemcpy(o2, pt_off, 8, cudaMemcpyDeviceToHost));
+          MDC_CHECK(o2[0] == 0 && o2[1] > 0 && o2[1] <= H * W, "pt_off corrupted (%d, %d) right after the forward of op '%s'", o2[0], o2[1],
+                    op->name.c_str());
+        }
+      }
+    }
   else
     for (auto it = ops.rbegin(); it != ops.rend(); ++it) (*it)->bwd(stream);
 }
@@ -1407,9 +1584,25 @@ inline void Engine::step_launches() {
   TailGeom g{N, H, W, ph, pw, PPH, PPW, dec_out->ld};
   launch_k(begin_step_kernel, dim3(1), dim3(1024), 0, stream, tables, counter, cur, temb_cur, lr_x, lr_s);
   launch_k(unet_input_kernel, dim3((lat_pix + 255) / 256), dim3(256), 0, stream, img_lat, x, N, hw, unet_in->d);
+  auto dbg_points = [&](const char* tag) {  // MDC_DEBUG_SYNC: has anything scribbled over the compacted point list?
+    static const bool on = getenv("MDC_DEBUG_SYNC") != nullptr;
+    if (!on) return;
+    std::vector<int> o2(N + 1);
+    MDC_CUDA(cudaMemcpy(o2.data(), pt_off, o2.size() * 4, cudaMemcpyDeviceToHost));
+    MDC_CHECK(o2[0] == 0 && o2[N] > 0 && o2[N] <= N * H * W, "%s: pt_off corrupted (%d .. %d)", tag, o2[0], o2[N]);
+    std::vector<int> idx(o2[N]);
+    MDC_CUDA(cudaMemcpy(idx.data(), pt_idx, idx.size() * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < idx.size(); ++i) MDC_CHECK(idx[i] >= 0 && idx[i] < H * W, "%s: pt_idx[%zu] = %d corrupted", tag, i, idx[i]);
+    StepAccum a;
+    MDC_CUDA(cudaMemcpy(&a, accum, sizeof(a), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[mdc debug] %s: points ok, scale %g shift %g, dmean %p dec %p acc %p\n", tag, a.scale[0], a.shift[0], (void*)dmean,
+            (void*)dec_out->d, (void*)accum);
+  };
   run_ops(unet_ops, false);
+  dbg_points("after unet fwd");
   launch_k(x0_kernel, dim3(pgrid), dim3(256), 0, stream, unet_out->d, x, cur, N, hw, cfg.vae_scaling, dec_in->d, eps_part);
   run_ops(dec_ops, false);
+  dbg_points("after decoder fwd");
   launch_k(loss_points_kernel, dim3(N), dim3(512), 0, stream, dec_out->d, g, pt_idx, pt_val, pt_off, gminmax, accum, dmean);
   const long long npix = 1LL * N * PPH * PPW;
   launch_k(dec_grad_kernel, dim3(static_cast<int>((npix + 255) / 256)), dim3(256), 0, stream, dmean, npix, dec_out->g);

@@ -62,6 +62,7 @@ struct GemmParams {
   const __nv_bfloat16* res;
   long long ldr, sr0, sr1;
   float alpha;
+  int relu;  // clamp the finished value at zero (AutoencoderTiny's conv + ReLU, applied after bias / residual)
   // TMA-store epilogue (bf16 outputs): each 128-row x 32-column chunk is staged in 64B-swizzled shared memory and
   // written with one bulk tensor store (coalesced, hardware-clipped) instead of 16-byte scattered stores per thread.
   int tma_store;
@@ -440,6 +441,10 @@ __device__ __forceinline__ void umma_gemm_body(const GemmParams& p) {
                   if (j < ncol) v[j] += __bfloat162float(e_res[off_r + col0 + j]);
               }
             }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
             uint4* o4 = reinterpret_cast<uint4*>(panel + row * 64);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -494,6 +499,10 @@ __device__ __forceinline__ void umma_gemm_body(const GemmParams& p) {
               }
             }
           }
+          if (p.relu && p.ksplit <= 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
           if (e_f32) {
             float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(e_out) + off_c + col0);
 #pragma unroll
@@ -517,6 +526,7 @@ __device__ __forceinline__ void umma_gemm_body(const GemmParams& p) {
             float x = __uint_as_float(raw[j]) * e_alpha;
             if (has_bias) x += sbias[c0 + j];
             if (e_res) x += __bfloat162float(e_res[off_r + col]);
+            if (p.relu && p.ksplit <= 1) x = fmaxf(x, 0.f);
             if (e_f32)
               static_cast<float*>(e_out)[off_c + col] = x;
             else
@@ -637,6 +647,7 @@ struct Epilogue {
   const __nv_bfloat16* res = nullptr;
   long long ldr = 0, sr0 = 0, sr1 = 0;
   float alpha = 1.f;
+  int relu = 0;
 };
 
 struct GemmPlan {
@@ -772,7 +783,7 @@ inline void finish_plan(GemmPlan& g) {
 inline void fill_epilogue(GemmParams& p, const Epilogue& e) {
   p.out = e.out, p.out_f32 = e.out_f32, p.ldc = e.ldc, p.sc0 = e.sc0, p.sc1 = e.sc1;
   p.bias = e.bias, p.bias_img = e.bias_img, p.res = e.res, p.ldr = e.ldr, p.sr0 = e.sr0, p.sr1 = e.sr1;
-  p.alpha = e.alpha;
+  p.alpha = e.alpha, p.relu = e.relu;
 }
 
 // Batched GEMM: for each (b0, b1): D = alpha * A . B^T (+...).  K need not be a multiple of 64 (TMA zero-fills).
@@ -882,6 +893,20 @@ inline bool g_use_pdl() {
   if (v < 0) v = getenv("MDC_NO_PDL") ? 0 : 1;
   return v == 1;
 }
+// MDC_DEBUG_SYNC=1 (not under graph capture): synchronise after every launch and name the kernel that faulted.
+inline void debug_sync(const void* func, cudaStream_t st) {
+  static const bool on = getenv("MDC_DEBUG_SYNC") != nullptr;
+  if (!on) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (cs != cudaStreamCaptureStatusNone) return;
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    const char* name = "?";
+    cudaFuncGetName(&name, func);
+    throw HostError{std::string("kernel ") + name + " failed: " + cudaGetErrorString(e)};
+  }
+}
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg;
@@ -892,6 +917,7 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr, cfg.numAttrs = g_use_pdl() ? 1 : 0;
   MDC_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  debug_sync(reinterpret_cast<const void*>(kernel), st);
 }
 
 // Fused nearest-2x upsample + conv3x3 (pad 1) as four 2x2 "phase" convolutions on the LOW-resolution input:
@@ -1019,12 +1045,26 @@ inline void launch_gemm_kernel(const GemmPlan& g, cudaStream_t st) {
   }
   cfg.attrs = attr, cfg.numAttrs = na;
   MDC_CUDA(cudaLaunchKernelEx(&cfg, g.p.pair ? umma_gemm_pair_kernel : umma_gemm_kernel, g.p));
+  if (getenv("MDC_DEBUG_SYNC")) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs == cudaStreamCaptureStatusNone) {
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) {
+        char b[400];
+        snprintf(b, sizeof(b), "GEMM failed (%s): conv %d M %d N %d BN %d tiles %d x %d k-chunks %d H %d W %d pair %d ksplit %d nphase %d res %p out %p",
+                 cudaGetErrorString(e), g.p.conv, g.p.M, g.p.N, g.p.BN, g.p.m_tiles, g.p.n_tiles, g.p.num_k_chunks, g.p.H, g.p.W, g.p.pair,
+                 g.p.ksplit, g.p.nphase, (const void*)g.p.res, g.p.out);
+        throw HostError{std::string(b)};
+      }
+    }
+  }
 }
 
 // Decide on split-K for a finished plan: few output tiles, long K loop.  `ws` must hold ws_floats(plan) floats.
 inline int choose_ksplit(const GemmPlan& g) {
   const GemmParams& p = g.p;
-  if (p.nb0 != 1 || p.nb1 != 1 || p.bias_img || p.out_f32 || p.conv == 2 || p.nphase > 1) return 1;
+  if (p.nb0 != 1 || p.nb1 != 1 || p.bias_img || p.out_f32 || p.conv == 2 || p.nphase > 1 || p.relu) return 1;
   if (g_tune().ksplit > 0) return g_tune().ksplit;
   const int tiles = ((p.m_tiles + p.cs - 1) / p.cs) * p.cs * p.n_tiles, nk = p.num_k_chunks, sms = (g_num_sms() / p.cs) * p.cs;
   static const int max_tiles = getenv("MDC_SPLITK_MAXTILES") ? atoi(getenv("MDC_SPLITK_MAXTILES")) : 100;

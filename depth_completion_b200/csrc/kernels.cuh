@@ -657,6 +657,68 @@ __global__ void __launch_bounds__(512, 1) gn_fused_bwd_kernel(const bf16* __rest
   }
 }
 
+// =========================================================================== AutoencoderTiny element-wise pieces
+// g = (y > 0) ? g : 0 in place: backward of the ReLU that produced y (applied once y's gradient is complete)
+__global__ void relu_mask_kernel(bf16* __restrict__ g, long long ldg, const bf16* __restrict__ y, long long ldy,
+                                 long long rows, int C) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  const int cv = C >> 3;
+  const long long total = rows * cv;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const long long r = i / cv;
+    const int v = static_cast<int>(i % cv) * 8;
+    float fy[8], fg[8];
+    bf8_to_f(*reinterpret_cast<const BF8*>(y + r * ldy + v), fy);
+    bf8_to_f(*reinterpret_cast<const BF8*>(g + r * ldg + v), fg);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) fg[k] = fy[k] > 0.f ? fg[k] : 0.f;
+    *reinterpret_cast<BF8*>(g + r * ldg + v) = f_to_bf8(fg);
+  }
+}
+// DecoderTiny input clamp: y = tanh(x / m) * m (each step rounded to bf16 like the reference's bf16 tensors);
+// backward: dx (+)= dy * (1 - tanh(x / m)^2).  C <= 8 channels per row (latents), one thread per element.
+__global__ void tanh_clamp_fwd_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
+                                      long long rows, int C, float m) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  const long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const long long r = i / C;
+  const int c = static_cast<int>(i % C);
+  const float t = bf16r(tanhf(bf16r(__bfloat162float(x[r * ldx + c]) / m)));
+  y[r * ldy + c] = __float2bfloat16(t * m);
+}
+__global__ void tanh_clamp_bwd_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ dy, long long lddy,
+                                      bf16* __restrict__ dx, long long lddx, long long rows, int C, float m, int acc) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  const long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const long long r = i / C;
+  const int c = static_cast<int>(i % C);
+  const float t = tanhf(__bfloat162float(x[r * ldx + c]) / m);
+  float g = __bfloat162float(dy[r * lddy + c]) * (1.f - t * t);
+  if (acc) g += __bfloat162float(dx[r * lddx + c]);
+  dx[r * lddx + c] = __float2bfloat16(g);
+}
+// EncoderTiny input map: y = (x + 1) / 2, rounded to bf16 after each step
+__global__ void unit_range_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
+                                  long long rows, int C) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  const long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const long long r = i / C;
+  const int c = static_cast<int>(i % C);
+  y[r * ldy + c] = __float2bfloat16(bf16r(__bfloat162float(x[r * ldx + c]) + 1.f) * 0.5f);
+}
+// v = scale * v + shift on a small fp32 vector (biases folded into a scaled / shifted epilogue)
+__global__ void vec_affine_kernel(float* __restrict__ v, long long n, float scale, float shift) {
+  const long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = scale * v[i] + shift;
+}
+
 // =========================================================================== LayerNorm (one warp per row)
 constexpr int LN_MAXV = 5;  // supports d <= 32*8*5 = 1280
 

@@ -27,6 +27,8 @@ class MdcConfig(C.Structure):
         ("unet_down_attn", C.c_int * MAX_BLOCKS),
         ("vae_nblocks", C.c_int), ("vae_layers_per_block", C.c_int), ("vae_groups", C.c_int),
         ("vae_latent_ch", C.c_int), ("vae_block_ch", C.c_int * MAX_BLOCKS), ("vae_scaling", C.c_float),
+        ("vae_kind", C.c_int), ("tiny_enc_blocks", C.c_int * MAX_BLOCKS), ("tiny_dec_blocks", C.c_int * MAX_BLOCKS),
+        ("tiny_magnitude", C.c_float),
     ]
 
 
@@ -103,6 +105,11 @@ class StepEngine:
         c.vae_groups, c.vae_latent_ch, c.vae_scaling = vae_cfg.norm_num_groups, vae_cfg.latent_channels, vae_cfg.scaling_factor
         for i, v in enumerate(vae_cfg.block_out_channels):
             c.vae_block_ch[i] = v
+        c.vae_kind = 1 if vae_cfg.kind == "tiny" else 0
+        if c.vae_kind:
+            for i, (ne, nd) in enumerate(zip(vae_cfg.num_encoder_blocks, vae_cfg.num_decoder_blocks)):
+                c.tiny_enc_blocks[i], c.tiny_dec_blocks[i] = ne, nd
+            c.tiny_magnitude = vae_cfg.latent_magnitude
         with torch.cuda.device(dev):
             check(self.lib.mdc_create(C.byref(c), C.byref(self._h)))
         self._keep = []

@@ -40,7 +40,15 @@ typedef struct mdc_config {
   /* AutoencoderKL decoder config (Appendix A.2) */
   int vae_nblocks, vae_layers_per_block, vae_groups, vae_latent_ch;
   int vae_block_ch[MDC_MAX_BLOCKS];
-  float vae_scaling;          /* 0.18215 */
+  float vae_scaling;          /* 0.18215 (AutoencoderKL) / 1.0 (AutoencoderTiny) */
+  /* vae_kind 0: AutoencoderKL (fields above).  1: AutoencoderTiny, the reference CLI's default VAE (predict.py:44-52,
+   * :484-488): vae_nblocks stages of width vae_block_ch[i] (all equal), tiny_dec_blocks[i] / tiny_enc_blocks[i] residual
+   * blocks per stage, latents clamped with tanh(z / tiny_magnitude) * tiny_magnitude; vae_layers_per_block / vae_groups
+   * are ignored. */
+  int vae_kind;
+  int tiny_enc_blocks[MDC_MAX_BLOCKS];
+  int tiny_dec_blocks[MDC_MAX_BLOCKS];
+  float tiny_magnitude;
 } mdc_config;
 
 typedef struct mdc_handle mdc_handle;

@@ -194,3 +194,24 @@ def test_oracle_reproduces_golden_fixture():
     assert np.allclose(out["step_x_adam"][0], gold["step_x_adam"][0], atol=1e-4)
     assert np.allclose(out["step_losses"], gold["step_losses"], rtol=2e-2)
     assert np.abs(out["dense"] - gold["dense"]).mean() < 1e-2 * float(gold["max_depth"])
+
+
+def test_autoencoder_tiny_structure():
+    """Structural pins of the AutoencoderTiny restatement (oracle/taesd.py; diffusers is absent, parity unpinned):
+    1.22 M parameters per half like the published TAESD, diffusers' key layout, x8 geometry, output ranges."""
+    from oracle.taesd import AutoencoderTiny
+
+    m = AutoencoderTiny()
+    n_enc = sum(p.numel() for p in m.encoder.parameters())
+    n_dec = sum(p.numel() for p in m.decoder.parameters())
+    assert (n_enc, n_dec) == (1222532, 1222531)
+    keys = set(m.state_dict().keys())
+    for k in ("encoder.layers.0.weight", "encoder.layers.1.conv.4.bias", "encoder.layers.2.weight", "encoder.layers.14.bias",
+              "decoder.layers.0.bias", "decoder.layers.2.conv.0.weight", "decoder.layers.6.weight", "decoder.layers.18.bias"):
+        assert k in keys, k
+    assert "encoder.layers.2.bias" not in keys and "decoder.layers.6.bias" not in keys  # stride-2 / post-upsample convs: no bias
+    x = torch.rand(2, 3, 32, 48) * 2 - 1
+    z = m.encode_mode(x)
+    assert z.shape == (2, 4, 4, 6)
+    y = m.decode(z * 50)  # tanh clamp keeps huge latents finite
+    assert y.shape == x.shape and torch.isfinite(y).all()
