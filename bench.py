@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--tiny", action="store_true", help="narrow UNet/VAE on a 96x128 frame (debugging only; invalid as a bench)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--vae", default="original", choices=["original", "light"],
+                    help="original = SD2 AutoencoderKL (BASELINE.json's configs); light = AutoencoderTiny, the reference CLI's default "
+                         "(predict.py:44-52) -- a different workload, reported under its own name")
     ap.add_argument("--no-batch2", action="store_true", help="skip the informational two-frames-in-flight measurement")
     return ap.parse_args()
 
@@ -94,8 +97,9 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ models / inputs
-def make_models(device, tiny: bool, dtype=torch.bfloat16, seed=1234):
-    """Random-init SD2-derived UNet (in_channels 8) and SD2 VAE; weights created directly on `device`."""
+def make_models(device, tiny: bool, dtype=torch.bfloat16, seed=1234, vae_kind="original"):
+    """Random-init SD2-derived UNet (in_channels 8) and SD2 VAE (or, vae_kind "light", the AutoencoderTiny the reference
+    CLI uses by default); weights created directly on `device`."""
     from oracle.sd2_modules import (AutoencoderKL, UNet2DConditionModel, UNetConfig, VAEConfig, tiny_unet_config,
                                     tiny_vae_config)
     from oracle.marigold_dc import make_empty_text_embedding
@@ -104,6 +108,9 @@ def make_models(device, tiny: bool, dtype=torch.bfloat16, seed=1234):
     torch.manual_seed(seed)
     with torch.device(device):
         unet, vae = UNet2DConditionModel(ucfg), AutoencoderKL(vcfg)
+        if vae_kind == "light":
+            from oracle.taesd import AutoencoderTiny
+            vae = AutoencoderTiny()
     unet, vae = unet.to(dtype).requires_grad_(False), vae.to(dtype).requires_grad_(False)
     ctx = make_empty_text_embedding(ucfg.cross_attention_dim, device=device, dtype=dtype)
     return unet, vae, ctx
@@ -116,9 +123,15 @@ def workload(tiny: bool):
     return w
 
 
-def config_dict(w, latent=None):
+def config_dict(w, latent=None, vae_kind="original"):
     """Identical for both arms (the reference arm runs on our arm's config)."""
     lat = f" (latent {latent[0]}x{latent[1]})" if latent else ""
+    if vae_kind == "light":
+        return {"workload": f"{w['H']}x{w['W']} RGB + {w['n_points']} sparse points, resolution {w['resolution']}{lat}, "
+                            f"{w['frame_steps']}-step guided completion, 1 frame in flight per GPU, random-init SD2 UNet (866M) / "
+                            "AutoencoderTiny (2.4M; the reference CLI's default --vae light, NOT the BASELINE.json config)",
+                "l2": "per-step working set >> 126 MB L2, no flush needed",
+                "frames_sharding": "independent frames per rank, no collective inside the step"}
     return {"workload": f"{w['H']}x{w['W']} RGB + {w['n_points']} sparse points, resolution {w['resolution']}{lat}, "
                         f"{w['frame_steps']}-step guided completion, 1 frame in flight per GPU, "
                         "random-init SD2 UNet (866M) / VAE decoder (49.5M)",
@@ -135,7 +148,7 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_reference_steps(n_steps: int, warmup: int, sample_res: int, tiny: bool):
+def cpu_reference_steps(n_steps: int, warmup: int, sample_res: int, tiny: bool, vae_kind: str = "original"):
     """Times guided steps of the reference algorithm (oracle port, fp32) on the host cores, on a bounded sample:
     the same frame at a lower processing resolution, scaled to the full workload by algorithmic FLOPs."""
     from depth_completion_b200.config import UNetConfig, VAEConfig
@@ -151,7 +164,7 @@ def cpu_reference_steps(n_steps: int, warmup: int, sample_res: int, tiny: bool):
     except AttributeError:
         ncpu = os.cpu_count() or 1
     torch.set_num_threads(max(1, ncpu))
-    unet, vae, ctx = make_models("cpu", tiny, dtype=torch.float32)
+    unet, vae, ctx = make_models("cpu", tiny, dtype=torch.float32, vae_kind=vae_kind)
     pipe = OraclePipeline(unet, vae, ctx)
     fr = make_frame(H=w["H"], W=w["W"], n_points=w["n_points"], max_depth=w["max_depth"])
     times = []
@@ -183,12 +196,12 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     w = workload(args.tiny)
     res = 128 if args.tiny else 224
-    r = cpu_reference_steps(max(1, args.steps), max(0, args.warmup), res, args.tiny)
+    r = cpu_reference_steps(max(1, args.steps), max(0, args.warmup), res, args.tiny, args.vae)
     line = {
         "impl": "reference", "metric": "guided_steps_per_sec", "value": r["value"], "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / r["value"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(w, (w["resolution"] * w["H"] // (8 * max(w["H"], w["W"])),
+        "config": config_dict(w, vae_kind=args.vae, latent=(w["resolution"] * w["H"] // (8 * max(w["H"], w["W"])),
                                   w["resolution"] * w["W"] // (8 * max(w["H"], w["W"])))),
         "cpu_baseline": {"value": r["value"], "unit": "steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -214,7 +227,7 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     w = workload(args.tiny)
-    unet, vae, ctx = make_models(dev, args.tiny)
+    unet, vae, ctx = make_models(dev, args.tiny, vae_kind=args.vae)
     pipe = MarigoldDepthCompletionPipeline(unet, vae)
     pipe.empty_text_embedding = ctx
     H, W, res, fs = w["H"], w["W"], w["resolution"], w["frame_steps"]
@@ -307,7 +320,7 @@ def run_ours(args):
     # (profiles/summarize_launches.py); only valid for the full-size default workload
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if not args.tiny and os.path.exists(tpath):
+    if not args.tiny and args.vae == "original" and os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
     roof = {"bound": "tensor", "kernel": "umma_gemm_pair_kernel + umma_gemm_kernel (gemm.cuh, cta_group::2 / ::1)",
@@ -341,13 +354,13 @@ def run_ours(args):
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
-            r = cpu_reference_steps(2, 1, 128 if args.tiny else 224, args.tiny)
+            r = cpu_reference_steps(2, 1, 128 if args.tiny else 224, args.tiny, args.vae)
             cpu = {"value": r["value"], "unit": "steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
         line = {
             "metric": "guided_steps_per_sec", "value": steps_per_s, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": config_dict(w, (eng.lh, eng.lw)),
+            "config": config_dict(w, (eng.lh, eng.lw), args.vae),
             "frames_per_sec_device": steps_per_s / fs,
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "e2e_two_frames_in_flight": two,

@@ -70,7 +70,42 @@ def unet_forward_flops(cfg: UNetConfig, lh: int, lw: int) -> float:
     return f
 
 
+def _tiny_block(c, h, w):
+    return 3 * _conv(c, c, h, w)
+
+
+def tiny_decoder_forward_flops(cfg: VAEConfig, lh: int, lw: int) -> float:
+    """AutoencoderTiny decoder: conv, [blocks, nearest x2, conv] per stage, conv to 3 channels."""
+    ch, nblk = cfg.block_out_channels, cfg.num_decoder_blocks
+    h, w = lh, lw
+    f = _conv(cfg.latent_channels, ch[0], h, w)
+    for i, n in enumerate(nblk):
+        f += n * _tiny_block(ch[i], h, w)
+        if i != len(nblk) - 1:
+            h, w = 2 * h, 2 * w
+            f += _conv(ch[i], ch[i], h, w)
+        else:
+            f += _conv(ch[i], cfg.out_channels, h, w)
+    return f
+
+
+def tiny_encoder_forward_flops(cfg: VAEConfig, ph: int, pw: int) -> float:
+    ch, nblk = cfg.block_out_channels, cfg.num_encoder_blocks
+    h, w = ph, pw
+    f = 0.0
+    for i, n in enumerate(nblk):
+        if i == 0:
+            f += _conv(cfg.in_channels, ch[0], h, w)
+        else:
+            h, w = h // 2, w // 2
+            f += _conv(ch[i], ch[i], h, w)
+        f += n * _tiny_block(ch[i], h, w)
+    return f + _conv(ch[-1], cfg.latent_channels, h, w)
+
+
 def vae_decoder_forward_flops(cfg: VAEConfig, lh: int, lw: int) -> float:
+    if cfg.kind == "tiny":
+        return tiny_decoder_forward_flops(cfg, lh, lw)
     boc, L = cfg.block_out_channels, cfg.layers_per_block
     nb = len(boc)
     h, w = lh, lw
@@ -91,6 +126,8 @@ def vae_decoder_forward_flops(cfg: VAEConfig, lh: int, lw: int) -> float:
 
 
 def vae_encoder_forward_flops(cfg: VAEConfig, ph: int, pw: int) -> float:
+    if cfg.kind == "tiny":
+        return tiny_encoder_forward_flops(cfg, ph, pw)
     boc, L = cfg.block_out_channels, cfg.layers_per_block
     nb = len(boc)
     h, w = ph, pw
