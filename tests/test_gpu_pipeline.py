@@ -217,3 +217,27 @@ def test_begin_frame_sparse_normalisation(models, cuda, norm):
     sp[0] = 0
     with pytest.raises(ValueError, match="No valid values found in mask"):
         eng.begin_frame(img, sp, x, 10.0, 0.6, norm)
+
+
+def test_sequence_driver_with_temporal_prior(models, cuda):
+    """video.complete_sequence (predict.py:585-700): with use_prev_latent every frame starts from the blend of the seeded
+    latent and the previous frame's result, exactly as chaining the calls by hand; without it frames are batched."""
+    from depth_completion_b200.pipeline import MarigoldDepthCompletionPipeline
+    from depth_completion_b200.synthetic import make_batch
+    from depth_completion_b200.video import complete_sequence
+
+    unet, vae, ctx, _, _ = models
+    b = make_batch(3, H=96, W=128, n_points=80)
+    img, sp = b["img"].to(cuda), b["sparse"].to(cuda)
+    pipe = MarigoldDepthCompletionPipeline(unet, vae)
+    pipe.empty_text_embedding = ctx
+    with pytest.warns(UserWarning):
+        dense, rng, last = complete_sequence(pipe, img, sp, 10.0, batch_size=2, use_prev_latent=True, beta=0.7, steps=6, resolution=128)
+    assert rng == (0, 3) and dense.shape == (3, 1, 96, 128) and torch.isfinite(dense).all()
+    prev, manual = None, []
+    for i in range(3):
+        d, prev = pipe(img[i:i + 1], sp[i:i + 1], 10.0, pred_latents_prev=prev, beta=0.7, steps=6, resolution=128)
+        manual.append(d)
+    assert torch.equal(dense, torch.cat(manual, 0)) and torch.equal(last, prev)
+    d2, rng2, _ = complete_sequence(pipe, img, sp, 10.0, batch_size=2, steps=6, resolution=128, rank=1, world=2)
+    assert rng2 == (2, 3) and d2.shape == (1, 1, 96, 128)

@@ -185,3 +185,22 @@ def test_two_rank_frame_sharding_gloo(tmp_path):
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_sequence_batches_mirror_the_reference_loop():
+    """depth_completion_b200.video.sequence_batches: predict.py:599-603 batching, :423-430 forced batch 1 with the
+    temporal prior, frames sharded over ranks only when they are independent."""
+    from depth_completion_b200.video import sequence_batches
+
+    assert sequence_batches(5, 2, False) == [(0, 2), (2, 4), (4, 5)]
+    assert sequence_batches(5, 4, True) == [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5)]
+    assert sequence_batches(0, 3, False) == []
+    got = [sequence_batches(64, 4, False, r, 8) for r in range(8)]
+    assert sum(len(g) for g in got) == 16 and got[0][0] == (0, 4) and got[7][-1] == (60, 64)
+    flat = [f for g in got for (s, e) in g for f in range(s, e)]
+    assert flat == list(range(64))
+    assert [sequence_batches(10, 4, False, r, 3) for r in range(3)] == [[(0, 4)], [(4, 7)], [(7, 10)]]
+    with pytest.raises(ValueError):
+        sequence_batches(8, 1, True, 0, 2)
+    with pytest.raises(ValueError):
+        sequence_batches(8, 0, False)
