@@ -16,9 +16,8 @@ for r in rows[1:]:
     d[r[mi]] = float(r[vi].replace(",", ""))
 L = list(launch.values())
 starts = [i for i, d in enumerate(L) if d["name"].endswith("begin_step_kernel")]
-step = L[starts[-1]:]
-if len(starts) > 1:
-    step = step[: starts[-1] - starts[-2]]
+# the last COMPLETE step: between the last two markers (the final one may be cut off by a launch-count / time limit)
+step = L[starts[-2]:starts[-1]] if len(starts) > 1 else L[starts[-1]:]
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
 for d in step:
     a = agg[d["name"]]
