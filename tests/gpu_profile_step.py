@@ -10,7 +10,7 @@ tiny = os.environ.get("TINY", "0") == "1"
 steps = int(os.environ.get("STEPS", "2"))
 dev = torch.device("cuda:0")
 w = bench.workload(tiny)
-unet, vae, ctx = bench.make_models(dev, tiny)
+unet, vae, ctx = bench.make_models(dev, tiny, vae_kind=os.environ.get("VAE", "original"))
 pipe = MarigoldDepthCompletionPipeline(unet, vae)
 pipe.empty_text_embedding = ctx
 fr = make_frame(H=w["H"], W=w["W"], n_points=w["n_points"], max_depth=w["max_depth"])
