@@ -204,3 +204,23 @@ def test_sequence_batches_mirror_the_reference_loop():
         sequence_batches(8, 1, True, 0, 2)
     with pytest.raises(ValueError):
         sequence_batches(8, 0, False)
+
+
+def test_vae_config_detection_kl_and_tiny():
+    """config.vae_config_from: AutoencoderKL vs AutoencoderTiny (diffusers config names), and what is rejected."""
+    from depth_completion_b200.config import vae_config_from
+    from oracle.sd2_modules import AutoencoderKL, tiny_vae_config
+    from oracle.taesd import AutoencoderTiny
+
+    kl = vae_config_from(AutoencoderKL(tiny_vae_config()))
+    assert kl.kind == "kl" and kl.block_out_channels == (64, 64, 128, 128) and abs(kl.scaling_factor - 0.18215) < 1e-9
+    tiny = vae_config_from(AutoencoderTiny())
+    assert tiny.kind == "tiny" and tiny.block_out_channels == (64, 64, 64, 64) and tiny.scaling_factor == 1.0
+    assert tiny.num_encoder_blocks == (1, 3, 3, 3) and tiny.num_decoder_blocks == (3, 3, 3, 1) and tiny.latent_magnitude == 3.0
+    d = dict(encoder_block_out_channels=(64, 64, 64, 64), decoder_block_out_channels=(64, 64, 64, 64), num_encoder_blocks=(1, 3, 3, 3),
+             num_decoder_blocks=(3, 3, 3, 1), latent_magnitude=3, scaling_factor=1.0, act_fn="relu")
+    assert vae_config_from(d).kind == "tiny"   # a diffusers-style config dict
+    with pytest.raises(ValueError):
+        vae_config_from({**d, "decoder_block_out_channels": (64, 64, 64, 32)})
+    with pytest.raises(ValueError):
+        vae_config_from({**d, "act_fn": "gelu"})
