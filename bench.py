@@ -116,6 +116,22 @@ def make_models(device, tiny: bool, dtype=torch.bfloat16, seed=1234, vae_kind="o
     return unet, vae, ctx
 
 
+def make_product_models(device, tiny: bool, vae_kind="original", seed=1234):
+    """Random-init weights of the same architectures for OUR arm, generated by the product package itself
+    (depth_completion_b200.synthetic.random_init_modules): nothing under oracle/ is imported on that arm."""
+    from depth_completion_b200.config import UNetConfig, VAEConfig
+    from depth_completion_b200.synthetic import random_init_modules
+
+    if tiny:
+        ucfg = UNetConfig(block_out_channels=(64, 128, 128, 128), attention_heads=(1, 2, 2, 2), cross_attention_dim=64)
+        vcfg = VAEConfig(block_out_channels=(64, 64, 128, 128))
+    else:
+        ucfg, vcfg = UNetConfig(), VAEConfig()
+    if vae_kind == "light":
+        vcfg = VAEConfig(block_out_channels=(64, 64, 64, 64), layers_per_block=0, norm_num_groups=0, scaling_factor=1.0, kind="tiny")
+    return random_init_modules(ucfg, vcfg, device, torch.bfloat16, seed)
+
+
 def workload(tiny: bool):
     w = dict(WORKLOAD)
     if tiny:
@@ -227,7 +243,7 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     w = workload(args.tiny)
-    unet, vae, ctx = make_models(dev, args.tiny, vae_kind=args.vae)
+    unet, vae, ctx = make_product_models(dev, args.tiny, args.vae)   # no oracle code on this arm
     pipe = MarigoldDepthCompletionPipeline(unet, vae)
     pipe.empty_text_embedding = ctx
     H, W, res, fs = w["H"], w["W"], w["resolution"], w["frame_steps"]

@@ -49,6 +49,8 @@ def unet_config_from(module) -> UNetConfig:
     if isinstance(module, UNetConfig):
         return module
     c = _get(module, "cfg") or _get(module, "config") or module
+    if isinstance(c, UNetConfig):
+        return c
     boc = tuple(_get(c, "block_out_channels"))
     heads = _get(c, "attention_heads") or _get(c, "attention_head_dim")
     heads = tuple(heads) if isinstance(heads, (list, tuple)) else (heads,) * len(boc)
@@ -67,6 +69,8 @@ def vae_config_from(module) -> VAEConfig:
     if isinstance(module, VAEConfig):
         return module
     c = _get(module, "cfg") or _get(module, "config") or module
+    if isinstance(c, VAEConfig):
+        return c
     if _get(c, "decoder_block_out_channels") is not None:  # AutoencoderTiny (diffusers config names)
         enc, dec = tuple(_get(c, "encoder_block_out_channels")), tuple(_get(c, "decoder_block_out_channels"))
         if enc != dec or len(set(dec)) != 1:

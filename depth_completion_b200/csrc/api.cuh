@@ -55,6 +55,19 @@ int mdc_num_weights(mdc_handle* h) { return h ? static_cast<int>(h->keys.size())
 const char* mdc_weight_key(mdc_handle* h, int i) {
   return (h && i >= 0 && i < static_cast<int>(h->keys.size())) ? h->keys[i].c_str() : nullptr;
 }
+int mdc_weight_shape(mdc_handle* h, int i, long long* shape4_host, int* ndim_host) {
+  return mdc::guarded([&] {
+    MDC_CHECK(h && shape4_host && ndim_host && i >= 0 && i < static_cast<int>(h->keys.size()), "bad argument");
+    const mdc::WeightSlot* s = h->e->wmap.at(h->keys[i]).front();
+    if (s->kind == mdc::W_CONV3 || s->kind == mdc::W_UPCONV) {
+      shape4_host[0] = s->out, shape4_host[1] = s->in, shape4_host[2] = 3, shape4_host[3] = 3, *ndim_host = 4;
+    } else if (s->kind == mdc::W_LIN) {
+      shape4_host[0] = s->out, shape4_host[1] = s->in, *ndim_host = 2;
+    } else {
+      shape4_host[0] = s->out, *ndim_host = 1;
+    }
+  });
+}
 int mdc_set_weight(mdc_handle* h, const char* key, const void* dev_ptr, const long long* shape_host, int ndim, int dtype) {
   return mdc::guarded([&] {
     MDC_CHECK(h && key && dev_ptr && shape_host, "null argument");

@@ -41,6 +41,7 @@ def _declare(l):
     l.mdc_num_weights.argtypes = [C.c_void_p]
     l.mdc_weight_key.argtypes = [C.c_void_p, C.c_int]
     l.mdc_weight_key.restype = C.c_char_p
+    l.mdc_weight_shape.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     l.mdc_set_weight.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_longlong), C.c_int, C.c_int]
     l.mdc_prepare.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     l.mdc_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -130,6 +131,15 @@ class StepEngine:
     def weight_keys(self):
         n = self.lib.mdc_num_weights(self._h)
         return [self.lib.mdc_weight_key(self._h, i).decode() for i in range(n)]
+
+    def weight_shapes(self) -> dict:
+        """{key: shape} of every parameter the tapes need (mdc_weight_shape)."""
+        out = {}
+        for i in range(self.lib.mdc_num_weights(self._h)):
+            shp, nd = (C.c_longlong * 4)(), C.c_int(0)
+            check(self.lib.mdc_weight_shape(self._h, i, shp, C.byref(nd)))
+            out[self.lib.mdc_weight_key(self._h, i).decode()] = tuple(shp[: nd.value])
+        return out
 
     def load_weights(self, unet_sd: dict, vae_sd: dict):
         """Hands every parameter the tapes need to mdc_set_weight (keys: 'unet.' / 'vae.' + diffusers name)."""

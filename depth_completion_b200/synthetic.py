@@ -67,3 +67,45 @@ def make_batch(n_frames: int, **kw):
     out = {k: torch.cat([f[k] for f in frames], 0) for k in ("img", "sparse", "gt", "holdout")}
     out["max_depth"] = frames[0]["max_depth"]
     return out
+
+
+class ParamBag:
+    """Stands in for a diffusers module where only `.config` and `.state_dict()` are read (which is all the drop-in
+    pipeline class reads): random-init weights of a given architecture without instantiating any model code."""
+
+    def __init__(self, cfg, state: dict):
+        self.config = cfg
+        self._state = state
+
+    def state_dict(self):
+        return self._state
+
+
+def random_init_modules(unet_cfg, vae_cfg, device, dtype=torch.bfloat16, seed: int = 1234):
+    """(unet, vae, empty_text_embedding) with random weights of the given architecture (BASELINE.json: "random-init SD2
+    UNet/VAE").  Parameter names and shapes come from the library itself (`mdc_weight_key` / `mdc_weight_shape` of a
+    throw-away handle on a small geometry).  Matrices ~ U(-1, 1) / sqrt(fan_in) (PyTorch's default bound), norm scales
+    1, biases small -- enough for finite, well-scaled activations; throughput does not depend on the values."""
+    from .engine import StepEngine
+
+    dev = torch.device(device)
+    eng = StepEngine(unet_cfg, vae_cfg, 1, 64, 64, 64, 1, dev)
+    shapes = eng.weight_shapes()
+    eng.close()
+    g = torch.Generator(device=dev).manual_seed(seed)
+    sds = {"unet": {}, "vae": {}}
+    for key in sorted(shapes):
+        shp = shapes[key]
+        prefix, name = key.split(".", 1)
+        if len(shp) >= 2:
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            t = (torch.rand(shp, device=dev, generator=g) * 2 - 1) / fan_in ** 0.5
+        elif name.endswith("weight"):   # GroupNorm / LayerNorm scale
+            t = torch.ones(shp, device=dev)
+        else:
+            t = (torch.rand(shp, device=dev, generator=g) * 2 - 1) * 0.02
+        sds[prefix][name] = t.to(dtype)
+    ctx = torch.randn(1, 2, unet_cfg.cross_attention_dim, device=dev, generator=g).to(dtype)
+    return ParamBag(unet_cfg, sds["unet"]), ParamBag(vae_cfg, sds["vae"]), ctx

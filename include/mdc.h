@@ -63,6 +63,9 @@ void mdc_destroy(mdc_handle* h);
  * (SURVEY.md Appendix A.5), e.g. "unet.down_blocks.0.resnets.0.conv1.weight". */
 int mdc_num_weights(mdc_handle* h);
 const char* mdc_weight_key(mdc_handle* h, int i);
+/* Logical shape of parameter i as the reference's modules hold it: [out,in,3,3] (conv3x3), [out,in] (linear and 1x1
+ * conv; a [out,in,1,1] tensor is accepted too) or [n] (bias / norm vectors).  shape4_host has room for 4 entries. */
+int mdc_weight_shape(mdc_handle* h, int i, long long* shape4_host, int* ndim_host);
 /* Re-packs one parameter (device pointer, contiguous, dtype MDC_DTYPE_*) into the library's layouts. */
 int mdc_set_weight(mdc_handle* h, const char* key, const void* dev_ptr, const long long* shape_host, int ndim,
                    int dtype);
