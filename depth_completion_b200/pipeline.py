@@ -37,20 +37,55 @@ class MarigoldDepthCompletionPipeline:
     def __init__(self, unet, vae, scheduler=None, text_encoder=None, tokenizer=None, prediction_type=None,
                  scale_invariant=True, shift_invariant=True, default_denoising_steps=None,
                  default_processing_resolution=None):
-        self.unet, self.vae, self.scheduler = unet, vae, scheduler
+        self._engines: dict = {}
+        self._sd_cache = None
+        self.unet, self.vae, self.scheduler = unet, vae, scheduler   # property setters below
         self.text_encoder, self.tokenizer = text_encoder, tokenizer
         self.prediction_type = prediction_type
         self.scale_invariant, self.shift_invariant = scale_invariant, shift_invariant
         self.default_denoising_steps = default_denoising_steps
         self.default_processing_resolution = default_processing_resolution
         self.empty_text_embedding = None
-        self.unet_cfg = unet_config_from(unet)
-        self.vae_cfg = vae_config_from(vae)
         p = next(iter(unet.state_dict().values()))
         self.device = p.device
         self.dtype = torch.bfloat16  # the engine computes in bf16 (BASELINE.json configs b-e)
-        self._engines: dict = {}
+
+    # The reference swaps modules on a live pipeline (predict.py:484-488 `pipe.vae = AutoencoderTiny...`, :491-494
+    # `pipe.scheduler = DDIMScheduler...`): re-derive the config and drop everything built from the old module.
+    def _invalidate(self):
+        for eng in getattr(self, "_engines", {}).values():
+            eng.close()
+        self._engines = {}
         self._sd_cache = None
+
+    @property
+    def unet(self):
+        return self._unet
+
+    @unet.setter
+    def unet(self, m):
+        self._unet = m
+        self.unet_cfg = unet_config_from(m)
+        self._invalidate()
+
+    @property
+    def vae(self):
+        return self._vae
+
+    @vae.setter
+    def vae(self, m):
+        self._vae = m
+        self.vae_cfg = vae_config_from(m)
+        self._invalidate()
+
+    @property
+    def scheduler(self):
+        return self._scheduler
+
+    @scheduler.setter
+    def scheduler(self, sch):
+        self._scheduler = sch
+        self._invalidate()
 
     # ------------------------------------------------------------------ plumbing
     def to(self, device):

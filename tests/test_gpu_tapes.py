@@ -229,3 +229,28 @@ def test_autoencoder_tiny_pipeline(cuda):
     rng = fr["max_depth"]
     ours, ref = ((dense - d32).abs().mean() / rng).item(), ((d16 - d32).abs().mean() / rng).item()
     assert ours < max(2.0 * ref, 1e-2) + 1e-2, f"mean |dense - fp32 oracle| / range: ours {ours:.4f}, torch-bf16 {ref:.4f}"
+
+
+def test_swapping_the_vae_on_a_live_pipeline(cuda):
+    """predict.py:484-488 assigns `pipe.vae = AutoencoderTiny(...)` AFTER building the pipeline: the drop-in class must
+    pick the new module up (config, weights, engine) instead of running on what it cached at construction."""
+    from helpers import build_models
+    from depth_completion_b200.pipeline import MarigoldDepthCompletionPipeline
+    from depth_completion_b200.synthetic import make_frame
+
+    unet, vae_kl, ctx, _, _ = build_models(cuda, tiny=True)
+    _, vae_tiny, _, eng = _tiny_vae_setup(cuda)
+    eng.close()
+    fr = make_frame(H=96, W=128, n_points=100, seed=3)
+    img, sp = fr["img"].to(cuda), fr["sparse"].to(cuda)
+    pipe = MarigoldDepthCompletionPipeline(unet, vae_kl)
+    pipe.empty_text_embedding = ctx
+    d_kl, _ = pipe(img, sp, 10.0, steps=4, resolution=128)
+    assert pipe.vae_cfg.kind == "kl"
+    pipe.vae = vae_tiny
+    assert pipe.vae_cfg.kind == "tiny" and not pipe._engines
+    d_tiny, _ = pipe(img, sp, 10.0, steps=4, resolution=128)
+    ref = MarigoldDepthCompletionPipeline(unet, vae_tiny)
+    ref.empty_text_embedding = ctx
+    d_ref, _ = ref(img, sp, 10.0, steps=4, resolution=128)
+    assert torch.equal(d_tiny, d_ref) and not torch.equal(d_tiny, d_kl)
