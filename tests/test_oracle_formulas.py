@@ -215,3 +215,27 @@ def test_autoencoder_tiny_structure():
     assert z.shape == (2, 4, 4, 6)
     y = m.decode(z * 50)  # tanh clamp keeps huge latents finite
     assert y.shape == x.shape and torch.isfinite(y).all()
+
+
+def test_oracle_reproduces_taesd_golden_fixture():
+    """tests/golden/tiny_96x128_taesd.npz: the same pinned run with the AutoencoderTiny VAE (the reference CLI default)."""
+    import importlib.util
+    import os
+
+    import numpy as np
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = np.load(os.path.join(here, "golden", "tiny_96x128_taesd.npz"))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    nt = torch.get_num_threads()
+    try:
+        out = mg.run_taesd()
+    finally:
+        torch.set_num_threads(nt)
+    assert np.array_equal(out["x_init"], gold["x_init"])
+    assert np.allclose(out["img_latents"], gold["img_latents"], rtol=1e-4, atol=1e-5)
+    assert np.allclose(out["step_v"][0], gold["step_v"][0], rtol=1e-3, atol=1e-4)
+    assert np.allclose(out["step_losses"][0], gold["step_losses"][0], rtol=1e-4)
+    assert np.allclose(out["step_x_adam"][0], gold["step_x_adam"][0], atol=1e-4)
