@@ -89,10 +89,17 @@ int mdc_begin(mdc_handle* h, const void* img_latents_bf16, const void* x_bf16, c
   });
 }
 int mdc_begin_frame(mdc_handle* h, const void* imgs, int img_dtype, int channels, const float* sparse, const void* x_bf16,
-                    float max_depth, float min_depth, int norm_const, float lr_latent, float lr_scaling) {
+                    float max_depth, float min_depth, int norm_mode, float lr_latent, float lr_scaling) {
   return mdc::guarded([&] {
     MDC_CHECK(h, "null handle");
-    h->e->begin_frame(imgs, img_dtype, channels, sparse, x_bf16, max_depth, min_depth, norm_const, lr_latent, lr_scaling);
+    h->e->begin_frame(imgs, img_dtype, channels, sparse, x_bf16, max_depth, min_depth, norm_mode, lr_latent, lr_scaling);
+  });
+}
+int mdc_set_options(mdc_handle* h, int projection, int inv, int opt, const float* loss_weights4_host, int kld_mode,
+                    float kld_weight, float percentile_lo, float percentile_hi) {
+  return mdc::guarded([&] {
+    MDC_CHECK(h, "null handle");
+    h->e->set_options(projection, inv, opt, loss_weights4_host, kld_mode, kld_weight, percentile_lo, percentile_hi);
   });
 }
 int mdc_run(mdc_handle* h, int n_steps) {
@@ -143,7 +150,7 @@ int mdc_dbg_forward(mdc_handle* h, int which, int step, const float* in_nchw, fl
     mdc::Tensor* out = which == 0 ? e->unet_out : e->dec_out;
     int s = step;
     MDC_CUDA(cudaMemcpy(e->counter, &s, 4, cudaMemcpyHostToDevice));
-    mdc::begin_step_kernel<<<1, 1024, 0, e->stream>>>(e->tables, e->counter, e->cur, e->temb_cur, e->lr_x, e->lr_s);
+    mdc::begin_step_kernel<<<1, 1024, 0, e->stream>>>(e->tables, e->counter, e->cur, e->temb_cur, e->opts);
     mdc::load_nchw(in, in->d, in_nchw, e->stream);
     e->run_ops(which == 0 ? e->unet_ops : e->dec_ops, false);
     mdc::store_nchw(out, out->d, out_nchw, e->stream);
@@ -217,8 +224,12 @@ int mdc_dbg_loss(mdc_handle* h, const float* dec_nchw, float* ddec_nchw, float* 
     mdc::load_nchw(e->dec_out, e->dec_out->d, dec_nchw, e->stream);
     mdc::TailGeom g{e->N, e->H, e->W, e->ph, e->pw, e->PPH, e->PPW, e->dec_out->ld};
     mdc::loss_points_kernel<<<e->N, 512, 0, e->stream>>>(e->dec_out->d, g, e->pt_idx, e->pt_val, e->pt_off, e->gminmax,
-                                                         e->accum, e->dmean);
-    const long long npix = 1LL * e->N * e->PPH * e->PPW;
+                                                         e->depth_minmax, e->opts, e->accum, e->dmean);
+    const long long npix = 1LL * e->N * e->PPH * e->PPW, opix = 1LL * e->N * e->H * e->W;
+    mdc::dense_map_kernel<<<static_cast<int>((opix + 255) / 256), 256, 0, e->stream>>>(e->dec_out->d, g, e->gminmax, e->depth_minmax,
+                                                                                      e->opts, e->accum, e->dn_map);
+    mdc::dense_loss_kernel<<<dim3(std::max(1, std::min(148, (e->H * e->W + 255) / 256)), e->N), 256, 0, e->stream>>>(
+        e->dec_out->d, g, e->gminmax, e->depth_minmax, e->opts, e->dn_map, e->gray_gx, e->gray_gy, e->accum, e->dmean);
     mdc::dec_grad_kernel<<<static_cast<int>((npix + 255) / 256), 256, 0, e->stream>>>(e->dmean, npix, e->dec_out->g);
     mdc::store_nchw(e->dec_out, e->dec_out->g, ddec_nchw, e->stream);
     MDC_CUDA(cudaGetLastError());
@@ -233,18 +244,19 @@ int mdc_dbg_update(mdc_handle* h, const float* v_nchw, const float* dz_nchw, con
     mdc::Engine* e = h->e;
     MDC_CHECK(e->begun, "mdc_begin first");
     const int hw = e->lh * e->lw, lat_pix = e->N * hw, pgrid = e->N * e->parts_per_img;
-    mdc::begin_step_kernel<<<1, 1024, 0, e->stream>>>(e->tables, e->counter, e->cur, e->temb_cur, e->lr_x, e->lr_s);
+    mdc::begin_step_kernel<<<1, 1024, 0, e->stream>>>(e->tables, e->counter, e->cur, e->temb_cur, e->opts);
     mdc::load_nchw(e->unet_out, e->unet_out->d, v_nchw, e->stream);
     mdc::x0_kernel<<<pgrid, 256, 0, e->stream>>>(e->unet_out->d, e->x, e->cur, e->N, hw, e->cfg.vae_scaling, e->dec_in->d,
-                                                e->eps_part);
+                                                e->eps_part, e->x1_part, e->x2_part);
     mdc::load_nchw(e->dec_in, e->dec_in->g, dz_nchw, e->stream);
     mdc::dx0_kernel<<<(lat_pix + 255) / 256, 256, 0, e->stream>>>(e->dec_in->g, e->cur, e->N, hw, e->cfg.vae_scaling,
                                                                   e->unet_out->g, e->dx_direct);
     mdc::load_nchw(e->unet_in, e->unet_in->g, dunet_in_nchw, e->stream);
-    mdc::grad_total_kernel<<<pgrid, 256, 0, e->stream>>>(e->dx_direct, e->unet_in->g, e->N, hw, e->gbuf, e->g_part);
+    mdc::grad_total_kernel<<<pgrid, 256, 0, e->stream>>>(e->dx_direct, e->unet_in->g, e->N, hw, e->gbuf, e->g_part, e->x,
+                                                         e->x1_part, e->x2_part, e->opts, e->accum);
     mdc::adam_ddim_kernel<<<pgrid, 256, 0, e->stream>>>(e->gbuf, e->eps_part, e->g_part, e->parts_per_img, e->unet_out->d,
                                                        e->cur, e->N, hw, e->x, e->m1, e->m2, e->accum, e->counter,
-                                                       e->x_adam_dbg);
+                                                       e->x_adam_dbg, e->opts);
     MDC_CUDA(cudaGetLastError());
     MDC_CUDA(cudaStreamSynchronize(e->stream));
   });

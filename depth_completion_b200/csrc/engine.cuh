@@ -16,6 +16,8 @@
 #include <map>
 #include <memory>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "../../include/mdc.h"
 #include "flash.cuh"
 #include "gemm.cuh"
@@ -395,6 +397,18 @@ struct Engine {
   int* pt_off = nullptr;
   float *gminmax = nullptr, *depth_minmax = nullptr;
   float lr_x = 0.05f, lr_s = 0.005f;
+  TailOpts h_opts{0, 0, 0, 0, 0.1f, 1.f, 1.f, 0.f, 0.f, 0.05f, 0.005f};  // defaults of marigold_dc.py:467-493; mdc_set_options
+  TailOpts* opts = nullptr;                                               // device copy, refreshed by begin()
+  float *x1_part = nullptr, *x2_part = nullptr;                           // partial sums of x, x^2 (kld)
+  float *dn_map = nullptr, *gray_gx = nullptr, *gray_gy = nullptr;        // edge / smooth losses: dense map, image gradients
+  bool have_gray = false;
+  float q_lo = 0.01f, q_hi = 0.99f;                                       // norm="percentile"
+  float *pc_vals = nullptr, *pc_sorted = nullptr, *pc_range = nullptr;
+  int* pc_counts = nullptr;
+  void* pc_tmp = nullptr;
+  size_t pc_tmp_bytes = 0;
+  void percentile_ranges(const float* sparse);
+  void set_options(int projection, int inv, int opt, const float* loss_weights4, int kld_mode, float kld_weight, float qlo, float qhi);
   bool prepared = false, begun = false;
   int steps_done = 0;
   long long launches = 0;
@@ -445,7 +459,7 @@ struct Engine {
   Tensor* vae_mid_attention(Tensor* h, const std::string& A);
   void encode(const void* imgs, int dtype, int channels, void* latents_out);
   void begin_frame(const void* imgs, int dtype, int channels, const float* sparse, const void* x0, float max_depth,
-                   float min_depth, int norm_const, float lrx, float lrs);
+                   float min_depth, int norm_mode, float lrx, float lrs);
   bf16* enc_lat = nullptr;       // img latents of the current frame (begin_frame)
   float* fr_guide = nullptr;     // normalised sparse depth of the current frame
   uint8_t* fr_mask = nullptr;
@@ -1291,6 +1305,9 @@ inline Engine::Engine(const mdc_config& c) : cfg(c) {
   dx_direct = arena.make<float>(lat), gbuf = arena.make<float>(lat);
   parts_per_img = std::max(1, std::min(64, (lh * lw + 255) / 256));
   eps_part = arena.make<float>(1ull * N * parts_per_img), g_part = arena.make<float>(1ull * N * parts_per_img);
+  x1_part = arena.make<float>(1ull * N * parts_per_img), x2_part = arena.make<float>(1ull * N * parts_per_img);
+  opts = arena.make<TailOpts>(1);
+  dn_map = arena.make<float>(1ull * N * H * W), gray_gx = arena.make<float>(1ull * N * H * W), gray_gy = arena.make<float>(1ull * N * H * W);
   dmean = arena.make<float>(1ull * N * PPH * PPW);
   pt_idx = arena.make<int>(1ull * N * H * W), pt_val = arena.make<float>(1ull * N * H * W);
   pt_off = arena.make<int>(N + 1);
@@ -1429,6 +1446,7 @@ inline void Engine::prepare(const void* ctx_bf16, const float* alphas_cumprod, c
   cudaFree(d_ts), cudaFree(emb), cudaFree(h1), cudaFree(h2);
   tables.sqrt_a = d_sqrt_a, tables.sqrt_1ma = d_sqrt_1ma, tables.sqrt_ap = d_sqrt_ap, tables.sqrt_1map = d_sqrt_1map;
   tables.temb_bias = temb_table, tables.temb_total = temb_total, tables.steps = n_steps;
+  MDC_CUDA(cudaMemcpy(opts, &h_opts, sizeof(h_opts), cudaMemcpyHostToDevice));
   MDC_CUDA(cudaGetLastError());
   prepared = true;
 }
@@ -1449,6 +1467,10 @@ inline void Engine::begin(const void* img_latents, const void* x0, const float* 
   MDC_CUDA(cudaMemcpyAsync(accum, &a, sizeof(a), cudaMemcpyHostToDevice, stream));
   MDC_CUDA(cudaMemcpyAsync(gminmax, gmm, 8ull * N, cudaMemcpyHostToDevice, stream));
   MDC_CUDA(cudaMemcpyAsync(depth_minmax, dmm, 8ull * N, cudaMemcpyHostToDevice, stream));
+  MDC_CHECK(h_opts.w_edge == 0.f || have_gray, "image must be provided for edge loss (use mdc_begin_frame)");
+  have_gray = false;
+  h_opts.lr_x = lrx, h_opts.lr_s = lrs;
+  MDC_CUDA(cudaMemcpyAsync(opts, &h_opts, sizeof(h_opts), cudaMemcpyHostToDevice, stream));
   // valid-point lists (host does the counting once per call; not on the per-step path)
   std::vector<uint8_t> hm(1ull * N * H * W);
   MDC_CUDA(cudaMemcpyAsync(hm.data(), mask, hm.size(), cudaMemcpyDeviceToHost, stream));
@@ -1596,7 +1618,7 @@ inline void Engine::step_launches() {
   const int hw = lh * lw, lat_pix = N * hw;
   const int pgrid = N * parts_per_img;
   TailGeom g{N, H, W, ph, pw, PPH, PPW, dec_out->ld};
-  launch_k(begin_step_kernel, dim3(1), dim3(1024), 0, stream, tables, counter, cur, temb_cur, lr_x, lr_s);
+  launch_k(begin_step_kernel, dim3(1), dim3(1024), 0, stream, tables, counter, cur, temb_cur, opts);
   launch_k(unet_input_kernel, dim3((lat_pix + 255) / 256), dim3(256), 0, stream, img_lat, x, N, hw, unet_in->d);
   auto dbg_points = [&](const char* tag) {  // MDC_DEBUG_SYNC: has anything scribbled over the compacted point list?
     static const bool on = getenv("MDC_DEBUG_SYNC") != nullptr;
@@ -1614,18 +1636,23 @@ inline void Engine::step_launches() {
   };
   run_ops(unet_ops, false);
   dbg_points("after unet fwd");
-  launch_k(x0_kernel, dim3(pgrid), dim3(256), 0, stream, unet_out->d, x, cur, N, hw, cfg.vae_scaling, dec_in->d, eps_part);
+  launch_k(x0_kernel, dim3(pgrid), dim3(256), 0, stream, unet_out->d, x, cur, N, hw, cfg.vae_scaling, dec_in->d, eps_part, x1_part, x2_part);
   run_ops(dec_ops, false);
   dbg_points("after decoder fwd");
-  launch_k(loss_points_kernel, dim3(N), dim3(512), 0, stream, dec_out->d, g, pt_idx, pt_val, pt_off, gminmax, accum, dmean);
-  const long long npix = 1LL * N * PPH * PPW;
+  launch_k(loss_points_kernel, dim3(N), dim3(512), 0, stream, dec_out->d, g, pt_idx, pt_val, pt_off, gminmax, depth_minmax, opts, accum, dmean);
+  const long long npix = 1LL * N * PPH * PPW, opix = 1LL * N * H * W;
+  // "edge" / "smooth" (marigold_dc.py:195-236); both return immediately unless loss_funcs lists them
+  launch_k(dense_map_kernel, dim3(static_cast<int>((opix + 255) / 256)), dim3(256), 0, stream, dec_out->d, g, gminmax, depth_minmax, opts,
+           accum, dn_map);
+  launch_k(dense_loss_kernel, dim3(std::max(1, std::min(148, (H * W + 255) / 256)), N), dim3(256), 0, stream, dec_out->d, g, gminmax,
+           depth_minmax, opts, dn_map, gray_gx, gray_gy, accum, dmean);
   launch_k(dec_grad_kernel, dim3(static_cast<int>((npix + 255) / 256)), dim3(256), 0, stream, dmean, npix, dec_out->g);
   run_ops(dec_ops, true);
   launch_k(dx0_kernel, dim3((lat_pix + 255) / 256), dim3(256), 0, stream, dec_in->g, cur, N, hw, cfg.vae_scaling, unet_out->g, dx_direct);
   run_ops(unet_ops, true);
-  launch_k(grad_total_kernel, dim3(pgrid), dim3(256), 0, stream, dx_direct, unet_in->g, N, hw, gbuf, g_part);
+  launch_k(grad_total_kernel, dim3(pgrid), dim3(256), 0, stream, dx_direct, unet_in->g, N, hw, gbuf, g_part, x, x1_part, x2_part, opts, accum);
   launch_k(adam_ddim_kernel, dim3(pgrid), dim3(256), 0, stream, gbuf, eps_part, g_part, parts_per_img, unet_out->d, cur, N, hw, x, m1, m2,
-                                              accum, counter, x_adam_dbg);
+                                              accum, counter, x_adam_dbg, opts);
 }
 
 inline void Engine::decode_final(float* dense_out) {
@@ -1641,7 +1668,8 @@ inline void Engine::decode_final(float* dense_out) {
   MDC_CUDA(cudaMemsetAsync(unet_out->d, 0, static_cast<size_t>(unet_out->rows()) * unet_out->ld * 2, stream));
   float* scratch = nullptr;
   MDC_CUDA(cudaMalloc(&scratch, 4ull * N * parts_per_img));
-  launch_k(x0_kernel, dim3(N * parts_per_img), dim3(256), 0, stream, unet_out->d, x, tmp, N, hw, cfg.vae_scaling, dec_in->d, scratch);
+  launch_k(x0_kernel, dim3(N * parts_per_img), dim3(256), 0, stream, unet_out->d, x, tmp, N, hw, cfg.vae_scaling, dec_in->d, scratch, static_cast<float*>(nullptr),
+           static_cast<float*>(nullptr));
   run_ops(dec_ops, false);
   TailGeom g{N, H, W, ph, pw, PPH, PPW, dec_out->ld};
   const long long tot = 1LL * N * H * W;
@@ -1669,11 +1697,48 @@ inline void Engine::encode(const void* imgs, int dtype, int channels, void* late
   MDC_CUDA(cudaStreamSynchronize(stream));
 }
 
+// norm="percentile" (marigold_dc.py:715-728): per sample, torch.quantile of the positive sparse values at (q_lo, q_hi):
+// compaction, one radix sort per sample (cub), linear-interpolated ranks.  Prologue only (once per frame).
+inline void Engine::percentile_ranges(const float* sparse) {
+  const size_t HW = 1ull * H * W;
+  if (!pc_vals) {
+    pc_vals = arena.make<float>(N * HW + 64), pc_sorted = arena.make<float>(HW + 64);
+    pc_range = arena.make<float>(2ull * MAXN), pc_counts = arena.make<int>(MAXN);
+    MDC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, pc_tmp_bytes, pc_vals, pc_sorted, static_cast<int>(HW), 0, 32, stream));
+    pc_tmp = arena.make<uint8_t>(pc_tmp_bytes + 256);
+  }
+  launch_k(compact_positive_kernel, dim3(N), dim3(1024), 0, stream, sparse, static_cast<int>(HW), pc_vals, pc_counts);
+  std::vector<int> cnt(N);
+  MDC_CUDA(cudaMemcpyAsync(cnt.data(), pc_counts, 4ull * N, cudaMemcpyDeviceToHost, stream));
+  MDC_CUDA(cudaStreamSynchronize(stream));
+  for (int n = 0; n < N; ++n) {
+    // the reference fails inside torch.quantile for an empty selection ("quantile() input tensor must be non-empty")
+    MDC_CHECK(cnt[n] > 0, "quantile() input tensor must be non-empty (sample %d has no valid sparse-depth point)", n);
+    size_t tb = pc_tmp_bytes;
+    MDC_CUDA(cub::DeviceRadixSort::SortKeys(pc_tmp, tb, pc_vals + n * HW, pc_sorted, cnt[n], 0, 32, stream));
+    launch_k(quantile_range_kernel, dim3(1), dim3(32), 0, stream, pc_sorted, cnt[n], q_lo, q_hi, pc_range + 2 * n);
+  }
+  MDC_CUDA(cudaGetLastError());
+}
+inline void Engine::set_options(int projection, int inv, int opt, const float* w4, int kld_mode, float kld_weight, float qlo, float qhi) {
+  MDC_CHECK(projection >= 0 && projection <= 2, "Unknown projection method: %d (0 linear, 1 log, 2 log10)", projection);
+  MDC_CHECK(opt >= 0 && opt <= 2, "Unknown optimizer: %d (0 adam, 1 sgd, 2 adagrad)", opt);
+  MDC_CHECK(kld_mode >= 0 && kld_mode <= 2, "Unknown mode: %d (0 off, 1 simple, 2 strict)", kld_mode);
+  MDC_CHECK(w4 && w4[0] + w4[1] + w4[2] + w4[3] > 0.f, "loss_funcs must contain at least one loss function");
+  MDC_CHECK(qlo >= 0.f && qlo <= 1.f && qhi >= 0.f && qhi <= 1.f, "percentile must be in [0, 1], but got (%g, %g)", qlo, qhi);
+  h_opts.projection = projection, h_opts.inv = inv ? 1 : 0, h_opts.opt = opt, h_opts.kld_mode = kld_mode, h_opts.kld_weight = kld_weight;
+  h_opts.w_l1 = w4[0], h_opts.w_l2 = w4[1], h_opts.w_edge = w4[2], h_opts.w_smooth = w4[3];
+  q_lo = qlo, q_hi = qhi;
+}
+
 // One call per frame: image prologue + sparse-depth normalisation + per-call state.
 // Raises "No valid values found in mask ..." for a sample without a positive sparse value, like utils.py:132-136.
 inline void Engine::begin_frame(const void* imgs, int dtype, int channels, const float* sparse, const void* x0,
-                                float max_depth, float min_depth, int norm_const, float lrx, float lrs) {
+                                float max_depth, float min_depth, int norm_mode, float lrx, float lrs) {
   MDC_CHECK(sparse && x0, "mdc_begin_frame: null pointer");
+  MDC_CHECK(norm_mode >= 0 && norm_mode <= 2, "Unknown norm method: %d (0 minmax, 1 const, 2 percentile)", norm_mode);
+  MDC_CHECK(!((h_opts.projection != 0 || h_opts.inv) && min_depth <= 1e-7f),
+            "min_depth must be > 1e-07 when projection is 'log' or 'log10' or inv is True, but got %g", min_depth);
   if (!enc_lat) {
     enc_lat = arena.make<bf16>(4ull * N * lh * lw + 64);
     fr_guide = arena.make<float>(1ull * N * H * W + 64);
@@ -1681,7 +1746,15 @@ inline void Engine::begin_frame(const void* imgs, int dtype, int channels, const
     fr_stats = arena.make<float>(5ull * MAXN);
   }
   encode(imgs, dtype, channels, enc_lat);
-  launch_k(sparse_norm_kernel, dim3(N), dim3(1024), 0, stream, sparse, H * W, min_depth, max_depth, norm_const, fr_guide, fr_mask, fr_stats);
+  if (norm_mode == 2) percentile_ranges(sparse);
+  if (h_opts.w_edge != 0.f) {
+    const long long opix = 1LL * N * H * W;
+    launch_k(gray_grad_kernel, dim3(static_cast<int>((opix + 255) / 256)), dim3(256), 0, stream, imgs, dtype == 0 ? 1 : 0, channels, N, H, W,
+             gray_gx, gray_gy);
+    have_gray = true;
+  }
+  launch_k(sparse_norm_kernel, dim3(N), dim3(1024), 0, stream, sparse, H * W, min_depth, max_depth, norm_mode, pc_range, h_opts.projection,
+           h_opts.inv, fr_guide, fr_mask, fr_stats);
   MDC_CUDA(cudaGetLastError());
   std::vector<float> st(5ull * N);
   MDC_CUDA(cudaMemcpyAsync(st.data(), fr_stats, st.size() * 4, cudaMemcpyDeviceToHost, stream));

@@ -34,13 +34,30 @@ struct StepAccum {             // per-sample accumulators (device memory)
   float s_m[MAXN], s_v[MAXN], t_m[MAXN], t_v[MAXN];
 };
 
+// Per-call options of the non-default branches of marigold_dc.py:467-493 (device memory, written by mdc_set_options /
+// mdc_begin so that the captured step graph stays valid when they change between calls).
+struct TailOpts {
+  int projection;    // 0 linear, 1 log, 2 log10 (get_projection_fn, marigold_dc.py:23-50)
+  int inv;           // 1: inverse depth (:743-749, :848-862)
+  int opt;           // 0 adam, 1 sgd, 2 adagrad (:776-789; torch defaults otherwise)
+  int kld_mode;      // 0 off, 1 simple, 2 strict (utils.py:28-86)
+  float kld_weight;
+  float w_l1, w_l2;  // how many times "l1" / "l2" appear in loss_funcs (:177-193 loops over the list)
+  float w_edge, w_smooth;  // likewise for "edge" / "smooth" (:195-236)
+  float lr_x, lr_s;  // learning rates of the latent and of scale / shift (:649, :776-783)
+};
+__device__ __forceinline__ float project_depth(float d, int projection) {
+  return projection == 1 ? logf(d) : projection == 2 ? log10f(d) : d;
+}
+
 // Select the step: fill StepCur and the current time-embedding biases.  One block.
 __global__ void begin_step_kernel(StepTables tb, int* __restrict__ counter, StepCur* __restrict__ cur,
-                                  float* __restrict__ temb_cur, float lr_x, float lr_s) {
+                                  float* __restrict__ temb_cur, const TailOpts* __restrict__ opts) {
   ptx::pdl_wait();
   ptx::pdl_launch();
   const int s = min(*counter, tb.steps - 1);
   if (threadIdx.x == 0) {
+    const float lr_x = opts->lr_x, lr_s = opts->lr_s;
     cur->sqrt_a = tb.sqrt_a[s], cur->sqrt_1ma = tb.sqrt_1ma[s];
     cur->sqrt_ap = tb.sqrt_ap[s], cur->sqrt_1map = tb.sqrt_1map[s];
     const double t = s + 1;
@@ -74,13 +91,14 @@ __global__ void unet_input_kernel(const bf16* __restrict__ img_lat, const bf16* 
 // x0 = sqrt(a) x - sqrt(1-a) v ; eps = sqrt(a) v + sqrt(1-a) x  (marigold_dc.py:813-826); z = x0 / scaling -> NHWC
 // eps_part[n*bpi + b] = partial sum of eps^2 (fixed-order reduction later).
 __global__ void x0_kernel(const bf16* __restrict__ v_nhwc, const bf16* __restrict__ x, const StepCur* __restrict__ cur,
-                          int N, int hw, float scaling, bf16* __restrict__ z_nhwc, float* __restrict__ eps_part) {
+                          int N, int hw, float scaling, bf16* __restrict__ z_nhwc, float* __restrict__ eps_part,
+                          float* __restrict__ x1_part, float* __restrict__ x2_part) {
   ptx::pdl_wait();
   ptx::pdl_launch();
   __shared__ float red[32];
   const int bpi = gridDim.x / N, n = blockIdx.x / bpi, b = blockIdx.x % bpi;
   const float sa = cur->sqrt_a, sb = cur->sqrt_1ma;
-  float acc = 0.f;
+  float acc = 0.f, xs1 = 0.f, xs2 = 0.f;
   for (int p = b * blockDim.x + threadIdx.x; p < hw; p += bpi * blockDim.x) {
     BF8 vv = *reinterpret_cast<const BF8*>(v_nhwc + (1LL * n * hw + p) * 8);
     const bf16* vb = reinterpret_cast<const bf16*>(&vv);
@@ -92,6 +110,7 @@ __global__ void x0_kernel(const bf16* __restrict__ v_nhwc, const bf16* __restric
       float x0 = bf16r(bf16r(sa * xv) - bf16r(sb * vf));
       float e = bf16r(bf16r(sa * vf) + bf16r(sb * xv));
       acc += e * e;
+      xs1 += xv, xs2 += xv * xv;
       ob[c] = __float2bfloat16(x0 / scaling);
       ob[4 + c] = __float2bfloat16(0.f);
     }
@@ -99,6 +118,11 @@ __global__ void x0_kernel(const bf16* __restrict__ v_nhwc, const bf16* __restric
   }
   acc = block_sum(acc, red);
   if (threadIdx.x == 0) eps_part[blockIdx.x] = acc;
+  if (x1_part) {  // sums of x and x^2 for the kld penalty (utils.py:69-77)
+    xs1 = block_sum(xs1, red);
+    xs2 = block_sum(xs2, red);
+    if (threadIdx.x == 0) x1_part[blockIdx.x] = xs1, x2_part[blockIdx.x] = xs2;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -129,7 +153,8 @@ __device__ __forceinline__ float affine_at(const bf16* __restrict__ dec, long lo
 // dmean[N, PPH, PPW] (fp32, zero on entry) receives d loss / d mean_c(dec) by atomics (4 taps per point).
 __global__ void loss_points_kernel(const bf16* __restrict__ dec, TailGeom g, const int* __restrict__ pt_idx,
                                    const float* __restrict__ pt_val, const int* __restrict__ pt_off,
-                                   const float* __restrict__ gminmax, StepAccum* __restrict__ acc,
+                                   const float* __restrict__ gminmax, const float* __restrict__ depth_minmax,
+                                   const TailOpts* __restrict__ opts, StepAccum* __restrict__ acc,
                                    float* __restrict__ dmean) {
   ptx::pdl_wait();
   ptx::pdl_launch();
@@ -139,6 +164,16 @@ __global__ void loss_points_kernel(const bf16* __restrict__ dec, TailGeom g, con
   const float cnt = static_cast<float>(p1 - p0);
   const float s = acc->scale[n], t = acc->shift[n];
   const float gmin = gminmax[2 * n], gmax = gminmax[2 * n + 1], range = gmax - gmin;
+  // depth-space conversion of the prediction (marigold_dc.py:842-862): metric range and its projected ends
+  const int projection = opts->projection, inv = opts->inv;
+  const bool convert = projection != 0 || inv != 0;
+  const float w_l1 = opts->w_l1, w_l2 = opts->w_l2;
+  const float dlo = depth_minmax[2 * n], dhi = depth_minmax[2 * n + 1];
+  float plo = project_depth(dlo, projection), phi = project_depth(dhi, projection);
+  if (inv) {
+    const float a = 1.f / phi, b = 1.f / plo;
+    plo = a, phi = b;
+  }
   const float sy = static_cast<float>(g.ph) / g.H, sx = static_cast<float>(g.pw) / g.W;
   float l_sum = 0.f, ds = 0.f, dt = 0.f;
   for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x) {
@@ -158,10 +193,22 @@ __global__ void loss_points_kernel(const bf16* __restrict__ dec, TailGeom g, con
     const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
     const float aff = bf16r(w00 * a00 + w01 * a01 + w10 * a10 + w11 * a11);
     const float pre = s * s * range * aff + t * t * gmin;
-    const float dense = fminf(fmaxf(pre, 0.f), 1.f);
+    float dense = fminf(fmaxf(pre, 0.f), 1.f);
+    float chain = 1.f;  // d(guide-space value) / d(normalised linear depth)
+    if (convert) {
+      const float metric = dense * (dhi - dlo) + dlo;
+      float pr = project_depth(metric, projection);
+      chain = (dhi - dlo) * (projection == 1 ? 1.f / metric : projection == 2 ? 0.4342944819f / metric : 1.f);
+      if (inv) {
+        pr = 1.f / pr;
+        chain *= -pr * pr;
+      }
+      dense = (pr - plo) / (phi - plo);
+      chain /= (phi - plo);
+    }
     const float diff = dense - guide;
-    l_sum += (fabsf(diff) + diff * diff) / cnt;
-    float dd = ((diff > 0.f) - (diff < 0.f) + 2.f * diff) / cnt;
+    l_sum += (w_l1 * fabsf(diff) + w_l2 * diff * diff) / cnt;
+    float dd = (w_l1 * ((diff > 0.f) - (diff < 0.f)) + w_l2 * 2.f * diff) / cnt * chain;
     if (pre < 0.f || pre > 1.f) dd = 0.f;  // clamp backward
     ds += dd * 2.f * s * range * aff;
     dt += dd * 2.f * t * gmin;
@@ -176,6 +223,158 @@ __global__ void loss_points_kernel(const bf16* __restrict__ dec, TailGeom g, con
   dt = block_sum(dt, red);
   if (threadIdx.x == 0) acc->loss[n] = l_sum, acc->s_grad[n] = ds, acc->t_grad[n] = dt;
 }
+// ---- "edge" / "smooth" terms (marigold_dc.py:195-236): dense losses on the whole H x W map.  Both kernels return at
+// once unless loss_funcs lists one of them (opts->w_edge / w_smooth), so the default path only pays two empty launches.
+// Prediction in the guide's space at one output pixel and d(that) / d(pre-clamp value); shared by both kernels.
+struct DensePix {
+  long long q[4];
+  float w[4];
+  bool in[4];
+  float aff, value, chain;
+};
+__device__ __forceinline__ DensePix dense_pixel(const bf16* __restrict__ dec, const TailGeom& g, int n, int Y, int X, float s,
+                                                float t, float gmin, float range, float dlo, float dhi, float plo,
+                                                float phi, int projection, int inv) {
+  DensePix r;
+  const float sy = static_cast<float>(g.ph) / g.H, sx = static_cast<float>(g.pw) / g.W;
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilinear_src(Y, sy, g.ph, y0, y1, ly);
+  bilinear_src(X, sx, g.pw, x0, x1, lx);
+  const long long base = 1LL * n * g.PPH * g.PPW;
+  r.q[0] = base + 1LL * y0 * g.PPW + x0, r.q[1] = base + 1LL * y0 * g.PPW + x1;
+  r.q[2] = base + 1LL * y1 * g.PPW + x0, r.q[3] = base + 1LL * y1 * g.PPW + x1;
+  r.w[0] = (1.f - ly) * (1.f - lx), r.w[1] = (1.f - ly) * lx, r.w[2] = ly * (1.f - lx), r.w[3] = ly * lx;
+  float a = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a += r.w[k] * affine_at(dec, g.ld_dec, r.q[k], r.in[k]);
+  r.aff = bf16r(a);
+  const float pre = s * s * range * r.aff + t * t * gmin;
+  float v = fminf(fmaxf(pre, 0.f), 1.f), chain = (pre < 0.f || pre > 1.f) ? 0.f : 1.f;
+  if (projection != 0 || inv != 0) {
+    const float metric = v * (dhi - dlo) + dlo;
+    float pr = project_depth(metric, projection);
+    chain *= (dhi - dlo) * (projection == 1 ? 1.f / metric : projection == 2 ? 0.4342944819f / metric : 1.f);
+    if (inv) {
+      pr = 1.f / pr;
+      chain *= -pr * pr;
+    }
+    v = (pr - plo) / (phi - plo);
+    chain /= (phi - plo);
+  }
+  r.value = v, r.chain = chain;
+  return r;
+}
+__device__ __forceinline__ void projected_ends(const float* __restrict__ depth_minmax, int n, int projection, int inv,
+                                               float& dlo, float& dhi, float& plo, float& phi) {
+  dlo = depth_minmax[2 * n], dhi = depth_minmax[2 * n + 1];
+  plo = project_depth(dlo, projection), phi = project_depth(dhi, projection);
+  if (inv) {
+    const float a = 1.f / phi, b = 1.f / plo;
+    plo = a, phi = b;
+  }
+}
+// dn[N, H, W] fp32: the dense prediction in the guide's space (:829-862).
+__global__ void dense_map_kernel(const bf16* __restrict__ dec, TailGeom g, const float* __restrict__ gminmax,
+                                 const float* __restrict__ depth_minmax, const TailOpts* __restrict__ opts,
+                                 const StepAccum* __restrict__ acc, float* __restrict__ dn) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  if (opts->w_edge == 0.f && opts->w_smooth == 0.f) return;
+  const long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+  if (i >= 1LL * g.N * g.H * g.W) return;
+  const int X = i % g.W, Y = (i / g.W) % g.H, n = i / (1LL * g.W * g.H);
+  float dlo, dhi, plo, phi;
+  projected_ends(depth_minmax, n, opts->projection, opts->inv, dlo, dhi, plo, phi);
+  const float gmin = gminmax[2 * n], gmax = gminmax[2 * n + 1];
+  dn[i] = dense_pixel(dec, g, n, Y, X, acc->scale[n], acc->shift[n], gmin, gmax - gmin, dlo, dhi, plo, phi, opts->projection,
+                      opts->inv).value;
+}
+// Loss and gradient of w_smooth * (mean|d_y dn| + mean|d_x dn|) + w_edge * (mean||d_x dn| - gx| + mean||d_y dn| - gy|)
+// with gx / gy the absolute forward differences of the grey image (gray_grad_kernel).  Pixel (Y, X) owns the pairs to
+// its right and below for the loss, and gathers the gradient of its four pairs.  grid = (blocks per image, N).
+__global__ void dense_loss_kernel(const bf16* __restrict__ dec, TailGeom g, const float* __restrict__ gminmax,
+                                  const float* __restrict__ depth_minmax, const TailOpts* __restrict__ opts,
+                                  const float* __restrict__ dn, const float* __restrict__ gx, const float* __restrict__ gy,
+                                  StepAccum* __restrict__ acc, float* __restrict__ dmean) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  const float we = opts->w_edge, ws = opts->w_smooth;
+  if (we == 0.f && ws == 0.f) return;
+  __shared__ float red[32];
+  const int n = blockIdx.y, HW = g.H * g.W;
+  const float s = acc->scale[n], t = acc->shift[n];
+  const float gmin = gminmax[2 * n], gmax = gminmax[2 * n + 1], range = gmax - gmin;
+  float dlo, dhi, plo, phi;
+  projected_ends(depth_minmax, n, opts->projection, opts->inv, dlo, dhi, plo, phi);
+  const float cx = 1.f / (1.f * g.H * (g.W - 1)), cy = 1.f / (1.f * (g.H - 1) * g.W);
+  const float* d = dn + 1LL * n * HW;
+  const float* ex = gx + 1LL * n * HW;
+  const float* ey = gy + 1LL * n * HW;
+  auto sgn = [](float v) { return static_cast<float>((v > 0.f) - (v < 0.f)); };
+  // d loss / d (a - b) of one pair with image gradient e and mean factor c
+  auto pair_grad = [&](float diff, float e, float c) { return c * sgn(diff) * (ws + we * sgn(fabsf(diff) - e)); };
+  float l_sum = 0.f, ds = 0.f, dt = 0.f;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    const int Y = p / g.W, X = p % g.W;
+    const float v = d[p];
+    float grad = 0.f;
+    if (X + 1 < g.W) {
+      const float diff = v - d[p + 1];
+      l_sum += cx * (ws * fabsf(diff) + we * fabsf(fabsf(diff) - ex[p]));
+      grad += pair_grad(diff, ex[p], cx);
+    }
+    if (X > 0) grad -= pair_grad(d[p - 1] - v, ex[p - 1], cx);
+    if (Y + 1 < g.H) {
+      const float diff = v - d[p + g.W];
+      l_sum += cy * (ws * fabsf(diff) + we * fabsf(fabsf(diff) - ey[p]));
+      grad += pair_grad(diff, ey[p], cy);
+    }
+    if (Y > 0) grad -= pair_grad(d[p - g.W] - v, ey[p - g.W], cy);
+    if (grad != 0.f) {
+      const DensePix px = dense_pixel(dec, g, n, Y, X, s, t, gmin, range, dlo, dhi, plo, phi, opts->projection, opts->inv);
+      const float dd = grad * px.chain;
+      ds += dd * 2.f * s * range * px.aff;
+      dt += dd * 2.f * t * gmin;
+      const float da = dd * s * s * range * 0.5f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (px.in[k] && px.w[k] != 0.f) atomicAdd(&dmean[px.q[k]], da * px.w[k]);
+    }
+  }
+  l_sum = block_sum(l_sum, red);
+  ds = block_sum(ds, red);
+  dt = block_sum(dt, red);
+  if (threadIdx.x == 0) atomicAdd(&acc->loss[n], l_sum), atomicAdd(&acc->s_grad[n], ds), atomicAdd(&acc->t_grad[n], dt);
+}
+// Absolute forward differences of the grey image the edge loss compares with (marigold_dc.py:199-216), computed on the
+// RAW images exactly as the reference does: 0.299 R + 0.587 G + 0.114 B in fp32 (0..255 for uint8 input), or the single
+// channel itself -- for a uint8 single channel the subtraction wraps modulo 256 like torch's uint8 arithmetic.
+__global__ void gray_grad_kernel(const void* __restrict__ img, int is_u8, int C, int N, int H, int W, float* __restrict__ gx,
+                                 float* __restrict__ gy) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  const long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+  if (i >= 1LL * N * H * W) return;
+  const int X = i % W, Y = (i / W) % H, n = i / (1LL * W * H);
+  const long long HW = 1LL * H * W;
+  auto px = [&](int c, int y, int x) -> float {
+    const long long o = (1LL * n * C + c) * HW + 1LL * y * W + x;
+    return is_u8 ? static_cast<float>(static_cast<const uint8_t*>(img)[o]) : static_cast<const float*>(img)[o];
+  };
+  auto gray = [&](int y, int x) -> float {
+    if (C == 1) return px(0, y, x);
+    return __fadd_rn(__fadd_rn(__fmul_rn(0.299f, px(0, y, x)), __fmul_rn(0.587f, px(1, y, x))), __fmul_rn(0.114f, px(2, y, x)));
+  };
+  auto adiff = [&](float a, float b) -> float {
+    if (C == 1 && is_u8) return static_cast<float>(static_cast<uint8_t>(static_cast<int>(a) - static_cast<int>(b)));
+    return fabsf(a - b);
+  };
+  const float v = gray(Y, X);
+  gx[i] = X + 1 < W ? adiff(v, gray(Y, X + 1)) : 0.f;
+  gy[i] = Y + 1 < H ? adiff(v, gray(Y + 1, X)) : 0.f;
+}
+
 // d dec[n, y, x, c] = dmean / 3 for c < 3 (bf16); clears dmean for the next step.
 __global__ void dec_grad_kernel(float* __restrict__ dmean, long long npix, bf16* __restrict__ ddec) {
   ptx::pdl_wait();
@@ -216,12 +415,35 @@ __global__ void dx0_kernel(const bf16* __restrict__ dz_nhwc, const StepCur* __re
 }
 
 // total latent gradient g = direct + UNet path (channels 4..7 of the UNet-input gradient); partial sums of g^2.
+// With the kld penalty (marigold_dc.py:238-241, utils.py:69-77) the latent also receives kld_weight * d dist / d x:
+// simple: dist = mean(x^2); strict: dist = (mu^2 + var - log(var + eps) - 1) / 2 with eps = finfo(bf16).eps.
 __global__ void grad_total_kernel(const float* __restrict__ dx_direct, const bf16* __restrict__ din_nhwc, int N, int hw,
-                                  float* __restrict__ gbuf, float* __restrict__ g_part) {
+                                  float* __restrict__ gbuf, float* __restrict__ g_part, const bf16* __restrict__ x,
+                                  const float* __restrict__ x1_part, const float* __restrict__ x2_part,
+                                  const TailOpts* __restrict__ opts, StepAccum* __restrict__ accum) {
   ptx::pdl_wait();
   ptx::pdl_launch();
   __shared__ float red[32];
   const int bpi = gridDim.x / N, n = blockIdx.x / bpi, b = blockIdx.x % bpi;
+  const int kld = opts->kld_mode;
+  float kc = 0.f, kb = 0.f;  // kld gradient = kc * x + kb
+  if (kld) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < bpi; ++k) s1 += x1_part[n * bpi + k], s2 += x2_part[n * bpi + k];
+    const float M = 4.f * hw, kw = bf16r(opts->kld_weight);
+    float dist;
+    if (kld == 1) {
+      dist = bf16r(s2 / M);
+      kc = 2.f * bf16r(kw / M);
+    } else {
+      const float mu = bf16r(s1 / M), var = bf16r(fmaxf(s2 / M - (s1 / M) * (s1 / M), 0.f)), eps = 0.0078125f;
+      dist = 0.5f * (mu * mu + var - logf(var + eps) - 1.f);
+      const float r = 1.f - 1.f / (var + eps);
+      kc = kw / M * r;
+      kb = kw / M * mu * (1.f - r);
+    }
+    if (b == 0 && threadIdx.x == 0) accum->loss[n] += opts->kld_weight * dist;
+  }
   float acc = 0.f;
   for (int p = b * blockDim.x + threadIdx.x; p < hw; p += bpi * blockDim.x) {
     BF8 in = *reinterpret_cast<const BF8*>(din_nhwc + (1LL * n * hw + p) * 8);
@@ -230,6 +452,7 @@ __global__ void grad_total_kernel(const float* __restrict__ dx_direct, const bf1
     for (int c = 0; c < 4; ++c) {
       long long j = (1LL * n * 4 + c) * hw + p;
       float gg = bf16r(dx_direct[j] + __bfloat162float(ib[4 + c]));
+      if (kld) gg = bf16r(gg + bf16r(kc * __bfloat162float(x[j]) + kb));
       gbuf[j] = gg;
       acc += gg * gg;
     }
@@ -238,16 +461,19 @@ __global__ void grad_total_kernel(const float* __restrict__ dx_direct, const bf1
   if (threadIdx.x == 0) g_part[blockIdx.x] = acc;
 }
 
-// grad-norm rescale (marigold_dc.py:881-894) + torch.optim.Adam foreach update in the parameter dtype (bf16 latent,
-// fp32 scale/shift; :897) + DDIM prev_sample with the stale v and the updated x (:901-904).  Advances the step counter.
+// grad-norm rescale (marigold_dc.py:881-894) + torch.optim.Adam (or SGD / Adagrad, :776-789) foreach update in the
+// parameter dtype (bf16 latent, fp32 scale/shift; :897) + DDIM prev_sample with the stale v and the updated x (:901-904).  Advances the step counter.
 __global__ void adam_ddim_kernel(const float* __restrict__ gbuf, const float* __restrict__ eps_part,
                                  const float* __restrict__ g_part, int parts_per_img, const bf16* __restrict__ v_nhwc,
                                  const StepCur* __restrict__ cur, int N, int hw, bf16* __restrict__ x,
                                  bf16* __restrict__ m1, bf16* __restrict__ m2, StepAccum* __restrict__ acc,
-                                 int* __restrict__ counter, bf16* __restrict__ x_adam_dbg) {
+                                 int* __restrict__ counter, bf16* __restrict__ x_adam_dbg,
+                                 const TailOpts* __restrict__ opts) {
   ptx::pdl_wait();
   ptx::pdl_launch();
   const int bpi = gridDim.x / N, n = blockIdx.x / bpi, b = blockIdx.x % bpi;
+  const int opt = opts->opt;
+  const float lr_x = opts->lr_x, lr_s = opts->lr_s;
   float e2 = 0.f, g2 = 0.f;
   for (int k = 0; k < parts_per_img; ++k) e2 += eps_part[n * parts_per_img + k], g2 += g_part[n * parts_per_img + k];
   const float en = bf16r(sqrtf(e2)), gn = bf16r(sqrtf(g2));
@@ -262,13 +488,21 @@ __global__ void adam_ddim_kernel(const float* __restrict__ gbuf, const float* __
       const long long j = (1LL * n * 4 + c) * hw + p;
       const float g = bf16r(gbuf[j] * factor);
       float m = __bfloat162float(m1[j]), v2 = __bfloat162float(m2[j]), xv = __bfloat162float(x[j]);
-      m = bf16r(m + 0.1f * (g - m));                      // exp_avg.lerp_(grad, 1 - beta1)
-      v2 = bf16r(v2 * 0.999f);                            // exp_avg_sq.mul_(beta2)
-      v2 = bf16r(v2 + 0.001f * g * g);                    //           .addcmul_(grad, grad, 1 - beta2)
-      float den = bf16r(sqrtf(v2));
-      den = bf16r(den / bc2s);
-      den = bf16r(den + 1e-8f);
-      xv = bf16r(xv - step_size * (m / den));             // param.addcdiv_(exp_avg, denom, -step_size)
+      if (opt == 0) {
+        m = bf16r(m + 0.1f * (g - m));                      // exp_avg.lerp_(grad, 1 - beta1)
+        v2 = bf16r(v2 * 0.999f);                            // exp_avg_sq.mul_(beta2)
+        v2 = bf16r(v2 + 0.001f * g * g);                    //           .addcmul_(grad, grad, 1 - beta2)
+        float den = bf16r(sqrtf(v2));
+        den = bf16r(den / bc2s);
+        den = bf16r(den + 1e-8f);
+        xv = bf16r(xv - step_size * (m / den));             // param.addcdiv_(exp_avg, denom, -step_size)
+      } else if (opt == 1) {                                // torch.optim.SGD, no momentum: param.add_(grad, alpha=-lr)
+        xv = bf16r(xv - lr_x * g);
+      } else {                                              // torch.optim.Adagrad (foreach): lr_decay 0, eps 1e-10
+        v2 = bf16r(v2 + g * g);                             // state_sum.addcmul_(grad, grad, value=1)
+        const float sd = bf16r(bf16r(sqrtf(v2)) + 1e-10f);  // std = state_sum.sqrt().add_(eps)
+        xv = bf16r(xv + bf16r(-lr_x * g) / sd);             // param.addcdiv_(grad * -clr, std)
+      }
       m1[j] = __float2bfloat16(m), m2[j] = __float2bfloat16(v2);
       if (x_adam_dbg) x_adam_dbg[j] = __float2bfloat16(xv);
       const float vf = __bfloat162float(vb[c]);
@@ -277,14 +511,24 @@ __global__ void adam_ddim_kernel(const float* __restrict__ gbuf, const float* __
       x[j] = __float2bfloat16(bf16r(sap * x0) + bf16r(sbp * e));
     }
   }
-  if (b == 0 && threadIdx.x == 0) {  // fp32 Adam on scale / shift of sample n
+  if (b == 0 && threadIdx.x == 0) {  // fp32 update of scale / shift of sample n
     const float ss = cur->adam_step_size_s;
     float gs = acc->s_grad[n], gt = acc->t_grad[n];
-    float sm = acc->s_m[n] + 0.1f * (gs - acc->s_m[n]), sv = acc->s_v[n] * 0.999f + 0.001f * gs * gs;
-    float tm = acc->t_m[n] + 0.1f * (gt - acc->t_m[n]), tv = acc->t_v[n] * 0.999f + 0.001f * gt * gt;
-    acc->scale[n] -= ss * (sm / (sqrtf(sv) / bc2s + 1e-8f));
-    acc->shift[n] -= ss * (tm / (sqrtf(tv) / bc2s + 1e-8f));
-    acc->s_m[n] = sm, acc->s_v[n] = sv, acc->t_m[n] = tm, acc->t_v[n] = tv;
+    if (opt == 0) {
+      float sm = acc->s_m[n] + 0.1f * (gs - acc->s_m[n]), sv = acc->s_v[n] * 0.999f + 0.001f * gs * gs;
+      float tm = acc->t_m[n] + 0.1f * (gt - acc->t_m[n]), tv = acc->t_v[n] * 0.999f + 0.001f * gt * gt;
+      acc->scale[n] -= ss * (sm / (sqrtf(sv) / bc2s + 1e-8f));
+      acc->shift[n] -= ss * (tm / (sqrtf(tv) / bc2s + 1e-8f));
+      acc->s_m[n] = sm, acc->s_v[n] = sv, acc->t_m[n] = tm, acc->t_v[n] = tv;
+    } else if (opt == 1) {
+      acc->scale[n] -= lr_s * gs;
+      acc->shift[n] -= lr_s * gt;
+    } else {
+      const float sv = acc->s_v[n] + gs * gs, tv = acc->t_v[n] + gt * gt;
+      acc->scale[n] += (-lr_s * gs) / (sqrtf(sv) + 1e-10f);
+      acc->shift[n] += (-lr_s * gt) / (sqrtf(tv) + 1e-10f);
+      acc->s_v[n] = sv, acc->t_v[n] = tv;
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *counter = *counter + 1;
 }
@@ -383,9 +627,14 @@ __global__ void preprocess_image_kernel(const void* __restrict__ img, PreGeom g,
 // "const": (lo, hi) = (min_depth, max_depth); guide = (clamp(sparse) - lo) / (hi - lo).  Also the masked min / max of
 // the guide that _affine_to_metric recomputes every step (:326).  One block per sample, fp32 like the reference.
 // out_stats[n] = {lo, hi, gmin, gmax, n_valid}.
+// norm_mode 2 ("percentile", :715-728): (lo, hi) come from range_in[2n], range_in[2n+1] (quantile_range_kernel) and
+// are then treated like the min / max of "minmax".  projection / inv (:737-756): lo, hi and the clamped values go
+// through log / log10 and 1 / x (swapping the ends) before the normalisation; out_stats keeps the metric lo / hi.
 __global__ void sparse_norm_kernel(const float* __restrict__ sparse, int HW, float min_depth, float max_depth,
-                                   int norm_const, float* __restrict__ guide, uint8_t* __restrict__ mask,
+                                   int norm_mode, const float* __restrict__ range_in, int projection, int inv,
+                                   float* __restrict__ guide, uint8_t* __restrict__ mask,
                                    float* __restrict__ out_stats) {
+  const int norm_const = norm_mode == 1;
   ptx::pdl_wait();
   ptx::pdl_launch();
   __shared__ float s_lo[32], s_hi[32];
@@ -415,12 +664,20 @@ __global__ void sparse_norm_kernel(const float* __restrict__ sparse, int HW, flo
   int total;
   block_minmax(lo, hi, cnt, mlo, mhi, total);
   float clo = norm_const ? min_depth : mlo, chi = norm_const ? max_depth : mhi;  // clamp range of the raw values
+  if (norm_mode == 2) clo = range_in[2 * n], chi = range_in[2 * n + 1];
   float nlo = clo, nhi = chi;                                                      // normalisation range
   if (!norm_const) nlo = fmaxf(clo, min_depth), nhi = fminf(chi, max_depth);
+  float plo = project_depth(nlo, projection), phi = project_depth(nhi, projection);
+  if (inv) {
+    const float a = 1.f / phi, b = 1.f / plo;
+    plo = a, phi = b;
+  }
   float glo = INFINITY, ghi = -INFINITY;
   for (int i = threadIdx.x; i < HW; i += blockDim.x) {
     const float v = sp[i];
-    const float g = (fminf(fmaxf(v, clo), chi) - nlo) / (nhi - nlo);
+    float pv = project_depth(fminf(fmaxf(v, clo), chi), projection);
+    if (inv) pv = 1.f / pv;
+    const float g = (pv - plo) / (phi - plo);
     guide[1LL * n * HW + i] = g;
     const bool m = v > 0.f;
     mask[1LL * n * HW + i] = m ? 1 : 0;
@@ -433,6 +690,38 @@ __global__ void sparse_norm_kernel(const float* __restrict__ sparse, int HW, flo
     float* o = out_stats + 5 * n;
     o[0] = nlo, o[1] = nhi, o[2] = ogl, o[3] = ogh, o[4] = static_cast<float>(total);
   }
+}
+
+// norm="percentile" (marigold_dc.py:715-728): the positive values of each sample, compacted (any order) into
+// vals[n * HW ...]; counts[n] = how many.  One block per sample.
+__global__ void compact_positive_kernel(const float* __restrict__ sparse, int HW, float* __restrict__ vals,
+                                        int* __restrict__ counts) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  __shared__ int s_count;
+  const int n = blockIdx.x;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float v = sparse[1LL * n * HW + i];
+    if (v > 0.f) vals[1LL * n * HW + atomicAdd(&s_count, 1)] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) counts[n] = s_count;
+}
+// torch.quantile(sorted, q) with linear interpolation (aten Sorting.cpp quantile_compute): rank = q * (n - 1) in
+// fp32, lerp between the neighbours with torch's lerp formula (w < 0.5 ? a + w (b - a) : b - (b - a)(1 - w)).
+__global__ void quantile_range_kernel(const float* __restrict__ sorted, int count, float q_lo, float q_hi,
+                                      float* __restrict__ range_out) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  if (threadIdx.x >= 2 || blockIdx.x != 0) return;
+  const float q = threadIdx.x == 0 ? q_lo : q_hi;
+  const float rank = q * static_cast<float>(count - 1);
+  const float below = floorf(rank), w = rank - below;
+  const int i0 = static_cast<int>(below), i1 = static_cast<int>(ceilf(rank));
+  const float a = sorted[i0], b = sorted[i1];
+  range_out[threadIdx.x] = w < 0.5f ? a + w * (b - a) : b - (b - a) * (1.f - w);
 }
 
 // img_latent = mode * scaling (marigold_dc.py:696-698): first `C` channels of the NHWC moments -> NCHW bf16

@@ -52,6 +52,7 @@ def _declare(l):
     l.mdc_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     l.mdc_begin_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                   C.c_int, C.c_float, C.c_float]
+    l.mdc_set_options.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float]
     l.mdc_launch_count.argtypes = [C.c_void_p]
     l.mdc_launch_count.restype = C.c_longlong
     l.mdc_device_bytes.argtypes = [C.c_void_p]
@@ -214,6 +215,26 @@ class StepEngine:
             raise ValueError(f"Image dtype={imgs.dtype} is not supported.")
         return imgs.to(self.device).contiguous(), dt
 
+    PROJECTIONS = {"linear": 0, "log": 1, "log10": 2}
+    OPTIMIZERS = {"adam": 0, "sgd": 1, "adagrad": 2}
+    KLD_MODES = {"simple": 1, "strict": 2}
+    NORMS = {"minmax": 0, "const": 1, "percentile": 2}
+
+    def set_options(self, projection="linear", inv=False, opt="adam", loss_funcs=("l1", "l2"), kld=False, kld_weight=0.1,
+                    kld_mode="simple", percentile=(0.01, 0.99)):
+        """Non-default branches of the reference call (mdc_set_options; marigold_dc.py:467-493): they apply to the next
+        begin / begin_frame.  loss_funcs is the reference's list (a term listed twice counts twice, :177-236)."""
+        if projection not in self.PROJECTIONS:
+            raise ValueError(f"Unknown projection method: {projection}")
+        if opt not in self.OPTIMIZERS:
+            raise ValueError(f"Unknown optimizer: {opt}")
+        if kld and kld_mode not in self.KLD_MODES:
+            raise ValueError(f"Unknown mode: {kld_mode}")
+        w = np.array([sum(f == k for f in loss_funcs) for k in ("l1", "l2", "edge", "smooth")], dtype=np.float32)
+        check(self.lib.mdc_set_options(self._h, self.PROJECTIONS[projection], int(bool(inv)), self.OPTIMIZERS[opt],
+                                       w.ctypes.data_as(C.c_void_p), self.KLD_MODES[kld_mode] if kld else 0,
+                                       float(kld_weight), float(percentile[0]), float(percentile[1])))
+
     def begin_frame(self, imgs, sparses, x, max_depth, min_depth=0.0, norm="minmax", lr_latent=0.05, lr_scaling=0.005):
         """The per-frame prologue in one library call (mdc_begin_frame): image preprocess + VAE encoder, sparse-depth
         normalisation, per-call state (marigold_dc.py:687-789).  Raises ValueError for a sample with an empty mask."""
@@ -223,9 +244,9 @@ class StepEngine:
         assert sparses.numel() == self.n * self.H * self.W and tuple(x.shape) == (self.n, 4, self.lh, self.lw)
         try:
             check(self.lib.mdc_begin_frame(self._h, ptr(imgs), dt, int(imgs.shape[1]), ptr(sparses), ptr(x), float(max_depth),
-                                           float(min_depth), 1 if norm == "const" else 0, float(lr_latent), float(lr_scaling)))
+                                           float(min_depth), self.NORMS[norm], float(lr_latent), float(lr_scaling)))
         except MdcError as e:
-            if "No valid values found in mask" in str(e):
+            if "No valid values found in mask" in str(e) or "min_depth must be" in str(e):
                 raise ValueError(str(e)) from None
             raise
 

@@ -4,8 +4,7 @@
 
 Same constructor and call signature, same return tuple `(denses [N,1,H,W] fp32 metric, pred_latents [N,4,EH,EW])`,
 same ValueError conventions.  Non-default branches the north star leaves out of scope
-(log/inverse projection, percentile norm, sgd/adagrad, kld/edge/smooth losses, closed-form / no-grad paths,
-per-input training) raise NotImplementedError instead of silently doing something else.
+(closed-form / no-grad paths, per-input training, non-bilinear interpolation) raise NotImplementedError instead of silently doing something else.
 
 The host keeps, in PyTorch, only what runs once per call: argument checks, image resize/pad, the VAE *encoder*,
 sparse-depth normalisation and the seeded initial latent (marigold_dc.py:659-756).
@@ -187,22 +186,16 @@ class MarigoldDepthCompletionPipeline:
             raise ValueError(f"Unknown optimizer: {opt}")
         # --- branches outside the hot path this library implements (OUT OF SCOPE rows)
         unsupported = []
-        if projection != "linear" or inv:
-            unsupported.append("projection/inv")
-        if norm == "percentile":
-            unsupported.append("norm='percentile'")
-        if opt != "adam":
-            unsupported.append(f"opt='{opt}'")
-        if kld:
-            unsupported.append("kld")
-        if sorted(loss_funcs) != ["l1", "l2"]:
-            unsupported.append(f"loss_funcs={loss_funcs}")
+        if len(loss_funcs) == 0:
+            raise ValueError("loss_funcs must contain at least one loss function")  # compute_loss, marigold_dc.py:171-172
+        if kld and kld_mode not in ("simple", "strict"):
+            raise ValueError(f"Unknown mode: {kld_mode}")                           # utils.py:78-79
         if not train_latents or closed_form or train_method != "per-step":
             unsupported.append("train_latents=False / closed_form / per-input")
         if interp_mode != "bilinear":
             unsupported.append(f"interp_mode='{interp_mode}'")
         if unsupported:
-            raise NotImplementedError("outside the B200 hot path (guided per-step Adam, linear projection, l1+l2): "
+            raise NotImplementedError("outside the B200 hot path (guided per-step optimisation of the latent): "
                                       + ", ".join(unsupported))
         ph, pw, pad_h, pad_w = processed_geometry(H, W, resolution)
         if ((ph + pad_h) // 8, (pw + pad_w) // 8) != (EH, EW):
@@ -222,6 +215,7 @@ class MarigoldDepthCompletionPipeline:
         # marigold_dc.py:687-789 inside libmdc_b200.so (mdc_begin_frame): image preprocess + VAE encoder, sparse-depth
         # normalisation (mask, masked min / max, clamp, guide and its min / max), per-call optimiser state.
         # An empty mask raises ValueError like utils.py:132-136.
+        eng.set_options(projection, inv, opt, loss_funcs, kld, kld_weight, kld_mode, percentile)
         eng.begin_frame(imgs, sparses, x, max_depth, min_depth, norm, lr_latent, lr_scaling)
         if _begin_only:  # bench.py: leave the engine at step 0 with everything resident in HBM
             return None, None

@@ -90,14 +90,26 @@ int mdc_encode(mdc_handle* h, const void* imgs, int dtype, int channels, void* l
 int mdc_begin(mdc_handle* h, const void* img_latents_bf16, const void* x_bf16, const float* guide, const uint8_t* mask,
               const float* guide_minmax_host, const float* depth_minmax_host, float lr_latent, float lr_scaling);
 
-/* The whole per-frame prologue in one call (marigold_dc.py:687-756, linear projection): mdc_encode on `imgs`, then the
- * sparse-depth normalisation on the device -- mask = sparse > 0, per-sample masked min / max ("minmax", norm_const =
- * 0) or the constant range [min_depth, max_depth] (norm_const = 1), clamp, guide = (d - lo) / (hi - lo), masked
- * min / max of the guide -- then mdc_begin with those.  sparse: device [N,1,H,W] fp32 metres (0 = missing); x_bf16:
+/* Per-call options of the non-default branches of the reference call (marigold_dc.py:467-493); they apply to the next
+ * mdc_begin / mdc_begin_frame and stay until changed.  Defaults: linear, no inverse, adam, l1 + l2, no kld, (0.01, 0.99).
+ *   projection   0 "linear", 1 "log", 2 "log10" (get_projection_fn, :23-50), inv != 0: inverse depth (:743-749, :842-862)
+ *   opt          0 "adam", 1 "sgd", 2 "adagrad" with torch's default hyper-parameters (:776-789)
+ *   loss_weights4_host  how many times "l1", "l2", "edge", "smooth" appear in loss_funcs (compute_loss, :171-236, sums
+ *                the listed terms); "edge" needs the images, i.e. mdc_begin_frame rather than mdc_begin
+ *   kld_mode     0 off, 1 "simple", 2 "strict" (utils.py:28-86), added as kld_weight * kld (:238-241)
+ *   percentile_lo / hi   the quantiles of norm = "percentile" (:715-728) */
+int mdc_set_options(mdc_handle* h, int projection, int inv, int opt, const float* loss_weights4_host, int kld_mode,
+                    float kld_weight, float percentile_lo, float percentile_hi);
+
+/* The whole per-frame prologue in one call (marigold_dc.py:687-756): mdc_encode on `imgs`, then the
+ * sparse-depth normalisation on the device -- mask = sparse > 0, per-sample masked min / max ("minmax", norm_mode =
+ * 0), the constant range [min_depth, max_depth] (norm_mode = 1) or per-sample quantiles of the valid values
+ * ("percentile", norm_mode = 2), clamp, projection / inverse as set by mdc_set_options, guide = (d - lo) / (hi - lo),
+ * masked min / max of the guide -- then mdc_begin with those.  sparse: device [N,1,H,W] fp32 metres (0 = missing); x_bf16:
  * the initial depth latent [N,4,EH,EW] (the reference draws it from torch's seeded generator, :677-684).
  * Fails with the reference's "No valid values found in mask ..." message (utils.py:132-136) for an empty sample. */
 int mdc_begin_frame(mdc_handle* h, const void* imgs, int img_dtype, int channels, const float* sparse, const void* x_bf16,
-                    float max_depth, float min_depth, int norm_const, float lr_latent, float lr_scaling);
+                    float max_depth, float min_depth, int norm_mode, float lr_latent, float lr_scaling);
 
 /* n guided steps (marigold_dc.py:801-904 each), asynchronous, no host synchronisation inside. */
 int mdc_run(mdc_handle* h, int n_steps);

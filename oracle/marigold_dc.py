@@ -1,8 +1,8 @@
 """ORACLE (test infrastructure): restatement of the reference's guided denoising path,
-MarigoldDepthCompletionPipeline.__call__ (marigold_dc.py:467-985), default branch only
-(projection="linear", inv=False, opt="adam", train_latents=True, train_method="per-step",
-closed_form=False, loss l1+l2, no kld), plus the helpers it uses (marigold_dc.py:53-128, :131-193,
-:284-371; utils.py:89-138, :692-739).
+MarigoldDepthCompletionPipeline.__call__ (marigold_dc.py:467-985) with train_latents=True,
+train_method="per-step", closed_form=False: every projection (linear / log / log10, inv), norm (minmax /
+percentile / const), optimiser (adam / sgd / adagrad), loss term (l1, l2, edge, smooth) and the kld penalty,
+plus the helpers it uses (marigold_dc.py:23-50, :53-128, :131-243, :284-371; utils.py:28-86, :89-138, :692-739).
 
 Differences from the reference, none of which change results:
   * UNet/VAE weights are frozen (the reference also accumulates unused weight gradients);
@@ -49,10 +49,46 @@ def compute_affine_params(affines, guides, masks):
     return scales.squeeze(1), shifts.squeeze(1)
 
 
-def compute_loss(denses, sparses, masks, loss_funcs=("l1", "l2")):
-    """marigold_dc.py:171-193 -- per-sample masked mean L1 + masked mean L2 -> [N]."""
+def get_projection_fn(projection):
+    """marigold_dc.py:23-50."""
+    if projection == "log":
+        return torch.log
+    if projection == "log10":
+        return torch.log10
+    if projection == "linear":
+        return lambda x: x
+    raise ValueError(f"Unknown projection method: {projection}")
+
+
+def kld_stdnorm(x, reduction="mean", mode="simple"):
+    """utils.py:28-86 -- KL divergence of the latent from N(0, 1), per sample ("none") or reduced."""
+    n = x.shape[0]
+    x_ = x.reshape(n, -1)
+    eps = torch.finfo(x.dtype).eps
+    if mode == "simple":
+        dist = x_.square().mean(dim=-1)
+    elif mode == "strict":
+        mu = x_.mean(dim=-1)
+        var = x_.var(dim=-1, unbiased=False)
+        dist = 0.5 * (mu.square() + var - torch.log(var + eps) - 1)
+    else:
+        raise ValueError(f"Unknown mode: {mode}")
+    if reduction == "mean":
+        return dist.mean()
+    if reduction == "sum":
+        return dist.sum()
+    if reduction == "none":
+        return dist
+    raise ValueError(f"Unknown reduction: {reduction}")
+
+
+def compute_loss(denses, sparses, masks, loss_funcs=("l1", "l2"), images=None, kld=False, kld_weight=0.1,
+                 kld_mode="simple", pred_latents=None):
+    """marigold_dc.py:131-243 -- per-sample sum of the listed terms (a term listed twice counts twice) -> [N]."""
     if len(loss_funcs) == 0:
         raise ValueError("loss_funcs must contain at least one loss function")
+    if kld and pred_latents is None:
+        raise ValueError("pred_latents must be provided when kl-divergence constraint is enabled")
     total = torch.zeros(denses.shape[0], device=denses.device)
     cnt = masks.sum(dim=(1, 2, 3))
     for f in loss_funcs:
@@ -60,8 +96,30 @@ def compute_loss(denses, sparses, masks, loss_funcs=("l1", "l2")):
             total = total + ((denses - sparses).abs() * masks).sum(dim=(1, 2, 3)) / cnt
         elif f == "l2":
             total = total + (((denses - sparses) ** 2) * masks).sum(dim=(1, 2, 3)) / cnt
+        elif f == "edge":
+            if images is None:
+                raise ValueError("image must be provided for edge loss")
+            c = images.shape[1]
+            if c == 3:
+                gray = 0.299 * images[:, 0:1] + 0.587 * images[:, 1:2] + 0.114 * images[:, 2:3]
+            elif c == 1:
+                gray = images
+            else:
+                raise ValueError(f"Image must have 1 or 3 channels, got {c}")
+            px = (denses[:, :, :, :-1] - denses[:, :, :, 1:]).abs()
+            py = (denses[:, :, :-1, :] - denses[:, :, 1:, :]).abs()
+            gx = (gray[:, :, :, :-1] - gray[:, :, :, 1:]).abs()
+            gy = (gray[:, :, :-1, :] - gray[:, :, 1:, :]).abs()
+            total = total + (px - gx).abs().mean(dim=(1, 2, 3)) + (py - gy).abs().mean(dim=(1, 2, 3))
+        elif f == "smooth":
+            if images is None:
+                raise ValueError("image must be provided for smooth loss")
+            total = total + (denses[:, :, :-1, :] - denses[:, :, 1:, :]).abs().mean(dim=(1, 2, 3)) \
+                + (denses[:, :, :, :-1] - denses[:, :, :, 1:]).abs().mean(dim=(1, 2, 3))
         else:
             raise ValueError(f"Unknown loss function: {f}")
+    if kld:
+        total = total + kld_weight * kld_stdnorm(pred_latents, reduction="none", mode=kld_mode)
     return total
 
 
@@ -127,8 +185,9 @@ class OraclePipeline:
         n = x.shape[0]
         return self.unet(torch.cat([img_latents, x], dim=1), t, self.empty_text_embedding.repeat(n, 1, 1))
 
-    def preprocess(self, imgs, sparses, max_depth, min_depth, norm, resolution, seed, pred_latents_prev, beta):
-        """marigold_dc.py:659-756 (linear projection).  Returns a dict of per-call constants."""
+    def preprocess(self, imgs, sparses, max_depth, min_depth, norm, resolution, seed, pred_latents_prev, beta,
+                   projection="linear", inv=False, percentile=(0.01, 0.99)):
+        """marigold_dc.py:659-756.  Returns a dict of per-call constants."""
         N, _, H, W = imgs.shape
         EH, EW = latent_size(H, W, resolution)
         with torch.no_grad():
@@ -141,19 +200,40 @@ class OraclePipeline:
             if norm == "minmax":
                 lo, hi = masked_minmax(sparses.view(N, -1), masks.view(N, -1), dim=-1)
                 lo, hi = lo.view(N, 1, 1, 1), hi.view(N, 1, 1, 1)
+            elif norm == "percentile":
+                p = torch.tensor(percentile, device=sparses.device)
+                ranges = torch.stack([torch.quantile(s[m], p) for s, m in zip(sparses, masks, strict=True)])
+                lo, hi = ranges[:, 0].view(N, 1, 1, 1), ranges[:, 1].view(N, 1, 1, 1)
             elif norm == "const":
                 lo = torch.full((N, 1, 1, 1), min_depth, device=sparses.device)
                 hi = torch.full((N, 1, 1, 1), max_depth, device=sparses.device)
             else:
                 raise ValueError(f"Unknown norm method: {norm}")
             clamped = sparses.clamp(min=lo, max=hi)
-            if norm == "minmax":
+            if norm in ("minmax", "percentile"):
                 lo, hi = lo.clamp(min=min_depth), hi.clamp(max=max_depth)
-            normed = (clamped - lo) / (hi - lo)
+            proj = get_projection_fn(projection)
+            lo_p, hi_p, clamped_p = proj(lo), proj(hi), proj(clamped)
+            if inv:
+                lo_p, hi_p = 1 / hi_p, 1 / lo_p
+                clamped_p = 1 / clamped_p
+            normed = (clamped_p - lo_p) / (hi_p - lo_p)
         return dict(x=x, img_latents=img_latents, masks=masks, sparses_normed=normed, min_depths=lo, max_depths=hi,
+                    min_depths_proj=lo_p, max_depths_proj=hi_p, projection=projection, inv=inv, imgs=imgs,
                     padding=padding, orig_res=orig_res)
 
-    def guided_step(self, st, t, x, scales, shifts, optimizer, trace=None, idx=0):
+    @staticmethod
+    def to_guide_space(dense, st):
+        """marigold_dc.py:842-862 -- normalised linear depth -> the projected / inverted space of the guide."""
+        if st.get("projection", "linear") == "linear" and not st.get("inv", False):
+            return dense
+        d = dense * (st["max_depths"] - st["min_depths"]) + st["min_depths"]
+        d = get_projection_fn(st["projection"])(d)
+        if st["inv"]:
+            d = 1 / d
+        return (d - st["min_depths_proj"]) / (st["max_depths_proj"] - st["min_depths_proj"])
+
+    def guided_step(self, st, t, x, scales, shifts, optimizer, trace=None, idx=0, loss_kw=None):
         """One iteration of marigold_dc.py:801-904.  x, scales, shifts are Parameters updated in place."""
         N = x.shape[0]
         optimizer.zero_grad()
@@ -164,7 +244,9 @@ class OraclePipeline:
         x0 = self.scheduler.step(v, t, x).pred_original_sample
         aff = self.latent_to_affine(x0, st["orig_res"], st["padding"])
         dense = self.affine_to_metric(aff, st["sparses_normed"], st["masks"], scales, shifts).clamp(min=0.0, max=1.0)
-        losses = compute_loss(dense, st["sparses_normed"], st["masks"])
+        dense = self.to_guide_space(dense, st)
+        losses = compute_loss(dense, st["sparses_normed"], st["masks"], images=st.get("imgs"), pred_latents=x,
+                              **(loss_kw or {}))
         losses.backward(torch.ones_like(losses))
         with torch.no_grad():
             raw_grad = x.grad.detach().clone()
@@ -184,21 +266,26 @@ class OraclePipeline:
         return losses.detach()
 
     def __call__(self, imgs, sparses, max_depth, min_depth=0.0, norm="minmax", pred_latents_prev=None, beta=0.9,
-                 steps=50, resolution=768, lr=None, seed=2024, trace=None, max_steps=None):
+                 steps=50, resolution=768, lr=None, seed=2024, trace=None, max_steps=None, projection="linear",
+                 inv=False, percentile=(0.01, 0.99), opt="adam", loss_funcs=None, kld=False, kld_weight=0.1,
+                 kld_mode="simple"):
         if imgs.ndim != 4 or sparses.ndim != 4 or imgs.shape[0] != sparses.shape[0] or imgs.shape[-2:] != sparses.shape[-2:]:
             raise ValueError("Shape of image must be [N, C, H, W] and shape of sparse must be [N, 1, H, W]")
         N = imgs.shape[0]
         lr_latent, lr_scaling = (0.05, 0.005) if lr is None else lr
-        st = self.preprocess(imgs, sparses, max_depth, min_depth, norm, resolution, seed, pred_latents_prev, beta)
+        st = self.preprocess(imgs, sparses, max_depth, min_depth, norm, resolution, seed, pred_latents_prev, beta,
+                             projection, inv, percentile)
+        loss_kw = dict(loss_funcs=tuple(loss_funcs or ("l1", "l2")), kld=kld, kld_weight=kld_weight, kld_mode=kld_mode)
         x = torch.nn.Parameter(st["x"])
         scales = torch.nn.Parameter(torch.ones(N, 1, 1, 1, device=self.device))
         shifts = torch.nn.Parameter(torch.zeros(N, 1, 1, 1, device=self.device))
-        opt = torch.optim.Adam([{"params": [x], "lr": lr_latent}, {"params": [scales, shifts], "lr": lr_scaling}])
+        groups = [{"params": [x], "lr": lr_latent}, {"params": [scales, shifts], "lr": lr_scaling}]
+        opt = {"adam": torch.optim.Adam, "sgd": torch.optim.SGD, "adagrad": torch.optim.Adagrad}[opt](groups)  # :776-789
         self.scheduler.set_timesteps(steps, device=self.device)
         for i, t in enumerate(self.scheduler.timesteps):
             if max_steps is not None and i >= max_steps:
                 break
-            self.guided_step(st, t, x, scales, shifts, opt, trace, i)
+            self.guided_step(st, t, x, scales, shifts, opt, trace, i, loss_kw)
         with torch.no_grad():
             xd = x.detach()
             aff = self.latent_to_affine(xd, st["orig_res"], st["padding"])

@@ -239,3 +239,84 @@ def test_oracle_reproduces_taesd_golden_fixture():
     assert np.allclose(out["step_v"][0], gold["step_v"][0], rtol=1e-3, atol=1e-4)
     assert np.allclose(out["step_losses"][0], gold["step_losses"][0], rtol=1e-4)
     assert np.allclose(out["step_x_adam"][0], gold["step_x_adam"][0], atol=1e-4)
+
+
+def tiny_models(seed=1234):
+    torch.manual_seed(seed)
+    return UNet2DConditionModel(tiny_unet_config()), AutoencoderKL(tiny_vae_config())
+
+
+def test_oracle_extra_loss_terms_known_answers():
+    """edge / smooth / kld of the oracle (marigold_dc.py:195-243, utils.py:28-86) on hand-computable inputs."""
+    d = torch.tensor([[[[0.0, 0.5, 0.5], [1.0, 0.5, 0.0]]]])          # [1,1,2,3]
+    z = torch.zeros_like(d)
+    m = torch.zeros_like(d, dtype=torch.bool)
+    m[0, 0, 0, 0] = True
+    img = torch.zeros(1, 3, 2, 3)
+    # smooth: mean |dy| over 3 pairs = (1 + 0 + .5) / 3, mean |dx| over 4 pairs = (.5 + 0 + .5 + .5) / 4
+    sm = om.compute_loss(d, z, m, ("smooth",), images=img)
+    assert abs(sm.item() - (1.5 / 3 + 1.5 / 4)) < 1e-6
+    # edge against a flat image equals smooth; against an image whose x-gradient is 0.5 everywhere only |dx| changes
+    assert torch.allclose(om.compute_loss(d, z, m, ("edge",), images=img), sm)
+    ramp = torch.tensor([0.0, 0.5, 1.0]).view(1, 1, 1, 3).expand(1, 3, 2, 3)
+    ed = om.compute_loss(d, z, m, ("edge",), images=ramp)
+    gray_step = 0.5 * (0.299 + 0.587 + 0.114)
+    assert abs(ed.item() - (1.5 / 3 + (0 + gray_step + 0 + 0) / 4)) < 1e-6
+    # a listed term counts as often as it is listed; images are required
+    assert torch.allclose(om.compute_loss(d, z, m, ("smooth", "smooth"), images=img), 2 * sm)
+    with pytest.raises(ValueError):
+        om.compute_loss(d, z, m, ("edge",))
+    with pytest.raises(ValueError):
+        om.compute_loss(d, z, m, ())
+    # kld: simple = E[x^2]; strict = KL(N(mu, var) || N(0, 1)), zero for a standardised sample
+    x = torch.randn(2, 4, 6, 8)
+    assert torch.allclose(om.kld_stdnorm(x, "none", "simple"), x.reshape(2, -1).square().mean(-1))
+    xs = (x - x.mean(dim=(1, 2, 3), keepdim=True)) / x.reshape(2, -1).std(-1, unbiased=False).view(2, 1, 1, 1)
+    assert om.kld_stdnorm(xs, "none", "strict").abs().max() < 1e-5
+    shifted = om.kld_stdnorm(xs * 2 + 1, "none", "strict")
+    assert torch.allclose(shifted, torch.full((2,), 0.5 * (1 + 4 - math.log(4) - 1)), atol=1e-4)
+    with pytest.raises(ValueError):
+        om.kld_stdnorm(x, "none", "exact")
+    tot = om.compute_loss(d, z, m, ("l1",), kld=True, kld_weight=0.5, pred_latents=x[:1])
+    assert abs(tot.item() - (0.0 + 0.5 * x[:1].square().mean().item())) < 1e-6
+
+
+def test_oracle_projection_and_percentile_normalisation():
+    """marigold_dc.py:707-756: every projection / inv / norm branch maps the clamped sparse depths into [0, 1] with the
+    range ends at 0 and 1, and the loop-side conversion (:842-862) is its inverse on the linear normalised depth."""
+    unet, vae = tiny_models()
+    pipe = om.OraclePipeline(unet, vae, om.make_empty_text_embedding(64))
+    g = torch.Generator().manual_seed(0)
+    img = torch.randint(0, 256, (2, 3, 32, 48), generator=g, dtype=torch.uint8)
+    # depths above 1 m: the reference's inverse of a log projection is singular at 1 m (log = 0)
+    sp = (torch.rand(2, 1, 32, 48, generator=g) * 9 + 2.0) * (torch.rand(2, 1, 32, 48, generator=g) < 0.2)
+    for projection, inv, norm in [("linear", False, "percentile"), ("log", False, "minmax"), ("log10", True, "const"),
+                                  ("linear", True, "minmax"), ("log", True, "percentile")]:
+        st = pipe.preprocess(img, sp, 12.0, 1.5, norm, 48, 2024, None, 0.9, projection, inv, (0.1, 0.9))
+        gd, m = st["sparses_normed"], st["masks"]
+        assert gd[m].min() >= -1e-6 and gd[m].max() <= 1 + 1e-6
+        if norm != "const":
+            assert abs(gd[m].min().item()) < 1e-6 and abs(gd[m].max().item() - 1) < 1e-6
+        if norm == "percentile":
+            for n in range(2):
+                q = torch.quantile(sp[n][m[n]], torch.tensor([0.1, 0.9]))
+                assert torch.allclose(torch.stack([st["min_depths"][n].flatten()[0], st["max_depths"][n].flatten()[0]]), q)
+        # linear normalised depth of the clamped points -> guide space reproduces the guide
+        lin = (sp.clamp(min=st["min_depths"], max=st["max_depths"]) - st["min_depths"]) / (st["max_depths"] - st["min_depths"])
+        assert torch.allclose(om.OraclePipeline.to_guide_space(lin, st)[m], gd[m], atol=1e-5)
+    with pytest.raises(ValueError):
+        om.get_projection_fn("sqrt")
+
+
+@pytest.mark.parametrize("kw", [dict(projection="log", min_depth=0.1), dict(opt="sgd"), dict(opt="adagrad"),
+                                dict(loss_funcs=("l1", "edge", "smooth")), dict(kld=True, kld_mode="strict"),
+                                dict(norm="percentile", inv=True, min_depth=0.1)])
+def test_oracle_runs_every_option(kw):
+    unet, vae = tiny_models()
+    pipe = om.OraclePipeline(unet, vae, om.make_empty_text_embedding(64))
+    g = torch.Generator().manual_seed(1)
+    img = torch.randint(0, 256, (1, 3, 32, 48), generator=g, dtype=torch.uint8)
+    sp = (torch.rand(1, 1, 32, 48, generator=g) * 9 + 2.0) * (torch.rand(1, 1, 32, 48, generator=g) < 0.1)
+    base, _ = pipe(img, sp, 12.0, steps=50, resolution=48, max_steps=2)
+    dense, lat = pipe(img, sp, 12.0, steps=50, resolution=48, max_steps=2, **kw)
+    assert torch.isfinite(dense).all() and torch.isfinite(lat).all() and not torch.equal(dense, base)
