@@ -6,8 +6,9 @@ Same constructor and call signature, same return tuple `(denses [N,1,H,W] fp32 m
 same ValueError conventions.  Non-default branches the north star leaves out of scope
 (closed-form / no-grad paths, per-input training, non-bilinear interpolation) raise NotImplementedError instead of silently doing something else.
 
-The host keeps, in PyTorch, only what runs once per call: argument checks, image resize/pad, the VAE *encoder*,
-sparse-depth normalisation and the seeded initial latent (marigold_dc.py:659-756).
+The host keeps, in PyTorch, only the argument checks and the seeded initial latent (torch's Philox stream,
+marigold_dc.py:661, :677-684); image preprocessing, the VAE encoder and the sparse-depth normalisation run inside the
+library (mdc_begin_frame), the per-call options travel through mdc_set_options.
 """
 from __future__ import annotations
 
