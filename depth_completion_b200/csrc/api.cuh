@@ -132,6 +132,19 @@ int mdc_encode(mdc_handle* h, const void* imgs, int dtype, int channels, void* l
     h->e->encode(imgs, dtype, channels, latents_out_bf16);
   });
 }
+int mdc_sample(mdc_handle* h, int n_steps) {
+  return mdc::guarded([&] {
+    MDC_CHECK(h, "null handle");
+    for (int i = 0; i < n_steps; ++i) h->e->sample_step();
+    MDC_CUDA(cudaGetLastError());
+  });
+}
+int mdc_decode_final_closed_form(mdc_handle* h, float* dense_out) {
+  return mdc::guarded([&] {
+    MDC_CHECK(h && dense_out, "null pointer");
+    h->e->decode_final(dense_out, true);
+  });
+}
 int mdc_decode_final(mdc_handle* h, float* dense_out) {
   return mdc::guarded([&] {
     MDC_CHECK(h && dense_out, "null argument");

@@ -446,9 +446,12 @@ struct Engine {
   void step_launches();  // the fixed launch sequence of one guided step
   void step();           // replays it as a CUDA graph (captured once; every step-dependent value lives in device memory)
   cudaGraphExec_t step_graph = nullptr;
+  cudaGraphExec_t sample_graph = nullptr;  // the no-grad DDIM step (train_latents=False)
+  void sample_launches();
+  void sample_step();
   bool use_graph = true;
   ~Engine();
-  void decode_final(float* dense_out);
+  void decode_final(float* dense_out, bool closed_form = false);
   void build_encoder();
   void build_tiny_decoder();
   void build_tiny_encoder();
@@ -1587,6 +1590,7 @@ inline void Engine::run_ops(std::vector<std::unique_ptr<Op>>& ops, bool backward
 
 inline Engine::~Engine() {
   if (step_graph) cudaGraphExecDestroy(step_graph);
+  if (sample_graph) cudaGraphExecDestroy(sample_graph);
   if (stream) cudaStreamDestroy(stream);
 }
 inline void Engine::step() {
@@ -1655,7 +1659,42 @@ inline void Engine::step_launches() {
                                               accum, counter, x_adam_dbg, opts);
 }
 
-inline void Engine::decode_final(float* dense_out) {
+// One step of the no-grad branch (marigold_dc.py:805-809, :905-909): UNet forward + DDIM prev_sample.
+inline void Engine::sample_launches() {
+  const int hw = lh * lw, lat_pix = N * hw;
+  launch_k(begin_step_kernel, dim3(1), dim3(1024), 0, stream, tables, counter, cur, temb_cur, opts);
+  launch_k(unet_input_kernel, dim3((lat_pix + 255) / 256), dim3(256), 0, stream, img_lat, x, N, hw, unet_in->d);
+  run_ops(unet_ops, false);
+  launch_k(ddim_only_kernel, dim3((lat_pix + 255) / 256), dim3(256), 0, stream, unet_out->d, cur, N, hw, x, counter);
+}
+inline void Engine::sample_step() {
+  MDC_CHECK(begun, "mdc_sample called before mdc_begin");
+  MDC_CHECK(steps_done < cfg.steps, "all %d steps already done", cfg.steps);
+  const long long before = launches;
+  if (!use_graph) {
+    sample_launches();
+  } else {
+    if (!sample_graph) {
+      cudaGraph_t graph = nullptr;
+      MDC_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        sample_launches();
+      } catch (...) {
+        cudaStreamEndCapture(stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      MDC_CUDA(cudaStreamEndCapture(stream, &graph));
+      MDC_CUDA(cudaGraphInstantiate(&sample_graph, graph, 0));
+      cudaGraphDestroy(graph);
+    }
+    MDC_CUDA(cudaGraphLaunch(sample_graph, stream));
+  }
+  (void)before;
+  ++steps_done;
+}
+
+inline void Engine::decode_final(float* dense_out, bool closed_form) {
   MDC_CHECK(begun, "mdc_decode_final called before mdc_begin");
   const int hw = lh * lw;
   // z = x / scaling as NHWC (reuse x0_kernel algebra with sqrt_a = 1, sqrt_1ma = 0 via a dedicated tiny path)
@@ -1673,8 +1712,9 @@ inline void Engine::decode_final(float* dense_out) {
   run_ops(dec_ops, false);
   TailGeom g{N, H, W, ph, pw, PPH, PPW, dec_out->ld};
   const long long tot = 1LL * N * H * W;
+  if (closed_form) launch_k(affine_lsq_kernel, dim3(N), dim3(512), 0, stream, dec_out->d, g, pt_idx, pt_val, pt_off, accum);
   launch_k(dense_out_kernel, dim3(static_cast<int>((tot + 255) / 256)), dim3(256), 0, stream, dec_out->d, g, gminmax, depth_minmax, accum,
-                                                                           dense_out);
+                                                                           dense_out, closed_form ? 1 : 0);
   MDC_CUDA(cudaGetLastError());
   MDC_CUDA(cudaStreamSynchronize(stream));
   cudaFree(tmp), cudaFree(scratch);

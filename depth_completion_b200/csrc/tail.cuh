@@ -533,10 +533,72 @@ __global__ void adam_ddim_kernel(const float* __restrict__ gbuf, const float* __
   if (blockIdx.x == 0 && threadIdx.x == 0) *counter = *counter + 1;
 }
 
+// Plain DDIM step of the no-grad branch (train_latents=False, marigold_dc.py:905-909): prev_sample from v and x, no
+// guidance.  Same bf16 rounding points as the guided kernel's tail.  Advances the step counter.
+__global__ void ddim_only_kernel(const bf16* __restrict__ v_nhwc, const StepCur* __restrict__ cur, int N, int hw,
+                                 bf16* __restrict__ x, int* __restrict__ counter) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  const float sa = cur->sqrt_a, sb = cur->sqrt_1ma, sap = cur->sqrt_ap, sbp = cur->sqrt_1map;
+  const long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+  if (i < 1LL * N * hw) {
+    const long long n = i / hw, p = i % hw;
+    BF8 vv = *reinterpret_cast<const BF8*>(v_nhwc + i * 8);
+    const bf16* vb = reinterpret_cast<const bf16*>(&vv);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const long long j = (n * 4 + c) * hw + p;
+      const float xv = __bfloat162float(x[j]), vf = __bfloat162float(vb[c]);
+      const float x0 = bf16r(bf16r(sa * xv) - bf16r(sb * vf));
+      const float e = bf16r(bf16r(sa * vf) + bf16r(sb * xv));
+      x[j] = __float2bfloat16(bf16r(sap * x0) + bf16r(sbp * e));
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *counter = *counter + 1;
+}
+
+// Closed-form masked least-squares scale / shift (compute_affine_params, marigold_dc.py:53-128) over the valid points of
+// one sample: scale = cov(a, g) / (var(a) + 1e-7), shift = mean(g) - scale * mean(a); the affine-side sums round to
+// bf16 like the reference's bf16 tensors.  Writes them to acc->scale / acc->shift.  One block per sample.
+__global__ void affine_lsq_kernel(const bf16* __restrict__ dec, TailGeom g, const int* __restrict__ pt_idx,
+                                  const float* __restrict__ pt_val, const int* __restrict__ pt_off,
+                                  StepAccum* __restrict__ acc) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  __shared__ float red[32];
+  __shared__ float s_am, s_gm;
+  const int n = blockIdx.x, p0 = pt_off[n], p1 = pt_off[n + 1];
+  const float cnt = static_cast<float>(p1 - p0);
+  auto aff_at = [&](int i) {
+    const int pix = pt_idx[i];
+    return dense_pixel(dec, g, n, pix / g.W, pix % g.W, 1.f, 0.f, 0.f, 1.f, 0.f, 1.f, 0.f, 1.f, 0, 0).aff;
+  };
+  float sa = 0.f, sg = 0.f;
+  for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x) sa += aff_at(i), sg += pt_val[i];
+  sa = block_sum(sa, red);
+  sg = block_sum(sg, red);
+  if (threadIdx.x == 0) s_am = bf16r(bf16r(sa) / cnt), s_gm = sg / cnt;
+  __syncthreads();
+  const float am = s_am, gm = s_gm;
+  float var = 0.f, cov = 0.f;
+  for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x) {
+    const float ac = bf16r(aff_at(i) - am);
+    var += bf16r(ac * ac);
+    cov += ac * (pt_val[i] - gm);
+  }
+  var = block_sum(var, red);
+  cov = block_sum(cov, red);
+  if (threadIdx.x == 0) {
+    const float sc = cov / (bf16r(var) + 1e-7f);
+    acc->scale[n] = sc;
+    acc->shift[n] = gm - sc * am;
+  }
+}
+
 // Final dense map (marigold_dc.py:970-984): clamp(s^2 range aff + t^2 gmin, 0, 1) * (max - min) + min -> fp32 [N,1,H,W]
 __global__ void dense_out_kernel(const bf16* __restrict__ dec, TailGeom g, const float* __restrict__ gminmax,
                                  const float* __restrict__ depth_minmax, const StepAccum* __restrict__ acc,
-                                 float* __restrict__ out) {
+                                 float* __restrict__ out, int closed_form) {
   ptx::pdl_wait();
   ptx::pdl_launch();
   long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
@@ -556,7 +618,8 @@ __global__ void dense_out_kernel(const bf16* __restrict__ dec, TailGeom g, const
   const float aff = bf16r((1.f - ly) * ((1.f - lx) * a00 + lx * a01) + ly * ((1.f - lx) * a10 + lx * a11));
   const float s = acc->scale[n], t = acc->shift[n];
   const float gmin = gminmax[2 * n], gmax = gminmax[2 * n + 1];
-  float d = s * s * (gmax - gmin) * aff + t * t * gmin;
+  float d = closed_form ? s * aff + t                           // :332-336, closed-form scale / shift
+                        : s * s * (gmax - gmin) * aff + t * t * gmin;  // :320-331, learned scale / shift
   d = fminf(fmaxf(d, 0.f), 1.f);
   const float dmin = depth_minmax[2 * n], dmax = depth_minmax[2 * n + 1];
   out[i] = d * (dmax - dmin) + dmin;

@@ -49,6 +49,8 @@ def _declare(l):
     l.mdc_run.argtypes = [C.c_void_p, C.c_int]
     l.mdc_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.mdc_decode_final.argtypes = [C.c_void_p, C.c_void_p]
+    l.mdc_sample.argtypes = [C.c_void_p, C.c_int]
+    l.mdc_decode_final_closed_form.argtypes = [C.c_void_p, C.c_void_p]
     l.mdc_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     l.mdc_begin_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                   C.c_int, C.c_float, C.c_float]
@@ -187,6 +189,10 @@ class StepEngine:
     def run(self, n_steps: int):
         check(self.lib.mdc_run(self._h, int(n_steps)))
 
+    def sample(self, n_steps: int):
+        """n plain DDIM steps without guidance: the train_latents=False branch (marigold_dc.py:905-909)."""
+        check(self.lib.mdc_sample(self._h, int(n_steps)))
+
     def get_state(self):
         x = torch.empty(self.n, 4, self.lh, self.lw, device=self.device, dtype=torch.bfloat16)
         sc = np.zeros(self.n, np.float32)
@@ -250,9 +256,12 @@ class StepEngine:
                 raise ValueError(str(e)) from None
             raise
 
-    def decode_final(self) -> torch.Tensor:
+    def decode_final(self, closed_form: bool = False) -> torch.Tensor:
+        """Final decode + affine + clamp + de-normalisation (marigold_dc.py:970-984); closed_form=True fits scale / shift
+        by masked least squares (:53-128) instead of using the learned ones."""
         out = torch.empty(self.n, 1, self.H, self.W, device=self.device, dtype=torch.float32)
-        check(self.lib.mdc_decode_final(self._h, ptr(out)))
+        fn = self.lib.mdc_decode_final_closed_form if closed_form else self.lib.mdc_decode_final
+        check(fn(self._h, ptr(out)))
         return out
 
     def launch_count(self) -> int:

@@ -121,6 +121,13 @@ int mdc_get_state(mdc_handle* h, void* x_out_bf16, float* scale_host, float* shi
 /* Final decode + affine + clamp + de-normalisation -> dense [N,1,H,W] fp32 metric depth (marigold_dc.py:970-984). */
 int mdc_decode_final(mdc_handle* h, float* dense_out);
 
+/* The no-grad branch of the call (train_latents = False, hence closed_form = True; marigold_dc.py:605-613): n plain DDIM
+ * steps -- UNet forward + scheduler.step(...).prev_sample, no decoder, no guidance (:805-809, :905-909) -- and the final
+ * decode with the closed-form masked least-squares scale / shift (compute_affine_params, :53-128, :332-336) instead of
+ * the learned ones.  mdc_get_state then returns that scale / shift. */
+int mdc_sample(mdc_handle* h, int n_steps);
+int mdc_decode_final_closed_form(mdc_handle* h, float* dense_out);
+
 /* Number of kernel launches issued by the handle so far, and bytes of device memory it owns. */
 long long mdc_launch_count(mdc_handle* h);
 long long mdc_device_bytes(mdc_handle* h);

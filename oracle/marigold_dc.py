@@ -1,6 +1,7 @@
 """ORACLE (test infrastructure): restatement of the reference's guided denoising path,
-MarigoldDepthCompletionPipeline.__call__ (marigold_dc.py:467-985) with train_latents=True,
-train_method="per-step", closed_form=False: every projection (linear / log / log10, inv), norm (minmax /
+MarigoldDepthCompletionPipeline.__call__ (marigold_dc.py:467-985) with train_method="per-step" and either
+train_latents=True / closed_form=False (the guided loop) or train_latents=False (plain sampling + closed-form affine):
+every projection (linear / log / log10, inv), norm (minmax /
 percentile / const), optimiser (adam / sgd / adagrad), loss term (l1, l2, edge, smooth) and the kld penalty,
 plus the helpers it uses (marigold_dc.py:23-50, :53-128, :131-243, :284-371; utils.py:28-86, :89-138, :692-739).
 
@@ -265,10 +266,26 @@ class OraclePipeline:
                        shifts=shifts.detach().clone(), eps_norm=en, grad_norm=gn))
         return losses.detach()
 
+    @torch.no_grad()
+    def sample_closed_form(self, st, steps, max_steps=None):
+        """train_latents=False (hence closed_form=True, marigold_dc.py:605-613): plain DDIM sampling (:805-809, :905-909)
+        and the final decode with the closed-form least-squares scale / shift (:332-336, :970-984)."""
+        x = st["x"]
+        self.scheduler.set_timesteps(steps, device=self.device)
+        for i, t in enumerate(self.scheduler.timesteps):
+            if max_steps is not None and i >= max_steps:
+                break
+            x = self.scheduler.step(self.predict_noise(st["img_latents"], x, t), t, x).prev_sample
+        aff = self.latent_to_affine(x, st["orig_res"], st["padding"])
+        n = aff.shape[0]
+        scales, shifts = compute_affine_params(aff, st["sparses_normed"], st["masks"])
+        dense = (scales.view(n, 1, 1, 1) * aff + shifts.view(n, 1, 1, 1)).clamp(min=0.0, max=1.0)
+        return dense * (st["max_depths"] - st["min_depths"]) + st["min_depths"], x
+
     def __call__(self, imgs, sparses, max_depth, min_depth=0.0, norm="minmax", pred_latents_prev=None, beta=0.9,
                  steps=50, resolution=768, lr=None, seed=2024, trace=None, max_steps=None, projection="linear",
                  inv=False, percentile=(0.01, 0.99), opt="adam", loss_funcs=None, kld=False, kld_weight=0.1,
-                 kld_mode="simple"):
+                 kld_mode="simple", train_latents=True):
         if imgs.ndim != 4 or sparses.ndim != 4 or imgs.shape[0] != sparses.shape[0] or imgs.shape[-2:] != sparses.shape[-2:]:
             raise ValueError("Shape of image must be [N, C, H, W] and shape of sparse must be [N, 1, H, W]")
         N = imgs.shape[0]
@@ -276,6 +293,8 @@ class OraclePipeline:
         st = self.preprocess(imgs, sparses, max_depth, min_depth, norm, resolution, seed, pred_latents_prev, beta,
                              projection, inv, percentile)
         loss_kw = dict(loss_funcs=tuple(loss_funcs or ("l1", "l2")), kld=kld, kld_weight=kld_weight, kld_mode=kld_mode)
+        if not train_latents:
+            return self.sample_closed_form(st, steps, max_steps)
         x = torch.nn.Parameter(st["x"])
         scales = torch.nn.Parameter(torch.ones(N, 1, 1, 1, device=self.device))
         shifts = torch.nn.Parameter(torch.zeros(N, 1, 1, 1, device=self.device))

@@ -259,3 +259,33 @@ def test_learning_rates_are_per_call(setup, cuda):
     fresh.empty_text_embedding = ctx
     b2, _ = fresh(img, sp, fr["max_depth"], steps=6, resolution=128, lr=(0.01, 0.001))
     assert torch.equal(b, b2)
+
+
+def test_no_grad_sampling_with_closed_form_affine(setup, cuda):
+    """train_latents=False (marigold_dc.py:605-613, :905-909, :53-128): plain DDIM sampling + least-squares scale / shift.
+    Without the guidance the loop is not chaotic, so the latent itself is compared."""
+    from depth_completion_b200.pipeline import MarigoldDepthCompletionPipeline
+    from depth_completion_b200.synthetic import make_frame
+    from helpers import rel_l2
+    from oracle.marigold_dc import OraclePipeline
+
+    (unet, vae, ctx), _ = setup
+    fr = make_frame(H=96, W=128, n_points=100, seed=4)
+    img, sp = fr["img"].to(cuda), fr["sparse"].to(cuda)
+    pipe = MarigoldDepthCompletionPipeline(unet, vae)
+    pipe.empty_text_embedding = ctx
+    dense, lat = pipe(img, sp, fr["max_depth"], steps=10, resolution=128, train_latents=False)
+    d32, l32 = OraclePipeline(copy.deepcopy(unet), copy.deepcopy(vae), ctx)(img, sp, fr["max_depth"], steps=10, resolution=128,
+                                                                            train_latents=False)
+    d16, l16 = OraclePipeline(copy.deepcopy(unet).bfloat16(), copy.deepcopy(vae).bfloat16(), ctx.bfloat16())(
+        img, sp, fr["max_depth"], steps=10, resolution=128, train_latents=False)
+    e_ours, e_ref = rel_l2(lat, l32), rel_l2(l16, l32)
+    assert e_ours < 1.25 * e_ref + 5e-3, f"latent after 10 DDIM steps: ours {e_ours:.4f}, torch-bf16 {e_ref:.4f}"
+    rng = fr["max_depth"]
+    ours = ((dense - d32).abs().mean() / rng).item()
+    ref = ((d16 - d32).abs().mean() / rng).item()
+    assert ours < max(2.0 * ref, 5e-3) + 5e-3, f"dense: ours {ours:.4f}, torch-bf16 {ref:.4f}"
+    guided, _ = pipe(img, sp, fr["max_depth"], steps=10, resolution=128)
+    assert not torch.equal(guided, dense)
+    with pytest.raises(NotImplementedError):
+        pipe(img, sp, fr["max_depth"], steps=10, resolution=128, closed_form=True)

@@ -320,3 +320,23 @@ def test_oracle_runs_every_option(kw):
     base, _ = pipe(img, sp, 12.0, steps=50, resolution=48, max_steps=2)
     dense, lat = pipe(img, sp, 12.0, steps=50, resolution=48, max_steps=2, **kw)
     assert torch.isfinite(dense).all() and torch.isfinite(lat).all() and not torch.equal(dense, base)
+
+
+def test_oracle_no_grad_branch_is_least_squares_optimal():
+    """train_latents=False: DDIM sampling + compute_affine_params; the fitted map's residual at the valid points is
+    orthogonal to the affine prediction and has zero mean (normal equations of marigold_dc.py:53-128)."""
+    unet, vae = tiny_models()
+    pipe = om.OraclePipeline(unet, vae, om.make_empty_text_embedding(64))
+    g = torch.Generator().manual_seed(1)
+    img = torch.randint(0, 256, (1, 3, 32, 48), generator=g, dtype=torch.uint8)
+    sp = (torch.rand(1, 1, 32, 48, generator=g) * 9 + 2.0) * (torch.rand(1, 1, 32, 48, generator=g) < 0.1)
+    st = pipe.preprocess(img, sp, 12.0, 0.0, "minmax", 48, 2024, None, 0.9)
+    dense, x = pipe.sample_closed_form(st, 50, max_steps=3)
+    assert dense.shape == (1, 1, 32, 48) and torch.isfinite(dense).all()
+    aff = pipe.latent_to_affine(x, st["orig_res"], st["padding"])
+    s, t = om.compute_affine_params(aff, st["sparses_normed"], st["masks"])
+    m = st["masks"]
+    r = (s.view(1, 1, 1, 1) * aff + t.view(1, 1, 1, 1) - st["sparses_normed"])[m]
+    assert abs(r.mean().item()) < 1e-5 and abs((r * (aff[m] - aff[m].mean())).sum().item()) < 1e-4
+    d2, x2 = pipe(img, sp, 12.0, steps=50, resolution=48, max_steps=3, train_latents=False)
+    assert torch.equal(d2, dense) and torch.equal(x2, x)
