@@ -231,3 +231,63 @@ def test_vae_config_detection_kl_and_tiny():
         vae_config_from({**d, "decoder_block_out_channels": (64, 64, 64, 32)})
     with pytest.raises(ValueError):
         vae_config_from({**d, "act_fn": "gelu"})
+
+
+def test_dataset_front_end_round_trip(tmp_path):
+    """dataset_io: discovery, pairing, sparse-PNG depth decoding, batch loop and saving (predict.py:512-728) around a
+    stand-in pipeline that returns the sparse map it was given."""
+    from PIL import Image
+
+    from depth_completion_b200 import dataset_io as dio
+
+    src, dst = tmp_path / "src", tmp_path / "dst"
+    g = torch.Generator().manual_seed(0)
+    depths = {}
+    for ds in ("seq_a", "nested/seq_b"):
+        (src / ds / "image" / "cam0").mkdir(parents=True)
+        (src / ds / "sparse" / "cam0").mkdir(parents=True)
+        for k in range(3):
+            img = torch.randint(0, 256, (12, 16, 3), generator=g, dtype=torch.uint8).numpy()
+            Image.fromarray(img).save(src / ds / "image" / "cam0" / f"{k:03d}.jpg")
+            d = torch.rand(12, 16, generator=g) * 100 * (torch.rand(12, 16, generator=g) < 0.3)
+            if k < 2:  # frame 002 has no sparse map -> dropped
+                Image.fromarray(dio.encode_depth_png(d, 120.0)).save(src / ds / "sparse" / "cam0" / f"{k:03d}.png")
+                depths[(ds.split("/")[-1], k)] = d
+    (src / "seq_a" / "image" / "notes.txt").write_text("not an image")
+    assert [p.name for p in dio.find_dataset_dirs(src)] == ["seq_b", "seq_a"] or \
+        sorted(p.name for p in dio.find_dataset_dirs(src)) == ["seq_a", "seq_b"]
+    assert dio.find_dataset_dirs(src / "seq_a") == [src / "seq_a"]
+    pairs = dio.find_pairs(src / "seq_a")
+    assert [i.name for i, _ in pairs] == ["000.jpg", "001.jpg"] and all(s.suffix == ".png" for _, s in pairs)
+    sp = dio.to_depth(torch.stack([dio.load_rgb(s) for _, s in pairs]), 120.0)
+    assert sp.shape == (2, 1, 12, 16) and sp.dtype == torch.float32
+    assert (sp[0, 0] - depths[("seq_a", 0)]).abs().max() <= 120.0 / 255 / 2 + 1e-5  # 256 levels (SURVEY A.6)
+    assert ((sp[0, 0] == 0) == (torch.round(depths[("seq_a", 0)] / 120 * 255) == 0)).all()
+    assert dio.load_rgb(src / "seq_a" / "image" / "notes.txt") is None
+
+    calls = []
+
+    class EchoPipe:
+        device = "cpu"
+
+        def __call__(self, imgs, sparses, max_depth, pred_latents_prev=None, beta=0.9, **kw):
+            calls.append((imgs.shape[0], pred_latents_prev is not None, kw))
+            assert imgs.dtype == torch.uint8 and imgs.shape[1] == 3 and sparses.shape[1] == 1
+            return sparses.clone(), torch.zeros(imgs.shape[0], 4, 1, 2)
+
+    saved = dio.complete_dataset(EchoPipe(), src, dst, 120.0, 120.0, batch_size=2, compress="npz", steps=5)
+    assert sorted(saved) == ["seq_a", "seq_b"] and all(len(v) == 2 for v in saved.values())
+    assert all(c[0] == 2 and not c[1] and c[2] == {"steps": 5} for c in calls)
+    out = dst / "nested" / "seq_b" / "dense" / "cam0" / "001.npz"
+    assert out in saved["seq_b"] and out.exists()
+    assert np.allclose(dio.load_dense(out)[0], dio.to_depth(dio.load_rgb(src / "nested/seq_b/sparse/cam0/001.png")[None], 120.0)[0, 0])
+    calls.clear()
+    dio.complete_dataset(EchoPipe(), src / "seq_a", dst / "chain", batch_size=4, use_prev_latent=True, compress=None)
+    assert [c[:2] for c in calls] == [(1, False), (1, True)]  # serial chain, batch forced to 1 (predict.py:423-430, :697-699)
+    assert (dst / "chain" / "dense" / "cam0" / "000.npy").exists()
+    with pytest.raises(ValueError):
+        dio.save_tensor(torch.zeros(2), tmp_path / "x.npy", compress="npz")
+    with pytest.raises(RuntimeError):
+        dio.save_tensor(torch.zeros(2), tmp_path / "x.bl2", compress="bl2")
+    with pytest.raises(FileNotFoundError):
+        dio.complete_dataset(EchoPipe(), tmp_path / "dst", tmp_path / "nowhere")
