@@ -96,10 +96,10 @@ int mdc_begin_frame(mdc_handle* h, const void* imgs, int img_dtype, int channels
   });
 }
 int mdc_set_options(mdc_handle* h, int projection, int inv, int opt, const float* loss_weights4_host, int kld_mode,
-                    float kld_weight, float percentile_lo, float percentile_hi) {
+                    float kld_weight, float percentile_lo, float percentile_hi, int closed_form) {
   return mdc::guarded([&] {
     MDC_CHECK(h, "null handle");
-    h->e->set_options(projection, inv, opt, loss_weights4_host, kld_mode, kld_weight, percentile_lo, percentile_hi);
+    h->e->set_options(projection, inv, opt, loss_weights4_host, kld_mode, kld_weight, percentile_lo, percentile_hi, closed_form);
   });
 }
 int mdc_run(mdc_handle* h, int n_steps) {
@@ -238,6 +238,8 @@ int mdc_dbg_loss(mdc_handle* h, const float* dec_nchw, float* ddec_nchw, float* 
     mdc::TailGeom g{e->N, e->H, e->W, e->ph, e->pw, e->PPH, e->PPW, e->dec_out->ld};
     mdc::loss_points_kernel<<<e->N, 512, 0, e->stream>>>(e->dec_out->d, g, e->pt_idx, e->pt_val, e->pt_off, e->gminmax,
                                                          e->depth_minmax, e->opts, e->accum, e->dmean);
+    mdc::loss_points_cf_kernel<<<e->N, 512, 0, e->stream>>>(e->dec_out->d, g, e->pt_idx, e->pt_val, e->pt_off, e->depth_minmax, e->opts,
+                                                            e->accum, e->dmean, e->pt_a, e->pt_G);
     const long long npix = 1LL * e->N * e->PPH * e->PPW, opix = 1LL * e->N * e->H * e->W;
     mdc::dense_map_kernel<<<static_cast<int>((opix + 255) / 256), 256, 0, e->stream>>>(e->dec_out->d, g, e->gminmax, e->depth_minmax,
                                                                                       e->opts, e->accum, e->dn_map);

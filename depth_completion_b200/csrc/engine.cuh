@@ -397,10 +397,11 @@ struct Engine {
   int* pt_off = nullptr;
   float *gminmax = nullptr, *depth_minmax = nullptr;
   float lr_x = 0.05f, lr_s = 0.005f;
-  TailOpts h_opts{0, 0, 0, 0, 0.1f, 1.f, 1.f, 0.f, 0.f, 0.05f, 0.005f};  // defaults of marigold_dc.py:467-493; mdc_set_options
+  TailOpts h_opts{0, 0, 0, 0, 0.1f, 1.f, 1.f, 0.f, 0.f, 0.05f, 0.005f, 0};  // defaults of marigold_dc.py:467-493; mdc_set_options
   TailOpts* opts = nullptr;                                               // device copy, refreshed by begin()
   float *x1_part = nullptr, *x2_part = nullptr;                           // partial sums of x, x^2 (kld)
   float *dn_map = nullptr, *gray_gx = nullptr, *gray_gy = nullptr;        // edge / smooth losses: dense map, image gradients
+  float *pt_a = nullptr, *pt_G = nullptr;                                 // closed-form loss: per-point scratch
   bool have_gray = false;
   float q_lo = 0.01f, q_hi = 0.99f;                                       // norm="percentile"
   float *pc_vals = nullptr, *pc_sorted = nullptr, *pc_range = nullptr;
@@ -408,7 +409,8 @@ struct Engine {
   void* pc_tmp = nullptr;
   size_t pc_tmp_bytes = 0;
   void percentile_ranges(const float* sparse);
-  void set_options(int projection, int inv, int opt, const float* loss_weights4, int kld_mode, float kld_weight, float qlo, float qhi);
+  void set_options(int projection, int inv, int opt, const float* loss_weights4, int kld_mode, float kld_weight, float qlo, float qhi,
+                   int closed_form);
   bool prepared = false, begun = false;
   int steps_done = 0;
   long long launches = 0;
@@ -1310,6 +1312,7 @@ inline Engine::Engine(const mdc_config& c) : cfg(c) {
   eps_part = arena.make<float>(1ull * N * parts_per_img), g_part = arena.make<float>(1ull * N * parts_per_img);
   x1_part = arena.make<float>(1ull * N * parts_per_img), x2_part = arena.make<float>(1ull * N * parts_per_img);
   opts = arena.make<TailOpts>(1);
+  pt_a = arena.make<float>(1ull * N * H * W), pt_G = arena.make<float>(1ull * N * H * W);
   dn_map = arena.make<float>(1ull * N * H * W), gray_gx = arena.make<float>(1ull * N * H * W), gray_gy = arena.make<float>(1ull * N * H * W);
   dmean = arena.make<float>(1ull * N * PPH * PPW);
   pt_idx = arena.make<int>(1ull * N * H * W), pt_val = arena.make<float>(1ull * N * H * W);
@@ -1644,6 +1647,8 @@ inline void Engine::step_launches() {
   run_ops(dec_ops, false);
   dbg_points("after decoder fwd");
   launch_k(loss_points_kernel, dim3(N), dim3(512), 0, stream, dec_out->d, g, pt_idx, pt_val, pt_off, gminmax, depth_minmax, opts, accum, dmean);
+  launch_k(loss_points_cf_kernel, dim3(N), dim3(512), 0, stream, dec_out->d, g, pt_idx, pt_val, pt_off, depth_minmax, opts, accum, dmean,
+           pt_a, pt_G);  // returns at once unless closed_form
   const long long npix = 1LL * N * PPH * PPW, opix = 1LL * N * H * W;
   // "edge" / "smooth" (marigold_dc.py:195-236); both return immediately unless loss_funcs lists them
   launch_k(dense_map_kernel, dim3(static_cast<int>((opix + 255) / 256)), dim3(256), 0, stream, dec_out->d, g, gminmax, depth_minmax, opts,
@@ -1760,7 +1765,10 @@ inline void Engine::percentile_ranges(const float* sparse) {
   }
   MDC_CUDA(cudaGetLastError());
 }
-inline void Engine::set_options(int projection, int inv, int opt, const float* w4, int kld_mode, float kld_weight, float qlo, float qhi) {
+inline void Engine::set_options(int projection, int inv, int opt, const float* w4, int kld_mode, float kld_weight, float qlo, float qhi,
+                                int closed_form) {
+  MDC_CHECK(!(closed_form && w4 && (w4[2] != 0.f || w4[3] != 0.f)),
+            "closed_form with edge / smooth losses is not implemented (gradient of the dense terms through the least-squares fit)");
   MDC_CHECK(projection >= 0 && projection <= 2, "Unknown projection method: %d (0 linear, 1 log, 2 log10)", projection);
   MDC_CHECK(opt >= 0 && opt <= 2, "Unknown optimizer: %d (0 adam, 1 sgd, 2 adagrad)", opt);
   MDC_CHECK(kld_mode >= 0 && kld_mode <= 2, "Unknown mode: %d (0 off, 1 simple, 2 strict)", kld_mode);
@@ -1769,6 +1777,7 @@ inline void Engine::set_options(int projection, int inv, int opt, const float* w
   h_opts.projection = projection, h_opts.inv = inv ? 1 : 0, h_opts.opt = opt, h_opts.kld_mode = kld_mode, h_opts.kld_weight = kld_weight;
   h_opts.w_l1 = w4[0], h_opts.w_l2 = w4[1], h_opts.w_edge = w4[2], h_opts.w_smooth = w4[3];
   q_lo = qlo, q_hi = qhi;
+  h_opts.closed_form = closed_form ? 1 : 0;
 }
 
 // One call per frame: image prologue + sparse-depth normalisation + per-call state.

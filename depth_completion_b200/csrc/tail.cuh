@@ -45,6 +45,7 @@ struct TailOpts {
   float w_l1, w_l2;  // how many times "l1" / "l2" appear in loss_funcs (:177-193 loops over the list)
   float w_edge, w_smooth;  // likewise for "edge" / "smooth" (:195-236)
   float lr_x, lr_s;  // learning rates of the latent and of scale / shift (:649, :776-783)
+  int closed_form;   // 1: scale / shift refitted by least squares every step instead of learned (:332-336)
 };
 __device__ __forceinline__ float project_depth(float d, int projection) {
   return projection == 1 ? logf(d) : projection == 2 ? log10f(d) : d;
@@ -159,6 +160,7 @@ __global__ void loss_points_kernel(const bf16* __restrict__ dec, TailGeom g, con
   ptx::pdl_wait();
   ptx::pdl_launch();
   __shared__ float red[32];
+  if (opts->closed_form) return;  // loss_points_cf_kernel does this step's loss
   const int n = blockIdx.x;
   const int p0 = pt_off[n], p1 = pt_off[n + 1];
   const float cnt = static_cast<float>(p1 - p0);
@@ -274,6 +276,93 @@ __device__ __forceinline__ void projected_ends(const float* __restrict__ depth_m
     plo = a, phi = b;
   }
 }
+// closed_form=True while the latent is trained (marigold_dc.py:332-336 inside the loop): every step refits
+// scale = cov(a, g) / (var(a) + 1e-7), shift = mean(g) - scale mean(a) over the valid points (:53-128) and the loss
+// gradient flows THROUGH the fit:  dL/da_k = s G_k + ds/da_k (sum G a - mean(a) sum G) - s sum G / n  with
+// G_i = dL/d dense_i and ds/da_k = ((g_k - mean g)(var + eps) - 2 cov (a_k - mean a)) / (var + eps)^2.
+// One block per sample; pt_a / pt_G are per-point scratch.  Returns at once unless opts->closed_form.
+__global__ void loss_points_cf_kernel(const bf16* __restrict__ dec, TailGeom g, const int* __restrict__ pt_idx,
+                                      const float* __restrict__ pt_val, const int* __restrict__ pt_off,
+                                      const float* __restrict__ depth_minmax, const TailOpts* __restrict__ opts,
+                                      StepAccum* __restrict__ acc, float* __restrict__ dmean, float* __restrict__ pt_a,
+                                      float* __restrict__ pt_G) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  if (!opts->closed_form) return;
+  __shared__ float red[32];
+  __shared__ float sh[6];
+  const int n = blockIdx.x, p0 = pt_off[n], p1 = pt_off[n + 1];
+  const float cnt = static_cast<float>(p1 - p0);
+  const int projection = opts->projection, inv = opts->inv;
+  const float w_l1 = opts->w_l1, w_l2 = opts->w_l2;
+  float dlo, dhi, plo, phi;
+  projected_ends(depth_minmax, n, projection, inv, dlo, dhi, plo, phi);
+  float sa = 0.f, sg = 0.f;
+  for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x) {
+    const int pix = pt_idx[i];
+    const float a = dense_pixel(dec, g, n, pix / g.W, pix % g.W, 1.f, 0.f, 0.f, 1.f, 0.f, 1.f, 0.f, 1.f, 0, 0).aff;
+    pt_a[i] = a;
+    sa += a, sg += pt_val[i];
+  }
+  sa = block_sum(sa, red);
+  sg = block_sum(sg, red);
+  if (threadIdx.x == 0) sh[0] = sa / cnt, sh[1] = sg / cnt;
+  __syncthreads();
+  const float am = sh[0], gm = sh[1];
+  float var = 0.f, cov = 0.f;
+  for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x) {
+    const float ac = pt_a[i] - am;
+    var += ac * ac, cov += ac * (pt_val[i] - gm);
+  }
+  var = block_sum(var, red);
+  cov = block_sum(cov, red);
+  if (threadIdx.x == 0) sh[2] = var + 1e-7f, sh[3] = cov;
+  __syncthreads();
+  const float vpe = sh[2], cv = sh[3], sc = cv / vpe, sf = gm - sc * am;
+  float l_sum = 0.f, SG = 0.f, SGa = 0.f;
+  for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x) {
+    const float a = pt_a[i], pre = sc * a + sf;
+    float dense = fminf(fmaxf(pre, 0.f), 1.f), chain = (pre < 0.f || pre > 1.f) ? 0.f : 1.f;
+    if (projection != 0 || inv != 0) {
+      const float metric = dense * (dhi - dlo) + dlo;
+      float pr = project_depth(metric, projection);
+      chain *= (dhi - dlo) * (projection == 1 ? 1.f / metric : projection == 2 ? 0.4342944819f / metric : 1.f);
+      if (inv) {
+        pr = 1.f / pr;
+        chain *= -pr * pr;
+      }
+      dense = (pr - plo) / (phi - plo);
+      chain /= (phi - plo);
+    }
+    const float diff = dense - pt_val[i];
+    l_sum += (w_l1 * fabsf(diff) + w_l2 * diff * diff) / cnt;
+    const float G = (w_l1 * ((diff > 0.f) - (diff < 0.f)) + w_l2 * 2.f * diff) / cnt * chain;
+    pt_G[i] = G;
+    SG += G, SGa += G * a;
+  }
+  l_sum = block_sum(l_sum, red);
+  SG = block_sum(SG, red);
+  SGa = block_sum(SGa, red);
+  if (threadIdx.x == 0) sh[4] = SG, sh[5] = SGa;
+  __syncthreads();
+  SG = sh[4], SGa = sh[5];
+  const float k1 = SGa - am * SG, k2 = sc * SG / cnt;
+  for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x) {
+    const float a = pt_a[i];
+    const float ds = ((pt_val[i] - gm) * vpe - 2.f * cv * (a - am)) / (vpe * vpe);
+    const float da = (sc * pt_G[i] + ds * k1 - k2) * 0.5f;  // 0.5: through (m + 1) / 2
+    const int pix = pt_idx[i];
+    const DensePix px = dense_pixel(dec, g, n, pix / g.W, pix % g.W, 1.f, 0.f, 0.f, 1.f, 0.f, 1.f, 0.f, 1.f, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (px.in[k] && px.w[k] != 0.f) atomicAdd(&dmean[px.q[k]], da * px.w[k]);
+  }
+  if (threadIdx.x == 0) {
+    acc->loss[n] = l_sum, acc->s_grad[n] = 0.f, acc->t_grad[n] = 0.f;  // no learned affine parameters (:764-775)
+    acc->scale[n] = sc, acc->shift[n] = sf;
+  }
+}
+
 // dn[N, H, W] fp32: the dense prediction in the guide's space (:829-862).
 __global__ void dense_map_kernel(const bf16* __restrict__ dec, TailGeom g, const float* __restrict__ gminmax,
                                  const float* __restrict__ depth_minmax, const TailOpts* __restrict__ opts,

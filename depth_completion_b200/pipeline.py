@@ -4,7 +4,7 @@
 
 Same constructor and call signature, same return tuple `(denses [N,1,H,W] fp32 metric, pred_latents [N,4,EH,EW])`,
 same ValueError conventions.  Non-default branches the north star leaves out of scope
-(closed_form=True while training the latent, per-input training, non-bilinear interpolation) raise NotImplementedError instead of silently doing something else.
+(per-input training, non-bilinear interpolation, closed_form with edge / smooth) raise NotImplementedError instead of silently doing something else.
 
 The host keeps, in PyTorch, only the argument checks and the seeded initial latent (torch's Philox stream,
 marigold_dc.py:661, :677-684); image preprocessing, the VAE encoder and the sparse-depth normalisation run inside the
@@ -191,8 +191,8 @@ class MarigoldDepthCompletionPipeline:
             raise ValueError("loss_funcs must contain at least one loss function")  # compute_loss, marigold_dc.py:171-172
         if kld and kld_mode not in ("simple", "strict"):
             raise ValueError(f"Unknown mode: {kld_mode}")                           # utils.py:78-79
-        if train_latents and closed_form:
-            unsupported.append("closed_form=True with train_latents=True (gradient through the least-squares fit)")
+        if train_latents and closed_form and any(f in ("edge", "smooth") for f in loss_funcs):
+            unsupported.append("closed_form=True with edge / smooth losses")
         if train_latents and train_method != "per-step":
             unsupported.append("train_method='per-input'")
         if interp_mode != "bilinear":
@@ -218,13 +218,14 @@ class MarigoldDepthCompletionPipeline:
         # marigold_dc.py:687-789 inside libmdc_b200.so (mdc_begin_frame): image preprocess + VAE encoder, sparse-depth
         # normalisation (mask, masked min / max, clamp, guide and its min / max), per-call optimiser state.
         # An empty mask raises ValueError like utils.py:132-136.
-        eng.set_options(projection, inv, opt, loss_funcs, kld, kld_weight, kld_mode, percentile)
+        eng.set_options(projection, inv, opt, loss_funcs, kld, kld_weight, kld_mode, percentile,
+                        closed_form=bool(closed_form and train_latents))
         eng.begin_frame(imgs, sparses, x, max_depth, min_depth, norm, lr_latent, lr_scaling)
         if _begin_only:  # bench.py: leave the engine at step 0 with everything resident in HBM
             return None, None
         if train_latents:
             eng.run(steps)                   # marigold_dc.py:799-904, no host sync inside
-            denses = eng.decode_final()      # marigold_dc.py:970-984
+            denses = eng.decode_final(closed_form=bool(closed_form))  # marigold_dc.py:970-984
         else:                                # no-grad branch: plain DDIM sampling + closed-form affine (:905-909, :53-128)
             eng.sample(steps)
             denses = eng.decode_final(closed_form=True)

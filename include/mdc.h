@@ -97,9 +97,12 @@ int mdc_begin(mdc_handle* h, const void* img_latents_bf16, const void* x_bf16, c
  *   loss_weights4_host  how many times "l1", "l2", "edge", "smooth" appear in loss_funcs (compute_loss, :171-236, sums
  *                the listed terms); "edge" needs the images, i.e. mdc_begin_frame rather than mdc_begin
  *   kld_mode     0 off, 1 "simple", 2 "strict" (utils.py:28-86), added as kld_weight * kld (:238-241)
- *   percentile_lo / hi   the quantiles of norm = "percentile" (:715-728) */
+ *   percentile_lo / hi   the quantiles of norm = "percentile" (:715-728)
+ *   closed_form  != 0: scale / shift are refitted by masked least squares every guided step (compute_affine_params,
+ *                :53-128, :332-336) and the loss gradient flows through the fit; finish with
+ *                mdc_decode_final_closed_form.  Not available together with edge / smooth. */
 int mdc_set_options(mdc_handle* h, int projection, int inv, int opt, const float* loss_weights4_host, int kld_mode,
-                    float kld_weight, float percentile_lo, float percentile_hi);
+                    float kld_weight, float percentile_lo, float percentile_hi, int closed_form);
 
 /* The whole per-frame prologue in one call (marigold_dc.py:687-756): mdc_encode on `imgs`, then the
  * sparse-depth normalisation on the device -- mask = sparse > 0, per-sample masked min / max ("minmax", norm_mode =

@@ -1,6 +1,6 @@
 """ORACLE (test infrastructure): restatement of the reference's guided denoising path,
 MarigoldDepthCompletionPipeline.__call__ (marigold_dc.py:467-985) with train_method="per-step" and either
-train_latents=True / closed_form=False (the guided loop) or train_latents=False (plain sampling + closed-form affine):
+train_latents=True (the guided loop, learned or closed-form scale / shift) or train_latents=False (plain sampling + closed-form affine):
 every projection (linear / log / log10, inv), norm (minmax /
 percentile / const), optimiser (adam / sgd / adagrad), loss term (l1, l2, edge, smooth) and the kld penalty,
 plus the helpers it uses (marigold_dc.py:23-50, :53-128, :131-243, :284-371; utils.py:28-86, :89-138, :692-739).
@@ -234,7 +234,7 @@ class OraclePipeline:
             d = 1 / d
         return (d - st["min_depths_proj"]) / (st["max_depths_proj"] - st["min_depths_proj"])
 
-    def guided_step(self, st, t, x, scales, shifts, optimizer, trace=None, idx=0, loss_kw=None):
+    def guided_step(self, st, t, x, scales, shifts, optimizer, trace=None, idx=0, loss_kw=None, closed_form=False):
         """One iteration of marigold_dc.py:801-904.  x, scales, shifts are Parameters updated in place."""
         N = x.shape[0]
         optimizer.zero_grad()
@@ -244,7 +244,11 @@ class OraclePipeline:
             eps_hat = (a_t ** 0.5) * v + ((1 - a_t) ** 0.5) * x
         x0 = self.scheduler.step(v, t, x).pred_original_sample
         aff = self.latent_to_affine(x0, st["orig_res"], st["padding"])
-        dense = self.affine_to_metric(aff, st["sparses_normed"], st["masks"], scales, shifts).clamp(min=0.0, max=1.0)
+        if closed_form:  # marigold_dc.py:332-336: refit by least squares, differentiably
+            cs, ct = compute_affine_params(aff, st["sparses_normed"], st["masks"])
+            dense = (cs.view(N, 1, 1, 1) * aff + ct.view(N, 1, 1, 1)).clamp(min=0.0, max=1.0)
+        else:
+            dense = self.affine_to_metric(aff, st["sparses_normed"], st["masks"], scales, shifts).clamp(min=0.0, max=1.0)
         dense = self.to_guide_space(dense, st)
         losses = compute_loss(dense, st["sparses_normed"], st["masks"], images=st.get("imgs"), pred_latents=x,
                               **(loss_kw or {}))
@@ -261,7 +265,8 @@ class OraclePipeline:
             x.data = self.scheduler.step(v, t, x).prev_sample
         if trace is not None:
             trace(dict(idx=idx, t=int(t), x_in=x_before, v=v.detach(), x0=x0.detach(), losses=losses.detach(),
-                       grad=raw_grad, s_grad=scales.grad.detach().clone(), t_grad=shifts.grad.detach().clone(),
+                       grad=raw_grad, s_grad=None if scales.grad is None else scales.grad.detach().clone(),
+                       t_grad=None if shifts.grad is None else shifts.grad.detach().clone(),
                        x_adam=x_adam, x_out=x.detach().clone(), scales=scales.detach().clone(),
                        shifts=shifts.detach().clone(), eps_norm=en, grad_norm=gn))
         return losses.detach()
@@ -285,7 +290,7 @@ class OraclePipeline:
     def __call__(self, imgs, sparses, max_depth, min_depth=0.0, norm="minmax", pred_latents_prev=None, beta=0.9,
                  steps=50, resolution=768, lr=None, seed=2024, trace=None, max_steps=None, projection="linear",
                  inv=False, percentile=(0.01, 0.99), opt="adam", loss_funcs=None, kld=False, kld_weight=0.1,
-                 kld_mode="simple", train_latents=True):
+                 kld_mode="simple", train_latents=True, closed_form=None):
         if imgs.ndim != 4 or sparses.ndim != 4 or imgs.shape[0] != sparses.shape[0] or imgs.shape[-2:] != sparses.shape[-2:]:
             raise ValueError("Shape of image must be [N, C, H, W] and shape of sparse must be [N, 1, H, W]")
         N = imgs.shape[0]
@@ -293,21 +298,28 @@ class OraclePipeline:
         st = self.preprocess(imgs, sparses, max_depth, min_depth, norm, resolution, seed, pred_latents_prev, beta,
                              projection, inv, percentile)
         loss_kw = dict(loss_funcs=tuple(loss_funcs or ("l1", "l2")), kld=kld, kld_weight=kld_weight, kld_mode=kld_mode)
+        closed_form = (not train_latents) if closed_form is None else closed_form
         if not train_latents:
             return self.sample_closed_form(st, steps, max_steps)
         x = torch.nn.Parameter(st["x"])
         scales = torch.nn.Parameter(torch.ones(N, 1, 1, 1, device=self.device))
         shifts = torch.nn.Parameter(torch.zeros(N, 1, 1, 1, device=self.device))
-        groups = [{"params": [x], "lr": lr_latent}, {"params": [scales, shifts], "lr": lr_scaling}]
+        groups = [{"params": [x], "lr": lr_latent}]
+        if not closed_form:  # marigold_dc.py:764-783: no affine parameters in closed-form mode
+            groups.append({"params": [scales, shifts], "lr": lr_scaling})
         opt = {"adam": torch.optim.Adam, "sgd": torch.optim.SGD, "adagrad": torch.optim.Adagrad}[opt](groups)  # :776-789
         self.scheduler.set_timesteps(steps, device=self.device)
         for i, t in enumerate(self.scheduler.timesteps):
             if max_steps is not None and i >= max_steps:
                 break
-            self.guided_step(st, t, x, scales, shifts, opt, trace, i, loss_kw)
+            self.guided_step(st, t, x, scales, shifts, opt, trace, i, loss_kw, closed_form)
         with torch.no_grad():
             xd = x.detach()
             aff = self.latent_to_affine(xd, st["orig_res"], st["padding"])
-            dense = self.affine_to_metric(aff, st["sparses_normed"], st["masks"], scales, shifts).clamp(min=0.0, max=1.0)
+            if closed_form:
+                cs, ct = compute_affine_params(aff, st["sparses_normed"], st["masks"])
+                dense = (cs.view(N, 1, 1, 1) * aff + ct.view(N, 1, 1, 1)).clamp(min=0.0, max=1.0)
+            else:
+                dense = self.affine_to_metric(aff, st["sparses_normed"], st["masks"], scales, shifts).clamp(min=0.0, max=1.0)
             denses = dense * (st["max_depths"] - st["min_depths"]) + st["min_depths"]
         return denses, xd

@@ -212,6 +212,8 @@ def test_kld_gradient(setup, mode):
     dict(loss_funcs=["l1", "l2", "smooth", "edge"]),
     dict(kld=True, kld_weight=0.1, kld_mode="simple"),
     dict(kld=True, kld_weight=0.05, kld_mode="strict", loss_funcs=["l2"]),
+    dict(closed_form=True),
+    dict(closed_form=True, projection="log", min_depth=0.1, opt="adagrad"),
 ])
 def test_pipeline_options_match_oracle(setup, cuda, kw):
     """The drop-in class with each non-default option against the oracle in bf16 on the same GPU, 12 guided steps:
@@ -288,4 +290,38 @@ def test_no_grad_sampling_with_closed_form_affine(setup, cuda):
     guided, _ = pipe(img, sp, fr["max_depth"], steps=10, resolution=128)
     assert not torch.equal(guided, dense)
     with pytest.raises(NotImplementedError):
-        pipe(img, sp, fr["max_depth"], steps=10, resolution=128, closed_form=True)
+        pipe(img, sp, fr["max_depth"], steps=10, resolution=128, closed_form=True, loss_funcs=["l1", "smooth"])
+
+
+def test_closed_form_loss_gradient_flows_through_the_fit(setup):
+    """closed_form=True inside the guided loop (marigold_dc.py:332-336 via :53-128): loss and d loss / d decoder output
+    against autograd through compute_affine_params; the fitted scale / shift are reported by get_state."""
+    from oracle.marigold_dc import OraclePipeline, compute_affine_params, compute_loss
+
+    (unet, vae, ctx), eng = setup
+    dev = eng.device
+    img, sparse, x = _inputs(eng, seed=17)
+    eng.set_options(closed_form=True)
+    eng.begin_frame(img, sparse, x, 12.0, 0.0, "minmax")
+    ref = OraclePipeline(unet, vae, ctx).preprocess(img, sparse, 12.0, 0.0, "minmax", 125, 2024, None, 0.9)
+    g = torch.Generator(device=dev).manual_seed(5)
+    low = torch.randn(eng.n, 1, 6, 8, device=dev, generator=g)
+    dec = torch.nn.functional.interpolate(low, (eng.lh * 8, eng.lw * 8), mode="bicubic").repeat(1, 3, 1, 1) * 0.5
+    dec = (dec + 0.02 * torch.randn(dec.shape, device=dev, generator=g)).bfloat16().float()
+    ddec, loss, gs, gt = eng.dbg_loss(dec)
+    d = dec.clone().requires_grad_(True)
+    r16 = lambda v: v + (v.bfloat16().float() - v).detach()
+    y = r16((r16(d.mean(1, keepdim=True)).clip(-1, 1) + 1) / 2)
+    a = r16(torch.nn.functional.interpolate(y[:, :, : eng.ph, : eng.pw], (eng.H, eng.W), mode="bilinear"))
+    cs, ct = compute_affine_params(a, ref["sparses_normed"], ref["masks"])
+    dense = (cs.view(-1, 1, 1, 1) * a + ct.view(-1, 1, 1, 1)).clamp(0, 1)
+    lref = compute_loss(dense, ref["sparses_normed"], ref["masks"])
+    lref.backward(torch.ones_like(lref))
+    assert torch.allclose(loss.to(dev), lref.detach(), rtol=2e-2, atol=1e-4), (loss, lref)
+    cos = torch.nn.functional.cosine_similarity(ddec.flatten(), d.grad.flatten(), dim=0).item()
+    ratio = (ddec.norm() / d.grad.norm()).item()
+    assert cos > 0.97 and abs(ratio - 1) < 0.05, (cos, ratio)
+    assert gs.abs().max() == 0 and gt.abs().max() == 0  # no learned affine parameters in this mode
+    _, sc, sh, _ = eng.get_state()
+    assert torch.allclose(sc.to(dev), cs.detach(), rtol=1e-3, atol=1e-4) and torch.allclose(sh.to(dev), ct.detach(), rtol=1e-3, atol=1e-4)
+    eng.set_options()

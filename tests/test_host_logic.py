@@ -132,12 +132,12 @@ def test_pipeline_argument_validation_without_gpu():
     for kw in [dict(loss_funcs=[]), dict(kld=True, kld_mode="exact")]:  # compute_loss :171-172, utils.py:78-79
         with pytest.raises(ValueError):
             pipe(img, sp, 10.0, **kw)
-    for kw in [dict(closed_form=True), dict(train_method="per-input"), dict(interp_mode="bicubic")]:
+    for kw in [dict(closed_form=True, loss_funcs=["l1", "edge"]), dict(train_method="per-input"), dict(interp_mode="bicubic")]:
         with pytest.raises(NotImplementedError):
             pipe(img, sp, 10.0, **kw)
     # branches that used to be refused now reach the device (and fail only because there is none here)
     for kw in [dict(opt="adagrad"), dict(kld=True), dict(loss_funcs=["l1", "edge"]), dict(projection="log", min_depth=0.5),
-               dict(norm="percentile"), dict(train_latents=False)]:
+               dict(norm="percentile"), dict(train_latents=False), dict(closed_form=True)]:
         with pytest.raises(MdcError):
             pipe(img, sp, 10.0, resolution=128, steps=2, **kw)
     with pytest.raises(ValueError):  # 352x1216 at resolution 768
