@@ -218,8 +218,9 @@ class MarigoldDepthCompletionPipeline:
         # marigold_dc.py:687-789 inside libmdc_b200.so (mdc_begin_frame): image preprocess + VAE encoder, sparse-depth
         # normalisation (mask, masked min / max, clamp, guide and its min / max), per-call optimiser state.
         # An empty mask raises ValueError like utils.py:132-136.
-        eng.set_options(projection, inv, opt, loss_funcs, kld, kld_weight, kld_mode, percentile,
-                        closed_form=bool(closed_form and train_latents))
+        # the reference only looks at `percentile` when norm == "percentile" (marigold_dc.py:628-629, :715-728)
+        eng.set_options(projection, inv, opt, loss_funcs, kld, kld_weight, kld_mode,
+                        percentile if norm == "percentile" else (0.01, 0.99), closed_form=bool(closed_form and train_latents))
         eng.begin_frame(imgs, sparses, x, max_depth, min_depth, norm, lr_latent, lr_scaling)
         if _begin_only:  # bench.py: leave the engine at step 0 with everything resident in HBM
             return None, None
