@@ -96,10 +96,12 @@ int mdc_begin_frame(mdc_handle* h, const void* imgs, int img_dtype, int channels
   });
 }
 int mdc_set_options(mdc_handle* h, int projection, int inv, int opt, const float* loss_weights4_host, int kld_mode,
-                    float kld_weight, float percentile_lo, float percentile_hi, int closed_form) {
+                    float kld_weight, float percentile_lo, float percentile_hi, int closed_form,
+                    int interp_nearest) {
   return mdc::guarded([&] {
     MDC_CHECK(h, "null handle");
-    h->e->set_options(projection, inv, opt, loss_weights4_host, kld_mode, kld_weight, percentile_lo, percentile_hi, closed_form);
+    h->e->set_options(projection, inv, opt, loss_weights4_host, kld_mode, kld_weight, percentile_lo, percentile_hi, closed_form,
+                      interp_nearest);
   });
 }
 int mdc_run(mdc_handle* h, int n_steps) {
@@ -235,7 +237,7 @@ int mdc_dbg_loss(mdc_handle* h, const float* dec_nchw, float* ddec_nchw, float* 
     mdc::Engine* e = h->e;
     MDC_CHECK(e->begun, "mdc_begin first");
     mdc::load_nchw(e->dec_out, e->dec_out->d, dec_nchw, e->stream);
-    mdc::TailGeom g{e->N, e->H, e->W, e->ph, e->pw, e->PPH, e->PPW, e->dec_out->ld};
+    mdc::TailGeom g{e->N, e->H, e->W, e->ph, e->pw, e->PPH, e->PPW, e->dec_out->ld, e->interp_nearest};
     mdc::loss_points_kernel<<<e->N, 512, 0, e->stream>>>(e->dec_out->d, g, e->pt_idx, e->pt_val, e->pt_off, e->gminmax,
                                                          e->depth_minmax, e->opts, e->accum, e->dmean);
     mdc::loss_points_cf_kernel<<<e->N, 512, 0, e->stream>>>(e->dec_out->d, g, e->pt_idx, e->pt_val, e->pt_off, e->depth_minmax, e->opts,

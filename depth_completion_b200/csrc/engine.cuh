@@ -403,6 +403,7 @@ struct Engine {
   float *dn_map = nullptr, *gray_gx = nullptr, *gray_gy = nullptr;        // edge / smooth losses: dense map, image gradients
   float *pt_a = nullptr, *pt_G = nullptr;                                 // closed-form loss: per-point scratch
   bool have_gray = false;
+  int interp_nearest = 0;  // baked into the step graph through TailGeom: changing it drops the captured graph
   float q_lo = 0.01f, q_hi = 0.99f;                                       // norm="percentile"
   float *pc_vals = nullptr, *pc_sorted = nullptr, *pc_range = nullptr;
   int* pc_counts = nullptr;
@@ -410,7 +411,7 @@ struct Engine {
   size_t pc_tmp_bytes = 0;
   void percentile_ranges(const float* sparse);
   void set_options(int projection, int inv, int opt, const float* loss_weights4, int kld_mode, float kld_weight, float qlo, float qhi,
-                   int closed_form);
+                   int closed_form, int nearest);
   bool prepared = false, begun = false;
   int steps_done = 0;
   long long launches = 0;
@@ -1277,7 +1278,8 @@ inline void Engine::finalize_plans() {
   split_ws = arena.make<float>(split_ws_floats + 64);
   for (GemmPlan* g : split_plans) g->p.ws = split_ws;
   launches_per_step += static_cast<long long>(n_split_step);
-  launches_per_step += 9;  // tail kernels of step()
+  launches_per_step += 12;  // tail kernels of step(): 9 of the default path + closed-form loss + dense map / dense loss (the
+                            // last three return at once unless their option is set)
 }
 
 inline Engine::Engine(const mdc_config& c) : cfg(c) {
@@ -1624,7 +1626,7 @@ inline void Engine::step() {
 inline void Engine::step_launches() {
   const int hw = lh * lw, lat_pix = N * hw;
   const int pgrid = N * parts_per_img;
-  TailGeom g{N, H, W, ph, pw, PPH, PPW, dec_out->ld};
+  TailGeom g{N, H, W, ph, pw, PPH, PPW, dec_out->ld, interp_nearest};
   launch_k(begin_step_kernel, dim3(1), dim3(1024), 0, stream, tables, counter, cur, temb_cur, opts);
   launch_k(unet_input_kernel, dim3((lat_pix + 255) / 256), dim3(256), 0, stream, img_lat, x, N, hw, unet_in->d);
   auto dbg_points = [&](const char* tag) {  // MDC_DEBUG_SYNC: has anything scribbled over the compacted point list?
@@ -1715,7 +1717,7 @@ inline void Engine::decode_final(float* dense_out, bool closed_form) {
   launch_k(x0_kernel, dim3(N * parts_per_img), dim3(256), 0, stream, unet_out->d, x, tmp, N, hw, cfg.vae_scaling, dec_in->d, scratch, static_cast<float*>(nullptr),
            static_cast<float*>(nullptr));
   run_ops(dec_ops, false);
-  TailGeom g{N, H, W, ph, pw, PPH, PPW, dec_out->ld};
+  TailGeom g{N, H, W, ph, pw, PPH, PPW, dec_out->ld, interp_nearest};
   const long long tot = 1LL * N * H * W;
   if (closed_form) launch_k(affine_lsq_kernel, dim3(N), dim3(512), 0, stream, dec_out->d, g, pt_idx, pt_val, pt_off, accum);
   launch_k(dense_out_kernel, dim3(static_cast<int>((tot + 255) / 256)), dim3(256), 0, stream, dec_out->d, g, gminmax, depth_minmax, accum,
@@ -1766,7 +1768,12 @@ inline void Engine::percentile_ranges(const float* sparse) {
   MDC_CUDA(cudaGetLastError());
 }
 inline void Engine::set_options(int projection, int inv, int opt, const float* w4, int kld_mode, float kld_weight, float qlo, float qhi,
-                                int closed_form) {
+                                int closed_form, int nearest) {
+  if ((nearest ? 1 : 0) != interp_nearest) {  // kernel argument of the captured step: re-capture on the next step
+    if (step_graph) cudaGraphExecDestroy(step_graph);
+    step_graph = nullptr;
+    interp_nearest = nearest ? 1 : 0;
+  }
   MDC_CHECK(!(closed_form && w4 && (w4[2] != 0.f || w4[3] != 0.f)),
             "closed_form with edge / smooth losses is not implemented (gradient of the dense terms through the least-squares fit)");
   MDC_CHECK(projection >= 0 && projection <= 2, "Unknown projection method: %d (0 linear, 1 log, 2 log10)", projection);

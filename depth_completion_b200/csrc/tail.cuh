@@ -132,8 +132,16 @@ __global__ void x0_kernel(const bf16* __restrict__ v_nhwc, const bf16* __restric
 struct TailGeom {
   int N, H, W, ph, pw, PPH, PPW;
   long long ld_dec;  // pixel stride of the decoder output (8)
+  int nearest;       // interp_mode: 0 "bilinear", 1 "nearest" (marigold_dc.py:343, :366-370; predict.py:200-206)
 };
-__device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+// Source taps of one output index for F.interpolate(size=...): bilinear (align_corners=False) or, with `nearest`, the
+// single tap min(floor(dst * in / out), in - 1) with weight 1.
+__device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int& i0, int& i1, float& l1, int nearest) {
+  if (nearest) {
+    i0 = i1 = min(static_cast<int>(floorf(dst * scale)), in_size - 1);
+    l1 = 0.f;
+    return;
+  }
   float src = scale * (dst + 0.5f) - 0.5f;
   if (src < 0.f) src = 0.f;
   i0 = min(static_cast<int>(src), in_size - 1);
@@ -184,8 +192,8 @@ __global__ void loss_points_kernel(const bf16* __restrict__ dec, TailGeom g, con
     const float guide = pt_val[i];
     int y0, y1, x0, x1;
     float ly, lx;
-    bilinear_src(Y, sy, g.ph, y0, y1, ly);
-    bilinear_src(X, sx, g.pw, x0, x1, lx);
+    bilinear_src(Y, sy, g.ph, y0, y1, ly, g.nearest);
+    bilinear_src(X, sx, g.pw, x0, x1, lx, g.nearest);
     const long long base = 1LL * n * g.PPH * g.PPW;
     const long long q00 = base + 1LL * y0 * g.PPW + x0, q01 = base + 1LL * y0 * g.PPW + x1;
     const long long q10 = base + 1LL * y1 * g.PPW + x0, q11 = base + 1LL * y1 * g.PPW + x1;
@@ -241,8 +249,8 @@ __device__ __forceinline__ DensePix dense_pixel(const bf16* __restrict__ dec, co
   const float sy = static_cast<float>(g.ph) / g.H, sx = static_cast<float>(g.pw) / g.W;
   int y0, y1, x0, x1;
   float ly, lx;
-  bilinear_src(Y, sy, g.ph, y0, y1, ly);
-  bilinear_src(X, sx, g.pw, x0, x1, lx);
+  bilinear_src(Y, sy, g.ph, y0, y1, ly, g.nearest);
+  bilinear_src(X, sx, g.pw, x0, x1, lx, g.nearest);
   const long long base = 1LL * n * g.PPH * g.PPW;
   r.q[0] = base + 1LL * y0 * g.PPW + x0, r.q[1] = base + 1LL * y0 * g.PPW + x1;
   r.q[2] = base + 1LL * y1 * g.PPW + x0, r.q[3] = base + 1LL * y1 * g.PPW + x1;
@@ -696,8 +704,8 @@ __global__ void dense_out_kernel(const bf16* __restrict__ dec, TailGeom g, const
   const float sy = static_cast<float>(g.ph) / g.H, sx = static_cast<float>(g.pw) / g.W;
   int y0, y1, x0, x1;
   float ly, lx;
-  bilinear_src(Y, sy, g.ph, y0, y1, ly);
-  bilinear_src(X, sx, g.pw, x0, x1, lx);
+  bilinear_src(Y, sy, g.ph, y0, y1, ly, g.nearest);
+  bilinear_src(X, sx, g.pw, x0, x1, lx, g.nearest);
   const long long base = 1LL * n * g.PPH * g.PPW;
   bool in;
   const float a00 = affine_at(dec, g.ld_dec, base + 1LL * y0 * g.PPW + x0, in);

@@ -55,7 +55,7 @@ def _declare(l):
     l.mdc_begin_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                   C.c_int, C.c_float, C.c_float]
     l.mdc_set_options.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float,
-                                  C.c_int]
+                                  C.c_int, C.c_int]
     l.mdc_launch_count.argtypes = [C.c_void_p]
     l.mdc_launch_count.restype = C.c_longlong
     l.mdc_device_bytes.argtypes = [C.c_void_p]
@@ -228,19 +228,22 @@ class StepEngine:
     NORMS = {"minmax": 0, "const": 1, "percentile": 2}
 
     def set_options(self, projection="linear", inv=False, opt="adam", loss_funcs=("l1", "l2"), kld=False, kld_weight=0.1,
-                    kld_mode="simple", percentile=(0.01, 0.99), closed_form=False):
+                    kld_mode="simple", percentile=(0.01, 0.99), closed_form=False, interp_mode="bilinear"):
         """Non-default branches of the reference call (mdc_set_options; marigold_dc.py:467-493): they apply to the next
         begin / begin_frame.  loss_funcs is the reference's list (a term listed twice counts twice, :177-236)."""
         if projection not in self.PROJECTIONS:
             raise ValueError(f"Unknown projection method: {projection}")
         if opt not in self.OPTIMIZERS:
             raise ValueError(f"Unknown optimizer: {opt}")
+        if interp_mode not in ("bilinear", "nearest"):
+            raise NotImplementedError(f"interp_mode='{interp_mode}' (the reference CLI offers bilinear and nearest)")
         if kld and kld_mode not in self.KLD_MODES:
             raise ValueError(f"Unknown mode: {kld_mode}")
         w = np.array([sum(f == k for f in loss_funcs) for k in ("l1", "l2", "edge", "smooth")], dtype=np.float32)
         check(self.lib.mdc_set_options(self._h, self.PROJECTIONS[projection], int(bool(inv)), self.OPTIMIZERS[opt],
                                        w.ctypes.data_as(C.c_void_p), self.KLD_MODES[kld_mode] if kld else 0,
-                                       float(kld_weight), float(percentile[0]), float(percentile[1]), int(bool(closed_form))))
+                                       float(kld_weight), float(percentile[0]), float(percentile[1]), int(bool(closed_form)),
+                                       int(interp_mode == "nearest")))
 
     def begin_frame(self, imgs, sparses, x, max_depth, min_depth=0.0, norm="minmax", lr_latent=0.05, lr_scaling=0.005):
         """The per-frame prologue in one library call (mdc_begin_frame): image preprocess + VAE encoder, sparse-depth

@@ -195,7 +195,7 @@ class MarigoldDepthCompletionPipeline:
             unsupported.append("closed_form=True with edge / smooth losses")
         if train_latents and train_method != "per-step":
             unsupported.append("train_method='per-input'")
-        if interp_mode != "bilinear":
+        if interp_mode not in ("bilinear", "nearest"):  # the two modes the reference CLI offers (predict.py:200-206)
             unsupported.append(f"interp_mode='{interp_mode}'")
         if unsupported:
             raise NotImplementedError("outside the B200 hot path (guided per-step optimisation of the latent): "
@@ -220,7 +220,8 @@ class MarigoldDepthCompletionPipeline:
         # An empty mask raises ValueError like utils.py:132-136.
         # the reference only looks at `percentile` when norm == "percentile" (marigold_dc.py:628-629, :715-728)
         eng.set_options(projection, inv, opt, loss_funcs, kld, kld_weight, kld_mode,
-                        percentile if norm == "percentile" else (0.01, 0.99), closed_form=bool(closed_form and train_latents))
+                        percentile if norm == "percentile" else (0.01, 0.99), closed_form=bool(closed_form and train_latents),
+                        interp_mode=interp_mode)
         eng.begin_frame(imgs, sparses, x, max_depth, min_depth, norm, lr_latent, lr_scaling)
         if _begin_only:  # bench.py: leave the engine at step 0 with everything resident in HBM
             return None, None

@@ -100,9 +100,11 @@ int mdc_begin(mdc_handle* h, const void* img_latents_bf16, const void* x_bf16, c
  *   percentile_lo / hi   the quantiles of norm = "percentile" (:715-728)
  *   closed_form  != 0: scale / shift are refitted by masked least squares every guided step (compute_affine_params,
  *                :53-128, :332-336) and the loss gradient flows through the fit; finish with
- *                mdc_decode_final_closed_form.  Not available together with edge / smooth. */
+ *                mdc_decode_final_closed_form.  Not available together with edge / smooth.
+ *   interp_nearest  != 0: interp_mode = "nearest" for the resize of the prediction to the input resolution (:366-370)
+ *                instead of "bilinear" (the two modes predict.py:200-206 offers) */
 int mdc_set_options(mdc_handle* h, int projection, int inv, int opt, const float* loss_weights4_host, int kld_mode,
-                    float kld_weight, float percentile_lo, float percentile_hi, int closed_form);
+                    float kld_weight, float percentile_lo, float percentile_hi, int closed_form, int interp_nearest);
 
 /* The whole per-frame prologue in one call (marigold_dc.py:687-756): mdc_encode on `imgs`, then the
  * sparse-depth normalisation on the device -- mask = sparse > 0, per-sample masked min / max ("minmax", norm_mode =

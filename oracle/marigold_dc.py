@@ -243,7 +243,7 @@ class OraclePipeline:
             a_t = self.scheduler.alphas_cumprod[int(t)]
             eps_hat = (a_t ** 0.5) * v + ((1 - a_t) ** 0.5) * x
         x0 = self.scheduler.step(v, t, x).pred_original_sample
-        aff = self.latent_to_affine(x0, st["orig_res"], st["padding"])
+        aff = self.latent_to_affine(x0, st["orig_res"], st["padding"], st.get("interp_mode", "bilinear"))
         if closed_form:  # marigold_dc.py:332-336: refit by least squares, differentiably
             cs, ct = compute_affine_params(aff, st["sparses_normed"], st["masks"])
             dense = (cs.view(N, 1, 1, 1) * aff + ct.view(N, 1, 1, 1)).clamp(min=0.0, max=1.0)
@@ -281,7 +281,7 @@ class OraclePipeline:
             if max_steps is not None and i >= max_steps:
                 break
             x = self.scheduler.step(self.predict_noise(st["img_latents"], x, t), t, x).prev_sample
-        aff = self.latent_to_affine(x, st["orig_res"], st["padding"])
+        aff = self.latent_to_affine(x, st["orig_res"], st["padding"], st.get("interp_mode", "bilinear"))
         n = aff.shape[0]
         scales, shifts = compute_affine_params(aff, st["sparses_normed"], st["masks"])
         dense = (scales.view(n, 1, 1, 1) * aff + shifts.view(n, 1, 1, 1)).clamp(min=0.0, max=1.0)
@@ -290,7 +290,7 @@ class OraclePipeline:
     def __call__(self, imgs, sparses, max_depth, min_depth=0.0, norm="minmax", pred_latents_prev=None, beta=0.9,
                  steps=50, resolution=768, lr=None, seed=2024, trace=None, max_steps=None, projection="linear",
                  inv=False, percentile=(0.01, 0.99), opt="adam", loss_funcs=None, kld=False, kld_weight=0.1,
-                 kld_mode="simple", train_latents=True, closed_form=None):
+                 kld_mode="simple", train_latents=True, closed_form=None, interp_mode="bilinear"):
         if imgs.ndim != 4 or sparses.ndim != 4 or imgs.shape[0] != sparses.shape[0] or imgs.shape[-2:] != sparses.shape[-2:]:
             raise ValueError("Shape of image must be [N, C, H, W] and shape of sparse must be [N, 1, H, W]")
         N = imgs.shape[0]
@@ -298,6 +298,7 @@ class OraclePipeline:
         st = self.preprocess(imgs, sparses, max_depth, min_depth, norm, resolution, seed, pred_latents_prev, beta,
                              projection, inv, percentile)
         loss_kw = dict(loss_funcs=tuple(loss_funcs or ("l1", "l2")), kld=kld, kld_weight=kld_weight, kld_mode=kld_mode)
+        st["interp_mode"] = interp_mode
         closed_form = (not train_latents) if closed_form is None else closed_form
         if not train_latents:
             return self.sample_closed_form(st, steps, max_steps)
@@ -315,7 +316,7 @@ class OraclePipeline:
             self.guided_step(st, t, x, scales, shifts, opt, trace, i, loss_kw, closed_form)
         with torch.no_grad():
             xd = x.detach()
-            aff = self.latent_to_affine(xd, st["orig_res"], st["padding"])
+            aff = self.latent_to_affine(xd, st["orig_res"], st["padding"], interp_mode)
             if closed_form:
                 cs, ct = compute_affine_params(aff, st["sparses_normed"], st["masks"])
                 dense = (cs.view(N, 1, 1, 1) * aff + ct.view(N, 1, 1, 1)).clamp(min=0.0, max=1.0)

@@ -325,3 +325,55 @@ def test_closed_form_loss_gradient_flows_through_the_fit(setup):
     _, sc, sh, _ = eng.get_state()
     assert torch.allclose(sc.to(dev), cs.detach(), rtol=1e-3, atol=1e-4) and torch.allclose(sh.to(dev), ct.detach(), rtol=1e-3, atol=1e-4)
     eng.set_options()
+
+
+def test_interp_mode_nearest(setup, cuda):
+    """interp_mode="nearest" (predict.py:200-206; marigold_dc.py:366-370): the prediction is resized to the input
+    resolution with F.interpolate(mode="nearest") in the loop and in the final decode."""
+    from depth_completion_b200.pipeline import MarigoldDepthCompletionPipeline
+    from depth_completion_b200.synthetic import make_frame
+    from oracle.marigold_dc import OraclePipeline
+
+    (unet, vae, ctx), eng = setup
+    dev = eng.device
+    # kernel level: loss + gradient at 80x111 <- 90x125 (non-integer ratio) against autograd
+    img, sparse, x = _inputs(eng, seed=19)
+    eng.set_options(interp_mode="nearest")
+    eng.begin_frame(img, sparse, x, 12.0, 0.0, "minmax")
+    ref = OraclePipeline(unet, vae, ctx).preprocess(img, sparse, 12.0, 0.0, "minmax", 125, 2024, None, 0.9)
+    g = torch.Generator(device=dev).manual_seed(5)
+    dec = (torch.randn(eng.n, 3, eng.lh * 8, eng.lw * 8, device=dev, generator=g) * 0.6).bfloat16().float()
+    ddec, loss, gs, gt = eng.dbg_loss(dec)
+    d = dec.clone().requires_grad_(True)
+    r16 = lambda v: v + (v.bfloat16().float() - v).detach()
+    y = r16((r16(d.mean(1, keepdim=True)).clip(-1, 1) + 1) / 2)
+    a = torch.nn.functional.interpolate(y[:, :, : eng.ph, : eng.pw], (eng.H, eng.W), mode="nearest")
+    from oracle.marigold_dc import compute_loss, masked_minmax
+
+    N = eng.n
+    gmin, gmax = masked_minmax(ref["sparses_normed"].view(N, -1), ref["masks"].view(N, -1), dim=-1)
+    dense = ((gmax - gmin).view(-1, 1, 1, 1) * a).clamp(0, 1)
+    lref = compute_loss(dense, ref["sparses_normed"], ref["masks"])
+    lref.backward(torch.ones_like(lref))
+    assert torch.allclose(loss.to(dev), lref.detach(), rtol=1e-3, atol=1e-5), (loss, lref)
+    cos = torch.nn.functional.cosine_similarity(ddec.flatten(), d.grad.flatten(), dim=0).item()
+    assert cos > 0.99 and abs((ddec.norm() / d.grad.norm()).item() - 1) < 0.02, cos
+    eng.set_options()
+    # end to end, switching modes on one live pipeline (the step graph is re-captured when the mode changes)
+    fr = make_frame(H=90, W=120, n_points=100, seed=6)
+    im, sp = fr["img"].to(cuda), fr["sparse"].to(cuda)
+    pipe = MarigoldDepthCompletionPipeline(unet, vae)
+    pipe.empty_text_embedding = ctx
+    bil, _ = pipe(im, sp, fr["max_depth"], steps=8, resolution=128)
+    near, _ = pipe(im, sp, fr["max_depth"], steps=8, resolution=128, interp_mode="nearest")
+    bil2, _ = pipe(im, sp, fr["max_depth"], steps=8, resolution=128)
+    assert torch.equal(bil, bil2) and not torch.equal(bil, near)
+    d32, _ = OraclePipeline(copy.deepcopy(unet), copy.deepcopy(vae), ctx)(im, sp, fr["max_depth"], steps=8, resolution=128,
+                                                                          interp_mode="nearest")
+    d16, _ = OraclePipeline(copy.deepcopy(unet).bfloat16(), copy.deepcopy(vae).bfloat16(), ctx.bfloat16())(
+        im, sp, fr["max_depth"], steps=8, resolution=128, interp_mode="nearest")
+    rng = fr["max_depth"]
+    ours, refd = ((near - d32).abs().mean() / rng).item(), ((d16 - d32).abs().mean() / rng).item()
+    assert ours < max(2.0 * refd, 1e-2) + 1e-2, f"nearest: ours {ours:.4f}, torch-bf16 {refd:.4f}"
+    with pytest.raises(NotImplementedError):
+        pipe(im, sp, fr["max_depth"], steps=8, resolution=128, interp_mode="bicubic")

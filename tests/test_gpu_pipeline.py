@@ -134,8 +134,10 @@ def test_error_conventions(models, cuda):
         pipe(img, sp, 10.0, opt="lion")
     with pytest.raises(ValueError):  # empty mask
         pipe(img, torch.zeros_like(sp), 10.0, resolution=128, steps=2)
+    with pytest.raises(ValueError):  # compute_loss, marigold_dc.py:171-172
+        pipe(img, sp, 10.0, resolution=128, steps=2, loss_funcs=[])
     with pytest.raises(NotImplementedError):
-        pipe(img, sp, 10.0, opt="sgd")
+        pipe(img, sp, 10.0, train_method="per-input")
 
 
 @pytest.mark.parametrize("H,W,res,kind,max_depth", [(88, 304, 304, "kitti", 80.0),   # config (c) shape /4: latent 11x38

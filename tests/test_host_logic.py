@@ -137,7 +137,7 @@ def test_pipeline_argument_validation_without_gpu():
             pipe(img, sp, 10.0, **kw)
     # branches that used to be refused now reach the device (and fail only because there is none here)
     for kw in [dict(opt="adagrad"), dict(kld=True), dict(loss_funcs=["l1", "edge"]), dict(projection="log", min_depth=0.5),
-               dict(norm="percentile"), dict(train_latents=False), dict(closed_form=True)]:
+               dict(norm="percentile"), dict(train_latents=False), dict(closed_form=True), dict(interp_mode="nearest")]:
         with pytest.raises(MdcError):
             pipe(img, sp, 10.0, resolution=128, steps=2, **kw)
     with pytest.raises(ValueError):  # 352x1216 at resolution 768

@@ -310,7 +310,8 @@ def test_oracle_projection_and_percentile_normalisation():
 
 @pytest.mark.parametrize("kw", [dict(projection="log", min_depth=0.1), dict(opt="sgd"), dict(opt="adagrad"),
                                 dict(loss_funcs=("l1", "edge", "smooth")), dict(kld=True, kld_mode="strict"),
-                                dict(norm="percentile", inv=True, min_depth=0.1), dict(closed_form=True)])
+                                dict(norm="percentile", inv=True, min_depth=0.1), dict(closed_form=True),
+                                dict(interp_mode="nearest")])
 def test_oracle_runs_every_option(kw):
     unet, vae = tiny_models()
     pipe = om.OraclePipeline(unet, vae, om.make_empty_text_embedding(64))
