@@ -94,6 +94,8 @@ class MarigoldDepthCompletionPipeline:
             if m is not None and hasattr(m, "to"):
                 m.to(self.device)
         self._sd_cache = None
+        for eng in self._engines.values():  # free the old device's workspace instead of waiting for the collector
+            eng.close()
         self._engines.clear()
         return self
 

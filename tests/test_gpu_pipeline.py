@@ -243,3 +243,33 @@ def test_sequence_driver_with_temporal_prior(models, cuda):
     assert torch.equal(dense, torch.cat(manual, 0)) and torch.equal(last, prev)
     d2, rng2, _ = complete_sequence(pipe, img, sp, 10.0, batch_size=2, steps=6, resolution=128, rank=1, world=2)
     assert rng2 == (2, 3) and d2.shape == (1, 1, 96, 128)
+
+
+def test_dataset_front_end_on_the_gpu(models, cuda, tmp_path):
+    """Files in, files out: dataset_io.complete_dataset drives the drop-in class over a dataset directory
+    written to disk (JPEG images, depth-coded sparse PNGs) and stores one dense map per pair; the stored map equals a
+    direct call on the decoded tensors."""
+    from PIL import Image
+
+    from depth_completion_b200 import dataset_io as dio
+    from depth_completion_b200.pipeline import MarigoldDepthCompletionPipeline
+
+    unet, vae, ctx, _, _ = models
+    src, dst = tmp_path / "src", tmp_path / "dst"
+    (src / "seq" / "image").mkdir(parents=True)
+    (src / "seq" / "sparse").mkdir(parents=True)
+    for k in range(3):
+        fr = _frame("cpu", H=96, W=128, n_points=100, seed=20 + k)
+        Image.fromarray(fr["img"][0].permute(1, 2, 0).numpy()).save(src / "seq" / "image" / f"{k:04d}.png")
+        Image.fromarray(dio.encode_depth_png(fr["sparse"][0, 0], 10.0)).save(src / "seq" / "sparse" / f"{k:04d}.png")
+    pipe = MarigoldDepthCompletionPipeline(unet, vae).to(cuda)
+    pipe.empty_text_embedding = ctx
+    saved = dio.complete_dataset(pipe, src, dst, max_depth=10.0, max_sparse_depth=10.0, batch_size=2, compress="npz",
+                                 steps=6, resolution=128)
+    assert [p.name for p in saved["seq"]] == ["0000.npz", "0001.npz", "0002.npz"]
+    img = dio.load_rgb(src / "seq" / "image" / "0002.png")[None].to(cuda)
+    sp = dio.to_depth(dio.load_rgb(src / "seq" / "sparse" / "0002.png")[None].to(cuda), 10.0)
+    direct, _ = pipe(img, sp, 10.0, steps=6, resolution=128)
+    stored = torch.from_numpy(dio.load_dense(dst / "seq" / "dense" / "0002.npz")).to(cuda)
+    assert stored.shape == (1, 96, 128) and torch.isfinite(stored).all()
+    assert torch.equal(stored, direct[0])
