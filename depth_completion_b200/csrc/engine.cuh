@@ -472,6 +472,7 @@ struct Engine {
   float* fr_stats = nullptr;     // per sample: lo, hi, guide min, guide max, valid count
   void read_tensor(const std::string& name, int which, float* out_nchw);
   long long launches_per_step = 0;
+  long long launches_per_sample_step = 3;  // no-grad step: step tables + UNet input + UNet forward ops + DDIM update
   // split-K: plans with few output tiles and a long K loop share one fp32 partial-sum workspace
   std::vector<GemmPlan*> split_plans;
   size_t split_ws_floats = 0;
@@ -1274,6 +1275,8 @@ inline void Engine::finalize_plans() {
     if (ops == &enc_ops) continue;  // forward only, not part of the guided step
     for (auto it = ops->rbegin(); it != ops->rend(); ++it) (*it)->plan_bwd();
     for (auto& op : *ops) launches_per_step += op->n_fwd() + op->n_bwd();
+    if (ops == &unet_ops)
+      for (auto& op : *ops) launches_per_sample_step += op->n_fwd();
   }
   split_ws = arena.make<float>(split_ws_floats + 64);
   for (GemmPlan* g : split_plans) g->p.ws = split_ws;
@@ -1677,7 +1680,6 @@ inline void Engine::sample_launches() {
 inline void Engine::sample_step() {
   MDC_CHECK(begun, "mdc_sample called before mdc_begin");
   MDC_CHECK(steps_done < cfg.steps, "all %d steps already done", cfg.steps);
-  const long long before = launches;
   if (!use_graph) {
     sample_launches();
   } else {
@@ -1697,7 +1699,7 @@ inline void Engine::sample_step() {
     }
     MDC_CUDA(cudaGraphLaunch(sample_graph, stream));
   }
-  (void)before;
+  launches += launches_per_sample_step;
   ++steps_done;
 }
 
