@@ -285,6 +285,11 @@ def test_dataset_front_end_round_trip(tmp_path):
     dio.complete_dataset(EchoPipe(), src / "seq_a", dst / "chain", batch_size=4, use_prev_latent=True, compress=None)
     assert [c[:2] for c in calls] == [(1, False), (1, True)]  # serial chain, batch forced to 1 (predict.py:423-430, :697-699)
     assert (dst / "chain" / "dense" / "cam0" / "000.npy").exists()
+    # rank sharding of independent frames: every rank writes its own files, together they cover the dataset
+    parts = [dio.complete_dataset(EchoPipe(), src / "seq_a", dst / "sharded", compress="npy", rank=r, world=2)["seq_a"] for r in (0, 1)]
+    assert [len(p) for p in parts] == [1, 1] and sorted(p.name for p in parts[0] + parts[1]) == ["000.npy", "001.npy"]
+    with pytest.raises(ValueError):  # a serial chain cannot be sharded
+        dio.complete_dataset(EchoPipe(), src / "seq_a", dst / "bad", use_prev_latent=True, rank=0, world=2)
     with pytest.raises(ValueError):
         dio.save_tensor(torch.zeros(2), tmp_path / "x.npy", compress="npz")
     with pytest.raises(RuntimeError):
