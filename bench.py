@@ -302,6 +302,7 @@ def run_ours(args):
     total_ms = t.item()
     steps_per_s = world * args.steps / (total_ms * 1e-3)
 
+    accuracy = None
     # ---- end to end: pinned host inputs -> pipeline call (H2D, prologue, 50 steps, final decode) -> host dense
     e2e = None
     if not args.no_e2e:
@@ -326,6 +327,7 @@ def run_ours(args):
         e2e = {"value": frames * fs / dt, "unit": "steps/s", "frames_per_sec": frames / dt, "sec_per_frame": dt / args.frames,
                "h2d_bytes_per_step": (imgs_h[0].numel() + sparses_h[0].numel() * 4) / fs,
                "d2h_bytes_per_step": H * W * 4 / fs}
+        accuracy = holdout_accuracy(out_h, fr, args.frames)
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM / implicit-GEMM conv): FLOPs of its launches in one step
     #      / the sum of their in-situ durations (CUDA events around every launch of an instrumented step)
@@ -380,11 +382,27 @@ def run_ours(args):
             "frames_per_sec_device": steps_per_s / fs,
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "e2e_two_frames_in_flight": two,
+            "accuracy": accuracy,
             "device_mem_gb": dev_mem_gb,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def holdout_accuracy(dense_h, fr, n_frames):
+    """MAE / RMSE (utils.py:692-739) of rank 0's end-to-end dense maps in metres: at the hold-out points the loop never
+    saw and at the guidance points it fitted.  With random-init weights these are parity numbers (the GPU tests compare
+    them with the oracle's), not quality numbers.  Never raises: the bench line must not depend on it."""
+    try:
+        gt = fr["gt"][:n_frames].float()
+        err = dense_h[:n_frames].float() - gt
+        hold, seen = fr["holdout"][:n_frames].bool(), fr["sparse"][:n_frames] > 0
+        return {"holdout_mae_m": err[hold].abs().mean().item(), "holdout_rmse_m": err[hold].pow(2).mean().sqrt().item(),
+                "guided_mae_m": err[seen].abs().mean().item(), "holdout_points": int(hold.sum()), "guided_points": int(seen.sum()),
+                "note": "random-init weights: parity numbers, not quality"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
 
 
 def main():
