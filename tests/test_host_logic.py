@@ -290,6 +290,23 @@ def test_dataset_front_end_round_trip(tmp_path):
     assert [len(p) for p in parts] == [1, 1] and sorted(p.name for p in parts[0] + parts[1]) == ["000.npy", "001.npy"]
     with pytest.raises(ValueError):  # a serial chain cannot be sharded
         dio.complete_dataset(EchoPipe(), src / "seq_a", dst / "bad", use_prev_latent=True, rank=0, world=2)
+    # metrics.evaluate_dataset (analyze.py:225-300): the echo pipeline returned the sparse maps, so the error at the
+    # measured points is exactly zero; shifting one stored map by a constant gives that constant back
+    from depth_completion_b200 import metrics as mt
+
+    res = mt.evaluate_dataset(src / "seq_a", dst / "seq_a", 120.0, 0.0, 120.0, bin_size=40.0, batch_size=2)
+    assert res["overall"] == {"mae": 0.0, "rmse": 0.0} and res["num_points"] > 0 and len(res["bins"]) == 3
+    assert sum(b["num_points"] for b in res["bins"]) >= res["num_points"]  # bin edges are inclusive on both sides
+    f = dst / "seq_a" / "dense" / "cam0" / "000.npz"
+    np.savez_compressed(f, dio.load_dense(f) + 2.0)
+    res = mt.evaluate_dataset(src / "seq_a", dst / "seq_a", 120.0, 0.0, 200.0, batch_size=1)
+    assert abs(res["overall"]["mae"] - 1.0) < 1e-5 and abs(res["overall"]["rmse"] - 1.0) < 1e-5  # mean of per-batch 2.0 and 0.0
+    a, b = torch.tensor([1.0, 2.0, 5.0]), torch.tensor([0.0, 4.0, 5.0])
+    assert mt.mae(a, b).item() == 1.0 and abs(mt.rmse(a, b).item() - (5 / 3) ** 0.5) < 1e-6
+    assert mt.mae(a, b, torch.tensor([True, False, False])).item() == 1.0
+    assert mt.calc_bins(0.0, 100.0, 40.0) == [(0.0, 40.0), (40.0, 80.0), (80.0, 100.0)]
+    with pytest.raises(ValueError):
+        mt.calc_bins(5.0, 5.0, 1.0)
     with pytest.raises(ValueError):
         dio.save_tensor(torch.zeros(2), tmp_path / "x.npy", compress="npz")
     with pytest.raises(RuntimeError):
