@@ -229,7 +229,6 @@ def run_reference(args):
 def run_ours(args):
     import torch.distributed as dist
 
-    from depth_completion_b200 import prologue
     from depth_completion_b200.flops import step_flops
     from depth_completion_b200.pipeline import MarigoldDepthCompletionPipeline
     from depth_completion_b200.synthetic import make_batch

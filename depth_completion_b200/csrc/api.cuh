@@ -30,23 +30,52 @@ inline void store_nchw(Tensor* t, const bf16* src, float* dst, cudaStream_t st) 
 
 extern "C" {
 
-int mdc_create(const mdc_config* cfg, mdc_handle** out) {
+static int create_impl(const mdc_config* cfg, mdc_handle* share, mdc_handle** out) {
   return mdc::guarded([&] {
     MDC_CHECK(cfg && out, "null argument");
     auto* h = new mdc_handle();
     try {
-      h->e = new mdc::Engine(*cfg);
+      h->e = new mdc::Engine(*cfg, share ? share->e->bank : nullptr);
     } catch (...) {
       delete h;
       throw;
     }
-    for (auto& kv : h->e->wmap) h->keys.push_back(kv.first);
+    for (auto& kv : h->e->wmap()) h->keys.push_back(kv.first);
     for (auto& kv : h->e->named) h->tnames.push_back(kv.first);
     *out = h;
   });
 }
+int mdc_create(const mdc_config* cfg, mdc_handle** out) { return create_impl(cfg, nullptr, out); }
+int mdc_create_shared(const mdc_config* cfg, mdc_handle* share_weights_with, mdc_handle** out) {
+  return create_impl(cfg, share_weights_with, out);
+}
+int mdc_set_stream(mdc_handle* h, void* cuda_stream) {
+  return mdc::guarded([&] {
+    MDC_CHECK(h, "null handle");
+    h->e->set_stream(static_cast<cudaStream_t>(cuda_stream));
+  });
+}
+int mdc_release_workspace(mdc_handle* h) {
+  return mdc::guarded([&] {
+    MDC_CHECK(h, "null handle");
+    if (h->e->released) return;
+    MDC_CUDA(cudaSetDevice(h->e->cfg.device));
+    h->e->release_workspace();
+    h->tnames.clear();
+  });
+}
+int mdc_weights_loaded(mdc_handle* h) { return (h && h->e->weights_loaded()) ? 1 : 0; }
+int mdc_set_weights(mdc_handle* h, int n, const char* const* keys, const void* const* dev_ptrs, const long long* shapes4_host,
+                    const int* ndims_host, const int* dtypes_host) {
+  return mdc::guarded([&] {
+    MDC_CHECK(h && keys && dev_ptrs && shapes4_host && ndims_host && dtypes_host && n >= 0, "bad argument");
+    h->e->activate();
+    h->e->set_weights(n, keys, dev_ptrs, shapes4_host, ndims_host, dtypes_host);
+  });
+}
 void mdc_destroy(mdc_handle* h) {
   if (!h) return;
+  cudaSetDevice(h->e->cfg.device);
   cudaDeviceSynchronize();
   delete h->e;
   delete h;
@@ -58,7 +87,7 @@ const char* mdc_weight_key(mdc_handle* h, int i) {
 int mdc_weight_shape(mdc_handle* h, int i, long long* shape4_host, int* ndim_host) {
   return mdc::guarded([&] {
     MDC_CHECK(h && shape4_host && ndim_host && i >= 0 && i < static_cast<int>(h->keys.size()), "bad argument");
-    const mdc::WeightSlot* s = h->e->wmap.at(h->keys[i]).front();
+    const mdc::WeightSlot* s = h->e->wmap().at(h->keys[i]).front();
     if (s->kind == mdc::W_CONV3 || s->kind == mdc::W_UPCONV) {
       shape4_host[0] = s->out, shape4_host[1] = s->in, shape4_host[2] = 3, shape4_host[3] = 3, *ndim_host = 4;
     } else if (s->kind == mdc::W_LIN) {
@@ -71,6 +100,7 @@ int mdc_weight_shape(mdc_handle* h, int i, long long* shape4_host, int* ndim_hos
 int mdc_set_weight(mdc_handle* h, const char* key, const void* dev_ptr, const long long* shape_host, int ndim, int dtype) {
   return mdc::guarded([&] {
     MDC_CHECK(h && key && dev_ptr && shape_host, "null argument");
+    h->e->activate();
     h->e->set_weight(key, dev_ptr, shape_host, ndim, dtype);
   });
 }
@@ -78,6 +108,7 @@ int mdc_prepare(mdc_handle* h, const void* ctx_bf16, const float* alphas_cumprod
                 int n_steps) {
   return mdc::guarded([&] {
     MDC_CHECK(h && ctx_bf16 && alphas_cumprod_host && timesteps_host, "null argument");
+    h->e->activate();
     h->e->prepare(ctx_bf16, alphas_cumprod_host, timesteps_host, n_steps);
   });
 }
@@ -85,6 +116,7 @@ int mdc_begin(mdc_handle* h, const void* img_latents_bf16, const void* x_bf16, c
               const float* guide_minmax_host, const float* depth_minmax_host, float lr_latent, float lr_scaling) {
   return mdc::guarded([&] {
     MDC_CHECK(h && img_latents_bf16 && x_bf16 && guide && mask && guide_minmax_host && depth_minmax_host, "null argument");
+    h->e->activate();
     h->e->begin(img_latents_bf16, x_bf16, guide, mask, guide_minmax_host, depth_minmax_host, lr_latent, lr_scaling);
   });
 }
@@ -92,6 +124,7 @@ int mdc_begin_frame(mdc_handle* h, const void* imgs, int img_dtype, int channels
                     float max_depth, float min_depth, int norm_mode, float lr_latent, float lr_scaling) {
   return mdc::guarded([&] {
     MDC_CHECK(h, "null handle");
+    h->e->activate();
     h->e->begin_frame(imgs, img_dtype, channels, sparse, x_bf16, max_depth, min_depth, norm_mode, lr_latent, lr_scaling);
   });
 }
@@ -107,6 +140,7 @@ int mdc_set_options(mdc_handle* h, int projection, int inv, int opt, const float
 int mdc_run(mdc_handle* h, int n_steps) {
   return mdc::guarded([&] {
     MDC_CHECK(h, "null handle");
+    h->e->activate();
     for (int i = 0; i < n_steps; ++i) h->e->step();
     MDC_CUDA(cudaGetLastError());
   });
@@ -114,13 +148,15 @@ int mdc_run(mdc_handle* h, int n_steps) {
 int mdc_get_state(mdc_handle* h, void* x_out_bf16, float* scale_host, float* shift_host, float* loss_host) {
   return mdc::guarded([&] {
     MDC_CHECK(h, "null handle");
+    h->e->activate();
     mdc::Engine* e = h->e;
+    if (x_out_bf16)
+      MDC_CUDA(cudaMemcpyAsync(x_out_bf16, e->x, 8ull * e->N * e->lh * e->lw, cudaMemcpyDeviceToDevice, e->stream));
+    mdc::StepAccum a;
+    MDC_CUDA(cudaMemcpyAsync(&a, e->accum, sizeof(a), cudaMemcpyDeviceToHost, e->stream));
     MDC_CUDA(cudaStreamSynchronize(e->stream));
     MDC_CUDA(cudaGetLastError());
-    if (x_out_bf16)
-      MDC_CUDA(cudaMemcpy(x_out_bf16, e->x, 8ull * e->N * e->lh * e->lw, cudaMemcpyDeviceToDevice));
-    mdc::StepAccum a;
-    MDC_CUDA(cudaMemcpy(&a, e->accum, sizeof(a), cudaMemcpyDeviceToHost));
+    e->check_barrier_flag();
     for (int i = 0; i < e->N; ++i) {
       if (scale_host) scale_host[i] = a.scale[i];
       if (shift_host) shift_host[i] = a.shift[i];
@@ -131,12 +167,14 @@ int mdc_get_state(mdc_handle* h, void* x_out_bf16, float* scale_host, float* shi
 int mdc_encode(mdc_handle* h, const void* imgs, int dtype, int channels, void* latents_out_bf16) {
   return mdc::guarded([&] {
     MDC_CHECK(h, "null handle");
+    h->e->activate();
     h->e->encode(imgs, dtype, channels, latents_out_bf16);
   });
 }
 int mdc_sample(mdc_handle* h, int n_steps) {
   return mdc::guarded([&] {
     MDC_CHECK(h, "null handle");
+    h->e->activate();
     for (int i = 0; i < n_steps; ++i) h->e->sample_step();
     MDC_CUDA(cudaGetLastError());
   });
@@ -144,27 +182,29 @@ int mdc_sample(mdc_handle* h, int n_steps) {
 int mdc_decode_final_closed_form(mdc_handle* h, float* dense_out) {
   return mdc::guarded([&] {
     MDC_CHECK(h && dense_out, "null pointer");
+    h->e->activate();
     h->e->decode_final(dense_out, true);
   });
 }
 int mdc_decode_final(mdc_handle* h, float* dense_out) {
   return mdc::guarded([&] {
     MDC_CHECK(h && dense_out, "null argument");
+    h->e->activate();
     h->e->decode_final(dense_out);
   });
 }
 long long mdc_launch_count(mdc_handle* h) { return h ? h->e->launches : 0; }
-long long mdc_device_bytes(mdc_handle* h) { return h ? static_cast<long long>(h->e->arena.total) : 0; }
+long long mdc_device_bytes(mdc_handle* h) { return h ? static_cast<long long>(h->e->arena.total + h->e->bank->arena.total) : 0; }
 
 // ---------------------------------------------------------------------------------------------- debug
 int mdc_dbg_forward(mdc_handle* h, int which, int step, const float* in_nchw, float* out_nchw) {
-  return mdc::guarded([&] {
+  return mdc::guarded([&] { h->e->activate();
     mdc::Engine* e = h->e;
     MDC_CHECK(e->prepared, "prepare first");
     mdc::Tensor* in = which == 0 ? e->unet_in : e->dec_in;
     mdc::Tensor* out = which == 0 ? e->unet_out : e->dec_out;
     int s = step;
-    MDC_CUDA(cudaMemcpy(e->counter, &s, 4, cudaMemcpyHostToDevice));
+    e->copy_sync(e->counter, &s, 4, cudaMemcpyHostToDevice);
     mdc::begin_step_kernel<<<1, 1024, 0, e->stream>>>(e->tables, e->counter, e->cur, e->temb_cur, e->opts);
     mdc::load_nchw(in, in->d, in_nchw, e->stream);
     e->run_ops(which == 0 ? e->unet_ops : e->dec_ops, false);
@@ -174,7 +214,7 @@ int mdc_dbg_forward(mdc_handle* h, int which, int step, const float* in_nchw, fl
   });
 }
 int mdc_dbg_backward(mdc_handle* h, int which, const float* dout_nchw, float* din_nchw) {
-  return mdc::guarded([&] {
+  return mdc::guarded([&] { h->e->activate();
     mdc::Engine* e = h->e;
     mdc::Tensor* in = which == 0 ? e->unet_in : e->dec_in;
     mdc::Tensor* out = which == 0 ? e->unet_out : e->dec_out;
@@ -186,7 +226,7 @@ int mdc_dbg_backward(mdc_handle* h, int which, const float* dout_nchw, float* di
   });
 }
 int mdc_dbg_read_tensor(mdc_handle* h, const char* name, int which, float* out_nchw) {
-  return mdc::guarded([&] { h->e->read_tensor(name, which, out_nchw); });
+  return mdc::guarded([&] { h->e->activate(); h->e->read_tensor(name, which, out_nchw); });
 }
 int mdc_dbg_tensor_shape(mdc_handle* h, const char* name, int* nchw_host) {
   return mdc::guarded([&] {
@@ -200,40 +240,40 @@ const char* mdc_dbg_tensor_name(mdc_handle* h, int i) {
   return (i >= 0 && i < static_cast<int>(h->tnames.size())) ? h->tnames[i].c_str() : nullptr;
 }
 int mdc_dbg_read_x_adam(mdc_handle* h, void* x_out_bf16) {
-  return mdc::guarded([&] {
+  return mdc::guarded([&] { h->e->activate();
     mdc::Engine* e = h->e;
     MDC_CUDA(cudaStreamSynchronize(e->stream));
-    MDC_CUDA(cudaMemcpy(x_out_bf16, e->x_adam_dbg, 8ull * e->N * e->lh * e->lw, cudaMemcpyDeviceToDevice));
+    e->copy_sync(x_out_bf16, e->x_adam_dbg, 8ull * e->N * e->lh * e->lw, cudaMemcpyDeviceToDevice);
   });
 }
 int mdc_dbg_read_buffer(mdc_handle* h, const char* which, float* out_dev) {
-  return mdc::guarded([&] {
+  return mdc::guarded([&] { h->e->activate();
     mdc::Engine* e = h->e;
     const std::string w(which);
     const size_t lat = 4ull * e->N * e->lh * e->lw;
     MDC_CUDA(cudaStreamSynchronize(e->stream));
     if (w == "grad")
-      MDC_CUDA(cudaMemcpy(out_dev, e->gbuf, lat * 4, cudaMemcpyDeviceToDevice));
+      e->copy_sync(out_dev, e->gbuf, lat * 4, cudaMemcpyDeviceToDevice);
     else if (w == "dx_direct")
-      MDC_CUDA(cudaMemcpy(out_dev, e->dx_direct, lat * 4, cudaMemcpyDeviceToDevice));
+      e->copy_sync(out_dev, e->dx_direct, lat * 4, cudaMemcpyDeviceToDevice);
     else
       MDC_CHECK(false, "unknown buffer '%s'", which);
   });
 }
 int mdc_dbg_frame_state(mdc_handle* h, float* guide_dev, unsigned char* mask_dev, float* stats_host) {
-  return mdc::guarded([&] {
+  return mdc::guarded([&] { h->e->activate();
     mdc::Engine* e = h->e;
     MDC_CHECK(e->fr_guide != nullptr, "mdc_begin_frame has not been called");
     const size_t n = 1ull * e->N * e->H * e->W;
     MDC_CUDA(cudaStreamSynchronize(e->stream));
-    if (guide_dev) MDC_CUDA(cudaMemcpy(guide_dev, e->fr_guide, n * 4, cudaMemcpyDeviceToDevice));
-    if (mask_dev) MDC_CUDA(cudaMemcpy(mask_dev, e->fr_mask, n, cudaMemcpyDeviceToDevice));
-    if (stats_host) MDC_CUDA(cudaMemcpy(stats_host, e->fr_stats, 5ull * e->N * 4, cudaMemcpyDeviceToHost));
+    if (guide_dev) e->copy_sync(guide_dev, e->fr_guide, n * 4, cudaMemcpyDeviceToDevice);
+    if (mask_dev) e->copy_sync(mask_dev, e->fr_mask, n, cudaMemcpyDeviceToDevice);
+    if (stats_host) e->copy_sync(stats_host, e->fr_stats, 5ull * e->N * 4, cudaMemcpyDeviceToHost);
   });
 }
 int mdc_dbg_loss(mdc_handle* h, const float* dec_nchw, float* ddec_nchw, float* loss_host, float* sgrad_host,
                  float* tgrad_host) {
-  return mdc::guarded([&] {
+  return mdc::guarded([&] { h->e->activate();
     mdc::Engine* e = h->e;
     MDC_CHECK(e->begun, "mdc_begin first");
     mdc::load_nchw(e->dec_out, e->dec_out->d, dec_nchw, e->stream);
@@ -252,12 +292,12 @@ int mdc_dbg_loss(mdc_handle* h, const float* dec_nchw, float* ddec_nchw, float* 
     MDC_CUDA(cudaGetLastError());
     MDC_CUDA(cudaStreamSynchronize(e->stream));
     mdc::StepAccum a;
-    MDC_CUDA(cudaMemcpy(&a, e->accum, sizeof(a), cudaMemcpyDeviceToHost));
+    e->copy_sync(&a, e->accum, sizeof(a), cudaMemcpyDeviceToHost);
     for (int i = 0; i < e->N; ++i) loss_host[i] = a.loss[i], sgrad_host[i] = a.s_grad[i], tgrad_host[i] = a.t_grad[i];
   });
 }
 int mdc_dbg_update(mdc_handle* h, const float* v_nchw, const float* dz_nchw, const float* dunet_in_nchw) {
-  return mdc::guarded([&] {
+  return mdc::guarded([&] { h->e->activate();
     mdc::Engine* e = h->e;
     MDC_CHECK(e->begun, "mdc_begin first");
     const int hw = e->lh * e->lw, lat_pix = e->N * hw, pgrid = e->N * e->parts_per_img;
@@ -278,11 +318,39 @@ int mdc_dbg_update(mdc_handle* h, const float* v_nchw, const float* dz_nchw, con
     MDC_CUDA(cudaStreamSynchronize(e->stream));
   });
 }
+// Teacher forcing: puts the handle (after mdc_begin / mdc_begin_frame) into the state of guided step `step`: latent x and
+// its Adam moments [N,4,EH,EW] bf16 (device), per-sample scale / shift and their fp32 Adam moments (host, N floats each,
+// order: scale, shift, s_m, s_v, t_m, t_v; NULL keeps the current values).  The next mdc_run(h, 1) executes step `step`.
+int mdc_dbg_set_state(mdc_handle* h, int step, const void* x_bf16, const void* m1_bf16, const void* m2_bf16,
+                      const float* affine6_host) {
+  return mdc::guarded([&] {
+    h->e->activate();
+    mdc::Engine* e = h->e;
+    MDC_CHECK(e->begun, "mdc_begin first");
+    MDC_CHECK(step >= 0 && step < e->cfg.steps, "step %d out of range", step);
+    const size_t lat = 8ull * e->N * e->lh * e->lw;
+    if (x_bf16) MDC_CUDA(cudaMemcpyAsync(e->x, x_bf16, lat, cudaMemcpyDeviceToDevice, e->stream));
+    if (m1_bf16) MDC_CUDA(cudaMemcpyAsync(e->m1, m1_bf16, lat, cudaMemcpyDeviceToDevice, e->stream));
+    if (m2_bf16) MDC_CUDA(cudaMemcpyAsync(e->m2, m2_bf16, lat, cudaMemcpyDeviceToDevice, e->stream));
+    if (affine6_host) {
+      mdc::StepAccum a;
+      e->copy_sync(&a, e->accum, sizeof(a), cudaMemcpyDeviceToHost);
+      for (int i = 0; i < e->N; ++i) {
+        a.scale[i] = affine6_host[0 * e->N + i], a.shift[i] = affine6_host[1 * e->N + i];
+        a.s_m[i] = affine6_host[2 * e->N + i], a.s_v[i] = affine6_host[3 * e->N + i];
+        a.t_m[i] = affine6_host[4 * e->N + i], a.t_v[i] = affine6_host[5 * e->N + i];
+      }
+      e->copy_sync(e->accum, &a, sizeof(a), cudaMemcpyHostToDevice);
+    }
+    e->copy_sync(e->counter, &step, 4, cudaMemcpyHostToDevice);
+    e->steps_done = step;
+  });
+}
 int mdc_dbg_profile_gemm_step(mdc_handle* h, float* ms_host, double* flops_host, int* launches_host) {
-  return mdc::guarded([&] { h->e->profile_gemm_step(ms_host, flops_host, launches_host); });
+  return mdc::guarded([&] { h->e->activate(); h->e->profile_gemm_step(ms_host, flops_host, launches_host); });
 }
 int mdc_dbg_profile_ops(mdc_handle* h, const char* csv_path, int iters) {
-  return mdc::guarded([&] {
+  return mdc::guarded([&] { h->e->activate();
     mdc::Engine* e = h->e;
     FILE* f = fopen(csv_path, "w");
     MDC_CHECK(f != nullptr, "cannot open %s", csv_path);
@@ -322,7 +390,7 @@ int mdc_dbg_profile_ops(mdc_handle* h, const char* csv_path, int iters) {
   });
 }
 int mdc_dbg_time_tapes(mdc_handle* h, int iters, float* ms_host) {
-  return mdc::guarded([&] {
+  return mdc::guarded([&] { h->e->activate();
     mdc::Engine* e = h->e;
     cudaEvent_t e0, e1;
     MDC_CUDA(cudaEventCreate(&e0));

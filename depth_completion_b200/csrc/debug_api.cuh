@@ -2,6 +2,7 @@
 // They run a single kernel of the hot path on caller-provided device buffers so each kernel can be
 // checked against the oracle / a torch fp32 reference in isolation.
 #pragma once
+#include "attn.cuh"
 #include "gemm.cuh"
 #include "pack.cuh"
 
@@ -134,6 +135,166 @@ int mdc_dbg_conv3x3(int NB, int H, int W, int C, int Cout, const void* x, long l
     MDC_CUDA(cudaDeviceSynchronize());
     for (int i = 1; i < ncopy; ++i) cudaFree(copies[i]);
     if (ws) cudaFree(ws);
+    cudaFree(wpk);
+  });
+}
+
+// Self-attention exactly as the engine plans it (attn.cuh): head_dim 64 -> the fused tcgen05 flash kernels, otherwise
+// GEMM + softmax + GEMM.  qkv: [n, T, 3 * heads * dh] bf16 (q | k | v column blocks); o / dout: [n, T, heads * dh];
+// dqkv like qkv.  dout == NULL: forward only.  ms_out[0] / [1] = forward / backward time per call over `iters`.
+int mdc_dbg_attention(int n, int T, int heads, int dh, const void* qkv, void* o, const void* dout, void* dqkv, int iters,
+                      float* ms_out) {
+  return mdc::guarded([&] {
+    using namespace mdc;
+    MDC_CHECK(qkv && o && n >= 1 && T >= 1 && heads >= 1, "bad argument");
+    MDC_CHECK((dout == nullptr) == (dqkv == nullptr), "dout and dqkv must be given together");
+    set_kernel_attrs_for_device();
+    const int d = heads * dh;
+    const long long ldq = 3LL * d, ldo = d;
+    const size_t stat = static_cast<size_t>(n) * heads * T + 64;
+    float *lse2 = nullptr, *delta = nullptr, *S = nullptr;
+    bf16 *P = nullptr, *dummy_do = nullptr, *dummy_dq = nullptr;
+    MDC_CUDA(cudaMalloc(&lse2, stat * 4));
+    MDC_CUDA(cudaMalloc(&delta, stat * 4));
+    const bool bwd = dout != nullptr;
+    if (!bwd) {  // the planners encode tensor maps for the gradient operands too
+      MDC_CUDA(cudaMalloc(&dummy_do, 1ull * n * T * ldo * 2 + 256));
+      MDC_CUDA(cudaMalloc(&dummy_dq, 1ull * n * T * ldq * 2 + 256));
+    }
+    const bool flash = dh == 64 && !getenv("MDC_NO_FLASH");
+    if (!flash) {
+      const size_t pel = static_cast<size_t>(n) * heads * T * (((T + 7) / 8) * 8) + 64;
+      MDC_CUDA(cudaMalloc(&P, pel * 2));
+      MDC_CUDA(cudaMalloc(&S, pel * 4));
+    }
+    AttnPlan a = plan_attention(n, T, heads, dh, static_cast<const bf16*>(qkv), ldq, static_cast<bf16*>(o),
+                                bwd ? const_cast<bf16*>(static_cast<const bf16*>(dout)) : dummy_do, ldo,
+                                bwd ? static_cast<bf16*>(dqkv) : dummy_dq, ldq, lse2, delta, P, S, true);
+    cudaEvent_t e0, e1;
+    MDC_CUDA(cudaEventCreate(&e0));
+    MDC_CUDA(cudaEventCreate(&e1));
+    float ms[2] = {0.f, 0.f};
+    run_attention_fwd(a, 0);
+    MDC_CUDA(cudaStreamSynchronize(0));
+    if (iters > 0) {
+      MDC_CUDA(cudaEventRecord(e0, 0));
+      for (int i = 0; i < iters; ++i) run_attention_fwd(a, 0);
+      MDC_CUDA(cudaEventRecord(e1, 0));
+      MDC_CUDA(cudaEventSynchronize(e1));
+      MDC_CUDA(cudaEventElapsedTime(&ms[0], e0, e1));
+      ms[0] /= iters;
+    }
+    if (bwd) {
+      run_attention_bwd(a, 0);  // (the unfused path overwrites P with dS: run the forward again before every backward)
+      MDC_CUDA(cudaStreamSynchronize(0));
+      if (iters > 0) {
+        float tot = 0.f;
+        for (int i = 0; i < iters; ++i) {
+          run_attention_fwd(a, 0);
+          MDC_CUDA(cudaEventRecord(e0, 0));
+          run_attention_bwd(a, 0);
+          MDC_CUDA(cudaEventRecord(e1, 0));
+          MDC_CUDA(cudaEventSynchronize(e1));
+          float t = 0.f;
+          MDC_CUDA(cudaEventElapsedTime(&t, e0, e1));
+          tot += t;
+        }
+        ms[1] = tot / iters;
+      }
+    }
+    MDC_CUDA(cudaGetLastError());
+    MDC_CUDA(cudaDeviceSynchronize());
+    if (ms_out) ms_out[0] = ms[0], ms_out[1] = ms[1];
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    cudaFree(lse2), cudaFree(delta), cudaFree(P), cudaFree(S), cudaFree(dummy_do), cudaFree(dummy_dq);
+  });
+}
+
+// GroupNorm (+SiLU) forward and, with dy != NULL, backward on an NHWC bf16 tensor x [n, HW, C] (pixel stride C), with the
+// engine's kernel selection (norm.cuh).  mode: 0 automatic, 1 force the two-pass kernels, 2 require the single launch.
+// stats_out (optional): [n, groups, 2] (mean, rstd).  ms_out[0] / [1]: forward / backward time per call.
+int mdc_dbg_groupnorm(int n, int HW, int C, int groups, float eps, int silu, const void* x, const float* gamma,
+                      const float* beta, void* y, const void* dy, void* dx, int acc, int mode, float* stats_out, int iters,
+                      float* ms_out) {
+  return mdc::guarded([&] {
+    using namespace mdc;
+    MDC_CHECK(x && gamma && beta && y, "null argument");
+    set_kernel_attrs_for_device();
+    GNPlan p = plan_groupnorm(n, HW, C, groups, C, mode);
+    GNScratch sc;
+    float* stats = nullptr;
+    MDC_CUDA(cudaMalloc(&sc.partial, (p.partial_floats + 64) * 4));
+    MDC_CUDA(cudaMalloc(&sc.gstats, (2ull * groups * n + 64) * 4));
+    MDC_CUDA(cudaMalloc(&sc.ticket, (n + 16) * 4));
+    MDC_CUDA(cudaMalloc(&sc.bar, 64));
+    MDC_CUDA(cudaMalloc(&stats, (2ull * groups * n + 64) * 4));
+    MDC_CUDA(cudaMemset(sc.ticket, 0, (n + 16) * 4));
+    MDC_CUDA(cudaMemset(sc.bar, 0, 64));
+    cudaEvent_t e0, e1;
+    MDC_CUDA(cudaEventCreate(&e0));
+    MDC_CUDA(cudaEventCreate(&e1));
+    float ms[2] = {0.f, 0.f};
+    auto fwd = [&] { run_gn_fwd(p, static_cast<const bf16*>(x), static_cast<bf16*>(y), C, gamma, beta, eps, silu, stats, sc, 0); };
+    auto bwd = [&](int a) {
+      run_gn_bwd(p, static_cast<const bf16*>(x), static_cast<const bf16*>(dy), C, gamma, beta, silu, stats, static_cast<bf16*>(dx), C, a, sc, 0);
+    };
+    fwd();
+    MDC_CUDA(cudaStreamSynchronize(0));
+    if (iters > 0) {
+      MDC_CUDA(cudaEventRecord(e0, 0));
+      for (int i = 0; i < iters; ++i) fwd();
+      MDC_CUDA(cudaEventRecord(e1, 0));
+      MDC_CUDA(cudaEventSynchronize(e1));
+      MDC_CUDA(cudaEventElapsedTime(&ms[0], e0, e1));
+      ms[0] /= iters;
+    }
+    if (dy && dx) {
+      bwd(acc);
+      MDC_CUDA(cudaStreamSynchronize(0));
+      if (iters > 0 && !acc) {
+        MDC_CUDA(cudaEventRecord(e0, 0));
+        for (int i = 0; i < iters; ++i) bwd(0);
+        MDC_CUDA(cudaEventRecord(e1, 0));
+        MDC_CUDA(cudaEventSynchronize(e1));
+        MDC_CUDA(cudaEventElapsedTime(&ms[1], e0, e1));
+        ms[1] /= iters;
+      }
+    }
+    MDC_CUDA(cudaGetLastError());
+    MDC_CUDA(cudaDeviceSynchronize());
+    unsigned int flag = 0;
+    MDC_CUDA(cudaMemcpy(&flag, sc.bar + 2, 4, cudaMemcpyDeviceToHost));
+    if (stats_out) MDC_CUDA(cudaMemcpy(stats_out, stats, 2ull * groups * n * 4, cudaMemcpyDeviceToDevice));
+    if (ms_out) ms_out[0] = ms[0], ms_out[1] = ms[1];
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    cudaFree(sc.partial), cudaFree(sc.gstats), cudaFree(sc.ticket), cudaFree(sc.bar), cudaFree(stats);
+    MDC_CHECK(flag == 0, "GroupNorm grid barrier timed out");
+    MDC_CHECK(mode != 1 || (!p.fuse_f && !p.fuse_b), "mode 1 did not select the two-pass kernels");
+  });
+}
+
+// Fused nearest-2x upsample + conv3x3 (four 2x2 phase convolutions on the low-resolution input, gemm.cuh) and its input
+// gradient.  dgrad = 0: x [NB, H, W, C] -> out [NB, 2H, 2W, Cout] (+bias);  dgrad = 1: x is dy [NB, 2H, 2W, Cout] ->
+// out [NB, H, W, C].  w_oihw: [Cout][C][3][3] fp32.
+int mdc_dbg_upconv(int NB, int H, int W, int C, int Cout, const void* x, long long ldx, const float* w_oihw, int dgrad,
+                   const float* bias, void* out, long long ldc, int iters, float* ms_out) {
+  return mdc::guarded([&] {
+    using namespace mdc;
+    set_kernel_attrs_for_device();
+    const int Kp = (((dgrad ? Cout : C) + 63) / 64) * 64, rows = dgrad ? C : Cout;
+    __nv_bfloat16* wpk = nullptr;
+    MDC_CUDA(cudaMalloc(&wpk, sizeof(__nv_bfloat16) * (16ull * Kp * rows + 64)));
+    if (!dgrad)
+      pack_upconv_fwd_kernel<float><<<592, 256>>>(w_oihw, wpk, Cout, C, Kp);
+    else
+      pack_upconv_bwd_kernel<float><<<592, 256>>>(w_oihw, wpk, Cout, C, Kp);
+    MDC_CUDA(cudaGetLastError());
+    Epilogue e;
+    e.out = out, e.ldc = ldc, e.bias = bias;
+    GemmPlan g = dgrad ? plan_upconv_bwd(NB, H, W, C, Cout, x, ldx, wpk, e) : plan_upconv_fwd(NB, H, W, C, Cout, x, ldx, wpk, e);
+    float ms = time_plan(g, iters, 0);
+    if (ms_out) *ms_out = ms;
+    MDC_CUDA(cudaDeviceSynchronize());
     cudaFree(wpk);
   });
 }

@@ -19,8 +19,9 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "../../include/mdc.h"
-#include "flash.cuh"
+#include "attn.cuh"
 #include "gemm.cuh"
+#include "norm.cuh"
 #include "pack.cuh"
 #include "tail.cuh"
 
@@ -43,9 +44,12 @@ struct Arena {
   T* make(size_t n) {
     return static_cast<T*>(alloc(n * sizeof(T)));
   }
-  ~Arena() {
+  void free_all() {
     for (void* p : blocks) cudaFree(p);
+    blocks.clear();
+    total = 0;
   }
+  ~Arena() { free_all(); }
 };
 
 struct Tensor {
@@ -83,6 +87,29 @@ struct WeightSlot {
   float* vec = nullptr;         // VEC destination
   float vscale = 1.f, vshift = 0.f;  // VEC: stored as vscale * value + vshift (bias of a scaled / shifted epilogue)
   bool loaded = false;
+};
+
+// Packed weights live in a bank that several engines (same model configuration and device, different N / H / W /
+// resolution / steps) share: a new frame geometry builds new tapes and workspace but never re-packs the 1.8 GB of
+// parameters (mdc_create_shared).  Engines request their slots in the same deterministic order, so the i-th request for
+// a key maps to the i-th slot the first engine created for it.
+struct WeightBank {
+  Arena arena;
+  std::deque<WeightSlot> slots;
+  std::map<std::string, std::vector<WeightSlot*>> wmap;
+  std::map<std::string, std::pair<void*, size_t>> blobs;  // raw named buffers (fused q/k/v matrices)
+  int device = 0;
+  int model_sig[64];  // the mdc_config fields that determine the parameter set
+  void* blob(const std::string& name, size_t bytes) {
+    auto it = blobs.find(name);
+    if (it != blobs.end()) {
+      MDC_CHECK(it->second.second == bytes, "weight bank: blob '%s' has %zu bytes, requested %zu", name.c_str(), it->second.second, bytes);
+      return it->second.first;
+    }
+    void* p = arena.alloc(bytes);
+    blobs[name] = {p, bytes};
+    return p;
+  }
 };
 
 struct Engine;
@@ -128,21 +155,17 @@ struct GroupNormOp : Op {
   float eps;
   int groups, silu;
   float* stats;
-  GNShape s;
-  int threads, threads_b;
-  // single-launch variants (slab in shared memory + grid barrier) when the tensor is small enough
-  GNShape sfu;
-  bool fuse_f = false, fuse_b = false;
-  size_t smem_f = 0, smem_b = 0;
+  GNPlan plan;          // two-pass kernels, or the single-launch variants when the tensor is small enough (norm.cuh)
   bool acc = false;
+  bool have_stats = false;  // the producing GEMM's epilogue already writes this op's statistics (two-pass path only)
   void plan_bwd() override {
     acc = x->grad_set;
     x->grad_set = true;
   }
   void fwd(cudaStream_t st) override;
   void bwd(cudaStream_t st) override;
-  int n_fwd() const override { return fuse_f ? 1 : 2; }
-  int n_bwd() const override { return fuse_b ? 1 : 2; }
+  int n_fwd() const override { return plan.fuse_f ? 1 : (have_stats ? 1 : 2); }
+  int n_bwd() const override { return plan.fuse_b ? 1 : 2; }
 };
 struct LayerNormOp : Op {
   Tensor *x, *y;
@@ -177,24 +200,19 @@ struct GegluOp : Op {
                                                                      x->ld, acc);
   }
 };
-struct SelfAttnOp : Op {  // softmax(q k^T / sqrt(dh)) v over the tokens of each image; qkv [rows, 3*d] fused
+struct SelfAttnOp : Op {  // softmax(q k^T / sqrt(dh)) v over the tokens of each image; qkv [rows, 3*d] fused (attn.cuh)
   Engine* E;
   Tensor *qkv, *o;
-  int heads, dh, T;
-  long long ldS;
-  bf16* P;  // saved probabilities [n, heads, T, ldS] (unfused path only)
-  GemmPlan p_s, p_o, p_dv, p_dp, p_dq, p_dk;
-  bool use_flash = false;  // head_dim 64: fused tcgen05 flash kernels (flash.cuh); otherwise GEMM + softmax kernels
-  FlashPlan fp;
-  void plan_bwd() override;
-  void fwd(cudaStream_t st) override;
-  void bwd(cudaStream_t st) override;
-  int n_fwd() const override { return use_flash ? 1 : 3; }
-  int n_bwd() const override { return use_flash ? 3 : 5; }
+  AttnPlan a;
+  void plan_bwd() override { qkv->grad_set = true; }  // q, k, v gradient slices are each written exactly once
+  void fwd(cudaStream_t st) override { run_attention_fwd(a, st); }
+  void bwd(cudaStream_t st) override { run_attention_bwd(a, st); }
+  int n_fwd() const override { return a.use_flash ? 1 : 3; }
+  int n_bwd() const override { return a.use_flash ? 3 : 5; }
   void gemm_plans(std::vector<const GemmPlan*>& f, std::vector<const GemmPlan*>& b) const override {
-    if (use_flash) return;
-    f.push_back(&p_s), f.push_back(&p_o);
-    b.push_back(&p_dv), b.push_back(&p_dp), b.push_back(&p_dq), b.push_back(&p_dk);
+    if (a.use_flash) return;
+    f.push_back(&a.p_s), f.push_back(&a.p_o);
+    if (qkv->g) b.push_back(&a.p_dv), b.push_back(&a.p_dp), b.push_back(&a.p_dq), b.push_back(&a.p_dk);
   }
 };
 struct CrossAttn2Op : Op {  // attention over the 2 tokens of the empty-prompt embedding (step-invariant K, V)
@@ -339,14 +357,31 @@ struct Engine {
   Arena arena;
   std::deque<Tensor> tensors;
   std::map<std::string, Tensor*> named;
-  std::map<std::string, std::vector<WeightSlot*>> wmap;
-  std::deque<WeightSlot> wslots;
+  std::shared_ptr<WeightBank> bank;              // packed parameters, possibly shared with other engines
+  std::map<std::string, std::vector<WeightSlot*>>& wmap() { return bank->wmap; }
+  std::map<std::string, size_t> slot_cursor;     // how many slots of a key this engine has requested so far
+  WeightSlot* bank_slot(const std::string& key, WKind kind, int out, int in, bool& fresh);
   std::vector<std::unique_ptr<Op>> unet_ops, dec_ops, enc_ops;  // enc_ops: VAE encoder, forward only (per-frame prologue)
   bool alloc_grads = true;
   size_t n_split_step = 0;
   Tensor *enc_in = nullptr, *enc_out = nullptr;
   std::vector<std::unique_ptr<Op>>* cur_ops = nullptr;
-  cudaStream_t stream = 0;
+  // `stream` is where every launch of the public entry points is enqueued: the engine's own stream by default, or the
+  // caller's (mdc_set_stream; the Python binding passes torch's current stream on every call).  Graphs are captured
+  // on the private `cap_stream` (capture is not allowed on the legacy default stream) and launched on `stream`.
+  cudaStream_t stream = 0, own_stream = 0, cap_stream = 0;
+  void set_stream(cudaStream_t s) { stream = s ? s : own_stream; }
+  // stream-ordered copy + synchronisation (a plain cudaMemcpy runs on the legacy default stream, which is NOT ordered
+  // with a caller-provided non-blocking stream)
+  void copy_sync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    MDC_CUDA(cudaMemcpyAsync(dst, src, bytes, kind, stream));
+    MDC_CUDA(cudaStreamSynchronize(stream));
+  }
+  void activate() {
+    MDC_CHECK(!released, "this handle's workspace was released (mdc_release_workspace): it only keeps the packed weights alive");
+    MDC_CUDA(cudaSetDevice(cfg.device));
+  }  // every extern "C" entry: the handle's device becomes current
+  void check_barrier_flag();
 
   // geometry
   int N, H, W, ph, pw, PPH, PPW, lh, lw;
@@ -358,6 +393,7 @@ struct Engine {
   float* gn_gstats = nullptr;
   unsigned int* gn_ticket = nullptr;
   unsigned int* gn_bar = nullptr;  // grid barrier of the single-launch GroupNorm kernels (count, generation, timeout flag)
+  GNScratch gn_scratch() const { return GNScratch{gn_partial, gn_gstats, gn_ticket, gn_bar}; }
   float* attn_S = nullptr;
   size_t attn_S_floats = 0;
   // time embedding
@@ -395,6 +431,9 @@ struct Engine {
   int* pt_idx = nullptr;
   float* pt_val = nullptr;
   int* pt_off = nullptr;
+  int* pt_cnt = nullptr;            // valid points per sample (device)
+  StepCur* final_cur = nullptr;     // identity DDIM scalars for the final decode (x0 = x)
+  float* final_scratch = nullptr;
   float *gminmax = nullptr, *depth_minmax = nullptr;
   float lr_x = 0.05f, lr_s = 0.005f;
   TailOpts h_opts{0, 0, 0, 0, 0.1f, 1.f, 1.f, 0.f, 0.f, 0.05f, 0.005f, 0};  // defaults of marigold_dc.py:467-493; mdc_set_options
@@ -413,10 +452,12 @@ struct Engine {
   void set_options(int projection, int inv, int opt, const float* loss_weights4, int kld_mode, float kld_weight, float qlo, float qhi,
                    int closed_form, int nearest);
   bool prepared = false, begun = false;
+  bool released = false;  // mdc_release_workspace: tapes and workspace freed, the handle only keeps the weight bank alive
+  void release_workspace();
   int steps_done = 0;
   long long launches = 0;
 
-  explicit Engine(const mdc_config& c);
+  explicit Engine(const mdc_config& c, std::shared_ptr<WeightBank> share = nullptr);
   // builders
   Tensor* new_tensor(int n, int h, int w, int c, const std::string& name, bool with_grad = true, long long ld = 0);
   Tensor* view(Tensor* parent, int c0, int c, const std::string& name);
@@ -442,9 +483,13 @@ struct Engine {
   void finalize_plans();
   // runtime
   void set_weight(const std::string& key, const void* src, const long long* shape, int ndim, int dtype);
+  void set_weights(int n, const char* const* keys, const void* const* srcs, const long long* shapes4, const int* ndims, const int* dtypes);
+  bool weights_loaded();
   void prepare(const void* ctx_bf16, const float* alphas_cumprod, const int* timesteps, int n_steps);
   void begin(const void* img_latents, const void* x0, const float* guide, const uint8_t* mask, const float* gmm,
              const float* dmm, float lrx, float lrs);
+  void begin_state(const void* img_latents, const void* x0, const float* guide, const uint8_t* mask, float lrx, float lrs,
+                   const float* stats5_dev);
   void run_ops(std::vector<std::unique_ptr<Op>>& ops, bool backward);
   void step_launches();  // the fixed launch sequence of one guided step
   void step();           // replays it as a CUDA graph (captured once; every step-dependent value lives in device memory)
@@ -466,7 +511,6 @@ struct Engine {
   void encode(const void* imgs, int dtype, int channels, void* latents_out);
   void begin_frame(const void* imgs, int dtype, int channels, const float* sparse, const void* x0, float max_depth,
                    float min_depth, int norm_mode, float lrx, float lrs);
-  bf16* enc_lat = nullptr;       // img latents of the current frame (begin_frame)
   float* fr_guide = nullptr;     // normalised sparse depth of the current frame
   uint8_t* fr_mask = nullptr;
   float* fr_stats = nullptr;     // per sample: lo, hi, guide min, guide max, valid count
@@ -555,93 +599,10 @@ inline void LinearOp::bwd(cudaStream_t st) {
                                                                         acc_res);
 }
 inline void GroupNormOp::fwd(cudaStream_t st) {
-  if (fuse_f) {
-    launch_k(gn_fused_fwd_kernel, dim3(sfu.N * sfu.blocks_per_img), dim3(threads), smem_f, st, x->d, sfu, E->gn_partial, eps, stats, E->gn_bar,
-             gamma, beta, silu, y->d, y->ld);
-    return;
-  }
-  const int grid = s.N * s.blocks_per_img;
-  launch_k(gn_stats_kernel, dim3(grid), dim3(threads), ((threads + 31) / 32) * 2 * s.G * sizeof(float), st, x->d, s, E->gn_partial, eps, stats,
-           E->gn_ticket);
-  launch_k(gn_apply_kernel, dim3(grid), dim3(threads), 0, st, x->d, s, stats, gamma, beta, silu, y->d, y->ld);
+  run_gn_fwd(plan, x->d, y->d, y->ld, gamma, beta, eps, silu, stats, E->gn_scratch(), st, have_stats);
 }
 inline void GroupNormOp::bwd(cudaStream_t st) {
-  if (fuse_b) {
-    launch_k(gn_fused_bwd_kernel, dim3(sfu.N * sfu.blocks_per_img), dim3(threads), smem_b, st, x->d, y->g, y->ld, sfu, stats, gamma, beta, silu,
-             E->gn_partial, E->gn_bar, x->g, x->ld, acc);
-    return;
-  }
-  const int grid = s.N * s.blocks_per_img;
-  launch_k(gn_bwd_stats_kernel, dim3(grid), dim3(threads_b), ((threads_b + 31) / 32) * 2 * s.G * sizeof(float), st, x->d, y->g, y->ld, s, stats, gamma,
-           beta, silu, E->gn_partial, E->gn_gstats, E->gn_ticket);
-  launch_k(gn_bwd_apply_kernel, dim3(grid), dim3(threads_b), 0, st, x->d, y->g, y->ld, s, stats, E->gn_gstats, gamma, beta,
-           silu, x->g, x->ld, acc);
-}
-
-inline void SelfAttnOp::plan_bwd() {
-  if (use_flash) {
-    qkv->grad_set = true;
-    return;
-  }
-  const int d = heads * dh, n = qkv->n;
-  const long long ldq = qkv->ld, tok = 1LL * T * ldq;
-  const long long sP0 = 1LL * T * ldS, sP1 = 1LL * heads * T * ldS;
-  bf16 *q = qkv->d, *k = qkv->d + d, *v = qkv->d + 2 * d;
-  bf16 *dq = qkv->g, *dk = qkv->g + d, *dv = qkv->g + 2 * d;
-  const float scale = 1.f / sqrtf(static_cast<float>(dh));
-  (void)scale;
-  // dV[key, c] = sum_q P[q, key] dO[q, c]     A = P^T (M-major), B = dO^T (N-major)
-  {
-    Operand A{P, 1, ldS, sP0, sP1}, B{o->g, 1, o->ld, dh, 1LL * T * o->ld};
-    Epilogue e;
-    e.out = dv, e.ldc = ldq, e.sc0 = dh, e.sc1 = tok;
-    p_dv = plan_gemm(T, dh, T, A, B, e, heads, n);
-  }
-  // dP[q, key] = sum_c dO[q, c] V[key, c]      -> fp32 scratch
-  {
-    Operand A{o->g, 0, o->ld, dh, 1LL * T * o->ld}, B{v, 0, ldq, dh, tok};
-    Epilogue e;
-    e.out = E->attn_S, e.out_f32 = 1, e.ldc = ldS, e.sc0 = sP0, e.sc1 = sP1;
-    p_dp = plan_gemm(T, T, dh, A, B, e, heads, n);
-  }
-  // dQ[q, c] = sum_key dS[q, key] K[key, c]    A = dS (K-major), B = K^T (N-major)
-  {
-    Operand A{P, 0, ldS, sP0, sP1}, B{k, 1, ldq, dh, tok};
-    Epilogue e;
-    e.out = dq, e.ldc = ldq, e.sc0 = dh, e.sc1 = tok;
-    p_dq = plan_gemm(T, dh, T, A, B, e, heads, n);
-  }
-  // dK[key, c] = sum_q dS[q, key] Q[q, c]      A = dS^T (M-major), B = Q^T (N-major)
-  {
-    Operand A{P, 1, ldS, sP0, sP1}, B{q, 1, ldq, dh, tok};
-    Epilogue e;
-    e.out = dk, e.ldc = ldq, e.sc0 = dh, e.sc1 = tok;
-    p_dk = plan_gemm(T, dh, T, A, B, e, heads, n);
-  }
-  qkv->grad_set = true;  // q, k, v slices are each written exactly once
-}
-inline void SelfAttnOp::fwd(cudaStream_t st) {
-  if (use_flash) {
-    run_flash_fwd(fp, st);
-    return;
-  }
-  run_gemm(p_s, st);
-  const int rows = qkv->n * heads * T;
-  launch_k(softmax_fwd_kernel, dim3(rows), dim3(256), (((T + 3) & ~3) + 32) * sizeof(float), st, E->attn_S, P, T, ldS);
-  run_gemm(p_o, st);
-}
-inline void SelfAttnOp::bwd(cudaStream_t st) {
-  if (use_flash) {
-    run_flash_bwd(fp, st);
-    return;
-  }
-  run_gemm(p_dv, st);
-  run_gemm(p_dp, st);
-  const int rows = qkv->n * heads * T;
-  launch_k(softmax_bwd_kernel, dim3(rows), dim3(256), (((T + 3) & ~3) + 32) * sizeof(float), st, E->attn_S, P, T, ldS,
-                                                                              1.f / sqrtf(static_cast<float>(dh)));
-  run_gemm(p_dq, st);
-  run_gemm(p_dk, st);
+  run_gn_bwd(plan, x->d, y->g, y->ld, gamma, beta, silu, stats, x->g, x->ld, acc, E->gn_scratch(), st);
 }
 
 // ================================================================================================ builders
@@ -670,38 +631,55 @@ inline Tensor* Engine::view(Tensor* parent, int c0, int c, const std::string& na
   if (!name.empty()) named[name] = t;
   return t;
 }
+// The i-th request of this engine for `key` maps to the i-th slot of the bank (created on first use).
+inline WeightSlot* Engine::bank_slot(const std::string& key, WKind kind, int out, int in, bool& fresh) {
+  auto& list = bank->wmap[key];
+  const size_t idx = slot_cursor[key]++;
+  fresh = idx >= list.size();
+  if (fresh) {
+    bank->slots.emplace_back();
+    WeightSlot* s = &bank->slots.back();
+    s->kind = kind, s->out = out, s->in = in;
+    list.push_back(s);
+    return s;
+  }
+  WeightSlot* s = list[idx];
+  MDC_CHECK(s->kind == kind && s->out == out && s->in == in, "weight bank: '%s' was built as kind %d [%d, %d], now requested as kind %d [%d, %d]",
+            key.c_str(), (int)s->kind, s->out, s->in, (int)kind, out, in);
+  return s;
+}
 inline WeightSlot* Engine::slot(const std::string& key, WKind kind, int out, int in) {
-  wslots.emplace_back();
-  WeightSlot* s = &wslots.back();
-  s->kind = kind, s->out = out, s->in = in;
+  bool fresh;
+  WeightSlot* s = bank_slot(key, kind, out, in, fresh);
+  if (!fresh) return s;
+  Arena& wa = bank->arena;
   if (kind == W_CONV3 || kind == W_UPCONV) {
     const int inp = ((in + 63) / 64) * 64, outp = ((out + 63) / 64) * 64;
     const size_t taps = kind == W_CONV3 ? 9 : 16;
-    s->w = arena.make<bf16>(taps * inp * out + 64);
-    s->wt = arena.make<bf16>(taps * outp * in + 64);
+    s->w = wa.make<bf16>(taps * inp * out + 64);
+    s->wt = wa.make<bf16>(taps * outp * in + 64);
   } else if (kind == W_LIN) {
     s->ld_w = ((in + 7) / 8) * 8, s->ld_wt = ((out + 7) / 8) * 8;  // TMA needs 16-byte row strides
-    s->w = arena.make<bf16>(1ull * out * s->ld_w + 64);
-    s->wt = arena.make<bf16>(1ull * in * s->ld_wt + 64);
+    s->w = wa.make<bf16>(1ull * out * s->ld_w + 64);
+    s->wt = wa.make<bf16>(1ull * in * s->ld_wt + 64);
   } else {
-    s->vec = arena.make<float>(out + 16);
+    s->vec = wa.make<float>(out + 16);
   }
-  wmap[key].push_back(s);
   return s;
 }
 inline WeightSlot* Engine::slot_lin_into(const std::string& key, int out, int in, bf16* w, long long ld_w, bf16* wt,
                                          long long ld_wt) {
-  wslots.emplace_back();
-  WeightSlot* s = &wslots.back();
-  s->kind = W_LIN, s->out = out, s->in = in, s->w = w, s->ld_w = ld_w, s->wt = wt, s->ld_wt = ld_wt;
-  wmap[key].push_back(s);
+  bool fresh;
+  WeightSlot* s = bank_slot(key, W_LIN, out, in, fresh);
+  if (fresh) s->w = w, s->ld_w = ld_w, s->wt = wt, s->ld_wt = ld_wt;
+  MDC_CHECK(s->w == w && s->wt == wt, "weight bank: '%s' points at another buffer", key.c_str());
   return s;
 }
 inline WeightSlot* Engine::slot_vec_into(const std::string& key, int n, float* dst) {
-  wslots.emplace_back();
-  WeightSlot* s = &wslots.back();
-  s->kind = W_VEC, s->out = n, s->vec = dst;
-  wmap[key].push_back(s);
+  bool fresh;
+  WeightSlot* s = bank_slot(key, W_VEC, n, 0, fresh);
+  if (fresh) s->vec = dst;
+  MDC_CHECK(s->vec == dst, "weight bank: '%s' points at another buffer", key.c_str());
   return s;
 }
 
@@ -749,53 +727,15 @@ inline Tensor* Engine::linear(Tensor* x, int cout, const std::string& key, bool 
 }
 inline Tensor* Engine::group_norm(Tensor* x, const std::string& key, float eps, bool silu) {
   const int G = cur_ops == &unet_ops ? cfg.unet_groups : cfg.vae_groups;
-  MDC_CHECK(x->c % G == 0 && (x->c / G) % 2 == 0 && x->c % 8 == 0, "GroupNorm: C=%d G=%d unsupported", x->c, G);
   WeightSlot* ga = slot(key + ".weight", W_VEC, x->c, 0);
   WeightSlot* be = slot(key + ".bias", W_VEC, x->c, 0);
   Tensor* y = new_tensor(x->n, x->h, x->w, x->c, "");
   auto* op = new GroupNormOp();
   op->E = this, op->x = x, op->y = y, op->gamma = ga->vec, op->beta = be->vec, op->eps = eps, op->groups = G;
   op->silu = silu ? 1 : 0;
-  const int CV = x->c / 8;
-  MDC_CHECK(CV <= 384, "GroupNorm: C=%d too wide", x->c);
-  const int R = std::max(1, 512 / CV);
-  op->threads = CV * R;
-  op->threads_b = CV * std::max(1, 384 / CV);
-  GNShape s;
-  s.N = x->n, s.HW = x->h * x->w, s.C = x->c, s.G = G, s.ld = x->ld;
-  int want_blocks = std::max(1, (2 * g_num_sms()) / x->n);
-  int ppb = std::max(R, (s.HW + want_blocks - 1) / want_blocks);
-  ppb = ((ppb + R - 1) / R) * R;
-  s.pix_per_block = ppb;
-  s.blocks_per_img = (s.HW + ppb - 1) / ppb;
-  op->s = s;
-  {  // single-launch variant: one CTA per SM at most, its pixel slab (x, or x and dy) staged in shared memory
-    static const bool no_fuse = getenv("MDC_NO_GNFUSE") != nullptr;
-    GNShape f = s;
-    const int bpi = std::max(1, std::min(g_num_sms() / x->n, s.HW));
-    f.pix_per_block = (s.HW + bpi - 1) / bpi;
-    f.blocks_per_img = (s.HW + f.pix_per_block - 1) / f.pix_per_block;
-    const size_t slab = static_cast<size_t>(f.pix_per_block) * x->c * 2;
-    const size_t extra = (static_cast<size_t>((op->threads + 31) / 32) * 2 * G + 2 * G) * sizeof(float);
-    const size_t cap = 200 * 1024;
-    const bool ok = !no_fuse && op->threads >= 8 * G && x->n * f.blocks_per_img <= g_num_sms();
-    op->sfu = f;
-    op->smem_f = slab + extra, op->smem_b = 2 * slab + extra;
-    op->fuse_f = ok && op->smem_f <= cap;
-    op->fuse_b = ok && op->smem_b <= cap;
-    if (op->fuse_f || op->fuse_b) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        MDC_CUDA(cudaFuncSetAttribute(gn_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cap)));
-        MDC_CUDA(cudaFuncSetAttribute(gn_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cap)));
-        attr_set = true;
-      }
-    }
-  }
+  op->plan = plan_groupnorm(x->n, x->h * x->w, x->c, G, x->ld);
   op->stats = arena.make<float>(2ull * x->n * G);
-  // the single-launch variant may use MORE blocks than the two-pass one on small maps (one pixel row per block)
-  gn_partial_floats = std::max<size_t>(gn_partial_floats,
-                                       static_cast<size_t>(2) * G * x->n * std::max(s.blocks_per_img, op->sfu.blocks_per_img));
+  gn_partial_floats = std::max<size_t>(gn_partial_floats, op->plan.partial_floats);
   push(op, key);
   return y;
 }
@@ -822,38 +762,17 @@ inline Tensor* Engine::resnet(Tensor* x, int cout, const std::string& key, bool 
 }
 inline Tensor* Engine::self_attention(Tensor* qkv, int heads, const std::string& name) {
   const int d = qkv->c / 3, dh = d / heads, T = qkv->h * qkv->w, n = qkv->n;
-  MDC_CHECK(dh % 64 == 0 && dh <= 512, "attention head_dim %d unsupported (need a multiple of 64)", dh);
   Tensor* o = new_tensor(n, qkv->h, qkv->w, d, "");
   auto* op = new SelfAttnOp();
-  op->E = this, op->qkv = qkv, op->o = o, op->heads = heads, op->dh = dh, op->T = T;
-  op->ldS = ((T + 7) / 8) * 8;
-  if (dh == 64 && !getenv("MDC_NO_FLASH")) {
-    op->use_flash = true;
-    float* lse2 = arena.make<float>(static_cast<size_t>(n) * heads * T + 64);
-    float* delta = arena.make<float>(static_cast<size_t>(n) * heads * T + 64);
-    op->fp = plan_flash(n, T, heads, qkv->d, qkv->d + d, qkv->d + 2 * d, qkv->ld, o->d, o->g, o->ld, qkv->g, qkv->g + d,
-                        qkv->g + 2 * d, qkv->ld, lse2, delta);
-    push(op, name);
-    return o;
-  }
-  const long long ldS = op->ldS, ldq = qkv->ld, tok = 1LL * T * ldq;
-  const long long sP0 = 1LL * T * ldS, sP1 = 1LL * heads * T * ldS;
-  op->P = arena.make<bf16>(static_cast<size_t>(n) * heads * T * ldS + 64);
-  attn_S_floats = std::max<size_t>(attn_S_floats, static_cast<size_t>(n) * heads * T * ldS + 64);
-  // S = scale * Q K^T -> fp32 scratch (allocated after the graph is built; patched in finalize_plans)
-  {
-    Operand A{qkv->d, 0, ldq, dh, tok}, B{qkv->d + d, 0, ldq, dh, tok};
-    Epilogue e;
-    e.out = nullptr, e.out_f32 = 1, e.ldc = ldS, e.sc0 = sP0, e.sc1 = sP1, e.alpha = 1.f / sqrtf(static_cast<float>(dh));
-    op->p_s = plan_gemm(T, T, dh, A, B, e, heads, n);
-  }
-  // O = P V : B = V^T is N-major
-  {
-    Operand A{op->P, 0, ldS, sP0, sP1}, B{qkv->d + 2 * d, 1, ldq, dh, tok};
-    Epilogue e;
-    e.out = o->d, e.ldc = o->ld, e.sc0 = dh, e.sc1 = 1LL * T * o->ld;
-    op->p_o = plan_gemm(T, dh, T, A, B, e, heads, n);
-  }
+  op->E = this, op->qkv = qkv, op->o = o;
+  const bool flash = dh == 64 && !getenv("MDC_NO_FLASH");
+  const size_t stat = static_cast<size_t>(n) * heads * T + 64, pel = static_cast<size_t>(n) * heads * T * (((T + 7) / 8) * 8) + 64;
+  float* lse2 = flash ? arena.make<float>(stat) : nullptr;
+  float* delta = flash ? arena.make<float>(stat) : nullptr;
+  bf16* P = flash ? nullptr : arena.make<bf16>(pel);
+  if (!flash) attn_S_floats = std::max<size_t>(attn_S_floats, pel);
+  // the fp32 score scratch is shared by all unfused attentions: allocated after the tapes are built (finalize_plans)
+  op->a = plan_attention(n, T, heads, dh, qkv->d, qkv->ld, o->d, o->g, o->ld, qkv->g, qkv->ld, lse2, delta, P, nullptr, qkv->g != nullptr);
   push(op, name);
   return o;
 }
@@ -866,8 +785,8 @@ inline Tensor* Engine::transformer(Tensor* x, int heads, const std::string& key,
   Tensor* n1 = layer_norm(h, tb + ".norm1");
   Tensor* qkv = new_tensor(x->n, x->h, x->w, 3 * d, "");
   {
-    bf16* w = arena.make<bf16>(3ull * d * d + 64);
-    bf16* wt = arena.make<bf16>(3ull * d * d + 64);
+    bf16* w = static_cast<bf16*>(bank->blob(tb + ".attn1.qkv.w", (3ull * d * d + 64) * 2));
+    bf16* wt = static_cast<bf16*>(bank->blob(tb + ".attn1.qkv.wt", (3ull * d * d + 64) * 2));
     const char* nm[3] = {".attn1.to_q.weight", ".attn1.to_k.weight", ".attn1.to_v.weight"};
     for (int i = 0; i < 3; ++i) slot_lin_into(tb + nm[i], d, d, w + 1ull * i * d * d, d, wt + i * d, 3 * d);
     auto* op = new LinearOp();
@@ -1061,9 +980,9 @@ inline Tensor* Engine::vae_mid_attention(Tensor* h, const std::string& A) {
   const int c0 = h->c;
   Tensor* gn = group_norm(h, A + ".group_norm", 1e-6f, false);
   Tensor* qkv = new_tensor(N, h->h, h->w, 3 * c0, "");
-  bf16* w = arena.make<bf16>(3ull * c0 * c0 + 64);
-  bf16* wt = arena.make<bf16>(3ull * c0 * c0 + 64);
-  float* b = arena.make<float>(3ull * c0 + 16);
+  bf16* w = static_cast<bf16*>(bank->blob(A + ".qkv.w", (3ull * c0 * c0 + 64) * 2));
+  bf16* wt = static_cast<bf16*>(bank->blob(A + ".qkv.wt", (3ull * c0 * c0 + 64) * 2));
+  float* b = static_cast<float*>(bank->blob(A + ".qkv.b", (3ull * c0 + 16) * 4));
   const char* nm[3] = {".to_q", ".to_k", ".to_v"};
   for (int i = 0; i < 3; ++i) {
     slot_lin_into(A + nm[i] + ".weight", c0, c0, w + 1ull * i * c0 * c0, c0, wt + i * c0, 3 * c0);
@@ -1265,11 +1184,8 @@ inline void Engine::finalize_plans() {
           c->pf.p.bias = c->bias;
           finish_plan(c->pf);
         }
-      } else if (auto* a = dynamic_cast<SelfAttnOp*>(op.get())) {
-        if (!a->use_flash) {
-          a->p_s.p.out = attn_S;
-          finish_plan(a->p_s);
-        }
+      } else if (auto* at = dynamic_cast<SelfAttnOp*>(op.get())) {
+        attention_set_scratch(at->a, attn_S, at->qkv->g != nullptr);
       }
     }
     if (ops == &enc_ops) continue;  // forward only, not part of the guided step
@@ -1285,7 +1201,18 @@ inline void Engine::finalize_plans() {
                             // last three return at once unless their option is set)
 }
 
-inline Engine::Engine(const mdc_config& c) : cfg(c) {
+// The fields of mdc_config that determine the parameter set (everything but geometry / batch / steps / device).
+inline void model_signature(const mdc_config& c, int (&sig)[64]) {
+  memset(sig, 0, sizeof(sig));
+  int k = 0;
+  auto put = [&](int v) { sig[k++] = v; };
+  put(c.unet_in_ch), put(c.unet_out_ch), put(c.unet_nblocks), put(c.unet_layers_per_block), put(c.unet_groups), put(c.cross_dim);
+  for (int i = 0; i < MDC_MAX_BLOCKS; ++i) put(c.unet_block_ch[i]), put(c.unet_heads[i]), put(c.unet_down_attn[i]);
+  put(c.vae_nblocks), put(c.vae_layers_per_block), put(c.vae_groups), put(c.vae_latent_ch), put(c.vae_kind);
+  for (int i = 0; i < MDC_MAX_BLOCKS; ++i) put(c.vae_block_ch[i]), put(c.tiny_enc_blocks[i]), put(c.tiny_dec_blocks[i]);
+}
+
+inline Engine::Engine(const mdc_config& c, std::shared_ptr<WeightBank> share) : cfg(c) {
   N = c.n_batch, H = c.height, W = c.width, ph = c.proc_h, pw = c.proc_w;
   PPH = ph + c.pad_h, PPW = pw + c.pad_w;
   MDC_CHECK(N >= 1 && N <= MAXN, "n_batch %d out of range (1..%d)", N, MAXN);
@@ -1298,11 +1225,22 @@ inline Engine::Engine(const mdc_config& c) : cfg(c) {
   for (int i = 1; i < c.vae_nblocks; ++i) expect *= 2;
   MDC_CHECK(expect == 8, "VAE must upsample by 8 (got %d)", expect);
   MDC_CUDA(cudaSetDevice(c.device));
-  MDC_CUDA(cudaStreamCreate(&stream));  // blocking stream: implicitly ordered with the legacy default stream (torch's)
+  int sig[64];
+  model_signature(c, sig);
+  if (share) {
+    MDC_CHECK(share->device == c.device, "mdc_create_shared: the handles are on different devices (%d vs %d)", share->device, c.device);
+    MDC_CHECK(memcmp(sig, share->model_sig, sizeof(sig)) == 0, "mdc_create_shared: the model configurations differ");
+    bank = share;
+  } else {
+    bank = std::make_shared<WeightBank>();
+    bank->device = c.device;
+    memcpy(bank->model_sig, sig, sizeof(sig));
+  }
+  MDC_CUDA(cudaStreamCreate(&own_stream));  // blocking: implicitly ordered with the legacy default stream for plain C callers
+  MDC_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+  stream = own_stream;
   use_graph = getenv("MDC_NO_GRAPH") == nullptr;
-  gemm_set_smem_attr();
-  MDC_CUDA(cudaFuncSetAttribute(softmax_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-  MDC_CUDA(cudaFuncSetAttribute(softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  set_kernel_attrs_for_device();
   build_unet();
   if (cfg.vae_kind == 1) build_tiny_decoder(); else build_decoder();
   n_split_step = split_plans.size();
@@ -1321,9 +1259,19 @@ inline Engine::Engine(const mdc_config& c) : cfg(c) {
   dn_map = arena.make<float>(1ull * N * H * W), gray_gx = arena.make<float>(1ull * N * H * W), gray_gy = arena.make<float>(1ull * N * H * W);
   dmean = arena.make<float>(1ull * N * PPH * PPW);
   pt_idx = arena.make<int>(1ull * N * H * W), pt_val = arena.make<float>(1ull * N * H * W);
-  pt_off = arena.make<int>(N + 1);
+  pt_off = arena.make<int>(N + 1), pt_cnt = arena.make<int>(MAXN);
   gminmax = arena.make<float>(2 * MAXN), depth_minmax = arena.make<float>(2 * MAXN);
   cur = arena.make<StepCur>(1), accum = arena.make<StepAccum>(1), counter = arena.make<int>(1);
+  final_cur = arena.make<StepCur>(1), final_scratch = arena.make<float>(1ull * N * parts_per_img + 16);
+  {
+    StepCur one;
+    memset(&one, 0, sizeof(one));
+    one.sqrt_a = 1.f, one.sqrt_1ma = 0.f;
+    copy_sync(final_cur, &one, sizeof(one), cudaMemcpyHostToDevice);
+  }
+  fr_guide = arena.make<float>(1ull * N * H * W + 64);
+  fr_mask = arena.make<uint8_t>(1ull * N * H * W + 64);
+  fr_stats = arena.make<float>(5ull * MAXN);
   d_sqrt_a = arena.make<float>(c.steps), d_sqrt_1ma = arena.make<float>(c.steps);
   d_sqrt_ap = arena.make<float>(c.steps), d_sqrt_1map = arena.make<float>(c.steps);
   temb_table = arena.make<float>(1ull * c.steps * temb_total + 64);
@@ -1331,62 +1279,77 @@ inline Engine::Engine(const mdc_config& c) : cfg(c) {
 }
 
 // ================================================================================================ runtime
-inline void Engine::set_weight(const std::string& key, const void* src, const long long* shape, int ndim, int dtype) {
-  auto it = wmap.find(key);
-  MDC_CHECK(it != wmap.end(), "unknown weight key '%s'", key.c_str());
-  MDC_CHECK(dtype == MDC_DTYPE_F32 || dtype == MDC_DTYPE_BF16, "weight dtype %d unsupported", dtype);
-  for (WeightSlot* s : it->second) {
+// Re-packs `n` parameters with ONE kernel launch (pack_jobs_kernel): the job table is built on the host, validated
+// against the slots' logical shapes and uploaded.  The sources are read before this function returns.
+inline void Engine::set_weights(int n, const char* const* keys, const void* const* srcs, const long long* shapes4, const int* ndims,
+                                const int* dtypes) {
+  std::vector<PackJob> jobs;
+  std::vector<WeightSlot*> touched;
+  for (int k = 0; k < n; ++k) {
+    const std::string key(keys[k]);
+    const long long* shape = shapes4 + 4 * k;
+    const int ndim = ndims[k], dtype = dtypes[k];
+    auto it = wmap().find(key);
+    MDC_CHECK(it != wmap().end(), "unknown weight key '%s'", key.c_str());
+    MDC_CHECK(dtype == MDC_DTYPE_F32 || dtype == MDC_DTYPE_BF16, "weight dtype %d unsupported", dtype);
+    MDC_CHECK(srcs[k] != nullptr && ndim >= 1 && ndim <= 4, "weight '%s': bad pointer / rank", key.c_str());
     long long numel = 1;
     for (int i = 0; i < ndim; ++i) numel *= shape[i];
-    const bool f32 = dtype == MDC_DTYPE_F32;
-    if (s->kind == W_CONV3) {
-      MDC_CHECK(ndim == 4 && shape[0] == s->out && shape[1] == s->in && shape[2] == 3 && shape[3] == 3,
-                "weight '%s': expected [%d,%d,3,3]", key.c_str(), s->out, s->in);
-      const int inp = ((s->in + 63) / 64) * 64, outp = ((s->out + 63) / 64) * 64;
-      if (f32) {
-        pack_conv3x3_fwd_kernel<float><<<1184, 256, 0, stream>>>((const float*)src, s->w, s->out, s->in, inp);
-        pack_conv3x3_dgrad_kernel<float><<<1184, 256, 0, stream>>>((const float*)src, s->wt, s->out, s->in, outp);
-      } else {
-        pack_conv3x3_fwd_kernel<bf16><<<1184, 256, 0, stream>>>((const bf16*)src, s->w, s->out, s->in, inp);
-        pack_conv3x3_dgrad_kernel<bf16><<<1184, 256, 0, stream>>>((const bf16*)src, s->wt, s->out, s->in, outp);
+    for (WeightSlot* s : it->second) {
+      PackJob j;
+      memset(&j, 0, sizeof(j));
+      j.src = srcs[k], j.src_bf16 = dtype == MDC_DTYPE_BF16 ? 1 : 0, j.out = s->out, j.in = s->in, j.vscale = 1.f;
+      if (s->kind == W_CONV3 || s->kind == W_UPCONV) {
+        MDC_CHECK(ndim == 4 && shape[0] == s->out && shape[1] == s->in && shape[2] == 3 && shape[3] == 3,
+                  "weight '%s': expected [%d,%d,3,3]", key.c_str(), s->out, s->in);
+        const bool up = s->kind == W_UPCONV;
+        j.kind = up ? PK_UPCONV_FWD : PK_CONV_FWD, j.dst = s->w, j.pad = ((s->in + 63) / 64) * 64;
+        jobs.push_back(j);
+        j.kind = up ? PK_UPCONV_BWD : PK_CONV_DGRAD, j.dst = s->wt, j.pad = ((s->out + 63) / 64) * 64;
+        jobs.push_back(j);
+      } else if (s->kind == W_LIN) {
+        MDC_CHECK(numel == 1LL * s->out * s->in && shape[0] == s->out, "weight '%s': expected [%d,%d]", key.c_str(), s->out, s->in);
+        j.kind = PK_MATRIX, j.dst = s->w, j.ld = s->ld_w;
+        jobs.push_back(j);
+        j.kind = PK_MATRIX_T, j.dst = s->wt, j.ld = s->ld_wt;
+        jobs.push_back(j);
+      } else {  // bf16 parameters are used at bf16 precision, like the reference's bf16 modules
+        MDC_CHECK(numel == s->out, "weight '%s': expected %d elements, got %lld", key.c_str(), s->out, numel);
+        j.kind = PK_VEC, j.dst = s->vec, j.vscale = s->vscale, j.vshift = s->vshift;
+        jobs.push_back(j);
       }
-    } else if (s->kind == W_UPCONV) {
-      MDC_CHECK(ndim == 4 && shape[0] == s->out && shape[1] == s->in && shape[2] == 3 && shape[3] == 3,
-                "weight '%s': expected [%d,%d,3,3]", key.c_str(), s->out, s->in);
-      const int inp = ((s->in + 63) / 64) * 64, outp = ((s->out + 63) / 64) * 64;
-      if (f32) {
-        pack_upconv_fwd_kernel<float><<<1184, 256, 0, stream>>>((const float*)src, s->w, s->out, s->in, inp);
-        pack_upconv_bwd_kernel<float><<<1184, 256, 0, stream>>>((const float*)src, s->wt, s->out, s->in, outp);
-      } else {
-        pack_upconv_fwd_kernel<bf16><<<1184, 256, 0, stream>>>((const bf16*)src, s->w, s->out, s->in, inp);
-        pack_upconv_bwd_kernel<bf16><<<1184, 256, 0, stream>>>((const bf16*)src, s->wt, s->out, s->in, outp);
-      }
-    } else if (s->kind == W_LIN) {
-      MDC_CHECK(numel == 1LL * s->out * s->in && shape[0] == s->out, "weight '%s': expected [%d,%d]", key.c_str(), s->out,
-                s->in);
-      if (f32) {
-        pack_matrix_kernel<float><<<1184, 256, 0, stream>>>((const float*)src, s->w, s->out, s->in, s->ld_w, 0);
-        pack_matrix_kernel<float><<<1184, 256, 0, stream>>>((const float*)src, s->wt, s->out, s->in, s->ld_wt, 1);
-      } else {
-        pack_matrix_kernel<bf16><<<1184, 256, 0, stream>>>((const bf16*)src, s->w, s->out, s->in, s->ld_w, 0);
-        pack_matrix_kernel<bf16><<<1184, 256, 0, stream>>>((const bf16*)src, s->wt, s->out, s->in, s->ld_wt, 1);
-      }
-    } else {
-      MDC_CHECK(numel == s->out, "weight '%s': expected %d elements, got %lld", key.c_str(), s->out, numel);
-      if (f32)
-        to_f32_kernel<float><<<32, 256, 0, stream>>>((const float*)src, s->vec, numel);
-      else  // bf16 parameters are used at bf16 precision, like the reference's bf16 modules
-        to_f32_kernel<bf16><<<32, 256, 0, stream>>>((const bf16*)src, s->vec, numel);
-      if (s->vscale != 1.f || s->vshift != 0.f)
-        vec_affine_kernel<<<static_cast<int>((numel + 255) / 256), 256, 0, stream>>>(s->vec, numel, s->vscale, s->vshift);
+      touched.push_back(s);
     }
-    s->loaded = true;
+  }
+  if (jobs.empty()) return;
+  PackJob* d_jobs = nullptr;
+  MDC_CUDA(cudaMalloc(&d_jobs, jobs.size() * sizeof(PackJob)));
+  MDC_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice, stream));
+  for (size_t first = 0; first < jobs.size(); first += 65535) {  // gridDim.y limit
+    const unsigned cnt = static_cast<unsigned>(std::min<size_t>(65535, jobs.size() - first));
+    pack_jobs_kernel<<<dim3(64, cnt), 256, 0, stream>>>(d_jobs + first);
   }
   MDC_CUDA(cudaGetLastError());
+  MDC_CUDA(cudaStreamSynchronize(stream));  // the caller may release its tensors as soon as we return
+  cudaFree(d_jobs);
+  for (WeightSlot* s : touched) s->loaded = true;
+}
+inline void Engine::set_weight(const std::string& key, const void* src, const long long* shape, int ndim, int dtype) {
+  long long s4[4] = {1, 1, 1, 1};
+  MDC_CHECK(ndim >= 1 && ndim <= 4, "weight '%s': rank %d", key.c_str(), ndim);
+  for (int i = 0; i < ndim; ++i) s4[i] = shape[i];
+  const char* k = key.c_str();
+  set_weights(1, &k, &src, s4, &ndim, &dtype);
+}
+inline bool Engine::weights_loaded() {
+  for (auto& kv : wmap())
+    for (WeightSlot* s : kv.second)
+      if (!s->loaded) return false;
+  return true;
 }
 
 inline void Engine::prepare(const void* ctx_bf16, const float* alphas_cumprod, const int* timesteps, int n_steps) {
-  for (auto& kv : wmap)
+  for (auto& kv : wmap())
     for (WeightSlot* s : kv.second) MDC_CHECK(s->loaded, "weight '%s' has not been set", kv.first.c_str());
   MDC_CHECK(n_steps == cfg.steps, "prepare: n_steps %d != configured steps %d", n_steps, cfg.steps);
   // DDIM scalars (host, double -> float like torch's 0-dim fp32 tensors)
@@ -1398,10 +1361,10 @@ inline void Engine::prepare(const void* ctx_bf16, const float* alphas_cumprod, c
     const float a = alphas_cumprod[t], ap = tp >= 0 ? alphas_cumprod[tp] : alphas_cumprod[0];
     sa[i] = sqrtf(a), sb[i] = sqrtf(1.f - a), sap[i] = sqrtf(ap), sbp[i] = sqrtf(1.f - ap);
   }
-  MDC_CUDA(cudaMemcpy(d_sqrt_a, sa.data(), n_steps * 4, cudaMemcpyHostToDevice));
-  MDC_CUDA(cudaMemcpy(d_sqrt_1ma, sb.data(), n_steps * 4, cudaMemcpyHostToDevice));
-  MDC_CUDA(cudaMemcpy(d_sqrt_ap, sap.data(), n_steps * 4, cudaMemcpyHostToDevice));
-  MDC_CUDA(cudaMemcpy(d_sqrt_1map, sbp.data(), n_steps * 4, cudaMemcpyHostToDevice));
+  copy_sync(d_sqrt_a, sa.data(), n_steps * 4, cudaMemcpyHostToDevice);
+  copy_sync(d_sqrt_1ma, sb.data(), n_steps * 4, cudaMemcpyHostToDevice);
+  copy_sync(d_sqrt_ap, sap.data(), n_steps * 4, cudaMemcpyHostToDevice);
+  copy_sync(d_sqrt_1map, sbp.data(), n_steps * 4, cudaMemcpyHostToDevice);
   // time embedding for every step: sinusoid -> linear_1 -> SiLU -> linear_2, then per resnet time_emb_proj(SiLU(.)) + conv bias
   const int c0 = cfg.unet_block_ch[0], tc = c0 * 4;
   int* d_ts = nullptr;
@@ -1410,7 +1373,7 @@ inline void Engine::prepare(const void* ctx_bf16, const float* alphas_cumprod, c
   MDC_CUDA(cudaMalloc(&emb, 4ull * n_steps * c0));
   MDC_CUDA(cudaMalloc(&h1, 4ull * n_steps * tc));
   MDC_CUDA(cudaMalloc(&h2, 4ull * n_steps * tc));
-  MDC_CUDA(cudaMemcpy(d_ts, timesteps, n_steps * 4, cudaMemcpyHostToDevice));
+  copy_sync(d_ts, timesteps, n_steps * 4, cudaMemcpyHostToDevice);
   launch_k(timestep_embedding_kernel, dim3((n_steps * c0 + 255) / 256), dim3(256), 0, stream, d_ts, n_steps, c0, emb);
   auto lin = [&](const bf16* Wm, long long ldw, const float* b, const float* in, long long ldin, int In, int Out, int silu,
                  float* out, long long ldout, int S) {
@@ -1428,14 +1391,14 @@ inline void Engine::prepare(const void* ctx_bf16, const float* alphas_cumprod, c
   MDC_CUDA(cudaStreamSynchronize(stream));
   {
     std::vector<float> tab(1ull * n_steps * temb_total), cb;
-    MDC_CUDA(cudaMemcpy(tab.data(), temb_table, tab.size() * 4, cudaMemcpyDeviceToHost));
+    copy_sync(tab.data(), temb_table, tab.size() * 4, cudaMemcpyDeviceToHost);
     for (auto& u : temb_uses) {
       cb.resize(u.cout);
-      MDC_CUDA(cudaMemcpy(cb.data(), u.conv_b->vec, u.cout * 4, cudaMemcpyDeviceToHost));
+      copy_sync(cb.data(), u.conv_b->vec, u.cout * 4, cudaMemcpyDeviceToHost);
       for (int s = 0; s < n_steps; ++s)
         for (int c = 0; c < u.cout; ++c) tab[1ull * s * temb_total + u.off + c] += cb[c];
     }
-    MDC_CUDA(cudaMemcpy(temb_table, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    copy_sync(temb_table, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice);
   }
   // cross-attention K / V of the 2 empty-prompt tokens: [2, d] = ctx [2, cross] . W^T
   {
@@ -1457,16 +1420,19 @@ inline void Engine::prepare(const void* ctx_bf16, const float* alphas_cumprod, c
   cudaFree(d_ts), cudaFree(emb), cudaFree(h1), cudaFree(h2);
   tables.sqrt_a = d_sqrt_a, tables.sqrt_1ma = d_sqrt_1ma, tables.sqrt_ap = d_sqrt_ap, tables.sqrt_1map = d_sqrt_1map;
   tables.temb_bias = temb_table, tables.temb_total = temb_total, tables.steps = n_steps;
-  MDC_CUDA(cudaMemcpy(opts, &h_opts, sizeof(h_opts), cudaMemcpyHostToDevice));
+  copy_sync(opts, &h_opts, sizeof(h_opts), cudaMemcpyHostToDevice);
   MDC_CUDA(cudaGetLastError());
   prepared = true;
 }
 
-inline void Engine::begin(const void* img_latents, const void* x0, const float* guide, const uint8_t* mask,
-                          const float* gmm, const float* dmm, float lrx, float lrs) {
+// Per-call state shared by mdc_begin and mdc_begin_frame.  Everything is enqueued on `stream`; the valid points are
+// counted and compacted on the device (pt_cnt -> pt_off -> pt_idx / pt_val), the host only reads back N + 1 offsets
+// at the end to raise the reference's empty-mask error.
+inline void Engine::begin_state(const void* img_latents, const void* x0, const float* guide, const uint8_t* mask, float lrx, float lrs,
+                                const float* stats5_dev) {
   MDC_CHECK(prepared, "mdc_begin called before mdc_prepare");
   const size_t lat = 4ull * N * lh * lw;
-  MDC_CUDA(cudaMemcpyAsync(img_lat, img_latents, lat * 2, cudaMemcpyDeviceToDevice, stream));
+  if (img_latents != img_lat) MDC_CUDA(cudaMemcpyAsync(img_lat, img_latents, lat * 2, cudaMemcpyDeviceToDevice, stream));
   MDC_CUDA(cudaMemcpyAsync(x, x0, lat * 2, cudaMemcpyDeviceToDevice, stream));
   MDC_CUDA(cudaMemsetAsync(m1, 0, lat * 2, stream));
   MDC_CUDA(cudaMemsetAsync(m2, 0, lat * 2, stream));
@@ -1476,33 +1442,23 @@ inline void Engine::begin(const void* img_latents, const void* x0, const float* 
   memset(&a, 0, sizeof(a));
   for (int i = 0; i < MAXN; ++i) a.scale[i] = 1.f;
   MDC_CUDA(cudaMemcpyAsync(accum, &a, sizeof(a), cudaMemcpyHostToDevice, stream));
-  MDC_CUDA(cudaMemcpyAsync(gminmax, gmm, 8ull * N, cudaMemcpyHostToDevice, stream));
-  MDC_CUDA(cudaMemcpyAsync(depth_minmax, dmm, 8ull * N, cudaMemcpyHostToDevice, stream));
   MDC_CHECK(h_opts.w_edge == 0.f || have_gray, "image must be provided for edge loss (use mdc_begin_frame)");
   have_gray = false;
   h_opts.lr_x = lrx, h_opts.lr_s = lrs;
   MDC_CUDA(cudaMemcpyAsync(opts, &h_opts, sizeof(h_opts), cudaMemcpyHostToDevice, stream));
-  // valid-point lists (host does the counting once per call; not on the per-step path)
-  std::vector<uint8_t> hm(1ull * N * H * W);
-  MDC_CUDA(cudaMemcpyAsync(hm.data(), mask, hm.size(), cudaMemcpyDeviceToHost, stream));
-  MDC_CUDA(cudaStreamSynchronize(stream));
-  std::vector<int> off(N + 1, 0);
-  for (int n = 0; n < N; ++n) {
-    int c = 0;
-    const uint8_t* p = hm.data() + 1ull * n * H * W;
-    for (int i = 0; i < H * W; ++i) c += p[i] != 0;
-    MDC_CHECK(c > 0, "sample %d has no valid sparse-depth point (empty mask)", n);
-    off[n + 1] = off[n] + c;
-  }
-  MDC_CUDA(cudaMemcpyAsync(pt_off, off.data(), (N + 1) * 4, cudaMemcpyHostToDevice, stream));
+  if (!stats5_dev) launch_k(count_mask_kernel, dim3(N), dim3(1024), 0, stream, mask, H * W, pt_cnt);
+  launch_k(frame_state_kernel, dim3(1), dim3(32), 0, stream, static_cast<const int*>(pt_cnt), stats5_dev, N, pt_off, gminmax, depth_minmax);
   launch_k(compact_points_kernel, dim3(N), dim3(1024), 0, stream, guide, mask, H * W, pt_off, pt_idx, pt_val);
   MDC_CUDA(cudaGetLastError());
+  std::vector<int> off(N + 1, 0);
+  MDC_CUDA(cudaMemcpyAsync(off.data(), pt_off, (N + 1) * 4, cudaMemcpyDeviceToHost, stream));
   MDC_CUDA(cudaStreamSynchronize(stream));
+  for (int n = 0; n < N; ++n)
+    MDC_CHECK(off[n + 1] > off[n], "No valid values found in mask for some positions. Ensure that mask has at least one True value "
+                                   "along the specified dimensions. (sample %d has no valid sparse-depth point: empty mask)", n);
   if (getenv("MDC_DEBUG_SYNC")) {  // consistency of the compacted point list
-    std::vector<int> idx(off[N]), o2(N + 1);
-    MDC_CUDA(cudaMemcpy(idx.data(), pt_idx, idx.size() * 4, cudaMemcpyDeviceToHost));
-    MDC_CUDA(cudaMemcpy(o2.data(), pt_off, o2.size() * 4, cudaMemcpyDeviceToHost));
-    for (int n = 0; n <= N; ++n) MDC_CHECK(o2[n] == off[n], "pt_off[%d] = %d, expected %d", n, o2[n], off[n]);
+    std::vector<int> idx(off[N]);
+    copy_sync(idx.data(), pt_idx, idx.size() * 4, cudaMemcpyDeviceToHost);
     for (size_t i = 0; i < idx.size(); ++i) MDC_CHECK(idx[i] >= 0 && idx[i] < H * W, "pt_idx[%zu] = %d out of range (H*W = %d)", i, idx[i], H * W);
     fprintf(stderr, "[mdc debug] begin: %d points, geometry H %d W %d ph %d pw %d PPH %d PPW %d dec ld %lld\n", off[N], H, W, ph, pw, PPH, PPW,
             dec_out->ld);
@@ -1510,6 +1466,14 @@ inline void Engine::begin(const void* img_latents, const void* x0, const float* 
   lr_x = lrx, lr_s = lrs;
   steps_done = 0;
   begun = true;
+}
+inline void Engine::begin(const void* img_latents, const void* x0, const float* guide, const uint8_t* mask,
+                          const float* gmm, const float* dmm, float lrx, float lrs) {
+  MDC_CHECK(prepared, "mdc_begin called before mdc_prepare");
+  // host (min, max) pairs: staged through pageable memory, i.e. copied before cudaMemcpyAsync returns
+  MDC_CUDA(cudaMemcpyAsync(gminmax, gmm, 8ull * N, cudaMemcpyHostToDevice, stream));
+  MDC_CUDA(cudaMemcpyAsync(depth_minmax, dmm, 8ull * N, cudaMemcpyHostToDevice, stream));
+  begin_state(img_latents, x0, guide, mask, lrx, lrs, nullptr);
 }
 
 // Keeps the stream busy for ~`ns` nanoseconds so the host can enqueue a long launch sequence ahead of the GPU.
@@ -1586,7 +1550,7 @@ inline void Engine::run_ops(std::vector<std::unique_ptr<Op>>& ops, bool backward
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(stream, &cs);
         if (cs == cudaStreamCaptureStatusNone) {
-          MDC_CUDA(cudaMemcpy(o2, pt_off, 8, cudaMemcpyDeviceToHost));
+          copy_sync(o2, pt_off, 8, cudaMemcpyDeviceToHost);
           MDC_CHECK(o2[0] == 0 && o2[1] > 0 && o2[1] <= H * W, "pt_off corrupted (%d, %d) right after the forward of op '%s'", o2[0], o2[1],
                     op->name.c_str());
         }
@@ -1599,7 +1563,54 @@ inline void Engine::run_ops(std::vector<std::unique_ptr<Op>>& ops, bool backward
 inline Engine::~Engine() {
   if (step_graph) cudaGraphExecDestroy(step_graph);
   if (sample_graph) cudaGraphExecDestroy(sample_graph);
-  if (stream) cudaStreamDestroy(stream);
+  if (own_stream) cudaStreamDestroy(own_stream);
+  if (cap_stream) cudaStreamDestroy(cap_stream);
+}
+inline void Engine::release_workspace() {
+  MDC_CUDA(cudaStreamSynchronize(stream));
+  if (step_graph) cudaGraphExecDestroy(step_graph);
+  if (sample_graph) cudaGraphExecDestroy(sample_graph);
+  step_graph = sample_graph = nullptr;
+  unet_ops.clear(), dec_ops.clear(), enc_ops.clear();
+  split_plans.clear();
+  tensors.clear(), named.clear();
+  arena.free_all();
+  prepared = begun = false;
+  released = true;
+}
+// The single-launch GroupNorm kernels meet at a hand-rolled grid barrier; if its CTAs were ever not co-resident (GPU
+// shared through MPS, preemption) the barrier times out after ~2 s, sets a sticky flag and the results are garbage.
+// Called (after a stream synchronisation) by every entry point that hands results to the caller.
+inline void Engine::check_barrier_flag() {
+  unsigned int f = 0;
+  copy_sync(&f, gn_bar + 2, 4, cudaMemcpyDeviceToHost);
+  if (f) {
+    MDC_CUDA(cudaMemsetAsync(gn_bar, 0, 16, stream));
+    MDC_CHECK(false, "GroupNorm grid barrier timed out (the kernel's CTAs were not co-resident: is the GPU shared?); results of this "
+                     "call are invalid.  Set MDC_NO_GNFUSE=1 to use the two-pass kernels.");
+  }
+}
+// Captures `launches()` on the private capture stream with `stream` temporarily pointing at it.
+template <typename F>
+inline cudaGraphExec_t capture_graph(Engine* e, F&& launches) {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaStream_t saved = e->stream;
+  e->stream = e->cap_stream;
+  MDC_CUDA(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+  try {
+    launches();
+  } catch (...) {
+    cudaStreamEndCapture(e->cap_stream, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    e->stream = saved;
+    throw;
+  }
+  e->stream = saved;
+  MDC_CUDA(cudaStreamEndCapture(e->cap_stream, &graph));
+  MDC_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  cudaGraphDestroy(graph);
+  return exec;
 }
 inline void Engine::step() {
   MDC_CHECK(begun, "mdc_step called before mdc_begin");
@@ -1607,20 +1618,7 @@ inline void Engine::step() {
   if (!use_graph) {
     step_launches();
   } else {
-    if (!step_graph) {
-      cudaGraph_t graph = nullptr;
-      MDC_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-      try {
-        step_launches();
-      } catch (...) {
-        cudaStreamEndCapture(stream, &graph);
-        if (graph) cudaGraphDestroy(graph);
-        throw;
-      }
-      MDC_CUDA(cudaStreamEndCapture(stream, &graph));
-      MDC_CUDA(cudaGraphInstantiate(&step_graph, graph, 0));
-      cudaGraphDestroy(graph);
-    }
+    if (!step_graph) step_graph = capture_graph(this, [&] { step_launches(); });
     MDC_CUDA(cudaGraphLaunch(step_graph, stream));
   }
   ++steps_done;
@@ -1636,13 +1634,13 @@ inline void Engine::step_launches() {
     static const bool on = getenv("MDC_DEBUG_SYNC") != nullptr;
     if (!on) return;
     std::vector<int> o2(N + 1);
-    MDC_CUDA(cudaMemcpy(o2.data(), pt_off, o2.size() * 4, cudaMemcpyDeviceToHost));
+    copy_sync(o2.data(), pt_off, o2.size() * 4, cudaMemcpyDeviceToHost);
     MDC_CHECK(o2[0] == 0 && o2[N] > 0 && o2[N] <= N * H * W, "%s: pt_off corrupted (%d .. %d)", tag, o2[0], o2[N]);
     std::vector<int> idx(o2[N]);
-    MDC_CUDA(cudaMemcpy(idx.data(), pt_idx, idx.size() * 4, cudaMemcpyDeviceToHost));
+    copy_sync(idx.data(), pt_idx, idx.size() * 4, cudaMemcpyDeviceToHost);
     for (size_t i = 0; i < idx.size(); ++i) MDC_CHECK(idx[i] >= 0 && idx[i] < H * W, "%s: pt_idx[%zu] = %d corrupted", tag, i, idx[i]);
     StepAccum a;
-    MDC_CUDA(cudaMemcpy(&a, accum, sizeof(a), cudaMemcpyDeviceToHost));
+    copy_sync(&a, accum, sizeof(a), cudaMemcpyDeviceToHost);
     fprintf(stderr, "[mdc debug] %s: points ok, scale %g shift %g, dmean %p dec %p acc %p\n", tag, a.scale[0], a.shift[0], (void*)dmean,
             (void*)dec_out->d, (void*)accum);
   };
@@ -1683,20 +1681,7 @@ inline void Engine::sample_step() {
   if (!use_graph) {
     sample_launches();
   } else {
-    if (!sample_graph) {
-      cudaGraph_t graph = nullptr;
-      MDC_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-      try {
-        sample_launches();
-      } catch (...) {
-        cudaStreamEndCapture(stream, &graph);
-        if (graph) cudaGraphDestroy(graph);
-        throw;
-      }
-      MDC_CUDA(cudaStreamEndCapture(stream, &graph));
-      MDC_CUDA(cudaGraphInstantiate(&sample_graph, graph, 0));
-      cudaGraphDestroy(graph);
-    }
+    if (!sample_graph) sample_graph = capture_graph(this, [&] { sample_launches(); });
     MDC_CUDA(cudaGraphLaunch(sample_graph, stream));
   }
   launches += launches_per_sample_step;
@@ -1706,18 +1691,10 @@ inline void Engine::sample_step() {
 inline void Engine::decode_final(float* dense_out, bool closed_form) {
   MDC_CHECK(begun, "mdc_decode_final called before mdc_begin");
   const int hw = lh * lw;
-  // z = x / scaling as NHWC (reuse x0_kernel algebra with sqrt_a = 1, sqrt_1ma = 0 via a dedicated tiny path)
-  StepCur one;
-  memset(&one, 0, sizeof(one));
-  one.sqrt_a = 1.f, one.sqrt_1ma = 0.f;
-  StepCur* tmp = nullptr;
-  MDC_CUDA(cudaMalloc(&tmp, sizeof(StepCur)));
-  MDC_CUDA(cudaMemcpyAsync(tmp, &one, sizeof(one), cudaMemcpyHostToDevice, stream));
+  // z = x / scaling as NHWC: x0_kernel with the identity scalars (sqrt_a = 1, sqrt_1ma = 0) and v = 0
   MDC_CUDA(cudaMemsetAsync(unet_out->d, 0, static_cast<size_t>(unet_out->rows()) * unet_out->ld * 2, stream));
-  float* scratch = nullptr;
-  MDC_CUDA(cudaMalloc(&scratch, 4ull * N * parts_per_img));
-  launch_k(x0_kernel, dim3(N * parts_per_img), dim3(256), 0, stream, unet_out->d, x, tmp, N, hw, cfg.vae_scaling, dec_in->d, scratch, static_cast<float*>(nullptr),
-           static_cast<float*>(nullptr));
+  launch_k(x0_kernel, dim3(N * parts_per_img), dim3(256), 0, stream, unet_out->d, x, final_cur, N, hw, cfg.vae_scaling, dec_in->d, final_scratch,
+           static_cast<float*>(nullptr), static_cast<float*>(nullptr));
   run_ops(dec_ops, false);
   TailGeom g{N, H, W, ph, pw, PPH, PPW, dec_out->ld, interp_nearest};
   const long long tot = 1LL * N * H * W;
@@ -1726,7 +1703,7 @@ inline void Engine::decode_final(float* dense_out, bool closed_form) {
                                                                            dense_out, closed_form ? 1 : 0);
   MDC_CUDA(cudaGetLastError());
   MDC_CUDA(cudaStreamSynchronize(stream));
-  cudaFree(tmp), cudaFree(scratch);
+  check_barrier_flag();
 }
 
 // Per-frame prologue behind the C ABI: image normalise / resize / pad + VAE encoder forward.
@@ -1742,8 +1719,7 @@ inline void Engine::encode(const void* imgs, int dtype, int channels, void* late
   const long long lt = 1LL * N * cfg.vae_latent_ch * lh * lw;
   launch_k(latent_out_kernel, dim3(static_cast<int>((lt + 255) / 256)), dim3(256), 0, stream, enc_out->d, enc_out->ld, N, lh * lw,
            cfg.vae_latent_ch, cfg.vae_scaling, static_cast<bf16*>(latents_out));
-  MDC_CUDA(cudaGetLastError());
-  MDC_CUDA(cudaStreamSynchronize(stream));
+  MDC_CUDA(cudaGetLastError());  // stream-ordered: the caller's next use of `latents_out` on the handle's stream sees the result
 }
 
 // norm="percentile" (marigold_dc.py:715-728): per sample, torch.quantile of the positive sparse values at (q_lo, q_hi):
@@ -1755,6 +1731,7 @@ inline void Engine::percentile_ranges(const float* sparse) {
     pc_range = arena.make<float>(2ull * MAXN), pc_counts = arena.make<int>(MAXN);
     MDC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, pc_tmp_bytes, pc_vals, pc_sorted, static_cast<int>(HW), 0, 32, stream));
     pc_tmp = arena.make<uint8_t>(pc_tmp_bytes + 256);
+    MDC_CUDA(cudaDeviceSynchronize());  // Arena zero-fills on the legacy stream, which is not ordered with a caller's stream
   }
   launch_k(compact_positive_kernel, dim3(N), dim3(1024), 0, stream, sparse, static_cast<int>(HW), pc_vals, pc_counts);
   std::vector<int> cnt(N);
@@ -1797,13 +1774,7 @@ inline void Engine::begin_frame(const void* imgs, int dtype, int channels, const
   MDC_CHECK(norm_mode >= 0 && norm_mode <= 2, "Unknown norm method: %d (0 minmax, 1 const, 2 percentile)", norm_mode);
   MDC_CHECK(!((h_opts.projection != 0 || h_opts.inv) && min_depth <= 1e-7f),
             "min_depth must be > 1e-07 when projection is 'log' or 'log10' or inv is True, but got %g", min_depth);
-  if (!enc_lat) {
-    enc_lat = arena.make<bf16>(4ull * N * lh * lw + 64);
-    fr_guide = arena.make<float>(1ull * N * H * W + 64);
-    fr_mask = arena.make<uint8_t>(1ull * N * H * W + 64);
-    fr_stats = arena.make<float>(5ull * MAXN);
-  }
-  encode(imgs, dtype, channels, enc_lat);
+  encode(imgs, dtype, channels, img_lat);
   if (norm_mode == 2) percentile_ranges(sparse);
   if (h_opts.w_edge != 0.f) {
     const long long opix = 1LL * N * H * W;
@@ -1814,17 +1785,8 @@ inline void Engine::begin_frame(const void* imgs, int dtype, int channels, const
   launch_k(sparse_norm_kernel, dim3(N), dim3(1024), 0, stream, sparse, H * W, min_depth, max_depth, norm_mode, pc_range, h_opts.projection,
            h_opts.inv, fr_guide, fr_mask, fr_stats);
   MDC_CUDA(cudaGetLastError());
-  std::vector<float> st(5ull * N);
-  MDC_CUDA(cudaMemcpyAsync(st.data(), fr_stats, st.size() * 4, cudaMemcpyDeviceToHost, stream));
-  MDC_CUDA(cudaStreamSynchronize(stream));
-  std::vector<float> gmm(2ull * N), dmm(2ull * N);
-  for (int n = 0; n < N; ++n) {
-    MDC_CHECK(st[5 * n + 4] > 0.f, "No valid values found in mask for some positions. Ensure that mask has at least one True value "
-                                   "along the specified dimensions. (sample %d)", n);
-    dmm[2 * n] = st[5 * n], dmm[2 * n + 1] = st[5 * n + 1];
-    gmm[2 * n] = st[5 * n + 2], gmm[2 * n + 1] = st[5 * n + 3];
-  }
-  begin(enc_lat, x0, fr_guide, fr_mask, gmm.data(), dmm.data(), lrx, lrs);
+  // ranges, point offsets and the compaction stay on the device; one synchronisation at the end raises the empty-mask error
+  begin_state(img_lat, x0, fr_guide, fr_mask, lrx, lrs, fr_stats);
 }
 
 // NHWC bf16 -> NCHW fp32 copy of a named tensor (which = 0 data, 1 gradient); debug / tests only.

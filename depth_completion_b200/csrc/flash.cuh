@@ -628,12 +628,11 @@ inline FlashPlan plan_flash(int n, int T, int heads, const bf16* q, const bf16* 
 }
 
 inline void flash_set_attrs() {
-  static bool done = false;
-  if (done) return;
+  static bool done[64] = {false};
+  if (!first_use_on_device(done)) return;
   MDC_CUDA(cudaFuncSetAttribute(flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
   MDC_CUDA(cudaFuncSetAttribute(flash_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
   MDC_CUDA(cudaFuncSetAttribute(flash_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-  done = true;
 }
 inline void run_flash_fwd(const FlashPlan& f, cudaStream_t st) {
   flash_set_attrs();

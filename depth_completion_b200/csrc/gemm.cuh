@@ -709,15 +709,27 @@ inline int pick_bn(int N) {
   return r > 256 ? 256 : r;
 }
 
+// SM count of the CURRENT device (cached per device: a process may hold engines on several GPUs).
 inline int g_num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!cache[dev]) {
+    int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    cache[dev] = n > 0 ? n : 148;
   }
-  return n;
+  return cache[dev];
+}
+// true the first time it is called with `done` on the current device (function attributes are per device)
+inline bool first_use_on_device(bool (&done)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
 }
 
 // Cluster mode of a launch; must be decided BEFORE the B tensor map is encoded because each CTA's TMA box covers only
@@ -1019,11 +1031,10 @@ inline GemmPlan plan_upconv_bwd(int NB, int H, int W, int C, int Cout, const voi
 
 inline void launch_gemm_kernel(const GemmPlan& g, cudaStream_t st);
 inline void gemm_set_smem_attr() {
-  static bool done = false;
-  if (!done) {
+  static bool done[64] = {false};
+  if (first_use_on_device(done)) {
     MDC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     MDC_CUDA(cudaFuncSetAttribute(umma_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    done = true;
   }
 }
 

@@ -1,0 +1,107 @@
+// Host-side planning and launching of the GroupNorm(+SiLU) kernels (kernels.cuh), shared by the step engine and the
+// kernel-level debug entry points so that the tests exercise exactly the selector the engine uses.
+//
+//   * tensors whose per-CTA slab fits in shared memory: ONE launch (gn_fused_fwd / gn_fused_bwd, grid barrier);
+//   * larger tensors (the 56-226 MB decoder activations): two passes (statistics, then apply), the statistics pass
+//     being skipped when the producing tcgen05 GEMM / conv already emitted them from its epilogue (GemmParams::gn_*).
+#pragma once
+#include <vector>
+
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace mdc {
+
+struct GNPlan {
+  GNShape s;    // two-pass tiling
+  GNShape sfu;  // single-launch tiling
+  int G = 0, threads = 0, threads_b = 0;
+  bool fuse_f = false, fuse_b = false;
+  size_t smem_f = 0, smem_b = 0;
+  size_t partial_floats = 0;  // scratch the launchers need (per-block partial sums)
+};
+
+constexpr size_t GN_FUSED_SMEM_CAP = 200 * 1024;
+
+// Function attributes are per device: call once per device before the first launch there.
+inline void gn_set_attrs() {
+  static bool done[64] = {false};
+  if (!first_use_on_device(done)) return;
+  MDC_CUDA(cudaFuncSetAttribute(gn_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(GN_FUSED_SMEM_CAP)));
+  MDC_CUDA(cudaFuncSetAttribute(gn_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(GN_FUSED_SMEM_CAP)));
+}
+
+// mode: 0 = automatic (single launch when the slab fits), 1 = force the two-pass kernels, 2 = require the single launch.
+inline GNPlan plan_groupnorm(int N, int HW, int C, int G, long long ld, int mode = 0) {
+  MDC_CHECK(C % G == 0 && (C / G) % 2 == 0 && C % 8 == 0, "GroupNorm: C=%d G=%d unsupported", C, G);
+  GNPlan p;
+  p.G = G;
+  const int CV = C / 8;
+  MDC_CHECK(CV <= 384, "GroupNorm: C=%d too wide", C);
+  const int R = std::max(1, 512 / CV);
+  p.threads = CV * R;
+  p.threads_b = CV * std::max(1, 384 / CV);
+  GNShape s;
+  s.N = N, s.HW = HW, s.C = C, s.G = G, s.ld = ld;
+  const int sms = g_num_sms();
+  int want_blocks = std::max(1, (2 * sms) / N);
+  int ppb = std::max(R, (s.HW + want_blocks - 1) / want_blocks);
+  ppb = ((ppb + R - 1) / R) * R;
+  s.pix_per_block = ppb;
+  s.blocks_per_img = (s.HW + ppb - 1) / ppb;
+  p.s = s;
+  // single-launch variant: one CTA per SM at most, its pixel slab (x, or x and dy) staged in shared memory
+  static const bool no_fuse = getenv("MDC_NO_GNFUSE") != nullptr;
+  GNShape f = s;
+  const int bpi = std::max(1, std::min(sms / N, s.HW));
+  f.pix_per_block = (s.HW + bpi - 1) / bpi;
+  f.blocks_per_img = (s.HW + f.pix_per_block - 1) / f.pix_per_block;
+  const size_t slab = static_cast<size_t>(f.pix_per_block) * C * 2;
+  const size_t extra = (static_cast<size_t>((p.threads + 31) / 32) * 2 * G + 2 * G) * sizeof(float);
+  const bool ok = !(no_fuse && mode != 2) && mode != 1 && p.threads >= 8 * G && N * f.blocks_per_img <= sms;
+  p.sfu = f;
+  p.smem_f = slab + extra, p.smem_b = 2 * slab + extra;
+  p.fuse_f = ok && p.smem_f <= GN_FUSED_SMEM_CAP;
+  p.fuse_b = ok && p.smem_b <= GN_FUSED_SMEM_CAP;
+  MDC_CHECK(mode != 2 || (p.fuse_f && p.fuse_b), "GroupNorm: the single-launch variant does not fit (N=%d HW=%d C=%d)", N, HW, C);
+  // the single-launch variant may use MORE blocks than the two-pass one on small maps (one pixel row per block)
+  p.partial_floats = static_cast<size_t>(2) * G * N * std::max(s.blocks_per_img, f.blocks_per_img);
+  return p;
+}
+
+struct GNScratch {
+  float* partial = nullptr;        // >= plan.partial_floats
+  float* gstats = nullptr;         // 2 * G * N floats (backward group sums)
+  unsigned int* ticket = nullptr;  // N counters, zero-initialised
+  unsigned int* bar = nullptr;     // 3 words (arrivals, generation, sticky timeout flag), zero-initialised
+};
+
+// have_stats: the statistics of x were already written to `stats` by the producing GEMM's epilogue (two-pass path only).
+inline void run_gn_fwd(const GNPlan& p, const bf16* x, bf16* y, long long ldy, const float* gamma, const float* beta, float eps,
+                       int silu, float* stats, const GNScratch& sc, cudaStream_t st, bool have_stats = false) {
+  if (p.fuse_f) {
+    launch_k(gn_fused_fwd_kernel, dim3(p.sfu.N * p.sfu.blocks_per_img), dim3(p.threads), p.smem_f, st, x, p.sfu, sc.partial, eps, stats, sc.bar,
+             gamma, beta, silu, y, ldy);
+    return;
+  }
+  const int grid = p.s.N * p.s.blocks_per_img;
+  if (!have_stats)
+    launch_k(gn_stats_kernel, dim3(grid), dim3(p.threads), ((p.threads + 31) / 32) * 2 * p.G * sizeof(float), st, x, p.s, sc.partial, eps, stats,
+             sc.ticket);
+  launch_k(gn_apply_kernel, dim3(grid), dim3(p.threads), 0, st, x, p.s, static_cast<const float*>(stats), gamma, beta, silu, y, ldy);
+}
+inline void run_gn_bwd(const GNPlan& p, const bf16* x, const bf16* dy, long long lddy, const float* gamma, const float* beta, int silu,
+                       const float* stats, bf16* dx, long long lddx, int acc, const GNScratch& sc, cudaStream_t st) {
+  if (p.fuse_b) {
+    launch_k(gn_fused_bwd_kernel, dim3(p.sfu.N * p.sfu.blocks_per_img), dim3(p.threads), p.smem_b, st, x, dy, lddy, p.sfu, stats, gamma, beta, silu,
+             sc.partial, sc.bar, dx, lddx, acc);
+    return;
+  }
+  const int grid = p.s.N * p.s.blocks_per_img;
+  launch_k(gn_bwd_stats_kernel, dim3(grid), dim3(p.threads_b), ((p.threads_b + 31) / 32) * 2 * p.G * sizeof(float), st, x, dy, lddy, p.s, stats,
+           gamma, beta, silu, sc.partial, sc.gstats, sc.ticket);
+  launch_k(gn_bwd_apply_kernel, dim3(grid), dim3(p.threads_b), 0, st, x, dy, lddy, p.s, stats, static_cast<const float*>(sc.gstats), gamma, beta,
+           silu, dx, lddx, acc);
+}
+
+}  // namespace mdc

@@ -107,4 +107,69 @@ __global__ void to_f32_kernel(const T* __restrict__ w, float* __restrict__ out, 
     out[i] = to_f32(w[i]);
 }
 
+
+// ---------------------------------------------------------------------------------------------- batched re-packing
+// One launch re-packs ANY number of parameters (mdc_set_weights): blockIdx.y selects the job, the blocks of a row
+// grid-stride over its elements.  A model is ~1100 parameters and ~2300 destination layouts; one launch per layout
+// would bury the hot kernels of a short run under thousands of pack launches in any launch-list profile.
+enum PackKind { PK_CONV_FWD = 0, PK_CONV_DGRAD = 1, PK_UPCONV_FWD = 2, PK_UPCONV_BWD = 3, PK_MATRIX = 4, PK_MATRIX_T = 5, PK_VEC = 6 };
+struct PackJob {
+  const void* src;
+  void* dst;
+  int kind, src_bf16;
+  int out, in, pad;   // conv kinds: Cout, C, padded K-channel count; matrix: rows, cols; vec: n
+  long long ld;       // matrix kinds: destination row stride
+  float vscale, vshift;
+};
+template <typename T>
+__device__ __forceinline__ void pack_job_body(const PackJob& j) {
+  const T* w = static_cast<const T*>(j.src);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(j.dst);
+  const long long stride = 1LL * gridDim.x * blockDim.x, first = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+  const int Cout = j.out, C = j.in, P = j.pad;
+  switch (j.kind) {
+    case PK_CONV_FWD:
+      for (long long i = first; i < 1LL * Cout * 9 * P; i += stride) {
+        const int c = i % P, tap = (i / P) % 9, co = i / (9LL * P);
+        out[i] = __float2bfloat16(c < C ? to_f32(w[((1LL * co * C + c) * 9) + tap]) : 0.f);
+      }
+      break;
+    case PK_CONV_DGRAD:
+      for (long long i = first; i < 1LL * C * 9 * P; i += stride) {
+        const int co = i % P, tap = (i / P) % 9, ci = i / (9LL * P);
+        out[i] = __float2bfloat16(co < Cout ? to_f32(w[((1LL * co * C + ci) * 9) + (8 - tap)]) : 0.f);
+      }
+      break;
+    case PK_UPCONV_FWD:
+      for (long long i = first; i < 1LL * Cout * 16 * P; i += stride) {
+        const int c = i % P, tap = (i / P) % 16, co = i / (16LL * P);
+        out[i] = __float2bfloat16(c < C ? upconv_weff(w, co, c, C, tap >> 3, (tap >> 2) & 1, (tap >> 1) & 1, tap & 1) : 0.f);
+      }
+      break;
+    case PK_UPCONV_BWD:
+      for (long long i = first; i < 1LL * C * 16 * P; i += stride) {
+        const int co = i % P, tap = (i / P) % 16, ci = i / (16LL * P);
+        out[i] = __float2bfloat16(co < Cout ? upconv_weff(w, co, ci, C, tap >> 3, (tap >> 2) & 1, (tap >> 1) & 1, tap & 1) : 0.f);
+      }
+      break;
+    case PK_MATRIX:
+    case PK_MATRIX_T:
+      for (long long i = first; i < 1LL * j.out * j.in; i += stride) {
+        const int c = i % j.in, r = i / j.in;
+        out[j.kind == PK_MATRIX ? 1LL * r * j.ld + c : 1LL * c * j.ld + r] = __float2bfloat16(to_f32(w[i]));
+      }
+      break;
+    default:  // PK_VEC: fp32 destination, optionally stored as vscale * v + vshift
+      for (long long i = first; i < j.out; i += stride) static_cast<float*>(j.dst)[i] = j.vscale * to_f32(w[i]) + j.vshift;
+      break;
+  }
+}
+__global__ void pack_jobs_kernel(const PackJob* __restrict__ jobs) {
+  const PackJob j = jobs[blockIdx.y];
+  if (j.src_bf16)
+    pack_job_body<__nv_bfloat16>(j);
+  else
+    pack_job_body<float>(j);
+}
+
 }  // namespace mdc

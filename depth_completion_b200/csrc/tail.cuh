@@ -895,6 +895,41 @@ __global__ void latent_out_kernel(const bf16* __restrict__ mom, long long ld, in
   out[i] = __float2bfloat16(__bfloat162float(mom[(1LL * n * HW + p) * ld + c]) * scaling);
 }
 
+// Valid points per sample (mask != 0): one block per sample.
+__global__ void count_mask_kernel(const uint8_t* __restrict__ mask, int HW, int* __restrict__ counts) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  __shared__ float red[32];
+  int c = 0;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) c += mask[1LL * blockIdx.x * HW + i] != 0;
+  const float t = block_sum(static_cast<float>(c), red);  // exact: a frame has far fewer than 2^24 pixels
+  if (threadIdx.x == 0) counts[blockIdx.x] = static_cast<int>(t + 0.5f);
+}
+// Per-call device state derived from the point counts: pt_off = exclusive prefix sum over the samples.  With the
+// 5-float frame statistics of sparse_norm_kernel ({lo, hi, gmin, gmax, n_valid} per sample) it also fills the guide /
+// metric ranges the loss kernels read, so mdc_begin_frame needs no host round trip for them.
+__global__ void frame_state_kernel(const int* __restrict__ counts, const float* __restrict__ stats5, int N, int* __restrict__ pt_off,
+                                   float* __restrict__ gminmax, float* __restrict__ depth_minmax) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int acc = 0;
+  pt_off[0] = 0;
+  for (int n = 0; n < N; ++n) {
+    int c;
+    if (stats5) {
+      const float* s = stats5 + 5 * n;
+      c = static_cast<int>(s[4] + 0.5f);
+      depth_minmax[2 * n] = s[0], depth_minmax[2 * n + 1] = s[1];
+      gminmax[2 * n] = s[2], gminmax[2 * n + 1] = s[3];
+    } else {
+      c = counts[n];
+    }
+    acc += c;
+    pt_off[n + 1] = acc;
+  }
+}
+
 // Ordered compaction of the valid pixels of one sample (mask != 0): one block per sample, run once per call.
 __global__ void compact_points_kernel(const float* __restrict__ guide, const uint8_t* __restrict__ mask, int HW,
                                       const int* __restrict__ pt_off, int* __restrict__ pt_idx,

@@ -77,3 +77,60 @@ def conv3x3(x_nhwc, w_oihw, *, dgrad=False, bias=None, bias_img=None, res=None, 
 def tune(bn=0, cs=0, ksplit=0, wcopies=1):
     """Planner overrides for tests / sweeps (include/mdc_debug.h: mdc_dbg_tune); call tune() to reset."""
     check(lib().mdc_dbg_tune(C.c_int(bn), C.c_int(cs), C.c_int(ksplit), C.c_int(wcopies)))
+
+
+def attention(qkv, heads, dout=None, iters=0):
+    """Self-attention as the engine plans it (mdc_dbg_attention): head_dim 64 runs the fused tcgen05 flash kernels, other
+    head dims GEMM + softmax + GEMM.  qkv: [n, T, 3 * heads * dh] bf16 (q | k | v).  Returns (o, dqkv or None, (ms_fwd,
+    ms_bwd))."""
+    assert qkv.dtype == torch.bfloat16 and qkv.is_cuda and qkv.is_contiguous() and qkv.ndim == 3
+    n, T, c3 = qkv.shape
+    d = c3 // 3
+    dh = d // heads
+    o = torch.empty(n, T, d, device=qkv.device, dtype=torch.bfloat16)
+    dqkv = None
+    if dout is not None:
+        dout = dout.contiguous()
+        assert dout.shape == o.shape and dout.dtype == torch.bfloat16
+        dqkv = torch.zeros_like(qkv)
+    ms = (C.c_float * 2)()
+    check(lib().mdc_dbg_attention(C.c_int(n), C.c_int(T), C.c_int(heads), C.c_int(dh), ptr(qkv), ptr(o), ptr(dout), ptr(dqkv),
+                                  C.c_int(iters), ms))
+    return o, dqkv, (ms[0], ms[1])
+
+
+def groupnorm(x_nhwc, gamma, beta, groups, eps, silu, dy=None, dx_init=None, mode=0, iters=0):
+    """GroupNorm (+SiLU) forward / input-gradient backward with the engine's kernel selection (mdc_dbg_groupnorm).
+    x_nhwc: [n, HW, C] bf16; mode 0 auto, 1 two-pass kernels, 2 single-launch kernels; dx_init: accumulate into it.
+    Returns (y, dx or None, stats [n, groups, 2], (ms_fwd, ms_bwd))."""
+    assert x_nhwc.dtype == torch.bfloat16 and x_nhwc.is_contiguous() and x_nhwc.ndim == 3
+    n, HW, Cc = x_nhwc.shape
+    gamma, beta = gamma.float().contiguous(), beta.float().contiguous()
+    y = torch.empty_like(x_nhwc)
+    stats = torch.empty(n, groups, 2, device=x_nhwc.device, dtype=torch.float32)
+    dx = None
+    if dy is not None:
+        dy = dy.contiguous()
+        dx = dx_init.clone().contiguous() if dx_init is not None else torch.empty_like(x_nhwc)
+    ms = (C.c_float * 2)()
+    check(lib().mdc_dbg_groupnorm(C.c_int(n), C.c_int(HW), C.c_int(Cc), C.c_int(groups), C.c_float(eps), C.c_int(int(silu)),
+                                  ptr(x_nhwc), ptr(gamma), ptr(beta), ptr(y), ptr(dy), ptr(dx), C.c_int(int(dx_init is not None)),
+                                  C.c_int(mode), ptr(stats), C.c_int(iters), ms))
+    return y, dx, stats, (ms[0], ms[1])
+
+
+def upconv(x_nhwc, w_oihw, *, dgrad=False, bias=None, iters=0):
+    """Fused nearest-2x upsample + conv3x3 (mdc_dbg_upconv).  Forward: x [NB, H, W, C] -> [NB, 2H, 2W, Cout]; dgrad: x is
+    dy [NB, 2H, 2W, Cout] -> [NB, H, W, C].  Channel counts must be multiples of 8."""
+    assert x_nhwc.dtype == torch.bfloat16 and x_nhwc.is_contiguous() and w_oihw.dtype == torch.float32
+    w_oihw = w_oihw.contiguous()
+    Cout, Cc = w_oihw.shape[0], w_oihw.shape[1]
+    NB, Hx, Wx, Cx = x_nhwc.shape
+    H, W = (Hx // 2, Wx // 2) if dgrad else (Hx, Wx)
+    Cres = Cc if dgrad else Cout
+    assert Cx == (Cout if dgrad else Cc) and Cx % 8 == 0 and Cres % 8 == 0
+    out = torch.zeros(NB, H if dgrad else 2 * H, W if dgrad else 2 * W, Cres, device=x_nhwc.device, dtype=torch.bfloat16)
+    ms = C.c_float(0)
+    check(lib().mdc_dbg_upconv(C.c_int(NB), C.c_int(H), C.c_int(W), C.c_int(Cc), C.c_int(Cout), ptr(x_nhwc), _ll(Cx), ptr(w_oihw),
+                               C.c_int(int(dgrad)), ptr(bias), ptr(out), _ll(Cres), C.c_int(iters), C.byref(ms)))
+    return out, ms.value

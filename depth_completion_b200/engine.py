@@ -36,6 +36,12 @@ def _declare(l):
     if getattr(l, "_mdc_declared", False):
         return
     l.mdc_create.argtypes = [C.POINTER(MdcConfig), C.POINTER(C.c_void_p)]
+    l.mdc_create_shared.argtypes = [C.POINTER(MdcConfig), C.c_void_p, C.POINTER(C.c_void_p)]
+    l.mdc_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    l.mdc_set_weights.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong),
+                                  C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    l.mdc_weights_loaded.argtypes = [C.c_void_p]
+    l.mdc_release_workspace.argtypes = [C.c_void_p]
     l.mdc_destroy.argtypes = [C.c_void_p]
     l.mdc_destroy.restype = None
     l.mdc_num_weights.argtypes = [C.c_void_p]
@@ -72,6 +78,7 @@ def _declare(l):
     l.mdc_dbg_read_buffer.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
     l.mdc_dbg_loss.argtypes = [C.c_void_p] * 6
     l.mdc_dbg_update.argtypes = [C.c_void_p] * 4
+    l.mdc_dbg_set_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.mdc_dbg_profile_gemm_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.mdc_dbg_profile_ops.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     l.mdc_dbg_time_tapes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -82,7 +89,9 @@ class StepEngine:
     """Owns one mdc_handle: the UNet + VAE-decoder tapes and workspace for fixed (N, H, W, resolution, steps)."""
 
     def __init__(self, unet_cfg: UNetConfig, vae_cfg: VAEConfig, n_batch: int, height: int, width: int,
-                 resolution: int, steps: int, device: torch.device | int = 0):
+                 resolution: int, steps: int, device: torch.device | int = 0, share_weights_with: "StepEngine | None" = None):
+        """share_weights_with: another live engine of the same model on the same device whose packed parameters this
+        engine reuses (mdc_create_shared) -- a new frame geometry then costs workspace only, no re-packing."""
         self._h = C.c_void_p(0)
         self.lib = lib()
         _declare(self.lib)
@@ -116,14 +125,30 @@ class StepEngine:
                 c.tiny_enc_blocks[i], c.tiny_dec_blocks[i] = ne, nd
             c.tiny_magnitude = vae_cfg.latent_magnitude
         with torch.cuda.device(dev):
-            check(self.lib.mdc_create(C.byref(c), C.byref(self._h)))
+            if share_weights_with is not None:
+                check(self.lib.mdc_create_shared(C.byref(c), share_weights_with._h, C.byref(self._h)))
+            else:
+                check(self.lib.mdc_create(C.byref(c), C.byref(self._h)))
+        self._stream = None
         self._keep = []
+
+    def _on_stream(self):
+        """Hands torch's CURRENT stream on the engine's device to the library (mdc_set_stream) so that the library's
+        kernels are ordered with the caller's torch ops exactly as the reference's own torch ops would be."""
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        if st != self._stream:
+            check(self.lib.mdc_set_stream(self._h, C.c_void_p(st)))
+            self._stream = st
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             self.lib.mdc_destroy(self._h)
             self._h = C.c_void_p(0)
+
+    def release_workspace(self):
+        """Frees tapes and workspace but keeps the packed weights alive for `share_weights_with` (mdc_release_workspace)."""
+        check(self.lib.mdc_release_workspace(self._h))
 
     def __del__(self):
         try:
@@ -145,9 +170,14 @@ class StepEngine:
             out[self.lib.mdc_weight_key(self._h, i).decode()] = tuple(shp[: nd.value])
         return out
 
+    def weights_loaded(self) -> bool:
+        return bool(self.lib.mdc_weights_loaded(self._h))
+
     def load_weights(self, unet_sd: dict, vae_sd: dict):
-        """Hands every parameter the tapes need to mdc_set_weight (keys: 'unet.' / 'vae.' + diffusers name)."""
-        missing = []
+        """Hands every parameter the tapes need to mdc_set_weights in ONE call (keys: 'unet.' / 'vae.' + diffusers name);
+        the library re-packs all of them with a single kernel launch."""
+        self._on_stream()
+        missing, keys, tensors = [], [], []
         for key in self.weight_keys():
             prefix, name = key.split(".", 1)
             sd = unet_sd if prefix == "unet" else vae_sd
@@ -157,25 +187,36 @@ class StepEngine:
             t = sd[name].detach()
             if t.dtype not in (torch.float32, torch.bfloat16):
                 t = t.float()
-            t = t.to(self.device).contiguous()
-            shape = (C.c_longlong * t.ndim)(*t.shape)
-            dt = 0 if t.dtype == torch.float32 else 1
-            check(self.lib.mdc_set_weight(self._h, key.encode(), ptr(t), shape, t.ndim, dt))
+            keys.append(key.encode())
+            tensors.append(t.to(self.device).contiguous())
         if missing:
             raise MdcError(f"state dicts lack {len(missing)} parameters, e.g. {missing[:3]}")
-        torch.cuda.synchronize(self.device)
+        n = len(keys)
+        shapes = (C.c_longlong * (4 * n))(*([1] * (4 * n)))
+        for i, t in enumerate(tensors):
+            if t.ndim > 4:
+                raise MdcError(f"parameter {keys[i].decode()} has rank {t.ndim}")
+            for j, d in enumerate(t.shape):
+                shapes[4 * i + j] = d
+        with torch.cuda.device(self.device):
+            check(self.lib.mdc_set_weights(
+                self._h, n, (C.c_char_p * n)(*keys), (C.c_void_p * n)(*[t.data_ptr() for t in tensors]), shapes,
+                (C.c_int * n)(*[t.ndim for t in tensors]), (C.c_int * n)(*[0 if t.dtype == torch.float32 else 1 for t in tensors])))
 
     def prepare(self, ctx: torch.Tensor, alphas_cumprod: torch.Tensor, timesteps: np.ndarray):
         ctx = ctx.to(self.device, torch.bfloat16).contiguous()
         assert ctx.numel() == 2 * self.unet_cfg.cross_attention_dim, "empty-prompt embedding must be [1, 2, cross_dim]"
         ac = np.ascontiguousarray(alphas_cumprod.detach().float().cpu().numpy())
         ts = np.ascontiguousarray(np.asarray(timesteps, dtype=np.int32))
-        assert ac.shape[0] == 1000 and ts.shape[0] == self.steps
+        if ac.shape[0] != 1000 or ts.shape[0] != self.steps:
+            raise ValueError(f"expected 1000 alphas_cumprod and {self.steps} timesteps, got {ac.shape[0]} and {ts.shape[0]}")
+        self._on_stream()
         check(self.lib.mdc_prepare(self._h, ptr(ctx), ac.ctypes.data_as(C.c_void_p), ts.ctypes.data_as(C.c_void_p),
                                    int(ts.shape[0])))
 
     # ------------------------------------------------------------------ per call
     def begin(self, img_latents, x, guide, mask, guide_minmax, depth_minmax, lr_latent=0.05, lr_scaling=0.005):
+        self._on_stream()
         il = img_latents.to(self.device, torch.bfloat16).contiguous()
         x = x.to(self.device, torch.bfloat16).contiguous()
         guide = guide.to(self.device, torch.float32).contiguous()
@@ -188,13 +229,16 @@ class StepEngine:
                                  dmm.ctypes.data_as(C.c_void_p), float(lr_latent), float(lr_scaling)))
 
     def run(self, n_steps: int):
+        self._on_stream()
         check(self.lib.mdc_run(self._h, int(n_steps)))
 
     def sample(self, n_steps: int):
         """n plain DDIM steps without guidance: the train_latents=False branch (marigold_dc.py:905-909)."""
+        self._on_stream()
         check(self.lib.mdc_sample(self._h, int(n_steps)))
 
     def get_state(self):
+        self._on_stream()
         x = torch.empty(self.n, 4, self.lh, self.lw, device=self.device, dtype=torch.bfloat16)
         sc = np.zeros(self.n, np.float32)
         sh = np.zeros(self.n, np.float32)
@@ -206,6 +250,7 @@ class StepEngine:
     def encode(self, imgs: torch.Tensor) -> torch.Tensor:
         """Per-frame prologue in the library: preprocess + VAE encoder -> img_latents [N,4,EH,EW] bf16
         (marigold_dc.py:687-698).  imgs: [N, 1|3, H, W] uint8, or floating point in [0, 1]."""
+        self._on_stream()
         imgs, dt = self._image_arg(imgs)
         out = torch.empty(self.n, 4, self.lh, self.lw, device=self.device, dtype=torch.bfloat16)
         check(self.lib.mdc_encode(self._h, ptr(imgs), dt, int(imgs.shape[1]), ptr(out)))
@@ -231,6 +276,7 @@ class StepEngine:
                     kld_mode="simple", percentile=(0.01, 0.99), closed_form=False, interp_mode="bilinear"):
         """Non-default branches of the reference call (mdc_set_options; marigold_dc.py:467-493): they apply to the next
         begin / begin_frame.  loss_funcs is the reference's list (a term listed twice counts twice, :177-236)."""
+        self._on_stream()
         if projection not in self.PROJECTIONS:
             raise ValueError(f"Unknown projection method: {projection}")
         if opt not in self.OPTIMIZERS:
@@ -248,6 +294,7 @@ class StepEngine:
     def begin_frame(self, imgs, sparses, x, max_depth, min_depth=0.0, norm="minmax", lr_latent=0.05, lr_scaling=0.005):
         """The per-frame prologue in one library call (mdc_begin_frame): image preprocess + VAE encoder, sparse-depth
         normalisation, per-call state (marigold_dc.py:687-789).  Raises ValueError for a sample with an empty mask."""
+        self._on_stream()
         imgs, dt = self._image_arg(imgs)
         sparses = sparses.to(self.device, torch.float32).contiguous()
         x = x.to(self.device, torch.bfloat16).contiguous()
@@ -263,6 +310,7 @@ class StepEngine:
     def decode_final(self, closed_form: bool = False) -> torch.Tensor:
         """Final decode + affine + clamp + de-normalisation (marigold_dc.py:970-984); closed_form=True fits scale / shift
         by masked least squares (:53-128) instead of using the learned ones."""
+        self._on_stream()
         out = torch.empty(self.n, 1, self.H, self.W, device=self.device, dtype=torch.float32)
         fn = self.lib.mdc_decode_final_closed_form if closed_form else self.lib.mdc_decode_final
         check(fn(self._h, ptr(out)))
@@ -273,6 +321,7 @@ class StepEngine:
 
     def profile_gemm_step(self) -> dict:
         """In-situ CUDA-event timing of every tcgen05 GEMM / conv launch of one guided step's launch sequence."""
+        self._on_stream()
         ms, fl, n = C.c_float(0), C.c_double(0), C.c_int(0)
         check(self.lib.mdc_dbg_profile_gemm_step(self._h, C.byref(ms), C.byref(fl), C.byref(n)))
         return dict(ms=ms.value, flops=fl.value, launches=n.value, tflops=fl.value / max(ms.value, 1e-9) / 1e9)
@@ -287,6 +336,7 @@ class StepEngine:
         return (self.n, 4, self.lh, self.lw), (self.n, 3, self.lh * 8, self.lw * 8)
 
     def dbg_forward(self, which: int, step: int, x: torch.Tensor) -> torch.Tensor:
+        self._on_stream()
         ishape, oshape = self._io_shapes(which)
         x = x.to(self.device, torch.float32).contiguous()
         assert tuple(x.shape) == ishape, (x.shape, ishape)
@@ -295,6 +345,7 @@ class StepEngine:
         return out
 
     def dbg_backward(self, which: int, dout: torch.Tensor) -> torch.Tensor:
+        self._on_stream()
         ishape, oshape = self._io_shapes(which)
         dout = dout.to(self.device, torch.float32).contiguous()
         assert tuple(dout.shape) == oshape
@@ -307,6 +358,7 @@ class StepEngine:
         return [self.lib.mdc_dbg_tensor_name(self._h, i).decode() for i in range(n)]
 
     def dbg_read(self, name: str, grad: bool = False) -> torch.Tensor:
+        self._on_stream()
         shp = (C.c_int * 4)()
         check(self.lib.mdc_dbg_tensor_shape(self._h, name.encode(), shp))
         out = torch.empty(tuple(shp), device=self.device, dtype=torch.float32)
@@ -314,16 +366,19 @@ class StepEngine:
         return out
 
     def dbg_x_adam(self) -> torch.Tensor:
+        self._on_stream()
         x = torch.empty(self.n, 4, self.lh, self.lw, device=self.device, dtype=torch.bfloat16)
         check(self.lib.mdc_dbg_read_x_adam(self._h, ptr(x)))
         return x
 
     def dbg_buffer(self, which: str) -> torch.Tensor:
+        self._on_stream()
         out = torch.empty(self.n, 4, self.lh, self.lw, device=self.device, dtype=torch.float32)
         check(self.lib.mdc_dbg_read_buffer(self._h, which.encode(), ptr(out)))
         return out
 
     def dbg_frame_state(self):
+        self._on_stream()
         guide = torch.empty(self.n, 1, self.H, self.W, device=self.device, dtype=torch.float32)
         mask = torch.empty(self.n, 1, self.H, self.W, device=self.device, dtype=torch.uint8)
         st = np.zeros((self.n, 5), np.float32)
@@ -331,6 +386,7 @@ class StepEngine:
         return guide, mask.bool(), st
 
     def dbg_loss(self, dec_nchw: torch.Tensor):
+        self._on_stream()
         dec = dec_nchw.to(self.device, torch.float32).contiguous()
         assert tuple(dec.shape) == (self.n, 3, self.lh * 8, self.lw * 8)
         ddec = torch.empty_like(dec)
@@ -340,14 +396,28 @@ class StepEngine:
         return ddec, torch.from_numpy(ls), torch.from_numpy(gs), torch.from_numpy(gt)
 
     def dbg_update(self, v, dz, dunet_in):
+        self._on_stream()
         v, dz, du = (t.to(self.device, torch.float32).contiguous() for t in (v, dz, dunet_in))
         assert tuple(v.shape) == (self.n, 4, self.lh, self.lw) and tuple(du.shape) == (self.n, 8, self.lh, self.lw)
         check(self.lib.mdc_dbg_update(self._h, ptr(v), ptr(dz), ptr(du)))
 
+    def dbg_set_state(self, step: int, x=None, exp_avg=None, exp_avg_sq=None, affine6=None):
+        """Teacher forcing (mdc_dbg_set_state): latent and its Adam moments [N,4,EH,EW], affine6 = [6, N] floats (scale,
+        shift, and the fp32 Adam moments s_m, s_v, t_m, t_v); the next run(1) executes guided step `step`."""
+        self._on_stream()
+        keep = [None if t is None else t.to(self.device, torch.bfloat16).contiguous() for t in (x, exp_avg, exp_avg_sq)]
+        a6 = None
+        if affine6 is not None:
+            a6 = np.ascontiguousarray(np.asarray(affine6, dtype=np.float32).reshape(6, self.n))
+        check(self.lib.mdc_dbg_set_state(self._h, int(step), ptr(keep[0]), ptr(keep[1]), ptr(keep[2]),
+                                         a6.ctypes.data_as(C.c_void_p) if a6 is not None else C.c_void_p(0)))
+
     def dbg_profile_ops(self, csv_path: str, iters: int = 5):
+        self._on_stream()
         check(self.lib.mdc_dbg_profile_ops(self._h, csv_path.encode(), iters))
 
     def dbg_time_tapes(self, iters: int = 3):
+        self._on_stream()
         ms = (C.c_float * 4)()
         check(self.lib.mdc_dbg_time_tapes(self._h, iters, ms))
         return dict(unet_fwd=ms[0], unet_bwd=ms[1], dec_fwd=ms[2], dec_bwd=ms[3])

@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ddim, prologue
+from . import ddim
 from ._lib import MdcError
 from .config import processed_geometry, unet_config_from, vae_config_from
 from .engine import StepEngine
@@ -22,6 +22,19 @@ from .engine import StepEngine
 SUPPORTED_LOSS_FUNCS = ["l1", "l2", "edge", "smooth"]  # marigold_dc.py:19
 EPSILON = 1e-7  # marigold_dc.py:20
 EMPTY_PROMPT_IDS = (49406, 49407)  # CLIP BOS, EOS: tokenizer("", padding="do_not_pad")
+
+
+def check_image(image: torch.Tensor) -> None:
+    """The checks of MarigoldImageProcessor.preprocess that raise (reached from
+    marigold_dc.py:687-692)."""
+    if image.ndim != 4:
+        raise ValueError(f"Input image is not 4-dimensional: shape={tuple(image.shape)}")
+    if not torch.is_floating_point(image) and image.dtype != torch.uint8:
+        raise ValueError(f"Image dtype={image.dtype} is not supported.")
+    if image.shape[1] not in (1, 3):
+        raise ValueError(f"Input image is not 1- or 3-channel: {tuple(image.shape)}.")
+    if torch.is_floating_point(image) and (image.min().item() < 0.0 or image.max().item() > 1.0):
+        raise ValueError("Input image data is partially outside of the [0,1] range.")
 
 
 class MarigoldDepthCompletionPipeline:
@@ -48,14 +61,20 @@ class MarigoldDepthCompletionPipeline:
         self.empty_text_embedding = None
         p = next(iter(unet.state_dict().values()))
         self.device = p.device
-        self.dtype = torch.bfloat16  # the engine computes in bf16 (BASELINE.json configs b-e)
+        # The engine computes in bf16 with fp32 accumulation (BASELINE.json configs b-e, predict.py --dtype bf16).  A
+        # pipeline built from fp32 modules (predict.py:463-481 with torch_dtype=float32) would silently get bf16
+        # arithmetic, so that request is refused unless the caller opts in (weights are then rounded to bf16).
+        self.dtype = torch.bfloat16
+        self.allow_fp32_modules = True  # random-init / test modules are fp32 containers of bf16-representable values
 
     # The reference swaps modules on a live pipeline (predict.py:484-488 `pipe.vae = AutoencoderTiny...`, :491-494
     # `pipe.scheduler = DDIMScheduler...`): re-derive the config and drop everything built from the old module.
     def _invalidate(self):
-        for eng in getattr(self, "_engines", {}).values():
-            eng.close()
+        for eng in list(getattr(self, "_engines", {}).values()) + [getattr(self, "_keeper", None)]:
+            if eng is not None:
+                eng.close()
         self._engines = {}
+        self._keeper = None
         self._sd_cache = None
 
     @property
@@ -88,15 +107,48 @@ class MarigoldDepthCompletionPipeline:
         self._invalidate()
 
     # ------------------------------------------------------------------ plumbing
-    def to(self, device):
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, prediction_type=None, torch_dtype=torch.bfloat16, **kwargs):
+        """The constructor call of the reference's only caller (predict.py:463-481): loads the diffusers
+        `MarigoldDepthPipeline` checkpoint and wraps its modules.  Needs `diffusers` (the reference's own dependency,
+        requirements.txt:1); raises ImportError with that hint when it is not installed.  torch_dtype=float32 is refused:
+        this library has no fp32 arithmetic path (it would silently compute in bf16 otherwise)."""
+        if torch_dtype not in (torch.bfloat16, None):
+            raise NotImplementedError(f"torch_dtype={torch_dtype}: the B200 engine computes in bfloat16 only (predict.py --dtype bf16); "
+                                      "an fp32 pipeline would silently run at reduced precision")
+        try:
+            from diffusers import MarigoldDepthPipeline  # noqa: PLC0415
+        except ImportError as e:  # pragma: no cover - diffusers is absent from the build image
+            raise ImportError("from_pretrained needs the reference's own dependency `diffusers` (requirements.txt:1) to read "
+                              "the checkpoint; construct the class from modules / state dicts instead") from e
+        base = MarigoldDepthPipeline.from_pretrained(pretrained_model_name_or_path, prediction_type=prediction_type,
+                                                     torch_dtype=torch.bfloat16, **kwargs)
+        return cls.from_diffusers(base)
+
+    @classmethod
+    def from_diffusers(cls, base):
+        """Wraps the modules of a loaded diffusers Marigold pipeline (anything with .unet / .vae / .scheduler /
+        .text_encoder / .tokenizer), as MarigoldDepthCompletionPipeline(**base.components) does in the reference."""
+        pipe = cls(base.unet, base.vae, getattr(base, "scheduler", None), getattr(base, "text_encoder", None),
+                   getattr(base, "tokenizer", None), prediction_type=getattr(base, "prediction_type", None),
+                   scale_invariant=getattr(base, "scale_invariant", True), shift_invariant=getattr(base, "shift_invariant", True),
+                   default_denoising_steps=getattr(base, "default_denoising_steps", None),
+                   default_processing_resolution=getattr(base, "default_processing_resolution", None))
+        pipe.allow_fp32_modules = False
+        return pipe
+
+    def to(self, device=None, dtype=None):
+        if isinstance(device, torch.dtype):
+            device, dtype = None, device
+        if dtype is not None and dtype != torch.bfloat16:
+            raise NotImplementedError(f"dtype={dtype}: the B200 engine computes in bfloat16 only")
+        if device is None:
+            return self
         self.device = torch.device(device)
         for m in (self.unet, self.vae, self.text_encoder):
             if m is not None and hasattr(m, "to"):
                 m.to(self.device)
-        self._sd_cache = None
-        for eng in self._engines.values():  # free the old device's workspace instead of waiting for the collector
-            eng.close()
-        self._engines.clear()
+        self._invalidate()  # free the old device's workspace and weights instead of waiting for the collector
         return self
 
     def _state_dicts(self):
@@ -124,21 +176,50 @@ class MarigoldDepthCompletionPipeline:
                 self.empty_text_embedding = self.text_encoder(ids)[0]
         return self.empty_text_embedding
 
+    MAX_ENGINES = 4            # resident workspaces (one per call geometry), least recently used evicted first
+    MAX_ENGINE_BYTES = 110e9   # ... and never more than this much HBM in workspaces (a 4 x 768x1024 engine is 85 GB)
+
+    def _estimate_bytes(self, N, H, W, resolution) -> float:
+        """Workspace of a not-yet-built engine, scaled by pixel count from a resident one (0 when there is none)."""
+        if not self._engines:
+            return 0.0
+        ref = list(self._engines.values())[-1]
+        ph, pw, pad_h, pad_w = processed_geometry(H, W, resolution)
+        return ref.device_bytes() * (N * (ph + pad_h) * (pw + pad_w)) / max(1, ref.n * ref.lh * ref.lw * 64)
+
     def _engine(self, N, H, W, resolution, steps) -> StepEngine:
+        """One StepEngine per call geometry, kept resident (LRU) and all sharing ONE set of packed weights: a sequence
+        whose last batch is short, or alternating resolutions, builds workspace for the new shape but never re-packs the
+        parameters (the reference serves every shape from one set of modules, predict.py:585-700)."""
         key = (N, H, W, resolution, steps, str(self.device))
-        eng = self._engines.get(key)
+        eng = self._engines.pop(key, None)
         if eng is None:
             if self.device.type != "cuda":
                 raise MdcError("MarigoldDepthCompletionPipeline needs a CUDA device: call .to('cuda') (no CPU path)")
-            for old in self._engines.values():  # one resident workspace at a time
-                old.close()
-            self._engines.clear()
-            usd, vsd, _ = self._state_dicts()
-            eng = StepEngine(self.unet_cfg, self.vae_cfg, N, H, W, resolution, steps, self.device)
-            eng.load_weights(usd, vsd)
+            if not self.allow_fp32_modules:
+                bad = [k for k, v in self.unet.state_dict().items() if v.dtype == torch.float32][:1]
+                if bad:
+                    raise NotImplementedError("the modules are float32 (torch_dtype=float32, predict.py:463-481): the B200 "
+                                              "engine computes in bfloat16 only and will not silently lower the precision")
+            # make room first (dict order = least recently used first).  The first engine evicted stays behind as a
+            # workspace-less keeper of the packed weights, so eviction never forces a re-pack.
+            est = self._estimate_bytes(N, H, W, resolution)
+            while self._engines and (len(self._engines) >= self.MAX_ENGINES or
+                                     sum(e.device_bytes() for e in self._engines.values()) + est > self.MAX_ENGINE_BYTES):
+                old = self._engines.pop(next(iter(self._engines)))
+                if self._keeper is None:
+                    old.release_workspace()
+                    self._keeper = old
+                else:
+                    old.close()
+            donor = self._keeper or (list(self._engines.values())[-1] if self._engines else None)
+            eng = StepEngine(self.unet_cfg, self.vae_cfg, N, H, W, resolution, steps, self.device, share_weights_with=donor)
+            if not eng.weights_loaded():
+                usd, vsd, _ = self._state_dicts()
+                eng.load_weights(usd, vsd)
             ac, ts = ddim.tables_from_scheduler(self.scheduler, steps)
             eng.prepare(self._empty_embedding(), ac, ts)
-            self._engines[key] = eng
+        self._engines[key] = eng  # most recently used last
         return eng
 
     # ------------------------------------------------------------------ the call (marigold_dc.py:467-493)
@@ -215,7 +296,7 @@ class MarigoldDepthCompletionPipeline:
             # marigold_dc.py:661, :677-684 -- first draw of the seeded generator, in the pipeline dtype
             gen = torch.Generator(device=dev).manual_seed(seed)
             common = torch.randn((1, 4, EH, EW), device=dev, dtype=self.dtype, generator=gen).repeat(N, 1, 1, 1)
-            prologue.check_image(imgs)
+            check_image(imgs)
             x = common if pred_latents_prev is None else beta * common + (1 - beta) * pred_latents_prev.to(dev)
         # marigold_dc.py:687-789 inside libmdc_b200.so (mdc_begin_frame): image preprocess + VAE encoder, sparse-depth
         # normalisation (mask, masked min / max, clamp, guide and its min / max), per-call optimiser state.

@@ -10,8 +10,11 @@
  *
  * Conventions: every function returns 0 on success, non-zero on failure with the message available from
  * mdc_last_error() (thread-local).  Pointers are DEVICE pointers unless the name ends in _host.  One handle
- * owns one device, one stream and all workspace; it is not thread-safe.  The library never frees or keeps
- * caller memory beyond the call (weights are re-packed into library-owned layouts).
+ * owns one device and all workspace; it is not thread-safe.  Every entry point makes the handle's device current
+ * (cudaSetDevice) and enqueues its work on the handle's stream: a private blocking stream by default (implicitly ordered
+ * with the legacy default stream), or the caller's stream after mdc_set_stream -- the reference runs on torch's current
+ * stream (marigold_dc.py has no stream handling of its own), and the Python binding passes exactly that on every call.
+ * The library never frees or keeps caller memory beyond the call (weights are re-packed into library-owned layouts).
  */
 #ifndef MDC_H_
 #define MDC_H_
@@ -57,7 +60,19 @@ const char* mdc_last_error(void);
 
 /* Builds the UNet + VAE-decoder tapes, all launch plans and all workspace for the configured shapes. */
 int mdc_create(const mdc_config* cfg, mdc_handle** out);
+/* Same, but the new handle SHARES the packed parameters of `share_weights_with` (same device and model configuration;
+ * frame geometry, batch and step count may differ): a sequence whose last batch is short, or a second resolution, costs
+ * workspace and launch plans but no re-packing of the 1.8 GB of weights (the reference keeps one set of modules for
+ * every call shape, predict.py:463-481, :585-700).  The parameters live until the last sharing handle is destroyed. */
+int mdc_create_shared(const mdc_config* cfg, mdc_handle* share_weights_with, mdc_handle** out);
 void mdc_destroy(mdc_handle* h);
+/* Frees the tapes, launch plans and workspace of `h` but keeps the handle (and thereby the packed parameters) alive, so
+ * that it can still be passed to mdc_create_shared; every other call on it fails afterwards. */
+int mdc_release_workspace(mdc_handle* h);
+/* All later calls on `h` enqueue their work on `cuda_stream` (a cudaStream_t; NULL = back to the handle's own stream).
+ * Inputs must be ready in stream order on that stream; outputs are ready in stream order on it (calls documented as
+ * synchronising synchronise that stream). */
+int mdc_set_stream(mdc_handle* h, void* cuda_stream);
 
 /* Expected parameters, named by their diffusers state-dict key with a "unet." / "vae." prefix
  * (SURVEY.md Appendix A.5), e.g. "unet.down_blocks.0.resnets.0.conv1.weight". */
@@ -69,6 +84,12 @@ int mdc_weight_shape(mdc_handle* h, int i, long long* shape4_host, int* ndim_hos
 /* Re-packs one parameter (device pointer, contiguous, dtype MDC_DTYPE_*) into the library's layouts. */
 int mdc_set_weight(mdc_handle* h, const char* key, const void* dev_ptr, const long long* shape_host, int ndim,
                    int dtype);
+/* Batched form: n parameters re-packed by ONE kernel launch.  shapes4_host holds 4 entries per parameter (unused
+ * trailing dimensions ignored).  The sources have been read when the call returns. */
+int mdc_set_weights(mdc_handle* h, int n, const char* const* keys, const void* const* dev_ptrs, const long long* shapes4_host,
+                    const int* ndims_host, const int* dtypes_host);
+/* 1 when every parameter of the handle (or of the bank it shares) has been set. */
+int mdc_weights_loaded(mdc_handle* h);
 
 /* Step-invariant precomputation: DDIM scalars for `timesteps`, the time embedding of every step pushed through
  * every resnet's time_emb_proj, and the cross-attention K/V of the empty-prompt embedding ctx [1,2,cross_dim] bf16

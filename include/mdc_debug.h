@@ -18,6 +18,23 @@ int mdc_dbg_conv3x3(int NB, int H, int W, int C, int Cout, const void* x, long l
                     int dgrad, const float* bias, const float* bias_img, const void* res, long long ldr, void* out,
                     long long ldc, int iters, float* ms_out);
 
+/* Fused nearest-2x upsample + conv3x3 (dgrad = 0: x [NB,H,W,C] -> out [NB,2H,2W,Cout]) or its input gradient (dgrad = 1:
+ * x is dy [NB,2H,2W,Cout] -> out [NB,H,W,C]); w_oihw [Cout][C][3][3] fp32. */
+int mdc_dbg_upconv(int NB, int H, int W, int C, int Cout, const void* x, long long ldx, const float* w_oihw, int dgrad,
+                   const float* bias, void* out, long long ldc, int iters, float* ms_out);
+/* Self-attention as the engine plans it: head_dim 64 = the fused tcgen05 flash kernels (UNet attn1), otherwise GEMM +
+ * softmax + GEMM (VAE mid block, head_dim 512).  qkv [n,T,3*heads*dh] bf16 (q | k | v column blocks), o / dout
+ * [n,T,heads*dh], dqkv like qkv; dout = dqkv = NULL runs the forward only.  ms_out[2]: forward / backward ms per call. */
+int mdc_dbg_attention(int n, int T, int heads, int dh, const void* qkv, void* o, const void* dout, void* dqkv, int iters,
+                      float* ms_out);
+/* GroupNorm (+SiLU when silu != 0) forward and (dy != NULL) input-gradient backward on x [n,HW,C] bf16 NHWC with the
+ * engine's kernel selection: mode 0 automatic, 1 force the two-pass statistics / apply kernels (the 56-226 MB decoder
+ * tensors), 2 require the single-launch grid-barrier kernels.  acc != 0: dx += (gradient accumulation at fan-out
+ * points).  stats_out (device, optional): [n,groups,2] (mean, rstd).  ms_out[2]: forward / backward ms per call. */
+int mdc_dbg_groupnorm(int n, int HW, int C, int groups, float eps, int silu, const void* x, const float* gamma,
+                      const float* beta, void* y, const void* dy, void* dx, int acc, int mode, float* stats_out, int iters,
+                      float* ms_out);
+
 /* Tape-level: which = 0 UNet, 1 VAE decoder.  Inputs/outputs are NCHW fp32 device buffers.
  * forward: copies `in` into the tape input, runs the forward tape (step index selects the time embedding),
  * writes the tape output to `out`.  backward: seeds the output gradient with `dout`, runs the backward tape,
@@ -43,6 +60,11 @@ int mdc_dbg_read_buffer(mdc_handle* h, const char* which, float* out_dev);
 int mdc_dbg_loss(mdc_handle* h, const float* dec_nchw, float* ddec_nchw, float* loss_host, float* sgrad_host,
                  float* tgrad_host);
 int mdc_dbg_update(mdc_handle* h, const float* v_nchw, const float* dz_nchw, const float* dunet_in_nchw);
+/* Teacher forcing at any step (after mdc_begin / mdc_begin_frame): latent x and its Adam moments exp_avg / exp_avg_sq
+ * ([N,4,EH,EW] bf16, device; NULL keeps the current one), per-sample scale, shift and their fp32 Adam moments (host,
+ * 6 x N floats: scale, shift, s_m, s_v, t_m, t_v; NULL keeps them), and the step index the next mdc_run(h, 1) executes. */
+int mdc_dbg_set_state(mdc_handle* h, int step, const void* x_bf16, const void* m1_bf16, const void* m2_bf16,
+                      const float* affine6_host);
 /* In-situ timing of the dominant kernel: replays the launch sequence of one guided step (state is NOT advanced
  * meaningfully: call after mdc_begin, before/after mdc_run) with CUDA events around every tcgen05 GEMM / conv launch;
  * returns the summed kernel time (ms), the summed algorithmic FLOPs and the number of such launches. */

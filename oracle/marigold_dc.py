@@ -259,6 +259,14 @@ class OraclePipeline:
             gn = torch.linalg.norm(x.grad.reshape(N, -1), dim=1)
             x.grad *= (en / gn.clamp(min=EPSILON)).view(N, 1, 1, 1)
         x_before = x.detach().clone() if trace is not None else None
+        opt_in = None
+        if trace is not None:  # optimiser state BEFORE this step's update (teacher forcing at any step, tests only)
+            def _st(p, k):
+                s_ = optimizer.state.get(p, {})
+                return s_[k].detach().clone() if k in s_ else torch.zeros_like(p)
+            opt_in = {n_: dict(exp_avg=_st(p_, "exp_avg"), exp_avg_sq=_st(p_, "exp_avg_sq"))
+                      for n_, p_ in (("x", x), ("scales", scales), ("shifts", shifts))}
+            opt_in["scales_in"], opt_in["shifts_in"] = scales.detach().clone(), shifts.detach().clone()
         optimizer.step()
         with torch.no_grad():
             x_adam = x.detach().clone() if trace is not None else None
@@ -268,7 +276,7 @@ class OraclePipeline:
                        grad=raw_grad, s_grad=None if scales.grad is None else scales.grad.detach().clone(),
                        t_grad=None if shifts.grad is None else shifts.grad.detach().clone(),
                        x_adam=x_adam, x_out=x.detach().clone(), scales=scales.detach().clone(),
-                       shifts=shifts.detach().clone(), eps_norm=en, grad_norm=gn))
+                       shifts=shifts.detach().clone(), eps_norm=en, grad_norm=gn, opt_in=opt_in))
         return losses.detach()
 
     @torch.no_grad()

@@ -78,9 +78,11 @@ def test_first_step_teacher_forced(models, cuda):
     assert abs(sc[0].item() - st["scales"].flatten()[0].item()) < 1e-6  # first Adam step = -lr * sign(grad)
     g, og = eng.dbg_buffer("grad"), st["grad"].float()
     cos = torch.nn.functional.cosine_similarity(g.flatten(), og.flatten(), dim=0).item()
-    assert cos > 0.85, cos  # a single L1 sign flip among 100 points already costs ~0.02 of cosine
+    print(f"[measured] first step vs torch-bf16 oracle: cos {cos:.4f}")
+    assert cos > 0.97, cos  # measured 0.987 (a single L1 sign flip among 100 points costs ~0.02 of cosine)
     agree = ((eng.dbg_x_adam().float() - st["x_adam"].float()).abs() < 1e-2).float().mean().item()
-    assert agree > 0.8, agree
+    print(f"[measured] first step Adam agreement {agree:.4f}")
+    assert agree > 0.93, agree  # measured 0.966
 
 
 def test_batch_and_const_norm_and_prev_latent(models, cuda):
@@ -158,6 +160,7 @@ def test_other_configs_match_oracle(models, cuda, H, W, res, kind, max_depth):
         fr["img"], fr["sparse"], max_depth, steps=20, resolution=res)
     assert dense.shape == d16.shape and lat.shape == l16.shape and torch.isfinite(dense).all()
     diff = ((dense - d16).abs().mean() / max_depth).item()
+    print(f"[measured] {H}x{W} res {res}: mean |dense - torch-bf16| / range = {diff:.4f}")
     assert diff < 4e-2, diff
     m_ours, m_ref = mae(dense, fr["gt"], fr["holdout"]).item(), mae(d16, fr["gt"], fr["holdout"]).item()
     assert abs(m_ours - m_ref) <= 0.08 * m_ref, (m_ours, m_ref)
@@ -198,7 +201,7 @@ def test_begin_frame_sparse_normalisation(models, cuda, norm):
     """mdc_begin_frame's device-side sparse-depth normalisation (marigold_dc.py:707-756) is bit-identical to the same
     arithmetic in PyTorch, and an empty mask raises the reference's ValueError (utils.py:132-136)."""
     from helpers import build_engine
-    from depth_completion_b200 import prologue
+    import torch_reference as prologue
     from depth_completion_b200.synthetic import make_batch
 
     unet, vae, ctx, ucfg, vcfg = models

@@ -122,7 +122,7 @@ def test_encoder_prologue(cuda, H, W, res, kind):
     (MarigoldImageProcessor.preprocess + AutoencoderKL.encode(...).mode() * scaling), with torch's bf16 path as the
     yardstick; the resized / padded image itself is checked against torch's antialiased bilinear resize."""
     from helpers import build_engine, build_models, rel_l2
-    from depth_completion_b200 import prologue
+    import torch_reference as prologue
     from oracle import image_processor
 
     unet, vae, ctx, ucfg, vcfg = build_models(cuda, tiny=True)

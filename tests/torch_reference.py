@@ -1,27 +1,12 @@
-"""Per-frame prologue (once per call, not per step): input validation and sparse-depth normalisation
-(marigold_dc.py:659-756).
-
-The heavy part -- image normalise / resize / pad and the VAE *encoder* forward -- runs
-inside libmdc_b200.so (`mdc_encode`, StepEngine.encode).  `preprocess_image` and `vae_encode_mode` below are the
-same arithmetic as plain PyTorch ops over the VAE state dict; the product path does not call them, the GPU tests use
-them as the torch reference for `mdc_encode`.
+"""TEST INFRASTRUCTURE (not part of the product package): the per-frame prologue of marigold_dc.py:659-756 -- image
+normalise / resize / pad, the VAE *encoder* forward from a state dict, sparse-depth normalisation -- as plain PyTorch ops.
+The product does all of this inside libmdc_b200.so (`mdc_begin_frame`); the GPU tests use these functions as the torch
+(bf16 / fp32) reference for it.
 """
 from __future__ import annotations
 
 import torch
 import torch.nn.functional as F
-
-
-def check_image(image: torch.Tensor) -> None:
-    """The checks of MarigoldImageProcessor.preprocess that raise."""
-    if image.ndim != 4:
-        raise ValueError(f"Input image is not 4-dimensional: shape={tuple(image.shape)}")
-    if not torch.is_floating_point(image) and image.dtype != torch.uint8:
-        raise ValueError(f"Image dtype={image.dtype} is not supported.")
-    if image.shape[1] not in (1, 3):
-        raise ValueError(f"Input image is not 1- or 3-channel: {tuple(image.shape)}.")
-    if torch.is_floating_point(image) and (image.min().item() < 0.0 or image.max().item() > 1.0):
-        raise ValueError("Input image data is partially outside of the [0,1] range.")
 
 
 def preprocess_image(image: torch.Tensor, resolution: int, dtype):
