@@ -65,6 +65,12 @@ int mdc_release_workspace(mdc_handle* h) {
   });
 }
 int mdc_weights_loaded(mdc_handle* h) { return (h && h->e->weights_loaded()) ? 1 : 0; }
+int mdc_weight_is_loaded(mdc_handle* h, int i) {
+  if (!h || i < 0 || i >= static_cast<int>(h->keys.size())) return 0;
+  for (const mdc::WeightSlot* s : h->e->wmap().at(h->keys[i]))
+    if (!s->loaded) return 0;
+  return 1;
+}
 int mdc_set_weights(mdc_handle* h, int n, const char* const* keys, const void* const* dev_ptrs, const long long* shapes4_host,
                     const int* ndims_host, const int* dtypes_host) {
   return mdc::guarded([&] {

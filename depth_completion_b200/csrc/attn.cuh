@@ -100,6 +100,13 @@ inline void set_kernel_attrs_for_device() {
   gn_set_attrs();
   MDC_CUDA(cudaFuncSetAttribute(softmax_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   MDC_CUDA(cudaFuncSetAttribute(softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  // collapsed cross-attention: the backward stages three fp32 copies of its rows (<= 8 x 640 or 4 x 1280 channels)
+  MDC_CUDA(cudaFuncSetAttribute(xattn_block_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  MDC_CUDA(cudaFuncSetAttribute(xattn_block_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  MDC_CUDA(cudaFuncSetAttribute(xattn_block_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  MDC_CUDA(cudaFuncSetAttribute(xattn_block_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  MDC_CUDA(cudaFuncSetAttribute(xattn_block_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  MDC_CUDA(cudaFuncSetAttribute(xattn_block_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
 }
 
 inline void run_attention_fwd(const AttnPlan& a, cudaStream_t st) {

@@ -292,7 +292,18 @@ int mdc_dbg_upconv(int NB, int H, int W, int C, int Cout, const void* x, long lo
     Epilogue e;
     e.out = out, e.ldc = ldc, e.bias = bias;
     GemmPlan g = dgrad ? plan_upconv_bwd(NB, H, W, C, Cout, x, ldx, wpk, e) : plan_upconv_fwd(NB, H, W, C, Cout, x, ldx, wpk, e);
+    float* ws = nullptr;
+    if (g_tune().ksplit) {  // forced (> 0) or cost-model (< 0) split-K, as the engine applies it to the input gradient
+      const size_t fl = enable_splitk(g, choose_ksplit(g));
+      if (fl) MDC_CUDA(cudaMalloc(&ws, fl * 4 + 256));
+      g.p.ws = ws;
+      if (ms_out) fprintf(stderr, "[dbg] upconv ksplit = %d (tiles %d x %d, k-chunks %d)\n", g.p.ksplit, g.p.m_tiles, g.p.n_tiles, g.p.num_k_chunks);
+    }
     float ms = time_plan(g, iters, 0);
+    if (ws) {
+      MDC_CUDA(cudaDeviceSynchronize());
+      cudaFree(ws);
+    }
     if (ms_out) *ms_out = ms;
     MDC_CUDA(cudaDeviceSynchronize());
     cudaFree(wpk);
@@ -303,6 +314,11 @@ int mdc_dbg_upconv(int NB, int H, int W, int C, int Cout, const void* x, long lo
 // the engine's cost model also in the debug entry points), number of weight copies rotated in timed loops.
 int mdc_dbg_tune(int bn, int cs, int ksplit, int wcopies) {
   mdc::g_tune().bn = bn, mdc::g_tune().cs = cs, mdc::g_tune().ksplit = ksplit, mdc::g_tune().wcopies = wcopies > 0 ? wcopies : 1;
+  return 0;
+}
+// Row-shared-taps mode of the 3x3 convolution (GemmParams::rowshare): 0 automatic, 1 off, 2 on whenever legal.
+int mdc_dbg_tune_rowshare(int mode) {
+  mdc::g_tune().rowshare = mode;
   return 0;
 }
 

@@ -235,7 +235,7 @@ struct CrossAttn2Op : Op {  // attention over the 2 tokens of the empty-prompt e
                                                                                  heads, kc, vc, 0.125f, q->g, q->ld, acc);
   }
 };
-struct CrossAttnFusedOp : Op {  // LN2 + attn2 (2 constant key tokens) + to_out + residual, algebraically collapsed
+struct CrossAttnFusedOp : Op {  // LN2 + attn2 (2 constant key tokens) + to_out + residual, algebraically collapsed: ONE kernel each way
   Tensor *x, *y;
   int heads;
   const float *gamma, *beta, *At, *U, *bo;
@@ -245,24 +245,29 @@ struct CrossAttnFusedOp : Op {  // LN2 + attn2 (2 constant key tokens) + to_out 
     acc = x->grad_set;
     x->grad_set = true;
   }
-  template <int NV>
-  void run(cudaStream_t st, bool backward) {
+  // rows per CTA: enough CTAs to fill the chip on the small maps, longer reuse of At / U on the large ones
+  int rows_per_block() const {
     const long long rows = x->rows();
-    const dim3 grid(static_cast<unsigned>((rows * 32 + 255) / 256)), block(256);
-    if (!backward)
-      launch_k(xattn_fused_fwd_kernel<NV>, grid, block, 0, st, x->d, x->ld, rows, x->c, 2 * heads, gamma, beta, At, U, bo, y->d,
-               y->ld, stats);
-    else
-      launch_k(xattn_fused_bwd_kernel<NV>, grid, block, 0, st, x->d, x->ld, y->g, y->ld, rows, x->c, 2 * heads, gamma, beta, At,
-               U, stats, x->g, x->ld, static_cast<int>(acc));
+    return rows >= 1500 ? 8 : (rows >= 400 ? 4 : 2);
+  }
+  template <int RB>
+  void run(cudaStream_t st, bool backward) {
+    const int rows = static_cast<int>(x->rows()), d = x->c;
+    const dim3 grid(static_cast<unsigned>((rows + RB - 1) / RB)), block(XB_THREADS);
+    if (!backward) {
+      const size_t smem = (static_cast<size_t>(RB) * d + RB * XB_LDS) * sizeof(float);
+      launch_k(xattn_block_fwd_kernel<RB>, grid, block, smem, st, x->d, x->ld, rows, d, 2 * heads, gamma, beta, At, U, bo, y->d, y->ld, stats);
+    } else {
+      const size_t smem = (3 * static_cast<size_t>(RB) * d + 2 * RB * XB_LDS) * sizeof(float);
+      launch_k(xattn_block_bwd_kernel<RB>, grid, block, smem, st, x->d, x->ld, y->g, y->ld, rows, d, 2 * heads, gamma, beta, At, U,
+               static_cast<const float*>(stats), x->g, x->ld, static_cast<int>(acc));
+    }
   }
   void dispatch(cudaStream_t st, bool backward) {
-    switch ((x->c / 8 + 31) / 32) {
-      case 1: run<1>(st, backward); break;
-      case 2: run<2>(st, backward); break;
-      case 3: run<3>(st, backward); break;
+    switch (rows_per_block()) {
+      case 8: run<8>(st, backward); break;
       case 4: run<4>(st, backward); break;
-      default: run<5>(st, backward); break;
+      default: run<2>(st, backward); break;
     }
   }
   void fwd(cudaStream_t st) override { dispatch(st, false); }
@@ -568,6 +573,7 @@ inline void UpConvOp::plan_bwd() {
   if (x->grad_set) e.res = x->g, e.ldr = x->ld;
   x->grad_set = true;
   pb = plan_upconv_bwd(x->n, x->h, x->w, x->c, y->c, y->g, y->ld, W->wt, e);
+  E->maybe_split(pb);  // 16 taps x C/64 k-chunks on a low-resolution map: few tiles, a very long K loop
 }
 inline void UpConvOp::bwd(cudaStream_t st) {
   run_gemm(pb, st);
@@ -631,21 +637,28 @@ inline Tensor* Engine::view(Tensor* parent, int c0, int c, const std::string& na
   if (!name.empty()) named[name] = t;
   return t;
 }
-// The i-th request of this engine for `key` maps to the i-th slot of the bank (created on first use).
+// The i-th request of this engine for (`key`, kind) maps to the i-th slot of that kind the bank holds for the key
+// (created on first use).  One parameter may be held in more than one layout: an upsampler's 3x3 weight is packed as
+// four 2x2 phase kernels for an exact 2x upsample (W_UPCONV) and as a plain 3x3 (W_CONV3) for the explicit-size
+// upsampling of odd latent sizes, depending on the frame geometry of the engine that asks.
 inline WeightSlot* Engine::bank_slot(const std::string& key, WKind kind, int out, int in, bool& fresh) {
   auto& list = bank->wmap[key];
-  const size_t idx = slot_cursor[key]++;
-  fresh = idx >= list.size();
-  if (fresh) {
-    bank->slots.emplace_back();
-    WeightSlot* s = &bank->slots.back();
-    s->kind = kind, s->out = out, s->in = in;
-    list.push_back(s);
-    return s;
+  const size_t want = slot_cursor[key + "#" + std::to_string(static_cast<int>(kind))]++;
+  size_t seen = 0;
+  for (WeightSlot* s : list) {
+    if (s->kind != kind) continue;
+    if (seen++ == want) {
+      MDC_CHECK(s->out == out && s->in == in, "weight bank: '%s' was built as [%d, %d], now requested as [%d, %d]", key.c_str(), s->out,
+                s->in, out, in);
+      fresh = false;
+      return s;
+    }
   }
-  WeightSlot* s = list[idx];
-  MDC_CHECK(s->kind == kind && s->out == out && s->in == in, "weight bank: '%s' was built as kind %d [%d, %d], now requested as kind %d [%d, %d]",
-            key.c_str(), (int)s->kind, s->out, s->in, (int)kind, out, in);
+  fresh = true;
+  bank->slots.emplace_back();
+  WeightSlot* s = &bank->slots.back();
+  s->kind = kind, s->out = out, s->in = in;
+  list.push_back(s);
   return s;
 }
 inline WeightSlot* Engine::slot(const std::string& key, WKind kind, int out, int in) {
@@ -803,7 +816,8 @@ inline Tensor* Engine::transformer(Tensor* x, int heads, const std::string& key,
   h = linear(ao, d, tb + ".attn1.to_out.0", true, h);
   // --- cross attention over the 2 empty-prompt tokens (K, V precomputed in prepare())
   MDC_CHECK(d / heads == 64 && 2 * heads <= XA_MAXC, "cross-attention needs head_dim 64 and <= %d heads", XA_MAXC / 2);
-  if (getenv("MDC_XFUSE")) {  // experimental (slower than the 4-kernel path at present): LN2 + to_q + attention + to_out + residual in one kernel
+  MDC_CHECK(d % 8 == 0 && d <= 32 * 8 * LN_MAXV, "cross-attention width %d unsupported", d);
+  if (!getenv("MDC_NO_XFUSE")) {  // LN2 + to_q + 2-token attention + to_out + residual collapsed into one kernel (kernels.cuh)
     XUse u;
     u.wk = slot(tb + ".attn2.to_k.weight", W_LIN, d, cfg.cross_dim);
     u.wv = slot(tb + ".attn2.to_v.weight", W_LIN, d, cfg.cross_dim);
@@ -1196,7 +1210,12 @@ inline void Engine::finalize_plans() {
   }
   split_ws = arena.make<float>(split_ws_floats + 64);
   for (GemmPlan* g : split_plans) g->p.ws = split_ws;
-  launches_per_step += static_cast<long long>(n_split_step);
+  for (auto* ops : {&unet_ops, &dec_ops}) {  // one reduction launch per split-K GEMM
+    std::vector<const GemmPlan*> f, b;
+    for (auto& op : *ops) op->gemm_plans(f, b);
+    for (auto* g : f) launches_per_step += g->p.ksplit > 1;
+    for (auto* g : b) launches_per_step += g->p.ksplit > 1;
+  }
   launches_per_step += 12;  // tail kernels of step(): 9 of the default path + closed-form loss + dense map / dense loss (the
                             // last three return at once unless their option is set)
 }

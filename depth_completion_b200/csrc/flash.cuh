@@ -33,6 +33,7 @@ struct FlashParams {
   CUtensorMap tmS1, tmS2;  // the two streamed 64-row tiles (box 64 rows)     fwd: K, V    dkv: Q, dO   dq: K, V
   int T, heads;
   float scale;             // 1/sqrt(head_dim)
+  float lazy;              // forward: O is rescaled only when a row maximum grows by more than 2^lazy (0 = always)
   // outputs / side inputs
   bf16* out1;              // fwd: O      dkv: dK     dq: dQ
   bf16* out2;              //             dkv: dV
@@ -156,9 +157,14 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
   FaCtx c = fa_setup(smem_raw, TCOLS);
   // extra barriers for the double buffers live in the spare m2 tile slot's first bytes? no: reuse FaSmem fields:
   //   acc_full/acc_empty -> S buffer 0, o_full/o_empty -> O tile, p_full/p_empty -> P buffer 0; buffer-1 barriers below.
-  uint64_t* x_bar = reinterpret_cast<uint64_t*>(c.m2);  // [0] s1_full [1] s1_empty [2] p1_full [3] p1_empty (m2 tile unused here)
+  // [0] s1_full [1] s1_empty [2] p1_full [3] p1_empty [4] o_final (m2 tile unused here).  o_full completes once per key
+  // tile and may only be waited on by a thread that is at most one phase behind (a parity wait cannot tell phase k from
+  // phase k - 2): the softmax threads are that close inside the loop (S(i) complete implies P(i-2) V(i-2) complete), but
+  // NOT after it -- the final accumulator is therefore published on its own single-use barrier.
+  uint64_t* x_bar = reinterpret_cast<uint64_t*>(c.m2);
   if (threadIdx.x == 0) {
     ptx::mbar_init(&x_bar[0], 1), ptx::mbar_init(&x_bar[1], 4), ptx::mbar_init(&x_bar[2], 4), ptx::mbar_init(&x_bar[3], 1);
+    ptx::mbar_init(&x_bar[4], 1);
     ptx::fence_mbar_init();
   }
   __syncthreads();
@@ -205,6 +211,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
         ptx::umma_commit(&c.b->o_full);
         ptx::umma_commit(pe(b));
         ptx::umma_commit(&c.b->s_empty[s]);
+        if (i + 1 == n_iter) ptx::umma_commit(&x_bar[4]);  // every P V has completed: O is final
       }
       __syncwarp();
     }
@@ -238,7 +245,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
 #pragma unroll
       for (int j = 0; j < 64; j += 2) mx = fa_max3(mx, __uint_as_float(raw[j]), __uint_as_float(raw[j + 1]));
       mx *= c2;
-      const bool grow = mx > m + 8.f;  // always true for the first tile (m = -inf)
+      const bool grow = mx > m + p.lazy;  // always true for the first tile (m = -inf)
       const float m_new = grow ? mx : m;
       const float alpha = grow ? fa_exp2(m - m_new) : 1.f;
       if (i > 0 && __any_sync(0xffffffffu, grow)) {  // rescale the TMEM accumulator rows of this warp
@@ -278,7 +285,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
     }
     {
       uint32_t raw[64];
-      ptx::mbar_wait(&c.b->o_full, (n_iter - 1) & 1);
+      ptx::mbar_wait(&x_bar[4], 0);
       ptx::tc_fence_after();
       ptx::tmem_ld32(t_row + 128, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
       ptx::tmem_ld32(t_row + 160, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
@@ -603,6 +610,7 @@ inline FlashPlan plan_flash(int n, int T, int heads, const bf16* q, const bf16* 
   FlashParams base;
   memset(&base, 0, sizeof(base));
   base.T = T, base.heads = heads, base.scale = 0.125f, base.lse2 = lse2, base.delta = delta;
+  base.lazy = getenv("MDC_FLASH_LAZY") ? static_cast<float>(atof(getenv("MDC_FLASH_LAZY"))) : 8.f;
   f.fwd = base;
   f.fwd.tmM1 = fa_map(q, ld_qkv, T, heads, n, 128);
   f.fwd.tmM2 = f.fwd.tmM1;

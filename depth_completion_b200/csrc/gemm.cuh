@@ -81,7 +81,15 @@ struct GemmParams {
   int ksplit, kc_per_split;
   float* ws;
   long long ws_ld, ws_split_stride;
+  // Row-shared taps (conv 3x3, tile = 128 consecutive pixels of ONE image row): the three taps of a kernel row read the
+  // same pixels shifted by -1 / 0 / +1, so ONE A box of 130 pixels [64 c, 130 w] is staged per (kernel row, channel
+  // chunk) and the three taps are issued as MMAs over row-offset views of it (descriptor start + 128 B x s, matrix base
+  // offset s), each with its own B tile.  A k-step then moves 16.6 KB of activations through L2 -> SM for three taps
+  // instead of 48 KB, which is what bounds the 128-output-channel convolutions (B is only BN x 128 B per tap).
+  int rowshare;
+  int a_stage;  // bytes between A stages (GEMM_A_STAGE, or 17 KiB for a 130-row box)
 };
+constexpr int GEMM_A_STAGE_RS = 17 * 1024;  // 130 rows x 128 B, rounded up to the 1024-byte swizzle atom
 
 // work item -> (n_tile, m_tile, b0, b1); with split-K the batch slot b0 carries the split index instead.  With
 // clusters a work item is a group of `cs` consecutive m-tiles and CTA rank r takes m_tile = group * cs + r (which may
@@ -112,8 +120,9 @@ __device__ __forceinline__ void umma_gemm_body(const GemmParams& p) {
   uint8_t* spanel = smem + GEMM_HEADER0;  // npanel x 8 KiB output panels
   uint8_t* sA = spanel + p.npanel * GEMM_PANEL;
   constexpr bool pair = kPair;
-  const uint32_t b_stage = static_cast<uint32_t>(pair ? p.BN / 2 : p.BN) * 128u;
-  uint8_t* sB = sA + p.stages * GEMM_A_STAGE;
+  const uint32_t b_tile = static_cast<uint32_t>(pair ? p.BN / 2 : p.BN) * 128u;  // one B tile (one tap)
+  const uint32_t b_stage = p.rowshare ? 3u * b_tile : b_tile;
+  uint8_t* sB = sA + p.stages * p.a_stage;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -161,7 +170,8 @@ __device__ __forceinline__ void umma_gemm_body(const GemmParams& p) {
     uint32_t phase = 0;
     const int bn_slice = p.BN / p.cs;                       // rows of the B tile this CTA loads (and multicasts)
     const uint32_t b_slice = static_cast<uint32_t>(bn_slice) * 128u;
-    const uint32_t tx_bytes = pair ? 2u * (p.bytesA + b_slice) : p.bytesA + p.bytesB;
+    const uint32_t ntap_b = p.rowshare ? 3u : 1u;
+    const uint32_t tx_bytes = pair ? 2u * (p.bytesA + ntap_b * b_slice) : p.bytesA + ntap_b * p.bytesB;
     const uint16_t mc_mask = static_cast<uint16_t>((1u << p.cs) - 1);
     const uint32_t full_leader = pair ? ptx::mapa_u32(&full_bar[0], 0) : 0u;  // leader's full barriers (cluster address)
     // operand loads: plain / pair (bytes complete on the leader's barrier) / multicast B
@@ -206,10 +216,15 @@ __device__ __forceinline__ void umma_gemm_body(const GemmParams& p) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         if (leader) {
           if (!pair || rank == 0) ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
-          uint8_t* a_dst = sA + stage * GEMM_A_STAGE;
+          uint8_t* a_dst = sA + stage * p.a_stage;
           uint8_t* b_dst = sB + stage * b_stage;
           const int k0 = kc * GEMM_BK;
-          if (p.conv == 1) {
+          if (p.rowshare) {  // `tap` counts kernel rows here: one 130-pixel A box, three B tiles
+            load_a(&p.tmA, stage, a_dst, cc * GEMM_BK, w0 - 1, h0 + tap - 1, img);
+#pragma unroll
+            for (int sx = 0; sx < 3; ++sx)
+              load_b(stage, b_dst + sx * b_tile, ((tap * 3 + sx) * p.chunks_per_tap + cc) * GEMM_BK, n0, 0, 0);
+          } else if (p.conv == 1) {
             const int r = (p.taps_w == 3) ? (tap >= 6 ? 2 : (tap >= 3 ? 1 : 0)) : (tap >> 1);
             const int sx = tap - r * p.taps_w;
             load_a(&p.tmA, stage, a_dst, cc * GEMM_BK, w0 + sx + p.off_w0 + pb, h0 + r + p.off_h0 + pa, img);
@@ -257,7 +272,7 @@ __device__ __forceinline__ void umma_gemm_body(const GemmParams& p) {
     const uint64_t a_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sA), p.a_mn ? 8192u : 16u, 1024);
     const uint64_t b_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sB), p.b_mn ? 8192u : 16u, 1024);
     const uint32_t a_kinc = (p.a_mn ? 2048u : 32u) >> 4, b_kinc = (p.b_mn ? 2048u : 32u) >> 4;
-    const uint32_t a_sinc = GEMM_A_STAGE >> 4, b_sinc = b_stage >> 4;
+    const uint32_t a_sinc = static_cast<uint32_t>(p.a_stage) >> 4, b_sinc = b_stage >> 4;
     const uint32_t idesc = p.idesc;
     const uint16_t mc_mask = static_cast<uint16_t>((1u << p.cs) - 1);
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
@@ -276,7 +291,23 @@ __device__ __forceinline__ void umma_gemm_body(const GemmParams& p) {
         if (leader) {
           const uint64_t ad = a_desc0 + static_cast<uint64_t>(stage * a_sinc);
           const uint64_t bd = b_desc0 + static_cast<uint64_t>(stage * b_sinc);
-          if (pair) {
+          if (p.rowshare) {
+#pragma unroll
+            for (uint32_t sx = 0; sx < 3; ++sx) {
+              // view of the A box shifted by sx pixel rows (128 B each): start address + 8, matrix base offset sx
+              const uint64_t as = ad + (sx << 3) + (static_cast<uint64_t>(sx) << 49);
+              const uint64_t bs = bd + sx * (b_tile >> 4);
+#pragma unroll
+              for (uint32_t kk = 0; kk < 4; ++kk) {
+                const uint32_t accu = (kc != 0 || sx != 0 || kk != 0) ? 1u : 0u;
+                if (pair)
+                  ptx::umma_bf16_pair(d_tmem, as + kk * a_kinc, bs + kk * b_kinc, idesc, accu);
+                else
+                  ptx::umma_bf16(d_tmem, as + kk * a_kinc, bs + kk * b_kinc, idesc, accu);
+              }
+            }
+            if (pair) ptx::umma_commit_pair(&empty_bar[stage], mc_mask);
+          } else if (pair) {
             ptx::umma_bf16_pair(d_tmem, ad, bd, idesc, kc != 0 ? 1u : 0u);
             ptx::umma_bf16_pair(d_tmem, ad + a_kinc, bd + b_kinc, idesc, 1u);
             ptx::umma_bf16_pair(d_tmem, ad + 2 * a_kinc, bd + 2 * b_kinc, idesc, 1u);
@@ -690,7 +721,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int ksplit, l
 
 // Test / tuning overrides (set through mdc_dbg_tune only; 0 = automatic).
 struct GemmTune {
-  int bn = 0, cs = 0, ksplit = 0, wcopies = 1;
+  int bn = 0, cs = 0, ksplit = 0, wcopies = 1, rowshare = 0;
 };
 inline GemmTune& g_tune() {
   static GemmTune t;
@@ -750,14 +781,15 @@ inline void decide_cluster(GemmParams& p) {
 }
 inline void finish_plan(GemmPlan& g) {
   GemmParams& p = g.p;
-  const int b_stage = (p.pair ? p.BN / 2 : p.BN) * 128;
+  const int b_stage = (p.pair ? p.BN / 2 : p.BN) * 128 * (p.rowshare ? 3 : 1);
+  p.a_stage = p.rowshare ? GEMM_A_STAGE_RS : GEMM_A_STAGE;
   auto stages_for = [&](int npanel) {
-    return std::min((GEMM_SMEM_BUDGET - GEMM_HEADER0 - npanel * GEMM_PANEL - 1024) / (GEMM_A_STAGE + b_stage), GEMM_MAX_STAGES);
+    return std::min((GEMM_SMEM_BUDGET - GEMM_HEADER0 - npanel * GEMM_PANEL - 1024) / (p.a_stage + b_stage), GEMM_MAX_STAGES);
   };
   p.npanel = (stages_for(4) == stages_for(2)) ? 4 : 2;  // never trade a pipeline stage for store depth
   const int stages = std::max(2, stages_for(p.npanel));
   p.stages = stages;
-  g.smem = GEMM_HEADER0 + p.npanel * GEMM_PANEL + 1024 + stages * (GEMM_A_STAGE + b_stage);
+  g.smem = GEMM_HEADER0 + p.npanel * GEMM_PANEL + 1024 + stages * (p.a_stage + b_stage);
   p.idesc = ptx::make_idesc_bf16(p.pair ? 2 * GEMM_BM : GEMM_BM, p.BN, p.a_mn, p.b_mn);
   if (p.cs < 1) p.cs = 1, p.pair = 0;  // set by the planners via decide_cluster() before the B map was built
   long long total = 1LL * ((p.m_tiles + p.cs - 1) / p.cs) * p.n_tiles * (p.ksplit > 1 ? p.ksplit : p.nb0) * p.nb1;
@@ -877,10 +909,18 @@ inline GemmPlan plan_conv3x3(int NB, int H, int W, int C, int Cout, const void* 
   p.num_k_chunks = 9 * p.chunks_per_tap;
   p.bytesA = 64u * p.BW * p.BH * 2u;
   p.bytesB = p.BN * 128;
+  // row-shared taps: full-width row tiles, narrow N (the A operand dominates the L2 -> SM traffic), many tiles
+  static const bool no_rs = getenv("MDC_NO_ROWSHARE") != nullptr;
+  const int rs_tune = g_tune().rowshare;  // 0 auto, 1 off, 2 force when legal
+  p.rowshare = (p.BW == 128 && p.BH == 1 && rs_tune != 1 && ((!no_rs && p.BN <= 128 && p.m_tiles >= 1024) || rs_tune == 2)) ? 1 : 0;
+  if (p.rowshare) {
+    p.num_k_chunks = 3 * p.chunks_per_tap;  // one pipeline stage = one kernel row x one channel chunk = three taps
+    p.bytesA = 64u * 130u * 2u;
+  }
   {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
     uint64_t str[3] = {(uint64_t)ldx, (uint64_t)ldx * W, (uint64_t)ldx * W * H};
-    uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+    uint32_t box[4] = {64, (uint32_t)(p.rowshare ? 130 : p.BW), (uint32_t)p.BH, 1};
     p.tmA = make_tmap_bf16(x, dims, str, box);
   }
   {
@@ -1075,7 +1115,7 @@ inline void launch_gemm_kernel(const GemmPlan& g, cudaStream_t st) {
 // Decide on split-K for a finished plan: few output tiles, long K loop.  `ws` must hold ws_floats(plan) floats.
 inline int choose_ksplit(const GemmPlan& g) {
   const GemmParams& p = g.p;
-  if (p.nb0 != 1 || p.nb1 != 1 || p.bias_img || p.out_f32 || p.conv == 2 || p.nphase > 1 || p.relu) return 1;
+  if (p.nb0 != 1 || p.nb1 != 1 || p.bias_img || p.out_f32 || p.nphase > 1 || p.relu) return 1;
   if (g_tune().ksplit > 0) return g_tune().ksplit;
   const int tiles = ((p.m_tiles + p.cs - 1) / p.cs) * p.cs * p.n_tiles, nk = p.num_k_chunks, sms = (g_num_sms() / p.cs) * p.cs;
   static const int max_tiles = getenv("MDC_SPLITK_MAXTILES") ? atoi(getenv("MDC_SPLITK_MAXTILES")) : 100;

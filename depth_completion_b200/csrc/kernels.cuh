@@ -1191,6 +1191,256 @@ __global__ void xattn_fused_bwd_kernel(const bf16* __restrict__ h, long long ldh
   }
 }
 
+// ---- block-parallel form (the one the engine uses).  The one-warp-per-token kernels above serialise 2H dot products of
+// length d behind L2-latency loads, which is slow exactly where tokens are few (9x12 ... 18x24 maps, d = 1280, 2H = 40).
+// Here a 256-thread CTA owns RB tokens and every phase is spread over all of its warps:
+//   A  LayerNorm of the RB rows (warp per row)                              -> shared memory
+//   B  scores S[r][c] = n2[r] . At[c]: warp per column c, At[c] held in registers across the rows
+//   C  pairwise softmax over the 2 key tokens of each head (thread per (row, head))
+//   D  out[r] = h[r] + bo + sum_c P[r][c] U[c]: thread per (row, 8-channel vector)
+// Backward recomputes n2 / S / P from h and the saved LayerNorm statistics, then
+//   dP = dy U^T (as B),  dS = softmax-bwd(P, dP),  dn = dS At (as D),  dh = dy + LayerNorm-bwd(dn).
+constexpr int XB_THREADS = 256;
+constexpr int XB_LDS = XA_MAXC + 1;  // row stride of the small score arrays in shared memory
+
+template <int RB>
+__global__ void __launch_bounds__(XB_THREADS) xattn_block_fwd_kernel(const bf16* __restrict__ h, long long ldh, int rows, int d, int C,
+                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                     const float* __restrict__ At, const float* __restrict__ U,
+                                                                     const float* __restrict__ bo, bf16* __restrict__ out,
+                                                                     long long ldo, float* __restrict__ stats) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  extern __shared__ __align__(16) float xb_smem[];
+  float* n2s = xb_smem;            // [RB][d]
+  float* Ss = xb_smem + RB * d;    // [RB][XB_LDS]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NW = XB_THREADS / 32;
+  const int row0 = blockIdx.x * RB, nv = d >> 3;
+  // ---- A: LayerNorm (eps 1e-5), rounded to bf16 like the reference's bf16 LayerNorm output
+  for (int r = warp; r < RB; r += NW) {
+    const int row = row0 + r;
+    float f[LN_MAXV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nv && row < rows) {
+        bf8_to_f(*reinterpret_cast<const BF8*>(h + 1LL * row * ldh + v * 8), f[k]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sum += f[k][i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[k][i] = 0.f;
+      }
+    }
+    const float mean = warp_sum(sum) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nv) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float t = f[k][i] - mean;
+          q += t * t;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
+    if (lane == 0 && row < rows) stats[2LL * row] = mean, stats[2LL * row + 1] = rstd;
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nv) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+        const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = bf16r((f[k][i] - mean) * rstd * ga[i] + be[i]);
+        float4* dst = reinterpret_cast<float4*>(n2s + r * d + v * 8);
+        dst[0] = make_float4(o[0], o[1], o[2], o[3]), dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- B: scores; lane owns the float4 chunks lane, lane + 32, ... of a row (conflict-free shared-memory reads)
+  constexpr int K4 = LN_MAXV * 2;
+  const int nq = d >> 2;
+  for (int c = warp; c < C; c += NW) {
+    float4 a[K4];
+#pragma unroll
+    for (int k = 0; k < K4; ++k) {
+      const int qd = lane + 32 * k;
+      if (qd < nq) a[k] = __ldg(reinterpret_cast<const float4*>(At + 1LL * c * d) + qd);
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int k = 0; k < K4; ++k) {
+        const int qd = lane + 32 * k;
+        if (qd < nq) {
+          const float4 x = reinterpret_cast<const float4*>(n2s + r * d)[qd];
+          sacc += x.x * a[k].x + x.y * a[k].y + x.z * a[k].z + x.w * a[k].w;
+        }
+      }
+      sacc = warp_sum(sacc);
+      if (lane == 0) Ss[r * XB_LDS + c] = sacc;
+    }
+  }
+  __syncthreads();
+  // ---- C: softmax over the two key tokens of each head
+  for (int t = threadIdx.x; t < RB * (C >> 1); t += XB_THREADS) {
+    const int r = t / (C >> 1), hd = t % (C >> 1);
+    const float s0 = Ss[r * XB_LDS + 2 * hd], s1 = Ss[r * XB_LDS + 2 * hd + 1];
+    const float m = fmaxf(s0, s1), e0 = __expf(s0 - m), e1 = __expf(s1 - m), inv = 1.f / (e0 + e1);
+    Ss[r * XB_LDS + 2 * hd] = e0 * inv, Ss[r * XB_LDS + 2 * hd + 1] = e1 * inv;
+  }
+  __syncthreads();
+  // ---- D: output rows
+  for (int item = threadIdx.x; item < RB * nv; item += XB_THREADS) {
+    const int r = item / nv, v = item % nv, row = row0 + r;
+    if (row >= rows) continue;
+    float o[8];
+    bf8_to_f(*reinterpret_cast<const BF8*>(h + 1LL * row * ldh + v * 8), o);
+    {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bo + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bo + v * 8 + 4));
+      o[0] += b0.x, o[1] += b0.y, o[2] += b0.z, o[3] += b0.w, o[4] += b1.x, o[5] += b1.y, o[6] += b1.z, o[7] += b1.w;
+    }
+    for (int c = 0; c < C; ++c) {
+      const float pc = Ss[r * XB_LDS + c];
+      const float4 u0 = __ldg(reinterpret_cast<const float4*>(U + 1LL * c * d + v * 8)), u1 = __ldg(reinterpret_cast<const float4*>(U + 1LL * c * d + v * 8 + 4));
+      o[0] += pc * u0.x, o[1] += pc * u0.y, o[2] += pc * u0.z, o[3] += pc * u0.w;
+      o[4] += pc * u1.x, o[5] += pc * u1.y, o[6] += pc * u1.z, o[7] += pc * u1.w;
+    }
+    *reinterpret_cast<BF8*>(out + 1LL * row * ldo + v * 8) = f_to_bf8(o);
+  }
+}
+
+template <int RB>
+__global__ void __launch_bounds__(XB_THREADS) xattn_block_bwd_kernel(const bf16* __restrict__ h, long long ldh, const bf16* __restrict__ dy,
+                                                                     long long lddy, int rows, int d, int C,
+                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                     const float* __restrict__ At, const float* __restrict__ U,
+                                                                     const float* __restrict__ stats, bf16* __restrict__ dh,
+                                                                     long long lddh, int acc) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  extern __shared__ __align__(16) float xb_smem[];
+  float* xhs = xb_smem;                 // [RB][d] normalised rows
+  float* gs = xhs + RB * d;             // [RB][d] dy
+  float* n2s = gs + RB * d;             // [RB][d] bf16(xh gamma + beta); later reused for dn * gamma
+  float* Ss = n2s + RB * d;             // [RB][XB_LDS] scores -> dS
+  float* dPs = Ss + RB * XB_LDS;        // [RB][XB_LDS]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NW = XB_THREADS / 32;
+  constexpr int K4 = LN_MAXV * 2;       // float4 chunks per lane (d <= 1280)
+  const int row0 = blockIdx.x * RB, nv = d >> 3, nq = d >> 2;
+  // ---- A: stage xh, n2 and dy
+  for (int item = threadIdx.x; item < RB * nv; item += XB_THREADS) {
+    const int r = item / nv, v = item % nv, row = row0 + r;
+    float x[8], g[8], n2[8];
+    if (row < rows) {
+      const float mean = stats[2LL * row], rstd = stats[2LL * row + 1];
+      bf8_to_f(*reinterpret_cast<const BF8*>(h + 1LL * row * ldh + v * 8), x);
+      bf8_to_f(*reinterpret_cast<const BF8*>(dy + 1LL * row * lddy + v * 8), g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        x[i] = (x[i] - mean) * rstd;
+        n2[i] = bf16r(x[i] * __ldg(gamma + v * 8 + i) + __ldg(beta + v * 8 + i));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = g[i] = n2[i] = 0.f;
+    }
+    float4* dx = reinterpret_cast<float4*>(xhs + r * d + v * 8);
+    float4* dg = reinterpret_cast<float4*>(gs + r * d + v * 8);
+    float4* dn = reinterpret_cast<float4*>(n2s + r * d + v * 8);
+    dx[0] = make_float4(x[0], x[1], x[2], x[3]), dx[1] = make_float4(x[4], x[5], x[6], x[7]);
+    dg[0] = make_float4(g[0], g[1], g[2], g[3]), dg[1] = make_float4(g[4], g[5], g[6], g[7]);
+    dn[0] = make_float4(n2[0], n2[1], n2[2], n2[3]), dn[1] = make_float4(n2[4], n2[5], n2[6], n2[7]);
+  }
+  __syncthreads();
+  // ---- B: S = n2 At^T and dP = dy U^T; lane owns the float4 chunks lane, lane + 32, ... of a row (conflict-free)
+  for (int c = warp; c < C; c += NW) {
+    float4 a[K4], u[K4];
+#pragma unroll
+    for (int k = 0; k < K4; ++k) {
+      const int qd = lane + 32 * k;
+      if (qd < nq) {
+        a[k] = __ldg(reinterpret_cast<const float4*>(At + 1LL * c * d) + qd);
+        u[k] = __ldg(reinterpret_cast<const float4*>(U + 1LL * c * d) + qd);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      float sacc = 0.f, pacc = 0.f;
+#pragma unroll
+      for (int k = 0; k < K4; ++k) {
+        const int qd = lane + 32 * k;
+        if (qd < nq) {
+          const float4 x = reinterpret_cast<const float4*>(n2s + r * d)[qd], g = reinterpret_cast<const float4*>(gs + r * d)[qd];
+          sacc += x.x * a[k].x + x.y * a[k].y + x.z * a[k].z + x.w * a[k].w;
+          pacc += g.x * u[k].x + g.y * u[k].y + g.z * u[k].z + g.w * u[k].w;
+        }
+      }
+      sacc = warp_sum(sacc), pacc = warp_sum(pacc);
+      if (lane == 0) Ss[r * XB_LDS + c] = sacc, dPs[r * XB_LDS + c] = pacc;
+    }
+  }
+  __syncthreads();
+  // ---- C: dS of the pairwise softmax (in place over S)
+  for (int t = threadIdx.x; t < RB * (C >> 1); t += XB_THREADS) {
+    const int r = t / (C >> 1), hd = t % (C >> 1);
+    const float s0 = Ss[r * XB_LDS + 2 * hd], s1 = Ss[r * XB_LDS + 2 * hd + 1];
+    const float dp0 = dPs[r * XB_LDS + 2 * hd], dp1 = dPs[r * XB_LDS + 2 * hd + 1];
+    const float m = fmaxf(s0, s1), e0 = __expf(s0 - m), e1 = __expf(s1 - m), inv = 1.f / (e0 + e1);
+    const float p0 = e0 * inv, p1 = e1 * inv, dot = p0 * dp0 + p1 * dp1;
+    Ss[r * XB_LDS + 2 * hd] = p0 * (dp0 - dot), Ss[r * XB_LDS + 2 * hd + 1] = p1 * (dp1 - dot);
+  }
+  __syncthreads();
+  // ---- D: dn gamma = (dS At) gamma, over n2's storage (dead by now)
+  for (int item = threadIdx.x; item < RB * nq; item += XB_THREADS) {
+    const int r = item / nq, qd = item % nq;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < C; ++c) {
+      const float ds = Ss[r * XB_LDS + c];
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(At + 1LL * c * d) + qd);
+      o.x += ds * a0.x, o.y += ds * a0.y, o.z += ds * a0.z, o.w += ds * a0.w;
+    }
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + qd);
+    o.x *= gm.x, o.y *= gm.y, o.z *= gm.z, o.w *= gm.w;
+    reinterpret_cast<float4*>(n2s + r * d)[qd] = o;
+  }
+  __syncthreads();
+  // ---- E: LayerNorm backward per row, plus the residual path (dh = dy + ...)
+  for (int r = warp; r < RB; r += NW) {
+    const int row = row0 + r;
+    if (row >= rows) continue;
+    const float rstd = stats[2LL * row + 1];
+    float a = 0.f, b = 0.f;
+    for (int e = lane; e < d; e += 32) {
+      const float t = n2s[r * d + e];
+      a += t, b += t * xhs[r * d + e];
+    }
+    a = warp_sum(a) / d, b = warp_sum(b) / d;
+    for (int qd = lane; qd < nq; qd += 32) {  // 4 channels per lane and pass: 8-byte bf16 stores
+      const float4 g = reinterpret_cast<const float4*>(gs + r * d)[qd], dn = reinterpret_cast<const float4*>(n2s + r * d)[qd];
+      const float4 xh = reinterpret_cast<const float4*>(xhs + r * d)[qd];
+      float4 o = make_float4(g.x + rstd * (dn.x - a - xh.x * b), g.y + rstd * (dn.y - a - xh.y * b), g.z + rstd * (dn.z - a - xh.z * b),
+                             g.w + rstd * (dn.w - a - xh.w * b));
+      bf16* dst = dh + 1LL * row * lddh + qd * 4;
+      if (acc) {
+        const float4 old = ld_bf16x4(dst);
+        o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
+      }
+      st_bf16x4(dst, o.x, o.y, o.z, o.w);
+    }
+  }
+}
+
 // prepare-time: At[h*2+j][i] = scale * sum_r Wq[h*64+r][i] * kc[j][h*64+r];  U[h*2+j][o] = sum_r Wo[o][h*64+r] * vc[j][h*64+r]
 __global__ void xattn_collapse_kernel(const bf16* __restrict__ Wq, long long ldq, const bf16* __restrict__ Wo, long long ldwo,
                                       const float* __restrict__ kc, const float* __restrict__ vc, int d, int heads,

@@ -79,6 +79,11 @@ def tune(bn=0, cs=0, ksplit=0, wcopies=1):
     check(lib().mdc_dbg_tune(C.c_int(bn), C.c_int(cs), C.c_int(ksplit), C.c_int(wcopies)))
 
 
+def tune_rowshare(mode=0):
+    """0 automatic, 1 off, 2 force the row-shared-taps convolution mode wherever legal (mdc_dbg_tune_rowshare)."""
+    check(lib().mdc_dbg_tune_rowshare(C.c_int(mode)))
+
+
 def attention(qkv, heads, dout=None, iters=0):
     """Self-attention as the engine plans it (mdc_dbg_attention): head_dim 64 runs the fused tcgen05 flash kernels, other
     head dims GEMM + softmax + GEMM.  qkv: [n, T, 3 * heads * dh] bf16 (q | k | v).  Returns (o, dqkv or None, (ms_fwd,

@@ -42,6 +42,7 @@ def _declare(l):
                                   C.POINTER(C.c_int), C.POINTER(C.c_int)]
     l.mdc_weights_loaded.argtypes = [C.c_void_p]
     l.mdc_release_workspace.argtypes = [C.c_void_p]
+    l.mdc_weight_is_loaded.argtypes = [C.c_void_p, C.c_int]
     l.mdc_destroy.argtypes = [C.c_void_p]
     l.mdc_destroy.restype = None
     l.mdc_num_weights.argtypes = [C.c_void_p]
@@ -173,12 +174,15 @@ class StepEngine:
     def weights_loaded(self) -> bool:
         return bool(self.lib.mdc_weights_loaded(self._h))
 
-    def load_weights(self, unet_sd: dict, vae_sd: dict):
+    def load_weights(self, unet_sd: dict, vae_sd: dict, only_missing: bool = False):
         """Hands every parameter the tapes need to mdc_set_weights in ONE call (keys: 'unet.' / 'vae.' + diffusers name);
-        the library re-packs all of them with a single kernel launch."""
+        the library re-packs all of them with a single kernel launch.  only_missing: just the parameters some layout of
+        which is not packed yet (an engine sharing another's weight bank)."""
         self._on_stream()
         missing, keys, tensors = [], [], []
-        for key in self.weight_keys():
+        for i, key in enumerate(self.weight_keys()):
+            if only_missing and self.lib.mdc_weight_is_loaded(self._h, i):
+                continue
             prefix, name = key.split(".", 1)
             sd = unet_sd if prefix == "unet" else vae_sd
             if name not in sd:

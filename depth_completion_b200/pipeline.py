@@ -216,7 +216,7 @@ class MarigoldDepthCompletionPipeline:
             eng = StepEngine(self.unet_cfg, self.vae_cfg, N, H, W, resolution, steps, self.device, share_weights_with=donor)
             if not eng.weights_loaded():
                 usd, vsd, _ = self._state_dicts()
-                eng.load_weights(usd, vsd)
+                eng.load_weights(usd, vsd, only_missing=donor is not None)
             ac, ts = ddim.tables_from_scheduler(self.scheduler, steps)
             eng.prepare(self._empty_embedding(), ac, ts)
         self._engines[key] = eng  # most recently used last

@@ -88,8 +88,11 @@ int mdc_set_weight(mdc_handle* h, const char* key, const void* dev_ptr, const lo
  * trailing dimensions ignored).  The sources have been read when the call returns. */
 int mdc_set_weights(mdc_handle* h, int n, const char* const* keys, const void* const* dev_ptrs, const long long* shapes4_host,
                     const int* ndims_host, const int* dtypes_host);
-/* 1 when every parameter of the handle (or of the bank it shares) has been set. */
+/* 1 when every parameter of the handle (or of the bank it shares) has been set; mdc_weight_is_loaded: parameter i in
+ * every layout the sharing handles need (a handle with another frame geometry may add a layout of an already loaded
+ * parameter, e.g. the plain 3x3 form of an upsampler weight for odd latent sizes: only those need setting again). */
 int mdc_weights_loaded(mdc_handle* h);
+int mdc_weight_is_loaded(mdc_handle* h, int i);
 
 /* Step-invariant precomputation: DDIM scalars for `timesteps`, the time embedding of every step pushed through
  * every resnet's time_emb_proj, and the cross-attention K/V of the empty-prompt embedding ctx [1,2,cross_dim] bf16

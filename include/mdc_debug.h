@@ -81,6 +81,9 @@ int mdc_dbg_frame_state(mdc_handle* h, float* guide_dev, unsigned char* mask_dev
  * split-K factor (> 0 forced, < 0 = the engine's cost model also in mdc_dbg_conv3x3), and the number of weight copies
  * mdc_dbg_conv3x3 rotates through in its timed loop (so weights stream from HBM as in the real step). */
 int mdc_dbg_tune(int bn, int cs, int ksplit, int wcopies);
+/* Row-shared-taps mode of the 3x3 convolution (one 130-pixel A box per kernel row instead of one box per tap):
+ * 0 automatic (wide images, <= 128 output channels per tile), 1 off, 2 on whenever the tile shape allows it. */
+int mdc_dbg_tune_rowshare(int mode);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,7 @@ def _oracle_step_from(o, st, t, state, lr=(0.05, 0.005)):
             opt.state[p] = dict(step=torch.tensor(float(state["idx"])), exp_avg=state["opt_in"][name]["exp_avg"].to(p.dtype).clone(),
                                 exp_avg_sq=state["opt_in"][name]["exp_avg_sq"].to(p.dtype).clone())
     rec = []
+    o.scheduler.set_timesteps(50, device=dev)
     o.guided_step(st, t, x, scales, shifts, opt, rec.append, state["idx"], dict(loss_funcs=("l1", "l2"), kld=False))
     return rec[0]
 

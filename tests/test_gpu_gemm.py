@@ -100,3 +100,55 @@ def test_conv3x3_cluster_and_splitk_modes(cuda, H, W, C, Cout, cs, ksplit):
         debug.tune()
     err = _rel_err(out, ref)
     assert err < 2 ** -7, f"conv rel err {err} (cs={cs}, ksplit={ksplit})"
+
+
+@pytest.mark.parametrize("NB,H,W,C,Cout", [(1, 6, 256, 64, 128), (2, 5, 300, 128, 128), (1, 9, 128, 256, 64), (1, 4, 517, 192, 96),
+                                           (1, 3, 384, 128, 320)])  # the last one: BN > 128, forced anyway
+@pytest.mark.parametrize("dgrad", [False, True])
+def test_conv3x3_rowshare(cuda, NB, H, W, C, Cout, dgrad):
+    """Row-shared-taps mode (GemmParams::rowshare): one 130-pixel activation box per kernel row, the three taps as MMAs
+    over row-offset views of it (matrix base offset 0 / 1 / 2).  Same answer as the tap-by-tap mode and as torch fp32,
+    including the zero padding at both image borders and partial tiles (W not a multiple of 128)."""
+    from depth_completion_b200 import debug
+
+    g = torch.Generator(device="cuda").manual_seed(W * 13 + C)
+    w = torch.randn(Cout, C, 3, 3, device=cuda, generator=g) * (1.0 / (3 * C ** 0.5))
+    wq = w.bfloat16().float()
+    try:
+        debug.tune_rowshare(2)
+        if not dgrad:
+            x = torch.randn(NB, C, H, W, device=cuda, generator=g).bfloat16()
+            bias = torch.randn(Cout, device=cuda, generator=g)
+            res = torch.randn(NB, H, W, Cout, device=cuda, generator=g).bfloat16()
+            ref = torch.nn.functional.conv2d(x.float(), wq, bias, padding=1).permute(0, 2, 3, 1) + res.float()
+            out, _ = debug.conv3x3(x.permute(0, 2, 3, 1).contiguous(), w, bias=bias, res=res)
+        else:
+            dy = torch.randn(NB, Cout, H, W, device=cuda, generator=g).bfloat16()
+            ref = torch.nn.grad.conv2d_input((NB, C, H, W), wq, dy.float(), padding=1).permute(0, 2, 3, 1)
+            out, _ = debug.conv3x3(dy.permute(0, 2, 3, 1).contiguous(), w, dgrad=True)
+        torch.cuda.synchronize()
+    finally:
+        debug.tune_rowshare(0)
+    err = _rel_err(out, ref)
+    assert err < 2 ** -7, f"rowshare conv rel err {err}"
+
+
+def test_conv3x3_rowshare_speed(cuda):
+    """The decoder's 128-channel convolutions at 576x768 (14 launches per guided step): time with and without the mode."""
+    from depth_completion_b200 import debug
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    w = torch.randn(128, 128, 3, 3, device=cuda, generator=g) * 0.03
+    x = torch.randn(1, 576, 768, 128, device=cuda, generator=g).bfloat16()
+    out = {}
+    try:
+        for mode in (1, 2):
+            debug.tune_rowshare(mode)
+            o, ms = debug.conv3x3(x, w, iters=20)
+            out[mode] = (o.float().clone(), ms)
+    finally:
+        debug.tune_rowshare(0)
+    gf = 2.0 * 576 * 768 * 9 * 128 * 128 / 1e9
+    print(f"[measured] conv 128->128 @576x768: tap-by-tap {out[1][1] * 1e3:.1f} us ({gf / out[1][1]:.0f} TF/s), "
+          f"row-shared {out[2][1] * 1e3:.1f} us ({gf / out[2][1]:.0f} TF/s)")
+    assert torch.equal(out[1][0], out[2][0]) or (out[1][0] - out[2][0]).abs().max().item() < 2 ** -6

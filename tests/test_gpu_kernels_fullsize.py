@@ -161,3 +161,25 @@ def test_fused_upsample_conv_fullsize(cuda, NB, H, W, C):
     torch.cuda.synchronize()
     assert rel_l2(din, dref) < 4e-3
     assert ((din.float() - dref).abs().max() / dref.abs().max()).item() < 2 ** -6
+
+
+@pytest.mark.parametrize("H,W,C,ksplit", [(9, 12, 1280, -1), (18, 24, 1280, -1), (9, 12, 1280, 7)])
+def test_fused_upsample_conv_dgrad_splitk(cuda, H, W, C, ksplit):
+    """The UNet's upsamplers at 9x12 / 18x24: one or four output tiles and 320 k-chunks, so the input gradient runs
+    split-K (cost model: ksplit = -1) -- round 1 ran these two launches unsplit at 100-118 us each."""
+    from depth_completion_b200 import debug
+
+    g = torch.Generator(device=cuda).manual_seed(H + C)
+    w = torch.randn(C, C, 3, 3, device=cuda, generator=g) * (1.0 / (3 * C ** 0.5))
+    dy = torch.randn(1, C, 2 * H, 2 * W, device=cuda, generator=g).bfloat16()
+    xr = torch.zeros(1, C, H, W, device=cuda, requires_grad=True)
+    F.conv2d(F.interpolate(xr, scale_factor=2.0, mode="nearest"), w.bfloat16().float(), None, padding=1).backward(dy.float())
+    dref = xr.grad.permute(0, 2, 3, 1)
+    try:
+        debug.tune(ksplit=ksplit)
+        din, ms = debug.upconv(dy.permute(0, 2, 3, 1).contiguous(), w, dgrad=True, iters=5)
+        torch.cuda.synchronize()
+    finally:
+        debug.tune()
+    print(f"[measured] upconv dgrad {C}@{H}x{W} ksplit {ksplit}: {ms * 1e3:.1f} us")
+    assert rel_l2(din, dref) < 4e-3
