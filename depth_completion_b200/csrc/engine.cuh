@@ -61,6 +61,8 @@ struct Tensor {
   bool is_view = false;   // channel slice of a concat buffer: its gradient must stay inside the parent's
   bool relu_out = false;  // produced by a conv + ReLU epilogue: its gradient is masked by (value > 0) once complete
   bool mask_owned = false;  // ... by the backward of its first forward consumer (the last one to contribute)
+  struct GemmPlan* producer = nullptr;  // forward plan of the conv that writes this tensor (GroupNorm statistics in its epilogue)
+  bool producer_gn = false;             // ... already claimed by a GroupNorm
   std::string name;
   long long rows() const { return 1LL * n * h * w; }
 };
@@ -157,14 +159,14 @@ struct GroupNormOp : Op {
   float* stats;
   GNPlan plan;          // two-pass kernels, or the single-launch variants when the tensor is small enough (norm.cuh)
   bool acc = false;
-  bool have_stats = false;  // the producing GEMM's epilogue already writes this op's statistics (two-pass path only)
+  GemmPlan* epi = nullptr;  // the producing conv whose epilogue emits this op's statistics partials (two-pass path only)
   void plan_bwd() override {
     acc = x->grad_set;
     x->grad_set = true;
   }
   void fwd(cudaStream_t st) override;
   void bwd(cudaStream_t st) override;
-  int n_fwd() const override { return plan.fuse_f ? 1 : (have_stats ? 1 : 2); }
+  int n_fwd() const override { return plan.fuse_f ? 1 : (epi ? 1 : 2); }
   int n_bwd() const override { return plan.fuse_b ? 1 : 2; }
 };
 struct LayerNormOp : Op {
@@ -399,6 +401,9 @@ struct Engine {
   unsigned int* gn_ticket = nullptr;
   unsigned int* gn_bar = nullptr;  // grid barrier of the single-launch GroupNorm kernels (count, generation, timeout flag)
   GNScratch gn_scratch() const { return GNScratch{gn_partial, gn_gstats, gn_ticket, gn_bar}; }
+  float* gn_epi_partial = nullptr;       // statistics rows written by conv epilogues (GemmParams::gn_partial), one scratch for all
+  size_t gn_epi_floats = 0;
+  std::vector<GemmPlan*> gn_epi_plans;
   float* attn_S = nullptr;
   size_t attn_S_floats = 0;
   // time embedding
@@ -605,7 +610,8 @@ inline void LinearOp::bwd(cudaStream_t st) {
                                                                         acc_res);
 }
 inline void GroupNormOp::fwd(cudaStream_t st) {
-  run_gn_fwd(plan, x->d, y->d, y->ld, gamma, beta, eps, silu, stats, E->gn_scratch(), st, have_stats);
+  run_gn_fwd(plan, x->d, y->d, y->ld, gamma, beta, eps, silu, stats, E->gn_scratch(), st, epi ? E->gn_epi_partial : nullptr,
+             epi ? epi->grid : 0);
 }
 inline void GroupNormOp::bwd(cudaStream_t st) {
   run_gn_bwd(plan, x->d, y->g, y->ld, gamma, beta, silu, stats, x->g, x->ld, acc, E->gn_scratch(), st);
@@ -718,6 +724,7 @@ inline Tensor* Engine::conv3x3(Tensor* x, int cout, const std::string& key, Tens
   if (res) e.res = res->d, e.ldr = res->ld;
   op->pf = plan_conv3x3(x->n, x->h, x->w, x->c, cout, x->d, x->ld, W->w, e);
   maybe_split(op->pf);
+  if (!y->is_view) y->producer = &op->pf;
   push(op, key);
   return y;
 }
@@ -749,6 +756,27 @@ inline Tensor* Engine::group_norm(Tensor* x, const std::string& key, float eps, 
   op->plan = plan_groupnorm(x->n, x->h * x->w, x->c, G, x->ld);
   op->stats = arena.make<float>(2ull * x->n * G);
   gn_partial_floats = std::max<size_t>(gn_partial_floats, op->plan.partial_floats);
+  // Large tensors (two-pass path): let the conv that produces x emit the statistics from its epilogue
+  // (measured slower than the separate statistics kernel -- 22.10 vs 21.73 ms per step: the four epilogue warps are the
+  // scarce resource of the 128-channel convolutions, DESIGN.md section 4 -- so it is opt-in: MDC_GNEPI=1)
+  static const bool no_epi = getenv("MDC_GNEPI") == nullptr;
+  const int cpg = x->c / G;
+  if (!no_epi && !op->plan.fuse_f && x->producer && !x->producer_gn && G == 32 && 32 % cpg == 0 && x->c % 32 == 0) {
+    GemmPlan* g = x->producer;
+    if (g->p.conv == 1 && g->p.ksplit <= 1 && g->p.N == x->c && g->p.BN % 32 == 0 && !g->p.out_f32) {
+      g->p.gn_cpg = cpg, g->p.gn_nimg = x->n;
+      finish_plan(*g);  // shared-memory layout changes (accumulator columns), possibly one pipeline stage fewer
+      if (g->p.tma_store) {
+        x->producer_gn = true;
+        op->epi = g;
+        gn_epi_floats = std::max<size_t>(gn_epi_floats, static_cast<size_t>(x->n) * g->grid * 64);
+        gn_epi_plans.push_back(g);
+      } else {  // the statistics ride on the TMA-store epilogue path only
+        g->p.gn_cpg = 0;
+        finish_plan(*g);
+      }
+    }
+  }
   push(op, key);
   return y;
 }
@@ -877,6 +905,7 @@ inline Tensor* Engine::upsample_conv(Tensor* x, int H2, int W2, const std::strin
     Epilogue e;
     e.out = y->d, e.ldc = y->ld, e.bias = B->vec;
     op->pf = plan_upconv_fwd(x->n, x->h, x->w, x->c, x->c, x->d, x->ld, W->w, e);
+    if (!y->is_view) y->producer = &op->pf;
     push(op, key + ".conv");
     if (y->name.empty()) y->name = key, named[key] = y;
     return y;
@@ -1187,6 +1216,8 @@ inline void Engine::finalize_plans() {
   gn_gstats = arena.make<float>(2ull * 64 * MAXN + 64);
   gn_ticket = arena.make<unsigned int>(MAXN + 16);
   gn_bar = arena.make<unsigned int>(16);
+  gn_epi_partial = arena.make<float>(gn_epi_floats + 64);
+  for (GemmPlan* g : gn_epi_plans) g->p.gn_partial = gn_epi_partial;
   attn_S = arena.make<float>(attn_S_floats + 64);
   temb_cur = arena.make<float>(temb_total + 64);
   for (auto* ops : {&unet_ops, &dec_ops, &enc_ops}) {

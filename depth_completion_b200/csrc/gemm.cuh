@@ -83,12 +83,24 @@ struct GemmParams {
   long long ws_ld, ws_split_stride;
   // Row-shared taps (conv 3x3, tile = 128 consecutive pixels of ONE image row): the three taps of a kernel row read the
   // same pixels shifted by -1 / 0 / +1, so ONE A box of 130 pixels [64 c, 130 w] is staged per (kernel row, channel
-  // chunk) and the three taps are issued as MMAs over row-offset views of it (descriptor start + 128 B x s, matrix base
-  // offset s), each with its own B tile.  A k-step then moves 16.6 KB of activations through L2 -> SM for three taps
+  // chunk) and the three taps are issued as MMAs over row-offset views of it (descriptor start address + 128 B x s),
+  // each with its own B tile.  The 128-byte swizzle is a function of the absolute shared-memory address for both the
+  // TMA write and the MMA read, so a view that starts s rows into the box needs NO matrix base offset in the descriptor
+  // (measured on a B200: setting it to s gives wrong results, leaving it 0 is exact -- tools/rowshare_diag.py).  A k-step then moves 16.6 KB of activations through L2 -> SM for three taps
   // instead of 48 KB, which is what bounds the 128-output-channel convolutions (B is only BN x 128 B per tap).
   int rowshare;
   int a_stage;  // bytes between A stages (GEMM_A_STAGE, or 17 KiB for a 130-row box)
+  // GroupNorm statistics of the OUTPUT tensor as an epilogue side product (conv mode, 32 groups, no split-K): every
+  // epilogue thread accumulates (sum, sum of squares) of the values it stores, per group, in a private shared-memory
+  // column across all tiles of the persistent loop; per image the CTA reduces them once and writes one partial row
+  // gn_partial[(img * gridDim.x + cta) * 64 + 2 g + {0, 1}].  The consuming gn_apply kernel reduces the rows in a fixed
+  // order (deterministic) -- the separate statistics pass over the 56-226 MB decoder tensors disappears.
+  float* gn_partial;
+  int gn_cpg;     // channels per group (2, 4, 8, 16 or 32); 0 = off
+  int gn_nimg;
+  int gn_smem_off;  // byte offset of the accumulators inside the aligned dynamic shared memory
 };
+constexpr int GEMM_GN_SMEM = (64 * 128 + 4 * 64) * 4;  // accumulators [64][128] + per-warp sums [4][64]
 constexpr int GEMM_A_STAGE_RS = 17 * 1024;  // 130 rows x 128 B, rounded up to the 1024-byte swizzle atom
 
 // work item -> (n_tile, m_tile, b0, b1); with split-K the batch slot b0 carries the split index instead.  With
@@ -104,6 +116,31 @@ __device__ __forceinline__ void gemm_decode_tile(const GemmParams& p, int tile, 
   const int nb0 = p.ksplit > 1 ? p.ksplit : p.nb0;
   b0 = b % nb0;
   b1 = b / nb0;
+}
+
+// (sum, sum of squares) of a 32-column chunk, per GroupNorm group of `cpg` channels, added to this thread's private
+// accumulator column acc[(2 g) * 128], acc[(2 g + 1) * 128].  Indexing of v stays static (registers).
+template <int CPG>
+__device__ __forceinline__ void gn_accumulate_t(const float (&v)[32], float* __restrict__ acc, int g0) {
+#pragma unroll
+  for (int j0 = 0; j0 < 32; j0 += CPG) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int t = 0; t < CPG; ++t) s += v[j0 + t], q = fmaf(v[j0 + t], v[j0 + t], q);
+    float* a = acc + (2 * (g0 + j0 / CPG)) * 128;
+    a[0] += s;
+    a[128] += q;
+  }
+}
+__device__ __forceinline__ void gn_accumulate(const float (&v)[32], float* __restrict__ acc, int cpg, int col0) {
+  const int g0 = col0 / cpg;
+  switch (cpg) {
+    case 2: gn_accumulate_t<2>(v, acc, g0); break;
+    case 4: gn_accumulate_t<4>(v, acc, g0); break;
+    case 8: gn_accumulate_t<8>(v, acc, g0); break;
+    case 16: gn_accumulate_t<16>(v, acc, g0); break;
+    default: gn_accumulate_t<32>(v, acc, g0); break;
+  }
 }
 
 template <bool kPair>
@@ -294,8 +331,8 @@ __device__ __forceinline__ void umma_gemm_body(const GemmParams& p) {
           if (p.rowshare) {
 #pragma unroll
             for (uint32_t sx = 0; sx < 3; ++sx) {
-              // view of the A box shifted by sx pixel rows (128 B each): start address + 8, matrix base offset sx
-              const uint64_t as = ad + (sx << 3) + (static_cast<uint64_t>(sx) << 49);
+              // view of the A box shifted by sx pixel rows (128 B each): start address field + 8 (x 16 B)
+              const uint64_t as = ad + (sx << 3) + (p.rowshare == 2 ? (static_cast<uint64_t>(sx) << 49) : 0ull);
               const uint64_t bs = bd + sx * (b_tile >> 4);
 #pragma unroll
               for (uint32_t kk = 0; kk < 4; ++kk) {
@@ -351,6 +388,31 @@ __device__ __forceinline__ void umma_gemm_body(const GemmParams& p) {
     const uint32_t ring_mask = static_cast<uint32_t>(p.npanel - 1);
     const bool store_leader = (warp == 2) && ptx::elect_one();
     const uint32_t tempty_leader = pair ? ptx::mapa_u32(&tempty_bar[0], 0) : 0u;
+    // GroupNorm statistics of the output (see GemmParams::gn_partial)
+    const int etid = threadIdx.x - 64;  // 0..127
+    float* gacc = reinterpret_cast<float*>(smem + p.gn_smem_off);
+    int gn_img = -1;
+    if (p.gn_cpg) {
+      for (int i = 0; i < 64; ++i) gacc[i * 128 + etid] = 0.f;  // each thread only ever touches its own column
+      if (etid < 64)  // this CTA's rows of the partial table start at zero; flushes accumulate into them (a CTA may come
+                      // back to an image: the phases of the fused upsample conv sweep the images four times)
+        for (int im = 0; im < p.gn_nimg; ++im) p.gn_partial[(static_cast<long long>(im) * gridDim.x + blockIdx.x) * 64 + etid] = 0.f;
+    }
+    auto gn_flush = [&](int im) {
+      float* wsum = gacc + 64 * 128;
+      for (int g2 = 0; g2 < 64; ++g2) {
+        float v = gacc[g2 * 128 + etid];
+        gacc[g2 * 128 + etid] = 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) wsum[(etid >> 5) * 64 + g2] = v;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (etid < 64)
+        p.gn_partial[(static_cast<long long>(im) * gridDim.x + blockIdx.x) * 64 + etid] +=
+            wsum[etid] + wsum[64 + etid] + wsum[128 + etid] + wsum[192 + etid];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
       int n_tile, m_tile, b0, b1;
       gemm_decode_tile(p, tile, n_tile, m_tile, b0, b1, rank);
@@ -379,6 +441,10 @@ __device__ __forceinline__ void umma_gemm_body(const GemmParams& p) {
         sc1 = m_tile * GEMM_BM, sc2 = b0, sc3 = b1;
         off_c = b0 * p.sc0 + b1 * p.sc1 + static_cast<long long>(m) * p.ldc;
         off_r = b0 * p.sr0 + b1 * p.sr1 + static_cast<long long>(m) * p.ldr;
+      }
+      if (p.gn_cpg && m_tile < p.m_tiles && img != gn_img) {  // tiles are visited image by image
+        if (gn_img >= 0) gn_flush(gn_img);
+        gn_img = img;
       }
       // epilogue operands (split-K partials go to the fp32 workspace, raw)
       void* e_out = p.out;
@@ -476,6 +542,7 @@ __device__ __forceinline__ void umma_gemm_body(const GemmParams& p) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
+            if (p.gn_cpg) gn_accumulate(v, gacc + etid, p.gn_cpg, col0);
             uint4* o4 = reinterpret_cast<uint4*>(panel + row * 64);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -581,6 +648,7 @@ __device__ __forceinline__ void umma_gemm_body(const GemmParams& p) {
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
+    if (p.gn_cpg && gn_img >= 0) gn_flush(gn_img);  // last image of this CTA
   }
 
   if (p.tma_store && warp == 2) ptx::bulk_wait_all();  // (only the issuing lane has groups pending; a no-op elsewhere)
@@ -783,13 +851,15 @@ inline void finish_plan(GemmPlan& g) {
   GemmParams& p = g.p;
   const int b_stage = (p.pair ? p.BN / 2 : p.BN) * 128 * (p.rowshare ? 3 : 1);
   p.a_stage = p.rowshare ? GEMM_A_STAGE_RS : GEMM_A_STAGE;
+  const int gn_bytes = p.gn_cpg ? GEMM_GN_SMEM : 0;
   auto stages_for = [&](int npanel) {
-    return std::min((GEMM_SMEM_BUDGET - GEMM_HEADER0 - npanel * GEMM_PANEL - 1024) / (p.a_stage + b_stage), GEMM_MAX_STAGES);
+    return std::min((GEMM_SMEM_BUDGET - GEMM_HEADER0 - npanel * GEMM_PANEL - 1024 - gn_bytes) / (p.a_stage + b_stage), GEMM_MAX_STAGES);
   };
   p.npanel = (stages_for(4) == stages_for(2)) ? 4 : 2;  // never trade a pipeline stage for store depth
   const int stages = std::max(2, stages_for(p.npanel));
   p.stages = stages;
-  g.smem = GEMM_HEADER0 + p.npanel * GEMM_PANEL + 1024 + stages * (p.a_stage + b_stage);
+  p.gn_smem_off = GEMM_HEADER0 + p.npanel * GEMM_PANEL + stages * (p.a_stage + b_stage);
+  g.smem = GEMM_HEADER0 + p.npanel * GEMM_PANEL + 1024 + stages * (p.a_stage + b_stage) + gn_bytes;
   p.idesc = ptx::make_idesc_bf16(p.pair ? 2 * GEMM_BM : GEMM_BM, p.BN, p.a_mn, p.b_mn);
   if (p.cs < 1) p.cs = 1, p.pair = 0;  // set by the planners via decide_cluster() before the B map was built
   long long total = 1LL * ((p.m_tiles + p.cs - 1) / p.cs) * p.n_tiles * (p.ksplit > 1 ? p.ksplit : p.nb0) * p.nb1;
@@ -912,7 +982,8 @@ inline GemmPlan plan_conv3x3(int NB, int H, int W, int C, int Cout, const void* 
   // row-shared taps: full-width row tiles, narrow N (the A operand dominates the L2 -> SM traffic), many tiles
   static const bool no_rs = getenv("MDC_NO_ROWSHARE") != nullptr;
   const int rs_tune = g_tune().rowshare;  // 0 auto, 1 off, 2 force when legal
-  p.rowshare = (p.BW == 128 && p.BH == 1 && rs_tune != 1 && ((!no_rs && p.BN <= 128 && p.m_tiles >= 1024) || rs_tune == 2)) ? 1 : 0;
+  p.rowshare = (p.BW == 128 && p.BH == 1 && rs_tune != 1 && ((!no_rs && p.BN <= 128 && p.m_tiles >= 1024) || rs_tune >= 2)) ? 1 : 0;
+  if (p.rowshare && rs_tune == 3) p.rowshare = 2;  // diagnostic variant (wrong on purpose): additionally sets the matrix base offset
   if (p.rowshare) {
     p.num_k_chunks = 3 * p.chunks_per_tap;  // one pipeline stage = one kernel row x one channel chunk = three taps
     p.bytesA = 64u * 130u * 2u;

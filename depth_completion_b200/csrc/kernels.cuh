@@ -76,6 +76,23 @@ __device__ __forceinline__ float silu_grad(float x) {
   float s = sigmoidf_(x);
   return s * (1.f + x * (1.f - s));
 }
+// ---- packed fp32x2 forms (Blackwell issues two fp32 FMAs per instruction): the two-pass GroupNorm kernels on the
+// 56-226 MB decoder tensors are instruction-bound as much as HBM-bound, so their per-element math is written on channel
+// pairs with every per-channel affine step folded into one FMA.
+__device__ __forceinline__ float2 bf16r2(float2 v) { return __bfloat1622float2(__floats2bfloat162_rn(v.x, v.y)); }
+__device__ __forceinline__ float2 sigmoid2(float2 x) {
+  const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  float t0, t1;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h.y));
+  return __ffma2_rn(make_float2(t0, t1), make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+}
+__device__ __forceinline__ float2 silu2(float2 x) { return __fmul2_rn(x, sigmoid2(x)); }
+__device__ __forceinline__ float2 silu_grad2(float2 x) {  // s (1 + x (1 - s))
+  const float2 s = sigmoid2(x);
+  const float2 om = __ffma2_rn(s, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+  return __fmul2_rn(s, __ffma2_rn(x, om, make_float2(1.f, 1.f)));
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
@@ -228,24 +245,55 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int N, int
   }
 }
 
-// pass 2 of forward: y = act((x - mean) * rstd * gamma + beta)
+// pass 2 of forward: y = act((x - mean) * rstd * gamma + beta).
+// With `partial` != nullptr the statistics come from the epilogue of the GEMM that produced x (GemmParams::gn_partial):
+// `nparts` rows of (sum, sum of squares) per group and image, reduced here in a fixed order in double (every block
+// does it for its image: a few KB from L2), and block 0 of the image publishes (mean, rstd) to `stats` for the backward.
 __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const bf16* __restrict__ x, GNShape s,
-                                                          const float* __restrict__ stats,
+                                                          float* __restrict__ stats,
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, int silu,
-                                                          bf16* __restrict__ y, long long ldy) {
+                                                          bf16* __restrict__ y, long long ldy,
+                                                          const float* __restrict__ partial, int nparts, float eps) {
   ptx::pdl_wait();
   ptx::pdl_launch();
+  __shared__ float sstat[128];
   const int CV = s.C >> 3, cpg = s.C / s.G;
   const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
   const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
-  float sc[8], sf[8];
+  if (partial) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const double m = 1.0 * s.HW * cpg;
+    for (int g = warp; g < s.G; g += nwarps) {
+      double a = 0, q = 0;
+      for (int k = lane; k < nparts; k += 32) {
+        const float2 pv = __ldcg(reinterpret_cast<const float2*>(partial + (1LL * n * nparts + k) * 2 * s.G + 2 * g));
+        a += pv.x, q += pv.y;
+      }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    int c = cv * 8 + i, g = c / cpg;
-    float mean = stats[2 * (n * s.G + g)], rstd = stats[2 * (n * s.G + g) + 1];
-    sc[i] = rstd * gamma[c];
-    sf[i] = beta[c] - mean * sc[i];
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      if (lane == 0) {
+        const double mean = a / m;
+        double var = q / m - mean * mean;
+        if (var < 0) var = 0;
+        sstat[2 * g] = static_cast<float>(mean);
+        sstat[2 * g + 1] = static_cast<float>(1.0 / sqrt(var + eps));
+      }
+    }
+    __syncthreads();
+    if (b == 0)
+      for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) stats[2 * n * s.G + i] = sstat[i];
+  }
+  float2 sc[4], sf[4];  // per channel pair: y = act(x * sc + sf)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = cv * 8 + 2 * i, g = c / cpg;  // a pair never straddles a group (channels per group is even)
+    const float mean = partial ? sstat[2 * g] : stats[2 * (n * s.G + g)], rstd = partial ? sstat[2 * g + 1] : stats[2 * (n * s.G + g) + 1];
+    sc[i] = make_float2(rstd * gamma[c], rstd * gamma[c + 1]);
+    sf[i] = make_float2(beta[c] - mean * sc[i].x, beta[c + 1] - mean * sc[i].y);
   }
   const int p0 = b * s.pix_per_block, p1 = min(s.HW, p0 + s.pix_per_block);
   const bf16* xb = x + (1LL * n * s.HW) * s.ld + cv * 8;
@@ -258,14 +306,14 @@ __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const bf16* __restrict
 #pragma unroll
     for (int u = 0; u < GN_UNROLL; ++u)
       if (p + u * R < p1) {
-        float f[8];
-        bf8_to_f(v[u], f);
+        BF8 o;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float h = f[i] * sc[i] + sf[i];
-          f[i] = silu ? siluf_(bf16r(h)) : h;
+        for (int i = 0; i < 4; ++i) {
+          float2 h = __ffma2_rn(__bfloat1622float2(v[u].v[i]), sc[i], sf[i]);
+          if (silu) h = silu2(bf16r2(h));
+          o.v[i] = __floats2bfloat162_rn(h.x, h.y);
         }
-        *reinterpret_cast<BF8*>(yb + 1LL * (p + u * R) * ldy) = f_to_bf8(f);
+        *reinterpret_cast<BF8*>(yb + 1LL * (p + u * R) * ldy) = o;
       }
   }
 }
@@ -288,6 +336,34 @@ __device__ __forceinline__ void gn_load_const(GNBwdConst& k, const GNShape& s, i
   for (int i = 0; i < 8; ++i) k.ga[i] = gamma[cv * 8 + i], k.be[i] = beta[cv * 8 + i];
 }
 
+// Per-thread constants of the two-pass backward kernels, per channel pair, with every affine step folded:
+//   u  = x * A + B          (pre-activation: A = rstd gamma, B = beta - mean rstd gamma)
+//   xh = x * r + M          (normalised value: r = rstd, M = -mean rstd)
+//   d  = dy * act'(u) * gamma
+struct GNBwdPairs {
+  float2 A[4], B[4], G[4];
+  float r[4], M[4];
+};
+__device__ __forceinline__ void gn_load_pairs(GNBwdPairs& k, const GNShape& s, int n, int cv, const float* __restrict__ stats,
+                                              const float* __restrict__ gamma, const float* __restrict__ beta) {
+  const int cpg = s.C / s.G;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = cv * 8 + 2 * i, g = c / cpg;
+    const float mean = stats[2 * (n * s.G + g)], rstd = stats[2 * (n * s.G + g) + 1];
+    k.G[i] = make_float2(gamma[c], gamma[c + 1]);
+    k.A[i] = make_float2(rstd * k.G[i].x, rstd * k.G[i].y);
+    k.B[i] = make_float2(beta[c] - mean * k.A[i].x, beta[c + 1] - mean * k.A[i].y);
+    k.r[i] = rstd, k.M[i] = -mean * rstd;
+  }
+}
+// d = dy * act'(bf16(u)) * gamma for one channel pair
+__device__ __forceinline__ float2 gn_dxhat2(float2 x, float2 dy, const GNBwdPairs& k, int i, int silu) {
+  float2 d = __fmul2_rn(dy, k.G[i]);
+  if (silu) d = __fmul2_rn(d, silu_grad2(bf16r2(__ffma2_rn(x, k.A[i], k.B[i]))));
+  return d;
+}
+
 // backward pass 1: per-block partial (sum dxhat, sum dxhat*xhat) per group, dxhat = dy * act'(h) * gamma
 __global__ void __launch_bounds__(384, 2) gn_bwd_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
                                                               long long lddy, GNShape s,
@@ -306,9 +382,11 @@ __global__ void __launch_bounds__(384, 2) gn_bwd_stats_kernel(const bf16* __rest
   const int nwarps_ = (blockDim.x + 31) >> 5, wid_ = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < nwarps_ * 2 * s.G; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
-  GNBwdConst k;
-  gn_load_const(k, s, n, cv, stats, gamma, beta);
-  float sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
+  GNBwdPairs k;
+  gn_load_pairs(k, s, n, cv, stats, gamma, beta);
+  float2 sa2[4], sb2[4];  // lanes of a pair are summed at the end
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sa2[i] = sb2[i] = make_float2(0.f, 0.f);
   const int p0 = b * s.pix_per_block, p1 = min(s.HW, p0 + s.pix_per_block);
   const bf16* xb = x + (1LL * n * s.HW) * s.ld + cv * 8;
   const bf16* db = dy + (1LL * n * s.HW) * lddy + cv * 8;
@@ -324,17 +402,13 @@ __global__ void __launch_bounds__(384, 2) gn_bwd_stats_kernel(const bf16* __rest
 #pragma unroll
     for (int u = 0; u < U; ++u)
       if (p + u * R < p1) {
-        float fx[8], fd[8];
-        bf8_to_f(vx[u], fx);
-        bf8_to_f(vd[u], fd);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float xh = (fx[i] - k.mean[i >> 1]) * k.rstd[i >> 1];
-          float d = fd[i];
-          if (silu) d *= silu_grad(bf16r(xh * k.ga[i] + k.be[i]));
-          d *= k.ga[i];
-          sa[i >> 1] += d;
-          sb[i >> 1] += d * xh;
+        for (int i = 0; i < 4; ++i) {
+          const float2 xv = __bfloat1622float2(vx[u].v[i]);
+          const float2 d = gn_dxhat2(xv, __bfloat1622float2(vd[u].v[i]), k, i, silu);
+          const float2 xh = __ffma2_rn(xv, make_float2(k.r[i], k.r[i]), make_float2(k.M[i], k.M[i]));
+          sa2[i] = __fadd2_rn(sa2[i], d);
+          sb2[i] = __ffma2_rn(d, xh, sb2[i]);
         }
       }
   }
@@ -349,7 +423,7 @@ __global__ void __launch_bounds__(384, 2) gn_bwd_stats_kernel(const bf16* __rest
         atomicAdd(&mine[2 * gprev], a), atomicAdd(&mine[2 * gprev + 1], b);
         a = b = 0.f;
       }
-      gprev = g, a += sa[i], b += sb[i];
+      gprev = g, a += sa2[i].x + sa2[i].y, b += sb2[i].x + sb2[i].y;
     }
     atomicAdd(&mine[2 * gprev], a), atomicAdd(&mine[2 * gprev + 1], b);
   }
@@ -362,7 +436,8 @@ __global__ void __launch_bounds__(384, 2) gn_bwd_stats_kernel(const bf16* __rest
   gn_finalize_last_block(partial, n, s.G, s.blocks_per_img, 1.0 * s.HW * cpg, 0.f, 1, gstats_out, ticket);
 }
 
-// backward pass 2: dx (+)= rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat*xhat))
+// backward pass 2: dx (+)= rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat*xhat)) = dxhat * r + (x * C1 + C2) with
+// C1 = -r^2 m2, C2 = -r m1 - M r m2 per group
 __global__ void __launch_bounds__(384, 2) gn_bwd_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
                                                               long long lddy, GNShape s,
                                                               const float* __restrict__ stats,
@@ -375,13 +450,15 @@ __global__ void __launch_bounds__(384, 2) gn_bwd_apply_kernel(const bf16* __rest
   const int CV = s.C >> 3, cpg = s.C / s.G;
   const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
   const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
-  GNBwdConst k;
-  gn_load_const(k, s, n, cv, stats, gamma, beta);
-  float m1[4], m2[4];
+  GNBwdPairs k;
+  gn_load_pairs(k, s, n, cv, stats, gamma, beta);
+  float C1[4], C2[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    int g = (cv * 8 + 2 * i) / cpg;
-    m1[i] = gstats[2 * (n * s.G + g)], m2[i] = gstats[2 * (n * s.G + g) + 1];
+    const int g = (cv * 8 + 2 * i) / cpg;
+    const float m1 = gstats[2 * (n * s.G + g)], m2 = gstats[2 * (n * s.G + g) + 1];
+    C1[i] = -k.r[i] * k.r[i] * m2;
+    C2[i] = -k.r[i] * m1 - k.M[i] * k.r[i] * m2;
   }
   const int p0 = b * s.pix_per_block, p1 = min(s.HW, p0 + s.pix_per_block);
   const bf16* xb = x + (1LL * n * s.HW) * s.ld + cv * 8;
@@ -400,20 +477,16 @@ __global__ void __launch_bounds__(384, 2) gn_bwd_apply_kernel(const bf16* __rest
 #pragma unroll
     for (int u = 0; u < U; ++u)
       if (p + u * R < p1) {
-        float fx[8], fd[8], o[8];
-        bf8_to_f(vx[u], fx);
-        bf8_to_f(vd[u], fd);
-        if (acc) bf8_to_f(vo[u], o);
+        BF8 o;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float xh = (fx[i] - k.mean[i >> 1]) * k.rstd[i >> 1];
-          float d = fd[i];
-          if (silu) d *= silu_grad(bf16r(xh * k.ga[i] + k.be[i]));
-          d *= k.ga[i];
-          float g = k.rstd[i >> 1] * (d - m1[i >> 1] - xh * m2[i >> 1]);
-          o[i] = acc ? o[i] + g : g;
+        for (int i = 0; i < 4; ++i) {
+          const float2 xv = __bfloat1622float2(vx[u].v[i]);
+          const float2 d = gn_dxhat2(xv, __bfloat1622float2(vd[u].v[i]), k, i, silu);
+          float2 g = __ffma2_rn(d, make_float2(k.r[i], k.r[i]), __ffma2_rn(xv, make_float2(C1[i], C1[i]), make_float2(C2[i], C2[i])));
+          if (acc) g = __fadd2_rn(g, __bfloat1622float2(vo[u].v[i]));
+          o.v[i] = __floats2bfloat162_rn(g.x, g.y);
         }
-        *reinterpret_cast<BF8*>(ob + 1LL * (p + u * R) * lddx) = f_to_bf8(o);
+        *reinterpret_cast<BF8*>(ob + 1LL * (p + u * R) * lddx) = o;
       }
   }
 }

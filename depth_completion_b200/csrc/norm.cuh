@@ -76,9 +76,12 @@ struct GNScratch {
   unsigned int* bar = nullptr;     // 3 words (arrivals, generation, sticky timeout flag), zero-initialised
 };
 
-// have_stats: the statistics of x were already written to `stats` by the producing GEMM's epilogue (two-pass path only).
+// epi_partial / epi_parts: the producing GEMM's epilogue already emitted per-CTA (sum, sum of squares) rows for x
+// (GemmParams::gn_partial; two-pass path only): the statistics pass is skipped and gn_apply reduces those rows.
 inline void run_gn_fwd(const GNPlan& p, const bf16* x, bf16* y, long long ldy, const float* gamma, const float* beta, float eps,
-                       int silu, float* stats, const GNScratch& sc, cudaStream_t st, bool have_stats = false) {
+                       int silu, float* stats, const GNScratch& sc, cudaStream_t st, const float* epi_partial = nullptr,
+                       int epi_parts = 0) {
+  const bool have_stats = epi_partial != nullptr;
   if (p.fuse_f) {
     launch_k(gn_fused_fwd_kernel, dim3(p.sfu.N * p.sfu.blocks_per_img), dim3(p.threads), p.smem_f, st, x, p.sfu, sc.partial, eps, stats, sc.bar,
              gamma, beta, silu, y, ldy);
@@ -88,7 +91,7 @@ inline void run_gn_fwd(const GNPlan& p, const bf16* x, bf16* y, long long ldy, c
   if (!have_stats)
     launch_k(gn_stats_kernel, dim3(grid), dim3(p.threads), ((p.threads + 31) / 32) * 2 * p.G * sizeof(float), st, x, p.s, sc.partial, eps, stats,
              sc.ticket);
-  launch_k(gn_apply_kernel, dim3(grid), dim3(p.threads), 0, st, x, p.s, static_cast<const float*>(stats), gamma, beta, silu, y, ldy);
+  launch_k(gn_apply_kernel, dim3(grid), dim3(p.threads), 0, st, x, p.s, stats, gamma, beta, silu, y, ldy, epi_partial, epi_parts, eps);
 }
 inline void run_gn_bwd(const GNPlan& p, const bf16* x, const bf16* dy, long long lddy, const float* gamma, const float* beta, int silu,
                        const float* stats, bf16* dx, long long lddx, int acc, const GNScratch& sc, cudaStream_t st) {

@@ -32,6 +32,18 @@ def main():
     u_f, u_b = rel_l2(eng.dbg_forward(0, 0, xin), y), rel_l2(eng.dbg_backward(0, dout), x.grad)
     assert u_f < 4e-2 and u_b < 6e-2, ("unet", u_f, u_b)
     eng.close()
+    if os.environ.get("MDC_GNEPI") or os.environ.get("MDC_NO_ROWSHARE"):
+        # the switches that only act on large images: decoder tape on a 512x768 frame (two-pass GroupNorm with the
+        # statistics from the conv epilogues / tap-by-tap instead of row-shared convolutions)
+        big = build_engine(unet, vae, ctx, ucfg, vcfg, 2, 512, 768, 768, 50, dev)
+        z = torch.randn(2, 4, big.lh, big.lw, device=dev, generator=g).bfloat16().float()
+        x = z.clone().requires_grad_(True)
+        y = vae.decode(x)
+        dout = torch.randn(y.shape, device=dev, generator=g).bfloat16().float()
+        y.backward(dout)
+        b_f, b_b = rel_l2(big.dbg_forward(1, 0, z), y), rel_l2(big.dbg_backward(1, dout), x.grad)
+        assert b_f < 4e-2 and b_b < 6e-2, ("large decoder", b_f, b_b)
+        big.close()
     from depth_completion_b200.pipeline import MarigoldDepthCompletionPipeline
     from depth_completion_b200.synthetic import make_frame
     from oracle.marigold_dc import OraclePipeline

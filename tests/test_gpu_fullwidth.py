@@ -91,11 +91,17 @@ def _compare(tag, pipe, o32, o16, imgs, sparses, cfg, state32, t, st32, st16):
     r16 = _oracle_step_from(o16, st16, t, state32)
     v, grad, loss, eng = _engine_step_from(pipe, imgs, sparses, cfg, state32)
     out = {}
-    for name, ours, t16, ref in (("v", v, r16["v"], state32["v"]), ("grad", grad, r16["grad"], state32["grad"])):
+    # The latent gradient is the back-projection of sign(dense - guide) + 2 (dense - guide) at the valid points: one L1
+    # sign flip (a point whose residual is within bf16 noise of zero) changes it by ~sqrt(2 / points) in relative L2
+    # (6 % for 500 points), for torch's own bf16 run just as for the engine.  The bar for `grad` therefore allows two such
+    # flips on top of the torch-bf16 yardstick; `v` (no sign function on its path) is held to the yardstick itself.
+    npts = int((sparses > 0).sum().item())
+    flip = (2.0 / max(npts, 1)) ** 0.5
+    for name, ours, t16, ref, extra in (("v", v, r16["v"], state32["v"], 0.0), ("grad", grad, r16["grad"], state32["grad"], 2.0 * flip)):
         e_ours, e_16 = rel_l2(ours, ref), rel_l2(t16, ref)
         out[name] = (e_ours, e_16)
         assert torch.isfinite(ours).all(), f"{tag} {name}: non-finite"
-        assert e_ours <= 1.3 * e_16 + 3e-3, f"{tag} {name}: engine {e_ours:.3e} vs torch-bf16 {e_16:.3e} (rel L2 to the fp32 oracle)"
+        assert e_ours <= 1.3 * e_16 + 3e-3 + extra, f"{tag} {name}: engine {e_ours:.3e} vs torch-bf16 {e_16:.3e} (rel L2 to the fp32 oracle)"
     l32, l16 = state32["losses"].float().cpu(), r16["losses"].float().cpu()
     for i in range(cfg["N"]):
         tol = max(1.5 * abs(l16[i].item() - l32[i].item()), 1e-2 * l32[i].item())
@@ -152,3 +158,51 @@ def test_later_steps_full_width(full, cuda):
         res = _compare(f"step {k}", pipe, o32, o16, imgs, sparses, cfg, state, t, st32, st16)
         print(f"[full width] step {k}: rel-L2 to fp32 oracle (engine / torch-bf16): v {res['v'][0]:.3e} / {res['v'][1]:.3e}, "
               f"grad {res['grad'][0]:.3e} / {res['grad'][1]:.3e}")
+
+
+def test_tapes_full_width(full, cuda):
+    """The full-width UNet and VAE-decoder tapes at config (b) (latent 72x96, decoder output 576x768), forward and
+    input-gradient backward from a RANDOM output gradient (no sign function anywhere, so nothing is chaotic): every
+    full-size kernel of the guided step against torch autograd in fp32, with torch-bf16 as the yardstick."""
+    from helpers import rel_l2
+
+    cfg = CONFIGS["b_nyu_res768"]
+    o32, o16, pipe = full["o32"], full["o16"], full["pipe"]
+    imgs, sparses = _frames(cfg, cuda)
+    pipe(imgs, sparses, cfg["max_depth"], steps=50, resolution=cfg["res"], _begin_only=True)
+    eng = list(pipe._engines.values())[-1]
+    g = torch.Generator(device=cuda).manual_seed(77)
+
+    def check(name, ours, t16, ref):
+        e_ours, e_16 = rel_l2(ours, ref), rel_l2(t16, ref)
+        print(f"[full width] tape {name}: rel-L2 to fp32 (engine / torch-bf16) {e_ours:.3e} / {e_16:.3e}")
+        assert e_ours <= 1.25 * e_16 + 2e-3 and e_ours < 6e-2, f"{name}: engine {e_ours:.3e} vs torch-bf16 {e_16:.3e}"
+
+    # --- decoder
+    z = torch.randn(1, 4, eng.lh, eng.lw, device=cuda, generator=g).bfloat16().float()
+    x = z.clone().requires_grad_(True)
+    y = o32.vae.decode(x)
+    dout = torch.randn(y.shape, device=cuda, generator=g).bfloat16().float()
+    y.backward(dout)
+    x16 = z.bfloat16().requires_grad_(True)
+    y16 = o16.vae.decode(x16)
+    y16.backward(dout.bfloat16())
+    got, din = eng.dbg_forward(1, 0, z), eng.dbg_backward(1, dout)
+    check("decoder fwd", got, y16, y.detach())
+    check("decoder bwd", din, x16.grad, x.grad)
+    del y, y16
+    # --- UNet at an early and a late step
+    from depth_completion_b200 import ddim
+    for step in (0, 40):
+        t = torch.tensor(int(ddim.trailing_timesteps(50)[step]), device=cuda)
+        xin = torch.randn(1, 8, eng.lh, eng.lw, device=cuda, generator=g).bfloat16().float()
+        x = xin.clone().requires_grad_(True)
+        y = o32.unet(x, t, o32.empty_text_embedding)
+        dout = torch.randn(y.shape, device=cuda, generator=g).bfloat16().float()
+        y.backward(dout)
+        x16 = xin.bfloat16().requires_grad_(True)
+        y16 = o16.unet(x16, t, o16.empty_text_embedding)
+        y16.backward(dout.bfloat16())
+        got, din = eng.dbg_forward(0, step, xin), eng.dbg_backward(0, dout)
+        check(f"unet fwd (step {step})", got, y16, y.detach())
+        check(f"unet bwd (step {step})", din, x16.grad, x.grad)

@@ -119,8 +119,10 @@ def test_groupnorm_fullsize(cuda, n, H, W, C, mode, silu, eps):
     gamma = 1.0 + 0.3 * torch.randn(C, device=cuda, generator=g)
     beta = 0.2 * torch.randn(C, device=cuda, generator=g)
     dy = torch.randn(n, HW, C, device=cuda, generator=g).bfloat16()
-    y, dx, stats, _ = debug.groupnorm(x, gamma, beta, 32, eps, silu, dy, mode=mode)
+    y, dx, stats, ms = debug.groupnorm(x, gamma, beta, 32, eps, silu, dy, mode=mode, iters=5)
     torch.cuda.synchronize()
+    mb = x.numel() * 2 / 1e6
+    print(f"[measured] GroupNorm {n}x{H}x{W}x{C} mode {mode} ({mb:.0f} MB): fwd {ms[0] * 1e3:.1f} us, bwd {ms[1] * 1e3:.1f} us")
     y32, dx32 = _gn_ref(x, gamma, beta, 32, eps, silu, dy, torch.float32)
     y16, dx16 = _gn_ref(x, gamma, beta, 32, eps, silu, dy, torch.bfloat16)
     _check("groupnorm fwd", y, y16, y32, cap=6e-3, slack=1.5e-3)

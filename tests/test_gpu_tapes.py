@@ -280,3 +280,32 @@ def test_autoencoder_tiny_against_golden_fixture(cuda):
     # Adam's first step is -lr * sign(g) per element; with ReLU masks flipping between an fp32 and a bf16 evaluation the
     # sign of a small-gradient element is noisier than with the SiLU / GroupNorm VAE (0.8 there)
     assert agree > 0.6, agree
+
+
+def test_decoder_tape_large_frame(cuda):
+    """The narrow test VAE on a 512x768 frame (latent 64x96): its decoder's top-level GroupNorm tensors are 50-100 MB, so the
+    engine takes the two-pass GroupNorm path with the statistics emitted by the producing convolutions' epilogues
+    (GemmParams::gn_partial), the row-shared-taps convolution mode and many-tile persistent loops -- the code paths of
+    the full-size decoder, against torch fp32 / bf16."""
+    from helpers import build_engine, build_models
+
+    unet, vae, ctx, ucfg, vcfg = build_models(cuda, tiny=True, seed=21)
+    for n in (1, 2):
+        eng = build_engine(unet, vae, ctx, ucfg, vcfg, n, 512, 768, 768, 50, cuda)
+        g = torch.Generator(device=cuda).manual_seed(9 + n)
+        z = torch.randn(n, 4, eng.lh, eng.lw, device=cuda, generator=g).bfloat16().float()
+        if n == 2:
+            z[1] *= 2.5
+        x = z.clone().requires_grad_(True)
+        y = vae.decode(x)
+        dout = torch.randn(y.shape, device=cuda, generator=g).bfloat16().float()
+        y.backward(dout)
+        v16 = copy.deepcopy(vae).bfloat16()
+        x16 = z.bfloat16().requires_grad_(True)
+        y16 = v16.decode(x16)
+        y16.backward(dout.bfloat16())
+        got = eng.dbg_forward(1, 0, z)
+        din = eng.dbg_backward(1, dout)
+        _check(f"decoder fwd (n={n}, 512x768)", got, y16, y)
+        _check(f"decoder bwd (n={n}, 512x768)", din, x16.grad, x.grad)
+        eng.close()
