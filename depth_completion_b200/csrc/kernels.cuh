@@ -730,6 +730,264 @@ __global__ void __launch_bounds__(512, 1) gn_fused_bwd_kernel(const bf16* __rest
   }
 }
 
+// --------------------------------------------------------------------------- streamed two-pass GroupNorm
+// ncu on the register-fed kernels above (113 MB tensor, profiles/r02_ncu_groupnorm.md): DRAM 39-54 % busy, issue slots
+// 53-59 % busy, 35-49 % of the warp slots occupied -- neither memory nor instruction bound but LATENCY bound: a thread
+// keeps only 4 x 16 B in flight and cannot request the next batch before it has consumed the current one.  The streamed
+// variants decouple the two: a block's pixel slab is contiguous memory (pixel stride == C), so one thread feeds a ring
+// of shared-memory stages with 1-D bulk copies (cp.async.bulk, completion on an mbarrier) that runs GNS_STAGES - 1
+// chunks ahead of the arithmetic, and the bytes in flight per SM no longer depend on registers or occupancy.
+constexpr int GNS_STAGES = 4;
+constexpr int GNS_UNROLL = 2;  // pixel rows (of R pixels) per chunk and thread
+struct GnsPipe {
+  uint64_t* full;      // [GNS_STAGES]
+  uint8_t* buf;        // [GNS_STAGES][ntens][chunk_bytes]
+  uint32_t chunk_bytes, ntens;
+  const uint8_t* src[2];
+  long long total_bytes;  // bytes of this block's slab (per tensor)
+  int nchunks;
+};
+__device__ __forceinline__ void gns_issue(const GnsPipe& q, int k) {  // one thread
+  const int st = k % GNS_STAGES;
+  const long long off = 1LL * k * q.chunk_bytes;
+  const uint32_t bytes = static_cast<uint32_t>(min(static_cast<long long>(q.chunk_bytes), q.total_bytes - off));
+  ptx::mbar_expect_tx(&q.full[st], bytes * q.ntens);
+  for (uint32_t t = 0; t < q.ntens; ++t) ptx::bulk_load_1d(q.buf + (st * q.ntens + t) * q.chunk_bytes, q.src[t] + off, bytes, &q.full[st]);
+}
+// Sets the ring up and requests the first GNS_STAGES - 1 chunks.  smem: [8 x u64 barriers][stages x ntens x chunk].
+__device__ __forceinline__ GnsPipe gns_begin(uint8_t* smem, const bf16* t0, const bf16* t1, long long elem_off, long long elems, int C,
+                                             int R) {
+  GnsPipe q;
+  q.full = reinterpret_cast<uint64_t*>(smem);
+  q.buf = smem + 128;
+  q.ntens = t1 ? 2u : 1u;
+  q.chunk_bytes = static_cast<uint32_t>(R) * GNS_UNROLL * C * 2u;
+  q.src[0] = reinterpret_cast<const uint8_t*>(t0 + elem_off);
+  q.src[1] = t1 ? reinterpret_cast<const uint8_t*>(t1 + elem_off) : nullptr;
+  q.total_bytes = elems * 2;
+  q.nchunks = static_cast<int>((q.total_bytes + q.chunk_bytes - 1) / q.chunk_bytes);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < GNS_STAGES; ++i) ptx::mbar_init(&q.full[i], 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int k = 0; k < GNS_STAGES - 1 && k < q.nchunks; ++k) gns_issue(q, k);
+  return q;
+}
+// Per chunk: the refill of the stage consumed in the PREVIOUS iteration is requested first (every thread passed the
+// __syncthreads that ended that iteration), then the block waits for this chunk's bytes.
+__device__ __forceinline__ const uint8_t* gns_acquire(const GnsPipe& q, int k) {
+  if (threadIdx.x == 0 && k + GNS_STAGES - 1 < q.nchunks) gns_issue(q, k + GNS_STAGES - 1);
+  ptx::mbar_wait(&q.full[k % GNS_STAGES], (k / GNS_STAGES) & 1);
+  return q.buf + (k % GNS_STAGES) * q.ntens * q.chunk_bytes;
+}
+__host__ __device__ inline size_t gns_smem_bytes(int threads, int ntens) { return 128 + static_cast<size_t>(GNS_STAGES) * ntens * threads * GNS_UNROLL * 16; }
+
+__global__ void __launch_bounds__(512, 2) gn_stats_s_kernel(const bf16* __restrict__ x, GNShape s, float* __restrict__ partial, float eps,
+                                                            float* __restrict__ stats_out, unsigned int* __restrict__ ticket) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  extern __shared__ __align__(128) uint8_t gns_smem[];
+  const int CV = s.C >> 3, cpg = s.C / s.G;
+  const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
+  const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
+  const int nwarps_ = (blockDim.x + 31) >> 5;
+  float* sh = reinterpret_cast<float*>(gns_smem + gns_smem_bytes(blockDim.x, 1));  // [warps][2G]
+  for (int i = threadIdx.x; i < nwarps_ * 2 * s.G; i += blockDim.x) sh[i] = 0.f;
+  const int p0 = b * s.pix_per_block, npix = min(s.HW, p0 + s.pix_per_block) - p0;
+  GnsPipe q = gns_begin(gns_smem, x, nullptr, (1LL * n * s.HW + p0) * s.C, 1LL * npix * s.C, s.C, R);
+  float2 sum2[4], sq2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sum2[i] = sq2[i] = make_float2(0.f, 0.f);
+  for (int k = 0; k < q.nchunks; ++k) {
+    const BF8* st = reinterpret_cast<const BF8*>(gns_acquire(q, k));
+#pragma unroll
+    for (int u = 0; u < GNS_UNROLL; ++u) {
+      const int pl = (k * GNS_UNROLL + u) * R + r;
+      if (pl < npix) {
+        const BF8 v = st[(u * R + r) * CV + cv];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 t = __bfloat1622float2(v.v[i]);
+          sum2[i] = __fadd2_rn(sum2[i], t);
+          sq2[i] = __ffma2_rn(t, t, sq2[i]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float sa[4], sb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sa[i] = sum2[i].x + sum2[i].y, sb[i] = sq2[i].x + sq2[i].y;
+  gn_block_partial(sa, sb, cv, cpg, s.G, sh, partial);
+  gn_finalize_last_block(partial, n, s.G, s.blocks_per_img, 1.0 * s.HW * cpg, eps, 0, stats_out, ticket);
+}
+
+__global__ void __launch_bounds__(512, 2) gn_apply_s_kernel(const bf16* __restrict__ x, GNShape s, float* __restrict__ stats,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                                                            bf16* __restrict__ y, long long ldy, const float* __restrict__ partial,
+                                                            int nparts, float eps) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  extern __shared__ __align__(128) uint8_t gns_smem[];
+  __shared__ float sstat[128];
+  const int CV = s.C >> 3, cpg = s.C / s.G;
+  const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
+  const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
+  const int p0 = b * s.pix_per_block, npix = min(s.HW, p0 + s.pix_per_block) - p0;
+  GnsPipe q = gns_begin(gns_smem, x, nullptr, (1LL * n * s.HW + p0) * s.C, 1LL * npix * s.C, s.C, R);  // loads fly during the prologue
+  if (partial) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const double m = 1.0 * s.HW * cpg;
+    for (int g = warp; g < s.G; g += nwarps) {
+      double a = 0, qq = 0;
+      for (int k = lane; k < nparts; k += 32) {
+        const float2 pv = __ldcg(reinterpret_cast<const float2*>(partial + (1LL * n * nparts + k) * 2 * s.G + 2 * g));
+        a += pv.x, qq += pv.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        qq += __shfl_xor_sync(0xffffffffu, qq, o);
+      }
+      if (lane == 0) {
+        const double mean = a / m;
+        double var = qq / m - mean * mean;
+        if (var < 0) var = 0;
+        sstat[2 * g] = static_cast<float>(mean);
+        sstat[2 * g + 1] = static_cast<float>(1.0 / sqrt(var + eps));
+      }
+    }
+    __syncthreads();
+    if (b == 0)
+      for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) stats[2 * n * s.G + i] = sstat[i];
+  }
+  float2 sc[4], sf[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = cv * 8 + 2 * i, g = c / cpg;
+    const float mean = partial ? sstat[2 * g] : stats[2 * (n * s.G + g)], rstd = partial ? sstat[2 * g + 1] : stats[2 * (n * s.G + g) + 1];
+    sc[i] = make_float2(rstd * gamma[c], rstd * gamma[c + 1]);
+    sf[i] = make_float2(beta[c] - mean * sc[i].x, beta[c + 1] - mean * sc[i].y);
+  }
+  bf16* yb = y + (1LL * n * s.HW + p0) * ldy + cv * 8;
+  for (int k = 0; k < q.nchunks; ++k) {
+    const BF8* st = reinterpret_cast<const BF8*>(gns_acquire(q, k));
+#pragma unroll
+    for (int u = 0; u < GNS_UNROLL; ++u) {
+      const int pl = (k * GNS_UNROLL + u) * R + r;
+      if (pl < npix) {
+        const BF8 v = st[(u * R + r) * CV + cv];
+        BF8 o;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float2 h = __ffma2_rn(__bfloat1622float2(v.v[i]), sc[i], sf[i]);
+          if (silu) h = silu2(bf16r2(h));
+          o.v[i] = __floats2bfloat162_rn(h.x, h.y);
+        }
+        *reinterpret_cast<BF8*>(yb + 1LL * pl * ldy) = o;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(384, 2) gn_bwd_stats_s_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, GNShape s,
+                                                                const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, int silu, float* __restrict__ partial,
+                                                                float* __restrict__ gstats_out, unsigned int* __restrict__ ticket) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  extern __shared__ __align__(128) uint8_t gns_smem[];
+  const int CV = s.C >> 3, cpg = s.C / s.G;
+  const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
+  const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
+  const int nwarps_ = (blockDim.x + 31) >> 5;
+  float* sh = reinterpret_cast<float*>(gns_smem + gns_smem_bytes(blockDim.x, 2));
+  for (int i = threadIdx.x; i < nwarps_ * 2 * s.G; i += blockDim.x) sh[i] = 0.f;
+  const int p0 = b * s.pix_per_block, npix = min(s.HW, p0 + s.pix_per_block) - p0;
+  GnsPipe q = gns_begin(gns_smem, x, dy, (1LL * n * s.HW + p0) * s.C, 1LL * npix * s.C, s.C, R);
+  GNBwdPairs kk;
+  gn_load_pairs(kk, s, n, cv, stats, gamma, beta);
+  float2 sa2[4], sb2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sa2[i] = sb2[i] = make_float2(0.f, 0.f);
+  for (int k = 0; k < q.nchunks; ++k) {
+    const BF8* st = reinterpret_cast<const BF8*>(gns_acquire(q, k));
+    const BF8* sd = reinterpret_cast<const BF8*>(reinterpret_cast<const uint8_t*>(st) + q.chunk_bytes);
+#pragma unroll
+    for (int u = 0; u < GNS_UNROLL; ++u) {
+      const int pl = (k * GNS_UNROLL + u) * R + r;
+      if (pl < npix) {
+        const BF8 vx = st[(u * R + r) * CV + cv], vd = sd[(u * R + r) * CV + cv];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 xv = __bfloat1622float2(vx.v[i]);
+          const float2 d = gn_dxhat2(xv, __bfloat1622float2(vd.v[i]), kk, i, silu);
+          const float2 xh = __ffma2_rn(xv, make_float2(kk.r[i], kk.r[i]), make_float2(kk.M[i], kk.M[i]));
+          sa2[i] = __fadd2_rn(sa2[i], d);
+          sb2[i] = __ffma2_rn(d, xh, sb2[i]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float sa[4], sb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sa[i] = sa2[i].x + sa2[i].y, sb[i] = sb2[i].x + sb2[i].y;
+  gn_block_partial(sa, sb, cv, cpg, s.G, sh, partial);
+  gn_finalize_last_block(partial, n, s.G, s.blocks_per_img, 1.0 * s.HW * cpg, 0.f, 1, gstats_out, ticket);
+}
+
+__global__ void __launch_bounds__(384, 2) gn_bwd_apply_s_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, GNShape s,
+                                                                const float* __restrict__ stats, const float* __restrict__ gstats,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                                                                bf16* __restrict__ dx, long long lddx, int acc) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  extern __shared__ __align__(128) uint8_t gns_smem[];
+  const int CV = s.C >> 3, cpg = s.C / s.G;
+  const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
+  const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
+  const int p0 = b * s.pix_per_block, npix = min(s.HW, p0 + s.pix_per_block) - p0;
+  GnsPipe q = gns_begin(gns_smem, x, dy, (1LL * n * s.HW + p0) * s.C, 1LL * npix * s.C, s.C, R);
+  GNBwdPairs kk;
+  gn_load_pairs(kk, s, n, cv, stats, gamma, beta);
+  float C1[4], C2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int g = (cv * 8 + 2 * i) / cpg;
+    const float m1 = gstats[2 * (n * s.G + g)], m2 = gstats[2 * (n * s.G + g) + 1];
+    C1[i] = -kk.r[i] * kk.r[i] * m2;
+    C2[i] = -kk.r[i] * m1 - kk.M[i] * kk.r[i] * m2;
+  }
+  bf16* ob = dx + (1LL * n * s.HW + p0) * lddx + cv * 8;
+  for (int k = 0; k < q.nchunks; ++k) {
+    const BF8* st = reinterpret_cast<const BF8*>(gns_acquire(q, k));
+    const BF8* sd = reinterpret_cast<const BF8*>(reinterpret_cast<const uint8_t*>(st) + q.chunk_bytes);
+#pragma unroll
+    for (int u = 0; u < GNS_UNROLL; ++u) {
+      const int pl = (k * GNS_UNROLL + u) * R + r;
+      if (pl < npix) {
+        const BF8 vx = st[(u * R + r) * CV + cv], vd = sd[(u * R + r) * CV + cv];
+        BF8 vo, o;
+        if (acc) vo = *reinterpret_cast<const BF8*>(ob + 1LL * pl * lddx);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 xv = __bfloat1622float2(vx.v[i]);
+          const float2 d = gn_dxhat2(xv, __bfloat1622float2(vd.v[i]), kk, i, silu);
+          float2 g = __ffma2_rn(d, make_float2(kk.r[i], kk.r[i]), __ffma2_rn(xv, make_float2(C1[i], C1[i]), make_float2(C2[i], C2[i])));
+          if (acc) g = __fadd2_rn(g, __bfloat1622float2(vo.v[i]));
+          o.v[i] = __floats2bfloat162_rn(g.x, g.y);
+        }
+        *reinterpret_cast<BF8*>(ob + 1LL * pl * lddx) = o;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // =========================================================================== AutoencoderTiny element-wise pieces
 // g = (y > 0) ? g : 0 in place: backward of the ReLU that produced y (applied once y's gradient is complete)
 __global__ void relu_mask_kernel(bf16* __restrict__ g, long long ldg, const bf16* __restrict__ y, long long ldy,
@@ -1341,26 +1599,34 @@ __global__ void __launch_bounds__(XB_THREADS) xattn_block_fwd_kernel(const bf16*
   // ---- B: scores; lane owns the float4 chunks lane, lane + 32, ... of a row (conflict-free shared-memory reads)
   constexpr int K4 = LN_MAXV * 2;
   const int nq = d >> 2;
-  for (int c = warp; c < C; c += NW) {
-    float4 a[K4];
+  for (int c = warp; c < C; c += 2 * NW) {  // two columns per round: both vectors are requested before either is used
+    const int c1 = c + NW;
+    float4 a0[K4], a1[K4];
 #pragma unroll
     for (int k = 0; k < K4; ++k) {
       const int qd = lane + 32 * k;
-      if (qd < nq) a[k] = __ldg(reinterpret_cast<const float4*>(At + 1LL * c * d) + qd);
+      if (qd < nq) {
+        a0[k] = __ldg(reinterpret_cast<const float4*>(At + 1LL * c * d) + qd);
+        a1[k] = __ldg(reinterpret_cast<const float4*>(At + 1LL * min(c1, C - 1) * d) + qd);
+      }
     }
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
-      float sacc = 0.f;
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
       for (int k = 0; k < K4; ++k) {
         const int qd = lane + 32 * k;
         if (qd < nq) {
           const float4 x = reinterpret_cast<const float4*>(n2s + r * d)[qd];
-          sacc += x.x * a[k].x + x.y * a[k].y + x.z * a[k].z + x.w * a[k].w;
+          s0 += x.x * a0[k].x + x.y * a0[k].y + x.z * a0[k].z + x.w * a0[k].w;
+          s1 += x.x * a1[k].x + x.y * a1[k].y + x.z * a1[k].z + x.w * a1[k].w;
         }
       }
-      sacc = warp_sum(sacc);
-      if (lane == 0) Ss[r * XB_LDS + c] = sacc;
+      s0 = warp_sum(s0), s1 = warp_sum(s1);
+      if (lane == 0) {
+        Ss[r * XB_LDS + c] = s0;
+        if (c1 < C) Ss[r * XB_LDS + c1] = s1;
+      }
     }
   }
   __syncthreads();
@@ -1382,11 +1648,22 @@ __global__ void __launch_bounds__(XB_THREADS) xattn_block_fwd_kernel(const bf16*
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(bo + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bo + v * 8 + 4));
       o[0] += b0.x, o[1] += b0.y, o[2] += b0.z, o[3] += b0.w, o[4] += b1.x, o[5] += b1.y, o[6] += b1.z, o[7] += b1.w;
     }
-    for (int c = 0; c < C; ++c) {
-      const float pc = Ss[r * XB_LDS + c];
-      const float4 u0 = __ldg(reinterpret_cast<const float4*>(U + 1LL * c * d + v * 8)), u1 = __ldg(reinterpret_cast<const float4*>(U + 1LL * c * d + v * 8 + 4));
-      o[0] += pc * u0.x, o[1] += pc * u0.y, o[2] += pc * u0.z, o[3] += pc * u0.w;
-      o[4] += pc * u1.x, o[5] += pc * u1.y, o[6] += pc * u1.z, o[7] += pc * u1.w;
+    // 8 columns per round, all 16 loads issued before the first use (L2 latency once per round, not once per column)
+    for (int c = 0; c < C; c += 8) {
+      float4 u[8][2];
+      float pc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int cc = min(c + j, C - 1);
+        pc[j] = c + j < C ? Ss[r * XB_LDS + cc] : 0.f;
+        u[j][0] = __ldg(reinterpret_cast<const float4*>(U + 1LL * cc * d + v * 8));
+        u[j][1] = __ldg(reinterpret_cast<const float4*>(U + 1LL * cc * d + v * 8 + 4));
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[0] += pc[j] * u[j][0].x, o[1] += pc[j] * u[j][0].y, o[2] += pc[j] * u[j][0].z, o[3] += pc[j] * u[j][0].w;
+        o[4] += pc[j] * u[j][1].x, o[5] += pc[j] * u[j][1].y, o[6] += pc[j] * u[j][1].z, o[7] += pc[j] * u[j][1].w;
+      }
     }
     *reinterpret_cast<BF8*>(out + 1LL * row * ldo + v * 8) = f_to_bf8(o);
   }
@@ -1437,30 +1714,40 @@ __global__ void __launch_bounds__(XB_THREADS) xattn_block_bwd_kernel(const bf16*
   }
   __syncthreads();
   // ---- B: S = n2 At^T and dP = dy U^T; lane owns the float4 chunks lane, lane + 32, ... of a row (conflict-free)
-  for (int c = warp; c < C; c += NW) {
-    float4 a[K4], u[K4];
-#pragma unroll
-    for (int k = 0; k < K4; ++k) {
-      const int qd = lane + 32 * k;
-      if (qd < nq) {
-        a[k] = __ldg(reinterpret_cast<const float4*>(At + 1LL * c * d) + qd);
-        u[k] = __ldg(reinterpret_cast<const float4*>(U + 1LL * c * d) + qd);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      float sacc = 0.f, pacc = 0.f;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {  // pass 0: S = n2 At^T, pass 1: dP = dy U^T; two columns per round
+    const float* __restrict__ Mx = pass == 0 ? At : U;
+    const float* __restrict__ rows_s = pass == 0 ? n2s : gs;
+    float* __restrict__ dst = pass == 0 ? Ss : dPs;
+    for (int c = warp; c < C; c += 2 * NW) {
+      const int c1 = c + NW;
+      float4 a0[K4], a1[K4];
 #pragma unroll
       for (int k = 0; k < K4; ++k) {
         const int qd = lane + 32 * k;
         if (qd < nq) {
-          const float4 x = reinterpret_cast<const float4*>(n2s + r * d)[qd], g = reinterpret_cast<const float4*>(gs + r * d)[qd];
-          sacc += x.x * a[k].x + x.y * a[k].y + x.z * a[k].z + x.w * a[k].w;
-          pacc += g.x * u[k].x + g.y * u[k].y + g.z * u[k].z + g.w * u[k].w;
+          a0[k] = __ldg(reinterpret_cast<const float4*>(Mx + 1LL * c * d) + qd);
+          a1[k] = __ldg(reinterpret_cast<const float4*>(Mx + 1LL * min(c1, C - 1) * d) + qd);
         }
       }
-      sacc = warp_sum(sacc), pacc = warp_sum(pacc);
-      if (lane == 0) Ss[r * XB_LDS + c] = sacc, dPs[r * XB_LDS + c] = pacc;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < K4; ++k) {
+          const int qd = lane + 32 * k;
+          if (qd < nq) {
+            const float4 x = reinterpret_cast<const float4*>(rows_s + r * d)[qd];
+            s0 += x.x * a0[k].x + x.y * a0[k].y + x.z * a0[k].z + x.w * a0[k].w;
+            s1 += x.x * a1[k].x + x.y * a1[k].y + x.z * a1[k].z + x.w * a1[k].w;
+          }
+        }
+        s0 = warp_sum(s0), s1 = warp_sum(s1);
+        if (lane == 0) {
+          dst[r * XB_LDS + c] = s0;
+          if (c1 < C) dst[r * XB_LDS + c1] = s1;
+        }
+      }
     }
   }
   __syncthreads();
@@ -1478,10 +1765,17 @@ __global__ void __launch_bounds__(XB_THREADS) xattn_block_bwd_kernel(const bf16*
   for (int item = threadIdx.x; item < RB * nq; item += XB_THREADS) {
     const int r = item / nq, qd = item % nq;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = 0; c < C; ++c) {
-      const float ds = Ss[r * XB_LDS + c];
-      const float4 a0 = __ldg(reinterpret_cast<const float4*>(At + 1LL * c * d) + qd);
-      o.x += ds * a0.x, o.y += ds * a0.y, o.z += ds * a0.z, o.w += ds * a0.w;
+    for (int c = 0; c < C; c += 8) {  // 8 independent L2 loads in flight per round
+      float4 a0[8];
+      float ds[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int cc = min(c + j, C - 1);
+        ds[j] = c + j < C ? Ss[r * XB_LDS + cc] : 0.f;
+        a0[j] = __ldg(reinterpret_cast<const float4*>(At + 1LL * cc * d) + qd);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.x += ds[j] * a0[j].x, o.y += ds[j] * a0[j].y, o.z += ds[j] * a0[j].z, o.w += ds[j] * a0[j].w;
     }
     const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + qd);
     o.x *= gm.x, o.y *= gm.y, o.z *= gm.z, o.w *= gm.w;

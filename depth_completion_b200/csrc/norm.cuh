@@ -27,6 +27,10 @@ constexpr size_t GN_FUSED_SMEM_CAP = 200 * 1024;
 inline void gn_set_attrs() {
   static bool done[64] = {false};
   if (!first_use_on_device(done)) return;
+  MDC_CUDA(cudaFuncSetAttribute(gn_stats_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+  MDC_CUDA(cudaFuncSetAttribute(gn_apply_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+  MDC_CUDA(cudaFuncSetAttribute(gn_bwd_stats_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+  MDC_CUDA(cudaFuncSetAttribute(gn_bwd_apply_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
   MDC_CUDA(cudaFuncSetAttribute(gn_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(GN_FUSED_SMEM_CAP)));
   MDC_CUDA(cudaFuncSetAttribute(gn_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(GN_FUSED_SMEM_CAP)));
 }
@@ -88,9 +92,17 @@ inline void run_gn_fwd(const GNPlan& p, const bf16* x, bf16* y, long long ldy, c
     return;
   }
   const int grid = p.s.N * p.s.blocks_per_img;
-  if (!have_stats)
-    launch_k(gn_stats_kernel, dim3(grid), dim3(p.threads), ((p.threads + 31) / 32) * 2 * p.G * sizeof(float), st, x, p.s, sc.partial, eps, stats,
-             sc.ticket);
+  // streamed variants (bulk-copy fed shared-memory ring) need the block's pixel slab to be contiguous memory
+  static const bool no_stream = getenv("MDC_NO_GNSTREAM") != nullptr;
+  const size_t wsum = ((p.threads + 31) / 32) * 2 * p.G * sizeof(float);
+  if (!no_stream && p.s.ld == p.s.C) {
+    if (!have_stats)
+      launch_k(gn_stats_s_kernel, dim3(grid), dim3(p.threads), gns_smem_bytes(p.threads, 1) + wsum, st, x, p.s, sc.partial, eps, stats, sc.ticket);
+    launch_k(gn_apply_s_kernel, dim3(grid), dim3(p.threads), gns_smem_bytes(p.threads, 1), st, x, p.s, stats, gamma, beta, silu, y, ldy,
+             epi_partial, epi_parts, eps);
+    return;
+  }
+  if (!have_stats) launch_k(gn_stats_kernel, dim3(grid), dim3(p.threads), wsum, st, x, p.s, sc.partial, eps, stats, sc.ticket);
   launch_k(gn_apply_kernel, dim3(grid), dim3(p.threads), 0, st, x, p.s, stats, gamma, beta, silu, y, ldy, epi_partial, epi_parts, eps);
 }
 inline void run_gn_bwd(const GNPlan& p, const bf16* x, const bf16* dy, long long lddy, const float* gamma, const float* beta, int silu,
@@ -101,6 +113,15 @@ inline void run_gn_bwd(const GNPlan& p, const bf16* x, const bf16* dy, long long
     return;
   }
   const int grid = p.s.N * p.s.blocks_per_img;
+  static const bool no_stream = getenv("MDC_NO_GNSTREAM") != nullptr;
+  if (!no_stream && p.s.ld == p.s.C && lddy == p.s.C) {
+    const size_t wsum = ((p.threads_b + 31) / 32) * 2 * p.G * sizeof(float);
+    launch_k(gn_bwd_stats_s_kernel, dim3(grid), dim3(p.threads_b), gns_smem_bytes(p.threads_b, 2) + wsum, st, x, dy, p.s, stats, gamma, beta, silu,
+             sc.partial, sc.gstats, sc.ticket);
+    launch_k(gn_bwd_apply_s_kernel, dim3(grid), dim3(p.threads_b), gns_smem_bytes(p.threads_b, 2), st, x, dy, p.s, stats,
+             static_cast<const float*>(sc.gstats), gamma, beta, silu, dx, lddx, acc);
+    return;
+  }
   launch_k(gn_bwd_stats_kernel, dim3(grid), dim3(p.threads_b), ((p.threads_b + 31) / 32) * 2 * p.G * sizeof(float), st, x, dy, lddy, p.s, stats,
            gamma, beta, silu, sc.partial, sc.gstats, sc.ticket);
   launch_k(gn_bwd_apply_kernel, dim3(grid), dim3(p.threads_b), 0, st, x, dy, lddy, p.s, stats, static_cast<const float*>(sc.gstats), gamma, beta,

@@ -151,4 +151,5 @@ def test_conv3x3_rowshare_speed(cuda):
     gf = 2.0 * 576 * 768 * 9 * 128 * 128 / 1e9
     print(f"[measured] conv 128->128 @576x768: tap-by-tap {out[1][1] * 1e3:.1f} us ({gf / out[1][1]:.0f} TF/s), "
           f"row-shared {out[2][1] * 1e3:.1f} us ({gf / out[2][1]:.0f} TF/s)")
-    assert torch.equal(out[1][0], out[2][0]) or (out[1][0] - out[2][0]).abs().max().item() < 2 ** -6
+    # same products, another summation order: at most a bf16 rounding step apart
+    assert ((out[1][0] - out[2][0]).abs().max() / out[1][0].abs().max()).item() < 2 ** -7

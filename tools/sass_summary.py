@@ -1,0 +1,47 @@
+"""Per-kernel counts of the Blackwell-native SASS mnemonics in the shipped library (B200_PROFILING.md, "What proves a
+Blackwell-native kernel"): UTC*MMA = tcgen05.mma, UTMALDG / UTMASTG = TMA loads / stores, LDTM / STTM = tcgen05.ld / st,
+HMMA = legacy mma.sync (none expected).  Usage: python tools/sass_summary.py > profiles/sass_summary.txt"""
+import collections
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "depth_completion_b200", "lib", "libmdc_b200.so")
+PAT = {"UTC*MMA": re.compile(r"\bUTC[A-Z]*MMA\b"), "UTMALDG": re.compile(r"\bUTMALDG\b"), "UTMASTG": re.compile(r"\bUTMASTG\b"),
+       "LDTM": re.compile(r"\bLDTM\b"), "STTM": re.compile(r"\bSTTM\b"), "HMMA": re.compile(r"\bHMMA\b"),
+       "MUFU": re.compile(r"\bMUFU\b"), "FFMA2": re.compile(r"\bFFMA2\b")}
+
+
+def main():
+    out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
+    counts, order, cur = collections.defaultdict(collections.Counter), [], None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0]
+            cur = cur.replace("mdc::", "").replace("void ", "")
+            if cur not in order:
+                order.append(cur)
+            continue
+        if cur:
+            for k, p in PAT.items():
+                if p.search(line):
+                    counts[cur][k] += 1
+    print(f"# cuobjdump -sass {os.path.relpath(LIB, ROOT)} (sm_100a): instruction counts per kernel")
+    print("| kernel | " + " | ".join(PAT) + " |")
+    print("|---|" + "---|" * len(PAT))
+    for k in order:
+        c = counts[k]
+        if any(c[x] for x in ("UTC*MMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "HMMA")):
+            print(f"| {k} | " + " | ".join(str(c[x]) for x in PAT) + " |")
+    others = [k for k in order if not any(counts[k][x] for x in ("UTC*MMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "HMMA"))]
+    print(f"\n{len(others)} further kernels are bandwidth-bound CUDA-core kernels without tensor / TMA instructions "
+          f"(GroupNorm, LayerNorm, GEGLU, the step tail, ...): " + ", ".join(sorted(set(o.split("<")[0].split("::")[-1] for o in others))))
+    f2 = [k for k in order if counts[k]["FFMA2"]]
+    print("\nkernels using packed fp32x2 FMAs (FFMA2): " + ", ".join(f"{k.split('<')[0]} ({counts[k]['FFMA2']})" for k in f2))
+
+
+if __name__ == "__main__":
+    main()
