@@ -101,12 +101,12 @@ inline void set_kernel_attrs_for_device() {
   MDC_CUDA(cudaFuncSetAttribute(softmax_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   MDC_CUDA(cudaFuncSetAttribute(softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   // collapsed cross-attention: the backward stages three fp32 copies of its rows (<= 8 x 640 or 4 x 1280 channels)
-  MDC_CUDA(cudaFuncSetAttribute(xattn_block_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  MDC_CUDA(cudaFuncSetAttribute(xattn_block_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  MDC_CUDA(cudaFuncSetAttribute(xattn_block_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  MDC_CUDA(cudaFuncSetAttribute(xattn_block_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-  MDC_CUDA(cudaFuncSetAttribute(xattn_block_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-  MDC_CUDA(cudaFuncSetAttribute(xattn_block_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+#define MDC_XB_ATTR(RB, K4)                                                                                                          \
+  MDC_CUDA(cudaFuncSetAttribute(xattn_block_bwd_kernel<RB, K4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
+  MDC_CUDA(cudaFuncSetAttribute(xattn_block_fwd_kernel<RB, K4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  MDC_XB_ATTR(8, 3) MDC_XB_ATTR(8, 5) MDC_XB_ATTR(8, 10) MDC_XB_ATTR(4, 3) MDC_XB_ATTR(4, 5) MDC_XB_ATTR(4, 10)
+  MDC_XB_ATTR(2, 3) MDC_XB_ATTR(2, 5) MDC_XB_ATTR(2, 10)
+#undef MDC_XB_ATTR
 }
 
 inline void run_attention_fwd(const AttnPlan& a, cudaStream_t st) {

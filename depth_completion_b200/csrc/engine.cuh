@@ -252,24 +252,34 @@ struct CrossAttnFusedOp : Op {  // LN2 + attn2 (2 constant key tokens) + to_out 
     const long long rows = x->rows();
     return rows >= 1500 ? 8 : (rows >= 400 ? 4 : 2);
   }
-  template <int RB>
+  template <int RB, int K4>
   void run(cudaStream_t st, bool backward) {
     const int rows = static_cast<int>(x->rows()), d = x->c;
     const dim3 grid(static_cast<unsigned>((rows + RB - 1) / RB)), block(XB_THREADS);
     if (!backward) {
       const size_t smem = (static_cast<size_t>(RB) * d + RB * XB_LDS) * sizeof(float);
-      launch_k(xattn_block_fwd_kernel<RB>, grid, block, smem, st, x->d, x->ld, rows, d, 2 * heads, gamma, beta, At, U, bo, y->d, y->ld, stats);
+      launch_k(xattn_block_fwd_kernel<RB, K4>, grid, block, smem, st, x->d, x->ld, rows, d, 2 * heads, gamma, beta, At, U, bo, y->d, y->ld,
+               stats);
     } else {
       const size_t smem = (3 * static_cast<size_t>(RB) * d + 2 * RB * XB_LDS) * sizeof(float);
-      launch_k(xattn_block_bwd_kernel<RB>, grid, block, smem, st, x->d, x->ld, y->g, y->ld, rows, d, 2 * heads, gamma, beta, At, U,
+      launch_k(xattn_block_bwd_kernel<RB, K4>, grid, block, smem, st, x->d, x->ld, y->g, y->ld, rows, d, 2 * heads, gamma, beta, At, U,
                static_cast<const float*>(stats), x->g, x->ld, static_cast<int>(acc));
     }
   }
+  template <int RB>
+  void run_k(cudaStream_t st, bool backward) {  // loop bounds sized for the width class: d <= 384 / 640 / 1280
+    if (x->c <= 384)
+      run<RB, 3>(st, backward);
+    else if (x->c <= 640)
+      run<RB, 5>(st, backward);
+    else
+      run<RB, 10>(st, backward);
+  }
   void dispatch(cudaStream_t st, bool backward) {
     switch (rows_per_block()) {
-      case 8: run<8>(st, backward); break;
-      case 4: run<4>(st, backward); break;
-      default: run<2>(st, backward); break;
+      case 8: run_k<8>(st, backward); break;
+      case 4: run_k<4>(st, backward); break;
+      default: run_k<2>(st, backward); break;
     }
   }
   void fwd(cudaStream_t st) override { dispatch(st, false); }

@@ -1526,15 +1526,71 @@ __global__ void xattn_fused_bwd_kernel(const bf16* __restrict__ h, long long ldh
 // length d behind L2-latency loads, which is slow exactly where tokens are few (9x12 ... 18x24 maps, d = 1280, 2H = 40).
 // Here a 256-thread CTA owns RB tokens and every phase is spread over all of its warps:
 //   A  LayerNorm of the RB rows (warp per row)                              -> shared memory
-//   B  scores S[r][c] = n2[r] . At[c]: warp per column c, At[c] held in registers across the rows
+//   B  scores S[r][c] = n2[r] . At[c]: a warp takes two columns per round, their At rows held in registers across the
+//      RB rows; the 2 RB partial sums of a lane are reduced with ONE butterfly (2 RB + 4 shuffles instead of 10 RB)
 //   C  pairwise softmax over the 2 key tokens of each head (thread per (row, head))
-//   D  out[r] = h[r] + bo + sum_c P[r][c] U[c]: thread per (row, 8-channel vector)
+//   D  out[r] = h[r] + bo + sum_c P[r][c] U[c]: thread per 8-channel vector, all RB rows (U is read once per CTA)
 // Backward recomputes n2 / S / P from h and the saved LayerNorm statistics, then
 //   dP = dy U^T (as B),  dS = softmax-bwd(P, dP),  dn = dS At (as D),  dh = dy + LayerNorm-bwd(dn).
+// K4 = float4 chunks per lane and row (d <= 128 K4): the loops are sized for the width class instead of predicated --
+// ncu on the first version (every loop sized for d = 1280): 13.5 M warp instructions for 6912 x 320 tokens, issue bound.
 constexpr int XB_THREADS = 256;
 constexpr int XB_LDS = XA_MAXC + 1;  // row stride of the small score arrays in shared memory
 
-template <int RB>
+// Sum each of the NVAL per-lane values over the 32 lanes; afterwards lane l holds the total of value (l >> (5 - log2 NVAL)).
+template <int NVAL>
+__device__ __forceinline__ float warp_multi_sum(float (&v)[NVAL], int lane) {
+  int o = 16;
+#pragma unroll
+  for (int half = NVAL / 2; half >= 1; half /= 2, o /= 2) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half], keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  float t = v[0];
+  for (; o >= 1; o /= 2) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+// S[r][c], S[r][c1] for r < RB from rows_s [RB][d] (shared) and the matrix rows Mx[c], Mx[c1] (global, L2 / L1)
+template <int RB, int K4>
+__device__ __forceinline__ void xb_two_columns(const float* __restrict__ rows_s, const float* __restrict__ Mx, int d, int nq, int c, int c1,
+                                               int C, int lane, float* __restrict__ dst) {
+  float4 a0[K4], a1[K4];
+#pragma unroll
+  for (int k = 0; k < K4; ++k) {
+    const int qd = lane + 32 * k;
+    if (qd < nq) {
+      a0[k] = __ldg(reinterpret_cast<const float4*>(Mx + 1LL * c * d) + qd);
+      a1[k] = __ldg(reinterpret_cast<const float4*>(Mx + 1LL * min(c1, C - 1) * d) + qd);
+    } else {
+      a0[k] = a1[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  float v[2 * RB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < K4; ++k) {
+      const int qd = min(lane + 32 * k, nq - 1);  // (lanes past the row read a valid address; their a0 / a1 are zero)
+      const float4 x = reinterpret_cast<const float4*>(rows_s + r * d)[qd];
+      s0 += x.x * a0[k].x + x.y * a0[k].y + x.z * a0[k].z + x.w * a0[k].w;
+      s1 += x.x * a1[k].x + x.y * a1[k].y + x.z * a1[k].z + x.w * a1[k].w;
+    }
+    v[2 * r] = s0, v[2 * r + 1] = s1;
+  }
+  const float tot = warp_multi_sum<2 * RB>(v, lane);
+  constexpr int SH = (RB == 8 ? 1 : (RB == 4 ? 2 : 3));  // lane l holds value l >> SH
+  if ((lane & ((1 << SH) - 1)) == 0) {
+    const int idx = lane >> SH, r = idx >> 1, cc = (idx & 1) ? c1 : c;
+    if (cc < C) dst[r * XB_LDS + cc] = tot;
+  }
+}
+
+template <int RB, int K4>
 __global__ void __launch_bounds__(XB_THREADS) xattn_block_fwd_kernel(const bf16* __restrict__ h, long long ldh, int rows, int d, int C,
                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                      const float* __restrict__ At, const float* __restrict__ U,
@@ -1546,15 +1602,15 @@ __global__ void __launch_bounds__(XB_THREADS) xattn_block_fwd_kernel(const bf16*
   float* n2s = xb_smem;            // [RB][d]
   float* Ss = xb_smem + RB * d;    // [RB][XB_LDS]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int NW = XB_THREADS / 32;
-  const int row0 = blockIdx.x * RB, nv = d >> 3;
+  constexpr int NW = XB_THREADS / 32, NV = (K4 + 1) / 2;
+  const int row0 = blockIdx.x * RB, nv = d >> 3, nq = d >> 2;
   // ---- A: LayerNorm (eps 1e-5), rounded to bf16 like the reference's bf16 LayerNorm output
   for (int r = warp; r < RB; r += NW) {
     const int row = row0 + r;
-    float f[LN_MAXV][8];
+    float f[NV][8];
     float sum = 0.f;
 #pragma unroll
-    for (int k = 0; k < LN_MAXV; ++k) {
+    for (int k = 0; k < NV; ++k) {
       const int v = lane + 32 * k;
       if (v < nv && row < rows) {
         bf8_to_f(*reinterpret_cast<const BF8*>(h + 1LL * row * ldh + v * 8), f[k]);
@@ -1568,7 +1624,7 @@ __global__ void __launch_bounds__(XB_THREADS) xattn_block_fwd_kernel(const bf16*
     const float mean = warp_sum(sum) / d;
     float q = 0.f;
 #pragma unroll
-    for (int k = 0; k < LN_MAXV; ++k) {
+    for (int k = 0; k < NV; ++k) {
       const int v = lane + 32 * k;
       if (v < nv) {
 #pragma unroll
@@ -1581,7 +1637,7 @@ __global__ void __launch_bounds__(XB_THREADS) xattn_block_fwd_kernel(const bf16*
     const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
     if (lane == 0 && row < rows) stats[2LL * row] = mean, stats[2LL * row + 1] = rstd;
 #pragma unroll
-    for (int k = 0; k < LN_MAXV; ++k) {
+    for (int k = 0; k < NV; ++k) {
       const int v = lane + 32 * k;
       if (v < nv) {
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
@@ -1589,46 +1645,15 @@ __global__ void __launch_bounds__(XB_THREADS) xattn_block_fwd_kernel(const bf16*
         const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = bf16r((f[k][i] - mean) * rstd * ga[i] + be[i]);
+        for (int i = 0; i < 8; ++i) o[i] = row < rows ? bf16r((f[k][i] - mean) * rstd * ga[i] + be[i]) : 0.f;
         float4* dst = reinterpret_cast<float4*>(n2s + r * d + v * 8);
         dst[0] = make_float4(o[0], o[1], o[2], o[3]), dst[1] = make_float4(o[4], o[5], o[6], o[7]);
       }
     }
   }
   __syncthreads();
-  // ---- B: scores; lane owns the float4 chunks lane, lane + 32, ... of a row (conflict-free shared-memory reads)
-  constexpr int K4 = LN_MAXV * 2;
-  const int nq = d >> 2;
-  for (int c = warp; c < C; c += 2 * NW) {  // two columns per round: both vectors are requested before either is used
-    const int c1 = c + NW;
-    float4 a0[K4], a1[K4];
-#pragma unroll
-    for (int k = 0; k < K4; ++k) {
-      const int qd = lane + 32 * k;
-      if (qd < nq) {
-        a0[k] = __ldg(reinterpret_cast<const float4*>(At + 1LL * c * d) + qd);
-        a1[k] = __ldg(reinterpret_cast<const float4*>(At + 1LL * min(c1, C - 1) * d) + qd);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-      for (int k = 0; k < K4; ++k) {
-        const int qd = lane + 32 * k;
-        if (qd < nq) {
-          const float4 x = reinterpret_cast<const float4*>(n2s + r * d)[qd];
-          s0 += x.x * a0[k].x + x.y * a0[k].y + x.z * a0[k].z + x.w * a0[k].w;
-          s1 += x.x * a1[k].x + x.y * a1[k].y + x.z * a1[k].z + x.w * a1[k].w;
-        }
-      }
-      s0 = warp_sum(s0), s1 = warp_sum(s1);
-      if (lane == 0) {
-        Ss[r * XB_LDS + c] = s0;
-        if (c1 < C) Ss[r * XB_LDS + c1] = s1;
-      }
-    }
-  }
+  // ---- B: scores
+  for (int c = warp; c < C; c += 2 * NW) xb_two_columns<RB, K4>(n2s, At, d, nq, c, c + NW, C, lane, Ss);
   __syncthreads();
   // ---- C: softmax over the two key tokens of each head
   for (int t = threadIdx.x; t < RB * (C >> 1); t += XB_THREADS) {
@@ -1638,38 +1663,39 @@ __global__ void __launch_bounds__(XB_THREADS) xattn_block_fwd_kernel(const bf16*
     Ss[r * XB_LDS + 2 * hd] = e0 * inv, Ss[r * XB_LDS + 2 * hd + 1] = e1 * inv;
   }
   __syncthreads();
-  // ---- D: output rows
-  for (int item = threadIdx.x; item < RB * nv; item += XB_THREADS) {
-    const int r = item / nv, v = item % nv, row = row0 + r;
-    if (row >= rows) continue;
-    float o[8];
-    bf8_to_f(*reinterpret_cast<const BF8*>(h + 1LL * row * ldh + v * 8), o);
+  // ---- D: output rows; a thread owns one 8-channel vector of ALL RB rows, so U crosses L2 -> SM once per CTA
+  for (int v = threadIdx.x; v < nv; v += XB_THREADS) {
+    float o[RB][8];
     {
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(bo + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bo + v * 8 + 4));
-      o[0] += b0.x, o[1] += b0.y, o[2] += b0.z, o[3] += b0.w, o[4] += b1.x, o[5] += b1.y, o[6] += b1.z, o[7] += b1.w;
-    }
-    // 8 columns per round, all 16 loads issued before the first use (L2 latency once per round, not once per column)
-    for (int c = 0; c < C; c += 8) {
-      float4 u[8][2];
-      float pc[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int cc = min(c + j, C - 1);
-        pc[j] = c + j < C ? Ss[r * XB_LDS + cc] : 0.f;
-        u[j][0] = __ldg(reinterpret_cast<const float4*>(U + 1LL * cc * d + v * 8));
-        u[j][1] = __ldg(reinterpret_cast<const float4*>(U + 1LL * cc * d + v * 8 + 4));
-      }
+      for (int r = 0; r < RB; ++r) {
+        if (row0 + r < rows) {
+          bf8_to_f(*reinterpret_cast<const BF8*>(h + 1LL * (row0 + r) * ldh + v * 8), o[r]);
+        } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        o[0] += pc[j] * u[j][0].x, o[1] += pc[j] * u[j][0].y, o[2] += pc[j] * u[j][0].z, o[3] += pc[j] * u[j][0].w;
-        o[4] += pc[j] * u[j][1].x, o[5] += pc[j] * u[j][1].y, o[6] += pc[j] * u[j][1].z, o[7] += pc[j] * u[j][1].w;
+          for (int i = 0; i < 8; ++i) o[r][i] = 0.f;
+        }
+        o[r][0] += b0.x, o[r][1] += b0.y, o[r][2] += b0.z, o[r][3] += b0.w, o[r][4] += b1.x, o[r][5] += b1.y, o[r][6] += b1.z, o[r][7] += b1.w;
       }
     }
-    *reinterpret_cast<BF8*>(out + 1LL * row * ldo + v * 8) = f_to_bf8(o);
+#pragma unroll 5
+    for (int c = 0; c < C; ++c) {
+      const float4 u0 = __ldg(reinterpret_cast<const float4*>(U + 1LL * c * d + v * 8)), u1 = __ldg(reinterpret_cast<const float4*>(U + 1LL * c * d + v * 8 + 4));
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const float pc = Ss[r * XB_LDS + c];
+        o[r][0] += pc * u0.x, o[r][1] += pc * u0.y, o[r][2] += pc * u0.z, o[r][3] += pc * u0.w;
+        o[r][4] += pc * u1.x, o[r][5] += pc * u1.y, o[r][6] += pc * u1.z, o[r][7] += pc * u1.w;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+      if (row0 + r < rows) *reinterpret_cast<BF8*>(out + 1LL * (row0 + r) * ldo + v * 8) = f_to_bf8(o[r]);
   }
 }
 
-template <int RB>
+template <int RB, int K4>
 __global__ void __launch_bounds__(XB_THREADS) xattn_block_bwd_kernel(const bf16* __restrict__ h, long long ldh, const bf16* __restrict__ dy,
                                                                      long long lddy, int rows, int d, int C,
                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -1686,7 +1712,6 @@ __global__ void __launch_bounds__(XB_THREADS) xattn_block_bwd_kernel(const bf16*
   float* dPs = Ss + RB * XB_LDS;        // [RB][XB_LDS]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NW = XB_THREADS / 32;
-  constexpr int K4 = LN_MAXV * 2;       // float4 chunks per lane (d <= 1280)
   const int row0 = blockIdx.x * RB, nv = d >> 3, nq = d >> 2;
   // ---- A: stage xh, n2 and dy
   for (int item = threadIdx.x; item < RB * nv; item += XB_THREADS) {
@@ -1713,43 +1738,9 @@ __global__ void __launch_bounds__(XB_THREADS) xattn_block_bwd_kernel(const bf16*
     dn[0] = make_float4(n2[0], n2[1], n2[2], n2[3]), dn[1] = make_float4(n2[4], n2[5], n2[6], n2[7]);
   }
   __syncthreads();
-  // ---- B: S = n2 At^T and dP = dy U^T; lane owns the float4 chunks lane, lane + 32, ... of a row (conflict-free)
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {  // pass 0: S = n2 At^T, pass 1: dP = dy U^T; two columns per round
-    const float* __restrict__ Mx = pass == 0 ? At : U;
-    const float* __restrict__ rows_s = pass == 0 ? n2s : gs;
-    float* __restrict__ dst = pass == 0 ? Ss : dPs;
-    for (int c = warp; c < C; c += 2 * NW) {
-      const int c1 = c + NW;
-      float4 a0[K4], a1[K4];
-#pragma unroll
-      for (int k = 0; k < K4; ++k) {
-        const int qd = lane + 32 * k;
-        if (qd < nq) {
-          a0[k] = __ldg(reinterpret_cast<const float4*>(Mx + 1LL * c * d) + qd);
-          a1[k] = __ldg(reinterpret_cast<const float4*>(Mx + 1LL * min(c1, C - 1) * d) + qd);
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int k = 0; k < K4; ++k) {
-          const int qd = lane + 32 * k;
-          if (qd < nq) {
-            const float4 x = reinterpret_cast<const float4*>(rows_s + r * d)[qd];
-            s0 += x.x * a0[k].x + x.y * a0[k].y + x.z * a0[k].z + x.w * a0[k].w;
-            s1 += x.x * a1[k].x + x.y * a1[k].y + x.z * a1[k].z + x.w * a1[k].w;
-          }
-        }
-        s0 = warp_sum(s0), s1 = warp_sum(s1);
-        if (lane == 0) {
-          dst[r * XB_LDS + c] = s0;
-          if (c1 < C) dst[r * XB_LDS + c1] = s1;
-        }
-      }
-    }
-  }
+  // ---- B: S = n2 At^T and dP = dy U^T
+  for (int c = warp; c < C; c += 2 * NW) xb_two_columns<RB, K4>(n2s, At, d, nq, c, c + NW, C, lane, Ss);
+  for (int c = warp; c < C; c += 2 * NW) xb_two_columns<RB, K4>(gs, U, d, nq, c, c + NW, C, lane, dPs);
   __syncthreads();
   // ---- C: dS of the pairwise softmax (in place over S)
   for (int t = threadIdx.x; t < RB * (C >> 1); t += XB_THREADS) {
@@ -1761,25 +1752,30 @@ __global__ void __launch_bounds__(XB_THREADS) xattn_block_bwd_kernel(const bf16*
     Ss[r * XB_LDS + 2 * hd] = p0 * (dp0 - dot), Ss[r * XB_LDS + 2 * hd + 1] = p1 * (dp1 - dot);
   }
   __syncthreads();
-  // ---- D: dn gamma = (dS At) gamma, over n2's storage (dead by now)
-  for (int item = threadIdx.x; item < RB * nq; item += XB_THREADS) {
-    const int r = item / nq, qd = item % nq;
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = 0; c < C; c += 8) {  // 8 independent L2 loads in flight per round
-      float4 a0[8];
-      float ds[8];
+  // ---- D: dn gamma = (dS At) gamma over n2's storage (dead by now); a thread owns one 8-channel vector of all rows
+  for (int v = threadIdx.x; v < nv; v += XB_THREADS) {
+    float o[RB][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int cc = min(c + j, C - 1);
-        ds[j] = c + j < C ? Ss[r * XB_LDS + cc] : 0.f;
-        a0[j] = __ldg(reinterpret_cast<const float4*>(At + 1LL * cc * d) + qd);
+    for (int r = 0; r < RB; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[r][i] = 0.f;
+#pragma unroll 5
+    for (int c = 0; c < C; ++c) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(At + 1LL * c * d + v * 8)), a1 = __ldg(reinterpret_cast<const float4*>(At + 1LL * c * d + v * 8 + 4));
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const float ds = Ss[r * XB_LDS + c];
+        o[r][0] += ds * a0.x, o[r][1] += ds * a0.y, o[r][2] += ds * a0.z, o[r][3] += ds * a0.w;
+        o[r][4] += ds * a1.x, o[r][5] += ds * a1.y, o[r][6] += ds * a1.z, o[r][7] += ds * a1.w;
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o.x += ds[j] * a0[j].x, o.y += ds[j] * a0[j].y, o.z += ds[j] * a0[j].z, o.w += ds[j] * a0[j].w;
     }
-    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + qd);
-    o.x *= gm.x, o.y *= gm.y, o.z *= gm.z, o.w *= gm.w;
-    reinterpret_cast<float4*>(n2s + r * d)[qd] = o;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      float4* dst = reinterpret_cast<float4*>(n2s + r * d + v * 8);
+      dst[0] = make_float4(o[r][0] * g0.x, o[r][1] * g0.y, o[r][2] * g0.z, o[r][3] * g0.w);
+      dst[1] = make_float4(o[r][4] * g1.x, o[r][5] * g1.y, o[r][6] * g1.z, o[r][7] * g1.w);
+    }
   }
   __syncthreads();
   // ---- E: LayerNorm backward per row, plus the residual path (dh = dy + ...)
@@ -1788,9 +1784,10 @@ __global__ void __launch_bounds__(XB_THREADS) xattn_block_bwd_kernel(const bf16*
     if (row >= rows) continue;
     const float rstd = stats[2LL * row + 1];
     float a = 0.f, b = 0.f;
-    for (int e = lane; e < d; e += 32) {
-      const float t = n2s[r * d + e];
-      a += t, b += t * xhs[r * d + e];
+    for (int qd = lane; qd < nq; qd += 32) {
+      const float4 t = reinterpret_cast<const float4*>(n2s + r * d)[qd], xh = reinterpret_cast<const float4*>(xhs + r * d)[qd];
+      a += t.x + t.y + t.z + t.w;
+      b += t.x * xh.x + t.y * xh.y + t.z * xh.z + t.w * xh.w;
     }
     a = warp_sum(a) / d, b = warp_sum(b) / d;
     for (int qd = lane; qd < nq; qd += 32) {  // 4 channels per lane and pass: 8-byte bf16 stores
