@@ -28,7 +28,7 @@ class MdcConfig(C.Structure):
         ("vae_nblocks", C.c_int), ("vae_layers_per_block", C.c_int), ("vae_groups", C.c_int),
         ("vae_latent_ch", C.c_int), ("vae_block_ch", C.c_int * MAX_BLOCKS), ("vae_scaling", C.c_float),
         ("vae_kind", C.c_int), ("tiny_enc_blocks", C.c_int * MAX_BLOCKS), ("tiny_dec_blocks", C.c_int * MAX_BLOCKS),
-        ("tiny_magnitude", C.c_float),
+        ("tiny_magnitude", C.c_float), ("concurrent", C.c_int),
     ]
 
 
@@ -90,7 +90,8 @@ class StepEngine:
     """Owns one mdc_handle: the UNet + VAE-decoder tapes and workspace for fixed (N, H, W, resolution, steps)."""
 
     def __init__(self, unet_cfg: UNetConfig, vae_cfg: VAEConfig, n_batch: int, height: int, width: int,
-                 resolution: int, steps: int, device: torch.device | int = 0, share_weights_with: "StepEngine | None" = None):
+                 resolution: int, steps: int, device: torch.device | int = 0, share_weights_with: "StepEngine | None" = None,
+                 concurrent: bool = False):
         """share_weights_with: another live engine of the same model on the same device whose packed parameters this
         engine reuses (mdc_create_shared) -- a new frame geometry then costs workspace only, no re-packing."""
         self._h = C.c_void_p(0)
@@ -125,6 +126,7 @@ class StepEngine:
             for i, (ne, nd) in enumerate(zip(vae_cfg.num_encoder_blocks, vae_cfg.num_decoder_blocks)):
                 c.tiny_enc_blocks[i], c.tiny_dec_blocks[i] = ne, nd
             c.tiny_magnitude = vae_cfg.latent_magnitude
+        c.concurrent = int(bool(concurrent))  # several handles in flight on one GPU: no grid-barrier kernels (mdc.h)
         with torch.cuda.device(dev):
             if share_weights_with is not None:
                 check(self.lib.mdc_create_shared(C.byref(c), share_weights_with._h, C.byref(self._h)))

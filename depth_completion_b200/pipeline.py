@@ -187,11 +187,11 @@ class MarigoldDepthCompletionPipeline:
         ph, pw, pad_h, pad_w = processed_geometry(H, W, resolution)
         return ref.device_bytes() * (N * (ph + pad_h) * (pw + pad_w)) / max(1, ref.n * ref.lh * ref.lw * 64)
 
-    def _engine(self, N, H, W, resolution, steps) -> StepEngine:
+    def _engine(self, N, H, W, resolution, steps, slot: int = 0, concurrent: bool = False) -> StepEngine:
         """One StepEngine per call geometry, kept resident (LRU) and all sharing ONE set of packed weights: a sequence
         whose last batch is short, or alternating resolutions, builds workspace for the new shape but never re-packs the
         parameters (the reference serves every shape from one set of modules, predict.py:585-700)."""
-        key = (N, H, W, resolution, steps, str(self.device))
+        key = (N, H, W, resolution, steps, str(self.device), slot, bool(concurrent))
         eng = self._engines.pop(key, None)
         if eng is None:
             if self.device.type != "cuda":
@@ -213,7 +213,8 @@ class MarigoldDepthCompletionPipeline:
                 else:
                     old.close()
             donor = self._keeper or (list(self._engines.values())[-1] if self._engines else None)
-            eng = StepEngine(self.unet_cfg, self.vae_cfg, N, H, W, resolution, steps, self.device, share_weights_with=donor)
+            eng = StepEngine(self.unet_cfg, self.vae_cfg, N, H, W, resolution, steps, self.device, share_weights_with=donor,
+                             concurrent=concurrent)
             if not eng.weights_loaded():
                 usd, vsd, _ = self._state_dicts()
                 eng.load_weights(usd, vsd, only_missing=donor is not None)
@@ -228,6 +229,24 @@ class MarigoldDepthCompletionPipeline:
                  closed_form=None, opt="adam", lr=None, kld=False, kld_weight=0.1, kld_mode="simple",
                  interp_mode="bilinear", loss_funcs=None, seed=2024, train_latents=True, train_method="per-step",
                  train_steps=10, _begin_only=False):
+        """The reference call (marigold_dc.py:467-493): `submit` enqueues the prologue and the guided steps on the current
+        CUDA stream, `collect` decodes and synchronises."""
+        ticket = self.submit(imgs, sparses, max_depth, min_depth, projection, inv, norm, percentile, pred_latents_prev, beta, steps,
+                             resolution, closed_form, opt, lr, kld, kld_weight, kld_mode, interp_mode, loss_funcs, seed, train_latents,
+                             train_method, train_steps, _begin_only=_begin_only)
+        if _begin_only:  # bench.py / tests: leave the engine at step 0 with everything resident in HBM
+            return None, None
+        return self.collect(ticket)
+
+    def submit(self, imgs, sparses, max_depth, min_depth=0.0, projection="linear", inv=False, norm="minmax",
+               percentile=(0.01, 0.99), pred_latents_prev=None, beta=0.9, steps=50, resolution=768,
+               closed_form=None, opt="adam", lr=None, kld=False, kld_weight=0.1, kld_mode="simple",
+               interp_mode="bilinear", loss_funcs=None, seed=2024, train_latents=True, train_method="per-step",
+               train_steps=10, _begin_only=False, _slot=0, _concurrent=False):
+        """First half of the call: argument validation, per-frame prologue and all guided steps, enqueued on the current
+        CUDA stream without waiting for them (only the prologue's empty-mask check synchronises, a few ms in).  `_slot`
+        selects one of several engines of the same geometry so that frames on different streams can be in flight at once
+        (video.complete_sequence(frames_in_flight=...)); returns a ticket for `collect`."""
         # --- argument validation, same order and conditions as marigold_dc.py:583-656
         if (imgs.ndim != 4 or sparses.ndim != 4 or imgs.shape[0] != sparses.shape[0]
                 or imgs.shape[-2:] != sparses.shape[-2:]):
@@ -291,7 +310,7 @@ class MarigoldDepthCompletionPipeline:
 
         dev = self.device
         imgs, sparses = imgs.to(dev), sparses.to(dev)
-        eng = self._engine(N, H, W, resolution, steps)
+        eng = self._engine(N, H, W, resolution, steps, _slot, _concurrent)
         with torch.no_grad():
             # marigold_dc.py:661, :677-684 -- first draw of the seeded generator, in the pipeline dtype
             gen = torch.Generator(device=dev).manual_seed(seed)
@@ -306,14 +325,18 @@ class MarigoldDepthCompletionPipeline:
                         percentile if norm == "percentile" else (0.01, 0.99), closed_form=bool(closed_form and train_latents),
                         interp_mode=interp_mode)
         eng.begin_frame(imgs, sparses, x, max_depth, min_depth, norm, lr_latent, lr_scaling)
-        if _begin_only:  # bench.py: leave the engine at step 0 with everything resident in HBM
-            return None, None
-        if train_latents:
-            eng.run(steps)                   # marigold_dc.py:799-904, no host sync inside
-            denses = eng.decode_final(closed_form=bool(closed_form))  # marigold_dc.py:970-984
-        else:                                # no-grad branch: plain DDIM sampling + closed-form affine (:905-909, :53-128)
-            eng.sample(steps)
-            denses = eng.decode_final(closed_form=True)
+        if not _begin_only:
+            if train_latents:
+                eng.run(steps)               # marigold_dc.py:799-904, asynchronous, no host sync inside
+            else:                            # no-grad branch: plain DDIM sampling (:905-909)
+                eng.sample(steps)
+        return dict(eng=eng, closed_form=bool(closed_form) if train_latents else True)
+
+    def collect(self, ticket):
+        """Second half of the call, on the stream `submit` ran on: final decode + de-normalisation (marigold_dc.py:970-984)
+        and the returned latents; synchronises that stream."""
+        eng = ticket["eng"]
+        denses = eng.decode_final(closed_form=ticket["closed_form"])
         x_out, scales, shifts, losses = eng.get_state()
         self.last_scales, self.last_shifts, self.last_losses = scales, shifts, losses
         return denses, x_out

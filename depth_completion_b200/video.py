@@ -32,15 +32,28 @@ def sequence_batches(n_frames: int, batch_size: int, use_prev_latent: bool, rank
 
 
 def complete_sequence(pipe, imgs: torch.Tensor, sparses: torch.Tensor, max_depth: float, *, batch_size: int = 1,
-                      use_prev_latent: bool = False, beta: float = 0.9, rank: int = 0, world: int = 1, **pipe_kwargs):
+                      use_prev_latent: bool = False, beta: float = 0.9, rank: int = 0, world: int = 1,
+                      frames_in_flight: int = 1, **pipe_kwargs):
     """Runs `pipe` over imgs [F,C,H,W] / sparses [F,1,H,W]; returns (denses of this rank's frames [f,1,H,W] fp32,
-    their (start, stop) frame range, last pred_latents)."""
+    their (start, stop) frame range, last pred_latents).
+
+    frames_in_flight > 1 (independent frames only) keeps that many pipeline calls in flight on separate CUDA streams,
+    each on its own engine (shared weights): call k+1's prologue -- H2D copies, image preprocessing, VAE encoder -- and
+    its guided steps overlap call k's loop, whose batch-1 UNet layers leave most SMs idle.  This is a throughput mode:
+    a frame's latency grows, frames per second go up."""
     if imgs.shape[0] != sparses.shape[0]:
         raise ValueError(f"{imgs.shape[0]} images vs {sparses.shape[0]} sparse maps")
     if use_prev_latent and batch_size > 1:
         warnings.warn("batch_size is forced to 1 when use_prev_latent=True (predict.py:423-430)")
+    if frames_in_flight < 1:
+        raise ValueError(f"frames_in_flight={frames_in_flight}")
+    if frames_in_flight > 1 and use_prev_latent:
+        raise ValueError("use_prev_latent chains every frame on the previous one (predict.py:697-699): nothing can be in flight "
+                         "besides the current frame; use complete_sequences for several independent sequences")
     plan = sequence_batches(imgs.shape[0], batch_size, use_prev_latent, rank, world)
-    outs, prev = [], None
+    outs, prev, lat = [], None, None
+    if frames_in_flight > 1 and plan:
+        return _complete_in_flight(pipe, imgs, sparses, max_depth, plan, frames_in_flight, pipe_kwargs)
     for s, e in plan:
         dense, lat = pipe(imgs[s:e], sparses[s:e], max_depth, pred_latents_prev=prev if use_prev_latent else None, beta=beta,
                           **pipe_kwargs)
@@ -50,3 +63,57 @@ def complete_sequence(pipe, imgs: torch.Tensor, sparses: torch.Tensor, max_depth
     rng = (plan[0][0], plan[-1][1]) if plan else (0, 0)
     dense_all = torch.cat(outs, 0) if outs else torch.empty(0, 1, *imgs.shape[-2:])
     return dense_all, rng, (lat if plan else None)
+
+
+def _complete_in_flight(pipe, imgs, sparses, max_depth, plan, k, pipe_kwargs):
+    """`k` calls in flight, round robin over `k` engine slots and CUDA streams (submit / collect halves of the call)."""
+    dev = pipe.device
+    streams = [torch.cuda.Stream(device=dev) for _ in range(k)]
+    start = torch.cuda.Event()
+    start.record(torch.cuda.current_stream(dev))
+    tickets, outs, lat = {}, [None] * len(plan), None
+
+    def collect(i):
+        nonlocal lat
+        with torch.cuda.stream(streams[i % k]):
+            outs[i], lat = pipe.collect(tickets.pop(i))
+
+    for i, (s, e) in enumerate(plan):
+        if i - k in tickets:
+            collect(i - k)  # frees slot i % k; the other slots keep the GPU busy meanwhile
+        st = streams[i % k]
+        st.wait_event(start)  # inputs produced on the caller's stream before this call
+        with torch.cuda.stream(st):
+            tickets[i] = pipe.submit(imgs[s:e], sparses[s:e], max_depth, _slot=i % k, _concurrent=True, **pipe_kwargs)
+    for i in sorted(tickets):
+        collect(i)
+    cur = torch.cuda.current_stream(dev)
+    for st in streams:
+        cur.wait_stream(st)
+    rng = (plan[0][0], plan[-1][1])
+    return torch.cat(outs, 0), rng, lat
+
+
+def complete_sequences(pipe, imgs: torch.Tensor, sparses: torch.Tensor, max_depth: float, *, beta: float = 0.9, rank: int = 0,
+                       world: int = 1, seq_batch: int | None = None, **pipe_kwargs):
+    """Temporal prior WITHOUT the reference's batch-1 restriction (predict.py:423-430): S independent sequences (cameras,
+    clips) of F frames each, imgs [S,F,C,H,W] / sparses [S,F,1,H,W].  Frame k of `seq_batch` sequences goes through ONE
+    batched call whose `pred_latents_prev` holds every sequence's own previous latent (marigold_dc.py:598-603, :699-704 blend
+    per sample), so each sequence is the same serial chain the reference runs, and the batch dimension carries sequences
+    instead of consecutive frames.  Sequences are sharded over the ranks (they are independent); returns (denses
+    [s,F,1,H,W] of this rank's sequences, their (start, stop) sequence range)."""
+    if imgs.ndim != 5 or sparses.ndim != 5 or imgs.shape[:2] != sparses.shape[:2]:
+        raise ValueError(f"expected imgs [S,F,C,H,W] and sparses [S,F,1,H,W], got {tuple(imgs.shape)} and {tuple(sparses.shape)}")
+    S, Fr = imgs.shape[:2]
+    mine = shard_frames(S, rank, world)
+    seq_batch = seq_batch or max(1, len(mine))
+    outs = []
+    for b0 in range(mine.start, mine.stop, seq_batch):
+        b1 = min(b0 + seq_batch, mine.stop)
+        prev, per_frame = None, []
+        for f in range(Fr):
+            dense, prev = pipe(imgs[b0:b1, f], sparses[b0:b1, f], max_depth, pred_latents_prev=prev, beta=beta, **pipe_kwargs)
+            per_frame.append(dense)
+        outs.append(torch.stack(per_frame, 1))
+    dense_all = torch.cat(outs, 0) if outs else torch.empty(0, Fr, 1, *imgs.shape[-2:])
+    return dense_all, (mine.start, mine.stop)

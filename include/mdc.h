@@ -52,6 +52,10 @@ typedef struct mdc_config {
   int tiny_enc_blocks[MDC_MAX_BLOCKS];
   int tiny_dec_blocks[MDC_MAX_BLOCKS];
   float tiny_magnitude;
+  /* != 0: this handle will run CONCURRENTLY with other handles on the same GPU (several frames in flight on separate
+   * streams).  Kernels that need all of their CTAs co-resident -- the single-launch GroupNorm with its grid barrier -- are
+   * then replaced by their two-pass forms, because two such kernels from different streams can starve each other. */
+  int concurrent;
 } mdc_config;
 
 typedef struct mdc_handle mdc_handle;

@@ -276,3 +276,113 @@ def test_dataset_front_end_on_the_gpu(models, cuda, tmp_path):
     stored = torch.from_numpy(dio.load_dense(dst / "seq" / "dense" / "0002.npz")).to(cuda)
     assert stored.shape == (1, 96, 128) and torch.isfinite(stored).all()
     assert torch.equal(stored, direct[0])
+
+
+def test_frames_in_flight_and_parallel_sequences(models, cuda):
+    """SURVEY.md 8(f)-3.  (1) frames_in_flight = 2: consecutive calls on two engines / two CUDA streams (prologue and loop
+    of frame k+1 overlapping frame k) give, frame for frame, what sequential calls give on engines built the same way.
+    (2) complete_sequences: the temporal prior without the reference's batch-1 restriction -- S sequences advance in one
+    batched call per frame index, each chained on its OWN previous latent -- equals running every sequence alone."""
+    from depth_completion_b200.pipeline import MarigoldDepthCompletionPipeline
+    from depth_completion_b200.synthetic import make_batch
+    from depth_completion_b200.video import complete_sequence, complete_sequences
+
+    unet, vae, ctx, _, _ = models
+    b = make_batch(5, H=96, W=128, n_points=80)
+    img, sp = b["img"].to(cuda), b["sparse"].to(cuda)
+    pipe = MarigoldDepthCompletionPipeline(unet, vae)
+    pipe.empty_text_embedding = ctx
+    dense2, rng, _ = complete_sequence(pipe, img, sp, 10.0, frames_in_flight=2, steps=8, resolution=128)
+    assert rng == (0, 5) and dense2.shape == (5, 1, 96, 128) and torch.isfinite(dense2).all()
+    assert len(pipe._engines) >= 2  # two slots of the same geometry, one weight bank
+    # the in-flight engines use the two-pass GroupNorm kernels (no grid barrier), the default engine the single-launch
+    # ones: same arithmetic up to the summation order of the statistics
+    dense1, _, _ = complete_sequence(pipe, img, sp, 10.0, steps=8, resolution=128)
+    assert ((dense2 - dense1).abs().mean() / 10.0).item() < 5e-3
+    # bit-identical to the same frames submitted one at a time on the concurrent-mode engines
+    for i in (0, 3):
+        t = pipe.submit(img[i:i + 1], sp[i:i + 1], 10.0, steps=8, resolution=128, _slot=i % 2, _concurrent=True)
+        d, _ = pipe.collect(t)
+        assert torch.equal(d, dense2[i:i + 1])
+    with pytest.raises(ValueError):
+        complete_sequence(pipe, img, sp, 10.0, frames_in_flight=2, use_prev_latent=True, steps=8, resolution=128)
+    # --- S = 2 sequences of F = 3 frames, batched over sequences with per-sample previous latents
+    seqs_i, seqs_s = torch.stack([img[:3], img[2:5]]), torch.stack([sp[:3], sp[2:5]])
+    dense_b, srng = complete_sequences(pipe, seqs_i, seqs_s, 10.0, beta=0.7, steps=6, resolution=128)
+    assert srng == (0, 2) and dense_b.shape == (2, 3, 1, 96, 128)
+    for s_ in range(2):
+        prev, alone = None, []
+        for f in range(3):
+            d, prev = pipe(seqs_i[s_, f:f + 1], seqs_s[s_, f:f + 1], 10.0, pred_latents_prev=prev, beta=0.7, steps=6, resolution=128)
+            alone.append(d)
+        diff = ((dense_b[s_] - torch.cat(alone, 0)).abs().mean() / 10.0).item()
+        assert diff < 2e-2, diff  # batch-2 engine vs batch-1 engine: same per-sample arithmetic, other tile shapes
+    d_r1, r1 = complete_sequences(pipe, seqs_i, seqs_s, 10.0, beta=0.7, steps=6, resolution=128, rank=1, world=2)
+    assert r1 == (1, 2) and d_r1.shape == (1, 3, 1, 96, 128)
+
+
+def test_call_geometries_share_one_weight_bank(models, cuda):
+    """A second frame geometry, a short last batch and a return to the first geometry never re-pack the weights
+    (mdc_create_shared): engines stay resident, the bank is loaded once, results equal those of a fresh pipeline."""
+    from depth_completion_b200.pipeline import MarigoldDepthCompletionPipeline
+    from depth_completion_b200.synthetic import make_batch
+
+    unet, vae, ctx, _, _ = models
+    b = make_batch(2, H=96, W=128, n_points=80)
+    img, sp = b["img"].to(cuda), b["sparse"].to(cuda)
+    pipe = MarigoldDepthCompletionPipeline(unet, vae)
+    pipe.empty_text_embedding = ctx
+    calls = []
+    orig = __import__("depth_completion_b200.engine", fromlist=["StepEngine"]).StepEngine.load_weights
+
+    def counting(self, *a, **k):
+        calls.append(k.get("only_missing", False))
+        return orig(self, *a, **k)
+
+    import depth_completion_b200.engine as em
+    em.StepEngine.load_weights = counting
+    try:
+        d_a, _ = pipe(img, sp, 10.0, steps=4, resolution=128)            # N = 2
+        d_b, _ = pipe(img[:1], sp[:1], 10.0, steps=4, resolution=128)    # short last batch: N = 1
+        d_c, _ = pipe(img[:1, :, :80, :120], sp[:1, :, :80, :120], 10.0, steps=4, resolution=120)  # another geometry (odd latent 10x15)
+        d_a2, _ = pipe(img, sp, 10.0, steps=4, resolution=128)           # back to the first one: resident
+    finally:
+        em.StepEngine.load_weights = orig
+    assert torch.equal(d_a, d_a2) and len(pipe._engines) == 3
+    assert calls[0] is False and all(calls[1:]), calls  # one full load; later engines only add layouts they miss
+    fresh = MarigoldDepthCompletionPipeline(unet, vae)
+    fresh.empty_text_embedding = ctx
+    d_c2, _ = fresh(img[:1, :, :80, :120], sp[:1, :, :80, :120], 10.0, steps=4, resolution=120)
+    assert torch.equal(d_c, d_c2)
+    pipe.MAX_ENGINES = 2  # eviction: more geometries than resident slots leaves a workspace-less weight keeper behind
+    for (h_, w_) in ((64, 96), (48, 64)):
+        s_ = make_batch(1, H=h_, W=w_, n_points=40)
+        pipe(s_["img"].to(cuda), s_["sparse"].to(cuda), 10.0, steps=2, resolution=w_)
+    assert len(pipe._engines) <= 2 and pipe._keeper is not None
+    d_b2, _ = pipe(img[:1], sp[:1], 10.0, steps=4, resolution=128)
+    assert torch.equal(d_b, d_b2)
+
+
+def test_caller_stream_and_device_are_honoured(models, cuda):
+    """The library runs on torch's CURRENT stream (mdc_set_stream): a call inside torch.cuda.stream(side) whose inputs are
+    produced on that side stream by a long-running kernel must see them, and equals the default-stream result."""
+    from depth_completion_b200.pipeline import MarigoldDepthCompletionPipeline
+    from depth_completion_b200.synthetic import make_batch
+
+    unet, vae, ctx, _, _ = models
+    b = make_batch(1, H=96, W=128, n_points=80)
+    img, sp = b["img"].to(cuda), b["sparse"].to(cuda)
+    pipe = MarigoldDepthCompletionPipeline(unet, vae)
+    pipe.empty_text_embedding = ctx
+    ref, _ = pipe(img, sp, 10.0, steps=4, resolution=128)
+    side = torch.cuda.Stream(device=cuda)
+    big = torch.randn(4096, 4096, device=cuda)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        for _ in range(20):           # keeps the side stream busy for tens of ms ...
+            big = (big @ big).clamp(-1.0, 1.0)
+        sp2 = sp + 0.0 * big[0, 0]    # ... before the sparse map the call consumes even exists
+        img2 = img.clone()
+        out, _ = pipe(img2, sp2, 10.0, steps=4, resolution=128)
+    side.synchronize()
+    assert torch.equal(out, ref)
