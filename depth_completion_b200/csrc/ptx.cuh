@@ -115,6 +115,13 @@ __device__ __forceinline__ void bulk_wait_read() {  // all but the N most recent
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// L2 prefetch of a 4-D tile (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 // 1-D bulk copy global -> shared (no tensor map): `bytes` (multiple of 16, 16-byte aligned on both sides) complete on `bar`.
 __device__ __forceinline__ void bulk_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
