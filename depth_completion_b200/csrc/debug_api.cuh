@@ -269,7 +269,7 @@ int mdc_dbg_groupnorm(int n, int HW, int C, int groups, float eps, int silu, con
     cudaEventDestroy(e0), cudaEventDestroy(e1);
     cudaFree(sc.partial), cudaFree(sc.gstats), cudaFree(sc.ticket), cudaFree(sc.bar), cudaFree(stats);
     MDC_CHECK(flag == 0, "GroupNorm grid barrier timed out");
-    MDC_CHECK(mode != 1 || (!p.fuse_f && !p.fuse_b), "mode 1 did not select the two-pass kernels");
+    MDC_CHECK(mode != 1 || (!p.single_f() && !p.single_b()), "mode 1 did not select the two-pass kernels");
   });
 }
 

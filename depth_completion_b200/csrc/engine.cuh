@@ -166,8 +166,8 @@ struct GroupNormOp : Op {
   }
   void fwd(cudaStream_t st) override;
   void bwd(cudaStream_t st) override;
-  int n_fwd() const override { return plan.fuse_f ? 1 : (epi ? 1 : 2); }
-  int n_bwd() const override { return plan.fuse_b ? 1 : 2; }
+  int n_fwd() const override { return plan.single_f() ? 1 : (epi ? 1 : 2); }
+  int n_bwd() const override { return plan.single_b() ? 1 : 2; }
 };
 struct LayerNormOp : Op {
   Tensor *x, *y;
@@ -771,7 +771,7 @@ inline Tensor* Engine::group_norm(Tensor* x, const std::string& key, float eps, 
   // scarce resource of the 128-channel convolutions, DESIGN.md section 4 -- so it is opt-in: MDC_GNEPI=1)
   static const bool no_epi = getenv("MDC_GNEPI") == nullptr;
   const int cpg = x->c / G;
-  if (!no_epi && !op->plan.fuse_f && x->producer && !x->producer_gn && G == 32 && 32 % cpg == 0 && x->c % 32 == 0) {
+  if (!no_epi && !op->plan.single_f() && x->producer && !x->producer_gn && G == 32 && 32 % cpg == 0 && x->c % 32 == 0) {
     GemmPlan* g = x->producer;
     if (g->p.conv == 1 && g->p.ksplit <= 1 && g->p.N == x->c && g->p.BN % 32 == 0 && !g->p.out_f32) {
       g->p.gn_cpg = cpg, g->p.gn_nimg = x->n;

@@ -988,6 +988,160 @@ __global__ void __launch_bounds__(384, 2) gn_bwd_apply_s_kernel(const bf16* __re
   }
 }
 
+// --------------------------------------------------------------------------- cluster GroupNorm (no grid barrier)
+// GroupNorm statistics are independent per (image, group), so the single-launch form needs no grid-wide rendezvous: a
+// CLUSTER of K CTAs owns one (image, group), CTA k stages its slice of the pixels -- only the group's C/G channels of
+// each, a 20-160 byte segment per pixel -- in shared memory, the K partial sums meet through distributed shared memory
+// behind one hardware cluster barrier, and every CTA normalises its slice from shared memory.  Unlike the grid-barrier
+// kernels above this cannot starve when several kernels share the GPU, and its critical path is one cluster barrier
+// instead of ~150 CTAs polling one L2 word.  Thread mapping: a lane owns one bf16 PAIR position j of the group
+// (PP = C/G/2 pairs per pixel) and, with PP <= 16, one of 32/PP pixels of the warp's round.
+struct GNClusterShape {
+  int N, HW, C, G, K;     // K = cluster size (CTAs per (image, group))
+  long long ld;
+  int pix_per_cta;
+};
+__device__ __forceinline__ void gnc_map(int PP, int lane, int& ppw, int& sp, int& j0, int& jstep) {
+  // PP <= 32: 32 / PP pixels per warp round, lane -> (sub-pixel sp, pair j0); PP > 32: one pixel per round, lanes stride the pairs
+  if (PP <= 32) {
+    ppw = 32 / PP, sp = lane / PP, j0 = lane - sp * PP, jstep = PP;  // jstep = PP: a single pair per lane
+    if (sp >= ppw) sp = -1;                                            // idle lane
+  } else {
+    ppw = 1, sp = 0, j0 = lane, jstep = 32;
+  }
+}
+// block-wide sum of two values -> all threads; `red` holds 64 floats
+__device__ __forceinline__ void block_sum2(float& a, float& b, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  a = warp_sum(a), b = warp_sum(b);
+  __syncthreads();
+  if (lane == 0) red[w] = a, red[32 + w] = b;
+  __syncthreads();
+  float ra = lane < nw ? red[lane] : 0.f, rb = lane < nw ? red[32 + lane] : 0.f;
+  a = warp_sum(ra), b = warp_sum(rb);
+}
+// sum of the K CTAs' (a, b) through distributed shared memory, fixed order; `slot` = 2 floats of THIS CTA's shared memory
+__device__ __forceinline__ void cluster_sum2(float& a, float& b, float* slot, int K) {
+  if (threadIdx.x == 0) slot[0] = a, slot[1] = b;
+  ptx::cluster_sync_all();
+  double sa = 0, sb = 0;
+  for (int k = 0; k < K; ++k) {
+    const uint32_t addr = ptx::mapa_u32(slot, static_cast<uint32_t>(k));
+    sa += ptx::ld_shared_cluster_f32(addr), sb += ptx::ld_shared_cluster_f32(addr + 4);
+  }
+  a = static_cast<float>(sa), b = static_cast<float>(sb);
+  ptx::cluster_sync_all();  // nobody leaves (or reuses the slot) while a peer may still read it
+}
+
+// shared memory: [slab: pix_per_cta x C/G bf16][red 64 floats][slot 2 floats (+2 pad)]
+__global__ void __launch_bounds__(256) gn_cluster_fwd_kernel(const bf16* __restrict__ x, GNClusterShape s, float eps,
+                                                             float* __restrict__ stats_out, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, int silu, bf16* __restrict__ y,
+                                                             long long ldy) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  extern __shared__ __align__(16) uint8_t gnc_smem[];
+  const int cpg = s.C / s.G, PP = cpg >> 1;
+  const int cl = blockIdx.x / s.K, rank = static_cast<int>(ptx::cluster_ctarank());
+  const int n = cl / s.G, g = cl % s.G;
+  const int p0 = rank * s.pix_per_cta, npix = max(0, min(s.HW, p0 + s.pix_per_cta) - p0);
+  __nv_bfloat162* slab = reinterpret_cast<__nv_bfloat162*>(gnc_smem);
+  float* red = reinterpret_cast<float*>(gnc_smem + ((static_cast<size_t>(s.pix_per_cta) * cpg * 2 + 15) & ~size_t(15)));
+  float* slot = red + 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  int ppw, sp, j0, jstep;
+  gnc_map(PP, lane, ppw, sp, j0, jstep);
+  const bf16* xb = x + (1LL * n * s.HW + p0) * s.ld + g * cpg;
+  float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
+  if (sp >= 0)
+    for (int pl = warp * ppw + sp; pl < npix; pl += nw * ppw)
+      for (int j = j0; j < PP; j += jstep) {
+        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(xb + 1LL * pl * s.ld + 2 * j);
+        slab[pl * PP + j] = v;
+        const float2 t = __bfloat1622float2(v);
+        sum2 = __fadd2_rn(sum2, t);
+        sq2 = __ffma2_rn(t, t, sq2);
+      }
+  float a = sum2.x + sum2.y, b = sq2.x + sq2.y;
+  block_sum2(a, b, red);
+  cluster_sum2(a, b, slot, s.K);
+  const double m = 1.0 * s.HW * cpg, mean_d = a / m;
+  double var = b / m - mean_d * mean_d;
+  if (var < 0) var = 0;
+  const float mean = static_cast<float>(mean_d), rstd = static_cast<float>(1.0 / sqrt(var + eps));
+  if (rank == 0 && threadIdx.x == 0) stats_out[2 * (n * s.G + g)] = mean, stats_out[2 * (n * s.G + g) + 1] = rstd;
+  bf16* yb = y + (1LL * n * s.HW + p0) * ldy + g * cpg;
+  if (sp >= 0)
+    for (int j = j0; j < PP; j += jstep) {  // (a single j per lane when PP <= 32)
+      const int c = g * cpg + 2 * j;
+      const float2 sc = make_float2(rstd * gamma[c], rstd * gamma[c + 1]);
+      const float2 sf = make_float2(beta[c] - mean * sc.x, beta[c + 1] - mean * sc.y);
+      for (int pl = warp * ppw + sp; pl < npix; pl += nw * ppw) {
+        float2 h = __ffma2_rn(__bfloat1622float2(slab[pl * PP + j]), sc, sf);
+        if (silu) h = silu2(bf16r2(h));
+        *reinterpret_cast<__nv_bfloat162*>(yb + 1LL * pl * ldy + 2 * j) = __floats2bfloat162_rn(h.x, h.y);
+      }
+    }
+}
+
+// shared memory: [x slab][dy slab][red 64][slot 2]
+__global__ void __launch_bounds__(256) gn_cluster_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, long long lddy,
+                                                             GNClusterShape s, const float* __restrict__ stats,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             int silu, bf16* __restrict__ dx, long long lddx, int acc) {
+  ptx::pdl_wait();
+  ptx::pdl_launch();
+  extern __shared__ __align__(16) uint8_t gnc_smem[];
+  const int cpg = s.C / s.G, PP = cpg >> 1;
+  const int cl = blockIdx.x / s.K, rank = static_cast<int>(ptx::cluster_ctarank());
+  const int n = cl / s.G, g = cl % s.G;
+  const int p0 = rank * s.pix_per_cta, npix = max(0, min(s.HW, p0 + s.pix_per_cta) - p0);
+  const size_t slab_bytes = (static_cast<size_t>(s.pix_per_cta) * cpg * 2 + 15) & ~size_t(15);
+  __nv_bfloat162* slab_x = reinterpret_cast<__nv_bfloat162*>(gnc_smem);
+  float2* slab_d = reinterpret_cast<float2*>(gnc_smem + slab_bytes);  // dxhat kept in fp32: no second activation-derivative pass
+  float* red = reinterpret_cast<float*>(gnc_smem + slab_bytes + static_cast<size_t>(s.pix_per_cta) * cpg * 4);
+  float* slot = red + 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  int ppw, sp, j0, jstep;
+  gnc_map(PP, lane, ppw, sp, j0, jstep);
+  const float mean = stats[2 * (n * s.G + g)], rstd = stats[2 * (n * s.G + g) + 1], Mr = -mean * rstd;
+  const bf16* xb = x + (1LL * n * s.HW + p0) * s.ld + g * cpg;
+  const bf16* db = dy + (1LL * n * s.HW + p0) * lddy + g * cpg;
+  float2 sa2 = make_float2(0.f, 0.f), sb2 = make_float2(0.f, 0.f);
+  if (sp >= 0)
+    for (int j = j0; j < PP; j += jstep) {
+      const int c = g * cpg + 2 * j;
+      const float2 G2 = make_float2(gamma[c], gamma[c + 1]);
+      const float2 A2 = make_float2(rstd * G2.x, rstd * G2.y), B2 = make_float2(beta[c] - mean * A2.x, beta[c + 1] - mean * A2.y);
+      for (int pl = warp * ppw + sp; pl < npix; pl += nw * ppw) {
+        const __nv_bfloat162 vx = *reinterpret_cast<const __nv_bfloat162*>(xb + 1LL * pl * s.ld + 2 * j);
+        const float2 xv = __bfloat1622float2(vx);
+        float2 d = __fmul2_rn(__bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(db + 1LL * pl * lddy + 2 * j)), G2);
+        if (silu) d = __fmul2_rn(d, silu_grad2(bf16r2(__ffma2_rn(xv, A2, B2))));
+        const float2 xh = __ffma2_rn(xv, make_float2(rstd, rstd), make_float2(Mr, Mr));
+        slab_x[pl * PP + j] = vx;
+        slab_d[pl * PP + j] = d;
+        sa2 = __fadd2_rn(sa2, d);
+        sb2 = __ffma2_rn(d, xh, sb2);
+      }
+    }
+  float a = sa2.x + sa2.y, b = sb2.x + sb2.y;
+  block_sum2(a, b, red);
+  cluster_sum2(a, b, slot, s.K);
+  const float m = 1.f * s.HW * cpg, m1 = a / m, m2 = b / m;
+  const float C1 = -rstd * rstd * m2, C2 = -rstd * m1 - Mr * rstd * m2;
+  bf16* ob = dx + (1LL * n * s.HW + p0) * lddx + g * cpg;
+  if (sp >= 0)
+    for (int j = j0; j < PP; j += jstep)
+      for (int pl = warp * ppw + sp; pl < npix; pl += nw * ppw) {
+        const float2 xv = __bfloat1622float2(slab_x[pl * PP + j]);
+        float2 gx = __ffma2_rn(slab_d[pl * PP + j], make_float2(rstd, rstd), __ffma2_rn(xv, make_float2(C1, C1), make_float2(C2, C2)));
+        __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(ob + 1LL * pl * lddx + 2 * j);
+        if (acc) gx = __fadd2_rn(gx, __bfloat1622float2(*dst));
+        *dst = __floats2bfloat162_rn(gx.x, gx.y);
+      }
+}
+
 // =========================================================================== AutoencoderTiny element-wise pieces
 // g = (y > 0) ? g : 0 in place: backward of the ReLU that produced y (applied once y's gradient is complete)
 __global__ void relu_mask_kernel(bf16* __restrict__ g, long long ldg, const bf16* __restrict__ y, long long ldy,

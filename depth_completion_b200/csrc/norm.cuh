@@ -12,21 +12,50 @@
 
 namespace mdc {
 
+constexpr size_t GN_FUSED_SMEM_CAP = 200 * 1024;
+
 struct GNPlan {
   GNShape s;    // two-pass tiling
-  GNShape sfu;  // single-launch tiling
+  GNShape sfu;  // single-launch tiling (grid-barrier variant)
   int G = 0, threads = 0, threads_b = 0;
-  bool fuse_f = false, fuse_b = false;
+  bool fuse_f = false, fuse_b = false;  // grid-barrier single-launch kernels (kept for comparison: MDC_GN_GRIDBAR=1)
   size_t smem_f = 0, smem_b = 0;
+  // cluster single-launch kernels (one cluster of K CTAs per (image, group), no grid barrier): the default when they fit
+  bool cl_f = false, cl_b = false;
+  GNClusterShape cs_f{}, cs_b{};
+  size_t cl_smem_f = 0, cl_smem_b = 0;
   size_t partial_floats = 0;  // scratch the launchers need (per-block partial sums)
+  bool single_f() const { return cl_f || fuse_f; }
+  bool single_b() const { return cl_b || fuse_b; }
 };
+inline size_t gnc_smem_bytes(int pix_per_cta, int cpg, bool bwd) {
+  const size_t slab = (static_cast<size_t>(pix_per_cta) * cpg * 2 + 15) & ~size_t(15);
+  return slab + (bwd ? static_cast<size_t>(pix_per_cta) * cpg * 4 : 0) + 68 * sizeof(float);
+}
+// Smallest cluster size K in {1, 2, 4, 8} that gives the chip enough CTAs and whose pixel slice fits in shared memory.
+inline bool plan_gn_cluster(int N, int HW, int C, int G, long long ld, bool bwd, GNClusterShape& cs, size_t& smem) {
+  const int cpg = C / G;
+  int kpar = 1;
+  while (kpar < 8 && N * G * kpar < 96) kpar *= 2;
+  for (int K = kpar; K <= 8; K *= 2) {
+    const int ppc = (HW + K - 1) / K;
+    const size_t b = gnc_smem_bytes(ppc, cpg, bwd);
+    if (b <= GN_FUSED_SMEM_CAP) {
+      cs.N = N, cs.HW = HW, cs.C = C, cs.G = G, cs.K = K, cs.ld = ld, cs.pix_per_cta = ppc;
+      smem = b;
+      return true;
+    }
+  }
+  return false;
+}
 
-constexpr size_t GN_FUSED_SMEM_CAP = 200 * 1024;
 
 // Function attributes are per device: call once per device before the first launch there.
 inline void gn_set_attrs() {
   static bool done[64] = {false};
   if (!first_use_on_device(done)) return;
+  MDC_CUDA(cudaFuncSetAttribute(gn_cluster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(GN_FUSED_SMEM_CAP) + 1024));
+  MDC_CUDA(cudaFuncSetAttribute(gn_cluster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(GN_FUSED_SMEM_CAP) + 1024));
   MDC_CUDA(cudaFuncSetAttribute(gn_stats_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
   MDC_CUDA(cudaFuncSetAttribute(gn_apply_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
   MDC_CUDA(cudaFuncSetAttribute(gn_bwd_stats_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
@@ -62,15 +91,46 @@ inline GNPlan plan_groupnorm(int N, int HW, int C, int G, long long ld, int mode
   f.blocks_per_img = (s.HW + f.pix_per_block - 1) / f.pix_per_block;
   const size_t slab = static_cast<size_t>(f.pix_per_block) * C * 2;
   const size_t extra = (static_cast<size_t>((p.threads + 31) / 32) * 2 * G + 2 * G) * sizeof(float);
-  const bool ok = !(no_fuse && mode != 2) && mode != 1 && p.threads >= 8 * G && N * f.blocks_per_img <= sms;
+  const bool ok = !(no_fuse && mode != 2 && mode != 3) && mode != 1 && p.threads >= 8 * G && N * f.blocks_per_img <= sms;
   p.sfu = f;
   p.smem_f = slab + extra, p.smem_b = 2 * slab + extra;
   p.fuse_f = ok && p.smem_f <= GN_FUSED_SMEM_CAP;
   p.fuse_b = ok && p.smem_b <= GN_FUSED_SMEM_CAP;
-  MDC_CHECK(mode != 2 || (p.fuse_f && p.fuse_b), "GroupNorm: the single-launch variant does not fit (N=%d HW=%d C=%d)", N, HW, C);
+  // mode 0 / 2: cluster kernels when they fit (no co-residency requirement, so always allowed); the grid-barrier ones
+  // only on request (MDC_GN_GRIDBAR=1 or mode 3)
+  static const bool gridbar = getenv("MDC_GN_GRIDBAR") != nullptr;
+  if (mode != 1 && !(no_fuse && mode != 2) && mode != 3 && !gridbar) {
+    p.cl_f = plan_gn_cluster(N, HW, C, G, ld, false, p.cs_f, p.cl_smem_f);
+    p.cl_b = plan_gn_cluster(N, HW, C, G, ld, true, p.cs_b, p.cl_smem_b);
+    p.fuse_f = p.fuse_f && !p.cl_f && false;  // the grid-barrier kernels are never mixed in implicitly
+    p.fuse_b = p.fuse_b && !p.cl_b && false;
+  }
+  MDC_CHECK(mode != 2 || (p.single_f() && p.single_b()), "GroupNorm: the single-launch variant does not fit (N=%d HW=%d C=%d)", N, HW, C);
+  MDC_CHECK(mode != 3 || (p.fuse_f && p.fuse_b), "GroupNorm: the grid-barrier variant does not fit (N=%d HW=%d C=%d)", N, HW, C);
   // the single-launch variant may use MORE blocks than the two-pass one on small maps (one pixel row per block)
   p.partial_floats = static_cast<size_t>(2) * G * N * std::max(s.blocks_per_img, f.blocks_per_img);
   return p;
+}
+
+// launch_k with a thread-block cluster of `cluster` CTAs along x (plus the programmatic-dependent-launch attribute)
+template <typename... KArgs, typename... Args>
+inline void launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, int cluster, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (g_use_pdl()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = cluster, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
+  ++na;
+  cfg.attrs = attr, cfg.numAttrs = na;
+  MDC_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  debug_sync(reinterpret_cast<const void*>(kernel), st);
 }
 
 struct GNScratch {
@@ -86,6 +146,11 @@ inline void run_gn_fwd(const GNPlan& p, const bf16* x, bf16* y, long long ldy, c
                        int silu, float* stats, const GNScratch& sc, cudaStream_t st, const float* epi_partial = nullptr,
                        int epi_parts = 0) {
   const bool have_stats = epi_partial != nullptr;
+  if (p.cl_f) {
+    launch_cluster(gn_cluster_fwd_kernel, dim3(p.cs_f.N * p.cs_f.G * p.cs_f.K), dim3(256), p.cl_smem_f, p.cs_f.K, st, x, p.cs_f, eps, stats, gamma, beta,
+                   silu, y, ldy);
+    return;
+  }
   if (p.fuse_f) {
     launch_k(gn_fused_fwd_kernel, dim3(p.sfu.N * p.sfu.blocks_per_img), dim3(p.threads), p.smem_f, st, x, p.sfu, sc.partial, eps, stats, sc.bar,
              gamma, beta, silu, y, ldy);
@@ -107,6 +172,11 @@ inline void run_gn_fwd(const GNPlan& p, const bf16* x, bf16* y, long long ldy, c
 }
 inline void run_gn_bwd(const GNPlan& p, const bf16* x, const bf16* dy, long long lddy, const float* gamma, const float* beta, int silu,
                        const float* stats, bf16* dx, long long lddx, int acc, const GNScratch& sc, cudaStream_t st) {
+  if (p.cl_b) {
+    launch_cluster(gn_cluster_bwd_kernel, dim3(p.cs_b.N * p.cs_b.G * p.cs_b.K), dim3(256), p.cl_smem_b, p.cs_b.K, st, x, dy, lddy, p.cs_b, stats, gamma,
+                   beta, silu, dx, lddx, acc);
+    return;
+  }
   if (p.fuse_b) {
     launch_k(gn_fused_bwd_kernel, dim3(p.sfu.N * p.sfu.blocks_per_img), dim3(p.threads), p.smem_b, st, x, dy, lddy, p.sfu, stats, gamma, beta, silu,
              sc.partial, sc.bar, dx, lddx, acc);

@@ -105,8 +105,17 @@ def _gn_ref(x_nhwc, gamma, beta, groups, eps, silu, dy, dtype):
     (1, 288, 384, 512, 1, 1, 1e-6),   # up_blocks.2.resnets.0.norm1: 113 MB
     (2, 288, 384, 256, 0, 1, 1e-6),   # batch 2, automatic selection (two-pass at this size)
     (1, 72, 96, 512, 0, 0, 1e-6),     # mid-block attention norm (no SiLU), automatic = single launch
-    (1, 72, 96, 320, 2, 1, 1e-5),     # UNet level 0, single-launch kernels required
+    (1, 72, 96, 320, 2, 1, 1e-5),     # UNet level 0, single-launch (cluster) kernels required
+    (1, 72, 96, 320, 3, 1, 1e-5),     # ... the grid-barrier variant of the same (kept for comparison)
+    (1, 72, 96, 960, 2, 1, 1e-5),     # UNet up path concat at level 0 (13 MB): cluster of 8 per group
+    (1, 72, 96, 960, 3, 1, 1e-5),
+    (1, 36, 48, 640, 2, 1, 1e-5),     # level 1
+    (1, 18, 24, 1280, 2, 1, 1e-5),    # level 2
+    (1, 18, 24, 1280, 3, 1, 1e-5),
+    (1, 9, 12, 2560, 2, 1, 1e-5),     # level 3 concat: 80 channels per group (lanes stride the pairs)
+    (1, 9, 12, 2560, 3, 1, 1e-5),
     (2, 36, 48, 1920, 2, 1, 1e-5),    # UNet up path concat width, batch 2
+    (1, 144, 192, 512, 0, 1, 1e-6),   # decoder up_blocks.1 (28 MB): cluster forward, two-pass backward
     (1, 44, 152, 960, 0, 1, 1e-5)])   # KITTI-shaped level 0 concat
 def test_groupnorm_fullsize(cuda, n, H, W, C, mode, silu, eps):
     from depth_completion_b200 import debug
