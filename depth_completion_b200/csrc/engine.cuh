@@ -763,7 +763,7 @@ inline Tensor* Engine::group_norm(Tensor* x, const std::string& key, float eps, 
   auto* op = new GroupNormOp();
   op->E = this, op->x = x, op->y = y, op->gamma = ga->vec, op->beta = be->vec, op->eps = eps, op->groups = G;
   op->silu = silu ? 1 : 0;
-  op->plan = plan_groupnorm(x->n, x->h * x->w, x->c, G, x->ld, cfg.concurrent ? 1 : 0);
+  op->plan = plan_groupnorm(x->n, x->h * x->w, x->c, G, x->ld, cfg.concurrent ? 4 : 0);
   op->stats = arena.make<float>(2ull * x->n * G);
   gn_partial_floats = std::max<size_t>(gn_partial_floats, op->plan.partial_floats);
   // Large tensors (two-pass path): let the conv that produces x emit the statistics from its epilogue

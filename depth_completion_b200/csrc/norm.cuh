@@ -18,9 +18,9 @@ struct GNPlan {
   GNShape s;    // two-pass tiling
   GNShape sfu;  // single-launch tiling (grid-barrier variant)
   int G = 0, threads = 0, threads_b = 0;
-  bool fuse_f = false, fuse_b = false;  // grid-barrier single-launch kernels (kept for comparison: MDC_GN_GRIDBAR=1)
+  bool fuse_f = false, fuse_b = false;  // grid-barrier single-launch kernels (tensors whose slab fits one SM each)
   size_t smem_f = 0, smem_b = 0;
-  // cluster single-launch kernels (one cluster of K CTAs per (image, group), no grid barrier): the default when they fit
+  // cluster single-launch kernels (one cluster of K CTAs per (image, group), no grid barrier): concurrent handles
   bool cl_f = false, cl_b = false;
   GNClusterShape cs_f{}, cs_b{};
   size_t cl_smem_f = 0, cl_smem_b = 0;
@@ -64,7 +64,8 @@ inline void gn_set_attrs() {
   MDC_CUDA(cudaFuncSetAttribute(gn_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(GN_FUSED_SMEM_CAP)));
 }
 
-// mode: 0 = automatic (single launch when the slab fits), 1 = force the two-pass kernels, 2 = require the single launch.
+// mode: 0 = automatic, 1 = force the two-pass kernels, 2 = require a single-launch kernel (cluster kernels preferred),
+// 3 = require the grid-barrier single-launch kernels, 4 = automatic without grid-barrier kernels (concurrent handles).
 inline GNPlan plan_groupnorm(int N, int HW, int C, int G, long long ld, int mode = 0) {
   MDC_CHECK(C % G == 0 && (C / G) % 2 == 0 && C % 8 == 0, "GroupNorm: C=%d G=%d unsupported", C, G);
   GNPlan p;
@@ -91,20 +92,26 @@ inline GNPlan plan_groupnorm(int N, int HW, int C, int G, long long ld, int mode
   f.blocks_per_img = (s.HW + f.pix_per_block - 1) / f.pix_per_block;
   const size_t slab = static_cast<size_t>(f.pix_per_block) * C * 2;
   const size_t extra = (static_cast<size_t>((p.threads + 31) / 32) * 2 * G + 2 * G) * sizeof(float);
-  const bool ok = !(no_fuse && mode != 2 && mode != 3) && mode != 1 && p.threads >= 8 * G && N * f.blocks_per_img <= sms;
+  const bool ok = !(no_fuse && mode != 2 && mode != 3) && mode != 1 && mode != 4 && p.threads >= 8 * G && N * f.blocks_per_img <= sms;
   p.sfu = f;
   p.smem_f = slab + extra, p.smem_b = 2 * slab + extra;
   p.fuse_f = ok && p.smem_f <= GN_FUSED_SMEM_CAP;
   p.fuse_b = ok && p.smem_b <= GN_FUSED_SMEM_CAP;
-  // mode 0 / 2: cluster kernels when they fit (no co-residency requirement, so always allowed); the grid-barrier ones
-  // only on request (MDC_GN_GRIDBAR=1 or mode 3)
-  static const bool gridbar = getenv("MDC_GN_GRIDBAR") != nullptr;
-  if (mode != 1 && !(no_fuse && mode != 2) && mode != 3 && !gridbar) {
+  // Measured on a B200 (profiles/r02_groupnorm_variants.md): timed alone the cluster kernels win on tensors up to ~3.5 MB
+  // (7-11 us against 11-12 us) and lose on the 4-28 MB ones (20-160 byte channel segments; at 8 CTAs per group no
+  // longer one wave), but inside the captured step -- where programmatic dependent launch overlaps neighbouring small
+  // kernels -- a hybrid selection measured 20.80 ms per step against 20.70 ms for the grid-barrier kernels alone.  So
+  // the default (mode 0) keeps the grid-barrier kernels; the cluster kernels serve handles created with
+  // `mdc_config.concurrent` (mode 4), which must not spin on a grid barrier, and mode 2 (tests).
+  const bool want_cluster = mode == 2 || mode == 4;
+  if (want_cluster && !(no_fuse && mode != 2)) {
     p.cl_f = plan_gn_cluster(N, HW, C, G, ld, false, p.cs_f, p.cl_smem_f);
     p.cl_b = plan_gn_cluster(N, HW, C, G, ld, true, p.cs_b, p.cl_smem_b);
-    p.fuse_f = p.fuse_f && !p.cl_f && false;  // the grid-barrier kernels are never mixed in implicitly
-    p.fuse_b = p.fuse_b && !p.cl_b && false;
+    if (mode == 4 && (p.cs_f.K * N * G > 2 * sms || p.cs_b.K * N * G > 2 * sms)) p.cl_f = p.cl_b = false;  // too many waves: two-pass instead
   }
+  if (p.cl_f) p.fuse_f = false;
+  if (p.cl_b) p.fuse_b = false;
+  if (mode == 4) p.fuse_f = p.fuse_b = false;
   MDC_CHECK(mode != 2 || (p.single_f() && p.single_b()), "GroupNorm: the single-launch variant does not fit (N=%d HW=%d C=%d)", N, HW, C);
   MDC_CHECK(mode != 3 || (p.fuse_f && p.fuse_b), "GroupNorm: the grid-barrier variant does not fit (N=%d HW=%d C=%d)", N, HW, C);
   // the single-launch variant may use MORE blocks than the two-pass one on small maps (one pixel row per block)

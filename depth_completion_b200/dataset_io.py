@@ -114,9 +114,14 @@ def complete_dataset(pipe, src_root, dst_root, max_depth: float = 120.0, max_spa
                      device=None, rank: int = 0, world: int = 1, **pipe_kwargs) -> dict:
     """Runs `pipe` over every dataset directory under `src_root`; returns {dataset name: [saved dense paths]}.
 
-    Frames of one dataset form a sequence (`video.complete_sequence`); with world > 1 the independent frames are sharded
-    across ranks and every rank writes its own files (no collective at all).  Unreadable pairs are skipped like
-    `predict.py:636-655`; all frames of a dataset must share one resolution (they are stacked into one batch)."""
+    Like `predict.py:599-690`, one BATCH at a time is decoded, moved to the device, completed and written, so host and
+    device memory hold `batch_size` frames, never a whole dataset; frames of different resolutions may share a dataset
+    (a batch is cut where the resolution changes; every geometry keeps its engine resident on the shared weight bank).
+    With `use_prev_latent` the frames chain (batch 1, `predict.py:423-430, :697-699`) and the chain restarts where the
+    resolution changes.  With world > 1 the independent frames are sharded across ranks and every rank writes its own
+    files (no collective at all).  Unreadable pairs are skipped like `predict.py:636-655`."""
+    from .video import sequence_batches
+
     src_root, dst_root = Path(src_root), Path(dst_root)
     datasets = find_dataset_dirs(src_root)
     if not datasets:
@@ -128,24 +133,34 @@ def complete_dataset(pipe, src_root, dst_root, max_depth: float = 120.0, max_spa
         pairs = find_pairs(ds)
         if not pairs:
             raise FileNotFoundError(f"No valid input pairs found in {ds}")
-        loaded = [(load_rgb(i), load_rgb(s), s) for i, s in pairs]
-        loaded = [t for t in loaded if t[0] is not None and t[1] is not None]
-        if not loaded:
-            continue
-        imgs = torch.stack([t[0] for t in loaded]).to(device)
-        sparses = to_depth(torch.stack([t[1] for t in loaded]).to(device), max_distance=max_sparse_depth)
-        denses, (lo, hi), _ = complete_sequence(pipe, imgs, sparses, max_depth, batch_size=batch_size,
-                                                use_prev_latent=use_prev_latent, beta=beta, rank=rank, world=world,
-                                                **pipe_kwargs)
-        out = []
+        out, prev, prev_shape = [], None, None
         sparse_dir = ds / SPARSE_DIR
         rel_ds = ds.relative_to(src_root) if ds != src_root else Path(".")
-        for k, dense in zip(range(lo, hi), denses):
-            if torch.isnan(dense).any():
-                continue
-            sp = loaded[k][2]
-            path = (dst_root / rel_ds / DENSE_DIR / sp.relative_to(sparse_dir)).with_suffix(suffix)
-            save_tensor(dense, path, compress=compress)
-            out.append(path)
+        for b0, b1 in sequence_batches(len(pairs), batch_size, use_prev_latent, rank, world):
+            loaded = [(load_rgb(i), load_rgb(s), s) for i, s in pairs[b0:b1]]
+            loaded = [t for t in loaded if t[0] is not None and t[1] is not None]
+            # cut the batch where the resolution changes (one pipeline call per run of equal shapes)
+            runs, start = [], 0
+            for k in range(1, len(loaded) + 1):
+                if k == len(loaded) or loaded[k][0].shape != loaded[start][0].shape:
+                    runs.append(loaded[start:k])
+                    start = k
+            for run in runs:
+                if not run:
+                    continue
+                imgs = torch.stack([t[0] for t in run]).to(device)
+                sparses = to_depth(torch.stack([t[1] for t in run]).to(device), max_distance=max_sparse_depth)
+                if use_prev_latent and prev is not None and prev_shape != tuple(imgs.shape[-2:]):
+                    prev = None
+                denses, lat = pipe(imgs, sparses, max_depth, pred_latents_prev=prev if use_prev_latent else None, beta=beta,
+                                   **pipe_kwargs)
+                if use_prev_latent:
+                    prev, prev_shape = lat, tuple(imgs.shape[-2:])
+                for (_, _, sp), dense in zip(run, denses):
+                    if torch.isnan(dense).any():
+                        continue
+                    path = (dst_root / rel_ds / DENSE_DIR / sp.relative_to(sparse_dir)).with_suffix(suffix)
+                    save_tensor(dense, path, compress=compress)
+                    out.append(path)
         saved[ds.name] = out
     return saved
