@@ -34,6 +34,13 @@ struct FlashParams {
   int T, heads;
   float scale;             // 1/sqrt(head_dim)
   float lazy;              // forward: O is rescaled only when a row maximum grows by more than 2^lazy (0 = always)
+  // Two CTAs share an SM and, per sub-partition, one TMEM read port (16 B/clk) and one MUFU: a key tile costs each
+  // softmax warp ~512 clk of TMEM reads and ~512 clk of exponentials.  CTAs that start together run in lockstep -- both
+  // load, then both exponentiate -- and the tile takes the SUM of the two; started half a tile period apart they
+  // interleave (one loads while the other exponentiates).  The second resident CTA of an SM (linear block id / SM count
+  // odd) therefore delays its first loads by `stagger_ns`.
+  unsigned stagger_ns;
+  int num_sms;
   // outputs / side inputs
   bf16* out1;              // fwd: O      dkv: dK     dq: dQ
   bf16* out2;              //             dkv: dV
@@ -132,6 +139,10 @@ __device__ __forceinline__ void fa_teardown(const FaCtx& c, uint32_t tmem_cols) 
 // TMA producer shared by the three kernels: the resident tile(s) once, then the streamed pairs.
 __device__ __forceinline__ void fa_producer(const FaCtx& c, const FlashParams& p, int m_row0, int h, int n, int n_iter,
                                             bool two_m) {
+  if (p.stagger_ns) {
+    const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if ((lin / static_cast<unsigned>(p.num_sms)) & 1u) __nanosleep(p.stagger_ns);
+  }
   ptx::mbar_expect_tx(&c.b->m_full, two_m ? 32768u : 16384u);
   ptx::tma_load_4d(&p.tmM1, &c.b->m_full, c.m1, 0, m_row0, h, n);
   if (two_m) ptx::tma_load_4d(&p.tmM2, &c.b->m_full, c.m2, 0, m_row0, h, n);
@@ -611,19 +622,30 @@ inline FlashPlan plan_flash(int n, int T, int heads, const bf16* q, const bf16* 
   memset(&base, 0, sizeof(base));
   base.T = T, base.heads = heads, base.scale = 0.125f, base.lse2 = lse2, base.delta = delta;
   base.lazy = getenv("MDC_FLASH_LAZY") ? static_cast<float>(atof(getenv("MDC_FLASH_LAZY"))) : 8.f;
+  base.num_sms = g_num_sms();
+  const char* st_env = getenv("MDC_FLASH_STAGGER_NS");  // "fwd,dkv,dq" or one value for all three
+  unsigned st3[3] = {0u, 0u, 0u};
+  if (st_env) {
+    int a = 0, b = -1, c3 = -1;
+    sscanf(st_env, "%d,%d,%d", &a, &b, &c3);
+    st3[0] = a, st3[1] = b >= 0 ? b : a, st3[2] = c3 >= 0 ? c3 : (b >= 0 ? b : a);
+  }
   f.fwd = base;
+  f.fwd.stagger_ns = st3[0];
   f.fwd.tmM1 = fa_map(q, ld_qkv, T, heads, n, 128);
   f.fwd.tmM2 = f.fwd.tmM1;
   f.fwd.tmS1 = fa_map(k, ld_qkv, T, heads, n, 64);
   f.fwd.tmS2 = fa_map(v, ld_qkv, T, heads, n, 64);
   f.fwd.out1 = o, f.fwd.ld_out = ld_o, f.fwd.img_stride_out = 1LL * T * ld_o;
   f.dkv = base;
+  f.dkv.stagger_ns = st3[1];
   f.dkv.tmM1 = fa_map(k, ld_qkv, T, heads, n, 128);
   f.dkv.tmM2 = fa_map(v, ld_qkv, T, heads, n, 128);
   f.dkv.tmS1 = fa_map(q, ld_qkv, T, heads, n, 64);
   f.dkv.tmS2 = fa_map(dout, ld_o, T, heads, n, 64);
   f.dkv.out1 = dk, f.dkv.out2 = dv, f.dkv.ld_out = ld_dqkv, f.dkv.img_stride_out = 1LL * T * ld_dqkv;
   f.dq = base;
+  f.dq.stagger_ns = st3[2];
   f.dq.tmM1 = fa_map(q, ld_qkv, T, heads, n, 128);
   f.dq.tmM2 = fa_map(dout, ld_o, T, heads, n, 128);
   f.dq.tmS1 = fa_map(k, ld_qkv, T, heads, n, 64);
