@@ -151,11 +151,10 @@ int mdc_dbg_attention(int n, int T, int heads, int dh, const void* qkv, void* o,
     set_kernel_attrs_for_device();
     const int d = heads * dh;
     const long long ldq = 3LL * d, ldo = d;
-    const size_t stat = static_cast<size_t>(n) * heads * T + 64;
     float *lse2 = nullptr, *delta = nullptr, *S = nullptr;
     bf16 *P = nullptr, *dummy_do = nullptr, *dummy_dq = nullptr;
-    MDC_CUDA(cudaMalloc(&lse2, stat * 4));
-    MDC_CUDA(cudaMalloc(&delta, stat * 4));
+    MDC_CUDA(cudaMalloc(&lse2, flash_stat_floats(n, heads, T) * 4));
+    MDC_CUDA(cudaMalloc(&delta, flash_stat_floats(n, heads, T) * 4));
     const bool bwd = dout != nullptr;
     if (!bwd) {  // the planners encode tensor maps for the gradient operands too
       MDC_CUDA(cudaMalloc(&dummy_do, 1ull * n * T * ldo * 2 + 256));

@@ -817,9 +817,9 @@ inline Tensor* Engine::self_attention(Tensor* qkv, int heads, const std::string&
   auto* op = new SelfAttnOp();
   op->E = this, op->qkv = qkv, op->o = o;
   const bool flash = dh == 64 && !getenv("MDC_NO_FLASH");
-  const size_t stat = static_cast<size_t>(n) * heads * T + 64, pel = static_cast<size_t>(n) * heads * T * (((T + 7) / 8) * 8) + 64;
-  float* lse2 = flash ? arena.make<float>(stat) : nullptr;
-  float* delta = flash ? arena.make<float>(stat) : nullptr;
+  const size_t pel = static_cast<size_t>(n) * heads * T * (((T + 7) / 8) * 8) + 64;
+  float* lse2 = flash ? arena.make<float>(flash_stat_floats(n, heads, T)) : nullptr;
+  float* delta = flash ? arena.make<float>(flash_stat_floats(n, heads, T)) : nullptr;
   bf16* P = flash ? nullptr : arena.make<bf16>(pel);
   if (!flash) attn_S_floats = std::max<size_t>(attn_S_floats, pel);
   // the fp32 score scratch is shared by all unfused attentions: allocated after the tapes are built (finalize_plans)

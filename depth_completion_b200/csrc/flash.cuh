@@ -4,10 +4,14 @@
 // reference's F.scaled_dot_product_attention call (diffusers AttnProcessor2_0).
 //
 // All three kernels share one structure: a CTA owns a 128-row tile ("M side"), streams 64-row tiles of the other
-// side through a TMA pipeline, and alternates   MMA group 1 (scores)  ->  128 softmax threads (one per TMEM lane /
-// row)  ->  MMA group 2 (consumes the bf16 probabilities the softmax threads wrote to swizzled shared memory).
-// Everything is single-buffered inside a CTA; two CTAs share an SM (<= 96 KB smem, 256 TMEM columns each) so one
-// CTA's tensor work overlaps the other's exponentials.
+// side through a TMA pipeline, and alternates   MMA group 1 (scores)  ->  softmax / elementwise threads  ->  MMA group
+// 2 (consumes the bf16 probabilities the softmax threads wrote to swizzled shared memory).  Two CTAs share an SM
+// (<= 96 KB smem, 256 TMEM columns each) so one CTA's tensor work overlaps the other's exponentials.
+// Forward: four softmax warps, one per TMEM lane quadrant (a thread owns a whole row: the row maximum and sum need no
+// exchange).  Backward: eight elementwise warps, two per quadrant with 32 columns each -- nothing there reduces over a
+// row, a lone warp's per-tile chain (TMEM read -> exponentials -> two shared-memory tiles) is latency-bound, and twice
+// the warps at half the registers shortens it (dK/dV + dQ at T = 6912, 2 heads: 288 -> 229 us).  The same split of the
+// forward needs a per-tile exchange of row maxima and measured slower with two CTAs per SM (107 -> 121 us).
 //
 //   flash_fwd_kernel : CTA = 128 queries.  S = Q K^T (N = 64 keys), online softmax in registers, O += P V in TMEM
 //                      (rescaled lazily); writes O (bf16) and LSE2 = m2 + log2(l) (base-2, scale folded).
@@ -24,7 +28,8 @@
 
 namespace mdc {
 
-constexpr int FA_THREADS = 192;
+constexpr int FA_THREADS_FWD = 192;  // forward: producer, MMA issuer, 4 softmax warps (one per TMEM lane quadrant)
+constexpr int FA_THREADS = 320;      // backward: producer, MMA issuer, 8 elementwise warps (two per quadrant, 32 columns each)
 constexpr int FA_STAGES = 2;
 constexpr float FA_LOG2E = 1.4426950408889634f;
 
@@ -34,13 +39,7 @@ struct FlashParams {
   int T, heads;
   float scale;             // 1/sqrt(head_dim)
   float lazy;              // forward: O is rescaled only when a row maximum grows by more than 2^lazy (0 = always)
-  // Two CTAs share an SM and, per sub-partition, one TMEM read port (16 B/clk) and one MUFU: a key tile costs each
-  // softmax warp ~512 clk of TMEM reads and ~512 clk of exponentials.  CTAs that start together run in lockstep -- both
-  // load, then both exponentiate -- and the tile takes the SUM of the two; started half a tile period apart they
-  // interleave (one loads while the other exponentiates).  The second resident CTA of an SM (linear block id / SM count
-  // odd) therefore delays its first loads by `stagger_ns`.
-  unsigned stagger_ns;
-  int num_sms;
+  int Tp;                  // row stride of lse2 / delta: T rounded up to 64 (padding: lse2 = +inf, delta = 0)
   // outputs / side inputs
   bf16* out1;              // fwd: O      dkv: dK     dq: dQ
   bf16* out2;              //             dkv: dV
@@ -88,7 +87,6 @@ __device__ __forceinline__ float fa_max3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
-__device__ __forceinline__ void fa_named_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 struct FaSmem {
   uint64_t m_full, s_full[FA_STAGES], s_empty[FA_STAGES], acc_full, acc_empty, p_full, p_empty, o_full, o_empty;
@@ -105,7 +103,7 @@ struct FaCtx {
   uint32_t tmem;
   int warp, lane;
 };
-__device__ __forceinline__ FaCtx fa_setup(uint8_t* smem_raw, uint32_t tmem_cols) {
+__device__ __forceinline__ FaCtx fa_setup(uint8_t* smem_raw, uint32_t tmem_cols, uint32_t ew = 8) {
   FaCtx c;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   c.b = reinterpret_cast<FaSmem*>(smem);
@@ -116,9 +114,9 @@ __device__ __forceinline__ FaCtx fa_setup(uint8_t* smem_raw, uint32_t tmem_cols)
   if (threadIdx.x == 0) {
     ptx::mbar_init(&c.b->m_full, 1);
     for (int i = 0; i < FA_STAGES; ++i) ptx::mbar_init(&c.b->s_full[i], 1), ptx::mbar_init(&c.b->s_empty[i], 1);
-    ptx::mbar_init(&c.b->acc_full, 1), ptx::mbar_init(&c.b->acc_empty, 4);
-    ptx::mbar_init(&c.b->p_full, 4), ptx::mbar_init(&c.b->p_empty, 1);
-    ptx::mbar_init(&c.b->o_full, 1), ptx::mbar_init(&c.b->o_empty, 4);
+    ptx::mbar_init(&c.b->acc_full, 1), ptx::mbar_init(&c.b->acc_empty, ew);
+    ptx::mbar_init(&c.b->p_full, ew), ptx::mbar_init(&c.b->p_empty, 1);
+    ptx::mbar_init(&c.b->o_full, 1), ptx::mbar_init(&c.b->o_empty, ew);
     ptx::fence_mbar_init();
   }
   if (c.warp == 1) ptx::tmem_alloc(&c.b->tmem_slot, tmem_cols);
@@ -137,21 +135,24 @@ __device__ __forceinline__ void fa_teardown(const FaCtx& c, uint32_t tmem_cols) 
   if (c.warp == 1) ptx::tmem_dealloc(c.tmem, tmem_cols);
 }
 // TMA producer shared by the three kernels: the resident tile(s) once, then the streamed pairs.
+// `stats` (dK/dV kernel): LSE2 and delta of the streamed query tile ride on the same stage barrier as two 256-byte bulk
+// copies (rows are padded to a multiple of 64 entries, see FlashParams::Tp).
 __device__ __forceinline__ void fa_producer(const FaCtx& c, const FlashParams& p, int m_row0, int h, int n, int n_iter,
-                                            bool two_m) {
-  if (p.stagger_ns) {
-    const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    if ((lin / static_cast<unsigned>(p.num_sms)) & 1u) __nanosleep(p.stagger_ns);
-  }
+                                            bool two_m, bool stats = false) {
+  const long long srow = (static_cast<long long>(n) * p.heads + h) * p.Tp;
   ptx::mbar_expect_tx(&c.b->m_full, two_m ? 32768u : 16384u);
   ptx::tma_load_4d(&p.tmM1, &c.b->m_full, c.m1, 0, m_row0, h, n);
   if (two_m) ptx::tma_load_4d(&p.tmM2, &c.b->m_full, c.m2, 0, m_row0, h, n);
   for (int i = 0; i < n_iter; ++i) {
     const int s = i % FA_STAGES;
     ptx::mbar_wait(&c.b->s_empty[s], ((i / FA_STAGES) & 1) ^ 1);
-    ptx::mbar_expect_tx(&c.b->s_full[s], 16384u);
+    ptx::mbar_expect_tx(&c.b->s_full[s], stats ? 16384u + 512u : 16384u);
     ptx::tma_load_4d(&p.tmS1, &c.b->s_full[s], c.st + s * 16384, 0, i * 64, h, n);
     ptx::tma_load_4d(&p.tmS2, &c.b->s_full[s], c.st + s * 16384 + 8192, 0, i * 64, h, n);
+    if (stats) {
+      ptx::bulk_load_1d(&c.b->lse_s[s][0], p.lse2 + srow + i * 64, 256u, &c.b->s_full[s]);
+      ptx::bulk_load_1d(&c.b->del_s[s][0], p.delta + srow + i * 64, 256u, &c.b->s_full[s]);
+    }
   }
 }
 __device__ __forceinline__ void fa_warp_arrive(uint64_t* bar, int lane) {
@@ -162,10 +163,10 @@ __device__ __forceinline__ void fa_warp_arrive(uint64_t* bar, int lane) {
 // ---------------------------------------------------------------------------------------------------- forward
 // Software-pipelined: S is double-buffered in TMEM (S(i+1) = Q K(i+1)^T is issued before P(i) V(i)), P is
 // double-buffered in shared memory, O accumulates in TMEM (lazy rescaling, see the softmax loop).
-__global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_constant__ FlashParams p) {
+__global__ void __launch_bounds__(FA_THREADS_FWD, 2) flash_fwd_kernel(const __grid_constant__ FlashParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t TCOLS = 256;  // S0: [0,64)  S1: [64,128)  O tile: [128,192)
-  FaCtx c = fa_setup(smem_raw, TCOLS);
+  FaCtx c = fa_setup(smem_raw, TCOLS, 4);
   // extra barriers for the double buffers live in the spare m2 tile slot's first bytes? no: reuse FaSmem fields:
   //   acc_full/acc_empty -> S buffer 0, o_full/o_empty -> O tile, p_full/p_empty -> P buffer 0; buffer-1 barriers below.
   // [0] s1_full [1] s1_empty [2] p1_full [3] p1_empty [4] o_final (m2 tile unused here).  o_full completes once per key
@@ -252,10 +253,13 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
           if (j >= valid) raw[j] = 0xff800000u;  // -inf
       }
       // row maximum on the raw scores (the scale is positive), three-input max: 32 instructions for 64 columns
-      float mx = -INFINITY;
+      float mx = -INFINITY, mx1 = -INFINITY;  // two independent chains
 #pragma unroll
-      for (int j = 0; j < 64; j += 2) mx = fa_max3(mx, __uint_as_float(raw[j]), __uint_as_float(raw[j + 1]));
-      mx *= c2;
+      for (int j = 0; j < 64; j += 4) {
+        mx = fa_max3(mx, __uint_as_float(raw[j]), __uint_as_float(raw[j + 1]));
+        mx1 = fa_max3(mx1, __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]));
+      }
+      mx = fmaxf(mx, mx1) * c2;
       const bool grow = mx > m + p.lazy;  // always true for the first tile (m = -inf)
       const float m_new = grow ? mx : m;
       const float alpha = grow ? fa_exp2(m - m_new) : 1.f;
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
           for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[ch * 8 + j]) * inv;
           *reinterpret_cast<BF8*>(dst + ch * 8) = f_to_bf8(v);
         }
-        p.lse2[(static_cast<long long>(n) * p.heads + h) * p.T + q0 + row] = m + log2f(l);
+        p.lse2[(static_cast<long long>(n) * p.heads + h) * p.Tp + q0 + row] = m + log2f(l);
       }
     }
   }
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_fwd_kernel(const __grid_c
 
 // delta[n, h, t] = sum_c dO[n, t, h*64 + c] * O[n, t, h*64 + c]     (one warp per (token, head))
 __global__ void flash_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, long long ld, int N, int T,
-                                   int heads, float* __restrict__ delta) {
+                                   int Tp, int heads, float* __restrict__ delta) {
   ptx::pdl_wait();
   ptx::pdl_launch();
   const long long w = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) >> 5;
@@ -334,20 +338,23 @@ __global__ void flash_delta_kernel(const bf16* __restrict__ o, const bf16* __res
   float s = warp_sum(a.x * b.x + a.y * b.y);
   if (lane == 0) {
     const long long n = tok / T, t = tok % T;
-    delta[(n * heads + h) * T + t] = s;
+    delta[(n * heads + h) * Tp + t] = s;
   }
 }
 
 // ---------------------------------------------------------------------------------------------------- dK, dV
+// Eight elementwise warps: two per TMEM lane quadrant, each owning 32 of the tile's 64 columns.  The per-warp chain
+// (TMEM read -> exponentials -> two shared-memory tiles) is latency-bound, not throughput-bound, so twice the warps at
+// half the registers is what shortens it; nothing in the backward needs a row reduction, the split costs no exchange.
 __global__ void __launch_bounds__(FA_THREADS, 2) flash_dkv_kernel(const __grid_constant__ FlashParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t TCOLS = 256;  // S^T [0,64)  dP^T [64,128)  dV [128,192)  dK [192,256)
-  FaCtx c = fa_setup(smem_raw, TCOLS);
+  FaCtx c = fa_setup(smem_raw, TCOLS, 8);
   const int k0 = blockIdx.x * 128, h = blockIdx.y, n = blockIdx.z;
   const int n_iter = (p.T + 63) / 64;  // query tiles
   const uint32_t idesc_k = ptx::make_idesc_bf16(128, 64, 0, 0), idesc_mn = ptx::make_idesc_bf16(128, 64, 0, 1);
   if (c.warp == 0) {
-    if (c.lane == 0) fa_producer(c, p, k0, h, n, n_iter, true);
+    if (c.lane == 0) fa_producer(c, p, k0, h, n, n_iter, true, true);
     __syncwarp();
   } else if (c.warp == 1) {
     const bool leader = ptx::elect_one();
@@ -389,41 +396,32 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dkv_kernel(const __grid_c
     if (leader) ptx::umma_commit(&c.b->o_full);  // accumulators final
     __syncwarp();
   } else {
-    const int q = c.warp & 3, row = q * 32 + c.lane;
-    const uint32_t t_row = c.tmem + (static_cast<uint32_t>(q * 32) << 16);
+    const int q = c.warp & 3, row = q * 32 + c.lane, hf = (c.warp - 2) >> 2;  // column half of this warp
+    const uint32_t t_row = c.tmem + (static_cast<uint32_t>(q * 32) << 16) + hf * 32;
     const float c2 = p.scale * FA_LOG2E;
-    const float* lse = p.lse2 + (static_cast<long long>(n) * p.heads + h) * p.T;
-    const float* del = p.delta + (static_cast<long long>(n) * p.heads + h) * p.T;
-    const int st_tid = threadIdx.x - 64;  // 0..127
+    const float2 cc2 = make_float2(c2, c2), sc2 = make_float2(p.scale, p.scale);
     for (int i = 0; i < n_iter; ++i) {
-      const int qbase = i * 64, sb = i & 1;
-      {  // stage LSE2 / delta of this query tile; out-of-range queries get LSE2 = +inf, i.e. probability 0
-        const int j = st_tid & 63, qq = qbase + j;
-        if (st_tid < 64)
-          c.b->lse_s[sb][j] = qq < p.T ? __ldg(lse + qq) : INFINITY;
-        else
-          c.b->del_s[sb][j] = qq < p.T ? __ldg(del + qq) : 0.f;
-      }
-      fa_named_sync();
+      const int s = i % FA_STAGES;
       ptx::mbar_wait(&c.b->acc_full, i & 1);
       ptx::tc_fence_after();
-      uint32_t rs[64], rd[64];  // whole S^T / dP^T row of this tile; frees the TMEM buffers for the next tile's MMAs
-      ptx::tmem_ld32(t_row, *reinterpret_cast<uint32_t(*)[32]>(&rs[0]));
-      ptx::tmem_ld32(t_row + 32, *reinterpret_cast<uint32_t(*)[32]>(&rs[32]));
-      ptx::tmem_ld32(t_row + 64, *reinterpret_cast<uint32_t(*)[32]>(&rd[0]));
-      ptx::tmem_ld32(t_row + 96, *reinterpret_cast<uint32_t(*)[32]>(&rd[32]));
+      uint32_t rs[32], rd[32];  // this warp's half of the S^T / dP^T rows; frees the TMEM buffers for the next tile's MMAs
+      ptx::tmem_ld32(t_row, rs);
+      ptx::tmem_ld32(t_row + 64, rd);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       fa_warp_arrive(&c.b->acc_empty, c.lane);
+      // LSE2 / delta of the tile's queries arrived with Q / dO (same stage barrier; S^T complete implies they have landed,
+      // the wait only makes the bulk-copied bytes visible to this thread).  Padding queries carry LSE2 = +inf: probability 0.
+      ptx::mbar_wait(&c.b->s_full[s], (i / FA_STAGES) & 1);
       ptx::mbar_wait(&c.b->p_empty, (i & 1) ^ 1);
-      const float2 cc2 = make_float2(c2, c2), sc2 = make_float2(p.scale, p.scale);
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
+      for (int ch = 0; ch < 4; ++ch) {
         float pv[8], dv[8];
-        const float4 l0 = *reinterpret_cast<const float4*>(&c.b->lse_s[sb][ch * 8]);
-        const float4 l1 = *reinterpret_cast<const float4*>(&c.b->lse_s[sb][ch * 8 + 4]);
-        const float4 d0 = *reinterpret_cast<const float4*>(&c.b->del_s[sb][ch * 8]);
-        const float4 d1 = *reinterpret_cast<const float4*>(&c.b->del_s[sb][ch * 8 + 4]);
+        const int c0 = hf * 32 + ch * 8;
+        const float4 l0 = *reinterpret_cast<const float4*>(&c.b->lse_s[s][c0]);
+        const float4 l1 = *reinterpret_cast<const float4*>(&c.b->lse_s[s][c0 + 4]);
+        const float4 d0 = *reinterpret_cast<const float4*>(&c.b->del_s[s][c0]);
+        const float4 d1 = *reinterpret_cast<const float4*>(&c.b->del_s[s][c0 + 4]);
         const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
         const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
@@ -437,8 +435,8 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dkv_kernel(const __grid_c
           pv[j] = pr.x, pv[j + 1] = pr.y;
           dv[j] = d.x, dv[j + 1] = d.y;
         }
-        fa_store_row_chunk(c.p1, row, ch, pv);
-        fa_store_row_chunk(c.p2, row, ch, dv);
+        fa_store_row_chunk(c.p1, row, hf * 4 + ch, pv);
+        fa_store_row_chunk(c.p2, row, hf * 4 + ch, dv);
       }
       ptx::fence_proxy_async_smem();
       fa_warp_arrive(&c.b->p_full, c.lane);
@@ -446,23 +444,20 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dkv_kernel(const __grid_c
     ptx::mbar_wait(&c.b->o_full, 0);
     ptx::tc_fence_after();
     const bool ok = k0 + row < p.T;
-    const long long off = n * p.img_stride_out + static_cast<long long>(k0 + row) * p.ld_out + h * 64;
+    const long long off = n * p.img_stride_out + static_cast<long long>(k0 + row) * p.ld_out + h * 64 + hf * 32;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       bf16* dst = (which == 0 ? p.out2 : p.out1) + off;  // TMEM [128,192) = dV -> out2 ; [192,256) = dK -> out1
+      uint32_t r[32];
+      ptx::tmem_ld32(t_row + 128 + which * 64, r);
+      ptx::tmem_ld_wait();
+      if (ok) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t r[32];
-        ptx::tmem_ld32(t_row + 128 + which * 64 + half * 32, r);
-        ptx::tmem_ld_wait();
-        if (ok) {
+        for (int ch = 0; ch < 4; ++ch) {
+          float v[8];
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[ch * 8 + j]);
-            *reinterpret_cast<BF8*>(dst + half * 32 + ch * 8) = f_to_bf8(v);
-          }
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[ch * 8 + j]);
+          *reinterpret_cast<BF8*>(dst + ch * 8) = f_to_bf8(v);
         }
       }
     }
@@ -474,7 +469,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dkv_kernel(const __grid_c
 __global__ void __launch_bounds__(FA_THREADS, 2) flash_dq_kernel(const __grid_constant__ FlashParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t TCOLS = 256;  // S [0,64)  dP [64,128)  dQ [128,192)
-  FaCtx c = fa_setup(smem_raw, TCOLS);
+  FaCtx c = fa_setup(smem_raw, TCOLS, 8);
   const int q0 = blockIdx.x * 128, h = blockIdx.y, n = blockIdx.z;
   const int n_iter = (p.T + 63) / 64;  // key tiles
   const uint32_t idesc_k = ptx::make_idesc_bf16(128, 64, 0, 0), idesc_mn = ptx::make_idesc_bf16(128, 64, 0, 1);
@@ -520,31 +515,29 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dq_kernel(const __grid_co
     if (leader) ptx::umma_commit(&c.b->o_full);
     __syncwarp();
   } else {
-    const int q = c.warp & 3, row = q * 32 + c.lane;
-    const uint32_t t_row = c.tmem + (static_cast<uint32_t>(q * 32) << 16);
+    const int q = c.warp & 3, row = q * 32 + c.lane, hf = (c.warp - 2) >> 2;  // column half of this warp
+    const uint32_t t_row = c.tmem + (static_cast<uint32_t>(q * 32) << 16) + hf * 32;
     const float c2 = p.scale * FA_LOG2E;
     const bool ok = q0 + row < p.T;
-    const long long sidx = (static_cast<long long>(n) * p.heads + h) * p.T + q0 + row;
+    const long long sidx = (static_cast<long long>(n) * p.heads + h) * p.Tp + q0 + row;
     const float lse = ok ? p.lse2[sidx] : 0.f, del = ok ? p.delta[sidx] : 0.f;
     const float nlse = ok ? -lse : -INFINITY;  // rows past T produce probability 0
     const float ndel_s = -del * p.scale;
     for (int i = 0; i < n_iter; ++i) {
       ptx::mbar_wait(&c.b->acc_full, i & 1);
       ptx::tc_fence_after();
-      uint32_t rs[64], rd[64];
-      ptx::tmem_ld32(t_row, *reinterpret_cast<uint32_t(*)[32]>(&rs[0]));
-      ptx::tmem_ld32(t_row + 32, *reinterpret_cast<uint32_t(*)[32]>(&rs[32]));
-      ptx::tmem_ld32(t_row + 64, *reinterpret_cast<uint32_t(*)[32]>(&rd[0]));
-      ptx::tmem_ld32(t_row + 96, *reinterpret_cast<uint32_t(*)[32]>(&rd[32]));
+      uint32_t rs[32], rd[32];
+      ptx::tmem_ld32(t_row, rs);
+      ptx::tmem_ld32(t_row + 64, rd);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       fa_warp_arrive(&c.b->acc_empty, c.lane);
       ptx::mbar_wait(&c.b->p_empty, (i & 1) ^ 1);
-      const int valid = p.T - i * 64;
+      const int valid = p.T - i * 64 - hf * 32;  // keys of this warp's half that exist
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
+      for (int ch = 0; ch < 4; ++ch) {
         float dv[8];
-        if (valid >= 64) {
+        if (valid >= 32) {
 #pragma unroll
           for (int j = 0; j < 8; j += 2) {  // packed fp32x2
             const float2 a = __ffma2_rn(make_float2(__uint_as_float(rs[ch * 8 + j]), __uint_as_float(rs[ch * 8 + j + 1])),
@@ -563,27 +556,24 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_dq_kernel(const __grid_co
             dv[j] = pr * (__uint_as_float(rd[ch * 8 + j]) - del) * p.scale;
           }
         }
-        fa_store_row_chunk(c.p1, row, ch, dv);
+        fa_store_row_chunk(c.p1, row, hf * 4 + ch, dv);
       }
       ptx::fence_proxy_async_smem();
       fa_warp_arrive(&c.b->p_full, c.lane);
     }
     ptx::mbar_wait(&c.b->o_full, 0);
     ptx::tc_fence_after();
-    bf16* dst = p.out1 + n * p.img_stride_out + static_cast<long long>(q0 + row) * p.ld_out + h * 64;
+    bf16* dst = p.out1 + n * p.img_stride_out + static_cast<long long>(q0 + row) * p.ld_out + h * 64 + hf * 32;
+    uint32_t r[32];
+    ptx::tmem_ld32(t_row + 128, r);
+    ptx::tmem_ld_wait();
+    if (ok) {
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t r[32];
-      ptx::tmem_ld32(t_row + 128 + half * 32, r);
-      ptx::tmem_ld_wait();
-      if (ok) {
+      for (int ch = 0; ch < 4; ++ch) {
+        float v[8];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[ch * 8 + j]);
-          *reinterpret_cast<BF8*>(dst + half * 32 + ch * 8) = f_to_bf8(v);
-        }
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[ch * 8 + j]);
+        *reinterpret_cast<BF8*>(dst + ch * 8) = f_to_bf8(v);
       }
     }
   }
@@ -604,6 +594,14 @@ struct FlashPlan {
   double flops_fwd = 0, flops_bwd = 0;
 };
 
+// lse2 / delta are [n, heads, Tp] with Tp = T rounded up to the 64-query tile, + 64 floats of slack.
+inline int flash_stat_stride(int T) { return (T + 63) & ~63; }
+inline size_t flash_stat_floats(int n, int heads, int T) { return static_cast<size_t>(n) * heads * flash_stat_stride(T) + 64; }
+__global__ void flash_stat_init_kernel(float* lse2, float* delta, long long tot) {
+  const long long i = blockIdx.x * 256LL + threadIdx.x;
+  if (i < tot) lse2[i] = INFINITY, delta[i] = 0.f;
+}
+
 inline CUtensorMap fa_map(const bf16* base, long long ld, int T, int heads, int n, int box_rows) {
   uint64_t dims[4] = {64, (uint64_t)T, (uint64_t)heads, (uint64_t)n};
   uint64_t str[3] = {(uint64_t)ld, 64, (uint64_t)T * ld};
@@ -620,32 +618,27 @@ inline FlashPlan plan_flash(int n, int T, int heads, const bf16* q, const bf16* 
   f.grid = dim3((T + 127) / 128, heads, n);
   FlashParams base;
   memset(&base, 0, sizeof(base));
-  base.T = T, base.heads = heads, base.scale = 0.125f, base.lse2 = lse2, base.delta = delta;
-  base.lazy = getenv("MDC_FLASH_LAZY") ? static_cast<float>(atof(getenv("MDC_FLASH_LAZY"))) : 8.f;
-  base.num_sms = g_num_sms();
-  const char* st_env = getenv("MDC_FLASH_STAGGER_NS");  // "fwd,dkv,dq" or one value for all three
-  unsigned st3[3] = {0u, 0u, 0u};
-  if (st_env) {
-    int a = 0, b = -1, c3 = -1;
-    sscanf(st_env, "%d,%d,%d", &a, &b, &c3);
-    st3[0] = a, st3[1] = b >= 0 ? b : a, st3[2] = c3 >= 0 ? c3 : (b >= 0 ? b : a);
+  base.T = T, base.Tp = flash_stat_stride(T), base.heads = heads, base.scale = 0.125f, base.lse2 = lse2, base.delta = delta;
+  {  // padding entries of the statistics rows: LSE2 = +inf (probability 0), delta = 0; the kernels only write t < T
+    const long long tot = 1LL * n * heads * base.Tp;
+    flash_stat_init_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256>>>(lse2, delta, tot);
+    MDC_CUDA(cudaGetLastError());
+    MDC_CUDA(cudaStreamSynchronize(0));
   }
+  base.lazy = getenv("MDC_FLASH_LAZY") ? static_cast<float>(atof(getenv("MDC_FLASH_LAZY"))) : 8.f;
   f.fwd = base;
-  f.fwd.stagger_ns = st3[0];
   f.fwd.tmM1 = fa_map(q, ld_qkv, T, heads, n, 128);
   f.fwd.tmM2 = f.fwd.tmM1;
   f.fwd.tmS1 = fa_map(k, ld_qkv, T, heads, n, 64);
   f.fwd.tmS2 = fa_map(v, ld_qkv, T, heads, n, 64);
   f.fwd.out1 = o, f.fwd.ld_out = ld_o, f.fwd.img_stride_out = 1LL * T * ld_o;
   f.dkv = base;
-  f.dkv.stagger_ns = st3[1];
   f.dkv.tmM1 = fa_map(k, ld_qkv, T, heads, n, 128);
   f.dkv.tmM2 = fa_map(v, ld_qkv, T, heads, n, 128);
   f.dkv.tmS1 = fa_map(q, ld_qkv, T, heads, n, 64);
   f.dkv.tmS2 = fa_map(dout, ld_o, T, heads, n, 64);
   f.dkv.out1 = dk, f.dkv.out2 = dv, f.dkv.ld_out = ld_dqkv, f.dkv.img_stride_out = 1LL * T * ld_dqkv;
   f.dq = base;
-  f.dq.stagger_ns = st3[2];
   f.dq.tmM1 = fa_map(q, ld_qkv, T, heads, n, 128);
   f.dq.tmM2 = fa_map(dout, ld_o, T, heads, n, 128);
   f.dq.tmS1 = fa_map(k, ld_qkv, T, heads, n, 64);
@@ -666,13 +659,13 @@ inline void flash_set_attrs() {
 }
 inline void run_flash_fwd(const FlashPlan& f, cudaStream_t st) {
   flash_set_attrs();
-  launch_k(flash_fwd_kernel, f.grid, dim3(FA_THREADS), FA_SMEM, st, f.fwd);
+  launch_k(flash_fwd_kernel, f.grid, dim3(FA_THREADS_FWD), FA_SMEM, st, f.fwd);
 }
 inline void run_flash_bwd(const FlashPlan& f, cudaStream_t st) {
   flash_set_attrs();
   const long long warps = 1LL * f.N * f.T * f.heads;
   launch_k(flash_delta_kernel, dim3(static_cast<unsigned>((warps * 32 + 255) / 256)), dim3(256), 0, st, f.o, f.dout, f.ld_o,
-           f.N, f.T, f.heads, f.delta);
+           f.N, f.T, f.dq.Tp, f.heads, f.delta);
   launch_k(flash_dkv_kernel, f.grid, dim3(FA_THREADS), FA_SMEM, st, f.dkv);
   launch_k(flash_dq_kernel, f.grid, dim3(FA_THREADS), FA_SMEM, st, f.dq);
 }
