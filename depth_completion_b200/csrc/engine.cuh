@@ -69,6 +69,11 @@ struct Tensor {
 
 struct Op {
   std::string name;
+  // A resnet's 1x1 conv_shortcut only depends on the block input: it runs on the engine's side stream beside norm1 ->
+  // conv1 -> norm2 (forward) and beside norm2 <- conv1 <- ... (backward).  `side` marks that op; the block's norm1 carries
+  // `fork_fwd` (record the fork event before it is launched) and `join_bwd` (its backward accumulates into the gradient
+  // the shortcut's backward writes first: wait for the side stream before launching it).
+  bool side = false, fork_fwd = false, join_bwd = false;
   virtual ~Op() {}
   virtual void plan_bwd() {}
   virtual void fwd(cudaStream_t) = 0;
@@ -387,6 +392,9 @@ struct Engine {
   // caller's (mdc_set_stream; the Python binding passes torch's current stream on every call).  Graphs are captured
   // on the private `cap_stream` (capture is not allowed on the legacy default stream) and launched on `stream`.
   cudaStream_t stream = 0, own_stream = 0, cap_stream = 0;
+  cudaStream_t side_stream = 0;  // second branch of the step graph (Op::side); joins `stream` before anything reads its results
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  float* split_ws_side = nullptr;  // split-K workspace of the side-stream GEMMs (they overlap main-stream split-K GEMMs)
   void set_stream(cudaStream_t s) { stream = s ? s : own_stream; }
   // stream-ordered copy + synchronisation (a plain cudaMemcpy runs on the legacy default stream, which is NOT ordered
   // with a caller-provided non-blocking stream)
@@ -803,10 +811,15 @@ inline Tensor* Engine::layer_norm(Tensor* x, const std::string& key) {
 }
 inline Tensor* Engine::resnet(Tensor* x, int cout, const std::string& key, bool temb, float eps, Tensor* out) {
   Tensor* h = group_norm(x, key + ".norm1", eps, true);
+  Op* norm1 = cur_ops->back().get();
   h = conv3x3(h, cout, key + ".conv1", nullptr, nullptr, temb ? key + ".time_emb_proj" : "");
   h = group_norm(h, key + ".norm2", eps, true);
   Tensor* sc = x;
-  if (x->c != cout) sc = linear(x, cout, key + ".conv_shortcut", true);
+  if (x->c != cout) {
+    sc = linear(x, cout, key + ".conv_shortcut", true);
+    static const bool no_side = getenv("MDC_NO_SIDE") != nullptr;
+    if (!no_side) cur_ops->back()->side = true, norm1->fork_fwd = norm1->join_bwd = true;
+  }
   Tensor* y = conv3x3(h, cout, key + ".conv2", sc, out);
   if (y->name.empty()) y->name = key, named[key] = y;
   return y;
@@ -1251,6 +1264,24 @@ inline void Engine::finalize_plans() {
   }
   split_ws = arena.make<float>(split_ws_floats + 64);
   for (GemmPlan* g : split_plans) g->p.ws = split_ws;
+  {  // side-stream GEMMs get their own partial-sum workspace
+    size_t side_fl = 0;
+    std::vector<LinearOp*> side_ops;
+    for (auto* ops : {&unet_ops, &dec_ops})
+      for (auto& op : *ops)
+        if (op->side)
+          if (auto* l = dynamic_cast<LinearOp*>(op.get())) {
+            side_ops.push_back(l);
+            for (GemmPlan* g : {&l->pf, &l->pb})
+              if (g->p.ksplit > 1) side_fl = std::max(side_fl, static_cast<size_t>(g->p.ksplit) * static_cast<size_t>(g->p.ws_split_stride));
+          }
+    if (side_fl) {
+      split_ws_side = arena.make<float>(side_fl + 64);
+      for (LinearOp* l : side_ops)
+        for (GemmPlan* g : {&l->pf, &l->pb})
+          if (g->p.ksplit > 1) g->p.ws = split_ws_side;
+    }
+  }
   for (auto* ops : {&unet_ops, &dec_ops}) {  // one reduction launch per split-K GEMM
     std::vector<const GemmPlan*> f, b;
     for (auto& op : *ops) op->gemm_plans(f, b);
@@ -1298,6 +1329,9 @@ inline Engine::Engine(const mdc_config& c, std::shared_ptr<WeightBank> share) : 
   }
   MDC_CUDA(cudaStreamCreate(&own_stream));  // blocking: implicitly ordered with the legacy default stream for plain C callers
   MDC_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+  MDC_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+  MDC_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+  MDC_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
   stream = own_stream;
   use_graph = getenv("MDC_NO_GRAPH") == nullptr;
   set_kernel_attrs_for_device();
@@ -1602,9 +1636,21 @@ inline void Engine::profile_gemm_step(float* ms_out, double* flops_out, int* lau
 
 inline void Engine::run_ops(std::vector<std::unique_ptr<Op>>& ops, bool backward) {
   static const bool dbg = getenv("MDC_DEBUG_SYNC") != nullptr;
+  auto fork = [&]() {  // the side stream may start once everything launched on `stream` so far has finished
+    MDC_CUDA(cudaEventRecord(ev_fork, stream));
+    MDC_CUDA(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+  };
   if (!backward)
     for (auto& op : ops) {
-      op->fwd(stream);
+      if (op->fork_fwd) MDC_CUDA(cudaEventRecord(ev_fork, stream));
+      if (op->side) {  // depends on the block input only (event recorded before norm1); its consumer is the next op
+        MDC_CUDA(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+        op->fwd(side_stream);
+        MDC_CUDA(cudaEventRecord(ev_join, side_stream));
+        MDC_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+      } else {
+        op->fwd(stream);
+      }
       if (dbg && begun && pt_off) {  // which op scribbles over the point list?
         int o2[2] = {0, 0};
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -1616,8 +1662,25 @@ inline void Engine::run_ops(std::vector<std::unique_ptr<Op>>& ops, bool backward
         }
       }
     }
-  else
-    for (auto it = ops.rbegin(); it != ops.rend(); ++it) (*it)->bwd(stream);
+  else {
+    bool pending = false;
+    for (auto it = ops.rbegin(); it != ops.rend(); ++it) {
+      Op* op = it->get();
+      if (op->side) {  // reads the block's output gradient (complete by now), writes the first contribution to dx
+        fork();
+        op->bwd(side_stream);
+        MDC_CUDA(cudaEventRecord(ev_join, side_stream));
+        pending = true;
+        continue;
+      }
+      if (op->join_bwd && pending) {
+        MDC_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+        pending = false;
+      }
+      op->bwd(stream);
+    }
+    if (pending) MDC_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+  }
 }
 
 inline Engine::~Engine() {
@@ -1625,6 +1688,9 @@ inline Engine::~Engine() {
   if (sample_graph) cudaGraphExecDestroy(sample_graph);
   if (own_stream) cudaStreamDestroy(own_stream);
   if (cap_stream) cudaStreamDestroy(cap_stream);
+  if (side_stream) cudaStreamDestroy(side_stream);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
 }
 inline void Engine::release_workspace() {
   MDC_CUDA(cudaStreamSynchronize(stream));
