@@ -119,9 +119,9 @@ inline void run_attention_fwd(const AttnPlan& a, cudaStream_t st) {
   launch_k(softmax_fwd_kernel, dim3(rows), dim3(256), (((a.T + 3) & ~3) + 32) * sizeof(float), st, static_cast<const float*>(a.S), a.P, a.T, a.ldS);
   run_gemm(a.p_o, st);
 }
-inline void run_attention_bwd(const AttnPlan& a, cudaStream_t st) {
+inline void run_attention_bwd(const AttnPlan& a, cudaStream_t st, const SideBranch* sb = nullptr) {
   if (a.use_flash) {
-    run_flash_bwd(a.fp, st);
+    run_flash_bwd(a.fp, st, sb);
     return;
   }
   run_gemm(a.p_dv, st);

@@ -213,7 +213,7 @@ struct SelfAttnOp : Op {  // softmax(q k^T / sqrt(dh)) v over the tokens of each
   AttnPlan a;
   void plan_bwd() override { qkv->grad_set = true; }  // q, k, v gradient slices are each written exactly once
   void fwd(cudaStream_t st) override { run_attention_fwd(a, st); }
-  void bwd(cudaStream_t st) override { run_attention_bwd(a, st); }
+  void bwd(cudaStream_t st) override;
   int n_fwd() const override { return a.use_flash ? 1 : 3; }
   int n_bwd() const override { return a.use_flash ? 3 : 5; }
   void gemm_plans(std::vector<const GemmPlan*>& f, std::vector<const GemmPlan*>& b) const override {
@@ -393,7 +393,8 @@ struct Engine {
   // on the private `cap_stream` (capture is not allowed on the legacy default stream) and launched on `stream`.
   cudaStream_t stream = 0, own_stream = 0, cap_stream = 0;
   cudaStream_t side_stream = 0;  // second branch of the step graph (Op::side); joins `stream` before anything reads its results
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;    // resnet shortcut branch
+  cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;  // attention backward (dQ beside dK/dV)
   float* split_ws_side = nullptr;  // split-K workspace of the side-stream GEMMs (they overlap main-stream split-K GEMMs)
   void set_stream(cudaStream_t s) { stream = s ? s : own_stream; }
   // stream-ordered copy + synchronisation (a plain cudaMemcpy runs on the legacy default stream, which is NOT ordered
@@ -626,6 +627,11 @@ inline void LinearOp::bwd(cudaStream_t st) {
   if (res && !alias_res)
     launch_k(add_rows_kernel, dim3(ew_grid(res->rows() * (res->c / 8))), dim3(256), 0, st, y->g, y->ld, res->g, res->ld, res->rows(), res->c,
                                                                         acc_res);
+}
+inline void SelfAttnOp::bwd(cudaStream_t st) {
+  static const bool no_side = getenv("MDC_NO_SIDE") != nullptr;
+  SideBranch sb{E->side_stream, E->ev_fork2, E->ev_join2};
+  run_attention_bwd(a, st, no_side || st == E->side_stream ? nullptr : &sb);
 }
 inline void GroupNormOp::fwd(cudaStream_t st) {
   run_gn_fwd(plan, x->d, y->d, y->ld, gamma, beta, eps, silu, stats, E->gn_scratch(), st, epi ? E->gn_epi_partial : nullptr,
@@ -1332,6 +1338,8 @@ inline Engine::Engine(const mdc_config& c, std::shared_ptr<WeightBank> share) : 
   MDC_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
   MDC_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
   MDC_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  MDC_CUDA(cudaEventCreateWithFlags(&ev_fork2, cudaEventDisableTiming));
+  MDC_CUDA(cudaEventCreateWithFlags(&ev_join2, cudaEventDisableTiming));
   stream = own_stream;
   use_graph = getenv("MDC_NO_GRAPH") == nullptr;
   set_kernel_attrs_for_device();
@@ -1691,6 +1699,8 @@ inline Engine::~Engine() {
   if (side_stream) cudaStreamDestroy(side_stream);
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
+  if (ev_fork2) cudaEventDestroy(ev_fork2);
+  if (ev_join2) cudaEventDestroy(ev_join2);
 }
 inline void Engine::release_workspace() {
   MDC_CUDA(cudaStreamSynchronize(stream));
