@@ -3,8 +3,8 @@
 What `/root/reference/predict.py:512-773` does around the pipeline call, without the CLI: find dataset directories
 (`utils.py:193-227`: a directory holding `image/` and `sparse/`), pair every image with `sparse/<same relative path>.png`
 (`predict.py:547-575`), decode the sparse PNG's first channel as `max_sparse_depth * v / 255` metres with 0 = missing
-(`utils.py:1137-1158`), run the pipeline batch by batch (through `video.complete_sequence`, so `use_prev_latent` and rank
-sharding behave as in `predict.py:599-700`), skip maps containing NaN (`predict.py:712-714`) and store each dense map as
+(`utils.py:1137-1158`), run the pipeline batch by batch (`video.sequence_batches` cuts the batches, so `use_prev_latent` and
+rank sharding behave as in `predict.py:599-700`; every batch is loaded and moved to the GPU on its own), skip maps containing NaN (`predict.py:712-714`) and store each dense map as
 `<dst>/<dataset>/dense/<relative path>.npy|npz` (`predict.py:717-728`, `utils.py:592-690`).  `compress="bl2"` needs
 blosc2, which this image does not have: it raises instead of silently writing another format.  Visualisation
 (`predict.py:731-764`) and segmentation masks are outside the hot path's data formats and are not built.
@@ -16,7 +16,6 @@ from pathlib import Path
 import numpy as np
 import torch
 
-from .video import complete_sequence
 
 IMAGE_DIR, SPARSE_DIR, DENSE_DIR = "image", "sparse", "dense"  # utils.py:20-23
 _SAVE_SUFFIX = {None: ".npy", "npy": ".npy", "npz": ".npz", "bl2": ".bl2"}

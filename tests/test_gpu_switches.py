@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 CASES = {
     "two_pass_groupnorm__unfused_attention__single_cta": ["MDC_NO_GNFUSE", "MDC_NO_FLASH", "MDC_NO_PAIR"],
     "no_splitk__materialised_upsample__plain_stores__no_alias": ["MDC_NO_SPLITK", "MDC_NO_UPCONV", "MDC_NO_TMASTORE", "MDC_NO_ALIAS"],
-    "no_graph__no_pdl": ["MDC_NO_GRAPH", "MDC_NO_PDL"],
+    "no_graph__no_pdl__no_side_stream": ["MDC_NO_GRAPH", "MDC_NO_PDL", "MDC_NO_SIDE"],
     "unfused_cross_attention__tap_by_tap_conv__epilogue_groupnorm_stats": ["MDC_NO_XFUSE", "MDC_NO_ROWSHARE", "MDC_GNEPI"],
 }
 
