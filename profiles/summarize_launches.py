@@ -3,11 +3,13 @@ of tests/gpu_profile_step.py: per-kernel time shares of the LAST guided step and
 launches (bench.py's roofline.traffic).  Usage: python profiles/summarize_launches.py launches.csv out.md out.json"""
 import collections
 import csv
+import gzip
 import json
 import sys
 
 src, out_md, out_json = sys.argv[1:4]
-rows = list(csv.reader(l for l in open(src) if l.startswith('"')))
+opener = gzip.open if src.endswith(".gz") else open
+rows = list(csv.reader(l for l in opener(src, "rt") if l.startswith('"')))
 h = rows[0]
 ki, mi, vi, ii = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value"), h.index("ID")
 launch = collections.OrderedDict()

@@ -1,6 +1,6 @@
 """Per-kernel counts of the Blackwell-native SASS mnemonics in the shipped library (B200_PROFILING.md, "What proves a
 Blackwell-native kernel"): UTC*MMA = tcgen05.mma, UTMALDG / UTMASTG = TMA loads / stores, LDTM / STTM = tcgen05.ld / st,
-HMMA = legacy mma.sync (none expected).  Usage: python tools/sass_summary.py > profiles/sass_summary.txt"""
+HMMA = legacy mma.sync (none expected), UBLKCP = cp.async.bulk (1-D bulk copies), UCGABAR = cluster barriers.  Usage: python tools/sass_summary.py > profiles/sass_summary.txt"""
 import collections
 import os
 import re
@@ -11,7 +11,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "depth_completion_b200", "lib", "libmdc_b200.so")
 PAT = {"UTC*MMA": re.compile(r"\bUTC[A-Z]*MMA\b"), "UTMALDG": re.compile(r"\bUTMALDG\b"), "UTMASTG": re.compile(r"\bUTMASTG\b"),
        "LDTM": re.compile(r"\bLDTM\b"), "STTM": re.compile(r"\bSTTM\b"), "HMMA": re.compile(r"\bHMMA\b"),
-       "MUFU": re.compile(r"\bMUFU\b"), "FFMA2": re.compile(r"\bFFMA2\b")}
+       "UBLKCP": re.compile(r"\bUBLKCP\b"), "UCGABAR": re.compile(r"\bUCGABAR"), "MUFU": re.compile(r"\bMUFU\b"),
+       "FFMA2": re.compile(r"\bFFMA2\b")}
+NATIVE = ("UTC*MMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "HMMA", "UBLKCP", "UCGABAR")
 
 
 def main():
@@ -34,10 +36,10 @@ def main():
     print("|---|" + "---|" * len(PAT))
     for k in order:
         c = counts[k]
-        if any(c[x] for x in ("UTC*MMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "HMMA")):
+        if any(c[x] for x in NATIVE):
             print(f"| {k} | " + " | ".join(str(c[x]) for x in PAT) + " |")
-    others = [k for k in order if not any(counts[k][x] for x in ("UTC*MMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "HMMA"))]
-    print(f"\n{len(others)} further kernels are bandwidth-bound CUDA-core kernels without tensor / TMA instructions "
+    others = [k for k in order if not any(counts[k][x] for x in NATIVE)]
+    print(f"\n{len(others)} further kernels are bandwidth-bound CUDA-core kernels without tensor / TMA / bulk-copy / cluster instructions "
           f"(GroupNorm, LayerNorm, GEGLU, the step tail, ...): " + ", ".join(sorted(set(o.split("<")[0].split("::")[-1] for o in others))))
     f2 = [k for k in order if counts[k]["FFMA2"]]
     print("\nkernels using packed fp32x2 FMAs (FFMA2): " + ", ".join(f"{k.split('<')[0]} ({counts[k]['FFMA2']})" for k in f2))
