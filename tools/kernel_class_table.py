@@ -45,8 +45,13 @@ def conv_case(C, Cout, H, W):
     t_b = time_torch(lambda: torch.nn.grad.conv2d_input(x.shape, w16, dy, padding=1))
     xn = x.permute(0, 2, 3, 1).contiguous()
     dyn = dy.permute(0, 2, 3, 1).contiguous()
-    _, o_f = debug.conv3x3(xn, w, iters=10)
-    _, o_b = debug.conv3x3(dyn, w, dgrad=True, iters=10)
+    small = H * W < 4096  # low-resolution UNet layers: the engine runs these split-K, weights stream from HBM (not L2)
+    if small:
+        debug.tune(ksplit=-1, wcopies=8)
+    _, o_f = debug.conv3x3(xn, w, iters=16 if small else 10)
+    _, o_b = debug.conv3x3(dyn, w, dgrad=True, iters=16 if small else 10)
+    if small:
+        debug.tune()
     gf = 2.0 * H * W * 9 * C * Cout / 1e9
     rows.append((f"conv3x3 {C}->{Cout} @{H}x{W} fwd", o_f * 1e3, t_f, gf))
     rows.append((f"conv3x3 {C}->{Cout} @{H}x{W} dgrad", o_b * 1e3, t_b, gf))
