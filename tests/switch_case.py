@@ -57,6 +57,8 @@ def main():
         img, sp, fr["max_depth"], steps=5, resolution=128)
     d = ((dense - ref).abs().mean() / fr["max_depth"]).item()
     assert torch.isfinite(dense).all() and d < 3e-2, d
+    import hashlib
+    print("DENSE_SHA", hashlib.sha256(dense.detach().float().cpu().numpy().tobytes()).hexdigest())
     print(f"SWITCH_CASE_OK decoder {e_f:.3e}/{e_b:.3e} unet {u_f:.3e}/{u_b:.3e} pipeline {d:.3e}")
 
 

@@ -206,3 +206,28 @@ def test_tapes_full_width(full, cuda):
         got, din = eng.dbg_forward(0, step, xin), eng.dbg_backward(0, dout)
         check(f"unet fwd (step {step})", got, y16, y.detach())
         check(f"unet bwd (step {step})", din, x16.grad, x.grad)
+
+
+def test_full_width_step_is_deterministic(full, cuda):
+    """Config (b) at full width: two guided steps from the same state give bit-identical v, gradient and latent.  The
+    step graph has two branches (side stream) and every reduction is fixed-order: any race or missing join shows here."""
+    cfg = CONFIGS["b_nyu_res768"]
+    pipe = full["pipe"]
+    imgs, sparses = _frames(cfg, cuda)
+    N = cfg["N"]
+    g = torch.Generator(device=cuda).manual_seed(11)
+    pipe(imgs, sparses, cfg["max_depth"], steps=50, resolution=cfg["res"], _begin_only=True)
+    eng = list(pipe._engines.values())[-1]
+    x0 = torch.randn(N, 4, eng.lh, eng.lw, device=cuda, generator=g).bfloat16().float()
+    zero = torch.zeros_like(x0)
+    a6 = torch.tensor([[1.0] * N, [0.0] * N, [0.0] * N, [0.0] * N, [0.0] * N, [0.0] * N]).numpy()
+    outs = []
+    for _ in range(2):
+        pipe(imgs, sparses, cfg["max_depth"], steps=50, resolution=cfg["res"], _begin_only=True)
+        eng = list(pipe._engines.values())[-1]
+        eng.dbg_set_state(3, x0, zero, zero, a6)
+        eng.run(2)
+        x, sc, sh, ls = eng.get_state()
+        outs.append((eng.dbg_read("unet.out").clone(), eng.dbg_buffer("grad").clone(), x.clone()))
+    for a, b, what in zip(outs[0], outs[1], ("v", "gradient", "latent")):
+        assert torch.equal(a, b), f"{what} differs between two identical runs"
