@@ -992,6 +992,10 @@ inline GemmPlan plan_conv3x3(int NB, int H, int W, int C, int Cout, const void* 
   p.M = 0, p.N = Cout;
   p.nb0 = 1, p.nb1 = 1;
   p.BN = pick_bn(Cout);
+  // A single m-tile (the 9x12 maps: 108 pixels) is pure weight streaming: narrower n-tiles give the split-K planner more
+  // CTAs to spread the 9 * Cin * Cout weights over (tools/conv_tune_sweep.py: 1280 -> 1280 @ 9x12 21.3 -> 16.2 us)
+  static const int small_bn = getenv("MDC_SMALLM_BN") ? atoi(getenv("MDC_SMALLM_BN")) : 128;
+  if (!g_tune().bn && small_bn > 0 && p.m_tiles == 1 && Cout % small_bn == 0 && Cout >= 4 * small_bn) p.BN = small_bn;
   p.n_tiles = (Cout + p.BN - 1) / p.BN;
   p.chunks_per_tap = Cp / 64;
   p.num_k_chunks = 9 * p.chunks_per_tap;
