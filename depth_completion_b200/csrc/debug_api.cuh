@@ -64,9 +64,57 @@ int mdc_dbg_gemm(int M, int N, int K, const void* A, int a_mn, long long lda, lo
     mdc::Epilogue e;
     e.out = out, e.out_f32 = out_f32, e.ldc = ldc, e.sc0 = sc0, e.sc1 = sc1, e.bias = bias;
     e.res = static_cast<const __nv_bfloat16*>(res), e.ldr = ldr, e.sr0 = sr0, e.sr1 = sr1, e.alpha = alpha;
-    mdc::GemmPlan g = mdc::plan_gemm(M, N, K, a, b, e, nb0, nb1, bn_override);
-    float ms = mdc::time_plan(g, iters, 0);
+    // mdc_dbg_tune: split-K (< 0: the engine's cost model) and, for a plain K-major B, several weight copies used
+    // round-robin in the timed loop (weights then stream from HBM as in the real step instead of sitting in L2)
+    const int ncopy = (!b_mn && nb0 == 1 && nb1 == 1) ? std::max(1, mdc::g_tune().wcopies) : 1;
+    const size_t wbytes = static_cast<size_t>(N) * ldb * 2;
+    std::vector<const void*> copies(ncopy, B);
+    std::vector<void*> owned;
+    for (int i = 1; i < ncopy; ++i) {
+      void* c = nullptr;
+      MDC_CUDA(cudaMalloc(&c, wbytes));
+      MDC_CUDA(cudaMemcpy(c, B, wbytes, cudaMemcpyDeviceToDevice));
+      owned.push_back(c), copies[i] = c;
+    }
+    std::vector<mdc::GemmPlan> plans;
+    float* ws = nullptr;
+    for (int i = 0; i < ncopy; ++i) {
+      mdc::Operand bi{copies[i], b_mn, ldb, sb0, sb1};
+      mdc::GemmPlan g = mdc::plan_gemm(M, N, K, a, bi, e, nb0, nb1, bn_override);
+      if (mdc::g_tune().ksplit) {
+        size_t fl = mdc::enable_splitk(g, mdc::choose_ksplit(g));
+        if (fl && !ws) MDC_CUDA(cudaMalloc(&ws, fl * 4 + 256));
+        g.p.ws = ws;
+      }
+      plans.push_back(g);
+    }
+    if (ms_out && mdc::g_tune().ksplit < 0)
+      fprintf(stderr, "[dbg] auto ksplit = %d (tiles %d x %d, k-chunks %d, BN %d, cs %d)\n", plans[0].p.ksplit, plans[0].p.m_tiles,
+              plans[0].p.n_tiles, plans[0].p.num_k_chunks, plans[0].p.BN, plans[0].p.cs);
+    float ms = 0.f;
+    if (ncopy == 1) {
+      ms = mdc::time_plan(plans[0], iters, 0);
+    } else {
+      cudaEvent_t e0, e1;
+      MDC_CUDA(cudaEventCreate(&e0));
+      MDC_CUDA(cudaEventCreate(&e1));
+      for (int i = 0; i < ncopy; ++i) mdc::run_gemm(plans[i], 0);
+      MDC_CUDA(cudaStreamSynchronize(0));
+      if (iters > 0) {
+        MDC_CUDA(cudaEventRecord(e0, 0));
+        for (int i = 0; i < iters; ++i) mdc::run_gemm(plans[i % ncopy], 0);
+        MDC_CUDA(cudaEventRecord(e1, 0));
+        MDC_CUDA(cudaEventSynchronize(e1));
+        MDC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        ms /= iters;
+      }
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
     if (ms_out) *ms_out = ms;
+    MDC_CUDA(cudaDeviceSynchronize());
+    for (void* c : owned) cudaFree(c);
+    if (ws) cudaFree(ws);
   });
 }
 

@@ -446,8 +446,10 @@ __device__ __forceinline__ void umma_gemm_body(const GemmParams& p) {
         valid = m < p.M;
         img = b1;
         sc1 = m_tile * GEMM_BM, sc2 = b0, sc3 = b1;
-        off_c = b0 * p.sc0 + b1 * p.sc1 + static_cast<long long>(m) * p.ldc;
-        off_r = b0 * p.sr0 + b1 * p.sr1 + static_cast<long long>(m) * p.ldr;
+        // split-K: the batch slot b0 carries the split index (unbatched launches only), it must not move the row
+        const int bb0 = p.ksplit > 1 ? 0 : b0;
+        off_c = bb0 * p.sc0 + b1 * p.sc1 + static_cast<long long>(m) * p.ldc;
+        off_r = bb0 * p.sr0 + b1 * p.sr1 + static_cast<long long>(m) * p.ldr;
       }
       if (p.gn_cpg && m_tile < p.m_tiles && img != gn_img) {  // tiles are visited image by image
         if (gn_img >= 0) gn_flush(gn_img);
@@ -839,6 +841,52 @@ inline bool first_use_on_device(bool (&done)[64]) {
   return true;
 }
 
+// Cost model (microseconds) shared by the split-K and the output-tile-width choices.  A k-chunk is bound by the L2 -> SM
+// fill of its operand tiles (~100 GB/s per SM when every SM pulls), an item (tile x split) pays a pipeline fill +
+// epilogue, a split launch pays the reduction kernel and the fp32 partials' round trip through L2.  Work items beyond
+// one wave of CTAs serialise.  Returns the cost of the best split count (1 = unsplit) and that count.
+inline double gemm_cost_us(int tiles, int nk, double bytesA, int BN, int cs, bool may_split, int* best_split) {
+  const int sms = (g_num_sms() / cs) * cs;
+  static const int max_tiles = getenv("MDC_SPLITK_MAXTILES") ? atoi(getenv("MDC_SPLITK_MAXTILES")) : 100;
+  static const bool no_split = getenv("MDC_NO_SPLITK") != nullptr;
+  const double t_chunk = (bytesA + BN * 128.0 / cs) / 100e3, t_item = 2.5, t_red = 4.0, l2_bytes_per_us = 5e6;
+  auto waves = [&](int items) { return (items + sms - 1) / sms; };
+  int best = 1;
+  double best_cost = waves(tiles) * (nk * t_chunk + t_item);
+  if (may_split && !no_split && tiles <= max_tiles && nk >= 8) {
+    for (int s = 2; s <= std::min(nk / 4, 64); ++s) {
+      const int kc = (nk + s - 1) / s;
+      if ((nk + kc - 1) / kc != s) continue;  // enable_splitk would round this split count down
+      const int items = tiles * s;
+      const double cost = waves(items) * (kc * t_chunk + t_item) + t_red + 2.0 * items * GEMM_BM * BN * 4.0 / l2_bytes_per_us;
+      if (cost < (best == 1 ? 0.9 * best_cost : best_cost)) best = s, best_cost = cost;
+    }
+  }
+  if (best_split) *best_split = best;
+  return best_cost;
+}
+// Output-tile width of a launch with few m-tiles (the 18x24 and 9x12 levels of the UNet: 432 / 108 rows): the widest
+// divisor of N is not the best choice there -- narrower tiles give more CTAs for the weight stream and fewer idle SMs in
+// the last wave.  The same model that picks the split count ranks the candidates (tools/linear_tune_sweep.py: within
+// 0.5 % of the measured best over the UNet's linears at those levels, 10 % better than "widest divisor").
+inline int pick_bn_model(int N, int m_tiles, int nk, double bytesA, bool can_pair, bool may_split) {
+  const int wide = pick_bn(N);
+  static const bool off = getenv("MDC_NO_BNMODEL") != nullptr;
+  static const int max_mt = getenv("MDC_BNMODEL_MAXMT") ? atoi(getenv("MDC_BNMODEL_MAXMT")) : 8;
+  if (off || g_tune().bn || m_tiles > max_mt) return wide;
+  const int cs = (can_pair && m_tiles >= 2 && !getenv("MDC_NO_PAIR")) ? 2 : 1;
+  auto cost = [&](int bn) { return gemm_cost_us(((m_tiles + cs - 1) / cs) * cs * ((N + bn - 1) / bn), nk, bytesA, bn, cs, may_split, nullptr); };
+  const double wide_cost = cost(wide);
+  int best = wide;
+  double best_cost = wide_cost;
+  for (int bn = 64; bn <= 256; bn += 32) {
+    if (N % bn || bn == wide) continue;
+    const double c = cost(bn);
+    if (c < best_cost) best = bn, best_cost = c;
+  }
+  return best_cost < 0.97 * wide_cost ? best : wide;  // leave the widest divisor unless the model sees a real difference
+}
+
 // Cluster mode of a launch; must be decided BEFORE the B tensor map is encoded because each CTA's TMA box covers only
 // its BN/cs rows.  pair: CTA-pair MMA (see GemmParams::pair); otherwise cs > 1 = B multicast over cs CTAs (consecutive
 // m-tiles of one n-tile).  Both need a K-major B whose per-CTA slice is a whole number of 8-row swizzle atoms.
@@ -928,6 +976,8 @@ inline GemmPlan plan_gemm(int M, int N, int K, const Operand& A, const Operand& 
   p.nb0 = nb0, p.nb1 = nb1;
   p.a_mn = A.mn_major, p.b_mn = B.mn_major;
   p.BN = bn_override ? bn_override : pick_bn(N);
+  if (!bn_override && !p.b_mn && !p.a_mn && nb0 == 1 && nb1 == 1)  // plain linears: model-ranked tile width on the small maps
+    p.BN = pick_bn_model(N, (M + GEMM_BM - 1) / GEMM_BM, (K + GEMM_BK - 1) / GEMM_BK, GEMM_A_STAGE, true, !e.out_f32 && !e.bias_img);
   if (p.b_mn) p.BN = (N >= 256) ? 256 : ((N + 63) / 64) * 64;  // MN-major B is loaded in 64-wide chunks
   MDC_CHECK(p.BN % 16 == 0 && p.BN >= 16 && p.BN <= 256, "bad BN %d", p.BN);
   MDC_CHECK(!p.b_mn || p.BN % 64 == 0, "MN-major B needs BN %% 64 == 0");
@@ -992,10 +1042,8 @@ inline GemmPlan plan_conv3x3(int NB, int H, int W, int C, int Cout, const void* 
   p.M = 0, p.N = Cout;
   p.nb0 = 1, p.nb1 = 1;
   p.BN = pick_bn(Cout);
-  // A single m-tile (the 9x12 maps: 108 pixels) is pure weight streaming: narrower n-tiles give the split-K planner more
-  // CTAs to spread the 9 * Cin * Cout weights over (tools/conv_tune_sweep.py: 1280 -> 1280 @ 9x12 21.3 -> 16.2 us)
-  static const int small_bn = getenv("MDC_SMALLM_BN") ? atoi(getenv("MDC_SMALLM_BN")) : 128;
-  if (!g_tune().bn && small_bn > 0 && p.m_tiles == 1 && Cout % small_bn == 0 && Cout >= 4 * small_bn) p.BN = small_bn;
+  // few m-tiles (the 18x24 / 9x12 maps) are weight streaming: model-ranked tile width (tools/conv_tune_sweep.py)
+  p.BN = pick_bn_model(Cout, p.m_tiles, 9 * (Cp / 64), 64.0 * p.BW * p.BH * 2.0, true, !e.bias_img && !e.relu);
   p.n_tiles = (Cout + p.BN - 1) / p.BN;
   p.chunks_per_tap = Cp / 64;
   p.num_k_chunks = 9 * p.chunks_per_tap;
@@ -1210,23 +1258,9 @@ inline int choose_ksplit(const GemmPlan& g) {
   const GemmParams& p = g.p;
   if (p.nb0 != 1 || p.nb1 != 1 || p.bias_img || p.out_f32 || p.nphase > 1 || p.relu) return 1;
   if (g_tune().ksplit > 0) return g_tune().ksplit;
-  const int tiles = ((p.m_tiles + p.cs - 1) / p.cs) * p.cs * p.n_tiles, nk = p.num_k_chunks, sms = (g_num_sms() / p.cs) * p.cs;
-  static const int max_tiles = getenv("MDC_SPLITK_MAXTILES") ? atoi(getenv("MDC_SPLITK_MAXTILES")) : 100;
-  if (tiles > max_tiles || nk < 8) return 1;
-  // Cost model in microseconds.  A k-chunk is bound by the L2 -> SM fill of its operand tiles (~100 GB/s per SM when
-  // every SM pulls), an item (tile x split) pays a pipeline fill + epilogue, a split launch pays the reduction kernel
-  // and the fp32 partials' round trip through L2.  Work items beyond one wave of CTAs serialise.
-  const double t_chunk = (p.bytesA + p.BN * 128.0 / p.cs) / 100e3, t_item = 2.5, t_red = 4.0, l2_bytes_per_us = 5e6;
-  auto waves = [&](int items) { return (items + sms - 1) / sms; };
+  const int tiles = ((p.m_tiles + p.cs - 1) / p.cs) * p.cs * p.n_tiles;
   int best = 1;
-  double best_cost = waves(tiles) * (nk * t_chunk + t_item);
-  for (int s = 2; s <= std::min(nk / 4, 64); ++s) {
-    const int kc = (nk + s - 1) / s;
-    if ((nk + kc - 1) / kc != s) continue;  // enable_splitk would round this split count down
-    const int items = tiles * s;
-    const double cost = waves(items) * (kc * t_chunk + t_item) + t_red + 2.0 * items * GEMM_BM * p.BN * 4.0 / l2_bytes_per_us;
-    if (cost < (best == 1 ? 0.9 * best_cost : best_cost)) best = s, best_cost = cost;
-  }
+  gemm_cost_us(tiles, p.num_k_chunks, p.bytesA, p.BN, p.cs, true, &best);
   return best;
 }
 inline size_t enable_splitk(GemmPlan& g, int ksplit) {  // returns the workspace size in floats
