@@ -132,9 +132,18 @@ __device__ __forceinline__ void gn_finalize_last_block(const float* __restrict__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int g = warp; g < G; g += nwarps) {
     double a = 0, b = 0;
-    for (int k = lane; k < bpi; k += 32) {
-      const float2 pv = __ldcg(reinterpret_cast<const float2*>(partial + (1LL * (n * bpi + k) * G + g) * 2));
-      a += pv.x, b += pv.y;
+    // the whole GPU waits for this one block: issue all of a lane's loads before the first add (same order of adds)
+    constexpr int RK = 10;  // 32 x 10 = 320 partials per pass (two blocks per SM)
+    for (int base = 0; base < bpi; base += 32 * RK) {
+      float2 pv[RK];
+#pragma unroll
+      for (int i = 0; i < RK; ++i) {
+        const int k = base + lane + 32 * i;
+        pv[i] = k < bpi ? __ldcg(reinterpret_cast<const float2*>(partial + (1LL * (n * bpi + k) * G + g) * 2)) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < RK; ++i)
+        if (base + lane + 32 * i < bpi) a += pv[i].x, b += pv[i].y;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -531,10 +540,19 @@ __device__ __forceinline__ void gn_reduce_partials(const float* __restrict__ par
   const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
   if (g < G) {
     double a = 0, b = 0;
-#pragma unroll 4
-    for (int k = j; k < bpi; k += 8) {
-      const float2 pv = __ldcg(reinterpret_cast<const float2*>(partial + (1LL * (n * bpi + k) * G + g) * 2));
-      a += pv.x, b += pv.y;
+    // every CTA of the grid sits in this reduction right after the barrier: all of a lane's loads are issued before the
+    // first add (one L2 round trip instead of one per four partials); the adds keep their order, so the sums are the same
+    constexpr int RK = 20;  // 8 x 20 = 160 partials per pass (the grid never exceeds the SM count)
+    for (int base = 0; base < bpi; base += 8 * RK) {
+      float2 pv[RK];
+#pragma unroll
+      for (int i = 0; i < RK; ++i) {
+        const int k = base + j + 8 * i;
+        pv[i] = k < bpi ? __ldcg(reinterpret_cast<const float2*>(partial + (1LL * (n * bpi + k) * G + g) * 2)) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < RK; ++i)
+        if (base + j + 8 * i < bpi) a += pv[i].x, b += pv[i].y;
     }
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) {
