@@ -134,6 +134,16 @@ int mdc_begin_frame(mdc_handle* h, const void* imgs, int img_dtype, int channels
     h->e->begin_frame(imgs, img_dtype, channels, sparse, x_bf16, max_depth, min_depth, norm_mode, lr_latent, lr_scaling);
   });
 }
+int mdc_begin_frame_encoded(mdc_handle* h, const void* img_latents_bf16, const void* imgs, int img_dtype, int channels,
+                            const float* sparse, const void* x_bf16, float max_depth, float min_depth, int norm_mode, float lr_latent,
+                            float lr_scaling) {
+  return mdc::guarded([&] {
+    MDC_CHECK(h && img_latents_bf16, "null argument");
+    h->e->activate();
+    h->e->begin_frame(imgs, img_dtype, channels, sparse, x_bf16, max_depth, min_depth, norm_mode, lr_latent, lr_scaling,
+                      img_latents_bf16);
+  });
+}
 int mdc_set_options(mdc_handle* h, int projection, int inv, int opt, const float* loss_weights4_host, int kld_mode,
                     float kld_weight, float percentile_lo, float percentile_hi, int closed_form,
                     int interp_nearest) {

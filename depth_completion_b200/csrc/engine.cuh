@@ -539,7 +539,7 @@ struct Engine {
   Tensor* vae_mid_attention(Tensor* h, const std::string& A);
   void encode(const void* imgs, int dtype, int channels, void* latents_out);
   void begin_frame(const void* imgs, int dtype, int channels, const float* sparse, const void* x0, float max_depth,
-                   float min_depth, int norm_mode, float lrx, float lrs);
+                   float min_depth, int norm_mode, float lrx, float lrs, const void* img_latents = nullptr);
   float* fr_guide = nullptr;     // normalised sparse depth of the current frame
   uint8_t* fr_mask = nullptr;
   float* fr_stats = nullptr;     // per sample: lo, hi, guide min, guide max, valid count
@@ -1904,13 +1904,21 @@ inline void Engine::set_options(int projection, int inv, int opt, const float* w
 
 // One call per frame: image prologue + sparse-depth normalisation + per-call state.
 // Raises "No valid values found in mask ..." for a sample without a positive sparse value, like utils.py:132-136.
+// `img_latents` != nullptr (mdc_begin_frame_encoded): the image latents were produced earlier by mdc_encode -- e.g. by a
+// second handle on another stream while this handle was still running the previous frame --
+// and the encoder is skipped; `imgs` is then only needed for the edge loss.
 inline void Engine::begin_frame(const void* imgs, int dtype, int channels, const float* sparse, const void* x0,
-                                float max_depth, float min_depth, int norm_mode, float lrx, float lrs) {
+                                float max_depth, float min_depth, int norm_mode, float lrx, float lrs, const void* img_latents) {
   MDC_CHECK(sparse && x0, "mdc_begin_frame: null pointer");
   MDC_CHECK(norm_mode >= 0 && norm_mode <= 2, "Unknown norm method: %d (0 minmax, 1 const, 2 percentile)", norm_mode);
   MDC_CHECK(!((h_opts.projection != 0 || h_opts.inv) && min_depth <= 1e-7f),
             "min_depth must be > 1e-07 when projection is 'log' or 'log10' or inv is True, but got %g", min_depth);
-  encode(imgs, dtype, channels, img_lat);
+  if (img_latents) {
+    MDC_CHECK(imgs || h_opts.w_edge == 0.f, "image must be provided for edge loss");
+    MDC_CHECK(!imgs || ((dtype == 0 || dtype == 1) && (channels == 1 || channels == 3)), "mdc_begin_frame_encoded: bad image format");
+  } else {
+    encode(imgs, dtype, channels, img_lat);
+  }
   if (norm_mode == 2) percentile_ranges(sparse);
   if (h_opts.w_edge != 0.f) {
     const long long opix = 1LL * N * H * W;
@@ -1922,7 +1930,7 @@ inline void Engine::begin_frame(const void* imgs, int dtype, int channels, const
            h_opts.inv, fr_guide, fr_mask, fr_stats);
   MDC_CUDA(cudaGetLastError());
   // ranges, point offsets and the compaction stay on the device; one synchronisation at the end raises the empty-mask error
-  begin_state(img_lat, x0, fr_guide, fr_mask, lrx, lrs, fr_stats);
+  begin_state(img_latents ? img_latents : img_lat, x0, fr_guide, fr_mask, lrx, lrs, fr_stats);
 }
 
 // NHWC bf16 -> NCHW fp32 copy of a named tensor (which = 0 data, 1 gradient); debug / tests only.

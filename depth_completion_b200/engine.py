@@ -61,6 +61,8 @@ def _declare(l):
     l.mdc_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     l.mdc_begin_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                   C.c_int, C.c_float, C.c_float]
+    l.mdc_begin_frame_encoded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float,
+                                          C.c_float, C.c_int, C.c_float, C.c_float]
     l.mdc_set_options.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float,
                                   C.c_int, C.c_int]
     l.mdc_launch_count.argtypes = [C.c_void_p]
@@ -297,17 +299,29 @@ class StepEngine:
                                        float(kld_weight), float(percentile[0]), float(percentile[1]), int(bool(closed_form)),
                                        int(interp_mode == "nearest")))
 
-    def begin_frame(self, imgs, sparses, x, max_depth, min_depth=0.0, norm="minmax", lr_latent=0.05, lr_scaling=0.005):
+    def begin_frame(self, imgs, sparses, x, max_depth, min_depth=0.0, norm="minmax", lr_latent=0.05, lr_scaling=0.005,
+                    img_latents=None):
         """The per-frame prologue in one library call (mdc_begin_frame): image preprocess + VAE encoder, sparse-depth
-        normalisation, per-call state (marigold_dc.py:687-789).  Raises ValueError for a sample with an empty mask."""
+        normalisation, per-call state (marigold_dc.py:687-789).  Raises ValueError for a sample with an empty mask.
+        `img_latents` ([N,4,EH,EW] bf16 from an earlier `encode`, possibly of another engine on another stream) skips the
+        encoder (mdc_begin_frame_encoded)."""
         self._on_stream()
         imgs, dt = self._image_arg(imgs)
         sparses = sparses.to(self.device, torch.float32).contiguous()
         x = x.to(self.device, torch.bfloat16).contiguous()
         assert sparses.numel() == self.n * self.H * self.W and tuple(x.shape) == (self.n, 4, self.lh, self.lw)
         try:
-            check(self.lib.mdc_begin_frame(self._h, ptr(imgs), dt, int(imgs.shape[1]), ptr(sparses), ptr(x), float(max_depth),
-                                           float(min_depth), self.NORMS[norm], float(lr_latent), float(lr_scaling)))
+            if img_latents is None:
+                check(self.lib.mdc_begin_frame(self._h, ptr(imgs), dt, int(imgs.shape[1]), ptr(sparses), ptr(x), float(max_depth),
+                                               float(min_depth), self.NORMS[norm], float(lr_latent), float(lr_scaling)))
+            else:
+                if tuple(img_latents.shape) != (self.n, 4, self.lh, self.lw) or img_latents.dtype != torch.bfloat16:
+                    raise ValueError(f"img_latents must be bf16 [{self.n}, 4, {self.lh}, {self.lw}], got {img_latents.dtype} "
+                                     f"{tuple(img_latents.shape)}")
+                img_latents = img_latents.to(self.device).contiguous()
+                check(self.lib.mdc_begin_frame_encoded(self._h, ptr(img_latents), ptr(imgs), dt, int(imgs.shape[1]), ptr(sparses),
+                                                       ptr(x), float(max_depth), float(min_depth), self.NORMS[norm],
+                                                       float(lr_latent), float(lr_scaling)))
         except MdcError as e:
             if "No valid values found in mask" in str(e) or "min_depth must be" in str(e):
                 raise ValueError(str(e)) from None

@@ -242,7 +242,7 @@ class MarigoldDepthCompletionPipeline:
                percentile=(0.01, 0.99), pred_latents_prev=None, beta=0.9, steps=50, resolution=768,
                closed_form=None, opt="adam", lr=None, kld=False, kld_weight=0.1, kld_mode="simple",
                interp_mode="bilinear", loss_funcs=None, seed=2024, train_latents=True, train_method="per-step",
-               train_steps=10, _begin_only=False, _slot=0, _concurrent=False):
+               train_steps=10, _begin_only=False, _slot=0, _concurrent=False, _img_latents=None):
         """First half of the call: argument validation, per-frame prologue and all guided steps, enqueued on the current
         CUDA stream without waiting for them (only the prologue's empty-mask check synchronises, a few ms in).  `_slot`
         selects one of several engines of the same geometry so that frames on different streams can be in flight at once
@@ -324,13 +324,26 @@ class MarigoldDepthCompletionPipeline:
         eng.set_options(projection, inv, opt, loss_funcs, kld, kld_weight, kld_mode,
                         percentile if norm == "percentile" else (0.01, 0.99), closed_form=bool(closed_form and train_latents),
                         interp_mode=interp_mode)
-        eng.begin_frame(imgs, sparses, x, max_depth, min_depth, norm, lr_latent, lr_scaling)
+        eng.begin_frame(imgs, sparses, x, max_depth, min_depth, norm, lr_latent, lr_scaling, img_latents=_img_latents)
         if not _begin_only:
             if train_latents:
                 eng.run(steps)               # marigold_dc.py:799-904, asynchronous, no host sync inside
             else:                            # no-grad branch: plain DDIM sampling (:905-909)
                 eng.sample(steps)
         return dict(eng=eng, closed_form=bool(closed_form) if train_latents else True)
+
+    def encode_ahead(self, imgs, steps=50, resolution=768):
+        """The image half of the per-frame prologue (marigold_dc.py:687-698: preprocess + VAE encoder) on its own, enqueued on
+        the current CUDA stream by a SECOND engine of the call geometry (shared weights, no grid-wide barriers), so it can
+        run under another frame's guided loop (`video.complete_sequence(overlap_prologue=True)`).
+        Returns img_latents [N,4,EH,EW] bf16 for `submit(..., _img_latents=...)`."""
+        if imgs.ndim != 4:
+            raise ValueError(f"Input image is not 4-dimensional: shape={tuple(imgs.shape)}")
+        N, _, H, W = imgs.shape
+        imgs = imgs.to(self.device, non_blocking=True)
+        check_image(imgs)
+        eng = self._engine(N, H, W, resolution, steps, "enc", True)
+        return eng.encode(imgs)
 
     def collect(self, ticket):
         """Second half of the call, on the stream `submit` ran on: final decode + de-normalisation (marigold_dc.py:970-984)

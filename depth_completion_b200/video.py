@@ -33,14 +33,19 @@ def sequence_batches(n_frames: int, batch_size: int, use_prev_latent: bool, rank
 
 def complete_sequence(pipe, imgs: torch.Tensor, sparses: torch.Tensor, max_depth: float, *, batch_size: int = 1,
                       use_prev_latent: bool = False, beta: float = 0.9, rank: int = 0, world: int = 1,
-                      frames_in_flight: int = 1, **pipe_kwargs):
+                      frames_in_flight: int = 1, overlap_prologue: bool = False, **pipe_kwargs):
     """Runs `pipe` over imgs [F,C,H,W] / sparses [F,1,H,W]; returns (denses of this rank's frames [f,1,H,W] fp32,
     their (start, stop) frame range, last pred_latents).
 
     frames_in_flight > 1 (independent frames only) keeps that many pipeline calls in flight on separate CUDA streams,
     each on its own engine (shared weights): call k+1's prologue -- H2D copies, image preprocessing, VAE encoder -- and
     its guided steps overlap call k's loop, whose batch-1 UNet layers leave most SMs idle.  This is a throughput mode:
-    a frame's latency grows, frames per second go up."""
+    a frame's latency grows, frames per second go up.
+
+    overlap_prologue=True (one call in flight; works WITH use_prev_latent, whose chain only constrains the depth latent):
+    call k+1's image prologue -- H2D copy, preprocessing, VAE encoder (marigold_dc.py:687-698) -- runs on a side stream on a
+    second engine while call k is in its guided loop, and call k+1 starts from the encoded latents
+    (`mdc_begin_frame_encoded`): SURVEY.md section 8(f)-3, "pipeline frame k+1's encoder under frame k's loop"."""
     if imgs.shape[0] != sparses.shape[0]:
         raise ValueError(f"{imgs.shape[0]} images vs {sparses.shape[0]} sparse maps")
     if use_prev_latent and batch_size > 1:
@@ -52,8 +57,12 @@ def complete_sequence(pipe, imgs: torch.Tensor, sparses: torch.Tensor, max_depth
                          "besides the current frame; use complete_sequences for several independent sequences")
     plan = sequence_batches(imgs.shape[0], batch_size, use_prev_latent, rank, world)
     outs, prev, lat = [], None, None
+    if overlap_prologue and frames_in_flight > 1:
+        raise ValueError("overlap_prologue is the one-call-in-flight mode; frames_in_flight > 1 already overlaps whole calls")
     if frames_in_flight > 1 and plan:
         return _complete_in_flight(pipe, imgs, sparses, max_depth, plan, frames_in_flight, pipe_kwargs)
+    if overlap_prologue and plan:
+        return _complete_overlapped(pipe, imgs, sparses, max_depth, plan, use_prev_latent, beta, pipe_kwargs)
     for s, e in plan:
         dense, lat = pipe(imgs[s:e], sparses[s:e], max_depth, pred_latents_prev=prev if use_prev_latent else None, beta=beta,
                           **pipe_kwargs)
@@ -63,6 +72,42 @@ def complete_sequence(pipe, imgs: torch.Tensor, sparses: torch.Tensor, max_depth
     rng = (plan[0][0], plan[-1][1]) if plan else (0, 0)
     dense_all = torch.cat(outs, 0) if outs else torch.empty(0, 1, *imgs.shape[-2:])
     return dense_all, rng, (lat if plan else None)
+
+
+def _complete_overlapped(pipe, imgs, sparses, max_depth, plan, use_prev_latent, beta, pipe_kwargs):
+    """One call in flight, the NEXT call's image prologue under it: while the main engine replays call k's guided steps
+    on the caller's stream, a side stream copies call k+1's images to the device and encodes them on a second engine
+    (`pipe.encode_ahead`); call k+1 then begins from those latents.  The previous-latent chain (predict.py:697-699) is
+    untouched: only the depth latent depends on call k's result, the image latents never do."""
+    dev = pipe.device
+    cur = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(device=dev)
+    geo = {k: pipe_kwargs[k] for k in ("steps", "resolution") if k in pipe_kwargs}
+
+    def encode(i):
+        s, e = plan[i]
+        with torch.cuda.stream(side):
+            lat = pipe.encode_ahead(imgs[s:e], **geo)
+            done = torch.cuda.Event()
+            done.record(side)
+        return lat, done
+
+    side.wait_stream(cur)  # inputs produced on the caller's stream
+    nxt = encode(0)
+    outs, prev, lat = [], None, None
+    for i, (s, e) in enumerate(plan):
+        img_lat, done = nxt
+        cur.wait_event(done)
+        ticket = pipe.submit(imgs[s:e], sparses[s:e], max_depth, pred_latents_prev=prev if use_prev_latent else None, beta=beta,
+                             _img_latents=img_lat, **pipe_kwargs)
+        if i + 1 < len(plan):
+            nxt = encode(i + 1)  # enqueued while call i's guided steps are running
+        dense, lat = pipe.collect(ticket)
+        img_lat.record_stream(cur)
+        outs.append(dense)
+        if use_prev_latent:
+            prev = lat
+    return torch.cat(outs, 0), (plan[0][0], plan[-1][1]), lat
 
 
 def _complete_in_flight(pipe, imgs, sparses, max_depth, plan, k, pipe_kwargs):

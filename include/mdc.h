@@ -144,6 +144,15 @@ int mdc_set_options(mdc_handle* h, int projection, int inv, int opt, const float
 int mdc_begin_frame(mdc_handle* h, const void* imgs, int img_dtype, int channels, const float* sparse, const void* x_bf16,
                     float max_depth, float min_depth, int norm_mode, float lr_latent, float lr_scaling);
 
+/* mdc_begin_frame with the image latents already encoded ("pipeline frame k+1's encoder under frame
+ * k's loop", predict.py:599-700): img_latents_bf16 [N,4,EH,EW] is the output of an earlier mdc_encode -- typically of a
+ * second handle of the same geometry (mdc_create_shared, concurrent = 1) that ran on another stream while this handle
+ * was still in frame k's guided loop -- so only the sparse-depth normalisation and the per-call state are left on this
+ * handle's critical path.  imgs may be NULL unless the edge loss is selected (it reads the raw image, :195-236). */
+int mdc_begin_frame_encoded(mdc_handle* h, const void* img_latents_bf16, const void* imgs, int img_dtype, int channels,
+                            const float* sparse, const void* x_bf16, float max_depth, float min_depth, int norm_mode,
+                            float lr_latent, float lr_scaling);
+
 /* n guided steps (marigold_dc.py:801-904 each), asynchronous, no host synchronisation inside. */
 int mdc_run(mdc_handle* h, int n_steps);
 

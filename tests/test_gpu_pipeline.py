@@ -321,6 +321,56 @@ def test_frames_in_flight_and_parallel_sequences(models, cuda):
     assert r1 == (1, 2) and d_r1.shape == (1, 3, 1, 96, 128)
 
 
+def test_next_frame_prologue_overlaps_the_guided_loop(models, cuda):
+    """SURVEY.md 8(f)-3, "pipeline frame k+1's encoder under frame k's loop" (predict.py:599-700): with overlap_prologue the
+    image latents of call k+1 come from a second engine on a side stream (pipe.encode_ahead -> mdc_begin_frame_encoded)
+    while call k runs.  (1) those latents equal the main engine's own encoder up to the GroupNorm summation order;
+    (2) the driver -- with and without the previous-latent chain -- is bit-identical to hand-chained calls fed the same
+    latents; (3) against the plain serial driver only the summation-order noise is left."""
+    from depth_completion_b200.pipeline import MarigoldDepthCompletionPipeline
+    from depth_completion_b200.synthetic import make_batch
+    from depth_completion_b200.video import complete_sequence
+
+    unet, vae, ctx, _, _ = models
+    b = make_batch(4, H=96, W=128, n_points=80)
+    img, sp = b["img"].to(cuda), b["sparse"].to(cuda)
+    pipe = MarigoldDepthCompletionPipeline(unet, vae)
+    pipe.empty_text_embedding = ctx
+    kw = dict(steps=6, resolution=128)
+    dense_o, rng, last_o = complete_sequence(pipe, img, sp, 10.0, use_prev_latent=True, beta=0.7, overlap_prologue=True, **kw)
+    assert rng == (0, 4) and dense_o.shape == (4, 1, 96, 128) and torch.isfinite(dense_o).all()
+    # (1) side-engine latents vs the main engine's encoder
+    main = pipe._engine(1, 96, 128, 128, 6)
+    for i in range(2):
+        a = pipe.encode_ahead(img[i:i + 1], **kw).float()
+        m = main.encode(img[i:i + 1]).float()
+        assert ((a - m).norm() / m.norm()).item() < 1e-2
+    # (2) hand-chained calls on the same latents
+    prev, manual = None, []
+    for i in range(4):
+        lat = pipe.encode_ahead(img[i:i + 1], **kw)
+        t = pipe.submit(img[i:i + 1], sp[i:i + 1], 10.0, pred_latents_prev=prev, beta=0.7, _img_latents=lat, **kw)
+        d, prev = pipe.collect(t)
+        manual.append(d)
+    assert torch.equal(dense_o, torch.cat(manual, 0)) and torch.equal(last_o, prev)
+    # (3) the serial driver (its own encoder inside mdc_begin_frame)
+    dense_s, _, _ = complete_sequence(pipe, img, sp, 10.0, use_prev_latent=True, beta=0.7, **kw)
+    assert ((dense_o - dense_s).abs().mean() / 10.0).item() < 1e-2
+    # independent frames, batches of two, under a caller-chosen stream
+    st = torch.cuda.Stream(device=cuda)
+    st.wait_stream(torch.cuda.current_stream(cuda))
+    with torch.cuda.stream(st):
+        dense_b, rng_b, _ = complete_sequence(pipe, img, sp, 10.0, batch_size=2, overlap_prologue=True, **kw)
+        dense_p, _, _ = complete_sequence(pipe, img, sp, 10.0, batch_size=2, **kw)
+    st.synchronize()
+    assert rng_b == (0, 4) and ((dense_b - dense_p).abs().mean() / 10.0).item() < 1e-2
+    with pytest.raises(ValueError):
+        complete_sequence(pipe, img, sp, 10.0, frames_in_flight=2, overlap_prologue=True, **kw)
+    # bad latents are refused before anything is enqueued
+    with pytest.raises(ValueError):
+        pipe.submit(img[:1], sp[:1], 10.0, _img_latents=torch.zeros(1, 4, 3, 3, device=cuda, dtype=torch.bfloat16), **kw)
+
+
 def test_call_geometries_share_one_weight_bank(models, cuda):
     """A second frame geometry, a short last batch and a return to the first geometry never re-pack the weights
     (mdc_create_shared): engines stay resident, the bank is loaded once, results equal those of a fresh pipeline."""
