@@ -43,10 +43,12 @@ def calc_bins(lower: float, upper: float, size: float) -> list[tuple[float, floa
 
 def evaluate_dataset(dataset_dir, result_dir, max_sparse_depth: float = 120.0, min_depth: float = 0.0,
                      max_depth: float = 120.0, metrics=("mae", "rmse"), bin_size: float | None = None, batch_size: int = 1,
-                     device="cpu") -> dict:
+                     device="cpu", keep_batches: bool = False) -> dict:
     """{"overall": {metric: score}, "num_points": n, "bins": [{"range": (lo, hi), metric: score, "num_points": n}, ...]}.
 
-    `result_dir` is the directory holding `dense/` (what `complete_dataset` wrote for this dataset directory)."""
+    `result_dir` is the directory holding `dense/` (what `complete_dataset` wrote for this dataset directory).
+    keep_batches=True adds "batches": the per-batch score tensors and point counts, overall and per bin, which is what
+    the reference pools over ALL datasets for `results_all.json` (analyze.py:163-170, :322-348)."""
     for m in metrics:
         if m not in METRICS:
             raise ValueError(f"Unknown metric: {m}")
@@ -54,8 +56,7 @@ def evaluate_dataset(dataset_dir, result_dir, max_sparse_depth: float = 120.0, m
     sparse_dir, dense_dir = dataset_dir / dio.SPARSE_DIR, result_dir / dio.DENSE_DIR
     pairs = []
     for _, sp in dio.find_pairs(dataset_dir):
-        stem = dense_dir / sp.relative_to(sparse_dir)
-        found = next((stem.with_suffix(e) for e in (".npy", ".npz") if stem.with_suffix(e).exists()), None)
+        found = dio.find_dense(dense_dir / sp.relative_to(sparse_dir))
         if found is not None:
             pairs.append((sp, found))
     if not pairs:
@@ -86,4 +87,6 @@ def evaluate_dataset(dataset_dir, result_dir, max_sparse_depth: float = 120.0, m
         if n_binned[b]:
             out["bins"].append({"range": rng, "num_points": n_binned[b],
                                 **{m: float(torch.stack(v).mean()) for m, v in binned[b].items()}})
+    if keep_batches:
+        out["batches"] = {"overall": overall, "binned": binned, "num_points": n_pts, "num_binned": n_binned, "ranges": bins}
     return out
