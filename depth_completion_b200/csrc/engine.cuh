@@ -21,6 +21,7 @@
 #include "../../include/mdc.h"
 #include "attn.cuh"
 #include "gemm.cuh"
+#include "head.cuh"
 #include "norm.cuh"
 #include "pack.cuh"
 #include "tail.cuh"
@@ -132,7 +133,7 @@ struct ConvOp : Op {  // 3x3 stride-1 pad-1 convolution (+bias, +residual)
   float alpha = 1.f;     // y = alpha * conv(x) + bias (+ res); the input gradient carries the same factor
   bool mask_x = false;   // x is a ReLU output and this op is its first consumer: mask x's finished gradient by (x > 0)
   void plan_bwd() override;
-  void fwd(cudaStream_t st) override { run_gemm(pf, st); }
+  void fwd(cudaStream_t st) override;
   void bwd(cudaStream_t st) override;
   int n_bwd() const override { return ((res && !alias_res) ? 2 : 1) + (mask_x ? 1 : 0); }
   void gemm_plans(std::vector<const GemmPlan*>& f, std::vector<const GemmPlan*>& b) const override {
@@ -385,6 +386,15 @@ struct Engine {
   WeightSlot* bank_slot(const std::string& key, WKind kind, int out, int in, bool& fresh);
   std::vector<std::unique_ptr<Op>> unet_ops, dec_ops, enc_ops;  // enc_ops: VAE encoder, forward only (per-frame prologue)
   bool alloc_grads = true;
+  // Sparse output head (head.cuh): inside a guided step the KL decoder's conv_norm_out / conv_out are evaluated only
+  // where the loss looks.  `sparse_head` is raised around the decoder tape of step_launches() and read by the two ops.
+  struct GroupNormOp* head_gn = nullptr;
+  struct ConvOp* head_conv = nullptr;
+  unsigned char* head_act = nullptr;  // [N, PPH*PPW]: pixels that receive a gradient from conv_out in the current step
+  bool sparse_head = false;
+  bool sparse_head_allowed() const;
+  void head_fwd(cudaStream_t st);
+  void head_bwd(cudaStream_t st);
   size_t n_split_step = 0;
   Tensor *enc_in = nullptr, *enc_out = nullptr;
   std::vector<std::unique_ptr<Op>>* cur_ops = nullptr;
@@ -563,6 +573,13 @@ struct Engine {
 };
 
 // ================================================================================================ op bodies
+inline void ConvOp::fwd(cudaStream_t st) {
+  if (E->sparse_head && this == E->head_conv) {
+    E->head_fwd(st);
+    return;
+  }
+  run_gemm(pf, st);
+}
 inline void ConvOp::plan_bwd() {
   Epilogue e;
   e.out = x->g, e.ldc = x->ld, e.alpha = alpha;
@@ -585,6 +602,7 @@ inline void relu_mask(Tensor* x, cudaStream_t st) {
   launch_k(relu_mask_kernel, dim3(ew_grid(x->rows() * (x->c / 8))), dim3(256), 0, st, x->g, x->ld, x->d, x->ld, x->rows(), x->c);
 }
 inline void ConvOp::bwd(cudaStream_t st) {
+  if (E->sparse_head && this == E->head_conv) return;  // folded into the GroupNorm backward of the sparse head
   run_gemm(pb, st);
   if (res && !alias_res)
     launch_k(add_rows_kernel, dim3(ew_grid(res->rows() * (res->c / 8))), dim3(256), 0, st, y->g, y->ld, res->g, res->ld, res->rows(), res->c,
@@ -634,10 +652,18 @@ inline void SelfAttnOp::bwd(cudaStream_t st) {
   run_attention_bwd(a, st, no_side || st == E->side_stream ? nullptr : &sb);
 }
 inline void GroupNormOp::fwd(cudaStream_t st) {
+  if (E->sparse_head && this == E->head_gn) {  // statistics only; head_points_fwd_kernel normalises the pixels it needs
+    run_gn_stats(plan, x->d, eps, stats, E->gn_scratch(), st);
+    return;
+  }
   run_gn_fwd(plan, x->d, y->d, y->ld, gamma, beta, eps, silu, stats, E->gn_scratch(), st, epi ? E->gn_epi_partial : nullptr,
              epi ? epi->grid : 0);
 }
 inline void GroupNormOp::bwd(cudaStream_t st) {
+  if (E->sparse_head && this == E->head_gn) {
+    E->head_bwd(st);
+    return;
+  }
   run_gn_bwd(plan, x->d, y->g, y->ld, gamma, beta, silu, stats, x->g, x->ld, acc, E->gn_scratch(), st);
 }
 
@@ -1234,7 +1260,10 @@ inline void Engine::build_decoder() {
     if (i != nb - 1) h = upsample_conv(h, h->h * 2, h->w * 2, B + ".upsamplers.0");
   }
   h = group_norm(h, V + "decoder.conv_norm_out", 1e-6f, true);
+  head_gn = static_cast<GroupNormOp*>(cur_ops->back().get());
   dec_out = conv3x3(h, 3, V + "decoder.conv_out");
+  head_conv = static_cast<ConvOp*>(cur_ops->back().get());
+  head_act = arena.make<unsigned char>(static_cast<size_t>(N) * PPH * PPW + 64);
   named["vae.out"] = dec_out;
   MDC_CHECK(dec_out->h == PPH && dec_out->w == PPW, "decoder output %dx%d != padded size %dx%d", dec_out->h, dec_out->w,
             PPH, PPW);
@@ -1748,6 +1777,45 @@ inline cudaGraphExec_t capture_graph(Engine* e, F&& launches) {
   cudaGraphDestroy(graph);
   return exec;
 }
+// ---- sparse output head (head.cuh)
+inline bool Engine::sparse_head_allowed() const {
+  static const bool off = getenv("MDC_NO_SPARSEHEAD") != nullptr;
+  if (off || !head_gn || !head_conv) return false;
+  const GroupNormOp& gn = *head_gn;
+  const ConvOp& cv = *head_conv;
+  return !gn.plan.single_f() && !gn.plan.single_b() && !gn.epi && gn.silu && gn.x->ld == gn.x->c && gn.x->c % 64 == 0 && cv.y->c == 3 &&
+         !cv.res && cv.alpha == 1.f && cv.x == gn.y && h_opts.w_edge == 0.f && h_opts.w_smooth == 0.f &&
+         9 * gn.x->c * 4 + gn.plan.s.pix_per_block + 4096 <= 48 * 1024;  // wsum + flag bytes + warp sums in default shared memory
+}
+inline void Engine::head_fwd(cudaStream_t st) {
+  const GroupNormOp& gn = *head_gn;
+  const ConvOp& cv = *head_conv;
+  const Tensor* x = gn.x;
+  TailGeom g{N, H, W, ph, pw, PPH, PPW, dec_out->ld, interp_nearest};
+  const int Cp = ((x->c + 63) / 64) * 64;
+  launch_k(head_points_fwd_kernel, dim3(2 * g_num_sms()), dim3(256), 0, st, x->d, x->ld, x->c, gn.groups, Cp, gn.stats, gn.gamma, gn.beta, gn.silu,
+           cv.W->w, cv.bias, g, pt_idx, pt_off, dec_out->d);
+}
+inline void Engine::head_bwd(cudaStream_t st) {
+  const GroupNormOp& gn = *head_gn;
+  const ConvOp& cv = *head_conv;
+  const Tensor* x = gn.x;
+  const GNPlan& p = gn.plan;
+  const int Cp = ((x->c + 63) / 64) * 64;
+  SparseDy sp{dec_out->g, dec_out->ld, PPH, PPW};
+  const int grid = p.s.N * p.s.blocks_per_img;
+  const size_t wsum_b = static_cast<size_t>(9) * x->c * sizeof(float) + ((p.s.pix_per_block + 15) & ~15);  // + the block's flag bytes
+  const size_t warp_b = static_cast<size_t>((((p.threads_b + 31) / 32) * 2 * p.G + 3) & ~3) * sizeof(float);
+  const GNScratch sc = gn_scratch();
+  launch_k(gn_bwd_stats_sp_kernel, dim3(grid), dim3(p.threads_b), warp_b + wsum_b, st, x->d, sp, cv.W->w, Cp, p.s, gn.stats, gn.gamma, gn.beta,
+           gn.silu, sc.partial, sc.gstats, sc.ticket, head_act);
+  if (gn.acc)
+    launch_k(gn_bwd_apply_sp_kernel<true>, dim3(grid), dim3(p.threads_b), wsum_b, st, x->d, sp, cv.W->w, Cp, p.s, gn.stats,
+             static_cast<const float*>(sc.gstats), gn.gamma, gn.beta, gn.silu, static_cast<const unsigned char*>(head_act), x->g, x->ld);
+  else
+    launch_k(gn_bwd_apply_sp_kernel<false>, dim3(grid), dim3(p.threads_b), wsum_b, st, x->d, sp, cv.W->w, Cp, p.s, gn.stats,
+             static_cast<const float*>(sc.gstats), gn.gamma, gn.beta, gn.silu, static_cast<const unsigned char*>(head_act), x->g, x->ld);
+}
 inline void Engine::step() {
   MDC_CHECK(begun, "mdc_step called before mdc_begin");
   MDC_CHECK(steps_done < cfg.steps, "all %d steps already done", cfg.steps);
@@ -1758,7 +1826,7 @@ inline void Engine::step() {
     MDC_CUDA(cudaGraphLaunch(step_graph, stream));
   }
   ++steps_done;
-  launches += launches_per_step;
+  launches += launches_per_step - (sparse_head_allowed() ? 2 : 0);  // sparse head: no gn_apply forward, no conv_out dgrad
 }
 inline void Engine::step_launches() {
   const int hw = lh * lw, lat_pix = N * hw;
@@ -1783,6 +1851,11 @@ inline void Engine::step_launches() {
   run_ops(unet_ops, false);
   dbg_points("after unet fwd");
   launch_k(x0_kernel, dim3(pgrid), dim3(256), 0, stream, unet_out->d, x, cur, N, hw, cfg.vae_scaling, dec_in->d, eps_part, x1_part, x2_part);
+  struct HeadGuard {  // never leave the flag raised (an exception from a launch must not turn later dense decodes sparse)
+    bool& f;
+    ~HeadGuard() { f = false; }
+  } head_guard{sparse_head};
+  sparse_head = sparse_head_allowed();  // the loss below reads the decoded map at the tap pixels of the valid points only
   run_ops(dec_ops, false);
   dbg_points("after decoder fwd");
   launch_k(loss_points_kernel, dim3(N), dim3(512), 0, stream, dec_out->d, g, pt_idx, pt_val, pt_off, gminmax, depth_minmax, opts, accum, dmean);
@@ -1796,6 +1869,7 @@ inline void Engine::step_launches() {
            depth_minmax, opts, dn_map, gray_gx, gray_gy, accum, dmean);
   launch_k(dec_grad_kernel, dim3(static_cast<int>((npix + 255) / 256)), dim3(256), 0, stream, dmean, npix, dec_out->g);
   run_ops(dec_ops, true);
+  sparse_head = false;
   launch_k(dx0_kernel, dim3((lat_pix + 255) / 256), dim3(256), 0, stream, dec_in->g, cur, N, hw, cfg.vae_scaling, unet_out->g, dx_direct);
   run_ops(unet_ops, true);
   launch_k(grad_total_kernel, dim3(pgrid), dim3(256), 0, stream, dx_direct, unet_in->g, N, hw, gbuf, g_part, x, x1_part, x2_part, opts, accum);
@@ -1897,7 +1971,12 @@ inline void Engine::set_options(int projection, int inv, int opt, const float* w
   MDC_CHECK(w4 && w4[0] + w4[1] + w4[2] + w4[3] > 0.f, "loss_funcs must contain at least one loss function");
   MDC_CHECK(qlo >= 0.f && qlo <= 1.f && qhi >= 0.f && qhi <= 1.f, "percentile must be in [0, 1], but got (%g, %g)", qlo, qhi);
   h_opts.projection = projection, h_opts.inv = inv ? 1 : 0, h_opts.opt = opt, h_opts.kld_mode = kld_mode, h_opts.kld_weight = kld_weight;
+  const bool sparse_before = sparse_head_allowed();
   h_opts.w_l1 = w4[0], h_opts.w_l2 = w4[1], h_opts.w_edge = w4[2], h_opts.w_smooth = w4[3];
+  if (sparse_before != sparse_head_allowed() && step_graph) {  // the dense losses need the dense head: re-capture
+    cudaGraphExecDestroy(step_graph);
+    step_graph = nullptr;
+  }
   q_lo = qlo, q_hi = qhi;
   h_opts.closed_form = closed_form ? 1 : 0;
 }

@@ -776,15 +776,40 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int ksplit, l
   ptx::pdl_launch();
   const int nv = (N + 3) >> 2;
   const long long total = rows * nv;
+  // vector epilogue: every operand row starts on an 8-byte (bf16) / 16-byte (fp32) boundary
+  const bool vec = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                   (!res || ((ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(res) & 7) == 0));
   for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
     const long long r = i / nv;
     const int c = static_cast<int>(i % nv) * 4;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4  // four partial loads in flight per thread; the order of the additions is unchanged
     for (int s = 0; s < ksplit; ++s) {
       const float4 v = *reinterpret_cast<const float4*>(ws + s * split_stride + r * ws_ld + c);
       a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
     }
     float v[4] = {a.x * alpha, a.y * alpha, a.z * alpha, a.w * alpha};
+    if (vec && c + 3 < N) {  // same arithmetic as the scalar tail below, one 8- / 16-byte access per operand
+      if (bias) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] += bias[c + j];
+      }
+      if (res) {
+        const uint2 rr = *reinterpret_cast<const uint2*>(res + r * ldr + c);
+        const float2 r0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr.x));
+        const float2 r1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr.y));
+        v[0] += r0.x, v[1] += r0.y, v[2] += r1.x, v[3] += r1.y;
+      }
+      if (out_f32) {
+        *reinterpret_cast<float4*>(static_cast<float*>(out) + r * ldc + c) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+        uint2 o;
+        *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(v[0], v[1]);
+        *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + r * ldc + c) = o;
+      }
+      continue;
+    }
     for (int j = 0; j < 4 && c + j < N; ++j) {
       float x = v[j];
       if (bias) x += bias[c + j];

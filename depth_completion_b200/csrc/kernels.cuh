@@ -15,10 +15,20 @@ namespace mdc {
 
 typedef __nv_bfloat16 bf16;
 
+// Eight bf16 channels = one 16-byte access.  The copy operations move the whole vector as a uint4: a member-wise copy of
+// four __nv_bfloat162 is compiled into four 32-bit loads / stores (cuobjdump: LDG.E / STG.E instead of LDG.E.128 /
+// STG.E.128), i.e. four partially filled sector requests per warp instruction on every HBM stream of this file.
 struct alignas(16) BF8 {
   __nv_bfloat162 v[4];
+  __host__ __device__ __forceinline__ BF8() {}
+  __host__ __device__ __forceinline__ BF8(const BF8& o) { *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(o.v); }
+  __host__ __device__ __forceinline__ BF8& operator=(const BF8& o) {
+    *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(o.v);
+    return *this;
+  }
 };
-__device__ __forceinline__ void bf8_to_f(const BF8& b, float (&f)[8]) {
+// by value on purpose: the argument is usually a global / shared memory reference, and the copy is ONE 16-byte load
+__device__ __forceinline__ void bf8_to_f(const BF8 b, float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float2 t = __bfloat1622float2(b.v[i]);
@@ -1224,6 +1234,11 @@ __global__ void vec_affine_kernel(float* __restrict__ v, long long n, float scal
 
 // =========================================================================== LayerNorm (one warp per row)
 constexpr int LN_MAXV = 5;  // supports d <= 32*8*5 = 1280
+// eight consecutive parameters as two 16-byte loads (parameter vectors are 256-byte aligned arena blocks)
+__device__ __forceinline__ void ld_f8(const float* __restrict__ p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x, f[1] = a.y, f[2] = a.z, f[3] = a.w, f[4] = b.x, f[5] = b.y, f[6] = b.z, f[7] = b.w;
+}
 
 __global__ void ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, int rows, int d, const float* __restrict__ gamma,
                               const float* __restrict__ beta, float eps, bf16* __restrict__ y, long long ldy,
@@ -1263,9 +1278,11 @@ __global__ void ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, int row
   for (int k = 0; k < LN_MAXV; ++k) {
     int v = lane + 32 * k;
     if (v < nv) {
-      float o[8];
+      float o[8], ga[8], be[8];
+      ld_f8(gamma + v * 8, ga);
+      ld_f8(beta + v * 8, be);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = (f[k][i] - mean) * rstd * gamma[v * 8 + i] + beta[v * 8 + i];
+      for (int i = 0; i < 8; ++i) o[i] = (f[k][i] - mean) * rstd * ga[i] + be[i];
       *reinterpret_cast<BF8*>(y + row * ldy + v * 8) = f_to_bf8(o);
     }
   }
@@ -1286,13 +1303,14 @@ __global__ void ln_bwd_kernel(const bf16* __restrict__ x, long long ldx, const b
   for (int k = 0; k < LN_MAXV; ++k) {
     int v = lane + 32 * k;
     if (v < nv) {
-      float fx[8], fd[8];
+      float fx[8], fd[8], ga[8];
       bf8_to_f(*reinterpret_cast<const BF8*>(x + row * ldx + v * 8), fx);
       bf8_to_f(*reinterpret_cast<const BF8*>(dy + row * lddy + v * 8), fd);
+      ld_f8(gamma + v * 8, ga);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         xh[k][i] = (fx[i] - mean) * rstd;
-        dh[k][i] = fd[i] * gamma[v * 8 + i];
+        dh[k][i] = fd[i] * ga[i];
         a += dh[k][i];
         b += dh[k][i] * xh[k][i];
       }

@@ -78,7 +78,14 @@ inline GNPlan plan_groupnorm(int N, int HW, int C, int G, long long ld, int mode
   GNShape s;
   s.N = N, s.HW = HW, s.C = C, s.G = G, s.ld = ld;
   const int sms = g_num_sms();
-  int want_blocks = std::max(1, (2 * sms) / N);
+  // blocks per SM of the two-pass kernels (two are resident; more than two makes a second, self-balancing wave).
+  // MDC_GN_BPS overrides it for sweeps (read once).
+  static const int bps = [] {
+    const char* e = getenv("MDC_GN_BPS");
+    const int v = e ? atoi(e) : 0;
+    return v >= 1 && v <= 16 ? v : 2;
+  }();
+  int want_blocks = std::max(1, (bps * sms) / N);
   int ppb = std::max(R, (s.HW + want_blocks - 1) / want_blocks);
   ppb = ((ppb + R - 1) / R) * R;
   s.pix_per_block = ppb;
@@ -176,6 +183,18 @@ inline void run_gn_fwd(const GNPlan& p, const bf16* x, bf16* y, long long ldy, c
   }
   if (!have_stats) launch_k(gn_stats_kernel, dim3(grid), dim3(p.threads), wsum, st, x, p.s, sc.partial, eps, stats, sc.ticket);
   launch_k(gn_apply_kernel, dim3(grid), dim3(p.threads), 0, st, x, p.s, stats, gamma, beta, silu, y, ldy, epi_partial, epi_parts, eps);
+}
+// Forward statistics only (two-pass plans): (mean, rstd) per (image, group) into `stats`, no normalised output.  Used by
+// the sparse output head of the decoder (head.cuh), which evaluates the normalisation at a few thousand pixels itself.
+inline void run_gn_stats(const GNPlan& p, const bf16* x, float eps, float* stats, const GNScratch& sc, cudaStream_t st) {
+  MDC_CHECK(!p.single_f(), "run_gn_stats: two-pass plans only");
+  const int grid = p.s.N * p.s.blocks_per_img;
+  static const bool no_stream = getenv("MDC_NO_GNSTREAM") != nullptr;
+  const size_t wsum = ((p.threads + 31) / 32) * 2 * p.G * sizeof(float);
+  if (!no_stream && p.s.ld == p.s.C)
+    launch_k(gn_stats_s_kernel, dim3(grid), dim3(p.threads), gns_smem_bytes(p.threads, 1) + wsum, st, x, p.s, sc.partial, eps, stats, sc.ticket);
+  else
+    launch_k(gn_stats_kernel, dim3(grid), dim3(p.threads), wsum, st, x, p.s, sc.partial, eps, stats, sc.ticket);
 }
 inline void run_gn_bwd(const GNPlan& p, const bf16* x, const bf16* dy, long long lddy, const float* gamma, const float* beta, int silu,
                        const float* stats, bf16* dx, long long lddx, int acc, const GNScratch& sc, cudaStream_t st) {

@@ -281,11 +281,11 @@ def test_predict_and_analyze_commands_on_the_gpu(tmp_path):
     from depth_completion_b200 import dataset_io as dio
 
     for k in range(3):
-        a = dio.load_dense(dst / "dense" / "cam0" / f"{k:03d}.npz")
-        b = dio.load_dense(dst2 / "dense" / "cam0" / f"{k:03d}.npz")
+        a = dio.load_dense(dst / "seq_a" / "dense" / "cam0" / f"{k:03d}.npz")
+        b = dio.load_dense(dst2 / "seq_a" / "dense" / "cam0" / f"{k:03d}.npz")
         assert a.shape == (1, 96, 128) and np.isfinite(a).all() and a.min() >= 0.0 and a.max() <= 120.0
         assert np.array_equal(a, b)
-        assert (dst / "vis" / "cam0" / f"{k:03d}_vis.jpg").exists() and not (dst2 / "vis").exists()
+        assert (dst / "seq_a" / "vis" / "cam0" / f"{k:03d}_vis.jpg").exists() and not (dst2 / "seq_a" / "vis").exists()
     r = subprocess.run([sys.executable, "-m", "depth_completion_b200.analyze", str(src), str(dst)], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]

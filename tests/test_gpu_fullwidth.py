@@ -104,7 +104,12 @@ def _compare(tag, pipe, o32, o16, imgs, sparses, cfg, state32, t, st32, st16):
         assert e_ours <= 1.3 * e_16 + 3e-3 + extra, f"{tag} {name}: engine {e_ours:.3e} vs torch-bf16 {e_16:.3e} (rel L2 to the fp32 oracle)"
     l32, l16 = state32["losses"].float().cpu(), r16["losses"].float().cpu()
     for i in range(cfg["N"]):
-        tol = max(1.5 * abs(l16[i].item() - l32[i].item()), 1e-2 * l32[i].item())
+        # The loss sums |d| + d^2 over 500 points whose residuals sit near the L1 kink.  Measured over repeated runs (the
+        # fp32 oracle's own 50-step trajectory differs from run to run on the GPU): engine 0.15 - 1.7 % from the fp32 value,
+        # torch-bf16 0.1 - 5.8 %.  A 1 % floor failed one run in three whenever torch-bf16 happened to land within 0.1 %;
+        # the floor is 2x the largest engine deviation seen.
+        tol = max(1.5 * abs(l16[i].item() - l32[i].item()), 3e-2 * l32[i].item())
+        print(f"[full width] {tag} loss[{i}]: engine {loss[i].item():.5f}, fp32 oracle {l32[i].item():.5f}, torch-bf16 {l16[i].item():.5f}")
         assert abs(loss[i].item() - l32[i].item()) <= tol, f"{tag} loss[{i}]: {loss[i].item():.5f} vs fp32 {l32[i].item():.5f} (bf16 {l16[i].item():.5f})"
     # Adam: elements whose fp32 update direction is unambiguous must move the same way
     xa = eng.dbg_x_adam().float()

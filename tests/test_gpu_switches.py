@@ -46,3 +46,34 @@ def test_side_stream_and_graph_are_bitwise_neutral(cuda):
     assert a == b, "two identical runs differ: the step is not deterministic"
     assert a == c, "side-stream branch changes the result: a race or a missing join"
     assert a == d, "graph replay / programmatic dependent launch changes the result"
+
+
+@pytest.mark.parametrize("kind,n", [("nyu", 1), ("kitti", 1), ("nyu", 2)])
+def test_sparse_output_head_matches_dense_head(cuda, tmp_path, kind, n):
+    """head.cuh: inside a guided step conv_norm_out + conv_out of the KL decoder are evaluated only at the bilinear taps of
+    the valid points (forward) and their 3x3 neighbourhoods (backward).  Same state, same step, with and without
+    MDC_NO_SPARSEHEAD at full width (500 scattered points; a KITTI-shaped frame whose points sit on scan lines; batch 2):
+    the loss agrees to fp32 summation order and the gradients to a fraction of the bf16 rounding of one layer."""
+    import torch
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    recs = []
+    for tag, extra in (("sparse", {}), ("dense", {"MDC_NO_SPARSEHEAD": "1"})):
+        env = dict(os.environ)
+        env.update(extra)
+        out = tmp_path / f"{tag}.pt"
+        r = subprocess.run([sys.executable, os.path.join(here, "head_case.py"), str(out), kind, str(n)], env=env, capture_output=True,
+                           text=True, timeout=900)
+        assert r.returncode == 0 and "HEAD_CASE_OK" in r.stdout, f"{tag}: rc {r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-3000:]}"
+        recs.append(torch.load(out))
+    a, b = recs
+
+    def rel(u, v):
+        return ((u - v).norm() / v.norm().clamp_min(1e-30)).item()
+
+    assert torch.isfinite(a["grad0"]).all() and b["grad0"].norm() > 0
+    assert (a["loss0"] - b["loss0"]).abs().max().item() <= 2e-3 * b["loss0"].abs().max().item(), (a["loss0"], b["loss0"])
+    assert rel(a["dz0"], b["dz0"]) < 2e-2, rel(a["dz0"], b["dz0"])      # through the whole decoder backward in bf16
+    assert rel(a["grad0"], b["grad0"]) < 3e-2, rel(a["grad0"], b["grad0"])
+    # the second step starts from the first one's Adam update (+-lr per element): only the loss is compared
+    assert (a["loss1"] - b["loss1"]).abs().max().item() <= 5e-2 * b["loss1"].abs().max().item(), (a["loss1"], b["loss1"])
