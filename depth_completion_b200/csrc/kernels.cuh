@@ -120,6 +120,7 @@ struct GNShape {
   long long ld;        // pixel stride of x / y (elements)
   int pix_per_block;   // pixels handled by one block
   int blocks_per_img;  // gridDim.x = N * blocks_per_img
+  int stages1 = 0;     // ring depth of the streamed ONE-tensor kernels (gn_stats_s / gn_apply_s); 0 = GNS_STAGES
 };
 
 // The last block of an image to finish (atomic ticket) reduces the per-block partials of that image in a FIXED order,
@@ -771,12 +772,13 @@ struct GnsPipe {
   uint64_t* full;      // [GNS_STAGES]
   uint8_t* buf;        // [GNS_STAGES][ntens][chunk_bytes]
   uint32_t chunk_bytes, ntens;
+  int stages;
   const uint8_t* src[2];
   long long total_bytes;  // bytes of this block's slab (per tensor)
   int nchunks;
 };
 __device__ __forceinline__ void gns_issue(const GnsPipe& q, int k) {  // one thread
-  const int st = k % GNS_STAGES;
+  const int st = k % q.stages;
   const long long off = 1LL * k * q.chunk_bytes;
   const uint32_t bytes = static_cast<uint32_t>(min(static_cast<long long>(q.chunk_bytes), q.total_bytes - off));
   ptx::mbar_expect_tx(&q.full[st], bytes * q.ntens);
@@ -784,8 +786,9 @@ __device__ __forceinline__ void gns_issue(const GnsPipe& q, int k) {  // one thr
 }
 // Sets the ring up and requests the first GNS_STAGES - 1 chunks.  smem: [8 x u64 barriers][stages x ntens x chunk].
 __device__ __forceinline__ GnsPipe gns_begin(uint8_t* smem, const bf16* t0, const bf16* t1, long long elem_off, long long elems, int C,
-                                             int R) {
+                                             int R, int stages = GNS_STAGES) {
   GnsPipe q;
+  q.stages = stages;
   q.full = reinterpret_cast<uint64_t*>(smem);
   q.buf = smem + 128;
   q.ntens = t1 ? 2u : 1u;
@@ -795,22 +798,25 @@ __device__ __forceinline__ GnsPipe gns_begin(uint8_t* smem, const bf16* t0, cons
   q.total_bytes = elems * 2;
   q.nchunks = static_cast<int>((q.total_bytes + q.chunk_bytes - 1) / q.chunk_bytes);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < GNS_STAGES; ++i) ptx::mbar_init(&q.full[i], 1);
+    for (int i = 0; i < q.stages; ++i) ptx::mbar_init(&q.full[i], 1);
     ptx::fence_mbar_init();
   }
   __syncthreads();
   if (threadIdx.x == 0)
-    for (int k = 0; k < GNS_STAGES - 1 && k < q.nchunks; ++k) gns_issue(q, k);
+    for (int k = 0; k < q.stages - 1 && k < q.nchunks; ++k) gns_issue(q, k);
   return q;
 }
 // Per chunk: the refill of the stage consumed in the PREVIOUS iteration is requested first (every thread passed the
 // __syncthreads that ended that iteration), then the block waits for this chunk's bytes.
 __device__ __forceinline__ const uint8_t* gns_acquire(const GnsPipe& q, int k) {
-  if (threadIdx.x == 0 && k + GNS_STAGES - 1 < q.nchunks) gns_issue(q, k + GNS_STAGES - 1);
-  ptx::mbar_wait(&q.full[k % GNS_STAGES], (k / GNS_STAGES) & 1);
-  return q.buf + (k % GNS_STAGES) * q.ntens * q.chunk_bytes;
+  if (threadIdx.x == 0 && k + q.stages - 1 < q.nchunks) gns_issue(q, k + q.stages - 1);
+  ptx::mbar_wait(&q.full[k % q.stages], (k / q.stages) & 1);
+  return q.buf + (k % q.stages) * q.ntens * q.chunk_bytes;
 }
-__host__ __device__ inline size_t gns_smem_bytes(int threads, int ntens) { return 128 + static_cast<size_t>(GNS_STAGES) * ntens * threads * GNS_UNROLL * 16; }
+__host__ __device__ inline size_t gns_smem_bytes(int threads, int ntens, int stages = GNS_STAGES) {
+  return 128 + static_cast<size_t>(stages) * ntens * threads * GNS_UNROLL * 16;
+}
+__host__ __device__ inline int gns_stages1(const GNShape& s) { return s.stages1 > 0 ? s.stages1 : GNS_STAGES; }
 
 __global__ void __launch_bounds__(512, 2) gn_stats_s_kernel(const bf16* __restrict__ x, GNShape s, float* __restrict__ partial, float eps,
                                                             float* __restrict__ stats_out, unsigned int* __restrict__ ticket) {
@@ -821,10 +827,10 @@ __global__ void __launch_bounds__(512, 2) gn_stats_s_kernel(const bf16* __restri
   const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
   const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
   const int nwarps_ = (blockDim.x + 31) >> 5;
-  float* sh = reinterpret_cast<float*>(gns_smem + gns_smem_bytes(blockDim.x, 1));  // [warps][2G]
+  float* sh = reinterpret_cast<float*>(gns_smem + gns_smem_bytes(blockDim.x, 1, gns_stages1(s)));  // [warps][2G]
   for (int i = threadIdx.x; i < nwarps_ * 2 * s.G; i += blockDim.x) sh[i] = 0.f;
   const int p0 = b * s.pix_per_block, npix = min(s.HW, p0 + s.pix_per_block) - p0;
-  GnsPipe q = gns_begin(gns_smem, x, nullptr, (1LL * n * s.HW + p0) * s.C, 1LL * npix * s.C, s.C, R);
+  GnsPipe q = gns_begin(gns_smem, x, nullptr, (1LL * n * s.HW + p0) * s.C, 1LL * npix * s.C, s.C, R, gns_stages1(s));
   float2 sum2[4], sq2[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) sum2[i] = sq2[i] = make_float2(0.f, 0.f);
@@ -864,7 +870,7 @@ __global__ void __launch_bounds__(512, 2) gn_apply_s_kernel(const bf16* __restri
   const int cv = threadIdx.x % CV, r = threadIdx.x / CV, R = blockDim.x / CV;
   const int n = blockIdx.x / s.blocks_per_img, b = blockIdx.x % s.blocks_per_img;
   const int p0 = b * s.pix_per_block, npix = min(s.HW, p0 + s.pix_per_block) - p0;
-  GnsPipe q = gns_begin(gns_smem, x, nullptr, (1LL * n * s.HW + p0) * s.C, 1LL * npix * s.C, s.C, R);  // loads fly during the prologue
+  GnsPipe q = gns_begin(gns_smem, x, nullptr, (1LL * n * s.HW + p0) * s.C, 1LL * npix * s.C, s.C, R, gns_stages1(s));  // loads fly during the prologue
   if (partial) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const double m = 1.0 * s.HW * cpg;

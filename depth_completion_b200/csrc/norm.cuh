@@ -90,6 +90,15 @@ inline GNPlan plan_groupnorm(int N, int HW, int C, int G, long long ld, int mode
   ppb = ((ppb + R - 1) / R) * R;
   s.pix_per_block = ppb;
   s.blocks_per_img = (s.HW + ppb - 1) / ppb;
+  // ring depth of the streamed one-tensor kernels: as many 16 KB stages as two resident blocks can hold under the
+  // 112 KB opt-in (MDC_GNS_STAGES overrides it for sweeps, read once)
+  static const int st1 = [] {
+    const char* e = getenv("MDC_GNS_STAGES");
+    const int v = e ? atoi(e) : 0;
+    return v >= 2 && v <= 12 ? v : 6;  // 4 -> 6: 19.28 / 19.54 -> 19.22 / 19.31 ms per step in an interleaved sweep on one box
+  }();
+  s.stages1 = st1;
+  while (s.stages1 > 2 && gns_smem_bytes(p.threads, 1, s.stages1) + ((p.threads + 31) / 32) * 2 * G * sizeof(float) > 112 * 1024) --s.stages1;
   p.s = s;
   // single-launch variant: one CTA per SM at most, its pixel slab (x, or x and dy) staged in shared memory
   static const bool no_fuse = getenv("MDC_NO_GNFUSE") != nullptr;
@@ -176,8 +185,8 @@ inline void run_gn_fwd(const GNPlan& p, const bf16* x, bf16* y, long long ldy, c
   const size_t wsum = ((p.threads + 31) / 32) * 2 * p.G * sizeof(float);
   if (!no_stream && p.s.ld == p.s.C) {
     if (!have_stats)
-      launch_k(gn_stats_s_kernel, dim3(grid), dim3(p.threads), gns_smem_bytes(p.threads, 1) + wsum, st, x, p.s, sc.partial, eps, stats, sc.ticket);
-    launch_k(gn_apply_s_kernel, dim3(grid), dim3(p.threads), gns_smem_bytes(p.threads, 1), st, x, p.s, stats, gamma, beta, silu, y, ldy,
+      launch_k(gn_stats_s_kernel, dim3(grid), dim3(p.threads), gns_smem_bytes(p.threads, 1, gns_stages1(p.s)) + wsum, st, x, p.s, sc.partial, eps, stats, sc.ticket);
+    launch_k(gn_apply_s_kernel, dim3(grid), dim3(p.threads), gns_smem_bytes(p.threads, 1, gns_stages1(p.s)), st, x, p.s, stats, gamma, beta, silu, y, ldy,
              epi_partial, epi_parts, eps);
     return;
   }
@@ -192,7 +201,7 @@ inline void run_gn_stats(const GNPlan& p, const bf16* x, float eps, float* stats
   static const bool no_stream = getenv("MDC_NO_GNSTREAM") != nullptr;
   const size_t wsum = ((p.threads + 31) / 32) * 2 * p.G * sizeof(float);
   if (!no_stream && p.s.ld == p.s.C)
-    launch_k(gn_stats_s_kernel, dim3(grid), dim3(p.threads), gns_smem_bytes(p.threads, 1) + wsum, st, x, p.s, sc.partial, eps, stats, sc.ticket);
+    launch_k(gn_stats_s_kernel, dim3(grid), dim3(p.threads), gns_smem_bytes(p.threads, 1, gns_stages1(p.s)) + wsum, st, x, p.s, sc.partial, eps, stats, sc.ticket);
   else
     launch_k(gn_stats_kernel, dim3(grid), dim3(p.threads), wsum, st, x, p.s, sc.partial, eps, stats, sc.ticket);
 }

@@ -19,6 +19,7 @@ NATIVE = ("UTC*MMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "HMMA", "UBLKCP", "UC
 def main():
     out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
     counts, order, cur = collections.defaultdict(collections.Counter), [], None
+    widths = collections.defaultdict(collections.Counter)
     for line in out.splitlines():
         m = re.search(r"Function : (\S+)", line)
         if m:
@@ -31,6 +32,12 @@ def main():
             for k, p in PAT.items():
                 if p.search(line):
                     counts[cur][k] += 1
+            m2 = re.search(r"\b(LDG|STG)(\.[A-Z0-9]+)*", line)
+            if m2:
+                op = m2.group(0)
+                w = "128" if ".128" in op else "64" if ".64" in op else None if (".U8" in op or ".U16" in op or ".S8" in op or ".S16" in op) else "32"
+                if w:
+                    widths[cur][m2.group(1) + w] += 1
     print(f"# cuobjdump -sass {os.path.relpath(LIB, ROOT)} (sm_100a): instruction counts per kernel")
     print("| kernel | " + " | ".join(PAT) + " |")
     print("|---|" + "---|" * len(PAT))
@@ -41,6 +48,16 @@ def main():
     others = [k for k in order if not any(counts[k][x] for x in NATIVE)]
     print(f"\n{len(others)} further kernels are bandwidth-bound CUDA-core kernels without tensor / TMA / bulk-copy / cluster instructions "
           f"(GroupNorm, LayerNorm, GEGLU, the step tail, ...): " + ", ".join(sorted(set(o.split("<")[0].split("::")[-1] for o in others))))
+    # global access widths of the bandwidth kernels (a BF8 channel vector must move as ONE 16-byte access; before the copy
+    # operations of BF8 moved a uint4 these kernels issued four 32-bit accesses per vector)
+    print("\n## global load / store widths of the non-GEMM kernels that move channel vectors (instruction counts)")
+    print("| kernel | LDG.128 | LDG.64 | LDG.32 | STG.128 | STG.64 | STG.32 |")
+    print("|---|---|---|---|---|---|---|")
+    for k in order:
+        if widths[k]["LDG128"] + widths[k]["STG128"] == 0 or any(counts[k][x] for x in ("UTC*MMA",)) or "cub::" in k:
+            continue
+        w = widths[k]
+        print(f"| {k} | {w['LDG128']} | {w['LDG64']} | {w['LDG32']} | {w['STG128']} | {w['STG64']} | {w['STG32']} |")
     f2 = [k for k in order if counts[k]["FFMA2"]]
     print("\nkernels using packed fp32x2 FMAs (FFMA2): " + ", ".join(f"{k.split('<')[0]} ({counts[k]['FFMA2']})" for k in f2))
 
