@@ -5,9 +5,10 @@ Same arguments, option names, defaults and fall-backs as `predict.py:25-343` (op
 same outputs (`<dst>/<dataset>/dense/<rel>.{bl2,npz,npy}` and `<dst>/<dataset>/vis/<rel stem>_vis.jpg`, `:717-764`).  What
 differs, because the hot path behind it differs:
 
-* `--precision fp32`, `--model lcm`, `--interp-mode nearest`, `--train-method per-input` and `--train-latents False` name
-  arithmetic this library does not have: they stop with a CRITICAL message instead of silently
-  running the default arm.
+* `--precision fp32`, `--model lcm`, `--train-method per-input` and `--closed-form True` together with `edge` / `smooth`
+  name arithmetic this library does not have: they stop with a CRITICAL message instead of silently
+  running the default arm.  Everything else of the option table runs in the library, including `--interp-mode nearest`,
+  `--train-latents False` (plain DDIM sampling + closed-form scale / shift), the three optimisers, projections and norms.
 * `--compile-graph` / `--compile-mode` are accepted and ignored: the guided step is always one captured CUDA graph.
 * `--use-segmask`: the reference loads the masks and never hands them to the pipeline call (`predict.py:659-694`); here
   the flag only checks that the files exist, like the reference's pairing step does (`:520-571`).
@@ -82,10 +83,10 @@ def resolve_options(o: dict, log) -> dict:
         raise OptionError("--precision fp32: the B200 engine computes in bfloat16 with fp32 accumulation only")
     if o["model"] == "lcm":
         raise OptionError("--model lcm: the LCM scheduler arm is outside the B200 hot path (DDIM, v-prediction)")
-    if o["interp_mode"] != "bilinear":
-        raise OptionError(f"--interp-mode {o['interp_mode']}: only bilinear is built")
-    if o["train_method"] != "per-step" or not o["train_latents"]:
-        raise OptionError("--train-method per-input / --train-latents False are outside the B200 hot path")
+    if o["train_latents"] and o["train_method"] != "per-step":
+        raise OptionError("--train-method per-input is outside the B200 hot path (and fails upstream: SURVEY.md section 2)")
+    if o["train_latents"] and o["closed_form"] and any(f in ("edge", "smooth") for f in o["loss_funcs"]):
+        raise OptionError("--closed-form True with edge / smooth losses is not built (gradient of the dense terms through the fit)")
     if o["compile_graph"]:
         log.warning("--compile-graph is ignored: the guided step always runs as one captured CUDA graph")
     if o["compress"] is None:

@@ -101,10 +101,13 @@ def test_resolve_options_follows_the_reference_fallbacks():
     with pytest.raises(OptionError):
         resolve_options(_defaults(vis_order=["bogus"]), ListLog())
     assert resolve_options(_defaults(vis=False, vis_order=["bogus"], compress="npz"), ListLog())["vis_order"] == ["bogus"]
-    for bad in (dict(precision="fp32"), dict(model="lcm"), dict(interp_mode="nearest"), dict(train_method="per-input"),
-                dict(train_latents=False)):
+    for bad in (dict(precision="fp32"), dict(model="lcm"), dict(train_method="per-input"),
+                dict(closed_form=True, loss_funcs=["l1", "smooth"])):
         with pytest.raises(OptionError):
             resolve_options(_defaults(compress="npz", **bad), ListLog())
+    # branches the library does run: nearest resampling, plain DDIM sampling with the closed-form fit (predict.py:437-455)
+    o = resolve_options(_defaults(compress="npz", interp_mode="nearest", train_latents=False, train_method="per-input"), ListLog())
+    assert o["interp_mode"] == "nearest" and o["train_latents"] is False and o["closed_form"] is True
     from depth_completion_b200 import dataset_io as dio
 
     o = resolve_options(_defaults(), ListLog())
@@ -286,6 +289,13 @@ def test_predict_and_analyze_commands_on_the_gpu(tmp_path):
         assert a.shape == (1, 96, 128) and np.isfinite(a).all() and a.min() >= 0.0 and a.max() <= 120.0
         assert np.array_equal(a, b)
         assert (dst / "seq_a" / "vis" / "cam0" / f"{k:03d}_vis.jpg").exists() and not (dst2 / "seq_a" / "vis").exists()
+    # branches of the option table beside the default arm: plain DDIM sampling with the closed-form fit, nearest resampling
+    dst3 = tmp_path / "dst3"
+    cmd = base[:4] + [str(dst3)] + base[4:] + ["--train-latents", "False", "--interp-mode", "nearest", "--vis", "False", "-c", "npy"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    c = dio.load_dense(dst3 / "seq_a" / "dense" / "cam0" / "000.npy")
+    assert c.shape == (1, 96, 128) and np.isfinite(c).all()
     r = subprocess.run([sys.executable, "-m", "depth_completion_b200.analyze", str(src), str(dst)], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
