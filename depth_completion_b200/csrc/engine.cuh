@@ -1737,6 +1737,7 @@ inline void Engine::release_workspace() {
   if (sample_graph) cudaGraphExecDestroy(sample_graph);
   step_graph = sample_graph = nullptr;
   unet_ops.clear(), dec_ops.clear(), enc_ops.clear();
+  head_gn = nullptr, head_conv = nullptr, head_act = nullptr, sparse_head = false;  // they pointed into dec_ops / the arena
   split_plans.clear();
   tensors.clear(), named.clear();
   arena.free_all();
