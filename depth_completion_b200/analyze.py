@@ -43,7 +43,7 @@ def _report(name, overall, binned, n_binned, n_pts, ranges, metrics, min_depth, 
 
 
 def run(dataset_root: Path, result_root: Path, metrics, calc_binned_scores=True, bin_size=10.0, max_sparse_depth=120.0,
-        max_depth=120.0, min_depth=0.0, batch_size=32, device="cpu", log=None) -> dict:
+        max_depth=120.0, min_depth=0.0, batch_size=32, device="cpu", log=None, num_threads: int = 1) -> dict:
     """The body of analyze.py:153-361 without click; returns what goes into `results_all.json`."""
     log = log or get_logger()
     dataset_root, result_root = Path(dataset_root), Path(result_root)
@@ -62,7 +62,8 @@ def run(dataset_root: Path, result_root: Path, metrics, calc_binned_scores=True,
             continue
         try:
             r = mt.evaluate_dataset(ds, result_dir, max_sparse_depth, min_depth, max_depth, metrics,
-                                    bin_size if calc_binned_scores else None, batch_size, device, keep_batches=True)
+                                    bin_size if calc_binned_scores else None, batch_size, device, keep_batches=True,
+                                    num_threads=num_threads)
         except FileNotFoundError:
             log.warning(f"No dense & sparse depth map pairs found for {ds.name}. Skip this dataset")
             continue
@@ -106,7 +107,7 @@ def run(dataset_root: Path, result_root: Path, metrics, calc_binned_scores=True,
 @click.option("--min-depth", type=click.FloatRange(min=0), default=0.0, show_default=True)
 @click.option("-bs", "--batch-size", type=click.IntRange(min=1), default=32, show_default=True)
 @click.option("-nt", "--num-threads", type=click.IntRange(min=1), default=8, show_default=True,
-              help="Accepted for compatibility (files are decoded in the calling thread).")
+              help="Number of threads for loading sparse & dense depth maps.")
 @click.option("--cuda", type=bool, default=True, show_default=True, help="Whether to use CUDA for faster processing.")
 def main(dataset_root, result_root, log, log_level, metrics, calc_binned_scores, bin_size, max_sparse_depth, max_depth,
          min_depth, batch_size, num_threads, cuda) -> None:
@@ -127,7 +128,7 @@ def main(dataset_root, result_root, log, log_level, metrics, calc_binned_scores,
         sys.exit(1)
     try:
         run(dataset_root, result_root, kept, calc_binned_scores, bin_size, max_sparse_depth, max_depth, min_depth, batch_size,
-            "cuda" if cuda else "cpu", logger)
+            "cuda" if cuda else "cpu", logger, num_threads)
     except FileNotFoundError as e:
         logger.critical(str(e))
         sys.exit(1)

@@ -73,6 +73,18 @@ def load_rgb(path: Path) -> torch.Tensor | None:
     return torch.from_numpy(arr.copy()).permute(2, 0, 1).contiguous()
 
 
+def load_many(paths, loader=load_rgb, num_threads: int = 1) -> list:
+    """`loader` over `paths`, in order, on up to `num_threads` threads (utils.py:817-970 loads a batch's files in parallel:
+    PIL and numpy release the GIL while decoding / decompressing).  Failed loads stay None."""
+    paths = list(paths)
+    if num_threads <= 1 or len(paths) <= 1:
+        return [loader(p) for p in paths]
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=min(num_threads, len(paths))) as ex:
+        return list(ex.map(loader, paths))
+
+
 def to_depth(imgs: torch.Tensor, max_distance: float = 120.0, dtype=torch.float32) -> torch.Tensor:
     """[N, 3, H, W] depth-coded images -> [N, 1, H, W] metres: max_distance * channel0 / 255 (utils.py:1137-1158)."""
     return max_distance * (imgs.to(dtype)[:, 0] / 255.0).unsqueeze(1)
@@ -172,7 +184,9 @@ def complete_dataset(pipe, src_root, dst_root, max_depth: float = 120.0, max_spa
     def runs_of(pairs):
         """Batches of decoded files, cut where the resolution changes (one pipeline call per run of equal shapes)."""
         for b0, b1 in sequence_batches(len(pairs), batch_size, use_prev_latent, rank, world):
-            loaded = [(load_rgb(i), load_rgb(sp), i, sp) for i, sp in pairs[b0:b1]]
+            chunk = pairs[b0:b1]  # like predict.py:612-625: one thread per file of the batch
+            files = load_many([i for i, _ in chunk] + [sp for _, sp in chunk], num_threads=2 * len(chunk))
+            loaded = [(files[k], files[len(chunk) + k], i, sp) for k, (i, sp) in enumerate(chunk)]
             loaded = [t for t in loaded if t[0] is not None and t[1] is not None]
             start = 0
             for k in range(1, len(loaded) + 1):

@@ -43,7 +43,7 @@ def calc_bins(lower: float, upper: float, size: float) -> list[tuple[float, floa
 
 def evaluate_dataset(dataset_dir, result_dir, max_sparse_depth: float = 120.0, min_depth: float = 0.0,
                      max_depth: float = 120.0, metrics=("mae", "rmse"), bin_size: float | None = None, batch_size: int = 1,
-                     device="cpu", keep_batches: bool = False) -> dict:
+                     device="cpu", keep_batches: bool = False, num_threads: int = 1) -> dict:
     """{"overall": {metric: score}, "num_points": n, "bins": [{"range": (lo, hi), metric: score, "num_points": n}, ...]}.
 
     `result_dir` is the directory holding `dense/` (what `complete_dataset` wrote for this dataset directory).
@@ -67,8 +67,10 @@ def evaluate_dataset(dataset_dir, result_dir, max_sparse_depth: float = 120.0, m
     n_pts, n_binned = 0, [0] * len(bins)
     for i in range(0, len(pairs), batch_size):
         chunk = pairs[i:i + batch_size]
-        sparses = dio.to_depth(torch.stack([dio.load_rgb(sp) for sp, _ in chunk]), max_distance=max_sparse_depth).to(device)
-        denses = torch.stack([torch.from_numpy(dio.load_dense(d)).reshape(1, *sparses.shape[-2:]) for _, d in chunk]).to(device)
+        sparses = dio.to_depth(torch.stack(dio.load_many([sp for sp, _ in chunk], num_threads=num_threads)),
+                               max_distance=max_sparse_depth).to(device)
+        denses = torch.stack([torch.from_numpy(a).reshape(1, *sparses.shape[-2:])
+                              for a in dio.load_many([d for _, d in chunk], dio.load_dense, num_threads)]).to(device)
         mask = sparses > 0
         if not mask.any():
             continue
