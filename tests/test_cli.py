@@ -166,6 +166,30 @@ def test_visualisation_panels_and_grid(tmp_path):
         vis.save_img_tensor(torch.zeros(3, 4, 4, dtype=torch.int32), tmp_path / "b.png")
 
 
+def test_load_many_keeps_order_and_failures(tmp_path):
+    """dataset_io.load_many (the parallel batch loader of utils.py:817-970): results in input order, None for a file that
+    cannot be decoded, same result on one thread and on many."""
+    from PIL import Image
+
+    from depth_completion_b200 import dataset_io as dio
+
+    paths = []
+    for k in range(7):
+        p = tmp_path / f"{k}.png"
+        if k == 3:
+            p.write_bytes(b"not a png")
+        else:
+            Image.fromarray(np.full((4, 5, 3), 10 * k, np.uint8)).save(p)
+        paths.append(p)
+    one = dio.load_many(paths, num_threads=1)
+    many = dio.load_many(paths, num_threads=8)
+    assert [t is None for t in one] == [t is None for t in many] == [k == 3 for k in range(7)]
+    for k, (a, b) in enumerate(zip(one, many)):
+        if k != 3:
+            assert a.shape == (3, 4, 5) and int(a[0, 0, 0]) == 10 * k and torch.equal(a, b)
+    assert dio.load_many([], num_threads=4) == []
+
+
 class EchoPipe:
     """Returns the sparse map it was given (+ an offset) as the dense map: the files around the call are what is tested."""
     device = "cpu"
