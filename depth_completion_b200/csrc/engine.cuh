@@ -392,6 +392,7 @@ struct Engine {
   struct ConvOp* head_conv = nullptr;
   unsigned char* head_act = nullptr;  // [N, PPH*PPW]: pixels that receive a gradient from conv_out in the current step
   bool sparse_head = false;
+  bool head_points_ok = true;  // set per frame in begin_state(): the taps' 3x3 neighbourhoods are a small part of the map
   bool sparse_head_allowed() const;
   void head_fwd(cudaStream_t st);
   void head_bwd(cudaStream_t st);
@@ -1587,6 +1588,25 @@ inline void Engine::begin_state(const void* img_latents, const void* x0, const f
   for (int n = 0; n < N; ++n)
     MDC_CHECK(off[n + 1] > off[n], "No valid values found in mask for some positions. Ensure that mask has at least one True value "
                                    "along the specified dimensions. (sample %d has no valid sparse-depth point: empty mask)", n);
+  {
+    // Sparse output head (head.cuh): its backward does the full GroupNorm arithmetic per pixel in the 3x3 neighbourhoods
+    // of the taps (at most 4 taps x 9 pixels per point) and streams elsewhere.  A/B-measured with 500 scattered points
+    // (4 % of the 576x768 map active: -0.17 ms per step); the KITTI-shaped frame (21 k points on 64 scan lines, about a
+    // third of the map active) was benchmarked and parity-tested with it on, without an A/B of its own.  Once the valid
+    // points exceed ~11 % of the pixels every decoder pixel is active and the dense kernels cannot lose: such a frame
+    // keeps the dense head.
+    // MDC_SPARSEHEAD_MAXFRAC overrides the bound on 36 x points / pixels.
+    static const double max_frac = [] {
+      const char* e = getenv("MDC_SPARSEHEAD_MAXFRAC");
+      return e ? atof(e) : 4.0;
+    }();
+    const bool before = sparse_head_allowed();
+    head_points_ok = 36.0 * off[N] <= max_frac * N * PPH * PPW;
+    if (before != sparse_head_allowed() && step_graph) {  // the captured step holds the other head: capture again
+      cudaGraphExecDestroy(step_graph);
+      step_graph = nullptr;
+    }
+  }
   if (getenv("MDC_DEBUG_SYNC")) {  // consistency of the compacted point list
     std::vector<int> idx(off[N]);
     copy_sync(idx.data(), pt_idx, idx.size() * 4, cudaMemcpyDeviceToHost);
@@ -1781,7 +1801,7 @@ inline cudaGraphExec_t capture_graph(Engine* e, F&& launches) {
 // ---- sparse output head (head.cuh)
 inline bool Engine::sparse_head_allowed() const {
   static const bool off = getenv("MDC_NO_SPARSEHEAD") != nullptr;
-  if (off || !head_gn || !head_conv) return false;
+  if (off || !head_gn || !head_conv || !head_points_ok) return false;
   const GroupNormOp& gn = *head_gn;
   const ConvOp& cv = *head_conv;
   return !gn.plan.single_f() && !gn.plan.single_b() && !gn.epi && gn.silu && gn.x->ld == gn.x->c && gn.x->c % 64 == 0 && cv.y->c == 3 &&
